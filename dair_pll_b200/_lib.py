@@ -1,0 +1,57 @@
+"""ctypes binding of ``libdair_pll_b200.so`` (C ABI: ``include/dair_pll_b200.h``).
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails, the
+caller gets an exception.  The library is built in-tree by ``dair_pll_b200.build``.
+"""
+import ctypes
+import os
+
+from dair_pll_b200 import build as _build
+
+_LIB = None
+
+_c_void_p = ctypes.c_void_p
+_i64, _i32, _f64, _f32, _sz = ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_float, ctypes.c_size_t
+
+EXPORTS = {
+    'dpll_version': ([], ctypes.c_int),
+    'dpll_workspace_bytes': ([], _sz),
+    'dpll_cube_loss_f64': ([_c_void_p] * 6 + [_f64, _f64, _i64] + [_c_void_p] * 5 + [_c_void_p, _sz, _c_void_p],
+                           ctypes.c_int),
+    'dpll_cube_loss_f32': ([_c_void_p] * 6 + [_f32, _f32, _i64] + [_c_void_p] * 5 + [_c_void_p, _sz, _c_void_p],
+                           ctypes.c_int),
+    'dpll_cube_rollout_f64': ([_c_void_p] * 4 + [_f64, _f64, _i64, _i32] + [_c_void_p] * 4, ctypes.c_int),
+    'dpll_cube_rollout_f32': ([_c_void_p] * 4 + [_f32, _f32, _i64, _i32] + [_c_void_p] * 4, ctypes.c_int),
+    'dpll_fma_peak_f64': ([_c_void_p, _i32, _i64, _c_void_p], ctypes.c_int),
+    'dpll_fma_peak_f32': ([_c_void_p, _i32, _i64, _c_void_p], ctypes.c_int),
+}
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raises if it has not been built (no CPU fallback exists)."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f'{path} not found: build it with `python -m dair_pll_b200.build` '
+                '(nvcc, sm_100a). dair_pll_b200 has no CPU or PyTorch fallback.')
+        lib = ctypes.CDLL(path)
+        for name, (argtypes, restype) in EXPORTS.items():
+            fn = getattr(lib, name)      # AttributeError if the symbol is missing
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _LIB = lib
+    return _LIB
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    if rc > 0:
+        raise RuntimeError(f'{what}: CUDA error {rc}')
+    raise RuntimeError(f'{what}: argument error {rc} (see include/dair_pll_b200.h)')

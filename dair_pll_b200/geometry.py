@@ -1,0 +1,51 @@
+"""Learnable collision geometries: parameter containers mirroring ``dair_pll/geometry.py``.
+
+The collision maths itself (top-k support points :162-202, plane-convex collision :553-582)
+runs inside the CUDA kernels; these modules own the ``nn.Parameter`` s with the reference's
+names and shapes so checkpoints interchange (``Box.length_params`` (1,3) :375-397).
+Polygon, Sphere and mesh-mesh collision are not reached by any configuration of the
+hot path and are not provided.
+"""
+from typing import Dict
+
+import torch
+from torch import Tensor
+from torch.nn import Module, Parameter
+
+_TOTAL_ORDERING = ['Plane', 'Polygon', 'Box', 'Sphere', 'DeepSupportConvex']  # geometry.py:46
+
+
+class CollisionGeometry(Module):
+    """Base class; ``>`` / ``<`` follow the reference's type ordering used to orient pairs."""
+
+    def __ge__(self, other) -> bool:
+        return _TOTAL_ORDERING.index(type(self).__name__) > _TOTAL_ORDERING.index(type(other).__name__)
+
+    def __lt__(self, other) -> bool:
+        return other.__ge__(self)
+
+    def scalars(self) -> Dict[str, float]:
+        raise NotImplementedError
+
+
+class Plane(CollisionGeometry):
+    """Half space z <= 0 in its own frame; no parameters."""
+
+    def scalars(self) -> Dict[str, float]:
+        return {}
+
+
+class Box(CollisionGeometry):
+    """Cuboid; learnable ``length_params`` whose absolute values are the half lengths."""
+
+    def __init__(self, half_lengths: Tensor, n_query: int = 4) -> None:
+        super().__init__()
+        assert half_lengths.numel() == 3
+        self.n_query = n_query
+        self.length_params = Parameter(half_lengths.detach().clone().reshape(1, 3), requires_grad=True)
+
+    def get_half_lengths(self) -> Tensor:
+        return self.length_params.abs()
+
+    def scalars(self) -> Dict[str, float]:
+        return {f'len_{ax}': 2 * v.item() for ax, v in zip('xyz', self.get_half_lengths().reshape(-1))}

@@ -1,0 +1,108 @@
+"""``MultibodyLearnableSystem`` with the reference's API, backed by sm_100a kernels.
+
+Drop-in for ``dair_pll.multibody_learnable_system.MultibodyLearnableSystem``
+(multibody_learnable_system.py:41-333): same constructor, same method signatures and
+output shapes, same ``nn.Parameter`` names/shapes (so ``state_dict`` checkpoints
+interchange, experiment.py:530-538), same attributes (``space``, ``integrator``, ``dt``,
+``multibody_terms``, ``max_batch_dim``).  The per-sample work of ``contactnets_loss``
+(:104-197), ``forward_dynamics`` (:199-304) and the integrator loop runs in CUDA kernels
+through ``dair_pll_b200.ops``; inputs must be CUDA tensors -- there is no CPU path.
+"""
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from dair_pll_b200 import ops
+from dair_pll_b200.integrator import VelocityIntegrator
+from dair_pll_b200.multibody_terms import MultibodyTerms
+from dair_pll_b200.system import System, SystemSummary
+
+LOSS_EPS = 1e-3    # multibody_learnable_system.py:130
+STEP_EPS = 1e-4    # multibody_learnable_system.py:283, 298
+
+
+class KernelVelocityIntegrator(VelocityIntegrator):
+    """``VelocityIntegrator`` whose time loop is one persistent rollout kernel: all
+    ``steps`` of ``Integrator.simulate`` (integrator.py:95-98) run on-chip per sample."""
+
+    def __init__(self, space, partial_step_callback, dt, rollout) -> None:
+        super().__init__(space, partial_step_callback, dt)
+        self._rollout = rollout
+
+    def simulate(self, x_0: Tensor, carry_0: Tensor, steps: int) -> Tuple[Tensor, Tensor]:
+        assert steps >= 0 and x_0.shape[-1] == self.space.n_x
+        traj = self._rollout(x_0, steps)
+        carry = carry_0.unsqueeze(-2).expand(carry_0.shape[:-1] + (steps + 1, carry_0.shape[-1]))
+        return traj, carry
+
+
+class MultibodyLearnableSystem(System):
+    """Learnable rigid multibody system with contact (ContactNets loss + Anitescu step)."""
+
+    def __init__(self, init_urdfs: Dict[str, str], dt: float, output_urdfs_dir: Optional[str] = None) -> None:
+        multibody_terms = MultibodyTerms(init_urdfs)
+        space = multibody_terms.spec.space()
+        integrator = KernelVelocityIntegrator(space, self.sim_step, dt, self._rollout)
+        super().__init__(space, integrator)
+        self.multibody_terms = multibody_terms
+        self.init_urdfs = init_urdfs
+        self.output_urdfs_dir = output_urdfs_dir
+        self.visualization_system = None
+        self.solver = None      # the cone QP is solved inside the kernels (reference: sappy.SAPSolver(), :77)
+        self.dt = dt
+        self.set_carry_sampler(lambda: torch.Tensor([False]))
+        self.max_batch_dim = 1
+
+    # -- helpers ---------------------------------------------------------
+    def _kind(self) -> str:
+        return self.multibody_terms.spec.kind
+
+    def _flat(self, t: Tensor) -> Tensor:
+        return t.reshape(-1, t.shape[-1])
+
+    def _cube_params(self, dtype: torch.dtype):
+        inertia, mu, half = self.multibody_terms.kernel_parameters(dtype)
+        return inertia.reshape(10), mu.reshape(1), half[0]
+
+    # -- ContactNets loss --------------------------------------------------
+    def contactnets_loss(self, x: Tensor, u: Tensor, x_plus: Tensor, loss_pool=None) -> Tensor:
+        """(*, n_x), (*, 0), (*, n_x) -> (*,) ContactNets loss (:104-197)."""
+        del u, loss_pool   # unactuated assets; the kernel needs no process pool
+        assert x.shape[-1] == self.space.n_x and x_plus.shape == x.shape
+        batch = x.shape[:-1]
+        if self._kind() == 'cube':
+            inertia, mu, half = self._cube_params(x.dtype)
+            loss = ops.CubeContactNetsLoss.apply(self._flat(x), self._flat(x_plus), inertia, mu, half,
+                                                 float(self.dt), LOSS_EPS)
+        else:
+            raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r} yet')
+        return loss.reshape(batch)
+
+    # -- simulation ------------------------------------------------------
+    def _rollout(self, x_0: Tensor, steps: int) -> Tensor:
+        """(*, n_x) -> (*, steps+1, n_x)."""
+        batch = x_0.shape[:-1]
+        if self._kind() == 'cube':
+            inertia, mu, half = self._cube_params(x_0.dtype)
+            traj, _ = ops.cube_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(),
+                                       float(self.dt), steps, STEP_EPS)
+        else:
+            raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r} yet')
+        return traj.reshape(batch + (steps + 1, self.space.n_x))
+
+    def forward_dynamics(self, q: Tensor, v: Tensor, u: Tensor, dynamics_pool=None) -> Tensor:
+        """(*, n_q), (*, n_v) -> next velocity (*, n_v) by Anitescu's convex step (:199-304)."""
+        del u, dynamics_pool
+        x = self.space.x(q, v)
+        return self.space.v(self._rollout(x, 1)[..., 1, :])
+
+    def sim_step(self, x: Tensor, carry: Tensor) -> Tuple[Tensor, Tensor]:
+        """``Integrator.partial_step`` callback (:306-313)."""
+        q, v = self.space.q_v(x)
+        return self.forward_dynamics(q, v, x.new_zeros(x.shape[:-1] + (0,))), carry
+
+    def summary(self, statistics: Dict) -> SystemSummary:
+        del statistics
+        scalars, meshes = self.multibody_terms.scalars_and_meshes()
+        return SystemSummary(scalars=scalars, videos={}, meshes=meshes)

@@ -1,0 +1,106 @@
+"""Learnable multibody parameters with the reference's module tree and parameter names.
+
+Mirror of ``dair_pll/multibody_terms.py``: ``MultibodyTerms`` owns ``lagrangian_terms``
+(``inertial_parameters`` theta, (n_bodies,10), :156) and ``contact_terms``
+(``friction_params`` (n_geometries,), :317; ``geometries`` ModuleList, :312;
+``collision_candidates``, :319) so ``state_dict()`` keys are identical.  The per-sample
+evaluation of M, F, phi, J (``forward`` methods :214-237, :428-521, :584-609) happens in
+the CUDA kernels; what stays here is the per-*batch* parameter preparation
+(theta -> [m, c, I_cm/m], |friction| and Drake's pairwise combination, |length_params|),
+kept in PyTorch so autograd chains the kernels' callable-level gradients to the leaves.
+"""
+from typing import List, Tuple
+
+import torch
+from torch import Tensor
+from torch.nn import Module, ModuleList, Parameter
+
+from dair_pll_b200.geometry import Box, Plane
+from dair_pll_b200.inertia import InertialParameterConverter
+from dair_pll_b200.system_spec import SystemSpec
+
+
+class LagrangianTerms(Module):
+    """Owns theta; ``inertia_vector()`` is what the generated callables / kernels consume."""
+
+    def __init__(self, spec: SystemSpec) -> None:
+        super().__init__()
+        pi_cm = torch.stack([b.pi_cm() for b in spec.bodies])
+        self.inertial_parameters = Parameter(InertialParameterConverter.pi_cm_to_theta(pi_cm),
+                                             requires_grad=True)
+
+    def pi_cm(self) -> Tensor:
+        return InertialParameterConverter.theta_to_pi_cm(self.inertial_parameters)
+
+    def inertia_vector(self) -> Tensor:
+        """(n_bodies, 10) [m, c, I_cm/m] (multibody_terms.py:230-231)."""
+        return InertialParameterConverter.pi_cm_to_drake_spatial_inertia(self.pi_cm())
+
+
+class ContactTerms(Module):
+    """Owns friction and geometry parameters."""
+
+    def __init__(self, spec: SystemSpec) -> None:
+        super().__init__()
+        geoms = []
+        for g in spec.geometries:
+            if g.kind == 'box':
+                geoms.append(Box(torch.tensor(g.half_lengths, dtype=torch.float64), 4))
+            elif g.kind == 'plane':
+                geoms.append(Plane())
+            else:
+                raise NotImplementedError(f'geometry kind {g.kind!r} (mesh support: DeepSupportConvex)')
+        self.geometries = ModuleList(geoms)
+        self.friction_params = Parameter(torch.tensor([g.mu for g in spec.geometries], dtype=torch.float64),
+                                         requires_grad=True)
+        # (2, n_pairs): row 0 = geometry a (Plane sorts first, geometry.py:46), row 1 = geometry b
+        self.register_buffer('collision_candidates',
+                             torch.tensor(spec.collision_pairs, dtype=torch.long).t().contiguous(),
+                             persistent=False)
+
+    def get_friction_coefficients(self) -> Tensor:
+        return self.friction_params.abs()
+
+    def pair_friction(self) -> Tensor:
+        """(n_pairs,) combined coefficient 2 mu_a mu_b / (mu_a + mu_b) (multibody_terms.py:466-471)."""
+        mu = self.get_friction_coefficients()
+        mu_a, mu_b = mu[self.collision_candidates[0]], mu[self.collision_candidates[1]]
+        return 2 * mu_a * mu_b / (mu_a + mu_b)
+
+    def half_lengths(self) -> List[Tensor]:
+        """|length_params| (3,) of each pair's body geometry, in pair order."""
+        return [self.geometries[int(b)].get_half_lengths().reshape(3) for b in self.collision_candidates[1]]
+
+
+class MultibodyTerms(Module):
+    """Container for the learnable dynamics parameters of a URDF system."""
+
+    def __init__(self, urdfs) -> None:
+        super().__init__()
+        self.urdfs = urdfs
+        self.spec = SystemSpec.from_urdfs(urdfs)
+        self.lagrangian_terms = LagrangianTerms(self.spec)
+        self.contact_terms = ContactTerms(self.spec)
+        self.geometry_body_assignment = {
+            b.name: [gi for gi, g in enumerate(self.spec.geometries) if g.body == bi]
+            for bi, b in enumerate(self.spec.bodies)}
+
+    def kernel_parameters(self, dtype: torch.dtype) -> Tuple[Tensor, Tensor, List[Tensor]]:
+        """Callable-level parameters in the kernels' dtype, differentiable w.r.t. the leaves."""
+        inertia = self.lagrangian_terms.inertia_vector().to(dtype)
+        mu = self.contact_terms.pair_friction().to(dtype)
+        half = [h.to(dtype) for h in self.contact_terms.half_lengths()]
+        return inertia, mu, half
+
+    def scalars_and_meshes(self):
+        """Summary scalars per body (multibody_terms.py:536-582); no meshes for box geometries."""
+        scalars = {}
+        mu = self.contact_terms.get_friction_coefficients()
+        for body, pi in zip(self.spec.bodies, self.lagrangian_terms.pi_cm()):
+            for k, val in InertialParameterConverter.pi_cm_to_scalars(pi).items():
+                scalars[f'{body.name}_{k}'] = val
+            for gi in self.geometry_body_assignment[body.name]:
+                for k, val in self.contact_terms.geometries[gi].scalars().items():
+                    scalars[f'{body.name}_{k}'] = val
+                scalars[f'{body.name}_mu'] = mu[gi].item()
+        return scalars, {}

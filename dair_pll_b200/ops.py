@@ -1,0 +1,143 @@
+"""``torch.autograd.Function`` custom ops over the C ABI (``include/dair_pll_b200.h``).
+
+These are the seam between the unchanged Python host API
+(:class:`dair_pll_b200.multibody_learnable_system.MultibodyLearnableSystem`) and the
+sm_100a kernels.  Tensors must be CUDA, contiguous, fp64 or fp32; there is no CPU path.
+"""
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from dair_pll_b200 import _lib
+
+_SUFFIX = {torch.float64: 'f64', torch.float32: 'f32'}
+_workspaces = {}
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(device: torch.device) -> Tensor:
+    """Per-(device, stream) scratch for the gradient reduction (the library never allocates)."""
+    key = (device.index, _stream())
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.empty(_lib.load().dpll_workspace_bytes(), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _check_inputs(*tensors: Tensor) -> torch.dtype:
+    dtype = tensors[0].dtype
+    if dtype not in _SUFFIX:
+        raise TypeError(f'dair_pll_b200 kernels support float64/float32, got {dtype}')
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError('dair_pll_b200 has no CPU path: tensors must live on a CUDA device')
+        if t.dtype != dtype:
+            raise TypeError(f'mixed dtypes: {t.dtype} vs {dtype}')
+    return dtype
+
+
+def cube_loss_raw(x: Tensor, x_plus: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, dt: float,
+                  eps: float, weight: Optional[Tensor] = None, want_grad: bool = True,
+                  want_force: bool = False, want_iters: bool = False):
+    """Direct call of ``dpll_cube_loss_*``.  x, x_plus (B,13).  Returns
+    (loss (B,), grad (14,) | None, loss_sum (1,), force (B,12) | None, iters (B,) | None)."""
+    dtype = _check_inputs(x, x_plus, inertia, mu_pair, half)
+    x, x_plus = x.contiguous(), x_plus.contiguous()
+    inertia, mu_pair, half = inertia.contiguous(), mu_pair.contiguous(), half.contiguous()
+    if x.dim() != 2 or x.shape[1] != 13 or x_plus.shape != x.shape:
+        raise ValueError(f'expected (B,13) states, got {tuple(x.shape)} / {tuple(x_plus.shape)}')
+    if inertia.numel() != 10 or mu_pair.numel() != 1 or half.numel() != 3:
+        raise ValueError('cube parameters must be inertia (10), mu_pair (1), half (3)')
+    B = x.shape[0]
+    dev = x.device
+    loss = torch.empty(B, dtype=dtype, device=dev)
+    grad = torch.empty(14, dtype=dtype, device=dev) if want_grad else None
+    loss_sum = torch.empty(1, dtype=dtype, device=dev)
+    force = torch.empty((B, 12), dtype=dtype, device=dev) if want_force else None
+    iters = torch.empty(B, dtype=torch.int32, device=dev) if want_iters else None
+    if weight is not None:
+        weight = weight.to(dtype).contiguous()
+    ws = _workspace(dev)
+    fn = getattr(_lib.load(), 'dpll_cube_loss_' + _SUFFIX[dtype])
+    with torch.cuda.device(dev):
+        rc = fn(_ptr(x), _ptr(x_plus), _ptr(weight), _ptr(inertia), _ptr(mu_pair), _ptr(half), dt, eps, B,
+                _ptr(loss), _ptr(force), _ptr(iters), _ptr(grad), _ptr(loss_sum), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, 'dpll_cube_loss')
+    return loss, grad, loss_sum, force, iters
+
+
+class CubeContactNetsLoss(torch.autograd.Function):
+    """loss (B,) = ContactNets loss of the cube; differentiable w.r.t. the callable-level
+    parameters (inertia 10-vector, combined friction, box half lengths).  x and x_plus are
+    data (no gradient), as in the reference's training loop (drake_experiment.py:202-224).
+
+    The backward is fused into the forward kernel (envelope theorem,
+    multibody_learnable_system.py:172-175): the forward launch already returns
+    d(sum_b loss_b)/d params.  When autograd hands back a uniform upstream gradient (the
+    stride-0 expansion produced by ``loss.mean()`` / ``loss.sum()``) the backward is a
+    14-element scale; otherwise the kernel is re-run with per-sample weights.
+    """
+
+    @staticmethod
+    def forward(ctx, x, x_plus, inertia, mu_pair, half, dt, eps):
+        need = any(ctx.needs_input_grad[2:5])
+        loss, grad, _, _, _ = cube_loss_raw(x, x_plus, inertia, mu_pair, half, dt, eps, want_grad=need)
+        ctx.dt, ctx.eps = dt, eps
+        ctx.shapes = (inertia.shape, mu_pair.shape, half.shape)
+        if need:
+            ctx.save_for_backward(grad, x, x_plus, inertia, mu_pair, half)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        grad, x, x_plus, inertia, mu_pair, half = ctx.saved_tensors
+        if grad_loss.dim() == 1 and grad_loss.stride(0) == 0 and grad_loss.numel() > 0:
+            g = grad * grad_loss[0]
+        else:
+            _, g, _, _, _ = cube_loss_raw(x, x_plus, inertia, mu_pair, half, ctx.dt, ctx.eps,
+                                          weight=grad_loss.contiguous(), want_grad=True)
+        s_in, s_mu, s_h = ctx.shapes
+        return (None, None, g[0:10].reshape(s_in), g[10:11].reshape(s_mu), g[11:14].reshape(s_h), None, None)
+
+
+def cube_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, dt: float, steps: int,
+                 eps: float = 1e-4, want_force: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+    """(B,13) -> trajectory (B, steps+1, 13) through ``dpll_cube_rollout_*`` (no autograd)."""
+    dtype = _check_inputs(x0, inertia, mu_pair, half)
+    x0 = x0.contiguous()
+    if x0.dim() != 2 or x0.shape[1] != 13:
+        raise ValueError(f'expected (B,13) states, got {tuple(x0.shape)}')
+    B = x0.shape[0]
+    traj = torch.empty((B, steps + 1, 13), dtype=dtype, device=x0.device)
+    force = torch.empty((B, steps, 12), dtype=dtype, device=x0.device) if want_force else None
+    fn = getattr(_lib.load(), 'dpll_cube_rollout_' + _SUFFIX[dtype])
+    with torch.cuda.device(x0.device):
+        rc = fn(_ptr(x0), _ptr(inertia.contiguous()), _ptr(mu_pair.contiguous()), _ptr(half.contiguous()),
+                dt, eps, B, steps, _ptr(traj), _ptr(force), None, _stream())
+    _lib.check(rc, 'dpll_cube_rollout')
+    return traj, force
+
+
+def fma_peak(dtype: torch.dtype, device: torch.device, blocks: int, iters: int) -> float:
+    """Measured FMA throughput (FLOP/s) of the CUDA cores for ``dtype`` -- roofline denominator."""
+    out = torch.empty(blocks * 256, dtype=dtype, device=device)
+    fn = getattr(_lib.load(), 'dpll_fma_peak_' + _SUFFIX[dtype])
+    with torch.cuda.device(device):
+        _lib.check(fn(_ptr(out), blocks, 1000, _stream()), 'dpll_fma_peak')   # warm-up
+        torch.cuda.synchronize(device)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        _lib.check(fn(_ptr(out), blocks, iters, _stream()), 'dpll_fma_peak')
+        stop.record()
+        torch.cuda.synchronize(device)
+    ms = start.elapsed_time(stop)
+    return blocks * 256 * iters * 16 * 2 / (ms * 1e-3)

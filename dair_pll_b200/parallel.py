@@ -1,0 +1,99 @@
+"""Sample-level data parallelism and host->device pipelining around the loss kernels.
+
+The ContactNets loss is independent per (x, x_plus) pair (multibody_learnable_system.py:118-124);
+the only coupling is ``loss.mean()`` (drake_experiment.py:222-223) and the summed parameter
+gradient.  So: one process per GPU, each rank evaluates its shard of the batch, and ONE NCCL
+all-reduce moves a flat buffer [d/d theta (n_b x 10), d/d friction (n_g), d/d lengths ..., loss]
+(15 doubles for the cube).  Parameter ``.grad`` tensors are views into that buffer, so autograd
+accumulates straight into the NCCL send buffer and nothing is packed or copied per step.
+"""
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous shard [lo, hi) of n samples for ``rank``; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GradientAllReduce:
+    """Flat gradient buffer shared with the parameters' ``.grad`` + mean all-reduce over ranks."""
+
+    def __init__(self, params: List[Tensor], device: torch.device, world: int,
+                 group: Optional[dist.ProcessGroup] = None) -> None:
+        self.params = list(params)
+        self.world = world
+        self.group = group
+        self.numel = sum(p.numel() for p in self.params) + 1          # + 1 slot for the loss
+        dtype = self.params[0].dtype
+        self.flat = torch.zeros(self.numel, dtype=dtype, device=device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)        # autograd accumulates in place
+            off += p.numel()
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def rebind(self) -> None:
+        """Re-attach ``.grad`` views (after something set ``p.grad = None``)."""
+        off = 0
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != self.flat[off:].data_ptr():
+                g = self.flat[off:off + p.numel()].view_as(p)
+                if p.grad is not None:
+                    g.copy_(p.grad)
+                else:
+                    g.zero_()
+                p.grad = g
+            off += p.numel()
+
+    def __call__(self, local_mean_loss: Tensor) -> Tensor:
+        """Averages gradients (already in ``flat``) and the loss over ranks; returns ``flat``."""
+        self.rebind()
+        self.flat[-1:].copy_(local_mean_loss.detach().reshape(1))
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / self.world)
+        return self.flat
+
+
+class HostBatchPipeline:
+    """``loss.mean()`` of a batch that lives in (pinned) HOST memory: the batch is cut into
+    chunks whose host->device copies run on a side stream and overlap the loss kernels of the
+    previous chunks.  The result is differentiable w.r.t. the system's parameters."""
+
+    def __init__(self, system, device: torch.device, dtype: torch.dtype, max_batch: int, chunks: int = 8) -> None:
+        self.system = system
+        self.device = device
+        self.chunks = chunks
+        n_x = system.space.n_x
+        self.x_dev = torch.empty((max_batch, n_x), dtype=dtype, device=device)
+        self.xp_dev = torch.empty((max_batch, n_x), dtype=dtype, device=device)
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.events = [torch.cuda.Event() for _ in range(chunks)]
+
+    def loss_mean_from_host(self, x_host: Tensor, xp_host: Tensor) -> Tensor:
+        B = x_host.shape[0]
+        assert B <= self.x_dev.shape[0]
+        main = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_stream(main)            # previous step's kernels are done with the buffers
+        bounds = [shard_bounds(B, self.chunks, c) for c in range(self.chunks)]
+        with torch.cuda.stream(self.copy_stream):
+            for c, (lo, hi) in enumerate(bounds):
+                self.x_dev[lo:hi].copy_(x_host[lo:hi], non_blocking=True)
+                self.xp_dev[lo:hi].copy_(xp_host[lo:hi], non_blocking=True)
+                self.events[c].record(self.copy_stream)
+        total = None
+        for c, (lo, hi) in enumerate(bounds):
+            if hi == lo:
+                continue
+            main.wait_event(self.events[c])
+            part = self.system.contactnets_loss(self.x_dev[lo:hi], None, self.xp_dev[lo:hi]).sum()
+            total = part if total is None else total + part
+        return total / B

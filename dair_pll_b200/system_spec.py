@@ -1,0 +1,166 @@
+"""Host-side model ingestion: URDF -> :class:`SystemSpec`.
+
+In the reference this is done by pydrake (``drake_utils.MultibodyPlantDiagram``,
+drake_utils.py:227-335) followed by symbolic derivation (multibody_terms.py:114-157,
+267-319).  pydrake is not a dependency here: the two kinematic classes the kernels
+specialise (a single floating body; a floating body plus one revolute child) are read
+straight from the URDF XML.  Conventions reproduced from the reference:
+
+* a ground half-space z = 0 with mu = 1 is always added (drake_utils.py:280-288) and is
+  the LAST geometry; body geometries come first, in link order;
+* every (ground, body-geometry) pair is a collision candidate; body-body pairs inside one
+  URDF's ``collision_filter_group`` are filtered (contactnets_elbow.urdf:74-78);
+* theta is initialised from the URDF inertia via pi_cm -> pi_o -> theta
+  (multibody_terms.py:194-196);
+* state space = ProductSpace([FixedBaseSpace(0) (world), FloatingBaseSpace(n_joints)])
+  (drake_utils.py:309-335).
+"""
+import os
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from dair_pll_b200.state_space import FixedBaseSpace, FloatingBaseSpace, ProductSpace
+
+
+def _floats(text: Optional[str], n: int, default: float = 0.0) -> Tuple[float, ...]:
+    if text is None:
+        return tuple([default] * n)
+    vals = tuple(float(t) for t in text.split())
+    assert len(vals) == n, f'expected {n} numbers, got {text!r}'
+    return vals
+
+
+@dataclass
+class BodySpec:
+    name: str
+    mass: float
+    com: Tuple[float, float, float]
+    inertia_cm: Tuple[float, float, float, float, float, float]   # xx, yy, zz, xy, xz, yz
+
+    def pi_cm(self) -> torch.Tensor:
+        m = self.mass
+        return torch.tensor([m, m * self.com[0], m * self.com[1], m * self.com[2], *self.inertia_cm],
+                            dtype=torch.float64)
+
+
+@dataclass
+class GeometrySpec:
+    body: int                                   # index into bodies, -1 = world
+    kind: str                                   # 'box' | 'mesh' | 'plane'
+    offset: Tuple[float, float, float] = (0., 0., 0.)
+    half_lengths: Optional[Tuple[float, float, float]] = None
+    mesh_file: Optional[str] = None
+    mu: float = 1.0
+
+
+@dataclass
+class JointSpec:
+    parent: int
+    child: int
+    origin: Tuple[float, float, float]
+    axis: Tuple[float, float, float]
+
+
+@dataclass
+class SystemSpec:
+    kind: str                                   # 'cube' (1 floating body) | 'elbow' (+1 hinge)
+    bodies: List[BodySpec]
+    joints: List[JointSpec]
+    geometries: List[GeometrySpec]              # body geometries first, ground last
+    collision_pairs: List[Tuple[int, int]] = field(default_factory=list)   # (ground, body geometry)
+
+    @property
+    def n_joints(self) -> int:
+        return len(self.joints)
+
+    @property
+    def n_q(self) -> int:
+        return 7 + self.n_joints
+
+    @property
+    def n_v(self) -> int:
+        return 6 + self.n_joints
+
+    @property
+    def n_x(self) -> int:
+        return self.n_q + self.n_v
+
+    @property
+    def n_contacts(self) -> int:
+        return 4 * len(self.collision_pairs)    # n_query = 4 per pair (geometry.py:48-49, 491)
+
+    def space(self) -> ProductSpace:
+        return ProductSpace([FixedBaseSpace(0), FloatingBaseSpace(self.n_joints)])
+
+    @staticmethod
+    def from_urdfs(urdfs: Dict[str, str]) -> 'SystemSpec':
+        if len(urdfs) != 1:
+            raise NotImplementedError('one URDF (one kinematic chain) per system is supported')
+        (path,) = urdfs.values()
+        return SystemSpec.from_urdf(path)
+
+    @staticmethod
+    def from_urdf(path: str) -> 'SystemSpec':
+        root = ET.parse(path).getroot()
+        bodies, geometries, names = [], [], []
+        for link in root.findall('link'):
+            inertial = link.find('inertial')
+            if inertial is None:
+                raise NotImplementedError(f'link {link.get("name")} has no <inertial>')
+            origin = inertial.find('origin')
+            com = _floats(origin.get('xyz') if origin is not None else None, 3)
+            if origin is not None and any(abs(a) > 0 for a in _floats(origin.get('rpy'), 3)):
+                raise NotImplementedError('rotated inertial frames are not supported')
+            ine = inertial.find('inertia')
+            inertia_cm = tuple(float(ine.get(k)) for k in ('ixx', 'iyy', 'izz', 'ixy', 'ixz', 'iyz'))
+            names.append(link.get('name'))
+            bodies.append(BodySpec(link.get('name'), float(inertial.find('mass').get('value')), com, inertia_cm))
+            for col in link.findall('collision'):
+                corigin = col.find('origin')
+                offset = _floats(corigin.get('xyz') if corigin is not None else None, 3)
+                if corigin is not None and any(abs(a) > 0 for a in _floats(corigin.get('rpy'), 3)):
+                    raise NotImplementedError('rotated collision frames are not supported')
+                mu = 1.0
+                for prox in col.iter():
+                    if prox.tag.endswith('mu_static'):
+                        mu = float(prox.get('value'))
+                geom = col.find('geometry')
+                box, mesh = geom.find('box'), geom.find('mesh')
+                if box is not None:
+                    size = _floats(box.get('size'), 3)
+                    geometries.append(GeometrySpec(len(bodies) - 1, 'box', offset,
+                                                   tuple(0.5 * s for s in size), None, mu))
+                elif mesh is not None:
+                    fname = mesh.get('filename')
+                    if not os.path.isabs(fname):
+                        fname = os.path.join(os.path.dirname(os.path.abspath(path)), fname)
+                    geometries.append(GeometrySpec(len(bodies) - 1, 'mesh', offset, None, fname, mu))
+                else:
+                    raise NotImplementedError('only <box> and <mesh> collision geometries are supported')
+        joints = []
+        for joint in root.findall('joint'):
+            if joint.get('type') not in ('continuous', 'revolute'):
+                raise NotImplementedError(f'joint type {joint.get("type")}')
+            jo = joint.find('origin')
+            if jo is not None and any(abs(a) > 0 for a in _floats(jo.get('rpy'), 3)):
+                raise NotImplementedError('rotated joint frames are not supported')
+            axis = joint.find('axis')
+            joints.append(JointSpec(names.index(joint.find('parent').get('link')),
+                                    names.index(joint.find('child').get('link')),
+                                    _floats(jo.get('xyz') if jo is not None else None, 3),
+                                    _floats(axis.get('xyz') if axis is not None else '1 0 0', 3)))
+        if len(bodies) == 1 and not joints:
+            kind = 'cube'
+        elif len(bodies) == 2 and len(joints) == 1 and joints[0].parent == 0 and joints[0].child == 1:
+            kind = 'elbow'
+        else:
+            raise NotImplementedError(
+                'kernels are specialised for a single floating body or a floating body with one '
+                'revolute child; arbitrary trees need the symbolic path (SURVEY.md section 8(f) N2)')
+        ground = len(geometries)
+        geometries.append(GeometrySpec(-1, 'plane', (0., 0., 0.), None, None, 1.0))
+        pairs = [(ground, g) for g in range(ground)]
+        return SystemSpec(kind, bodies, joints, geometries, pairs)

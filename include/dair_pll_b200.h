@@ -1,0 +1,118 @@
+/*
+ * dair_pll_b200 -- C ABI of the B200 (sm_100a) ContactNets hot path.
+ *
+ * The reference (DAIRLab/dair_pll) is pure Python: the seam this library sits behind
+ * is the torch.nn.Module API of MultibodyLearnableSystem, not an FFI.  These entry
+ * points are what the reference-side binding (dair_pll_b200/ops.py, a ctypes stub; see
+ * INTEGRATION.md) calls from torch.autograd.Function objects.  Each one replaces a
+ * span of reference Python, cited per function.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller (torch tensors); contiguous,
+ *    row-major.  The library never allocates or frees; scratch is passed in
+ *    (`workspace`, at least dpll_workspace_bytes() bytes, 16-byte aligned).
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and
+ *    performs no host synchronisation.  Calls are re-entrant; there is no global state.
+ *  - Return value: 0 on success, a positive cudaError_t value if a launch failed, a
+ *    negative DPLL_E* value for argument errors.  Numerical failure of a sample's QP
+ *    is NOT an error: as in the reference (multibody_learnable_system.py:186-192) that
+ *    sample's force and loss are set to 0.
+ *  - State layout (state_space.py:400-486): cube x = [qw qx qy qz | px py pz |
+ *    w_body(3) | v_world(3)] (13); elbow adds the hinge angle after the position and the
+ *    hinge rate after the velocities (15).
+ *  - Parameter layout for the cube: inertia[10] = [m, cx, cy, cz, Ixx, Iyy, Izz, Ixy,
+ *    Ixz, Iyz] exactly as the reference's generated callables receive it
+ *    (multibody_terms.py:230-234; inertia.py:376-382), mu_pair[1] = combined friction
+ *    2 mu_a mu_b / (mu_a + mu_b) (multibody_terms.py:466-471), half[3] =
+ *    |length_params| (geometry.py:394-397).  Gradients come back in the same layout,
+ *    concatenated: grad[14] = [d/d inertia (10) | d/d mu_pair | d/d half (3)].
+ */
+#ifndef DAIR_PLL_B200_H_
+#define DAIR_PLL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPLL_OK 0
+#define DPLL_EINVAL (-1)     /* null pointer / negative size */
+#define DPLL_EWORKSPACE (-2) /* workspace too small */
+
+#define DPLL_CUBE_NX 13
+#define DPLL_CUBE_NC 4
+#define DPLL_CUBE_NPARAM 14
+
+/* Library/ABI version (major*100 + minor). */
+int dpll_version(void);
+
+/* Bytes of device scratch any entry point below may need. */
+size_t dpll_workspace_bytes(void);
+
+/*
+ * ContactNets loss and its fused envelope-theorem backward for the cube.
+ * Replaces MultibodyLearnableSystem.contactnets_loss
+ * (dair_pll/multibody_learnable_system.py:104-197) together with everything it calls
+ * per sample -- MultibodyTerms.forward (multibody_terms.py:584-609), ContactTerms.forward
+ * (:428-521), GeometryCollider.collide_plane_convex (geometry.py:553-582), the top-4 corner
+ * selection (geometry.py:162-202), SAPSolver.apply (sappy, un-vendored) -- and the autograd
+ * backward of `loss.sum()` w.r.t. the callable-level parameters.
+ *
+ *   x, x_plus : (B, 13)   states (only the velocity part of x is read, :127)
+ *   weight    : (B)       nullable; per-sample upstream gradient w_b.  NULL means w_b = 1.
+ *   loss      : (B)       per-sample loss (:194-197)
+ *   force     : (B, 12)   nullable; solved contact impulses in the reference's ordering
+ *                         [n_1..n_4, t_1x, t_1y, ..., t_4x, t_4y] (tensor_utils.py:460-497),
+ *                         contacts ordered by ascending box-vertex index
+ *   iters     : (B)       nullable; Newton iterations used
+ *   grad      : (14)      nullable; OVERWRITTEN with d(sum_b w_b loss_b)/d params
+ *   loss_sum  : (1)       nullable; OVERWRITTEN with sum_b loss_b
+ * Deterministic: fixed sample->thread mapping and fixed-order reductions (bitwise
+ * reproducible for a given B).
+ */
+int dpll_cube_loss_f64(const double* x, const double* x_plus, const double* weight,
+                       const double* inertia, const double* mu_pair, const double* half,
+                       double dt, double eps, int64_t B, double* loss, double* force, int32_t* iters, double* grad,
+                       double* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
+int dpll_cube_loss_f32(const float* x, const float* x_plus, const float* weight,
+                       const float* inertia, const float* mu_pair, const float* half, float dt,
+                       float eps, int64_t B, float* loss, float* force, int32_t* iters, float* grad, float* loss_sum,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Learnable time stepping for the cube: `steps` applications of
+ * VelocityIntegrator.step (dair_pll/integrator.py:153-162) around
+ * MultibodyLearnableSystem.sim_step / forward_dynamics
+ * (multibody_learnable_system.py:199-313) and FloatingBaseSpace.exponential
+ * (state_space.py:466-486; quaternion.py:89-104, 276-309); the time loop is
+ * Integrator.simulate (integrator.py:75-99).
+ *
+ *   x0    : (B, 13)              initial states
+ *   traj  : (B, steps+1, 13)     traj[:,0] = x0, traj[:,t+1] = step(traj[:,t])
+ *   force : (B, steps, 12)       nullable; impulses of every step (reference ordering)
+ *   iters : (B)                  nullable; total Newton iterations over the rollout
+ * eps is the QP regulariser (the reference hard-codes 1e-4, :283,298).
+ */
+int dpll_cube_rollout_f64(const double* x0, const double* inertia, const double* mu_pair,
+                          const double* half, double dt, double eps, int64_t B, int32_t steps,
+                          double* traj, double* force, int32_t* iters, void* stream);
+int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu_pair,
+                          const float* half, float dt, float eps, int64_t B, int32_t steps,
+                          float* traj, float* force, int32_t* iters, void* stream);
+
+/*
+ * FP64 / FP32 FMA throughput micro-benchmark used by bench.py to measure the CUDA-core
+ * roofline denominator on the box it runs on (MEASURED_PEAKS.json carries no FP64
+ * figure).  Launches `blocks` x 256 threads, each running `iters` x 16 independent FMAs
+ * per loop trip; writes one value per thread to out (blocks*256 elements) so the work is
+ * not optimised away.  FLOPs = blocks * 256 * iters * 16 * 2.
+ */
+int dpll_fma_peak_f64(double* out, int32_t blocks, int64_t iters, void* stream);
+int dpll_fma_peak_f32(float* out, int32_t blocks, int64_t iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAIR_PLL_B200_H_ */

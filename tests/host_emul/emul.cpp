@@ -1,0 +1,46 @@
+// Host build of the per-sample device math (dair_pll_b200/csrc/*.cuh) for debugging in a
+// container without a GPU.  TEST INFRASTRUCTURE ONLY: nothing in the package loads this.
+#include "../../dair_pll_b200/csrc/cn_cube.cuh"
+#include <cstdint>
+using namespace cn;
+extern "C" {
+int emul_cube_loss_f64(const double* x, const double* xp, const double* inertia, const double* mu,
+                       const double* half, double dt, double eps, int64_t B, double* loss, double* force,
+                       int32_t* iters, double* grad) {
+  CubeParams<double> P;
+  cube_params_init(P, inertia, mu, half, dt, eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  for (int i = 0; i < CUBE_NPARAM; ++i) if (grad) grad[i] = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    int it;
+    loss[b] = cube_loss_sample(P, cfg, x + 13 * b, xp + 13 * b, grad, force ? force + 12 * b : nullptr, &it);
+    if (iters) iters[b] = it;
+  }
+  return 0;
+}
+int emul_cube_loss_f32(const float* x, const float* xp, const float* inertia, const float* mu,
+                       const float* half, float dt, float eps, int64_t B, float* loss, float* force,
+                       int32_t* iters, float* grad) {
+  CubeParams<float> P;
+  cube_params_init(P, inertia, mu, half, dt, eps);
+  SolverCfg<float> cfg = default_cfg<float>();
+  for (int i = 0; i < CUBE_NPARAM; ++i) if (grad) grad[i] = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    int it;
+    loss[b] = cube_loss_sample(P, cfg, x + 13 * b, xp + 13 * b, grad, force ? force + 12 * b : nullptr, &it);
+    if (iters) iters[b] = it;
+  }
+  return 0;
+}
+int emul_cube_step_f64(const double* x, const double* inertia, const double* mu, const double* half,
+                       double dt, double eps, int64_t B, double* xn, double* force, int32_t* iters) {
+  CubeParams<double> P;
+  cube_params_init(P, inertia, mu, half, dt, eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  for (int64_t b = 0; b < B; ++b) {
+    int it = cube_step_sample(P, cfg, x + 13 * b, xn + 13 * b, force ? force + 12 * b : nullptr);
+    if (iters) iters[b] = it;
+  }
+  return 0;
+}
+}

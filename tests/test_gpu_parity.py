@@ -1,0 +1,215 @@
+"""GPU: the CUDA path, called through the C ABI (dair_pll_b200.ops -> libdair_pll_b200.so) and the
+reference-shaped module API, against (a) golden vectors from the reference's own Python,
+(b) the CPU oracle on seeded random inputs, (c) size-independent properties at full batch size."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from dair_pll_b200 import ops, synthetic  # noqa: E402
+from dair_pll_b200.multibody_learnable_system import MultibodyLearnableSystem  # noqa: E402
+from tests.util import kernel_level_params, load_golden, max_rel_to_scale, rel_err  # noqa: E402
+
+CASES = ['cube_real_nominal', 'cube_real_perturbed', 'cube_synthetic']
+DEV = 'cuda:0'
+
+
+def _system(g, assets_dir, dtype=torch.float64):
+    """Module with the golden file's learnable parameters loaded through state_dict()."""
+    s = MultibodyLearnableSystem({'cube': os.path.join(assets_dir, 'cube.urdf')}, float(g['dt']))
+    s.load_state_dict({
+        'multibody_terms.lagrangian_terms.inertial_parameters': torch.from_numpy(g['theta']),
+        'multibody_terms.contact_terms.friction_params': torch.from_numpy(g['friction_params']),
+        'multibody_terms.contact_terms.geometries.0.length_params': torch.from_numpy(g['half_lengths']).reshape(1, 3)})
+    return s.to(DEV)
+
+
+def test_native_library_is_loaded():
+    from dair_pll_b200 import _lib
+    _lib.load()
+    assert any('libdair_pll_b200.so' in line for line in open('/proc/self/maps'))
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_loss_and_gradients_match_reference_golden_fp64(name, assets_dir):
+    g = load_golden(name)
+    s = _system(g, assets_dir)
+    x = torch.from_numpy(g['x']).to(DEV)
+    xp = torch.from_numpy(g['x_plus']).to(DEV)
+    loss = s.contactnets_loss(x, torch.zeros(x.shape[0], 0, device=DEV), xp)
+    assert loss.shape == (x.shape[0],)
+    loss.mean().backward()
+    l = loss.detach().cpu().numpy()
+    assert np.abs(l - g['loss']).max() < 1e-13
+    assert rel_err(l, g['loss'], 1e-9).max() < 1e-9          # north_star tolerance (fp64)
+    mt = s.multibody_terms
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(mt.contact_terms.geometries[0].length_params.grad.cpu().numpy(), g['grad_length']) < 1e-9
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_impulses_match_reference_golden(name):
+    g = load_golden(name)
+    inertia, mu, half = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    _, _, _, force, iters = ops.cube_loss_raw(x, xp, inertia, mu, half, float(g['dt']), 1e-3, want_force=True,
+                                              want_iters=True)
+    scale = np.maximum(np.abs(g['force']).max(axis=1, keepdims=True), 1e-6)
+    assert (np.abs(force.cpu().numpy() - g['force']) / scale).max() < 1e-8
+    assert int(iters.max()) <= 60
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_rollout_matches_reference_golden(name, assets_dir):
+    g = load_golden(name)
+    s = _system(g, assets_dir)
+    x0 = torch.from_numpy(g['sim_x0']).to(DEV)
+    steps = g['sim_traj'].shape[1] - 1
+    with torch.no_grad():
+        traj, carry = s.simulate(x0.unsqueeze(-2), torch.zeros(x0.shape[0], 1, device=DEV), steps)
+    assert traj.shape == g['sim_traj'].shape and carry.shape == (x0.shape[0], steps + 1, 1)
+    t = traj.cpu().numpy()
+    assert np.abs(t[:, 1] - g['sim_traj'][:, 1]).max() < 1e-9     # one step: next states at 1e-9
+    assert np.abs(t - g['sim_traj']).max() < 1e-7                 # compounding contact sensitivity
+    # forward_dynamics / integrator.step agree with the rollout's first step
+    v_next = s.forward_dynamics(x0[:, :7], x0[:, 7:], torch.zeros(x0.shape[0], 0, device=DEV))
+    assert torch.equal(v_next, traj[:, 1, 7:])
+    x1, _ = s.integrator.step(x0, torch.zeros(x0.shape[0], 1, device=DEV))
+    assert torch.allclose(x1, traj[:, 1], atol=1e-14, rtol=0)
+
+
+def test_matches_cpu_oracle_on_random_inputs():
+    from oracle import contactnets_oracle as co
+    from oracle.callables import CUBE_TREE, TreeCallables
+    calls = TreeCallables(CUBE_TREE)
+    pi, fr, half = synthetic.cube_learnables_perturbed(5)
+    P = co.OracleParams(co.pi_cm_to_theta(pi), fr, [half.reshape(1, 3)]).requires_grad_()
+    x = synthetic.cube_states(2048, seed=21)
+    with torch.no_grad():
+        xp = synthetic.perturb_next_state(co.sim_step(calls, P, x, 0.0068), seed=22)
+    loss_o = co.contactnets_loss(calls, P, x, xp, 0.0068)
+    loss_o.sum().backward()
+    g = dict(theta=P.inertial_parameters.detach().numpy(), friction_params=fr.numpy(), half_lengths=half.numpy())
+    inertia, mu, hl = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    loss, grad, loss_sum, _, _ = ops.cube_loss_raw(x.to(DEV), xp.to(DEV), inertia, mu, hl, 0.0068, 1e-3)
+    assert rel_err(loss.cpu().numpy(), loss_o.detach().numpy(), 1e-9).max() < 1e-9
+    assert abs(loss_sum.item() - loss_o.sum().item()) < 1e-9 * abs(loss_o.sum().item())
+    # chain the kernel's callable-level gradient to the leaves and compare with oracle autograd
+    theta = P.inertial_parameters.detach().clone().requires_grad_()
+    frl = fr.clone().requires_grad_()
+    ln = half.clone().reshape(1, 3).requires_grad_()
+    m = frl.abs()
+    flat = torch.cat((co.theta_to_inertia_vector(theta).reshape(10), (2 * m[0] * m[1] / (m[0] + m[1])).reshape(1),
+                      ln.abs().reshape(3)))
+    flat.backward(grad.cpu())
+    assert max_rel_to_scale(theta.grad.numpy(), P.inertial_parameters.grad.numpy()) < 1e-9
+    assert max_rel_to_scale(frl.grad.numpy(), P.friction_params.grad.numpy()) < 1e-9
+    assert max_rel_to_scale(ln.grad.numpy(), P.length_params[0].grad.numpy()) < 1e-9
+
+
+def test_weighted_backward_equals_sum_of_per_sample_gradients():
+    g = load_golden('cube_synthetic')
+    inertia, mu, half = (torch.from_numpy(a).to(DEV).requires_grad_() for a in kernel_level_params(g))
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    w = torch.rand(x.shape[0], dtype=torch.float64, device=DEV)
+    loss = ops.CubeContactNetsLoss.apply(x, xp, inertia, mu, half, float(g['dt']), 1e-3)
+    (loss * w).sum().backward()                      # non-uniform upstream gradient -> weighted kernel pass
+    got = torch.cat((inertia.grad, mu.grad, half.grad)).cpu().numpy()
+    ref = np.zeros(14)
+    for lo in range(0, x.shape[0], 64):              # per-chunk uniform passes, weights applied outside
+        for i in range(lo, min(lo + 64, x.shape[0])):
+            _, gi, _, _, _ = ops.cube_loss_raw(x[i:i + 1], xp[i:i + 1], inertia.detach(), mu.detach(), half.detach(),
+                                               float(g['dt']), 1e-3)
+            ref += w[i].item() * gi.cpu().numpy()
+    assert max_rel_to_scale(got, ref) < 1e-11
+
+
+def test_empty_and_ragged_batches(assets_dir):
+    g = load_golden('cube_synthetic')
+    s = _system(g, assets_dir)
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    full = s.contactnets_loss(x, None, xp)
+    empty = s.contactnets_loss(x[:0], None, xp[:0])
+    assert empty.shape == (0,)
+    for n in (1, 31, 33, 129):
+        assert torch.equal(s.contactnets_loss(x[:n], None, xp[:n]), full[:n])
+    # extra leading batch dimensions (*, n_x) -> (*,)
+    two = s.contactnets_loss(x[:24].reshape(4, 6, 13), None, xp[:24].reshape(4, 6, 13))
+    assert two.shape == (4, 6) and torch.equal(two.reshape(-1), full[:24])
+    # strided (non-contiguous) views are accepted
+    assert torch.equal(s.contactnets_loss(x[::2], None, xp[::2]), full[::2])
+
+
+def test_bitwise_determinism_and_shard_additivity():
+    """Same inputs -> identical bits; gradient of the whole batch = sum over sample shards (the
+    property the multi-GPU path relies on)."""
+    pi, fr, half = synthetic.cube_learnables_perturbed(1)
+    from oracle import contactnets_oracle as co
+    g = dict(theta=co.pi_cm_to_theta(pi).numpy(), friction_params=fr.numpy(), half_lengths=half.numpy())
+    inertia, mu, hl = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    B = 1 << 20                                       # BASELINE.json full size (config 5)
+    x = synthetic.cube_states(B, seed=3, device=DEV)
+    traj, _ = ops.cube_rollout(x, inertia, mu, hl, 0.0068, 1)
+    xp = synthetic.perturb_next_state(traj[:, 1], seed=4)
+    l1, g1, s1, _, it = ops.cube_loss_raw(x, xp, inertia, mu, hl, 0.0068, 1e-3, want_iters=True)
+    l2, g2, s2, _, _ = ops.cube_loss_raw(x, xp, inertia, mu, hl, 0.0068, 1e-3)
+    assert torch.equal(l1, l2) and torch.equal(g1, g2) and torch.equal(s1, s2)
+    assert torch.isfinite(l1).all() and (l1 >= -1e-12).all()
+    assert int(it.max()) <= 60
+    parts = [ops.cube_loss_raw(x[i::8].contiguous(), xp[i::8].contiguous(), inertia, mu, hl, 0.0068, 1e-3)
+             for i in range(8)]
+    gsum = sum(p[1] for p in parts)
+    assert max_rel_to_scale(gsum.cpu().numpy(), g1.cpu().numpy()) < 1e-11
+    assert abs(sum(p[2] for p in parts).item() - s1.item()) < 1e-11 * abs(s1.item())
+    assert abs(l1.sum().item() - s1.item()) < 1e-11 * abs(s1.item())
+
+
+def test_symmetry_properties_full_size():
+    """Size-independent properties: the loss is invariant under world yaw and horizontal translation."""
+    pi, fr, half = synthetic.cube_learnables_perturbed(2)
+    from oracle import contactnets_oracle as co
+    g = dict(theta=co.pi_cm_to_theta(pi).numpy(), friction_params=fr.numpy(), half_lengths=half.numpy())
+    inertia, mu, hl = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    B = 65536
+    x = synthetic.cube_states(B, seed=5, device=DEV)
+    traj, _ = ops.cube_rollout(x, inertia, mu, hl, 0.0068, 1)
+    xp = synthetic.perturb_next_state(traj[:, 1], seed=6)
+    base = ops.cube_loss_raw(x, xp, inertia, mu, hl, 0.0068, 1e-3)[0]
+    ang = 0.7
+    qz = torch.tensor([np.cos(ang / 2), 0, 0, np.sin(ang / 2)], dtype=torch.float64, device=DEV)
+    Rz = torch.tensor([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]],
+                      dtype=torch.float64, device=DEV)
+    from dair_pll_b200 import quaternion
+
+    def yaw(s):
+        out = s.clone()
+        out[:, :4] = quaternion.multiply(qz.expand(s.shape[0], 4), s[:, :4])
+        out[:, 4:7] = s[:, 4:7] @ Rz.t() + torch.tensor([0.3, -1.2, 0.0], dtype=torch.float64, device=DEV)
+        out[:, 10:13] = s[:, 10:13] @ Rz.t()          # world-frame linear velocity rotates; body w does not
+        return out
+    moved = ops.cube_loss_raw(yaw(x), yaw(xp), inertia, mu, hl, 0.0068, 1e-3)[0]
+    err = (moved - base).abs() / base.abs().clamp(min=1e-9)
+    assert err.max().item() < 1e-7 and err.median().item() < 1e-12
+
+
+def test_fp32_variant_matches_reference_golden(assets_dir):
+    g = load_golden('cube_real_perturbed')
+    inertia, mu, half = (torch.from_numpy(a).float().to(DEV) for a in kernel_level_params(g))
+    x, xp = torch.from_numpy(g['x']).float().to(DEV), torch.from_numpy(g['x_plus']).float().to(DEV)
+    loss, grad, _, _, _ = ops.cube_loss_raw(x, xp, inertia, mu, half, float(g['dt']), 1e-3)
+    l = loss.cpu().numpy().astype(np.float64)
+    assert np.abs(l - g['loss']).max() < 1e-4 * max(np.abs(g['loss']).max(), 1e-3)
+    assert abs(l.mean() - g['loss'].mean()) < 1e-4 * abs(g['loss'].mean())
+
+
+def test_invalid_arguments_raise():
+    x = torch.zeros(4, 12, dtype=torch.float64, device=DEV)
+    p = torch.ones(10, dtype=torch.float64, device=DEV)
+    with pytest.raises(ValueError):
+        ops.cube_loss_raw(x, x, p, p[:1], p[:3], 0.0068, 1e-3)
+    with pytest.raises(TypeError):
+        ops.cube_loss_raw(x.half(), x.half(), p.half(), p[:1].half(), p[:3].half(), 0.0068, 1e-3)

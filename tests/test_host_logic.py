@@ -1,0 +1,107 @@
+"""CPU: host-side mirror of the reference API (no compute calls into the CUDA library)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from dair_pll_b200 import _lib, quaternion
+from dair_pll_b200.inertia import InertialParameterConverter as IPC
+from dair_pll_b200.multibody_learnable_system import MultibodyLearnableSystem
+from dair_pll_b200.state_space import FixedBaseSpace, FloatingBaseSpace, ProductSpace
+from dair_pll_b200.system_spec import SystemSpec
+from oracle import contactnets_oracle as co
+from tests.util import ROOT
+
+torch.manual_seed(0)
+
+
+def test_cube_spec_and_parameter_names(assets_dir):
+    system = MultibodyLearnableSystem({'cube': os.path.join(assets_dir, 'cube.urdf')}, 0.0068)
+    spec = system.multibody_terms.spec
+    assert (spec.kind, spec.n_q, spec.n_v, spec.n_x, spec.n_contacts) == ('cube', 7, 6, 13, 4)
+    # checkpoint compatibility: same state_dict keys/shapes as the reference module tree
+    sd = system.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        'multibody_terms.lagrangian_terms.inertial_parameters': (1, 10),
+        'multibody_terms.contact_terms.friction_params': (2,),
+        'multibody_terms.contact_terms.geometries.0.length_params': (1, 3)}
+    assert system.space.n_x == 13 and system.max_batch_dim == 1 and system.dt == 0.0068
+    assert torch.allclose(sd['multibody_terms.contact_terms.friction_params'], torch.tensor([0.15, 1.0]).double())
+    mu = system.multibody_terms.contact_terms.pair_friction()
+    assert abs(mu.item() - 2 * 0.15 / 1.15) < 1e-15     # 0.26087
+    theta = sd['multibody_terms.lagrangian_terms.inertial_parameters'][0]
+    assert np.allclose(theta[:4].numpy(), [-0.4971, -3.4087, -3.4087, -3.4087], atol=5e-5)
+
+
+def test_elbow_spec(assets_dir):
+    spec = SystemSpec.from_urdf(os.path.join(assets_dir, 'elbow.urdf'))
+    assert (spec.kind, spec.n_q, spec.n_v, spec.n_x, spec.n_contacts) == ('elbow', 8, 7, 15, 8)
+    assert spec.joints[0].origin == (-0.035, 0.06, 0.0) and spec.joints[0].axis == (0.0, 1.0, 0.0)
+    assert spec.geometries[1].offset == (0.035, 0.0, 0.0) and spec.geometries[-1].kind == 'plane'
+    assert spec.collision_pairs == [(2, 0), (2, 1)]
+
+
+def test_no_cpu_path(assets_dir):
+    system = MultibodyLearnableSystem({'cube': os.path.join(assets_dir, 'cube.urdf')}, 0.0068)
+    x = torch.zeros(3, 13, dtype=torch.float64)
+    x[:, 0] = 1
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        system.contactnets_loss(x, torch.zeros(3, 0), x)
+
+
+def test_inertia_conversions_roundtrip_and_match_oracle():
+    pi_cm = torch.tensor([[0.37, 0.37 * 0.002, -0.37 * 0.001, 0.37 * 0.003, 8.1e-4, 8.5e-4, 7.9e-4, 1e-5, -2e-5, 3e-5],
+                          [1.3, 0.02, 0.01, -0.03, 2e-3, 3e-3, 2.5e-3, 1e-4, 0, -2e-4]], dtype=torch.float64)
+    theta = IPC.pi_cm_to_theta(pi_cm)
+    assert torch.allclose(IPC.theta_to_pi_cm(theta), pi_cm, rtol=1e-12, atol=1e-16)
+    assert torch.allclose(IPC.pi_o_to_theta(IPC.theta_to_pi_o(theta)), theta, rtol=1e-12, atol=1e-14)
+    assert torch.allclose(theta, co.pi_cm_to_theta(pi_cm), rtol=1e-13, atol=1e-15)
+    vec = IPC.pi_cm_to_drake_spatial_inertia(IPC.theta_to_pi_cm(theta))
+    assert torch.allclose(vec, co.theta_to_inertia_vector(theta), rtol=1e-12, atol=1e-16)
+    assert torch.allclose(vec[:, 4:], pi_cm[:, 4:] / pi_cm[:, :1], rtol=1e-12)
+
+
+def test_state_space_exponential_and_difference_are_inverse():
+    space = ProductSpace([FixedBaseSpace(0), FloatingBaseSpace(1)])
+    assert (space.n_q, space.n_v, space.n_x) == (8, 7, 15)
+    q = torch.randn(5, 8, dtype=torch.float64)
+    q[:, :4] /= q[:, :4].norm(dim=-1, keepdim=True)
+    dq = 0.3 * torch.randn(5, 7, dtype=torch.float64)
+    q2 = space.exponential(q, dq)
+    assert torch.allclose(space.configuration_difference(q, q2), dq, atol=1e-12)
+    # same quaternion update as the oracle's restatement of state_space.py:466-486
+    ref = co.quat_mul(q[:, :4], co.quat_exp(dq[:, :3]))
+    assert torch.allclose(q2[:, :4], ref, atol=1e-15)
+    assert torch.allclose(quaternion.exp(torch.zeros(1, 3, dtype=torch.float64)),
+                          torch.tensor([[1., 0, 0, 0]], dtype=torch.float64))
+    x = torch.randn(5, 15, dtype=torch.float64)
+    assert torch.equal(space.x(*space.q_v(x)), x)
+
+
+def test_velocity_integrator_step_uses_callback():
+    from dair_pll_b200.integrator import VelocityIntegrator
+    space = ProductSpace([FixedBaseSpace(0), FloatingBaseSpace(0)])
+    integ = VelocityIntegrator(space, lambda x, c: (space.v(x) * 0 + 1.0, c), 0.1)
+    x = torch.zeros(2, 13, dtype=torch.float64)
+    x[:, 0] = 1
+    traj, carry = integ.simulate(x, torch.zeros(2, 1), 3)
+    assert traj.shape == (2, 4, 13) and carry.shape == (2, 4, 1)
+    assert torch.allclose(traj[:, -1, 4:7], torch.full((2, 3), 0.3, dtype=torch.float64))
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI shared library loads and exports each function include/*.h declares."""
+    header = open(os.path.join(ROOT, 'include', 'dair_pll_b200.h')).read()
+    declared = set(re.findall(r'\b(dpll_\w+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
+    lib = ctypes.CDLL(_lib.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.dpll_version.restype = ctypes.c_int
+    lib.dpll_workspace_bytes.restype = ctypes.c_size_t
+    assert lib.dpll_version() >= 100
+    assert lib.dpll_workspace_bytes() >= 14 * 8

@@ -1,0 +1,111 @@
+"""CPU: pins the portable oracle (oracle/contactnets_oracle.py + oracle/cone_qp.c) against the
+golden vectors produced by the reference's own Python (oracle/gen_golden.py), and certifies the
+QP solutions independently (KKT + a second algorithm)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cone_qp
+from oracle import contactnets_oracle as co
+from oracle.callables import CUBE_TREE, TreeCallables
+from tests.util import load_golden, max_rel_to_scale, oracle_params_from_golden, rel_err
+
+CASES = ['cube_real_nominal', 'cube_real_perturbed', 'cube_synthetic']
+CALLS = TreeCallables(CUBE_TREE)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_loss_force_and_gradients_match_reference_python(name):
+    g = load_golden(name)
+    P = oracle_params_from_golden(g)
+    x, xp = torch.from_numpy(g['x']), torch.from_numpy(g['x_plus'])
+    loss, force = co.contactnets_loss(CALLS, P, x, xp, float(g['dt']), return_force=True)
+    loss.mean().backward()
+    assert rel_err(loss.detach().numpy(), g['loss'], 1e-9).max() < 1e-9
+    assert np.abs(loss.detach().numpy() - g['loss']).max() < 1e-13
+    # forces: 1e-9 of the per-sample force scale (weakly determined components, cond(Q) ~ 5e5)
+    scale = np.maximum(np.abs(g['force']).max(axis=1, keepdims=True), 1e-6)
+    assert (np.abs(force.numpy() - g['force']) / scale).max() < 1e-8
+    assert max_rel_to_scale(P.inertial_parameters.grad.numpy(), g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(P.friction_params.grad.numpy(), g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(P.length_params[0].grad.numpy(), g['grad_length']) < 1e-9
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_terms_match_reference_python(name):
+    g = load_golden(name)
+    P = oracle_params_from_golden(g, False)
+    xp = torch.from_numpy(g['x_plus'])
+    M, J, phi, acc = co.multibody_terms(CALLS, P, xp[:, :7], xp[:, 7:])
+    assert np.abs(M.numpy() - g['terms_M']).max() < 1e-15
+    assert np.abs(acc.numpy() - g['terms_acc']).max() < 1e-11 * max(1.0, np.abs(g['terms_acc']).max())
+    assert np.abs(np.sort(phi.numpy(), -1) - g['terms_phi_sorted']).max() < 1e-15
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_simulation_matches_reference_python(name):
+    g = load_golden(name)
+    P = oracle_params_from_golden(g, False)
+    x0 = torch.from_numpy(g['sim_x0'])
+    steps = g['sim_traj'].shape[1] - 1
+    traj = co.simulate(CALLS, P, x0, float(g['dt']), steps).numpy()
+    # first step tight; later steps compound contact sensitivity
+    assert np.abs(traj[:, 1] - g['sim_traj'][:, 1]).max() < 1e-9
+    assert np.abs(traj - g['sim_traj']).max() < 1e-7
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_qp_solutions_are_kkt_certified(name):
+    """Solver-independent certificate: f in K, Qf+q in K, complementarity."""
+    g = load_golden(name)
+    A, q, eps = torch.from_numpy(g['qp_J']), torch.from_numpy(g['qp_q']), float(g['qp_eps'])
+    kkt_golden = cone_qp.kkt_residual(A, q, eps, torch.from_numpy(g['qp_f']))
+    assert kkt_golden.max().item() < 1e-11
+    f, _, iters, _ = cone_qp.solve(g['qp_J'], g['qp_q'], eps)
+    assert cone_qp.kkt_residual(A, q, eps, torch.from_numpy(f)).max().item() < 1e-11
+    assert iters.max() < 100
+
+
+def test_second_algorithm_agrees():
+    """Accelerated projected gradient on the dual (no shared logic beyond the projection)."""
+    g = load_golden('cube_real_perturbed')
+    sel = np.argsort(-np.abs(g['qp_f']).max(axis=1))[:64]
+    A, q, eps = g['qp_J'][sel], g['qp_q'][sel], float(g['qp_eps'])
+    f_newton, _, _, _ = cone_qp.solve(A, q, eps)
+    f_apg, _ = cone_qp.solve_apg(A, q, eps)
+    scale = np.abs(f_newton).max(axis=1, keepdims=True)
+    assert (np.abs(f_newton - f_apg) / scale).max() < 1e-9
+
+
+def test_survey_anchor_values():
+    """SURVEY.md Appendix C regression anchors (nominal URDF parameters, real tosses):
+    theta0 of the nominal cube and the free-flight step of 0.pt[0]."""
+    pi_cm = torch.tensor([[0.37, 0, 0, 0, .00081, .00081, .00081, 0, 0, 0]], dtype=torch.float64)
+    theta = co.pi_cm_to_theta(pi_cm)[0].numpy()
+    assert np.allclose(theta[:4], [-0.4971, -3.4087, -3.4087, -3.4087], atol=5e-5)
+    assert np.allclose(theta[4:], 0, atol=1e-15)
+    P = co.OracleParams(co.pi_cm_to_theta(pi_cm), torch.tensor([0.15, 1.0], dtype=torch.float64),
+                        [torch.tensor([[.0524] * 3], dtype=torch.float64)])
+    g = load_golden('cube_real_nominal')
+    x0 = torch.from_numpy(g['x'][:1])        # trajectory 0, first state: free flight
+    xn = co.sim_step(CALLS, P, x0, 0.0068)[0].numpy()
+    assert abs(xn[12] - (x0[0, 12].item() - 9.81 * 0.0068)) < 1e-12
+    assert np.allclose(xn[7:12], x0[0, 7:12].numpy(), atol=1e-12)
+    assert np.allclose(xn[:4], [-0.15705441058, -0.86646730033, 0.46472603915, 0.09272560657], atol=1e-10)
+
+
+def test_icnn_support_equals_autograd_of_support_function():
+    """deep_support_function.py:213-266: forward() is the input-Jacobian of the network output."""
+    torch.manual_seed(0)
+    W = 32
+    net = dict(Wd0=torch.randn(3, W, dtype=torch.float64), Wd1=torch.randn(3, W, dtype=torch.float64),
+               Wh=torch.randn(W, W, dtype=torch.float64) / W, wout=torch.randn(W, dtype=torch.float64),
+               perturbations=torch.zeros(4, 3, dtype=torch.float64))
+    d = torch.randn(17, 3, dtype=torch.float64)
+    d = (d / d.norm(dim=-1, keepdim=True)).requires_grad_()
+    lrelu = torch.nn.functional.leaky_relu
+    h0 = lrelu(d @ net['Wd0'], 0.5)
+    h1 = lrelu(h0 @ net['Wh'].abs() + d @ net['Wd1'], 0.5)
+    f = (h1 @ net['wout'].abs()).sum()
+    (jac,) = torch.autograd.grad(f, d)
+    assert torch.allclose(co.icnn_support(net, d.detach()), jac, atol=1e-12)
