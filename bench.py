@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument('--impl', choices=['b200', 'reference'], default='b200')
     ap.add_argument('--cpu-sample', type=int, default=65536, help='samples in the CPU baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--variant', type=int, default=0, help='0 = wavefront loss kernel, 1 = one sample per thread')
     return ap.parse_args()
 
 
@@ -198,6 +199,7 @@ def main():
         dist.init_process_group('nccl', device_id=device)
     dtype = torch.float64 if args.dtype == 'f64' else torch.float32
     from dair_pll_b200 import ops, parallel
+    ops.set_loss_variant(args.variant)
 
     system = make_system(device, dtype)
     B = args.batch
@@ -308,7 +310,7 @@ def main():
         'roofline': {'bound': 'fp64_cuda_core' if dtype == torch.float64 else 'fp32_cuda_core',
                      'achieved': achieved_tflops, 'peak': peak_flops / 1e12, 'unit': 'TFLOP/s',
                      'frac': achieved_tflops / (peak_flops / 1e12), 'traffic': None,
-                     'kernel': 'cube_loss_kernel', 'kernel_ms': ms_kernel,
+                     'kernel': 'cube_loss_wf_kernel' if args.variant == 0 else 'cube_loss_kernel', 'kernel_ms': ms_kernel,
                      'flops_per_sample': flops_per_sample,
                      'peak_source': 'measured in this run: dpll_fma_peak (dependent-free FMA chains, all SMs)',
                      'hbm': {'achieved_gbs': hbm_gbs, 'peak_gbs': hbm_peak, 'frac': hbm_gbs / hbm_peak,

@@ -16,9 +16,10 @@ _i64, _i32, _f64, _f32, _sz = ctypes.c_int64, ctypes.c_int32, ctypes.c_double, c
 EXPORTS = {
     'dpll_version': ([], ctypes.c_int),
     'dpll_workspace_bytes': ([], _sz),
-    'dpll_cube_loss_f64': ([_c_void_p] * 6 + [_f64, _f64, _i64] + [_c_void_p] * 5 + [_c_void_p, _sz, _c_void_p],
+    'dpll_set_loss_variant': ([ctypes.c_int], ctypes.c_int),
+    'dpll_cube_loss_f64': ([_c_void_p] * 6 + [_f64, _f64, _i64] + [_c_void_p] * 6 + [_c_void_p, _sz, _c_void_p],
                            ctypes.c_int),
-    'dpll_cube_loss_f32': ([_c_void_p] * 6 + [_f32, _f32, _i64] + [_c_void_p] * 5 + [_c_void_p, _sz, _c_void_p],
+    'dpll_cube_loss_f32': ([_c_void_p] * 6 + [_f32, _f32, _i64] + [_c_void_p] * 6 + [_c_void_p, _sz, _c_void_p],
                            ctypes.c_int),
     'dpll_cube_rollout_f64': ([_c_void_p] * 4 + [_f64, _f64, _i64, _i32] + [_c_void_p] * 4, ctypes.c_int),
     'dpll_cube_rollout_f32': ([_c_void_p] * 4 + [_f32, _f32, _i64, _i32] + [_c_void_p] * 4, ctypes.c_int),

@@ -20,6 +20,11 @@
 #pragma once
 #include "cn_common.cuh"
 
+#ifndef CN_STAT_LS
+#define CN_STAT_LS()
+#define CN_STAT_UNIT()
+#endif
+
 namespace cn {
 
 constexpr int CUBE_NQ = 7, CUBE_NV = 6, CUBE_NX = 13, CUBE_NC = 4, CUBE_K = 12;
@@ -259,65 +264,106 @@ CN_HD void cube_line(const CubeParams<T>& P, const T* r1, const T* ed, T uMd, T 
   }
 }
 
-// Newton solve.  u: in = start point, out = optimum.  Returns iterations; f = forces at u.
+// True iff u = 0 is already optimal: every contact's y = -q/eps lies in the polar cone, so
+// all forces vanish and the gradient M*0 - J^T 0 is exactly zero (free flight).
+template <typename T> CN_HD bool cube_trivially_solved(const CubeProblem<T>& S) {
+  bool open = true;
+#pragma unroll
+  for (int c = 0; c < CUBE_NC; ++c) {
+    const T qt2 = S.q[3 * c] * S.q[3 * c] + S.q[3 * c + 1] * S.q[3 * c + 1];
+    const T qn = S.q[3 * c + 2];
+    open = open && (qn >= T(0)) && (qt2 <= qn * qn);
+  }
+  return open;
+}
+
+template <typename T> CN_HD bool cube_converged(const SolverCfg<T>& cfg, T res2, T scale2) {
+  return !(res2 > cfg.tol_rel * cfg.tol_rel * scale2);   // also true for NaN
+}
+
+// One schedulable unit of the Newton solve (the wavefront kernel runs one unit per lane per
+// trip): Hessian at u, Cholesky step, trial point, derivative line search if the full step
+// overshoots.  Updates u / prev_res2 / it; returns true when the sample is finished.
+template <typename T>
+CN_HD bool cube_newton_unit(const CubeParams<T>& P, const CubeProblem<T>& S, const SolverCfg<T>& cfg, T* u,
+                            T& prev_res2, int& it) {
+  T g[6], H[36], res2, scale2;
+  CN_STAT_UNIT();
+  cube_eval<T, true>(P, S, u, g, H, (T*)nullptr, res2, scale2);
+  if (cube_converged(cfg, res2, scale2)) return true;
+  if (res2 <= cfg.tol_stall * cfg.tol_stall * scale2 && res2 >= T(0.25) * prev_res2) return true;  // rounding floor
+  if (it >= cfg.max_iter) return true;
+  prev_res2 = res2;
+  T d[6];
+  chol_solve_neg<T, 6>(H, g, d);
+  T d0 = T(0);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) d0 += g[i] * d[i];
+  T u1[6], g1[6], res2b, scale2b;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) u1[i] = u[i] + d[i];
+  cube_eval<T, false>(P, S, u1, g1, (T*)nullptr, (T*)nullptr, res2b, scale2b);
+  T d1 = T(0);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) d1 += g1[i] * d[i];
+  const T thresh = cfg.ls_c * t_abs(d0);
+  ++it;
+  if (d1 <= thresh) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) u[i] = u1[i];
+    return cube_converged(cfg, res2b, scale2b);
+  }
+  // overshoot: safeguarded Newton on phi' over (0,1)
+  T Md[6], uMd = T(0), dMd = T(0);
+  cube_mass_mul(P, S, d, Md);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { uMd += u[i] * Md[i]; dMd += d[i] * Md[i]; }
+  T r1[12], ed[12];
+#pragma unroll
+  for (int c = 0; c < CUBE_NC; ++c) {
+    T e[3], e1[3];
+    cross3(d, S.rho + 3 * c, e);
+    cross3(u1, S.rho + 3 * c, e1);
+    ed[3 * c] = P.mu * (e[0] + d[3]); ed[3 * c + 1] = P.mu * (e[1] + d[4]); ed[3 * c + 2] = e[2] + d[5];
+    r1[3 * c] = P.mu * (e1[0] + u1[3]) + S.q[3 * c];
+    r1[3 * c + 1] = P.mu * (e1[1] + u1[4]) + S.q[3 * c + 1];
+    r1[3 * c + 2] = (e1[2] + u1[5]) + S.q[3 * c + 2];
+  }
+  T lo = T(0), hi = T(1), alpha, da, ha;
+  cube_line(P, r1, ed, uMd, dMd, T(1), da, ha);       // first guess: Newton step on phi' from alpha = 1
+  alpha = T(1) - da / ha;
+  if (!(alpha > lo && alpha < hi)) alpha = T(0.5);
+  for (int ls = 0; ls < 40; ++ls) {
+    cube_line(P, r1, ed, uMd, dMd, alpha, da, ha);
+    CN_STAT_LS();
+    if (t_abs(da) <= thresh) break;
+    if (da < T(0)) lo = alpha; else hi = alpha;
+    T an = alpha - da / ha;
+    if (!(an > lo && an < hi)) an = T(0.5) * (lo + hi);
+    if (hi - lo <= T(4) * eps_of<T>() * hi) { alpha = lo > T(0) ? lo : an; break; }
+    alpha = an;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) u[i] += alpha * d[i];
+  return false;
+}
+
+// Forces f = Pi(-(D_mu J u + q)/eps) at u (sappy order).
+template <typename T>
+CN_HD void cube_forces(const CubeParams<T>& P, const CubeProblem<T>& S, const T* u, T* f) {
+  T g[6], res2, scale2;
+  cube_eval<T, false>(P, S, u, g, (T*)nullptr, f, res2, scale2);
+}
+
+// Newton solve from u (in: start point, out: optimum).  Returns iterations; f = forces at u.
 template <typename T>
 CN_HD int cube_solve(const CubeParams<T>& P, const CubeProblem<T>& S, const SolverCfg<T>& cfg, T* u, T* f) {
-  T g[6], H[36], res2, scale2;
-  cube_eval<T, true>(P, S, u, g, H, f, res2, scale2);
   int it = 0;
-  T prev = res2 * T(4) + T(1);
-  while (true) {
-    if (!(res2 > cfg.tol_rel * cfg.tol_rel * scale2)) break;                               // converged (or NaN)
-    if (res2 <= cfg.tol_stall * cfg.tol_stall * scale2 && res2 >= T(0.25) * prev) break;   // rounding floor
-    if (it >= cfg.max_iter) break;
-    prev = res2;
-    T d[6];
-    chol_solve_neg<T, 6>(H, g, d);
-    T d0 = T(0);
-    for (int i = 0; i < 6; ++i) d0 += g[i] * d[i];
-    T u1[6], g1[6];
-    for (int i = 0; i < 6; ++i) u1[i] = u[i] + d[i];
-    cube_eval<T, true>(P, S, u1, g1, H, f, res2, scale2);
-    T d1 = T(0);
-    for (int i = 0; i < 6; ++i) d1 += g1[i] * d[i];
-    const T thresh = cfg.ls_c * t_abs(d0);
-    if (d1 <= thresh) {
-      for (int i = 0; i < 6; ++i) { u[i] = u1[i]; g[i] = g1[i]; }
-    } else {
-      // overshoot: safeguarded Newton on phi' over (0,1)
-      T Md[6], uMd = T(0), dMd = T(0);
-      cube_mass_mul(P, S, d, Md);
-      for (int i = 0; i < 6; ++i) { uMd += u[i] * Md[i]; dMd += d[i] * Md[i]; }
-      T r1[12], ed[12];
-#pragma unroll
-      for (int c = 0; c < CUBE_NC; ++c) {
-        T e[3], e1[3];
-        cross3(d, S.rho + 3 * c, e);
-        cross3(u1, S.rho + 3 * c, e1);
-        ed[3 * c] = P.mu * (e[0] + d[3]); ed[3 * c + 1] = P.mu * (e[1] + d[4]); ed[3 * c + 2] = e[2] + d[5];
-        r1[3 * c] = P.mu * (e1[0] + u1[3]) + S.q[3 * c];
-        r1[3 * c + 1] = P.mu * (e1[1] + u1[4]) + S.q[3 * c + 1];
-        r1[3 * c + 2] = (e1[2] + u1[5]) + S.q[3 * c + 2];
-      }
-      T lo = T(0), hi = T(1), alpha, da, ha;
-      // first guess: Newton step on phi' from alpha = 1 using the curvature there
-      cube_line(P, r1, ed, uMd, dMd, T(1), da, ha);
-      alpha = T(1) - da / ha;
-      if (!(alpha > lo && alpha < hi)) alpha = T(0.5);
-      for (int ls = 0; ls < 40; ++ls) {
-        cube_line(P, r1, ed, uMd, dMd, alpha, da, ha);
-        if (t_abs(da) <= thresh) break;
-        if (da < T(0)) lo = alpha; else hi = alpha;
-        T an = alpha - da / ha;
-        if (!(an > lo && an < hi)) an = T(0.5) * (lo + hi);
-        if (hi - lo <= T(1e-12) * hi) { alpha = lo > T(0) ? lo : an; break; }
-        alpha = an;
-      }
-      for (int i = 0; i < 6; ++i) u[i] += alpha * d[i];
-      cube_eval<T, true>(P, S, u, g, H, f, res2, scale2);
-    }
-    ++it;
+  if (!cube_trivially_solved(S)) {
+    T prev = T(-1);
+    while (!cube_newton_unit(P, S, cfg, u, prev, it)) {}
   }
+  cube_forces(P, S, u, f);
   return it;
 }
 

@@ -40,7 +40,8 @@ cube_loss_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __r
                  const T* __restrict__ inertia,
                  const T* __restrict__ mu, const T* __restrict__ half, T dt, T eps, int64_t B,
                  T* __restrict__ loss, T* __restrict__ force, int32_t* __restrict__ iters,
-                 T* __restrict__ partials, int want_grad) {
+                 T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;
   cn::CubeParams<T> P;
   cn::cube_params_init(P, inertia, mu, half, dt, eps);
   const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
@@ -61,7 +62,7 @@ cube_loss_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __r
     const T w = weight ? weight[b] : T(1);
 #pragma unroll
     for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] += w * gs[i];
-    loss[b] = l;
+    if (loss) loss[b] = l;
     acc[14] += l;
     if (iters) iters[b] = it;
   }
@@ -82,10 +83,212 @@ cube_loss_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __r
   }
 }
 
+// ---------------------------------------------------------------------------
+// Wavefront variant of the loss kernel.
+//
+// The Newton solve needs 0 .. ~30 iterations depending on the sample (most free-flight
+// samples need none), so one-sample-per-thread leaves ~80% of the lanes idle (ncu:
+// 5.8 active threads per instruction, profiles/).  Here each WARP owns a pool of kWfSlots
+// sample slots in shared memory and three ring-buffer queues (free / active / done), and
+// runs warp-uniform phases, each processing up to 32 slots at full width:
+//   P  prologue : load 32 new samples, build their QPs, park the state in slots
+//   N  newton   : one Newton unit for 32 unconverged slots
+//   E  epilogue : loss + envelope backward for 32 converged slots
+// The phase choice depends only on the (warp-uniform) queue counts, so there is no
+// divergence between phases; all arithmetic is the same per-sample code as the simple
+// kernel, so per-sample results are bitwise identical to it.  Samples are assigned to
+// warps statically (contiguous ranges), which keeps the gradient reduction deterministic.
+// ---------------------------------------------------------------------------
+constexpr int kWfSlots = 64;
+constexpr int kWfWarps = 4;
+constexpr int kWfFields = 40;   // IW 6 | mcW 3 | rho 12 | q 12 | u 6 | prev_res2 1
+
+template <typename T> struct WfWarpPool {
+  T field[kWfFields][kWfSlots];
+  int32_t sample[kWfSlots];
+  int32_t iters[kWfSlots];
+  uint8_t q_free[kWfSlots], q_act[kWfSlots], q_done[kWfSlots];
+};
+
+template <typename T>
+__device__ __forceinline__ void wf_store_problem(WfWarpPool<T>* pool, int slot, const cn::CubeProblem<T>& S) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) pool->field[i][slot] = S.IW[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) pool->field[6 + i][slot] = S.mcW[i];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) pool->field[9 + i][slot] = S.rho[i];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) pool->field[21 + i][slot] = S.q[i];
+}
+
+template <typename T>
+__device__ __forceinline__ void wf_load_problem(const WfWarpPool<T>* pool, int slot, cn::CubeProblem<T>& S) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) S.IW[i] = pool->field[i][slot];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.mcW[i] = pool->field[6 + i][slot];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) S.rho[i] = pool->field[9 + i][slot];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) S.q[i] = pool->field[21 + i][slot];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWfWarps * 32)
+cube_loss_wf_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __restrict__ weight,
+                    const T* __restrict__ inertia, const T* __restrict__ mu, const T* __restrict__ half, T dt,
+                    T eps, int64_t B, T* __restrict__ loss, T* __restrict__ force, int32_t* __restrict__ iters,
+                    T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;
+  extern __shared__ __align__(16) unsigned char wf_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WfWarpPool<T>* pool = reinterpret_cast<WfWarpPool<T>*>(wf_smem) + warp;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  cn::CubeParams<T> P;
+  cn::cube_params_init(P, inertia, mu, half, dt, eps);
+  const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
+  T acc[kNAcc];
+#pragma unroll
+  for (int i = 0; i < kNAcc; ++i) acc[i] = T(0);
+
+  // static contiguous sample range of this warp
+  const int64_t gw = (int64_t)blockIdx.x * kWfWarps + warp, W = (int64_t)gridDim.x * kWfWarps;
+  const int64_t base = B / W, rem = B % W;
+  const int64_t lo = gw * base + (gw < rem ? gw : rem);
+  const int64_t hi = lo + base + (gw < rem ? 1 : 0);
+  int64_t next = lo;
+
+  for (int s = lane; s < kWfSlots; s += 32) pool->q_free[s] = (uint8_t)s;
+  int n_free = kWfSlots, n_act = 0, n_done = 0, h_free = 0, h_act = 0, h_done = 0;
+  __syncwarp();
+
+  while (true) {
+    const int64_t left = hi - next;
+    int phase;   // 0 = P, 1 = N, 2 = E
+    if (n_done >= 32 || (left == 0 && n_act == 0 && n_done > 0)) phase = 2;
+    else if (left > 0 && n_act < 32 && n_free >= (left < 32 ? (int)left : 32)) phase = 0;
+    else if (n_act > 0) phase = 1;
+    else if (n_done > 0) phase = 2;
+    else break;
+
+    if (phase == 0) {
+      const int k = left < 32 ? (int)left : 32;
+      const bool on = lane < k;
+      bool trivial = false;
+      int slot = 0;
+      if (on) {
+        slot = pool->q_free[(h_free + lane) % kWfSlots];
+        const int64_t b = next + lane;
+        T xs[13], xps[13];
+#pragma unroll
+        for (int i = 0; i < 13; ++i) { xs[i] = x[b * 13 + i]; xps[i] = xp[b * 13 + i]; }
+        cn::CubeProblem<T> S;
+        cn::CubeLossAux<T> A;
+        cn::cube_loss_prologue(P, xs, xps, S, A);
+        trivial = cn::cube_trivially_solved(S);
+        wf_store_problem(pool, slot, S);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = T(0);
+        pool->field[39][slot] = T(-1);
+        pool->sample[slot] = (int32_t)(b - lo);   // offset inside the warp's range
+        pool->iters[slot] = 0;
+      }
+      const unsigned m_done = __ballot_sync(0xffffffffu, on && trivial);
+      const unsigned m_act = __ballot_sync(0xffffffffu, on && !trivial);
+      if (on) {
+        if (trivial) pool->q_done[(h_done + n_done + __popc(m_done & lt_mask)) % kWfSlots] = (uint8_t)slot;
+        else pool->q_act[(h_act + n_act + __popc(m_act & lt_mask)) % kWfSlots] = (uint8_t)slot;
+      }
+      n_done += __popc(m_done); n_act += __popc(m_act);
+      h_free = (h_free + k) % kWfSlots; n_free -= k; next += k;
+    } else if (phase == 1) {
+      const int k = n_act < 32 ? n_act : 32;
+      const bool on = lane < k;
+      bool fin = false;
+      int slot = 0;
+      if (on) {
+        slot = pool->q_act[(h_act + lane) % kWfSlots];
+        cn::CubeProblem<T> S;
+        wf_load_problem(pool, slot, S);
+        T u[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) u[i] = pool->field[33 + i][slot];
+        T prev = pool->field[39][slot];
+        int it = pool->iters[slot];
+        fin = cn::cube_newton_unit(P, S, cfg, u, prev, it);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = u[i];
+        pool->field[39][slot] = prev;
+        pool->iters[slot] = it;
+      }
+      __syncwarp();
+      const unsigned m_done = __ballot_sync(0xffffffffu, on && fin);
+      const unsigned m_act = __ballot_sync(0xffffffffu, on && !fin);
+      h_act = (h_act + k) % kWfSlots; n_act -= k;
+      if (on) {
+        if (fin) pool->q_done[(h_done + n_done + __popc(m_done & lt_mask)) % kWfSlots] = (uint8_t)slot;
+        else pool->q_act[(h_act + n_act + __popc(m_act & lt_mask)) % kWfSlots] = (uint8_t)slot;
+      }
+      n_done += __popc(m_done); n_act += __popc(m_act);
+    } else {
+      const int k = n_done < 32 ? n_done : 32;
+      const bool on = lane < k;
+      int slot = 0;
+      if (on) {
+        slot = pool->q_done[(h_done + lane) % kWfSlots];
+        const int64_t b = lo + pool->sample[slot];
+        T xs[13], xps[13];
+#pragma unroll
+        for (int i = 0; i < 13; ++i) { xs[i] = x[b * 13 + i]; xps[i] = xp[b * 13 + i]; }
+        cn::CubeProblem<T> S;
+        cn::CubeLossAux<T> A;
+        cn::cube_loss_prologue(P, xs, xps, S, A);     // recomputed (cheap) instead of parked in shared memory
+        T u[6], f[12];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) u[i] = pool->field[33 + i][slot];
+        cn::cube_forces(P, S, u, f);
+        T gs[DPLL_CUBE_NPARAM];
+#pragma unroll
+        for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
+        const T l = cn::cube_loss_epilogue(P, S, A, f, want_grad ? gs : (T*)nullptr,
+                                           force ? force + b * 12 : (T*)nullptr);
+        const T w = weight ? weight[b] : T(1);
+#pragma unroll
+        for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] += w * gs[i];
+        if (loss) loss[b] = l;
+        acc[14] += l;
+        if (iters) iters[b] = pool->iters[slot];
+      }
+      __syncwarp();
+      if (on) pool->q_free[(h_free + n_free + lane) % kWfSlots] = (uint8_t)slot;
+      n_free += k; h_done = (h_done + k) % kWfSlots; n_done -= k;
+    }
+    __syncwarp();
+  }
+
+  if (!partials) return;
+  __shared__ T red[kWfWarps][kNAcc];
+#pragma unroll
+  for (int i = 0; i < kNAcc; ++i) {
+    const T s = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNAcc) {
+    T s = T(0);
+#pragma unroll
+    for (int w = 0; w < kWfWarps; ++w) s += red[w][threadIdx.x];
+    partials[(int64_t)blockIdx.x * kNAcc + threadIdx.x] = s;
+  }
+}
+
 // Fixed-order reduction of the per-block partials: warp w owns accumulator w.
 template <typename T>
 __global__ void reduce_partials_kernel(const T* __restrict__ partials, int nblocks, T* __restrict__ grad,
-                                       T* __restrict__ loss_sum) {
+                                       T* __restrict__ loss_sum, const int32_t* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (w >= kNAcc) return;
   T s = T(0);
@@ -138,30 +341,48 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int64_t iters) {
 }
 
 template <typename T>
-int launch_cube_loss(const T* x, const T* xp, const T* weight, const T* inertia, const T* mu, const T* half, T dt, T eps,
-                     int64_t B, T* loss, T* force, int32_t* iters, T* grad, T* loss_sum, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+int launch_cube_loss(int variant, const T* x, const T* xp, const T* weight, const T* inertia, const T* mu,
+                     const T* half, T dt, T eps, int64_t B, T* loss, T* force, int32_t* iters, T* grad, T* loss_sum,
+                     const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
   if (B < 0 || !inertia || !mu || !half) return DPLL_EINVAL;
-  if (B > 0 && (!x || !xp || !loss)) return DPLL_EINVAL;
+  if (B > 0 && (!x || !xp)) return DPLL_EINVAL;
   const bool want_red = grad || loss_sum;
   if (want_red && (!workspace || workspace_bytes < dpll_workspace_bytes())) return DPLL_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DeviceInfo di = device_info();
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_kernel<T>, kLossThreads, 0);
-  if (per_sm < 1) per_sm = 1;
-  int64_t need = (B + kLossThreads - 1) / kLossThreads;
-  int64_t cap = (int64_t)di.sms * per_sm;
-  if (cap > kMaxBlocks) cap = kMaxBlocks;
-  int blocks = (int)(need < cap ? need : cap);
-  if (blocks < 1) blocks = 1;
   T* partials = want_red ? static_cast<T*>(workspace) : nullptr;
-  cube_loss_kernel<T><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss, force,
-                                                       iters, partials, grad ? 1 : 0);
+  int blocks;
+  if (variant == 0) {
+    // wavefront kernel: persistent, one resident set of blocks
+    const size_t smem = sizeof(WfWarpPool<T>) * kWfWarps;
+    cudaError_t ea = cudaFuncSetAttribute(cube_loss_wf_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ea != cudaSuccess) return (int)ea;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_wf_kernel<T>, kWfWarps * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    int64_t need = (B + kWfWarps * 32 - 1) / (kWfWarps * 32);
+    int64_t cap = (int64_t)di.sms * per_sm;
+    if (cap > kMaxBlocks) cap = kMaxBlocks;
+    blocks = (int)(need < cap ? need : cap);
+    if (blocks < 1) blocks = 1;
+    cube_loss_wf_kernel<T><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss,
+                                                               force, iters, partials, grad ? 1 : 0, skip_flag);
+  } else {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_kernel<T>, kLossThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    int64_t need = (B + kLossThreads - 1) / kLossThreads;
+    int64_t cap = (int64_t)di.sms * per_sm;
+    if (cap > kMaxBlocks) cap = kMaxBlocks;
+    blocks = (int)(need < cap ? need : cap);
+    if (blocks < 1) blocks = 1;
+    cube_loss_kernel<T><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss, force,
+                                                         iters, partials, grad ? 1 : 0, skip_flag);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (want_red) {
-    reduce_partials_kernel<T><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, grad, loss_sum);
+    reduce_partials_kernel<T><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, grad, loss_sum, skip_flag);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
@@ -192,24 +413,32 @@ int launch_cube_rollout(const T* x0, const T* inertia, const T* mu, const T* hal
 
 extern "C" {
 
+// Kernel variant selector for A/B measurements (0 = wavefront [default], 1 = one sample per thread).
+static int g_loss_variant = 0;
+int dpll_set_loss_variant(int variant) {
+  if (variant < 0 || variant > 1) return DPLL_EINVAL;
+  g_loss_variant = variant;
+  return DPLL_OK;
+}
+
 int dpll_version(void) { return 100; }
 
 size_t dpll_workspace_bytes(void) { return (size_t)kMaxBlocks * kNAcc * sizeof(double); }
 
 int dpll_cube_loss_f64(const double* x, const double* x_plus, const double* weight, const double* inertia,
-                       const double* mu_pair, const double* half, double dt, double eps, int64_t B, double* loss, double* force,
-                       int32_t* iters, double* grad, double* loss_sum, void* workspace, size_t workspace_bytes,
-                       void* stream) {
-  return launch_cube_loss<double>(x, x_plus, weight, inertia, mu_pair, half, dt, eps, B, loss, force, iters, grad,
-                                  loss_sum, workspace, workspace_bytes, stream);
+                       const double* mu_pair, const double* half, double dt, double eps, int64_t B, double* loss,
+                       double* force, int32_t* iters, double* grad, double* loss_sum, const int32_t* skip_flag,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_cube_loss<double>(g_loss_variant, x, x_plus, weight, inertia, mu_pair, half, dt, eps, B, loss, force,
+                                  iters, grad, loss_sum, skip_flag, workspace, workspace_bytes, stream);
 }
 
 int dpll_cube_loss_f32(const float* x, const float* x_plus, const float* weight, const float* inertia,
-                       const float* mu_pair, const float* half, float dt, float eps, int64_t B, float* loss, float* force,
-                       int32_t* iters, float* grad, float* loss_sum, void* workspace, size_t workspace_bytes,
-                       void* stream) {
-  return launch_cube_loss<float>(x, x_plus, weight, inertia, mu_pair, half, dt, eps, B, loss, force, iters, grad,
-                                 loss_sum, workspace, workspace_bytes, stream);
+                       const float* mu_pair, const float* half, float dt, float eps, int64_t B, float* loss,
+                       float* force, int32_t* iters, float* grad, float* loss_sum, const int32_t* skip_flag,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_cube_loss<float>(g_loss_variant, x, x_plus, weight, inertia, mu_pair, half, dt, eps, B, loss, force,
+                                 iters, grad, loss_sum, skip_flag, workspace, workspace_bytes, stream);
 }
 
 int dpll_cube_rollout_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,

@@ -33,6 +33,11 @@ def _workspace(device: torch.device) -> Tensor:
     return ws
 
 
+def set_loss_variant(variant: int) -> None:
+    """0 = warp-level wavefront kernel (default), 1 = one sample per thread (A/B measurements)."""
+    _lib.check(_lib.load().dpll_set_loss_variant(variant), 'dpll_set_loss_variant')
+
+
 def _check_inputs(*tensors: Tensor) -> torch.dtype:
     dtype = tensors[0].dtype
     if dtype not in _SUFFIX:
@@ -47,7 +52,8 @@ def _check_inputs(*tensors: Tensor) -> torch.dtype:
 
 def cube_loss_raw(x: Tensor, x_plus: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, dt: float,
                   eps: float, weight: Optional[Tensor] = None, want_grad: bool = True,
-                  want_force: bool = False, want_iters: bool = False):
+                  want_force: bool = False, want_iters: bool = False, want_loss: bool = True,
+                  skip_flag: Optional[Tensor] = None, grad_out: Optional[Tensor] = None):
     """Direct call of ``dpll_cube_loss_*``.  x, x_plus (B,13).  Returns
     (loss (B,), grad (14,) | None, loss_sum (1,), force (B,12) | None, iters (B,) | None)."""
     dtype = _check_inputs(x, x_plus, inertia, mu_pair, half)
@@ -59,8 +65,8 @@ def cube_loss_raw(x: Tensor, x_plus: Tensor, inertia: Tensor, mu_pair: Tensor, h
         raise ValueError('cube parameters must be inertia (10), mu_pair (1), half (3)')
     B = x.shape[0]
     dev = x.device
-    loss = torch.empty(B, dtype=dtype, device=dev)
-    grad = torch.empty(14, dtype=dtype, device=dev) if want_grad else None
+    loss = torch.empty(B, dtype=dtype, device=dev) if want_loss else None
+    grad = (grad_out if grad_out is not None else torch.empty(14, dtype=dtype, device=dev)) if want_grad else None
     loss_sum = torch.empty(1, dtype=dtype, device=dev)
     force = torch.empty((B, 12), dtype=dtype, device=dev) if want_force else None
     iters = torch.empty(B, dtype=torch.int32, device=dev) if want_iters else None
@@ -70,7 +76,8 @@ def cube_loss_raw(x: Tensor, x_plus: Tensor, inertia: Tensor, mu_pair: Tensor, h
     fn = getattr(_lib.load(), 'dpll_cube_loss_' + _SUFFIX[dtype])
     with torch.cuda.device(dev):
         rc = fn(_ptr(x), _ptr(x_plus), _ptr(weight), _ptr(inertia), _ptr(mu_pair), _ptr(half), dt, eps, B,
-                _ptr(loss), _ptr(force), _ptr(iters), _ptr(grad), _ptr(loss_sum), _ptr(ws), ws.numel(), _stream())
+                _ptr(loss), _ptr(force), _ptr(iters), _ptr(grad), _ptr(loss_sum), _ptr(skip_flag), _ptr(ws), ws.numel(),
+                _stream())
     _lib.check(rc, 'dpll_cube_loss')
     return loss, grad, loss_sum, force, iters
 
@@ -82,9 +89,9 @@ class CubeContactNetsLoss(torch.autograd.Function):
 
     The backward is fused into the forward kernel (envelope theorem,
     multibody_learnable_system.py:172-175): the forward launch already returns
-    d(sum_b loss_b)/d params.  When autograd hands back a uniform upstream gradient (the
-    stride-0 expansion produced by ``loss.mean()`` / ``loss.sum()``) the backward is a
-    14-element scale; otherwise the kernel is re-run with per-sample weights.
+    d(sum_b loss_b)/d params.  When the upstream gradient is uniform (``loss.sum()`` /
+    ``loss.mean()``) the backward is a 14-element scale; otherwise the kernel is re-run with
+    per-sample weights.  Uniformity is decided on the device (skip flag), never by a host sync.
     """
 
     @staticmethod
@@ -100,11 +107,21 @@ class CubeContactNetsLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         grad, x, x_plus, inertia, mu_pair, half = ctx.saved_tensors
-        if grad_loss.dim() == 1 and grad_loss.stride(0) == 0 and grad_loss.numel() > 0:
-            g = grad * grad_loss[0]
+        if grad_loss.numel() == 0:
+            g = torch.zeros_like(grad)
+        elif grad_loss.dim() == 1 and grad_loss.stride(0) == 0:
+            g = grad * grad_loss[0]                      # loss.sum(): stride-0 expansion, provably uniform
         else:
-            _, g, _, _, _ = cube_loss_raw(x, x_plus, inertia, mu_pair, half, ctx.dt, ctx.eps,
-                                          weight=grad_loss.contiguous(), want_grad=True)
+            # loss.mean() materialises its (uniform) upstream gradient.  Decide on the DEVICE whether
+            # it is uniform: if so the weighted re-evaluation below turns into a no-op (skip flag) and
+            # the fused gradient from the forward launch is scaled; no host synchronisation.
+            grad_loss = grad_loss.contiguous()
+            lo, hi = torch.aminmax(grad_loss)
+            uniform = lo == hi
+            gw = torch.zeros_like(grad)
+            cube_loss_raw(x, x_plus, inertia, mu_pair, half, ctx.dt, ctx.eps, weight=grad_loss, want_grad=True,
+                          want_loss=False, skip_flag=uniform.to(torch.int32), grad_out=gw)
+            g = torch.where(uniform, grad * lo, gw)
         s_in, s_mu, s_h = ctx.shapes
         return (None, None, g[0:10].reshape(s_in), g[10:11].reshape(s_mu), g[11:14].reshape(s_h), None, None)
 

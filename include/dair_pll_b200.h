@@ -48,6 +48,11 @@ extern "C" {
 /* Library/ABI version (major*100 + minor). */
 int dpll_version(void);
 
+/* Selects the loss-kernel implementation, for A/B measurement only: 0 = warp-level wavefront
+ * scheduler (default), 1 = one sample per thread.  Both produce bitwise-identical per-sample
+ * losses.  Process-wide setting (the single piece of mutable library state). */
+int dpll_set_loss_variant(int variant);
+
 /* Bytes of device scratch any entry point below may need. */
 size_t dpll_workspace_bytes(void);
 
@@ -62,24 +67,30 @@ size_t dpll_workspace_bytes(void);
  *
  *   x, x_plus : (B, 13)   states (only the velocity part of x is read, :127)
  *   weight    : (B)       nullable; per-sample upstream gradient w_b.  NULL means w_b = 1.
- *   loss      : (B)       per-sample loss (:194-197)
+ *   loss      : (B)       nullable; per-sample loss (:194-197)
  *   force     : (B, 12)   nullable; solved contact impulses in the reference's ordering
  *                         [n_1..n_4, t_1x, t_1y, ..., t_4x, t_4y] (tensor_utils.py:460-497),
  *                         contacts ordered by ascending box-vertex index
  *   iters     : (B)       nullable; Newton iterations used
  *   grad      : (14)      nullable; OVERWRITTEN with d(sum_b w_b loss_b)/d params
  *   loss_sum  : (1)       nullable; OVERWRITTEN with sum_b loss_b
+ *   skip_flag : (1) int32 nullable DEVICE flag; if non-null and non-zero when the kernels start,
+ *                         the whole call is a no-op on the device (outputs untouched).  Lets a
+ *                         caller make the launch conditional on a device-side predicate without
+ *                         a host synchronisation (used by the autograd backward).
  * Deterministic: fixed sample->thread mapping and fixed-order reductions (bitwise
  * reproducible for a given B).
  */
 int dpll_cube_loss_f64(const double* x, const double* x_plus, const double* weight,
                        const double* inertia, const double* mu_pair, const double* half,
-                       double dt, double eps, int64_t B, double* loss, double* force, int32_t* iters, double* grad,
-                       double* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
+                       double dt, double eps, int64_t B, double* loss, double* force,
+                       int32_t* iters, double* grad, double* loss_sum, const int32_t* skip_flag,
+                       void* workspace, size_t workspace_bytes, void* stream);
 int dpll_cube_loss_f32(const float* x, const float* x_plus, const float* weight,
                        const float* inertia, const float* mu_pair, const float* half, float dt,
-                       float eps, int64_t B, float* loss, float* force, int32_t* iters, float* grad, float* loss_sum,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       float eps, int64_t B, float* loss, float* force, int32_t* iters,
+                       float* grad, float* loss_sum, const int32_t* skip_flag, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /*
  * Learnable time stepping for the cube: `steps` applications of

@@ -93,15 +93,16 @@ def test_matches_cpu_oracle_on_random_inputs():
         xp = synthetic.perturb_next_state(co.sim_step(calls, P, x, 0.0068), seed=22)
     loss_o = co.contactnets_loss(calls, P, x, xp, 0.0068)
     loss_o.sum().backward()
-    g = dict(theta=P.inertial_parameters.detach().numpy(), friction_params=fr.numpy(), half_lengths=half.numpy())
+    g = dict(theta=P.inertial_parameters.detach().numpy(), friction_params=fr.detach().numpy(),
+             half_lengths=half.detach().numpy())
     inertia, mu, hl = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
     loss, grad, loss_sum, _, _ = ops.cube_loss_raw(x.to(DEV), xp.to(DEV), inertia, mu, hl, 0.0068, 1e-3)
     assert rel_err(loss.cpu().numpy(), loss_o.detach().numpy(), 1e-9).max() < 1e-9
     assert abs(loss_sum.item() - loss_o.sum().item()) < 1e-9 * abs(loss_o.sum().item())
     # chain the kernel's callable-level gradient to the leaves and compare with oracle autograd
     theta = P.inertial_parameters.detach().clone().requires_grad_()
-    frl = fr.clone().requires_grad_()
-    ln = half.clone().reshape(1, 3).requires_grad_()
+    frl = fr.detach().clone().requires_grad_()
+    ln = half.detach().clone().reshape(1, 3).requires_grad_()
     m = frl.abs()
     flat = torch.cat((co.theta_to_inertia_vector(theta).reshape(10), (2 * m[0] * m[1] / (m[0] + m[1])).reshape(1),
                       ln.abs().reshape(3)))
@@ -126,6 +127,25 @@ def test_weighted_backward_equals_sum_of_per_sample_gradients():
                                                float(g['dt']), 1e-3)
             ref += w[i].item() * gi.cpu().numpy()
     assert max_rel_to_scale(got, ref) < 1e-11
+
+
+def test_wavefront_and_simple_kernels_agree_bitwise():
+    """Both kernel variants run the same per-sample arithmetic: identical losses, forces, iteration
+    counts; gradients equal up to summation order."""
+    g = load_golden('cube_synthetic')
+    inertia, mu, half = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    x = synthetic.cube_states(100003, seed=31, device=DEV)
+    traj, _ = ops.cube_rollout(x, inertia, mu, half, 0.0068, 1)
+    xp = synthetic.perturb_next_state(traj[:, 1], seed=32)
+    try:
+        ops.set_loss_variant(1)
+        a = ops.cube_loss_raw(x, xp, inertia, mu, half, 0.0068, 1e-3, want_force=True, want_iters=True)
+    finally:
+        ops.set_loss_variant(0)
+    b = ops.cube_loss_raw(x, xp, inertia, mu, half, 0.0068, 1e-3, want_force=True, want_iters=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    assert max_rel_to_scale(a[1].cpu().numpy(), b[1].cpu().numpy()) < 1e-12
+    assert abs(a[2].item() - b[2].item()) < 1e-12 * abs(b[2].item())
 
 
 def test_empty_and_ragged_batches(assets_dir):
