@@ -17,6 +17,11 @@
 // inverse is closed-form (Schur complement = R I_sym R^T).  The QP is solved in
 // primal (velocity) form:  min_u 1/2 u^T M u + eps/2 sum_c |Pi(-(D_mu J_c u + q_c)/eps)|^2
 // by Newton with a derivative-based line search; f_c = Pi(...) at the optimum.
+//
+// Code-size discipline: the kernels are instruction-cache sensitive (warps of one SM run
+// different phases), so per-contact work is written as loops over c whose unroll factor
+// UNR is a template parameter: UNR = 1 (rolled) when the per-sample problem lives in a
+// shared-memory slot (dynamic indexing is free there), UNR = 4 for register-resident use.
 #pragma once
 #include "cn_common.cuh"
 
@@ -28,7 +33,8 @@
 namespace cn {
 
 constexpr int CUBE_NQ = 7, CUBE_NV = 6, CUBE_NX = 13, CUBE_NC = 4, CUBE_K = 12;
-constexpr int CUBE_NPARAM = 14;  // [inertia 10 | mu_pair 1 | half_lengths 3]
+constexpr int CUBE_NPARAM = 14;      // [inertia 10 | mu_pair 1 | half_lengths 3]
+constexpr int CUBE_PROB_FIELDS = 33; // IW 6 | mcW 3 | rho 12 | q 12
 
 template <typename T> struct CubeParams {
   T m, c[3], Isym[6];   // the 10-vector the generated callables take (multibody_terms.py:198-205)
@@ -64,18 +70,19 @@ CN_HD void cube_params_init(CubeParams<T>& P, const T* inertia, const T* mu, con
   P.dscale[3] = P.dscale[4] = P.dscale[5] = P.inv_m;
 }
 
-// Per-sample quantities that stay fixed during the Newton solve.
-template <typename T> struct CubeProblem {
-  T R[9];        // world <- body rotation
-  T IW[6];       // R Io R^T
-  T mcW[3];      // m R c
-  T rho[12];     // world-frame lever arms of the 4 selected corners
-  T q[12];       // QP linear term, sappy order [tx, ty, n] per contact
-  uint32_t sel;  // 3 sign bits per selected corner (bit set = +h), corner c at bits 3c..3c+2 (x,y,z)
+// View of the per-sample quantities that stay fixed during the Newton solve: element k of
+// the 33-field record at p[k * s].  s = 1 over a local array (registers), s = #slots over a
+// shared-memory pool laid out field-major (bank-conflict-free across lanes).
+template <typename T> struct CubeProb {
+  T* p;
+  int s;
+  CN_HD T& IW(int i) const { return p[i * s]; }          // R Io R^T  [xx,yy,zz,xy,xz,yz]
+  CN_HD T& mcW(int i) const { return p[(6 + i) * s]; }   // m R c
+  CN_HD T& rho(int k) const { return p[(9 + k) * s]; }   // world lever arms, 3 per contact
+  CN_HD T& q(int k) const { return p[(21 + k) * s]; }    // QP linear term, sappy order [tx,ty,n] per contact
 };
 
-// apply the body-frame closed-form inverse mass matrix:  [aw; av] = M^-1 [tau; frc]
-// (tau, aw body frame; frc, av world frame).  Schur complement of M is I_sym.
+// [aw; av] = M^-1 [tau; frc]  (tau, aw body frame; frc, av world frame); Schur complement = I_sym.
 template <typename T>
 CN_HD void cube_minv(const CubeParams<T>& P, const T* R, const T* tau, const T* frc, T* aw, T* av) {
   T fb[3], cxf[3], rhs[3], cxa[3], rc[3];
@@ -90,80 +97,97 @@ CN_HD void cube_minv(const CubeParams<T>& P, const T* R, const T* tau, const T* 
 
 // u^ -> M^ u^ in world-twist coordinates
 template <typename T>
-CN_HD void cube_mass_mul(const CubeParams<T>& P, const CubeProblem<T>& S, const T* u, T* o) {
-  T a[3], b[3], c[3];
-  sym3_mul(S.IW, u, a);
-  cross3(S.mcW, u + 3, b);
-  cross3(S.mcW, u, c);
-  for (int i = 0; i < 3; ++i) { o[i] = a[i] + b[i]; o[3 + i] = P.m * u[3 + i] - c[i]; }
+CN_HD void cube_mass_mul(const CubeParams<T>& P, const CubeProb<T>& S, const T* u, T* o) {
+  const T I0 = S.IW(0), I1 = S.IW(1), I2 = S.IW(2), I3 = S.IW(3), I4 = S.IW(4), I5 = S.IW(5);
+  const T mc[3] = {S.mcW(0), S.mcW(1), S.mcW(2)};
+  T b[3], c[3];
+  cross3(mc, u + 3, b);
+  cross3(mc, u, c);
+  o[0] = I0 * u[0] + I3 * u[1] + I4 * u[2] + b[0];
+  o[1] = I3 * u[0] + I1 * u[1] + I5 * u[2] + b[1];
+  o[2] = I4 * u[0] + I5 * u[1] + I2 * u[2] + b[2];
+  for (int i = 0; i < 3; ++i) o[3 + i] = P.m * u[3 + i] - c[i];
 }
 
-// Select the 4 corners with the largest support in direction d (body frame) -- top-k of
-// d . (sigma o h) over the 8 sign patterns (geometry.py:191-197).  Returned in ascending
-// vertex-index order (the reference's order is unspecified: topk(sorted=False)).
+// The 4 corners with the largest support d . (sigma o h) (top-k of the reference,
+// geometry.py:191-197), in ascending vertex-index order (the reference's order is unspecified).
+// Closed form: with a_k = |d_k| h_k sorted s <= m <= l, the support values in decreasing order
+// are {none flipped, flip s, flip m, then flip s+m or flip l, whichever costs less}.
+// Returns the 4 vertex indices (i = 4 x + 2 y + z with bit set = +h, geometry.py:39-41)
+// packed 3 bits each, corner c at bits 3c..3c+2.
 template <typename T> CN_HD uint32_t cube_select_corners(const T* d, const T* h) {
-  const T a0 = d[0] * h[0], a1 = d[1] * h[1], a2 = d[2] * h[2];
-  T dots[8];
+  const T a0 = t_abs(d[0]) * h[0], a1 = t_abs(d[1]) * h[1], a2 = t_abs(d[2]) * h[2];
+  const uint32_t best = (d[0] >= T(0) ? 4u : 0u) | (d[1] >= T(0) ? 2u : 0u) | (d[2] >= T(0) ? 1u : 0u);
+  const bool c01 = a0 <= a1, c12 = a1 <= a2, c02 = a0 <= a2;
+  // axis of the smallest / largest a (ties towards the lower axis); axis k flips vertex bit 4 >> k
+  const int is = c01 ? (c02 ? 0 : 2) : (c12 ? 1 : 2);
+  const int il = c01 ? (c12 ? 2 : 1) : (c02 ? 2 : 0);
+  const int im = 3 - is - il;
+  const T lo01 = t_min(a0, a1), hi01 = t_max(a0, a1);
+  const T as = t_min(lo01, a2), al = t_max(hi01, a2), am = t_max(lo01, t_min(hi01, a2));
+  const uint32_t bs = 4u >> is, bm = 4u >> im, bl = 4u >> il;
+  const uint32_t v3 = (as + am <= al) ? (best ^ bs ^ bm) : (best ^ bl);
+  uint32_t mask = (1u << best) | (1u << (best ^ bs)) | (1u << (best ^ bm)) | (1u << v3);
+  uint32_t sel = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    dots[i] = ((i & 4) ? a0 : -a0) + ((i & 2) ? a1 : -a1) + ((i & 1) ? a2 : -a2);
-  uint32_t sel = 0; int n = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int rank = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) rank += (dots[j] > dots[i]) || (dots[j] == dots[i] && j < i);
-    if (rank < 4) {
-      // vertex i = (x: bit2, y: bit1, z: bit0) (geometry.py:39-41)
-      const uint32_t bits = ((i >> 2) & 1) | (((i >> 1) & 1) << 1) | ((i & 1) << 2);
-      sel |= bits << (3 * n);
-      ++n;
-    }
+  for (int c = 0; c < 4; ++c) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t i = (uint32_t)(__ffs((int)mask) - 1);
+#else
+    const uint32_t i = (uint32_t)(__builtin_ffs((int)mask) - 1);
+#endif
+    mask &= mask - 1u;
+    sel |= i << (3 * c);
   }
   return sel;
 }
 
+// sign (+1 / -1) of corner c of `sel` along axis (0 = x, 1 = y, 2 = z)
 template <typename T> CN_HD T sgn_bit(uint32_t sel, int c, int axis) {
-  return ((sel >> (3 * c + axis)) & 1u) ? T(1) : T(-1);
+  return ((sel >> (3 * c + 2 - axis)) & 1u) ? T(1) : T(-1);
 }
 
-// Shared geometry set-up: R, world inertia, corner selection, lever arms, phi.
-template <typename T>
-CN_HD void cube_geometry(const CubeParams<T>& P, const T* quat, T pos_z, CubeProblem<T>& S, T* phi) {
-  quat_to_rot(quat, S.R);
-  const T* R = S.R;
+// Shared geometry set-up: R, world inertia, corner selection, lever arms (phi_c = rho_c,z + pos_z,
+// geometry.py:568-571, is formed where it is used).
+template <typename T, int UNR>
+CN_HD void cube_geometry(const CubeParams<T>& P, const T* quat, T* R, uint32_t& sel, const CubeProb<T>& S) {
+  quat_to_rot(quat, R);
   // IW = R Io R^T
   T A[9];
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
     const T r0 = R[3 * i], r1 = R[3 * i + 1], r2 = R[3 * i + 2];
     A[3 * i + 0] = r0 * P.Io[0] + r1 * P.Io[3] + r2 * P.Io[4];
     A[3 * i + 1] = r0 * P.Io[3] + r1 * P.Io[1] + r2 * P.Io[5];
     A[3 * i + 2] = r0 * P.Io[4] + r1 * P.Io[5] + r2 * P.Io[2];
   }
-  S.IW[0] = A[0] * R[0] + A[1] * R[1] + A[2] * R[2];
-  S.IW[1] = A[3] * R[3] + A[4] * R[4] + A[5] * R[5];
-  S.IW[2] = A[6] * R[6] + A[7] * R[7] + A[8] * R[8];
-  S.IW[3] = A[0] * R[3] + A[1] * R[4] + A[2] * R[5];
-  S.IW[4] = A[0] * R[6] + A[1] * R[7] + A[2] * R[8];
-  S.IW[5] = A[3] * R[6] + A[4] * R[7] + A[5] * R[8];
+  S.IW(0) = A[0] * R[0] + A[1] * R[1] + A[2] * R[2];
+  S.IW(1) = A[3] * R[3] + A[4] * R[4] + A[5] * R[5];
+  S.IW(2) = A[6] * R[6] + A[7] * R[7] + A[8] * R[8];
+  S.IW(3) = A[0] * R[3] + A[1] * R[4] + A[2] * R[5];
+  S.IW(4) = A[0] * R[6] + A[1] * R[7] + A[2] * R[8];
+  S.IW(5) = A[3] * R[6] + A[4] * R[7] + A[5] * R[8];
   T cW[3];
   rot3(R, P.c, cW);
-  for (int i = 0; i < 3; ++i) S.mcW[i] = P.m * cW[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.mcW(i) = P.m * cW[i];
   // support direction in the body frame: -(third row of R)  (geometry.py:560-564)
   const T d[3] = {-R[6], -R[7], -R[8]};
-  S.sel = cube_select_corners(d, P.h);
+  sel = cube_select_corners(d, P.h);
   T Rh[9];
-  for (int i = 0; i < 3; ++i)
-    for (int k = 0; k < 3; ++k) Rh[3 * i + k] = R[3 * i + k] * P.h[k];
 #pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Rh[3 * i + k] = R[3 * i + k] * P.h[k];
+#pragma unroll UNR
   for (int c = 0; c < CUBE_NC; ++c) {
-    const T sx = sgn_bit<T>(S.sel, c, 0), sy = sgn_bit<T>(S.sel, c, 1), sz = sgn_bit<T>(S.sel, c, 2);
-    for (int i = 0; i < 3; ++i) S.rho[3 * c + i] = sx * Rh[3 * i] + sy * Rh[3 * i + 1] + sz * Rh[3 * i + 2];
-    phi[c] = S.rho[3 * c + 2] + pos_z;   // geometry.py:568-571
+    const T sx = sgn_bit<T>(sel, c, 0), sy = sgn_bit<T>(sel, c, 1), sz = sgn_bit<T>(sel, c, 2);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) S.rho(3 * c + i) = sx * Rh[3 * i] + sy * Rh[3 * i + 1] + sz * Rh[3 * i + 2];
   }
 }
 
-// Contact-free acceleration M^-1 F at (R, w_B, ...), in body(w)/world(v) state coordinates
+// Contact-free acceleration M^-1 F at (R, w_B), in body(w)/world(v) state coordinates
 // (closed form of the generated lagrangian_forces, see oracle/callables.py).
 template <typename T>
 CN_HD void cube_free_accel(const CubeParams<T>& P, const T* R, const T* wB, T* aw, T* av) {
@@ -181,48 +205,54 @@ CN_HD void cube_free_accel(const CubeParams<T>& P, const T* R, const T* wB, T* a
   cube_minv(P, R, tau, frc, aw, av);
 }
 
+// residual of contact c at twist u:  r = D_mu (u_w x rho_c + u_v) + q_c
+template <typename T>
+CN_HD void cube_contact_residual(const CubeParams<T>& P, const CubeProb<T>& S, int c, const T* u, T* rho, T* r) {
+  rho[0] = S.rho(3 * c); rho[1] = S.rho(3 * c + 1); rho[2] = S.rho(3 * c + 2);
+  T e[3];
+  cross3(u, rho, e);
+  r[0] = P.mu * (e[0] + u[3]) + S.q(3 * c);
+  r[1] = P.mu * (e[1] + u[4]) + S.q(3 * c + 1);
+  r[2] = (e[2] + u[5]) + S.q(3 * c + 2);
+}
+
 // Gradient (and optionally Hessian) of the primal objective at u (world twist).
-//   g = M u - sum_c J_c^T f~_c ;  H = M + sum_c J_c^T K_c J_c
-// Also returns the scaled norms used by the stopping test and, if f_out, the forces.
-template <typename T, bool WANT_H>
-CN_HD void cube_eval(const CubeParams<T>& P, const CubeProblem<T>& S, const T* u, T* g, T* H,
-                     T* f_out, T& res2, T& scale2) {
+//   g = M u - sum_c J_c^T f~_c ;  H = M + sum_c J_c^T K_c J_c   (H: full 6x6 row-major, lower part)
+// Also returns the scaled norms used by the stopping test.
+template <typename T, bool WANT_H, int UNR>
+CN_HD void cube_eval(const CubeParams<T>& P, const CubeProb<T>& S, const T* u, T* g, T* H, T& res2, T& scale2) {
   T Mu[6];
   cube_mass_mul(P, S, u, Mu);
   T z[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
   if (WANT_H) {
-    // H starts as M^
-    H[0] = S.IW[0]; H[7] = S.IW[1]; H[14] = S.IW[2];
-    H[6] = S.IW[3]; H[12] = S.IW[4]; H[13] = S.IW[5];
+    const T m0 = S.mcW(0), m1 = S.mcW(1), m2 = S.mcW(2);
+    H[0] = S.IW(0); H[7] = S.IW(1); H[14] = S.IW(2);
+    H[6] = S.IW(3); H[12] = S.IW(4); H[13] = S.IW(5);
     // M_vw = -S(mcW): rows 3..5, cols 0..2
-    H[18] = T(0);       H[19] = S.mcW[2];  H[20] = -S.mcW[1];
-    H[24] = -S.mcW[2];  H[25] = T(0);      H[26] = S.mcW[0];
-    H[30] = S.mcW[1];   H[31] = -S.mcW[0]; H[32] = T(0);
+    H[18] = T(0); H[19] = m2;   H[20] = -m1;
+    H[24] = -m2;  H[25] = T(0); H[26] = m0;
+    H[30] = m1;   H[31] = -m0;  H[32] = T(0);
     H[21] = P.m; H[28] = P.m; H[35] = P.m; H[27] = T(0); H[33] = T(0); H[34] = T(0);
   }
-#pragma unroll
+#pragma unroll UNR
   for (int c = 0; c < CUBE_NC; ++c) {
-    const T* rho = S.rho + 3 * c;
-    T e[3], r[3], f[3], K[6];
-    cross3(u, rho, e);
-    r[0] = P.mu * (e[0] + u[3]) + S.q[3 * c];
-    r[1] = P.mu * (e[1] + u[4]) + S.q[3 * c + 1];
-    r[2] = (e[2] + u[5]) + S.q[3 * c + 2];
+    T rho[3], r[3], f[3], K[6];
+    cube_contact_residual(P, S, c, u, rho, r);
     cone_eval<T, WANT_H>(r, P.inv_eps, P.mu, f, K);
-    if (f_out) { f_out[3 * c] = f[0]; f_out[3 * c + 1] = f[1]; f_out[3 * c + 2] = f[2]; }
     const T ft[3] = {P.mu * f[0], P.mu * f[1], f[2]};
     T tq[3];
     cross3(rho, ft, tq);
+#pragma unroll
     for (int i = 0; i < 3; ++i) { z[i] += tq[i]; z[3 + i] += ft[i]; }
     if (WANT_H) {
-      // Kfull rows
       const T K0[3] = {K[0], K[1], K[2]}, K1[3] = {K[1], K[3], K[4]}, K2[3] = {K[2], K[4], K[5]};
-      // P = S(rho) K : column j = rho x K_j  (K symmetric)
+      // Pm = S(rho) K : column j = rho x K_j  (K symmetric)
       T P0[3], P1[3], P2[3];
       cross3(rho, K0, P0); cross3(rho, K1, P1); cross3(rho, K2, P2);
-      // H_vw (rows 3+j, cols i) += P^T  i.e. H[(3+j)*6 + i] += P_j[i]
+      // H_vw (rows 3+j, cols i) += Pm^T
+#pragma unroll
       for (int i = 0; i < 3; ++i) { H[18 + i] += P0[i]; H[24 + i] += P1[i]; H[30 + i] += P2[i]; }
-      // H_ww += -P S(rho): row i = rho x (row i of P); row i of P = (P0[i], P1[i], P2[i])
+      // H_ww += -Pm S(rho): row i = rho x (row i of Pm)
       const T r0[3] = {P0[0], P1[0], P2[0]}, r1[3] = {P0[1], P1[1], P2[1]}, r2[3] = {P0[2], P1[2], P2[2]};
       T w0[3], w1[3], w2[3];
       cross3(rho, r0, w0); cross3(rho, r1, w1); cross3(rho, r2, w2);
@@ -243,21 +273,24 @@ CN_HD void cube_eval(const CubeParams<T>& P, const CubeProblem<T>& S, const T* u
   scale2 = t_max(a2, b2);
 }
 
-// 1-D derivative phi'(alpha) (and curvature) along u + alpha d, given the residuals r1 at
-// alpha = 1 and the direction images ed_c = D_mu J_c d:  r(alpha) = r1 - (1-alpha) ed.
-template <typename T>
-CN_HD void cube_line(const CubeParams<T>& P, const T* r1, const T* ed, T uMd, T dMd, T alpha, T& d1, T& d2) {
+// 1-D derivative phi'(alpha) (and curvature) along u + alpha d, expressed with the trial point
+// u1 = u + d:  r_c(alpha) = r_c(u1) - (1 - alpha) D_mu J_c d.
+template <typename T, int UNR>
+CN_HD void cube_line(const CubeParams<T>& P, const CubeProb<T>& S, const T* u1, const T* d, T uMd, T dMd, T alpha,
+                     T& d1, T& d2) {
   d1 = uMd + alpha * dMd;
   d2 = dMd;
   const T back = T(1) - alpha;
-#pragma unroll
+#pragma unroll UNR
   for (int c = 0; c < CUBE_NC; ++c) {
-    T r[3], f[3], K[6];
-    for (int j = 0; j < 3; ++j) r[j] = r1[3 * c + j] - back * ed[3 * c + j];
-    // cone_eval's K carries D_mu; the line needs the plain G/eps on ed (already D_mu-scaled),
-    // so evaluate with mu = 1.
+    T rho[3], r[3], e[3], f[3], K[6];
+    cube_contact_residual(P, S, c, u1, rho, r);
+    cross3(d, rho, e);
+    e[0] = P.mu * (e[0] + d[3]); e[1] = P.mu * (e[1] + d[4]); e[2] = e[2] + d[5];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[j] -= back * e[j];
+    // e is already D_mu-scaled, so the plain G/eps is wanted: evaluate with mu = 1
     cone_eval<T, true>(r, P.inv_eps, T(1), f, K);
-    const T* e = ed + 3 * c;
     d1 -= e[0] * f[0] + e[1] * f[1] + e[2] * f[2];
     d2 += e[0] * (K[0] * e[0] + K[1] * e[1] + K[2] * e[2]) + e[1] * (K[1] * e[0] + K[3] * e[1] + K[4] * e[2]) +
           e[2] * (K[2] * e[0] + K[4] * e[1] + K[5] * e[2]);
@@ -266,13 +299,12 @@ CN_HD void cube_line(const CubeParams<T>& P, const T* r1, const T* ed, T uMd, T 
 
 // True iff u = 0 is already optimal: every contact's y = -q/eps lies in the polar cone, so
 // all forces vanish and the gradient M*0 - J^T 0 is exactly zero (free flight).
-template <typename T> CN_HD bool cube_trivially_solved(const CubeProblem<T>& S) {
+template <typename T, int UNR> CN_HD bool cube_trivially_solved(const CubeProb<T>& S) {
   bool open = true;
-#pragma unroll
+#pragma unroll UNR
   for (int c = 0; c < CUBE_NC; ++c) {
-    const T qt2 = S.q[3 * c] * S.q[3 * c] + S.q[3 * c + 1] * S.q[3 * c + 1];
-    const T qn = S.q[3 * c + 2];
-    open = open && (qn >= T(0)) && (qt2 <= qn * qn);
+    const T q0 = S.q(3 * c), q1 = S.q(3 * c + 1), qn = S.q(3 * c + 2);
+    open = open && (qn >= T(0)) && (q0 * q0 + q1 * q1 <= qn * qn);
   }
   return open;
 }
@@ -281,90 +313,95 @@ template <typename T> CN_HD bool cube_converged(const SolverCfg<T>& cfg, T res2,
   return !(res2 > cfg.tol_rel * cfg.tol_rel * scale2);   // also true for NaN
 }
 
-// One schedulable unit of the Newton solve (the wavefront kernel runs one unit per lane per
-// trip): Hessian at u, Cholesky step, trial point, derivative line search if the full step
-// overshoots.  Updates u / prev_res2 / it; returns true when the sample is finished.
-template <typename T>
-CN_HD bool cube_newton_unit(const CubeParams<T>& P, const CubeProblem<T>& S, const SolverCfg<T>& cfg, T* u,
-                            T& prev_res2, int& it) {
+// One schedulable Newton step (the wavefront kernel runs one per lane per trip).  Each step is ONE
+// gradient/Hessian evaluation: the full step u <- u + d taken by the previous call is accepted
+// or rejected here, lazily, from the gradient at the new point (phi'(1) = g(u).d <= ls_c |phi'(0)|),
+// which the evaluation for the next direction provides anyway.  State: u (current, possibly
+// tentative point), d / d0 = phi'(0) of the pending step (d0 = 0: nothing pending), prev_res2, it.
+//   NEWTON_DONE        sample finished (converged / rounding floor / iteration cap), u final;
+//                      `it & 0xffff` = Newton directions taken
+//   NEWTON_CONTINUE    a new full step has been taken tentatively (u, d, d0 updated)
+//   NEWTON_LINESEARCH  the pending step overshoots: run cube_line_search (kept out of this
+//                      function so the wavefront kernel can run line searches as their own phase)
+enum { NEWTON_DONE = 0, NEWTON_CONTINUE = 1, NEWTON_LINESEARCH = 2 };
+
+template <typename T, int UNR>
+CN_HD int cube_newton_step(const CubeParams<T>& P, const CubeProb<T>& S, const SolverCfg<T>& cfg, T* u, T* d,
+                           T& d0, T& best_res2, int& it) {
   T g[6], H[36], res2, scale2;
   CN_STAT_UNIT();
-  cube_eval<T, true>(P, S, u, g, H, (T*)nullptr, res2, scale2);
-  if (cube_converged(cfg, res2, scale2)) return true;
-  if (res2 <= cfg.tol_stall * cfg.tol_stall * scale2 && res2 >= T(0.25) * prev_res2) return true;  // rounding floor
-  if (it >= cfg.max_iter) return true;
-  prev_res2 = res2;
-  T d[6];
-  chol_solve_neg<T, 6>(H, g, d);
-  T d0 = T(0);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) d0 += g[i] * d[i];
-  T u1[6], g1[6], res2b, scale2b;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) u1[i] = u[i] + d[i];
-  cube_eval<T, false>(P, S, u1, g1, (T*)nullptr, (T*)nullptr, res2b, scale2b);
-  T d1 = T(0);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) d1 += g1[i] * d[i];
-  const T thresh = cfg.ls_c * t_abs(d0);
-  ++it;
-  if (d1 <= thresh) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) u[i] = u1[i];
-    return cube_converged(cfg, res2b, scale2b);
+  cube_eval<T, true, UNR>(P, S, u, g, H, res2, scale2);
+  // a point with a negligible gradient is optimal (strong convexity), accepted step or not
+  if (cube_converged(cfg, res2, scale2)) return NEWTON_DONE;
+  // rounding floor: close to the optimum Newton contracts the residual quadratically, so three
+  // consecutive evaluations without a 4x reduction of the best residual mean the floor of this
+  // sample's conditioning has been reached (`it` carries the counter in its high bits)
+  if (res2 <= cfg.tol_stall * cfg.tol_stall * scale2 && !(res2 < T(0.25) * best_res2)) {
+    it += 1 << 16;
+    if ((it >> 16) >= 3) return NEWTON_DONE;
+  } else if (res2 < best_res2 || best_res2 < T(0)) {
+    it &= 0xffff;
   }
-  // overshoot: safeguarded Newton on phi' over (0,1)
+  if (res2 < best_res2 || best_res2 < T(0)) best_res2 = res2;
+  if (d0 < T(0)) {
+    T d1 = T(0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d1 += g[i] * d[i];
+    if (!(d1 <= -cfg.ls_c * d0)) return NEWTON_LINESEARCH;
+  }
+  if ((it & 0xffff) >= cfg.max_iter) return NEWTON_DONE;
+  block_solve6_neg<T>(H, g, d);
+  T dd = T(0);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { dd += g[i] * d[i]; u[i] += d[i]; }
+  d0 = dd < T(0) ? dd : T(0);     // a non-descent direction (rounding at the floor) is simply accepted
+  ++it;
+  return NEWTON_CONTINUE;
+}
+
+// Derivative-based line search for a rejected full step: u holds the tentative point u0 + d.
+// Safeguarded Newton on phi'(alpha) over (0,1) until |phi'(alpha)| <= ls_c |phi'(0)|;
+// u <- u0 + alpha d, d0 <- 0 (nothing pending).
+template <typename T, int UNR>
+CN_HD void cube_line_search(const CubeParams<T>& P, const CubeProb<T>& S, const SolverCfg<T>& cfg, T* u,
+                            const T* d, T& d0) {
+  const T thresh = -cfg.ls_c * d0;
   T Md[6], uMd = T(0), dMd = T(0);
   cube_mass_mul(P, S, d, Md);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { uMd += u[i] * Md[i]; dMd += d[i] * Md[i]; }
-  T r1[12], ed[12];
-#pragma unroll
-  for (int c = 0; c < CUBE_NC; ++c) {
-    T e[3], e1[3];
-    cross3(d, S.rho + 3 * c, e);
-    cross3(u1, S.rho + 3 * c, e1);
-    ed[3 * c] = P.mu * (e[0] + d[3]); ed[3 * c + 1] = P.mu * (e[1] + d[4]); ed[3 * c + 2] = e[2] + d[5];
-    r1[3 * c] = P.mu * (e1[0] + u1[3]) + S.q[3 * c];
-    r1[3 * c + 1] = P.mu * (e1[1] + u1[4]) + S.q[3 * c + 1];
-    r1[3 * c + 2] = (e1[2] + u1[5]) + S.q[3 * c + 2];
-  }
-  T lo = T(0), hi = T(1), alpha, da, ha;
-  cube_line(P, r1, ed, uMd, dMd, T(1), da, ha);       // first guess: Newton step on phi' from alpha = 1
-  alpha = T(1) - da / ha;
-  if (!(alpha > lo && alpha < hi)) alpha = T(0.5);
-  for (int ls = 0; ls < 40; ++ls) {
-    cube_line(P, r1, ed, uMd, dMd, alpha, da, ha);
+  for (int i = 0; i < 6; ++i) { uMd += (u[i] - d[i]) * Md[i]; dMd += d[i] * Md[i]; }
+  T lo = T(0), hi = T(1), alpha = T(1), da, ha;
+  for (int ls = 0; ls < 8; ++ls) {
+    cube_line<T, UNR>(P, S, u, d, uMd, dMd, alpha, da, ha);
     CN_STAT_LS();
-    if (t_abs(da) <= thresh) break;
-    if (da < T(0)) lo = alpha; else hi = alpha;
-    T an = alpha - da / ha;
+    if (ls > 0) {
+      if (t_abs(da) <= thresh) break;
+      if (da < T(0)) lo = alpha; else hi = alpha;
+    }
+    T an = alpha - da / ha;                         // Newton step on phi' (first from alpha = 1)
     if (!(an > lo && an < hi)) an = T(0.5) * (lo + hi);
     if (hi - lo <= T(4) * eps_of<T>() * hi) { alpha = lo > T(0) ? lo : an; break; }
-    alpha = an;
+    alpha = (ls == 7 && lo > T(0)) ? lo : an;      // evaluation budget spent: keep a point with phi' <= 0
   }
+  const T back = T(1) - alpha;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) u[i] += alpha * d[i];
-  return false;
+  for (int i = 0; i < 6; ++i) u[i] -= back * d[i];
+  d0 = T(0);
 }
 
-// Forces f = Pi(-(D_mu J u + q)/eps) at u (sappy order).
-template <typename T>
-CN_HD void cube_forces(const CubeParams<T>& P, const CubeProblem<T>& S, const T* u, T* f) {
-  T g[6], res2, scale2;
-  cube_eval<T, false>(P, S, u, g, (T*)nullptr, f, res2, scale2);
-}
-
-// Newton solve from u (in: start point, out: optimum).  Returns iterations; f = forces at u.
-template <typename T>
-CN_HD int cube_solve(const CubeParams<T>& P, const CubeProblem<T>& S, const SolverCfg<T>& cfg, T* u, T* f) {
+// Newton solve from u (in: start point, out: optimum).  Returns iterations.
+template <typename T, int UNR>
+CN_HD int cube_solve(const CubeParams<T>& P, const CubeProb<T>& S, const SolverCfg<T>& cfg, T* u) {
   int it = 0;
-  if (!cube_trivially_solved(S)) {
-    T prev = T(-1);
-    while (!cube_newton_unit(P, S, cfg, u, prev, it)) {}
+  if (!cube_trivially_solved<T, UNR>(S)) {
+    T d[6], d0 = T(0), best = T(-1);
+    while (true) {
+      const int st = cube_newton_step<T, UNR>(P, S, cfg, u, d, d0, best, it);
+      if (st == NEWTON_DONE) break;
+      if (st == NEWTON_LINESEARCH) cube_line_search<T, UNR>(P, S, cfg, u, d, d0);
+    }
   }
-  cube_forces(P, S, u, f);
-  return it;
+  return it & 0xffff;
 }
 
 // ---------------------------------------------------------------------------
@@ -373,42 +410,51 @@ CN_HD int cube_solve(const CubeParams<T>& P, const CubeProblem<T>& S, const Solv
 // the envelope theorem (:172-175), the parameter gradient in the same pass.
 // ---------------------------------------------------------------------------
 template <typename T> struct CubeLossAux {
+  T R[9];       // world <- body rotation at q+
   T dv[6];      // v+ - (v + dt a), state coordinates [body w ; world v]   (:156)
   T acc[6];     // contact-free acceleration, state coordinates
   T vp[6];      // v+, state coordinates
-  T phi[4];
+  T pos_z;
   T konst;      // 1/2 dv^T M dv + sum max(-phi,0)^2   (:163-170)
+  uint32_t sel; // selected corners (sign bits)
 };
 
-template <typename T>
-CN_HD void cube_loss_prologue(const CubeParams<T>& P, const T* x, const T* xp, CubeProblem<T>& S,
+template <typename T, int UNR>
+CN_HD void cube_loss_prologue(const CubeParams<T>& P, const T* x, const T* xp, const CubeProb<T>& S,
                               CubeLossAux<T>& A) {
-  cube_geometry(P, xp, xp[6], S, A.phi);
+  cube_geometry<T, UNR>(P, xp, A.R, A.sel, S);
+  A.pos_z = xp[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) A.vp[i] = xp[7 + i];
-  cube_free_accel(P, S.R, A.vp, A.acc, A.acc + 3);
+  cube_free_accel(P, A.R, A.vp, A.acc, A.acc + 3);
+#pragma unroll
   for (int i = 0; i < 6; ++i) A.dv[i] = A.vp[i] - (x[7 + i] + P.dt * A.acc[i]);
   // world twists
   T dvW[6], vW[6];
-  rot3(S.R, A.dv, dvW); rot3(S.R, A.vp, vW);
+  rot3(A.R, A.dv, dvW); rot3(A.R, A.vp, vW);
+#pragma unroll
   for (int i = 0; i < 3; ++i) { dvW[3 + i] = A.dv[3 + i]; vW[3 + i] = A.vp[3 + i]; }
   T pen = T(0);
-#pragma unroll
+#pragma unroll UNR
   for (int c = 0; c < CUBE_NC; ++c) {
-    const T* rho = S.rho + 3 * c;
+    const T rho[3] = {S.rho(3 * c), S.rho(3 * c + 1), S.rho(3 * c + 2)};
     T ed[3], ev[3];
     cross3(dvW, rho, ed); cross3(vW, rho, ev);
+#pragma unroll
     for (int i = 0; i < 3; ++i) { ed[i] += dvW[3 + i]; ev[i] += vW[3 + i]; }
     const T sx = P.mu * ev[0], sy = P.mu * ev[1];
     const T speed = t_sqrt(sx * sx + sy * sy);
-    S.q[3 * c] = -P.mu * ed[0] + P.dt * sx;                       // :158-161
-    S.q[3 * c + 1] = -P.mu * ed[1] + P.dt * sy;
-    S.q[3 * c + 2] = -ed[2] + t_abs(A.phi[c]) + P.dt * speed;
-    const T pneg = t_max(-A.phi[c], T(0));
+    const T phic = rho[2] + A.pos_z;
+    S.q(3 * c) = -P.mu * ed[0] + P.dt * sx;                       // :158-161
+    S.q(3 * c + 1) = -P.mu * ed[1] + P.dt * sy;
+    S.q(3 * c + 2) = -ed[2] + t_abs(phic) + P.dt * speed;
+    const T pneg = t_max(-phic, T(0));
     pen += pneg * pneg;
   }
   T Mdv[6];
   cube_mass_mul(P, S, dvW, Mdv);
   T e = T(0);
+#pragma unroll
   for (int i = 0; i < 6; ++i) e += dvW[i] * Mdv[i];
   A.konst = T(0.5) * e + pen;
 }
@@ -418,45 +464,43 @@ template <typename T> CN_HD void vex3(const T* X, T* o) {
   o[0] = X[7] - X[5]; o[1] = X[2] - X[6]; o[2] = X[3] - X[1];
 }
 
-// Loss value and (if grad != nullptr) += d loss / d [inertia(10), mu, half(3)].
-// f: solved forces, sappy order.  force_out (nullable): reference order [n(4); (tx,ty)(4)].
-template <typename T>
-CN_HD T cube_loss_epilogue(const CubeParams<T>& P, const CubeProblem<T>& S, const CubeLossAux<T>& A,
-                           const T* f_in, T* grad, T* force_out) {
-  T f[12];
-  bool bad = false;
-  for (int i = 0; i < 12; ++i) {
-    f[i] = f_in[i];
-    bad = bad || !(t_abs(f[i]) <= T(1e3));     // also catches NaN / Inf   (:186-189)
-  }
-  if (bad) {
-    if (force_out) for (int i = 0; i < 12; ++i) force_out[i] = T(0);
-    return T(0);                               // force := 0, constant := 0 (:191-192) => loss 0, grad 0
-  }
-  if (force_out) {
-    for (int c = 0; c < 4; ++c) {
-      force_out[c] = f[3 * c + 2];
-      force_out[4 + 2 * c] = f[3 * c];
-      force_out[4 + 2 * c + 1] = f[3 * c + 1];
-    }
-  }
-  const T* R = S.R;
-  // z = J^T f in world twist, then state coordinates
+// Loss value at the optimum u and (if grad != nullptr) += d loss / d [inertia(10), mu, half(3)].
+// force_out (nullable): reference order [n(4); (tx,ty)(4)].
+template <typename T, int UNR>
+CN_HD T cube_loss_epilogue(const CubeParams<T>& P, const CubeProb<T>& S, const CubeLossAux<T>& A, const T* u,
+                           T* grad, T* force_out) {
+  const T* R = A.R;
+  // pass 1: forces f_c = Pi(-(D_mu J_c u + q_c)/eps), z = J^T f (world twist), q.f, f.f, validity
   T zW[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-  T qf = T(0), ff = T(0);
-#pragma unroll
+  T qf = T(0), ff = T(0), fmax = T(0);
+#pragma unroll UNR
   for (int c = 0; c < CUBE_NC; ++c) {
-    const T ft[3] = {P.mu * f[3 * c], P.mu * f[3 * c + 1], f[3 * c + 2]};
+    T rho[3], r[3], f[3];
+    cube_contact_residual(P, S, c, u, rho, r);
+    cone_eval<T, false>(r, P.inv_eps, P.mu, f, (T*)nullptr);
+    const T ft[3] = {P.mu * f[0], P.mu * f[1], f[2]};
     T tq[3];
-    cross3(S.rho + 3 * c, ft, tq);
-    for (int i = 0; i < 3; ++i) { zW[i] += tq[i]; zW[3 + i] += ft[i]; }
-    for (int i = 0; i < 3; ++i) { qf += S.q[3 * c + i] * f[3 * c + i]; ff += f[3 * c + i] * f[3 * c + i]; }
+    cross3(rho, ft, tq);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      zW[i] += tq[i]; zW[3 + i] += ft[i];
+      qf += S.q(3 * c + i) * f[i]; ff += f[i] * f[i];
+      const T af = t_abs(f[i]);
+      fmax = (af > fmax || af != af) ? af : fmax;     // NaN-propagating max
+    }
+    if (force_out) { force_out[c] = f[2]; force_out[4 + 2 * c] = f[0]; force_out[4 + 2 * c + 1] = f[1]; }
+  }
+  if (!(fmax <= T(1e3))) {                 // |f| > 1e3, NaN or Inf: force := 0, constant := 0 (:186-192)
+    if (force_out) for (int i = 0; i < 12; ++i) force_out[i] = T(0);
+    return T(0);
   }
   T z[6], y[6];
   rot3t(R, zW, z);
+#pragma unroll
   for (int i = 0; i < 3; ++i) z[3 + i] = zW[3 + i];
   cube_minv(P, R, z, z + 3, y, y + 3);
   T zy = T(0);
+#pragma unroll
   for (int i = 0; i < 6; ++i) zy += z[i] * y[i];
   const T loss = T(0.5) * zy + T(0.5) * P.eps * ff + qf + A.konst;   // :194-195
   if (!grad) return loss;
@@ -464,38 +508,46 @@ CN_HD T cube_loss_epilogue(const CubeParams<T>& P, const CubeProblem<T>& S, cons
   // ---- envelope backward (forces fixed) ----
   const T* dv = A.dv; const T* a = A.acc; const T* w = A.vp;   // w = body angular velocity (first 3)
   T lam[6], b[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) { b[i] = y[i] - dv[i]; lam[i] = P.dt * b[i]; }   // lam = -dt (dv - y)
   // Mbar = -1/2 y y^T + 1/2 dv dv^T - lam a^T
   T Kww[9], N[9], trvv = T(0);
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) {
       Kww[3 * i + j] = T(0.5) * (dv[i] * dv[j] - y[i] * y[j]) - lam[i] * a[j];
       N[3 * i + j] = (dv[i] * dv[3 + j] - y[i] * y[3 + j]) - lam[i] * a[3 + j] - lam[3 + j] * a[i];
     }
+#pragma unroll
   for (int i = 0; i < 3; ++i) trvv += T(0.5) * (dv[3 + i] * dv[3 + i] - y[3 + i] * y[3 + i]) - lam[3 + i] * a[3 + i];
   // F-term into the I_o adjoint: (w x lam_w) w^T
   T wxl[3];
   cross3(w, lam, wxl);
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) Kww[3 * i + j] += wxl[i] * w[j];
   // I_sym
   grad[4] += Kww[0]; grad[5] += Kww[4]; grad[6] += Kww[8];
   grad[7] += Kww[1] + Kww[3]; grad[8] += Kww[2] + Kww[6]; grad[9] += Kww[5] + Kww[7];
-  // helpers
   const T* c = P.c;
   const T trK = Kww[0] + Kww[4] + Kww[8];
   T Kc[3], Ktc[3];
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
     Kc[i] = Kww[3 * i] * c[0] + Kww[3 * i + 1] * c[1] + Kww[3 * i + 2] * c[2];
     Ktc[i] = Kww[i] * c[0] + Kww[3 + i] * c[1] + Kww[6 + i] * c[2];
   }
   const T cc = dot3(c, c);
   T NR[9];
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) NR[3 * i + j] = N[3 * i] * R[j] + N[3 * i + 1] * R[3 + j] + N[3 * i + 2] * R[6 + j];
   T vNR[3];
   vex3(NR, vNR);
-  T gB[3] = {-P.grav * R[6], -P.grav * R[7], -P.grav * R[8]};
+  const T gB[3] = {-P.grav * R[6], -P.grav * R[7], -P.grav * R[8]};
   T ell[3];
   rot3t(R, lam + 3, ell);
   T cxg[3], wc[3], wwc[3], wl[3], wwl[3], gxl[3];
@@ -503,22 +555,24 @@ CN_HD T cube_loss_epilogue(const CubeParams<T>& P, const CubeProblem<T>& S, cons
   cross3(w, c, wc); cross3(w, wc, wwc);
   cross3(w, ell, wl); cross3(w, wl, wwl);
   cross3(gB, lam, gxl);
-  // mass
   grad[0] += cc * trK - dot3(c, Kc) + dot3(c, vNR) + trvv + dot3(lam, cxg) - dot3(ell, wwc) - P.grav * lam[5];
-  // com
+#pragma unroll
   for (int i = 0; i < 3; ++i)
     grad[1 + i] += P.m * (T(2) * trK * c[i] - Kc[i] - Ktc[i] + vNR[i] + gxl[i] - wwl[i]);
-  // contacts: mu and half lengths
+  // pass 2: contacts -> mu and half lengths (forces recomputed: cheaper than parking them)
   T bW[3], wW[3];
   rot3(R, b, bW); rot3(R, w, wW);
-  T gmu = T(0), gh[3] = {T(0), T(0), T(0)};
-#pragma unroll
+  T gmu = T(0), gh0 = T(0), gh1 = T(0), gh2 = T(0);
+#pragma unroll UNR
   for (int cidx = 0; cidx < CUBE_NC; ++cidx) {
-    const T* rho = S.rho + 3 * cidx;
+    T rho[3], r[3], f[3];
+    cube_contact_residual(P, S, cidx, u, rho, r);
+    cone_eval<T, false>(r, P.inv_eps, P.mu, f, (T*)nullptr);
     T eb[3], ev[3];
     cross3(bW, rho, eb); cross3(wW, rho, ev);
+#pragma unroll
     for (int i = 0; i < 3; ++i) { eb[i] += b[3 + i]; ev[i] += A.vp[3 + i]; }
-    const T ftx = f[3 * cidx], fty = f[3 * cidx + 1], fn = f[3 * cidx + 2];
+    const T ftx = f[0], fty = f[1], fn = f[2];
     const T sx = P.mu * ev[0], sy = P.mu * ev[1];
     const T speed = t_sqrt(sx * sx + sy * sy);
     const T ux = speed > T(0) ? sx / speed : T(0), uy = speed > T(0) ? sy / speed : T(0);
@@ -529,26 +583,29 @@ CN_HD T cube_loss_epilogue(const CubeParams<T>& P, const CubeProblem<T>& S, cons
     T ftB[3], gtB[3], p1[3], p2[3];
     rot3t(R, ft, ftB); rot3t(R, gt, gtB);
     cross3(ftB, b, p1); cross3(gtB, w, p2);
-    const T phic = A.phi[cidx];
+    const T phic = rho[2] + A.pos_z;
     const T phibar = (phic > T(0) ? fn : (phic < T(0) ? -fn : T(0))) - T(2) * t_max(-phic, T(0));
-    for (int k = 0; k < 3; ++k) gh[k] += sgn_bit<T>(S.sel, cidx, k) * (p1[k] + p2[k] + phibar * R[6 + k]);
+    gh0 += sgn_bit<T>(A.sel, cidx, 0) * (p1[0] + p2[0] + phibar * R[6]);
+    gh1 += sgn_bit<T>(A.sel, cidx, 1) * (p1[1] + p2[1] + phibar * R[7]);
+    gh2 += sgn_bit<T>(A.sel, cidx, 2) * (p1[2] + p2[2] + phibar * R[8]);
   }
   grad[10] += gmu;
-  for (int k = 0; k < 3; ++k) grad[11 + k] += gh[k];
+  grad[11] += gh0; grad[12] += gh1; grad[13] += gh2;
   return loss;
 }
 
-// Whole per-sample loss path (the simple, one-thread-per-sample composition).
+// Whole per-sample loss path (the simple, one-thread-per-sample composition; registers).
 template <typename T>
 CN_HD T cube_loss_sample(const CubeParams<T>& P, const SolverCfg<T>& cfg, const T* x, const T* xp, T* grad,
                          T* force_out, int* iters_out) {
-  CubeProblem<T> S;
+  T store[CUBE_PROB_FIELDS];
+  const CubeProb<T> S{store, 1};
   CubeLossAux<T> A;
-  cube_loss_prologue(P, x, xp, S, A);
-  T u[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, f[12];
-  const int it = cube_solve(P, S, cfg, u, f);
+  cube_loss_prologue<T, 4>(P, x, xp, S, A);
+  T u[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  const int it = cube_solve<T, 4>(P, S, cfg, u);
   if (iters_out) *iters_out = it;
-  return cube_loss_epilogue(P, S, A, f, grad, force_out);
+  return cube_loss_epilogue<T, 4>(P, S, A, u, grad, force_out);
 }
 
 // ---------------------------------------------------------------------------
@@ -556,46 +613,54 @@ CN_HD T cube_loss_sample(const CubeParams<T>& P, const SolverCfg<T>& cfg, const 
 // VelocityIntegrator.step (integrator.py:153-162) + FloatingBaseSpace.exponential
 // (state_space.py:466-486, quaternion.py:89-104, 276-309).  No quaternion renormalisation.
 // ---------------------------------------------------------------------------
-template <typename T>
-CN_HD int cube_step_sample(const CubeParams<T>& P, const SolverCfg<T>& cfg, const T* x, T* xn, T* force_out) {
-  CubeProblem<T> S;
-  T phi[4], acc[6], vm[6], vmW[6];
-  cube_geometry(P, x, x[6], S, phi);
-  cube_free_accel(P, S.R, x + 7, acc, acc + 3);
-  for (int i = 0; i < 6; ++i) vm[i] = x[7 + i] + P.dt * acc[i];            // :285
-  rot3(S.R, vm, vmW);
-  for (int i = 0; i < 3; ++i) vmW[3 + i] = vm[3 + i];
+template <typename T> struct CubeStepAux {
+  T R[9];
+  T vm[6];     // v + dt a  (state coordinates)   (:285)
+  uint32_t sel;
+};
+
+// builds the step QP at (q, v): q_c = D_mu J_c v_minus + [0, 0, phi_c / dt]   (:286)
+template <typename T, int UNR>
+CN_HD void cube_step_prologue(const CubeParams<T>& P, const T* x, const CubeProb<T>& S, CubeStepAux<T>& A) {
+  T acc[6], vmW[6];
+  cube_geometry<T, UNR>(P, x, A.R, A.sel, S);
+  cube_free_accel(P, A.R, x + 7, acc, acc + 3);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) A.vm[i] = x[7 + i] + P.dt * acc[i];
+  rot3(A.R, A.vm, vmW);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) vmW[3 + i] = A.vm[3 + i];
   const T inv_dt = T(1) / P.dt;
-#pragma unroll
+#pragma unroll UNR
   for (int c = 0; c < CUBE_NC; ++c) {
+    const T rho[3] = {S.rho(3 * c), S.rho(3 * c + 1), S.rho(3 * c + 2)};
     T e[3];
-    cross3(vmW, S.rho + 3 * c, e);
-    S.q[3 * c] = P.mu * (e[0] + vmW[3]);                                   // :286
-    S.q[3 * c + 1] = P.mu * (e[1] + vmW[4]);
-    S.q[3 * c + 2] = (e[2] + vmW[5]) + phi[c] * inv_dt;
+    cross3(vmW, rho, e);
+    S.q(3 * c) = P.mu * (e[0] + vmW[3]);
+    S.q(3 * c + 1) = P.mu * (e[1] + vmW[4]);
+    S.q(3 * c + 2) = (e[2] + vmW[5]) + (rho[2] + x[6]) * inv_dt;
   }
-  T u[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, f[12];
-  const int it = cube_solve(P, S, cfg, u, f);
-  if (force_out)
-    for (int c = 0; c < 4; ++c) {
-      force_out[c] = f[3 * c + 2]; force_out[4 + 2 * c] = f[3 * c]; force_out[4 + 2 * c + 1] = f[3 * c + 1];
+}
+
+// x_next from the solved twist u.  The reference forms v+ = v- + M^-1 J^T f (:303-304); at the
+// optimum M u = J^T f, so v+ = v- + u, which is used here because u is the better-conditioned
+// quantity (f = Pi(-(J u + q)/eps) amplifies rounding in u by 1/eps).  q+ = q (+) v+ dt.
+template <typename T, int UNR>
+CN_HD void cube_step_epilogue(const CubeParams<T>& P, const CubeProb<T>& S, const CubeStepAux<T>& A, const T* x,
+                              const T* u, T* xn, T* force_out) {
+  if (force_out) {
+#pragma unroll UNR
+    for (int c = 0; c < CUBE_NC; ++c) {
+      T rho[3], r[3], f[3];
+      cube_contact_residual(P, S, c, u, rho, r);
+      cone_eval<T, false>(r, P.inv_eps, P.mu, f, (T*)nullptr);
+      force_out[c] = f[2]; force_out[4 + 2 * c] = f[0]; force_out[4 + 2 * c + 1] = f[1];
     }
-  // v+ = v- + M^-1 J^T f = v- + u   (u is exactly M^-1 J^T f at the optimum; use the
-  // force form so the result is a function of f as in the reference, :303-304)
-  T zW[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-#pragma unroll
-  for (int c = 0; c < CUBE_NC; ++c) {
-    const T ft[3] = {P.mu * f[3 * c], P.mu * f[3 * c + 1], f[3 * c + 2]};
-    T tq[3];
-    cross3(S.rho + 3 * c, ft, tq);
-    for (int i = 0; i < 3; ++i) { zW[i] += tq[i]; zW[3 + i] += ft[i]; }
   }
-  T z[6], y[6], vn[6];
-  rot3t(S.R, zW, z);
-  for (int i = 0; i < 3; ++i) z[3 + i] = zW[3 + i];
-  cube_minv(P, S.R, z, z + 3, y, y + 3);
-  for (int i = 0; i < 6; ++i) vn[i] = vm[i] + y[i];
-  // q+ = q (+) v+ dt
+  T uB[3], vn[6];
+  rot3t(A.R, u, uB);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { vn[i] = A.vm[i] + uB[i]; vn[3 + i] = A.vm[3 + i] + u[3 + i]; }
   const T rx = vn[0] * P.dt, ry = vn[1] * P.dt, rz = vn[2] * P.dt;
   const T ang = t_sqrt(rx * rx + ry * ry + rz * rz);
   const T half = T(0.5) * ang;
@@ -607,8 +672,21 @@ CN_HD int cube_step_sample(const CubeParams<T>& P, const SolverCfg<T>& cfg, cons
   xn[1] = qw * dx + dw * qx + (qy * dz - qz * dy);
   xn[2] = qw * dy + dw * qy + (qz * dx - qx * dz);
   xn[3] = qw * dz + dw * qz + (qx * dy - qy * dx);
+#pragma unroll
   for (int i = 0; i < 3; ++i) xn[4 + i] = x[4 + i] + vn[3 + i] * P.dt;
+#pragma unroll
   for (int i = 0; i < 6; ++i) xn[7 + i] = vn[i];
+}
+
+template <typename T>
+CN_HD int cube_step_sample(const CubeParams<T>& P, const SolverCfg<T>& cfg, const T* x, T* xn, T* force_out) {
+  T store[CUBE_PROB_FIELDS];
+  const CubeProb<T> S{store, 1};
+  CubeStepAux<T> A;
+  cube_step_prologue<T, 4>(P, x, S, A);
+  T u[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  const int it = cube_solve<T, 4>(P, S, cfg, u);
+  cube_step_epilogue<T, 4>(P, S, A, x, u, xn, force_out);
   return it;
 }
 

@@ -89,50 +89,34 @@ cube_loss_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __r
 // The Newton solve needs 0 .. ~30 iterations depending on the sample (most free-flight
 // samples need none), so one-sample-per-thread leaves ~80% of the lanes idle (ncu:
 // 5.8 active threads per instruction, profiles/).  Here each WARP owns a pool of kWfSlots
-// sample slots in shared memory and three ring-buffer queues (free / active / done), and
-// runs warp-uniform phases, each processing up to 32 slots at full width:
-//   P  prologue : load 32 new samples, build their QPs, park the state in slots
-//   N  newton   : one Newton unit for 32 unconverged slots
-//   E  epilogue : loss + envelope backward for 32 converged slots
-// The phase choice depends only on the (warp-uniform) queue counts, so there is no
-// divergence between phases; all arithmetic is the same per-sample code as the simple
-// kernel, so per-sample results are bitwise identical to it.  Samples are assigned to
+// sample slots in shared memory and three ring-buffer queues, and runs warp-uniform phases,
+// each processing up to 32 slots at full width:
+//   N   one Newton step for 32 slots whose sample is not yet converged ("active" queue)
+//   L   the derivative line search for 32 slots whose full Newton step overshot (~14% of the
+//       steps; kept out of N so that N has no data-dependent loop)
+//   PE  for 32 slots of the "done" queue: a slot holding a finished sample is finalised
+//       (problem rebuilt from x, x+ -> loss + envelope backward -> outputs) and becomes
+//       empty; an empty slot receives the next input sample (problem built and parked in
+//       the slot; if it is already optimal at u = 0 -- free flight -- it is finalised on the
+//       spot).  One code instance of the prologue serves both cases.
+// Slots are conserved (active + linesearch + done = kWfSlots until the input runs out), so the
+// fullest queue always holds >= 22 entries and in practice ~32.  The phase choice
+// depends only on warp-uniform counters; there is no divergence between phases and the
+// per-sample arithmetic is the same code as the simple kernel.  Samples are assigned to
 // warps statically (contiguous ranges), which keeps the gradient reduction deterministic.
+// The hot loop is kept small (rolled per-contact loops over the shared-memory slot) because
+// warps of one SM sit in different phases and share the instruction cache.
 // ---------------------------------------------------------------------------
 constexpr int kWfSlots = 64;
 constexpr int kWfWarps = 4;
-constexpr int kWfFields = 40;   // IW 6 | mcW 3 | rho 12 | q 12 | u 6 | prev_res2 1
+constexpr int kWfFields = 47;   // IW 6 | mcW 3 | rho 12 | q 12 | u 6 | prev_res2 1 | d 6 | d0 1
 
 template <typename T> struct WfWarpPool {
   T field[kWfFields][kWfSlots];
-  int32_t sample[kWfSlots];
+  int32_t sample[kWfSlots];     // offset of the slot's sample in the warp's range; -1 = empty
   int32_t iters[kWfSlots];
-  uint8_t q_free[kWfSlots], q_act[kWfSlots], q_done[kWfSlots];
+  uint8_t q_act[kWfSlots], q_done[kWfSlots], q_ls[kWfSlots];
 };
-
-template <typename T>
-__device__ __forceinline__ void wf_store_problem(WfWarpPool<T>* pool, int slot, const cn::CubeProblem<T>& S) {
-#pragma unroll
-  for (int i = 0; i < 6; ++i) pool->field[i][slot] = S.IW[i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) pool->field[6 + i][slot] = S.mcW[i];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) pool->field[9 + i][slot] = S.rho[i];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) pool->field[21 + i][slot] = S.q[i];
-}
-
-template <typename T>
-__device__ __forceinline__ void wf_load_problem(const WfWarpPool<T>* pool, int slot, cn::CubeProblem<T>& S) {
-#pragma unroll
-  for (int i = 0; i < 6; ++i) S.IW[i] = pool->field[i][slot];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) S.mcW[i] = pool->field[6 + i][slot];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) S.rho[i] = pool->field[9 + i][slot];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) S.q[i] = pool->field[21 + i][slot];
-}
 
 template <typename T>
 __global__ void __launch_bounds__(kWfWarps * 32)
@@ -160,119 +144,137 @@ cube_loss_wf_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* 
   const int64_t hi = lo + base + (gw < rem ? 1 : 0);
   int64_t next = lo;
 
-  for (int s = lane; s < kWfSlots; s += 32) pool->q_free[s] = (uint8_t)s;
-  int n_free = kWfSlots, n_act = 0, n_done = 0, h_free = 0, h_act = 0, h_done = 0;
+  for (int s = lane; s < kWfSlots; s += 32) { pool->q_done[s] = (uint8_t)s; pool->sample[s] = -1; }
+  int n_act = 0, n_done = kWfSlots, n_ls = 0, h_act = 0, h_done = 0, h_ls = 0;
   __syncwarp();
 
   while (true) {
-    const int64_t left = hi - next;
-    int phase;   // 0 = P, 1 = N, 2 = E
-    if (n_done >= 32 || (left == 0 && n_act == 0 && n_done > 0)) phase = 2;
-    else if (left > 0 && n_act < 32 && n_free >= (left < 32 ? (int)left : 32)) phase = 0;
-    else if (n_act > 0) phase = 1;
-    else if (n_done > 0) phase = 2;
+    int phase;   // 0 = PE, 1 = N, 2 = L
+    if (n_done >= 32) phase = 0;
+    else if (n_act >= 32) phase = 1;
+    else if (n_ls >= 32) phase = 2;
+    else if (n_act > 0 && n_act >= n_ls && n_act >= n_done) phase = 1;
+    else if (n_ls > 0 && n_ls >= n_done) phase = 2;
+    else if (n_done > 0) phase = 0;
     else break;
 
-    if (phase == 0) {
-      const int k = left < 32 ? (int)left : 32;
+    if (phase == 2) {
+      const int k = n_ls < 32 ? n_ls : 32;
       const bool on = lane < k;
-      bool trivial = false;
       int slot = 0;
       if (on) {
-        slot = pool->q_free[(h_free + lane) % kWfSlots];
-        const int64_t b = next + lane;
-        T xs[13], xps[13];
+        slot = pool->q_ls[(h_ls + lane) % kWfSlots];
+        const cn::CubeProb<T> S{&pool->field[0][slot], kWfSlots};
+        T u[6], d[6];
 #pragma unroll
-        for (int i = 0; i < 13; ++i) { xs[i] = x[b * 13 + i]; xps[i] = xp[b * 13 + i]; }
-        cn::CubeProblem<T> S;
-        cn::CubeLossAux<T> A;
-        cn::cube_loss_prologue(P, xs, xps, S, A);
-        trivial = cn::cube_trivially_solved(S);
-        wf_store_problem(pool, slot, S);
+        for (int i = 0; i < 6; ++i) { u[i] = pool->field[33 + i][slot]; d[i] = pool->field[40 + i][slot]; }
+        T d0 = pool->field[46][slot];
+        cn::cube_line_search<T, 1>(P, S, cfg, u, d, d0);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = T(0);
-        pool->field[39][slot] = T(-1);
-        pool->sample[slot] = (int32_t)(b - lo);   // offset inside the warp's range
-        pool->iters[slot] = 0;
+        for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = u[i];
+        pool->field[46][slot] = d0;
+        pool->q_act[(h_act + n_act + lane) % kWfSlots] = (uint8_t)slot;
       }
-      const unsigned m_done = __ballot_sync(0xffffffffu, on && trivial);
-      const unsigned m_act = __ballot_sync(0xffffffffu, on && !trivial);
-      if (on) {
-        if (trivial) pool->q_done[(h_done + n_done + __popc(m_done & lt_mask)) % kWfSlots] = (uint8_t)slot;
-        else pool->q_act[(h_act + n_act + __popc(m_act & lt_mask)) % kWfSlots] = (uint8_t)slot;
-      }
-      n_done += __popc(m_done); n_act += __popc(m_act);
-      h_free = (h_free + k) % kWfSlots; n_free -= k; next += k;
+      h_ls = (h_ls + k) % kWfSlots; n_ls -= k; n_act += k;
     } else if (phase == 1) {
       const int k = n_act < 32 ? n_act : 32;
       const bool on = lane < k;
-      bool fin = false;
+      int st = -1;
       int slot = 0;
       if (on) {
         slot = pool->q_act[(h_act + lane) % kWfSlots];
-        cn::CubeProblem<T> S;
-        wf_load_problem(pool, slot, S);
-        T u[6];
+        const cn::CubeProb<T> S{&pool->field[0][slot], kWfSlots};
+        T u[6], d[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) u[i] = pool->field[33 + i][slot];
-        T prev = pool->field[39][slot];
+        for (int i = 0; i < 6; ++i) { u[i] = pool->field[33 + i][slot]; d[i] = pool->field[40 + i][slot]; }
+        T best = pool->field[39][slot], d0 = pool->field[46][slot];
         int it = pool->iters[slot];
-        fin = cn::cube_newton_unit(P, S, cfg, u, prev, it);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = u[i];
-        pool->field[39][slot] = prev;
+        st = cn::cube_newton_step<T, 1>(P, S, cfg, u, d, d0, best, it);
         pool->iters[slot] = it;
+        pool->field[39][slot] = best;
+        if (st == cn::NEWTON_CONTINUE) {       // (LINESEARCH leaves u, d, d0 as they were)
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { pool->field[33 + i][slot] = u[i]; pool->field[40 + i][slot] = d[i]; }
+          pool->field[46][slot] = d0;
+        }
       }
-      __syncwarp();
-      const unsigned m_done = __ballot_sync(0xffffffffu, on && fin);
-      const unsigned m_act = __ballot_sync(0xffffffffu, on && !fin);
+      const unsigned m_done = __ballot_sync(0xffffffffu, st == cn::NEWTON_DONE);
+      const unsigned m_act = __ballot_sync(0xffffffffu, st == cn::NEWTON_CONTINUE);
+      const unsigned m_ls = __ballot_sync(0xffffffffu, st == cn::NEWTON_LINESEARCH);
       h_act = (h_act + k) % kWfSlots; n_act -= k;
-      if (on) {
-        if (fin) pool->q_done[(h_done + n_done + __popc(m_done & lt_mask)) % kWfSlots] = (uint8_t)slot;
-        else pool->q_act[(h_act + n_act + __popc(m_act & lt_mask)) % kWfSlots] = (uint8_t)slot;
-      }
-      n_done += __popc(m_done); n_act += __popc(m_act);
+      if (st == cn::NEWTON_DONE) pool->q_done[(h_done + n_done + __popc(m_done & lt_mask)) % kWfSlots] = (uint8_t)slot;
+      else if (st == cn::NEWTON_CONTINUE) pool->q_act[(h_act + n_act + __popc(m_act & lt_mask)) % kWfSlots] = (uint8_t)slot;
+      else if (st == cn::NEWTON_LINESEARCH) pool->q_ls[(h_ls + n_ls + __popc(m_ls & lt_mask)) % kWfSlots] = (uint8_t)slot;
+      n_done += __popc(m_done); n_act += __popc(m_act); n_ls += __popc(m_ls);
     } else {
       const int k = n_done < 32 ? n_done : 32;
       const bool on = lane < k;
-      int slot = 0;
-      if (on) {
-        slot = pool->q_done[(h_done + lane) % kWfSlots];
-        const int64_t b = lo + pool->sample[slot];
+      int slot = 0, old = -1;
+      if (on) { slot = pool->q_done[(h_done + lane) % kWfSlots]; old = pool->sample[slot]; }
+      // empty slots take the next input samples, in lane order
+      const unsigned m_empty = __ballot_sync(0xffffffffu, on && old < 0);
+      const int64_t left = hi - next;
+      const int n_empty = __popc(m_empty);
+      const int n_new = left < n_empty ? (int)left : n_empty;
+      const int my_rank = __popc(m_empty & lt_mask);
+      const bool fresh = on && old < 0 && my_rank < n_new;
+      const bool work = fresh || (on && old >= 0);
+      bool to_active = false;
+      if (work) {
+        const int64_t b = fresh ? next + my_rank : lo + old;
         T xs[13], xps[13];
 #pragma unroll
         for (int i = 0; i < 13; ++i) { xs[i] = x[b * 13 + i]; xps[i] = xp[b * 13 + i]; }
-        cn::CubeProblem<T> S;
+        const cn::CubeProb<T> S{&pool->field[0][slot], kWfSlots};
         cn::CubeLossAux<T> A;
-        cn::cube_loss_prologue(P, xs, xps, S, A);     // recomputed (cheap) instead of parked in shared memory
-        T u[6], f[12];
+        cn::cube_loss_prologue<T, 1>(P, xs, xps, S, A);      // (re)builds IW, mcW, rho, q in the slot
+        const bool finished = !fresh || cn::cube_trivially_solved<T, 1>(S);
+        if (finished) {
+          T u[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) u[i] = pool->field[33 + i][slot];
-        cn::cube_forces(P, S, u, f);
-        T gs[DPLL_CUBE_NPARAM];
+          for (int i = 0; i < 6; ++i) u[i] = fresh ? T(0) : pool->field[33 + i][slot];
+          T gs[DPLL_CUBE_NPARAM];
 #pragma unroll
-        for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
-        const T l = cn::cube_loss_epilogue(P, S, A, f, want_grad ? gs : (T*)nullptr,
-                                           force ? force + b * 12 : (T*)nullptr);
-        const T w = weight ? weight[b] : T(1);
+          for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
+          const T l = cn::cube_loss_epilogue<T, 1>(P, S, A, u, want_grad ? gs : (T*)nullptr,
+                                                   force ? force + b * 12 : (T*)nullptr);
+          const T w = weight ? weight[b] : T(1);
 #pragma unroll
-        for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] += w * gs[i];
-        if (loss) loss[b] = l;
-        acc[14] += l;
-        if (iters) iters[b] = pool->iters[slot];
+          for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] += w * gs[i];
+          if (loss) loss[b] = l;
+          acc[14] += l;
+          if (iters) iters[b] = fresh ? 0 : (pool->iters[slot] & 0xffff);
+          pool->sample[slot] = -1;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = T(0);
+          pool->field[39][slot] = T(-1);
+          pool->field[46][slot] = T(0);
+          pool->sample[slot] = (int32_t)(b - lo);
+          pool->iters[slot] = 0;
+          to_active = true;
+        }
       }
-      __syncwarp();
-      if (on) pool->q_free[(h_free + n_free + lane) % kWfSlots] = (uint8_t)slot;
-      n_free += k; h_done = (h_done + k) % kWfSlots; n_done -= k;
+      next += n_new;
+      const bool more = next < hi;                       // empty slots are only kept while input remains
+      const unsigned m_act = __ballot_sync(0xffffffffu, to_active);
+      const unsigned m_keep = __ballot_sync(0xffffffffu, on && !to_active && more);
+      h_done = (h_done + k) % kWfSlots; n_done -= k;
+      if (to_active) pool->q_act[(h_act + n_act + __popc(m_act & lt_mask)) % kWfSlots] = (uint8_t)slot;
+      else if (on && more) pool->q_done[(h_done + n_done + __popc(m_keep & lt_mask)) % kWfSlots] = (uint8_t)slot;
+      n_act += __popc(m_act); n_done += __popc(m_keep);
     }
     __syncwarp();
   }
 
   if (!partials) return;
   __shared__ T red[kWfWarps][kNAcc];
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < kNAcc; ++i) {
-    const T s = warp_sum(acc[i]);
+    T v = T(0);
+#pragma unroll
+    for (int j = 0; j < kNAcc; ++j) v = (j == i) ? acc[j] : v;
+    const T s = warp_sum(v);
     if (lane == 0) red[warp][i] = s;
   }
   __syncthreads();
