@@ -306,7 +306,8 @@ def main():
                    'mean_newton_iters': mean_iters},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h},
-        'gpu_launches': 2 * args.steps,
+        'gpu_launches': 6 * args.steps,   # per step: prepare + loss/backward + reduce/chain, and the same three
+                                          # (device-side skipped) launches issued by autograd's backward
         'roofline': {'bound': 'fp64_cuda_core' if dtype == torch.float64 else 'fp32_cuda_core',
                      'achieved': achieved_tflops, 'peak': peak_flops / 1e12, 'unit': 'TFLOP/s',
                      'frac': achieved_tflops / (peak_flops / 1e12), 'traffic': None,

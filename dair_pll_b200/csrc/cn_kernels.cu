@@ -9,6 +9,7 @@
 
 #include "../../include/dair_pll_b200.h"
 #include "cn_cube.cuh"
+#include "cn_params.cuh"
 
 namespace {
 
@@ -302,6 +303,64 @@ __global__ void reduce_partials_kernel(const T* __restrict__ partials, int nbloc
   }
 }
 
+// ---- leaf-level parameter preparation / chain rule (cube: theta 10, friction 2 [box, ground], length 3) ----
+constexpr int kNLeaf = 15;
+
+template <typename T>
+__global__ void cube_prep_kernel(const T* __restrict__ theta, const T* __restrict__ friction,
+                                 const T* __restrict__ length, T* __restrict__ params /* [inertia 10 | mu 1 | half 3] */,
+                                 const int32_t* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;
+  if (threadIdx.x == 0) {
+    T th[10], out[10];
+    for (int i = 0; i < 10; ++i) th[i] = theta[i];
+    cn::theta_to_inertia_vector<T>(th, out);
+    for (int i = 0; i < 10; ++i) params[i] = out[i];
+    const T a = cn::t_abs(friction[0]), b = cn::t_abs(friction[1]);
+    params[10] = T(2) * a * b / (a + b);
+    for (int i = 0; i < 3; ++i) params[11 + i] = cn::t_abs(length[i]);
+  }
+}
+
+// Sums the per-block partials (fixed order) and pushes the callable-level gradient through the
+// parameter preparation: grad_leaf = [d/d theta (10) | d/d friction (2) | d/d length (3)].
+template <typename T>
+__global__ void reduce_partials_leaf_kernel(const T* __restrict__ partials, int nblocks, const T* __restrict__ theta,
+                                            const T* __restrict__ friction, const T* __restrict__ length,
+                                            T* __restrict__ grad_leaf, T* __restrict__ loss_sum,
+                                            const int32_t* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;
+  __shared__ T g[kNAcc];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (w < kNAcc) {
+    T s = T(0);
+    for (int b = lane; b < nblocks; b += 32) s += partials[(int64_t)b * kNAcc + w];
+    s = warp_sum(s);
+    if (lane == 0) g[w] = s;
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < 10 && grad_leaf) {
+    cn::Dual<T> th[10], out[10];
+    for (int i = 0; i < 10; ++i) th[i] = cn::Dual<T>(theta[i], i == t ? T(1) : T(0));
+    cn::theta_to_inertia_vector<cn::Dual<T>>(th, out);
+    T s = T(0);
+    for (int i = 0; i < 10; ++i) s += g[i] * out[i].d;
+    grad_leaf[t] = s;
+  } else if (t == 10 && grad_leaf) {
+    const T fa = friction[0], fb = friction[1];
+    const T a = cn::t_abs(fa), b = cn::t_abs(fb), den = (a + b) * (a + b);
+    const T sa = fa > T(0) ? T(1) : (fa < T(0) ? T(-1) : T(0)), sb = fb > T(0) ? T(1) : (fb < T(0) ? T(-1) : T(0));
+    grad_leaf[10] = g[10] * (T(2) * b * b / den) * sa;
+    grad_leaf[11] = g[10] * (T(2) * a * a / den) * sb;
+  } else if (t >= 11 && t < 14 && grad_leaf) {
+    const T l = length[t - 11];
+    grad_leaf[12 + (t - 11)] = g[t] * (l > T(0) ? T(1) : (l < T(0) ? T(-1) : T(0)));
+  } else if (t == 14 && loss_sum) {
+    *loss_sum = g[14];
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kLossThreads)
 cube_rollout_kernel(const T* __restrict__ x0, const T* __restrict__ inertia, const T* __restrict__ mu,
@@ -344,15 +403,22 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int64_t iters) {
 
 template <typename T>
 int launch_cube_loss(int variant, const T* x, const T* xp, const T* weight, const T* inertia, const T* mu,
-                     const T* half, T dt, T eps, int64_t B, T* loss, T* force, int32_t* iters, T* grad, T* loss_sum,
+                     const T* half, const T* theta, const T* friction, const T* length, T dt, T eps, int64_t B, T* loss, T* force, int32_t* iters, T* grad, T* loss_sum,
                      const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
-  if (B < 0 || !inertia || !mu || !half) return DPLL_EINVAL;
+  const bool leaf = theta != nullptr;
+  if (B < 0 || (leaf ? (!friction || !length) : (!inertia || !mu || !half))) return DPLL_EINVAL;
   if (B > 0 && (!x || !xp)) return DPLL_EINVAL;
   const bool want_red = grad || loss_sum;
-  if (want_red && (!workspace || workspace_bytes < dpll_workspace_bytes())) return DPLL_EWORKSPACE;
+  if ((want_red || leaf) && (!workspace || workspace_bytes < dpll_workspace_bytes())) return DPLL_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DeviceInfo di = device_info();
   T* partials = want_red ? static_cast<T*>(workspace) : nullptr;
+  if (leaf) {
+    // callable-level parameters are produced on the device, behind the partials in the workspace
+    T* params = static_cast<T*>(workspace) + (size_t)kMaxBlocks * kNAcc;
+    cube_prep_kernel<T><<<1, 32, 0, st>>>(theta, friction, length, params, skip_flag);
+    inertia = params; mu = params + 10; half = params + 11;
+  }
   int blocks;
   if (variant == 0) {
     // wavefront kernel: persistent, one resident set of blocks
@@ -384,7 +450,9 @@ int launch_cube_loss(int variant, const T* x, const T* xp, const T* weight, cons
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (want_red) {
-    reduce_partials_kernel<T><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, grad, loss_sum, skip_flag);
+    if (leaf) reduce_partials_leaf_kernel<T><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, theta, friction, length, grad,
+                                                                     loss_sum, skip_flag);
+    else reduce_partials_kernel<T><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, grad, loss_sum, skip_flag);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
@@ -425,22 +493,44 @@ int dpll_set_loss_variant(int variant) {
 
 int dpll_version(void) { return 100; }
 
-size_t dpll_workspace_bytes(void) { return (size_t)kMaxBlocks * kNAcc * sizeof(double); }
+size_t dpll_workspace_bytes(void) { return ((size_t)kMaxBlocks * kNAcc + 16) * sizeof(double); }
 
 int dpll_cube_loss_f64(const double* x, const double* x_plus, const double* weight, const double* inertia,
                        const double* mu_pair, const double* half, double dt, double eps, int64_t B, double* loss,
                        double* force, int32_t* iters, double* grad, double* loss_sum, const int32_t* skip_flag,
                        void* workspace, size_t workspace_bytes, void* stream) {
-  return launch_cube_loss<double>(g_loss_variant, x, x_plus, weight, inertia, mu_pair, half, dt, eps, B, loss, force,
-                                  iters, grad, loss_sum, skip_flag, workspace, workspace_bytes, stream);
+  return launch_cube_loss<double>(g_loss_variant, x, x_plus, weight, inertia, mu_pair, half, nullptr, nullptr, nullptr,
+                                  dt, eps, B, loss, force, iters, grad, loss_sum, skip_flag, workspace,
+                                  workspace_bytes, stream);
+}
+
+int dpll_cube_loss_leaf_f64(const double* x, const double* x_plus, const double* weight, const double* theta,
+                            const double* friction, const double* length, double dt, double eps, int64_t B,
+                            double* loss, double* force, int32_t* iters, double* grad_leaf, double* loss_sum,
+                            const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!theta) return DPLL_EINVAL;
+  return launch_cube_loss<double>(g_loss_variant, x, x_plus, weight, nullptr, nullptr, nullptr, theta, friction, length,
+                                  dt, eps, B, loss, force, iters, grad_leaf, loss_sum, skip_flag, workspace,
+                                  workspace_bytes, stream);
 }
 
 int dpll_cube_loss_f32(const float* x, const float* x_plus, const float* weight, const float* inertia,
                        const float* mu_pair, const float* half, float dt, float eps, int64_t B, float* loss,
                        float* force, int32_t* iters, float* grad, float* loss_sum, const int32_t* skip_flag,
                        void* workspace, size_t workspace_bytes, void* stream) {
-  return launch_cube_loss<float>(g_loss_variant, x, x_plus, weight, inertia, mu_pair, half, dt, eps, B, loss, force,
-                                 iters, grad, loss_sum, skip_flag, workspace, workspace_bytes, stream);
+  return launch_cube_loss<float>(g_loss_variant, x, x_plus, weight, inertia, mu_pair, half, nullptr, nullptr, nullptr,
+                                 dt, eps, B, loss, force, iters, grad, loss_sum, skip_flag, workspace, workspace_bytes,
+                                 stream);
+}
+
+int dpll_cube_loss_leaf_f32(const float* x, const float* x_plus, const float* weight, const float* theta,
+                            const float* friction, const float* length, float dt, float eps, int64_t B, float* loss,
+                            float* force, int32_t* iters, float* grad_leaf, float* loss_sum, const int32_t* skip_flag,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (!theta) return DPLL_EINVAL;
+  return launch_cube_loss<float>(g_loss_variant, x, x_plus, weight, nullptr, nullptr, nullptr, theta, friction, length,
+                                 dt, eps, B, loss, force, iters, grad_leaf, loss_sum, skip_flag, workspace,
+                                 workspace_bytes, stream);
 }
 
 int dpll_cube_rollout_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,

@@ -72,9 +72,12 @@ class MultibodyLearnableSystem(System):
         assert x.shape[-1] == self.space.n_x and x_plus.shape == x.shape
         batch = x.shape[:-1]
         if self._kind() == 'cube':
-            inertia, mu, half = self._cube_params(x.dtype)
-            loss = ops.CubeContactNetsLoss.apply(self._flat(x), self._flat(x_plus), inertia, mu, half,
-                                                 float(self.dt), LOSS_EPS)
+            lt, ct = self.multibody_terms.lagrangian_terms, self.multibody_terms.contact_terms
+            # the learnable leaves go straight to the library (parameter preparation, multibody_terms.py:230-231,
+            # 466-471, geometry.py:394-397, and its chain rule run on the device)
+            loss = ops.CubeContactNetsLossLeaf.apply(
+                self._flat(x), self._flat(x_plus), lt.inertial_parameters.to(x.dtype), ct.friction_params.to(x.dtype),
+                ct.geometries[0].length_params.to(x.dtype), float(self.dt), LOSS_EPS)
         else:
             raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r} yet')
         return loss.reshape(batch)

@@ -126,6 +126,70 @@ class CubeContactNetsLoss(torch.autograd.Function):
         return (None, None, g[0:10].reshape(s_in), g[10:11].reshape(s_mu), g[11:14].reshape(s_h), None, None)
 
 
+def cube_loss_leaf_raw(x: Tensor, x_plus: Tensor, theta: Tensor, friction: Tensor, length: Tensor, dt: float,
+                       eps: float, weight: Optional[Tensor] = None, want_grad: bool = True, want_loss: bool = True,
+                       skip_flag: Optional[Tensor] = None, grad_out: Optional[Tensor] = None):
+    """Direct call of ``dpll_cube_loss_leaf_*``: parameters are the module's learnable leaves
+    (theta (1,10), friction_params (2,) [box, ground], length_params (1,3)).  Returns
+    (loss (B,) | None, grad_leaf (15,) | None, loss_sum (1,))."""
+    dtype = _check_inputs(x, x_plus, theta, friction, length)
+    x, x_plus = x.contiguous(), x_plus.contiguous()
+    theta, friction, length = theta.contiguous(), friction.contiguous(), length.contiguous()
+    if x.dim() != 2 or x.shape[1] != 13 or x_plus.shape != x.shape:
+        raise ValueError(f'expected (B,13) states, got {tuple(x.shape)} / {tuple(x_plus.shape)}')
+    if theta.numel() != 10 or friction.numel() != 2 or length.numel() != 3:
+        raise ValueError('cube leaves must be theta (10), friction_params (2), length_params (3)')
+    B = x.shape[0]
+    dev = x.device
+    loss = torch.empty(B, dtype=dtype, device=dev) if want_loss else None
+    grad = (grad_out if grad_out is not None else torch.empty(15, dtype=dtype, device=dev)) if want_grad else None
+    loss_sum = torch.empty(1, dtype=dtype, device=dev)
+    if weight is not None:
+        weight = weight.to(dtype).contiguous()
+    ws = _workspace(dev)
+    fn = getattr(_lib.load(), 'dpll_cube_loss_leaf_' + _SUFFIX[dtype])
+    with torch.cuda.device(dev):
+        rc = fn(_ptr(x), _ptr(x_plus), _ptr(weight), _ptr(theta), _ptr(friction), _ptr(length), dt, eps, B,
+                _ptr(loss), None, None, _ptr(grad), _ptr(loss_sum), _ptr(skip_flag), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, 'dpll_cube_loss_leaf')
+    return loss, grad, loss_sum
+
+
+class CubeContactNetsLossLeaf(torch.autograd.Function):
+    """ContactNets loss of the cube as a function of the module's learnable LEAVES: parameter
+    preparation and its chain rule run inside the CUDA library (``dpll_cube_loss_leaf_*``), so
+    forward + backward is three kernel launches and no PyTorch glue.  Same backward protocol as
+    :class:`CubeContactNetsLoss` (fused gradient from the forward launch; device-side skip flag)."""
+
+    @staticmethod
+    def forward(ctx, x, x_plus, theta, friction, length, dt, eps):
+        need = any(ctx.needs_input_grad[2:5])
+        loss, grad, _ = cube_loss_leaf_raw(x, x_plus, theta, friction, length, dt, eps, want_grad=need)
+        ctx.dt, ctx.eps = dt, eps
+        ctx.shapes = (theta.shape, friction.shape, length.shape)
+        if need:
+            ctx.save_for_backward(grad, x, x_plus, theta, friction, length)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        grad, x, x_plus, theta, friction, length = ctx.saved_tensors
+        if grad_loss.numel() == 0:
+            g = torch.zeros_like(grad)
+        elif grad_loss.dim() == 1 and grad_loss.stride(0) == 0:
+            g = grad * grad_loss[0]
+        else:
+            grad_loss = grad_loss.contiguous()
+            lo, hi = torch.aminmax(grad_loss)
+            uniform = lo == hi
+            gw = torch.zeros_like(grad)
+            cube_loss_leaf_raw(x, x_plus, theta, friction, length, ctx.dt, ctx.eps, weight=grad_loss, want_grad=True,
+                               want_loss=False, skip_flag=uniform.to(torch.int32), grad_out=gw)
+            g = torch.where(uniform, grad * lo, gw)
+        s_t, s_f, s_l = ctx.shapes
+        return (None, None, g[0:10].reshape(s_t), g[10:12].reshape(s_f), g[12:15].reshape(s_l), None, None)
+
+
 def cube_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, dt: float, steps: int,
                  eps: float = 1e-4, want_force: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
     """(B,13) -> trajectory (B, steps+1, 13) through ``dpll_cube_rollout_*`` (no autograd)."""

@@ -93,6 +93,28 @@ int dpll_cube_loss_f32(const float* x, const float* x_plus, const float* weight,
                        size_t workspace_bytes, void* stream);
 
 /*
+ * Same computation driven by the LEARNABLE LEAVES instead of the callable-level parameters, so a
+ * training step needs no PyTorch glue: the preparation
+ *   theta (1,10) -> [m, c, I_cm/m]   (inertia.py:205-234, 304-331, 376-382; multibody_terms.py:230-231)
+ *   friction_params (2) [box, ground] -> |.| -> 2 mu_a mu_b/(mu_a+mu_b)   (multibody_terms.py:321-324, 466-471)
+ *   length_params (1,3) -> |.|       (geometry.py:394-397)
+ * runs in a one-thread kernel, and the reduction kernel applies its chain rule:
+ *   grad_leaf : (15) = [d/d theta (10) | d/d friction_params (2) | d/d length_params (3)] of sum_b w_b loss_b.
+ * Three launches per call (prepare, loss+backward, reduce+chain).  Other arguments as above.
+ */
+int dpll_cube_loss_leaf_f64(const double* x, const double* x_plus, const double* weight,
+                            const double* theta, const double* friction, const double* length,
+                            double dt, double eps, int64_t B, double* loss, double* force,
+                            int32_t* iters, double* grad_leaf, double* loss_sum,
+                            const int32_t* skip_flag, void* workspace, size_t workspace_bytes,
+                            void* stream);
+int dpll_cube_loss_leaf_f32(const float* x, const float* x_plus, const float* weight,
+                            const float* theta, const float* friction, const float* length, float dt,
+                            float eps, int64_t B, float* loss, float* force, int32_t* iters,
+                            float* grad_leaf, float* loss_sum, const int32_t* skip_flag,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Learnable time stepping for the cube: `steps` applications of
  * VelocityIntegrator.step (dair_pll/integrator.py:153-162) around
  * MultibodyLearnableSystem.sim_step / forward_dynamics

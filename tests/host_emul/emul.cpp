@@ -1,6 +1,7 @@
 // Host build of the per-sample device math (dair_pll_b200/csrc/*.cuh) for debugging in a
 // container without a GPU.  TEST INFRASTRUCTURE ONLY: nothing in the package loads this.
 #include "../../dair_pll_b200/csrc/cn_cube.cuh"
+#include "../../dair_pll_b200/csrc/cn_params.cuh"
 #include <cstdint>
 using namespace cn;
 extern "C" {
@@ -40,6 +41,22 @@ int emul_cube_step_f64(const double* x, const double* inertia, const double* mu,
   for (int64_t b = 0; b < B; ++b) {
     int it = cube_step_sample(P, cfg, x + 13 * b, xn + 13 * b, force ? force + 12 * b : nullptr);
     if (iters) iters[b] = it;
+  }
+  return 0;
+}
+// theta -> inertia vector and the reverse-direction product g^T J via dual numbers (as the reduce kernel does)
+int emul_theta_chain_f64(const double* theta, const double* g_inertia, double* inertia, double* grad_theta) {
+  double th[10], out[10];
+  for (int i = 0; i < 10; ++i) th[i] = theta[i];
+  theta_to_inertia_vector<double>(th, out);
+  for (int i = 0; i < 10; ++i) inertia[i] = out[i];
+  for (int t = 0; t < 10; ++t) {
+    Dual<double> dth[10], dout[10];
+    for (int i = 0; i < 10; ++i) dth[i] = Dual<double>(theta[i], i == t ? 1.0 : 0.0);
+    theta_to_inertia_vector<Dual<double>>(dth, dout);
+    double s = 0;
+    for (int i = 0; i < 10; ++i) s += g_inertia[i] * dout[i].d;
+    grad_theta[t] = s;
   }
   return 0;
 }

@@ -101,3 +101,20 @@ def test_device_math_matches_oracle_on_random_states():
     loss, _, _, _ = emul_loss(g)
     assert np.abs(loss - loss_o).max() < 1e-12
     assert rel_err(loss, loss_o, 1e-9).max() < 1e-9
+
+
+def test_device_parameter_preparation_and_chain_rule():
+    """cn_params.cuh: theta -> [m, c, I_cm/m] and its dual-number chain rule vs the oracle + autograd."""
+    lib = host_emulation_lib()
+    torch.manual_seed(3)
+    pi_cm = torch.tensor([[0.37, 0.37 * 0.002, -0.37 * 0.001, 0.37 * 0.003, 8.1e-4, 8.5e-4, 7.9e-4, 1e-5, -2e-5, 3e-5]],
+                         dtype=torch.float64)
+    theta = co.pi_cm_to_theta(pi_cm).clone().requires_grad_()
+    vec = co.theta_to_inertia_vector(theta).reshape(10)
+    g = torch.randn(10, dtype=torch.float64)
+    vec.backward(g)
+    th = theta.detach().numpy().reshape(10).copy()
+    inertia, grad = np.zeros(10), np.zeros(10)
+    lib.emul_theta_chain_f64(dptr(th), dptr(g.numpy().copy()), dptr(inertia), dptr(grad))
+    assert np.allclose(inertia, vec.detach().numpy(), rtol=1e-13, atol=1e-18)
+    assert np.allclose(grad, theta.grad.numpy().reshape(10), rtol=1e-11, atol=1e-16)
