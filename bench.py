@@ -196,6 +196,7 @@ def main():
     device = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the single JSON line
         dist.init_process_group('nccl', device_id=device)
     dtype = torch.float64 if args.dtype == 'f64' else torch.float32
     from dair_pll_b200 import ops, parallel
@@ -280,6 +281,14 @@ def main():
     except (OSError, ValueError):
         pass
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
+        key = f"cube_loss_wf_kernel_{args.dtype}_B{B}"
+        if args.variant == 0 and key in tr:
+            traffic = tr[key]['dram_bytes_read'] + tr[key]['dram_bytes_write']     # one ncu --set full capture, per launch
+    except (OSError, ValueError, KeyError):
+        pass
 
     if rank != 0:
         if world > 1:
@@ -310,7 +319,8 @@ def main():
                                           # (device-side skipped) launches issued by autograd's backward
         'roofline': {'bound': 'fp64_cuda_core' if dtype == torch.float64 else 'fp32_cuda_core',
                      'achieved': achieved_tflops, 'peak': peak_flops / 1e12, 'unit': 'TFLOP/s',
-                     'frac': achieved_tflops / (peak_flops / 1e12), 'traffic': None,
+                     'frac': achieved_tflops / (peak_flops / 1e12), 'traffic': traffic,
+                     'algorithmic_bytes': B * BYTES_PER_SAMPLE[dtype],
                      'kernel': 'cube_loss_wf_kernel' if args.variant == 0 else 'cube_loss_kernel', 'kernel_ms': ms_kernel,
                      'flops_per_sample': flops_per_sample,
                      'peak_source': 'measured in this run: dpll_fma_peak (dependent-free FMA chains, all SMs)',
