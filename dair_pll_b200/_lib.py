@@ -33,7 +33,8 @@ EXPORTS = {
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """In-tree library; DAIR_PLL_B200_LIB overrides it (A/B builds during kernel development)."""
+    return os.environ.get('DAIR_PLL_B200_LIB', _build.LIB_PATH)
 
 
 def load() -> ctypes.CDLL:

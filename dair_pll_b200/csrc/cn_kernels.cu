@@ -35,16 +35,33 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
-template <typename T>
+// load the callable-level parameters (stored as IO) into the compute type
+template <typename T, typename IO>
+__device__ __forceinline__ void load_cube_params(cn::CubeParams<T>& P, const IO* inertia, const IO* mu, const IO* half,
+                                                 T dt, T eps) {
+  T in[10], m[1], h[3];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) in[i] = T(inertia[i]);
+  m[0] = T(mu[0]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) h[i] = T(half[i]);
+  cn::cube_params_init(P, in, m, h, dt, eps);
+}
+
+// T = arithmetic type, IO = storage type of states / parameters / outputs.  The fp32 variant is
+// IO = float with T = double: on this latency-bound path fp32 arithmetic buys no speed (measured:
+// a pure-fp32 build is slower, its Newton needs more steps) and cannot hold 1e-4 on the gradients
+// (cond(H) ~ 1e4-1e5), while fp32 storage halves the HBM traffic.
+template <typename T, typename IO>
 __global__ void __launch_bounds__(kLossThreads)
-cube_loss_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __restrict__ weight,
-                 const T* __restrict__ inertia,
-                 const T* __restrict__ mu, const T* __restrict__ half, T dt, T eps, int64_t B,
-                 T* __restrict__ loss, T* __restrict__ force, int32_t* __restrict__ iters,
+cube_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
+                 const IO* __restrict__ inertia,
+                 const IO* __restrict__ mu, const IO* __restrict__ half, T dt, T eps, int64_t B,
+                 IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
                  T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag) {
   if (skip_flag && *skip_flag) return;
   cn::CubeParams<T> P;
-  cn::cube_params_init(P, inertia, mu, half, dt, eps);
+  load_cube_params<T, IO>(P, inertia, mu, half, dt, eps);
   const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
   T acc[kNAcc];
 #pragma unroll
@@ -53,17 +70,20 @@ cube_loss_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __r
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
     T xs[13], xps[13];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) { xs[i] = x[b * 13 + i]; xps[i] = xp[b * 13 + i]; }
+    for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * 13 + i]); xps[i] = T(xp[b * 13 + i]); }
     int it;
-    T gs[DPLL_CUBE_NPARAM];
+    T gs[DPLL_CUBE_NPARAM], fo[12];
 #pragma unroll
     for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
-    const T l = cn::cube_loss_sample<T>(P, cfg, xs, xps, want_grad ? gs : nullptr,
-                                        force ? force + b * 12 : nullptr, &it);
-    const T w = weight ? weight[b] : T(1);
+    const T l = cn::cube_loss_sample<T>(P, cfg, xs, xps, want_grad ? gs : nullptr, force ? fo : nullptr, &it);
+    if (force) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(fo[i]);
+    }
+    const T w = weight ? T(weight[b]) : T(1);
 #pragma unroll
     for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] += w * gs[i];
-    if (loss) loss[b] = l;
+    if (loss) loss[b] = IO(l);
     acc[14] += l;
     if (iters) iters[b] = it;
   }
@@ -108,6 +128,10 @@ cube_loss_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __r
 // The hot loop is kept small (rolled per-contact loops over the shared-memory slot) because
 // warps of one SM sit in different phases and share the instruction cache.
 // ---------------------------------------------------------------------------
+#ifndef CN_WF_UNR
+#define CN_WF_UNR 1
+#endif
+constexpr int kWfUnr = CN_WF_UNR;   // unroll factor of the per-contact loops inside the Newton step
 constexpr int kWfSlots = 64;
 constexpr int kWfWarps = 4;
 constexpr int kWfFields = 47;   // IW 6 | mcW 3 | rho 12 | q 12 | u 6 | prev_res2 1 | d 6 | d0 1
@@ -119,11 +143,11 @@ template <typename T> struct WfWarpPool {
   uint8_t q_act[kWfSlots], q_done[kWfSlots], q_ls[kWfSlots];
 };
 
-template <typename T>
+template <typename T, typename IO>
 __global__ void __launch_bounds__(kWfWarps * 32)
-cube_loss_wf_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __restrict__ weight,
-                    const T* __restrict__ inertia, const T* __restrict__ mu, const T* __restrict__ half, T dt,
-                    T eps, int64_t B, T* __restrict__ loss, T* __restrict__ force, int32_t* __restrict__ iters,
+cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
+                    const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half, T dt,
+                    T eps, int64_t B, IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
                     T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag) {
   if (skip_flag && *skip_flag) return;
   extern __shared__ __align__(16) unsigned char wf_smem[];
@@ -132,7 +156,7 @@ cube_loss_wf_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* 
   const unsigned lt_mask = (1u << lane) - 1u;
 
   cn::CubeParams<T> P;
-  cn::cube_params_init(P, inertia, mu, half, dt, eps);
+  load_cube_params<T, IO>(P, inertia, mu, half, dt, eps);
   const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
   T acc[kNAcc];
 #pragma unroll
@@ -190,7 +214,7 @@ cube_loss_wf_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* 
         for (int i = 0; i < 6; ++i) { u[i] = pool->field[33 + i][slot]; d[i] = pool->field[40 + i][slot]; }
         T best = pool->field[39][slot], d0 = pool->field[46][slot];
         int it = pool->iters[slot];
-        st = cn::cube_newton_step<T, 1>(P, S, cfg, u, d, d0, best, it);
+        st = cn::cube_newton_step<T, kWfUnr>(P, S, cfg, u, d, d0, best, it);
         pool->iters[slot] = it;
         pool->field[39][slot] = best;
         if (st == cn::NEWTON_CONTINUE) {       // (LINESEARCH leaves u, d, d0 as they were)
@@ -225,7 +249,7 @@ cube_loss_wf_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* 
         const int64_t b = fresh ? next + my_rank : lo + old;
         T xs[13], xps[13];
 #pragma unroll
-        for (int i = 0; i < 13; ++i) { xs[i] = x[b * 13 + i]; xps[i] = xp[b * 13 + i]; }
+        for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * 13 + i]); xps[i] = T(xp[b * 13 + i]); }
         const cn::CubeProb<T> S{&pool->field[0][slot], kWfSlots};
         cn::CubeLossAux<T> A;
         cn::cube_loss_prologue<T, 1>(P, xs, xps, S, A);      // (re)builds IW, mcW, rho, q in the slot
@@ -237,12 +261,16 @@ cube_loss_wf_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* 
           T gs[DPLL_CUBE_NPARAM];
 #pragma unroll
           for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
-          const T l = cn::cube_loss_epilogue<T, 1>(P, S, A, u, want_grad ? gs : (T*)nullptr,
-                                                   force ? force + b * 12 : (T*)nullptr);
-          const T w = weight ? weight[b] : T(1);
+          T fo[12];
+          const T l = cn::cube_loss_epilogue<T, 1>(P, S, A, u, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr);
+          if (force) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(fo[i]);
+          }
+          const T w = weight ? T(weight[b]) : T(1);
 #pragma unroll
           for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] += w * gs[i];
-          if (loss) loss[b] = l;
+          if (loss) loss[b] = IO(l);
           acc[14] += l;
           if (iters) iters[b] = fresh ? 0 : (pool->iters[slot] & 0xffff);
           pool->sample[slot] = -1;
@@ -288,9 +316,9 @@ cube_loss_wf_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* 
 }
 
 // Fixed-order reduction of the per-block partials: warp w owns accumulator w.
-template <typename T>
-__global__ void reduce_partials_kernel(const T* __restrict__ partials, int nblocks, T* __restrict__ grad,
-                                       T* __restrict__ loss_sum, const int32_t* __restrict__ skip_flag) {
+template <typename T, typename IO>
+__global__ void reduce_partials_kernel(const T* __restrict__ partials, int nblocks, IO* __restrict__ grad,
+                                       IO* __restrict__ loss_sum, const int32_t* __restrict__ skip_flag) {
   if (skip_flag && *skip_flag) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (w >= kNAcc) return;
@@ -298,36 +326,36 @@ __global__ void reduce_partials_kernel(const T* __restrict__ partials, int nbloc
   for (int b = lane; b < nblocks; b += 32) s += partials[(int64_t)b * kNAcc + w];
   s = warp_sum(s);
   if (lane == 0) {
-    if (w < DPLL_CUBE_NPARAM) { if (grad) grad[w] = s; }
-    else if (w == 14) { if (loss_sum) *loss_sum = s; }
+    if (w < DPLL_CUBE_NPARAM) { if (grad) grad[w] = IO(s); }
+    else if (w == 14) { if (loss_sum) *loss_sum = IO(s); }
   }
 }
 
 // ---- leaf-level parameter preparation / chain rule (cube: theta 10, friction 2 [box, ground], length 3) ----
 constexpr int kNLeaf = 15;
 
-template <typename T>
-__global__ void cube_prep_kernel(const T* __restrict__ theta, const T* __restrict__ friction,
-                                 const T* __restrict__ length, T* __restrict__ params /* [inertia 10 | mu 1 | half 3] */,
+template <typename T, typename IO>
+__global__ void cube_prep_kernel(const IO* __restrict__ theta, const IO* __restrict__ friction,
+                                 const IO* __restrict__ length, IO* __restrict__ params /* [inertia 10 | mu 1 | half 3] */,
                                  const int32_t* __restrict__ skip_flag) {
   if (skip_flag && *skip_flag) return;
   if (threadIdx.x == 0) {
     T th[10], out[10];
-    for (int i = 0; i < 10; ++i) th[i] = theta[i];
+    for (int i = 0; i < 10; ++i) th[i] = T(theta[i]);
     cn::theta_to_inertia_vector<T>(th, out);
-    for (int i = 0; i < 10; ++i) params[i] = out[i];
-    const T a = cn::t_abs(friction[0]), b = cn::t_abs(friction[1]);
-    params[10] = T(2) * a * b / (a + b);
-    for (int i = 0; i < 3; ++i) params[11 + i] = cn::t_abs(length[i]);
+    for (int i = 0; i < 10; ++i) params[i] = IO(out[i]);
+    const T a = cn::t_abs(T(friction[0])), b = cn::t_abs(T(friction[1]));
+    params[10] = IO(T(2) * a * b / (a + b));
+    for (int i = 0; i < 3; ++i) params[11 + i] = IO(cn::t_abs(T(length[i])));
   }
 }
 
 // Sums the per-block partials (fixed order) and pushes the callable-level gradient through the
 // parameter preparation: grad_leaf = [d/d theta (10) | d/d friction (2) | d/d length (3)].
-template <typename T>
-__global__ void reduce_partials_leaf_kernel(const T* __restrict__ partials, int nblocks, const T* __restrict__ theta,
-                                            const T* __restrict__ friction, const T* __restrict__ length,
-                                            T* __restrict__ grad_leaf, T* __restrict__ loss_sum,
+template <typename T, typename IO>
+__global__ void reduce_partials_leaf_kernel(const T* __restrict__ partials, int nblocks, const IO* __restrict__ theta,
+                                            const IO* __restrict__ friction, const IO* __restrict__ length,
+                                            IO* __restrict__ grad_leaf, IO* __restrict__ loss_sum,
                                             const int32_t* __restrict__ skip_flag) {
   if (skip_flag && *skip_flag) return;
   __shared__ T g[kNAcc];
@@ -342,44 +370,48 @@ __global__ void reduce_partials_leaf_kernel(const T* __restrict__ partials, int 
   const int t = threadIdx.x;
   if (t < 10 && grad_leaf) {
     cn::Dual<T> th[10], out[10];
-    for (int i = 0; i < 10; ++i) th[i] = cn::Dual<T>(theta[i], i == t ? T(1) : T(0));
+    for (int i = 0; i < 10; ++i) th[i] = cn::Dual<T>(T(theta[i]), i == t ? T(1) : T(0));
     cn::theta_to_inertia_vector<cn::Dual<T>>(th, out);
     T s = T(0);
     for (int i = 0; i < 10; ++i) s += g[i] * out[i].d;
-    grad_leaf[t] = s;
+    grad_leaf[t] = IO(s);
   } else if (t == 10 && grad_leaf) {
-    const T fa = friction[0], fb = friction[1];
+    const T fa = T(friction[0]), fb = T(friction[1]);
     const T a = cn::t_abs(fa), b = cn::t_abs(fb), den = (a + b) * (a + b);
     const T sa = fa > T(0) ? T(1) : (fa < T(0) ? T(-1) : T(0)), sb = fb > T(0) ? T(1) : (fb < T(0) ? T(-1) : T(0));
-    grad_leaf[10] = g[10] * (T(2) * b * b / den) * sa;
-    grad_leaf[11] = g[10] * (T(2) * a * a / den) * sb;
+    grad_leaf[10] = IO(g[10] * (T(2) * b * b / den) * sa);
+    grad_leaf[11] = IO(g[10] * (T(2) * a * a / den) * sb);
   } else if (t >= 11 && t < 14 && grad_leaf) {
-    const T l = length[t - 11];
-    grad_leaf[12 + (t - 11)] = g[t] * (l > T(0) ? T(1) : (l < T(0) ? T(-1) : T(0)));
+    const T l = T(length[t - 11]);
+    grad_leaf[12 + (t - 11)] = IO(g[t] * (l > T(0) ? T(1) : (l < T(0) ? T(-1) : T(0))));
   } else if (t == 14 && loss_sum) {
-    *loss_sum = g[14];
+    *loss_sum = IO(g[14]);
   }
 }
 
-template <typename T>
+template <typename T, typename IO>
 __global__ void __launch_bounds__(kLossThreads)
-cube_rollout_kernel(const T* __restrict__ x0, const T* __restrict__ inertia, const T* __restrict__ mu,
-                    const T* __restrict__ half, T dt, T eps, int64_t B, int steps, T* __restrict__ traj,
-                    T* __restrict__ force, int32_t* __restrict__ iters) {
+cube_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, const IO* __restrict__ mu,
+                    const IO* __restrict__ half, T dt, T eps, int64_t B, int steps, IO* __restrict__ traj,
+                    IO* __restrict__ force, int32_t* __restrict__ iters) {
   cn::CubeParams<T> P;
-  cn::cube_params_init(P, inertia, mu, half, dt, eps);
+  load_cube_params<T, IO>(P, inertia, mu, half, dt, eps);
   const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
-    T xc[13], xn[13];
-    T* out = traj + b * (int64_t)(steps + 1) * 13;
+    T xc[13], xn[13], fo[12];
+    IO* out = traj + b * (int64_t)(steps + 1) * 13;
 #pragma unroll
-    for (int i = 0; i < 13; ++i) { xc[i] = x0[b * 13 + i]; out[i] = xc[i]; }
+    for (int i = 0; i < 13; ++i) { xc[i] = T(x0[b * 13 + i]); out[i] = IO(xc[i]); }
     int total = 0;
     for (int s = 0; s < steps; ++s) {
-      total += cn::cube_step_sample<T>(P, cfg, xc, xn, force ? force + (b * steps + s) * 12 : nullptr);
+      total += cn::cube_step_sample<T>(P, cfg, xc, xn, force ? fo : nullptr);
+      if (force) {
 #pragma unroll
-      for (int i = 0; i < 13; ++i) { xc[i] = xn[i]; out[(int64_t)(s + 1) * 13 + i] = xn[i]; }
+        for (int i = 0; i < 12; ++i) force[(b * steps + s) * 12 + i] = IO(fo[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 13; ++i) { xc[i] = xn[i]; out[(int64_t)(s + 1) * 13 + i] = IO(xn[i]); }
     }
     if (iters) iters[b] = total;
   }
@@ -401,9 +433,10 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int64_t iters) {
   out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-template <typename T>
-int launch_cube_loss(int variant, const T* x, const T* xp, const T* weight, const T* inertia, const T* mu,
-                     const T* half, const T* theta, const T* friction, const T* length, T dt, T eps, int64_t B, T* loss, T* force, int32_t* iters, T* grad, T* loss_sum,
+template <typename T, typename IO>
+int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, const IO* inertia, const IO* mu,
+                     const IO* half, const IO* theta, const IO* friction, const IO* length, T dt, T eps, int64_t B,
+                     IO* loss, IO* force, int32_t* iters, IO* grad, IO* loss_sum,
                      const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
   const bool leaf = theta != nullptr;
   if (B < 0 || (leaf ? (!friction || !length) : (!inertia || !mu || !half))) return DPLL_EINVAL;
@@ -415,65 +448,65 @@ int launch_cube_loss(int variant, const T* x, const T* xp, const T* weight, cons
   T* partials = want_red ? static_cast<T*>(workspace) : nullptr;
   if (leaf) {
     // callable-level parameters are produced on the device, behind the partials in the workspace
-    T* params = static_cast<T*>(workspace) + (size_t)kMaxBlocks * kNAcc;
-    cube_prep_kernel<T><<<1, 32, 0, st>>>(theta, friction, length, params, skip_flag);
+    IO* params = reinterpret_cast<IO*>(static_cast<T*>(workspace) + (size_t)kMaxBlocks * kNAcc);
+    cube_prep_kernel<T, IO><<<1, 32, 0, st>>>(theta, friction, length, params, skip_flag);
     inertia = params; mu = params + 10; half = params + 11;
   }
   int blocks;
   if (variant == 0) {
     // wavefront kernel: persistent, one resident set of blocks
     const size_t smem = sizeof(WfWarpPool<T>) * kWfWarps;
-    cudaError_t ea = cudaFuncSetAttribute(cube_loss_wf_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ea = cudaFuncSetAttribute(cube_loss_wf_kernel<T, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ea != cudaSuccess) return (int)ea;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_wf_kernel<T>, kWfWarps * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_wf_kernel<T, IO>, kWfWarps * 32, smem);
     if (per_sm < 1) per_sm = 1;
     int64_t need = (B + kWfWarps * 32 - 1) / (kWfWarps * 32);
     int64_t cap = (int64_t)di.sms * per_sm;
     if (cap > kMaxBlocks) cap = kMaxBlocks;
     blocks = (int)(need < cap ? need : cap);
     if (blocks < 1) blocks = 1;
-    cube_loss_wf_kernel<T><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss,
+    cube_loss_wf_kernel<T, IO><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss,
                                                                force, iters, partials, grad ? 1 : 0, skip_flag);
   } else {
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_kernel<T>, kLossThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_kernel<T, IO>, kLossThreads, 0);
     if (per_sm < 1) per_sm = 1;
     int64_t need = (B + kLossThreads - 1) / kLossThreads;
     int64_t cap = (int64_t)di.sms * per_sm;
     if (cap > kMaxBlocks) cap = kMaxBlocks;
     blocks = (int)(need < cap ? need : cap);
     if (blocks < 1) blocks = 1;
-    cube_loss_kernel<T><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss, force,
+    cube_loss_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss, force,
                                                          iters, partials, grad ? 1 : 0, skip_flag);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (want_red) {
-    if (leaf) reduce_partials_leaf_kernel<T><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, theta, friction, length, grad,
+    if (leaf) reduce_partials_leaf_kernel<T, IO><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, theta, friction, length, grad,
                                                                      loss_sum, skip_flag);
-    else reduce_partials_kernel<T><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, grad, loss_sum, skip_flag);
+    else reduce_partials_kernel<T, IO><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, grad, loss_sum, skip_flag);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
   return DPLL_OK;
 }
 
-template <typename T>
-int launch_cube_rollout(const T* x0, const T* inertia, const T* mu, const T* half, T dt, T eps, int64_t B,
-                        int32_t steps, T* traj, T* force, int32_t* iters, void* stream) {
+template <typename T, typename IO>
+int launch_cube_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO* half, T dt, T eps, int64_t B,
+                        int32_t steps, IO* traj, IO* force, int32_t* iters, void* stream) {
   if (B < 0 || steps < 0 || !inertia || !mu || !half) return DPLL_EINVAL;
   if (B > 0 && (!x0 || !traj)) return DPLL_EINVAL;
   if (B == 0) return DPLL_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DeviceInfo di = device_info();
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_rollout_kernel<T>, kLossThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_rollout_kernel<T, IO>, kLossThreads, 0);
   if (per_sm < 1) per_sm = 1;
   int64_t need = (B + kLossThreads - 1) / kLossThreads;
   int64_t cap = (int64_t)di.sms * per_sm;
   int blocks = (int)(need < cap ? need : cap);
-  cube_rollout_kernel<T><<<blocks, kLossThreads, 0, st>>>(x0, inertia, mu, half, dt, eps, B, steps, traj, force,
+  cube_rollout_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x0, inertia, mu, half, dt, eps, B, steps, traj, force,
                                                           iters);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPLL_OK : (int)e;
@@ -499,7 +532,7 @@ int dpll_cube_loss_f64(const double* x, const double* x_plus, const double* weig
                        const double* mu_pair, const double* half, double dt, double eps, int64_t B, double* loss,
                        double* force, int32_t* iters, double* grad, double* loss_sum, const int32_t* skip_flag,
                        void* workspace, size_t workspace_bytes, void* stream) {
-  return launch_cube_loss<double>(g_loss_variant, x, x_plus, weight, inertia, mu_pair, half, nullptr, nullptr, nullptr,
+  return launch_cube_loss<double, double>(g_loss_variant, x, x_plus, weight, inertia, mu_pair, half, nullptr, nullptr, nullptr,
                                   dt, eps, B, loss, force, iters, grad, loss_sum, skip_flag, workspace,
                                   workspace_bytes, stream);
 }
@@ -509,7 +542,7 @@ int dpll_cube_loss_leaf_f64(const double* x, const double* x_plus, const double*
                             double* loss, double* force, int32_t* iters, double* grad_leaf, double* loss_sum,
                             const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
   if (!theta) return DPLL_EINVAL;
-  return launch_cube_loss<double>(g_loss_variant, x, x_plus, weight, nullptr, nullptr, nullptr, theta, friction, length,
+  return launch_cube_loss<double, double>(g_loss_variant, x, x_plus, weight, nullptr, nullptr, nullptr, theta, friction, length,
                                   dt, eps, B, loss, force, iters, grad_leaf, loss_sum, skip_flag, workspace,
                                   workspace_bytes, stream);
 }
@@ -518,9 +551,9 @@ int dpll_cube_loss_f32(const float* x, const float* x_plus, const float* weight,
                        const float* mu_pair, const float* half, float dt, float eps, int64_t B, float* loss,
                        float* force, int32_t* iters, float* grad, float* loss_sum, const int32_t* skip_flag,
                        void* workspace, size_t workspace_bytes, void* stream) {
-  return launch_cube_loss<float>(g_loss_variant, x, x_plus, weight, inertia, mu_pair, half, nullptr, nullptr, nullptr,
-                                 dt, eps, B, loss, force, iters, grad, loss_sum, skip_flag, workspace, workspace_bytes,
-                                 stream);
+  return launch_cube_loss<double, float>(g_loss_variant, x, x_plus, weight, inertia, mu_pair, half, nullptr, nullptr, nullptr,
+                                 (double)dt, (double)eps, B, loss, force, iters, grad, loss_sum, skip_flag, workspace,
+                                 workspace_bytes, stream);
 }
 
 int dpll_cube_loss_leaf_f32(const float* x, const float* x_plus, const float* weight, const float* theta,
@@ -528,21 +561,22 @@ int dpll_cube_loss_leaf_f32(const float* x, const float* x_plus, const float* we
                             float* force, int32_t* iters, float* grad_leaf, float* loss_sum, const int32_t* skip_flag,
                             void* workspace, size_t workspace_bytes, void* stream) {
   if (!theta) return DPLL_EINVAL;
-  return launch_cube_loss<float>(g_loss_variant, x, x_plus, weight, nullptr, nullptr, nullptr, theta, friction, length,
-                                 dt, eps, B, loss, force, iters, grad_leaf, loss_sum, skip_flag, workspace,
-                                 workspace_bytes, stream);
+  return launch_cube_loss<double, float>(g_loss_variant, x, x_plus, weight, nullptr, nullptr, nullptr, theta, friction,
+                                         length, (double)dt, (double)eps, B, loss, force, iters, grad_leaf, loss_sum,
+                                         skip_flag, workspace, workspace_bytes, stream);
 }
 
 int dpll_cube_rollout_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,
                           double dt, double eps, int64_t B, int32_t steps, double* traj, double* force,
                           int32_t* iters, void* stream) {
-  return launch_cube_rollout<double>(x0, inertia, mu_pair, half, dt, eps, B, steps, traj, force, iters, stream);
+  return launch_cube_rollout<double, double>(x0, inertia, mu_pair, half, dt, eps, B, steps, traj, force, iters, stream);
 }
 
 int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu_pair, const float* half, float dt,
                           float eps, int64_t B, int32_t steps, float* traj, float* force, int32_t* iters,
                           void* stream) {
-  return launch_cube_rollout<float>(x0, inertia, mu_pair, half, dt, eps, B, steps, traj, force, iters, stream);
+  return launch_cube_rollout<double, float>(x0, inertia, mu_pair, half, (double)dt, (double)eps, B, steps, traj, force,
+                                            iters, stream);
 }
 
 int dpll_fma_peak_f64(double* out, int32_t blocks, int64_t iters, void* stream) {

@@ -19,18 +19,28 @@ int emul_cube_loss_f64(const double* x, const double* xp, const double* inertia,
   }
   return 0;
 }
+// fp32 variant = fp32 storage, fp64 arithmetic (as the kernels: T = double, IO = float)
 int emul_cube_loss_f32(const float* x, const float* xp, const float* inertia, const float* mu,
                        const float* half, float dt, float eps, int64_t B, float* loss, float* force,
                        int32_t* iters, float* grad) {
-  CubeParams<float> P;
-  cube_params_init(P, inertia, mu, half, dt, eps);
-  SolverCfg<float> cfg = default_cfg<float>();
-  for (int i = 0; i < CUBE_NPARAM; ++i) if (grad) grad[i] = 0;
+  double in[10], m[1], h[3];
+  for (int i = 0; i < 10; ++i) in[i] = inertia[i];
+  m[0] = mu[0];
+  for (int i = 0; i < 3; ++i) h[i] = half[i];
+  CubeParams<double> P;
+  cube_params_init(P, in, m, h, (double)dt, (double)eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  double g[CUBE_NPARAM];
+  for (int i = 0; i < CUBE_NPARAM; ++i) g[i] = 0;
   for (int64_t b = 0; b < B; ++b) {
+    double xs[13], xps[13], fo[12];
+    for (int i = 0; i < 13; ++i) { xs[i] = x[13 * b + i]; xps[i] = xp[13 * b + i]; }
     int it;
-    loss[b] = cube_loss_sample(P, cfg, x + 13 * b, xp + 13 * b, grad, force ? force + 12 * b : nullptr, &it);
+    loss[b] = (float)cube_loss_sample(P, cfg, xs, xps, grad ? g : nullptr, force ? fo : nullptr, &it);
+    if (force) for (int i = 0; i < 12; ++i) force[12 * b + i] = (float)fo[i];
     if (iters) iters[b] = it;
   }
+  if (grad) for (int i = 0; i < CUBE_NPARAM; ++i) grad[i] = (float)g[i];
   return 0;
 }
 int emul_cube_step_f64(const double* x, const double* inertia, const double* mu, const double* half,

@@ -219,14 +219,29 @@ def test_symmetry_properties_full_size():
     assert err.max().item() < 1e-7 and err.median().item() < 1e-12
 
 
-def test_fp32_variant_matches_reference_golden(assets_dir):
-    g = load_golden('cube_real_perturbed')
-    inertia, mu, half = (torch.from_numpy(a).float().to(DEV) for a in kernel_level_params(g))
+@pytest.mark.parametrize('name', CASES)
+def test_fp32_variant_matches_reference_golden(name, assets_dir):
+    """fp32 variant (fp32 states/parameters/outputs, fp64 arithmetic inside): 1e-4 (north_star) on
+    losses, parameter gradients and next states, against the fp64 reference results."""
+    g = load_golden(name)
+    s = _system(g, assets_dir)
     x, xp = torch.from_numpy(g['x']).float().to(DEV), torch.from_numpy(g['x_plus']).float().to(DEV)
-    loss, grad, _, _, _ = ops.cube_loss_raw(x, xp, inertia, mu, half, float(g['dt']), 1e-3)
-    l = loss.cpu().numpy().astype(np.float64)
+    loss = s.contactnets_loss(x, None, xp)
+    assert loss.dtype == torch.float32
+    loss.mean().backward()
+    l = loss.detach().cpu().numpy().astype(np.float64)
     assert np.abs(l - g['loss']).max() < 1e-4 * max(np.abs(g['loss']).max(), 1e-3)
     assert abs(l.mean() - g['loss'].mean()) < 1e-4 * abs(g['loss'].mean())
+    mt = s.multibody_terms
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), g['grad_theta']) < 1e-4
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), g['grad_friction']) < 1e-4
+    assert max_rel_to_scale(mt.contact_terms.geometries[0].length_params.grad.cpu().numpy(), g['grad_length']) < 1e-4
+    x0 = torch.from_numpy(g['sim_x0']).float().to(DEV)
+    with torch.no_grad():
+        traj, _ = s.simulate(x0.unsqueeze(-2), torch.zeros(x0.shape[0], 1, device=DEV), 1)
+    assert traj.dtype == torch.float32
+    ref = g['sim_traj'][:, 1]
+    assert np.abs(traj[:, 1].cpu().numpy() - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
 
 
 def test_invalid_arguments_raise():

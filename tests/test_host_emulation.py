@@ -63,16 +63,18 @@ def test_device_math_fp64_matches_reference_golden(name):
 
 @pytest.mark.parametrize('name', CASES)
 def test_device_math_fp32_variant(name):
-    """fp32 variant: 1e-4 on losses and gradients (north_star)."""
+    """fp32 variant (fp32 storage, fp64 arithmetic): 1e-4 on losses and gradients (north_star).  The
+    comparison is against the fp64 reference results on the unrounded inputs, so it includes the
+    effect of rounding states and parameters to fp32."""
     g = load_golden(name)
     loss, _, _, grad = emul_loss(g, np.float32)
     B = loss.shape[0]
     assert np.abs(loss - g['loss']).max() < 1e-4 * max(np.abs(g['loss']).max(), 1e-3)
     assert abs(loss.mean() - g['loss'].mean()) < 1e-4 * abs(g['loss'].mean())
     gt, gf, gl = chain_to_leaves(g, grad.astype(np.float64) / B)
-    # TODO(fp32): pure-fp32 Newton reaches ~3e-3 on gradients (cond(H) ~ 1e4-1e5); the target is 1e-4.
-    assert max_rel_to_scale(gt, g['grad_theta']) < 1e-2
-    assert max_rel_to_scale(gl, g['grad_length']) < 1e-2
+    assert max_rel_to_scale(gt, g['grad_theta']) < 1e-4
+    assert max_rel_to_scale(gf, g['grad_friction']) < 1e-4
+    assert max_rel_to_scale(gl, g['grad_length']) < 1e-4
 
 
 @pytest.mark.parametrize('name', CASES)
