@@ -67,3 +67,70 @@ def cube_learnables_perturbed(seed: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
     friction = torch.tensor([CUBE_NOMINAL['mu_box'], CUBE_NOMINAL['mu_ground']], dtype=torch.float64) * r(2)
     half = CUBE_HALF * r(3)
     return cube_pi_cm_perturbed(seed), friction, half
+
+
+# ---------------------------------------------------------------------------
+# elbow (two 0.1 x 0.05 x 0.05 boxes, y-axis hinge at (-0.035, 0.06, 0))
+# ---------------------------------------------------------------------------
+ELBOW_HALF = (0.05, 0.025, 0.025)
+ELBOW_JOINT_ORIGIN = (-0.035, 0.06, 0.0)
+ELBOW_BOX2_OFFSET = (0.035, 0.0, 0.0)
+ELBOW_NOMINAL = dict(m=0.37, inertia=0.0006167, mu_box=0.3, mu_ground=1.0)
+
+
+def _quat_to_rot(quat: Tensor) -> Tensor:
+    w, x, y, z = quat.unbind(-1)
+    return torch.stack((
+        torch.stack((1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)), -1),
+        torch.stack((2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)), -1),
+        torch.stack((2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)), -1)), -2)
+
+
+def elbow_states(batch: int, seed: int = 0, dtype=torch.float64, device='cpu') -> Tensor:
+    """(batch, 15) elbow states [quat | pos | hinge angle | w_body | v_world | hinge rate]: random
+    orientation and hinge angle; height = (lowest corner of either box at z = 0) + delta with the same
+    contact-rich / flight mixture as :func:`cube_states`; hinge rate ~ N(0, 6^2)."""
+    g = torch.Generator().manual_seed(seed)
+    quat = torch.randn(batch, 4, generator=g, dtype=torch.float64)
+    quat = quat / quat.norm(dim=-1, keepdim=True)
+    xy = torch.rand(batch, 2, generator=g, dtype=torch.float64) - 0.5
+    theta = (2 * torch.rand(batch, generator=g, dtype=torch.float64) - 1) * math.pi
+    R1 = _quat_to_rot(quat)
+    c, s_ = torch.cos(theta), torch.sin(theta)
+    zero, one = torch.zeros_like(c), torch.ones_like(c)
+    Ry = torch.stack((torch.stack((c, zero, s_), -1), torch.stack((zero, one, zero), -1),
+                      torch.stack((-s_, zero, c), -1)), -2)
+    R2 = R1 @ Ry
+    half = torch.tensor(ELBOW_HALF, dtype=torch.float64)
+    pj = torch.tensor(ELBOW_JOINT_ORIGIN, dtype=torch.float64)
+    off = torch.tensor(ELBOW_BOX2_OFFSET, dtype=torch.float64)
+    low1 = -(R1[:, 2, :].abs() * half).sum(-1)
+    low2 = (R1 @ pj)[:, 2] + (R2 @ off)[:, 2] - (R2[:, 2, :].abs() * half).sum(-1)
+    lowest = torch.minimum(low1, low2)
+    near = torch.rand(batch, generator=g, dtype=torch.float64) < 0.5
+    u = torch.rand(batch, generator=g, dtype=torch.float64)
+    delta = torch.where(near, -0.005 + 0.015 * u, 0.01 + 0.19 * u)
+    z = -lowest + delta
+    omega = 5.0 * torch.randn(batch, 3, generator=g, dtype=torch.float64)
+    vel = torch.randn(batch, 3, generator=g, dtype=torch.float64)
+    rate = 6.0 * torch.randn(batch, 1, generator=g, dtype=torch.float64)
+    x = torch.cat((quat, xy, z[:, None], theta[:, None], omega, vel, rate), -1)
+    return x.to(dtype=dtype, device=device)
+
+
+def elbow_learnables_perturbed(seed: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
+    """pi_cm (2,10), friction_params (3,) [box1, box2, ground], half lengths (2,3): nominal URDF values
+    perturbed by 10%, plus mm-scale centre-of-mass offsets."""
+    g = torch.Generator().manual_seed(3000 + seed)
+    r = lambda n: 1 + 0.1 * (2 * torch.rand(n, generator=g, dtype=torch.float64) - 1)  # noqa: E731
+    rows = []
+    for com0 in ((0., 0., 0.), ELBOW_BOX2_OFFSET):
+        m = ELBOW_NOMINAL['m'] * r(1)
+        c = torch.tensor(com0, dtype=torch.float64) + 0.004 * (2 * torch.rand(3, generator=g, dtype=torch.float64) - 1)
+        diag = ELBOW_NOMINAL['inertia'] * r(3)
+        offd = 2e-5 * (2 * torch.rand(3, generator=g, dtype=torch.float64) - 1)
+        rows.append(torch.cat((m, m * c, diag, offd)))
+    friction = torch.tensor([ELBOW_NOMINAL['mu_box'], ELBOW_NOMINAL['mu_box'], ELBOW_NOMINAL['mu_ground']],
+                            dtype=torch.float64) * r(3)
+    half = torch.tensor([ELBOW_HALF, ELBOW_HALF], dtype=torch.float64) * r(6).reshape(2, 3)
+    return torch.stack(rows), friction, half

@@ -110,6 +110,38 @@ def cube_case(name, x, x_plus, pi_cm, friction, half, sim_states, rollout_steps)
     print(name, 'B', x.shape[0], 'mean loss %.12e' % loss.mean().item(), 'size %.1f KB' % (os.path.getsize(path) / 1e3))
 
 
+def elbow_case(name, x, x_plus, pi_cm, friction, half, sim_states, rollout_steps):
+    from dair_pll import tensor_utils
+    solver = RecordingSolver()
+    system = ref_shim.build_reference_system('elbow', DT, pi_cm, friction, [h.tolist() for h in half], solver=solver)
+    mt = system.multibody_terms
+    u = torch.zeros(x.shape[:-1] + (0,))
+    loss = system.contactnets_loss(x, u, x_plus)
+    loss.mean().backward()
+    J_s, q_s, eps, f_s = solver.calls[-1]
+    n_c = 8
+    P = tensor_utils.sappy_reorder_mat(n_c)
+    force_ref = (P @ f_s[..., None])[..., 0]
+    perm = canonical_contact_permutation(system, x_plus[:, :8])
+    out = dict(
+        dt=np.float64(DT), x=x.numpy(), x_plus=x_plus.numpy(), pi_cm=pi_cm.numpy(),
+        friction_params=friction.numpy(), half_lengths=half.numpy(),
+        theta=mt.lagrangian_terms.inertial_parameters.detach().numpy(),
+        loss=loss.detach().numpy(), force=reorder_force(force_ref, perm).numpy(),
+        grad_theta=mt.lagrangian_terms.inertial_parameters.grad.numpy(),
+        grad_friction=mt.contact_terms.friction_params.grad.numpy(),
+        grad_length=np.stack([mt.contact_terms.geometries[g].length_params.grad.numpy().reshape(3) for g in range(2)]))
+    with torch.no_grad():
+        D, M, J, phi, acc = mt(x_plus[:, :8], x_plus[:, 8:], u)
+    out.update(terms_M=M.numpy(), terms_acc=acc.numpy(), terms_phi_sorted=np.sort(phi.numpy(), -1))
+    with torch.no_grad():
+        traj, _ = system.simulate(sim_states.unsqueeze(-2), torch.zeros(sim_states.shape[0], 1), rollout_steps)
+    out.update(sim_x0=sim_states.numpy(), sim_traj=traj.numpy())
+    path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')
+    np.savez_compressed(path, **out)
+    print(name, 'B', x.shape[0], 'mean loss %.12e' % loss.mean().item(), 'size %.1f KB' % (os.path.getsize(path) / 1e3))
+
+
 def main():
     assert ref_shim.available(), 'needs the reference tree'
     ref_shim.import_reference()
@@ -133,6 +165,21 @@ def main():
         xn, _ = system.integrator.step(xs, torch.zeros(xs.shape[0], 1))
     xp = synthetic.perturb_next_state(xn, seed=8)
     cube_case('cube_synthetic', xs, xp, pi, fr, half, xs[:64], 4)
+    # (4) elbow (two boxes + hinge), nominal URDF parameters and perturbed ones, synthetic states
+    for name, seed, learn in (('elbow_nominal', 11, None), ('elbow_perturbed', 13, synthetic.elbow_learnables_perturbed(0))):
+        if learn is None:
+            m, i0 = synthetic.ELBOW_NOMINAL['m'], synthetic.ELBOW_NOMINAL['inertia']
+            pi_e = torch.tensor([[m, 0, 0, 0, i0, i0, i0, 0, 0, 0], [m, m * 0.035, 0, 0, i0, i0, i0, 0, 0, 0]])
+            fr_e = torch.tensor([0.3, 0.3, 1.0])
+            half_e = torch.tensor([synthetic.ELBOW_HALF, synthetic.ELBOW_HALF])
+        else:
+            pi_e, fr_e, half_e = learn
+        xe = synthetic.elbow_states(320, seed=seed)
+        system = ref_shim.build_reference_system('elbow', DT, pi_e, fr_e, [h.tolist() for h in half_e])
+        with torch.no_grad():
+            xn, _ = system.integrator.step(xe, torch.zeros(xe.shape[0], 1))
+        xpe = synthetic.perturb_next_state(xn, seed=seed + 1, n_q=8)
+        elbow_case(name, xe, xpe, pi_e, fr_e, half_e, xe[:48], 4)
 
 
 if __name__ == '__main__':

@@ -7,11 +7,13 @@ import torch
 
 from oracle import cone_qp
 from oracle import contactnets_oracle as co
-from oracle.callables import CUBE_TREE, TreeCallables
+from oracle.callables import CUBE_TREE, ELBOW_TREE, TreeCallables
 from tests.util import load_golden, max_rel_to_scale, oracle_params_from_golden, rel_err
 
 CASES = ['cube_real_nominal', 'cube_real_perturbed', 'cube_synthetic']
 CALLS = TreeCallables(CUBE_TREE)
+ELBOW_CASES = ['elbow_nominal', 'elbow_perturbed']
+ELBOW_CALLS = TreeCallables(ELBOW_TREE)
 
 
 @pytest.mark.parametrize('name', CASES)
@@ -109,3 +111,67 @@ def test_icnn_support_equals_autograd_of_support_function():
     f = (h1 @ net['wout'].abs()).sum()
     (jac,) = torch.autograd.grad(f, d)
     assert torch.allclose(co.icnn_support(net, d.detach()), jac, atol=1e-12)
+
+
+@pytest.mark.parametrize('name', ELBOW_CASES)
+def test_elbow_matches_reference_python(name):
+    """Two-body articulated system (contactnets_elbow.urdf): loss, impulses, gradients, terms, rollout."""
+    g = load_golden(name)
+    P = oracle_params_from_golden(g)
+    x, xp = torch.from_numpy(g['x']), torch.from_numpy(g['x_plus'])
+    loss, force = co.contactnets_loss(ELBOW_CALLS, P, x, xp, float(g['dt']), return_force=True)
+    loss.mean().backward()
+    assert np.abs(loss.detach().numpy() - g['loss']).max() < 1e-13
+    assert rel_err(loss.detach().numpy(), g['loss'], 1e-9).max() < 1e-9
+    scale = np.maximum(np.abs(g['force']).max(axis=1, keepdims=True), 1e-6)
+    assert (np.abs(force.numpy() - g['force']) / scale).max() < 1e-8
+    assert max_rel_to_scale(P.inertial_parameters.grad.numpy(), g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(P.friction_params.grad.numpy(), g['grad_friction']) < 1e-9
+    gl = np.stack([p.grad.numpy().reshape(3) for p in P.length_params])
+    assert max_rel_to_scale(gl, g['grad_length']) < 1e-9
+    with torch.no_grad():
+        M, J, phi, acc = co.multibody_terms(ELBOW_CALLS, P, xp[:, :8], xp[:, 8:])
+        assert np.abs(M.numpy() - g['terms_M']).max() < 1e-15
+        assert np.abs(acc.numpy() - g['terms_acc']).max() < 1e-10 * max(1.0, np.abs(g['terms_acc']).max())
+        steps = g['sim_traj'].shape[1] - 1
+        traj = co.simulate(ELBOW_CALLS, P, torch.from_numpy(g['sim_x0']), float(g['dt']), steps).numpy()
+    assert np.abs(traj[:, 1] - g['sim_traj'][:, 1]).max() < 1e-9
+    assert np.abs(traj - g['sim_traj']).max() < 1e-6
+
+
+@pytest.mark.parametrize('tree,n_q,seed', [(CUBE_TREE, 7, 1), (ELBOW_TREE, 8, 2)])
+def test_restated_callables_satisfy_the_power_balance(tree, n_q, seed):
+    """Physics certificate for the un-vendored symbolic callables (parity unpinned): along the
+    contact-free flow q' = q (+) v dt the generated M(q) and F(q, v) must conserve energy,
+        d/dt (1/2 v^T M v + V) = v^T F + 1/2 v^T Mdot v + Vdot = 0,
+    which ties the Coriolis/centrifugal and gravity terms of F to M independently of how either was
+    derived (Mdot, Vdot by central differences along the flow)."""
+    from dair_pll_b200 import synthetic
+    calls = TreeCallables(tree)
+    if tree is CUBE_TREE:
+        pi, _, _ = synthetic.cube_learnables_perturbed(0)
+        x = synthetic.cube_states(64, seed=seed)
+    else:
+        pi, _, _ = synthetic.elbow_learnables_perturbed(0)
+        x = synthetic.elbow_states(64, seed=seed)
+    inertia = co.theta_to_inertia_vector(co.pi_cm_to_theta(pi))
+    q, v = x[:, :n_q], x[:, n_q:]
+    ine = inertia.expand(q.shape[:-1] + inertia.shape)
+
+    def flow(h):
+        quat = co.quat_mul(q[:, :4], co.quat_exp(v[:, :3] * h))
+        return torch.cat((quat, q[:, 4:] + v[:, 3:] * h), -1)
+
+    def potential(qq):
+        R, o, *_ = calls.kinematics(qq)
+        return sum(inertia[i, 0] * 9.81 * (o[i][:, 2] + (R[i] @ inertia[i, 1:4])[:, 2]) for i in range(tree.n_bodies))
+
+    h = 1e-6
+    M = calls.mass_matrix(q, ine)
+    F = calls.lagrangian_forces(q, v, None, ine)
+    assert torch.allclose(M, M.transpose(-1, -2), atol=1e-15)
+    assert (torch.linalg.eigvalsh(M) > 0).all()
+    Mdot = (calls.mass_matrix(flow(h), ine) - calls.mass_matrix(flow(-h), ine)) / (2 * h)
+    Vdot = (potential(flow(h)) - potential(flow(-h))) / (2 * h)
+    power = (v * F).sum(-1) + 0.5 * (v * (Mdot @ v[..., None])[..., 0]).sum(-1) + Vdot
+    assert power.abs().max().item() < 1e-7 * (v * F).sum(-1).abs().max().item()

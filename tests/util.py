@@ -28,8 +28,9 @@ def max_rel_to_scale(a, b):
 
 def oracle_params_from_golden(g, requires_grad=True):
     from oracle import contactnets_oracle as co
+    halves = np.atleast_2d(g['half_lengths'])
     p = co.OracleParams(torch.from_numpy(g['theta']).clone(), torch.from_numpy(g['friction_params']).clone(),
-                        [torch.from_numpy(g['half_lengths']).clone().reshape(1, 3)])
+                        [torch.from_numpy(h.copy()).reshape(1, 3) for h in halves])
     return p.requires_grad_(requires_grad)
 
 
