@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libdair_pll_b200.so')
 SOURCES = ['cn_kernels.cu']
-HEADERS = ['cn_common.cuh', 'cn_cube.cuh', 'cn_params.cuh', os.path.join('..', '..', 'include', 'dair_pll_b200.h')]
+HEADERS = ['cn_common.cuh', 'cn_cube.cuh', 'cn_params.cuh', 'cn_elbow.cuh', os.path.join('..', '..', 'include', 'dair_pll_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 

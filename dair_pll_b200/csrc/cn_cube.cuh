@@ -464,6 +464,54 @@ template <typename T> CN_HD void vex3(const T* X, T* o) {
   o[0] = X[7] - X[5]; o[1] = X[2] - X[6]; o[2] = X[3] - X[1];
 }
 
+// Adjoint of a rigid body's mass matrix and force vector w.r.t. its inertia 10-vector
+// [m, c(3), Ixx, Iyy, Izz, Ixy, Ixz, Iyz] (body-frame angular / world-frame linear coordinates):
+//   M = [[I_o, m S(c) R^T], [-m R S(c), m I3]],  I_o = I_sym - m S(c)^2,
+//   F = [-w x (I_o w) + m c x (R^T g) ; -m R (w x (w x c)) + m g]
+// given the loss differential  <Kww, dM_ww> + <N, dM_wv> + trvv dm (from M_vv) + lam . dF,
+// with N = Mbar_wv + Mbar_vw^T.  grad[0..9] += d loss / d inertia-vector.
+template <typename T>
+CN_HD void rigid_body_inertia_adjoint(T m, const T* c, const T* R, const T* w, T grav, T* Kww, const T* N, T trvv,
+                                      const T* lam, T* grad) {
+  // F-term into the I_o adjoint: (w x lam_w) w^T
+  T wxl[3];
+  cross3(w, lam, wxl);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Kww[3 * i + j] += wxl[i] * w[j];
+  // I_sym
+  grad[4] += Kww[0]; grad[5] += Kww[4]; grad[6] += Kww[8];
+  grad[7] += Kww[1] + Kww[3]; grad[8] += Kww[2] + Kww[6]; grad[9] += Kww[5] + Kww[7];
+  const T trK = Kww[0] + Kww[4] + Kww[8];
+  T Kc[3], Ktc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Kc[i] = Kww[3 * i] * c[0] + Kww[3 * i + 1] * c[1] + Kww[3 * i + 2] * c[2];
+    Ktc[i] = Kww[i] * c[0] + Kww[3 + i] * c[1] + Kww[6 + i] * c[2];
+  }
+  const T cc = dot3(c, c);
+  T NR[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) NR[3 * i + j] = N[3 * i] * R[j] + N[3 * i + 1] * R[3 + j] + N[3 * i + 2] * R[6 + j];
+  T vNR[3];
+  vex3(NR, vNR);
+  const T gB[3] = {-grav * R[6], -grav * R[7], -grav * R[8]};
+  T ell[3];
+  rot3t(R, lam + 3, ell);
+  T cxg[3], wc[3], wwc[3], wl[3], wwl[3], gxl[3];
+  cross3(c, gB, cxg);
+  cross3(w, c, wc); cross3(w, wc, wwc);
+  cross3(w, ell, wl); cross3(w, wl, wwl);
+  cross3(gB, lam, gxl);
+  grad[0] += cc * trK - dot3(c, Kc) + dot3(c, vNR) + trvv + dot3(lam, cxg) - dot3(ell, wwc) - grav * lam[5];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    grad[1 + i] += m * (T(2) * trK * c[i] - Kc[i] - Ktc[i] + vNR[i] + gxl[i] - wwl[i]);
+}
+
 // Loss value at the optimum u and (if grad != nullptr) += d loss / d [inertia(10), mu, half(3)].
 // force_out (nullable): reference order [n(4); (tx,ty)(4)].
 template <typename T, int UNR>
@@ -521,44 +569,7 @@ CN_HD T cube_loss_epilogue(const CubeParams<T>& P, const CubeProb<T>& S, const C
     }
 #pragma unroll
   for (int i = 0; i < 3; ++i) trvv += T(0.5) * (dv[3 + i] * dv[3 + i] - y[3 + i] * y[3 + i]) - lam[3 + i] * a[3 + i];
-  // F-term into the I_o adjoint: (w x lam_w) w^T
-  T wxl[3];
-  cross3(w, lam, wxl);
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) Kww[3 * i + j] += wxl[i] * w[j];
-  // I_sym
-  grad[4] += Kww[0]; grad[5] += Kww[4]; grad[6] += Kww[8];
-  grad[7] += Kww[1] + Kww[3]; grad[8] += Kww[2] + Kww[6]; grad[9] += Kww[5] + Kww[7];
-  const T* c = P.c;
-  const T trK = Kww[0] + Kww[4] + Kww[8];
-  T Kc[3], Ktc[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    Kc[i] = Kww[3 * i] * c[0] + Kww[3 * i + 1] * c[1] + Kww[3 * i + 2] * c[2];
-    Ktc[i] = Kww[i] * c[0] + Kww[3 + i] * c[1] + Kww[6 + i] * c[2];
-  }
-  const T cc = dot3(c, c);
-  T NR[9];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) NR[3 * i + j] = N[3 * i] * R[j] + N[3 * i + 1] * R[3 + j] + N[3 * i + 2] * R[6 + j];
-  T vNR[3];
-  vex3(NR, vNR);
-  const T gB[3] = {-P.grav * R[6], -P.grav * R[7], -P.grav * R[8]};
-  T ell[3];
-  rot3t(R, lam + 3, ell);
-  T cxg[3], wc[3], wwc[3], wl[3], wwl[3], gxl[3];
-  cross3(c, gB, cxg);
-  cross3(w, c, wc); cross3(w, wc, wwc);
-  cross3(w, ell, wl); cross3(w, wl, wwl);
-  cross3(gB, lam, gxl);
-  grad[0] += cc * trK - dot3(c, Kc) + dot3(c, vNR) + trvv + dot3(lam, cxg) - dot3(ell, wwc) - P.grav * lam[5];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-    grad[1 + i] += P.m * (T(2) * trK * c[i] - Kc[i] - Ktc[i] + vNR[i] + gxl[i] - wwl[i]);
+  rigid_body_inertia_adjoint<T>(P.m, P.c, R, w, P.grav, Kww, N, trvv, lam, grad);
   // pass 2: contacts -> mu and half lengths (forces recomputed: cheaper than parking them)
   T bW[3], wW[3];
   rot3(R, b, bW); rot3(R, w, wW);

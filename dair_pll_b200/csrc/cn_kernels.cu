@@ -10,6 +10,7 @@
 #include "../../include/dair_pll_b200.h"
 #include "cn_cube.cuh"
 #include "cn_params.cuh"
+#include "cn_elbow.cuh"
 
 namespace {
 
@@ -316,18 +317,19 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
 }
 
 // Fixed-order reduction of the per-block partials: warp w owns accumulator w.
-template <typename T, typename IO>
+// NACC accumulators per block: [0, NPARAM) parameter gradients, slot NPARAM = loss sum.
+template <typename T, typename IO, int NACC, int NPARAM>
 __global__ void reduce_partials_kernel(const T* __restrict__ partials, int nblocks, IO* __restrict__ grad,
                                        IO* __restrict__ loss_sum, const int32_t* __restrict__ skip_flag) {
   if (skip_flag && *skip_flag) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (w >= kNAcc) return;
+  if (w >= NACC) return;
   T s = T(0);
-  for (int b = lane; b < nblocks; b += 32) s += partials[(int64_t)b * kNAcc + w];
+  for (int b = lane; b < nblocks; b += 32) s += partials[(int64_t)b * NACC + w];
   s = warp_sum(s);
   if (lane == 0) {
-    if (w < DPLL_CUBE_NPARAM) { if (grad) grad[w] = IO(s); }
-    else if (w == 14) { if (loss_sum) *loss_sum = IO(s); }
+    if (w < NPARAM) { if (grad) grad[w] = IO(s); }
+    else if (w == NPARAM) { if (loss_sum) *loss_sum = IO(s); }
   }
 }
 
@@ -417,6 +419,139 @@ cube_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, c
   }
 }
 
+// ---------------------------------------------------------------------------
+// Elbow (floating base + hinge, 8 contacts): one sample per thread, problem in thread-local arrays.
+// ---------------------------------------------------------------------------
+constexpr int kNAccE = 32;   // 28 parameter gradients + loss sum + pad
+
+template <typename T, typename IO>
+__device__ __forceinline__ void load_elbow_params(cn::ElbowParams<T>& P, const IO* inertia, const IO* mu, const IO* half,
+                                                  const IO* kin, T dt, T eps) {
+  T in[20], m[2], h[6], kn[cn::EL_NKIN];
+  for (int i = 0; i < 20; ++i) in[i] = T(inertia[i]);
+  for (int i = 0; i < 2; ++i) m[i] = T(mu[i]);
+  for (int i = 0; i < 6; ++i) h[i] = T(half[i]);
+  for (int i = 0; i < cn::EL_NKIN; ++i) kn[i] = T(kin[i]);
+  cn::elbow_params_init(P, in, m, h, kn, dt, eps);
+}
+
+template <typename T, typename IO>
+__global__ void __launch_bounds__(kLossThreads)
+elbow_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
+                  const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half,
+                  const IO* __restrict__ kin, T dt, T eps, int64_t B, IO* __restrict__ loss, IO* __restrict__ force,
+                  int32_t* __restrict__ iters, T* __restrict__ partials, int want_grad,
+                  const int32_t* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;
+  cn::ElbowParams<T> P;
+  load_elbow_params<T, IO>(P, inertia, mu, half, kin, dt, eps);
+  const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
+  T acc[kNAccE];
+  for (int i = 0; i < kNAccE; ++i) acc[i] = T(0);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
+    T xs[15], xps[15], gs[DPLL_ELBOW_NPARAM], fo[24];
+    for (int i = 0; i < 15; ++i) { xs[i] = T(x[b * 15 + i]); xps[i] = T(xp[b * 15 + i]); }
+    for (int i = 0; i < DPLL_ELBOW_NPARAM; ++i) gs[i] = T(0);
+    int it;
+    const T l = cn::elbow_loss_sample<T>(P, cfg, xs, xps, want_grad ? gs : nullptr, force ? fo : nullptr, &it);
+    if (force) for (int i = 0; i < 24; ++i) force[b * 24 + i] = IO(fo[i]);
+    const T w = weight ? T(weight[b]) : T(1);
+    for (int i = 0; i < DPLL_ELBOW_NPARAM; ++i) acc[i] += w * gs[i];
+    if (loss) loss[b] = IO(l);
+    acc[DPLL_ELBOW_NPARAM] += l;
+    if (iters) iters[b] = it;
+  }
+  if (!partials) return;
+  __shared__ T red[kLossThreads / 32][kNAccE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = 0; i < kNAccE; ++i) {
+    const T s = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNAccE) {
+    T s = T(0);
+    for (int w = 0; w < kLossThreads / 32; ++w) s += red[w][threadIdx.x];
+    partials[(int64_t)blockIdx.x * kNAccE + threadIdx.x] = s;
+  }
+}
+
+template <typename T, typename IO>
+__global__ void __launch_bounds__(kLossThreads)
+elbow_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, const IO* __restrict__ mu,
+                     const IO* __restrict__ half, const IO* __restrict__ kin, T dt, T eps, int64_t B, int steps,
+                     IO* __restrict__ traj, IO* __restrict__ force, int32_t* __restrict__ iters) {
+  cn::ElbowParams<T> P;
+  load_elbow_params<T, IO>(P, inertia, mu, half, kin, dt, eps);
+  const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
+    T xc[15], xn[15], fo[24];
+    IO* out = traj + b * (int64_t)(steps + 1) * 15;
+    for (int i = 0; i < 15; ++i) { xc[i] = T(x0[b * 15 + i]); out[i] = IO(xc[i]); }
+    int total = 0;
+    for (int s = 0; s < steps; ++s) {
+      total += cn::elbow_step_sample<T>(P, cfg, xc, xn, force ? fo : nullptr);
+      if (force) for (int i = 0; i < 24; ++i) force[(b * steps + s) * 24 + i] = IO(fo[i]);
+      for (int i = 0; i < 15; ++i) { xc[i] = xn[i]; out[(int64_t)(s + 1) * 15 + i] = IO(xn[i]); }
+    }
+    if (iters) iters[b] = total;
+  }
+}
+
+template <typename T, typename IO>
+int launch_elbow_loss(const IO* x, const IO* xp, const IO* weight, const IO* inertia, const IO* mu, const IO* half,
+                      const IO* kin, T dt, T eps, int64_t B, IO* loss, IO* force, int32_t* iters, IO* grad, IO* loss_sum,
+                      const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || !inertia || !mu || !half || !kin) return DPLL_EINVAL;
+  if (B > 0 && (!x || !xp)) return DPLL_EINVAL;
+  const bool want_red = grad || loss_sum;
+  if (want_red && (!workspace || workspace_bytes < dpll_workspace_bytes())) return DPLL_EWORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DeviceInfo di = device_info();
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, elbow_loss_kernel<T, IO>, kLossThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  int64_t need = (B + kLossThreads - 1) / kLossThreads;
+  int64_t cap = (int64_t)di.sms * per_sm;
+  if (cap > kMaxBlocks) cap = kMaxBlocks;
+  int blocks = (int)(need < cap ? need : cap);
+  if (blocks < 1) blocks = 1;
+  T* partials = want_red ? static_cast<T*>(workspace) : nullptr;
+  elbow_loss_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, kin, dt, eps, B, loss, force,
+                                                           iters, partials, grad ? 1 : 0, skip_flag);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (want_red) {
+    reduce_partials_kernel<T, IO, kNAccE, DPLL_ELBOW_NPARAM><<<1, 32 * kNAccE, 0, st>>>(partials, blocks, grad, loss_sum,
+                                                                                         skip_flag);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return DPLL_OK;
+}
+
+template <typename T, typename IO>
+int launch_elbow_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO* half, const IO* kin, T dt, T eps,
+                         int64_t B, int32_t steps, IO* traj, IO* force, int32_t* iters, void* stream) {
+  if (B < 0 || steps < 0 || !inertia || !mu || !half || !kin) return DPLL_EINVAL;
+  if (B > 0 && (!x0 || !traj)) return DPLL_EINVAL;
+  if (B == 0) return DPLL_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DeviceInfo di = device_info();
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, elbow_rollout_kernel<T, IO>, kLossThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  int64_t need = (B + kLossThreads - 1) / kLossThreads;
+  int64_t cap = (int64_t)di.sms * per_sm;
+  int blocks = (int)(need < cap ? need : cap);
+  elbow_rollout_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x0, inertia, mu, half, kin, dt, eps, B, steps, traj, force,
+                                                              iters);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPLL_OK : (int)e;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int64_t iters) {
   T a[16];
@@ -448,7 +583,7 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
   T* partials = want_red ? static_cast<T*>(workspace) : nullptr;
   if (leaf) {
     // callable-level parameters are produced on the device, behind the partials in the workspace
-    IO* params = reinterpret_cast<IO*>(static_cast<T*>(workspace) + (size_t)kMaxBlocks * kNAcc);
+    IO* params = reinterpret_cast<IO*>(static_cast<T*>(workspace) + (size_t)kMaxBlocks * 32);
     cube_prep_kernel<T, IO><<<1, 32, 0, st>>>(theta, friction, length, params, skip_flag);
     inertia = params; mu = params + 10; half = params + 11;
   }
@@ -485,7 +620,8 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
   if (want_red) {
     if (leaf) reduce_partials_leaf_kernel<T, IO><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, theta, friction, length, grad,
                                                                      loss_sum, skip_flag);
-    else reduce_partials_kernel<T, IO><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, grad, loss_sum, skip_flag);
+    else reduce_partials_kernel<T, IO, kNAcc, DPLL_CUBE_NPARAM><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, grad, loss_sum,
+                                                                                        skip_flag);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
@@ -526,7 +662,7 @@ int dpll_set_loss_variant(int variant) {
 
 int dpll_version(void) { return 100; }
 
-size_t dpll_workspace_bytes(void) { return ((size_t)kMaxBlocks * kNAcc + 16) * sizeof(double); }
+size_t dpll_workspace_bytes(void) { return ((size_t)kMaxBlocks * 32 + 16) * sizeof(double); }
 
 int dpll_cube_loss_f64(const double* x, const double* x_plus, const double* weight, const double* inertia,
                        const double* mu_pair, const double* half, double dt, double eps, int64_t B, double* loss,
@@ -577,6 +713,36 @@ int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu
                           void* stream) {
   return launch_cube_rollout<double, float>(x0, inertia, mu_pair, half, (double)dt, (double)eps, B, steps, traj, force,
                                             iters, stream);
+}
+
+int dpll_elbow_loss_f64(const double* x, const double* x_plus, const double* weight, const double* inertia,
+                        const double* mu_pair, const double* half, const double* kin, double dt, double eps, int64_t B,
+                        double* loss, double* force, int32_t* iters, double* grad, double* loss_sum,
+                        const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_elbow_loss<double, double>(x, x_plus, weight, inertia, mu_pair, half, kin, dt, eps, B, loss, force, iters,
+                                           grad, loss_sum, skip_flag, workspace, workspace_bytes, stream);
+}
+
+int dpll_elbow_loss_f32(const float* x, const float* x_plus, const float* weight, const float* inertia,
+                        const float* mu_pair, const float* half, const float* kin, float dt, float eps, int64_t B,
+                        float* loss, float* force, int32_t* iters, float* grad, float* loss_sum,
+                        const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_elbow_loss<double, float>(x, x_plus, weight, inertia, mu_pair, half, kin, (double)dt, (double)eps, B, loss,
+                                          force, iters, grad, loss_sum, skip_flag, workspace, workspace_bytes, stream);
+}
+
+int dpll_elbow_rollout_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,
+                           const double* kin, double dt, double eps, int64_t B, int32_t steps, double* traj,
+                           double* force, int32_t* iters, void* stream) {
+  return launch_elbow_rollout<double, double>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, force, iters,
+                                              stream);
+}
+
+int dpll_elbow_rollout_f32(const float* x0, const float* inertia, const float* mu_pair, const float* half,
+                           const float* kin, float dt, float eps, int64_t B, int32_t steps, float* traj, float* force,
+                           int32_t* iters, void* stream) {
+  return launch_elbow_rollout<double, float>(x0, inertia, mu_pair, half, kin, (double)dt, (double)eps, B, steps, traj,
+                                             force, iters, stream);
 }
 
 int dpll_fma_peak_f64(double* out, int32_t blocks, int64_t iters, void* stream) {

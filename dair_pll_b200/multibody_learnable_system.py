@@ -65,6 +65,14 @@ class MultibodyLearnableSystem(System):
         inertia, mu, half = self.multibody_terms.kernel_parameters(dtype)
         return inertia.reshape(10), mu.reshape(1), half[0]
 
+    def _elbow_params(self, dtype: torch.dtype, device: torch.device):
+        inertia, mu, half = self.multibody_terms.kernel_parameters(dtype)
+        spec = self.multibody_terms.spec
+        joint = spec.joints[0]
+        kin = torch.tensor([*joint.origin, *joint.axis, *spec.geometries[0].offset, *spec.geometries[1].offset],
+                           dtype=dtype, device=device)
+        return inertia.reshape(20), mu.reshape(2), torch.cat(half), kin
+
     # -- ContactNets loss --------------------------------------------------
     def contactnets_loss(self, x: Tensor, u: Tensor, x_plus: Tensor, loss_pool=None) -> Tensor:
         """(*, n_x), (*, 0), (*, n_x) -> (*,) ContactNets loss (:104-197)."""
@@ -78,8 +86,12 @@ class MultibodyLearnableSystem(System):
             loss = ops.CubeContactNetsLossLeaf.apply(
                 self._flat(x), self._flat(x_plus), lt.inertial_parameters.to(x.dtype), ct.friction_params.to(x.dtype),
                 ct.geometries[0].length_params.to(x.dtype), float(self.dt), LOSS_EPS)
+        elif self._kind() == 'elbow':
+            inertia, mu, half, kin = self._elbow_params(x.dtype, x.device)
+            loss = ops.ElbowContactNetsLoss.apply(self._flat(x), self._flat(x_plus), inertia, mu, half, kin,
+                                                  float(self.dt), LOSS_EPS)
         else:
-            raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r} yet')
+            raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r}')
         return loss.reshape(batch)
 
     # -- simulation ------------------------------------------------------
@@ -90,8 +102,12 @@ class MultibodyLearnableSystem(System):
             inertia, mu, half = self._cube_params(x_0.dtype)
             traj, _ = ops.cube_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(),
                                        float(self.dt), steps, STEP_EPS)
+        elif self._kind() == 'elbow':
+            inertia, mu, half, kin = self._elbow_params(x_0.dtype, x_0.device)
+            traj, _ = ops.elbow_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(), kin,
+                                        float(self.dt), steps, STEP_EPS)
         else:
-            raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r} yet')
+            raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r}')
         return traj.reshape(batch + (steps + 1, self.space.n_x))
 
     def forward_dynamics(self, q: Tensor, v: Tensor, u: Tensor, dynamics_pool=None) -> Tensor:

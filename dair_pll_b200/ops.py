@@ -208,6 +208,90 @@ def cube_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, dt:
     return traj, force
 
 
+def elbow_loss_raw(x: Tensor, x_plus: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, kin: Tensor, dt: float,
+                   eps: float, weight: Optional[Tensor] = None, want_grad: bool = True, want_force: bool = False,
+                   want_iters: bool = False, want_loss: bool = True, skip_flag: Optional[Tensor] = None,
+                   grad_out: Optional[Tensor] = None):
+    """Direct call of ``dpll_elbow_loss_*``.  x, x_plus (B,15); inertia (20), mu_pair (2), half (6), kin (12).
+    Returns (loss (B,) | None, grad (28,) | None, loss_sum (1,), force (B,24) | None, iters (B,) | None)."""
+    dtype = _check_inputs(x, x_plus, inertia, mu_pair, half, kin)
+    x, x_plus = x.contiguous(), x_plus.contiguous()
+    inertia, mu_pair, half, kin = inertia.contiguous(), mu_pair.contiguous(), half.contiguous(), kin.contiguous()
+    if x.dim() != 2 or x.shape[1] != 15 or x_plus.shape != x.shape:
+        raise ValueError(f'expected (B,15) states, got {tuple(x.shape)} / {tuple(x_plus.shape)}')
+    if inertia.numel() != 20 or mu_pair.numel() != 2 or half.numel() != 6 or kin.numel() != 12:
+        raise ValueError('elbow parameters must be inertia (20), mu_pair (2), half (6), kin (12)')
+    B = x.shape[0]
+    dev = x.device
+    loss = torch.empty(B, dtype=dtype, device=dev) if want_loss else None
+    grad = (grad_out if grad_out is not None else torch.empty(28, dtype=dtype, device=dev)) if want_grad else None
+    loss_sum = torch.empty(1, dtype=dtype, device=dev)
+    force = torch.empty((B, 24), dtype=dtype, device=dev) if want_force else None
+    iters = torch.empty(B, dtype=torch.int32, device=dev) if want_iters else None
+    if weight is not None:
+        weight = weight.to(dtype).contiguous()
+    ws = _workspace(dev)
+    fn = getattr(_lib.load(), 'dpll_elbow_loss_' + _SUFFIX[dtype])
+    with torch.cuda.device(dev):
+        rc = fn(_ptr(x), _ptr(x_plus), _ptr(weight), _ptr(inertia), _ptr(mu_pair), _ptr(half), _ptr(kin), dt, eps, B,
+                _ptr(loss), _ptr(force), _ptr(iters), _ptr(grad), _ptr(loss_sum), _ptr(skip_flag), _ptr(ws), ws.numel(),
+                _stream())
+    _lib.check(rc, 'dpll_elbow_loss')
+    return loss, grad, loss_sum, force, iters
+
+
+class ElbowContactNetsLoss(torch.autograd.Function):
+    """ContactNets loss of the elbow (floating base + hinge, two boxes); differentiable w.r.t. the
+    callable-level parameters (two inertia 10-vectors, two pair frictions, two half-length triples).
+    Same fused-backward protocol as :class:`CubeContactNetsLoss`."""
+
+    @staticmethod
+    def forward(ctx, x, x_plus, inertia, mu_pair, half, kin, dt, eps):
+        need = any(ctx.needs_input_grad[2:5])
+        loss, grad, _, _, _ = elbow_loss_raw(x, x_plus, inertia, mu_pair, half, kin, dt, eps, want_grad=need)
+        ctx.dt, ctx.eps = dt, eps
+        ctx.shapes = (inertia.shape, mu_pair.shape, half.shape)
+        if need:
+            ctx.save_for_backward(grad, x, x_plus, inertia, mu_pair, half, kin)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        grad, x, x_plus, inertia, mu_pair, half, kin = ctx.saved_tensors
+        if grad_loss.numel() == 0:
+            g = torch.zeros_like(grad)
+        elif grad_loss.dim() == 1 and grad_loss.stride(0) == 0:
+            g = grad * grad_loss[0]
+        else:
+            grad_loss = grad_loss.contiguous()
+            lo, hi = torch.aminmax(grad_loss)
+            uniform = lo == hi
+            gw = torch.zeros_like(grad)
+            elbow_loss_raw(x, x_plus, inertia, mu_pair, half, kin, ctx.dt, ctx.eps, weight=grad_loss, want_grad=True,
+                           want_loss=False, skip_flag=uniform.to(torch.int32), grad_out=gw)
+            g = torch.where(uniform, grad * lo, gw)
+        s_in, s_mu, s_h = ctx.shapes
+        return (None, None, g[0:20].reshape(s_in), g[20:22].reshape(s_mu), g[22:28].reshape(s_h), None, None, None)
+
+
+def elbow_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, kin: Tensor, dt: float, steps: int,
+                  eps: float = 1e-4, want_force: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+    """(B,15) -> trajectory (B, steps+1, 15) through ``dpll_elbow_rollout_*`` (no autograd)."""
+    dtype = _check_inputs(x0, inertia, mu_pair, half, kin)
+    x0 = x0.contiguous()
+    if x0.dim() != 2 or x0.shape[1] != 15:
+        raise ValueError(f'expected (B,15) states, got {tuple(x0.shape)}')
+    B = x0.shape[0]
+    traj = torch.empty((B, steps + 1, 15), dtype=dtype, device=x0.device)
+    force = torch.empty((B, steps, 24), dtype=dtype, device=x0.device) if want_force else None
+    fn = getattr(_lib.load(), 'dpll_elbow_rollout_' + _SUFFIX[dtype])
+    with torch.cuda.device(x0.device):
+        rc = fn(_ptr(x0), _ptr(inertia.contiguous()), _ptr(mu_pair.contiguous()), _ptr(half.contiguous()),
+                _ptr(kin.contiguous()), dt, eps, B, steps, _ptr(traj), _ptr(force), None, _stream())
+    _lib.check(rc, 'dpll_elbow_rollout')
+    return traj, force
+
+
 def fma_peak(dtype: torch.dtype, device: torch.device, blocks: int, iters: int) -> float:
     """Measured FMA throughput (FLOP/s) of the CUDA cores for ``dtype`` -- roofline denominator."""
     out = torch.empty(blocks * 256, dtype=dtype, device=device)

@@ -44,6 +44,10 @@ extern "C" {
 #define DPLL_CUBE_NX 13
 #define DPLL_CUBE_NC 4
 #define DPLL_CUBE_NPARAM 14
+#define DPLL_ELBOW_NX 15
+#define DPLL_ELBOW_NC 8
+#define DPLL_ELBOW_NPARAM 28
+#define DPLL_ELBOW_NKIN 12
 
 /* Library/ABI version (major*100 + minor). */
 int dpll_version(void);
@@ -134,6 +138,35 @@ int dpll_cube_rollout_f64(const double* x0, const double* inertia, const double*
 int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu_pair,
                           const float* half, float dt, float eps, int64_t B, int32_t steps,
                           float* traj, float* force, int32_t* iters, void* stream);
+
+/*
+ * The same two operations for the elbow (assets/contactnets_elbow.urdf: floating base + one
+ * revolute child, two boxes, 2 x 4 contacts): states (B, 15) = [quat | pos | hinge angle | w_body |
+ * v_world | hinge rate]; parameters inertia[20] (two bodies' 10-vectors), mu_pair[2] (ground-box1,
+ * ground-box2), half[6]; kin[12] = URDF constants [joint origin (3) in link 1 | joint axis (3) | box-1
+ * offset (3) | box-2 offset (3)] (not learnable).  force: (B, 24) = [n_1..n_8, t_1x, t_1y, ...], contacts
+ * of box 1 then box 2, each by ascending vertex index.  grad[28] = [d/d inertia (20) | d/d mu_pair (2) |
+ * d/d half (6)].  Same reference spans as the cube entry points; the articulated M(q), F(q,v) and
+ * geometry Jacobians are the closed forms of what multibody_terms.py:114-157, 267-319 derive
+ * symbolically.  One sample per thread in this version.
+ */
+int dpll_elbow_loss_f64(const double* x, const double* x_plus, const double* weight,
+                        const double* inertia, const double* mu_pair, const double* half,
+                        const double* kin, double dt, double eps, int64_t B, double* loss,
+                        double* force, int32_t* iters, double* grad, double* loss_sum,
+                        const int32_t* skip_flag, void* workspace, size_t workspace_bytes,
+                        void* stream);
+int dpll_elbow_loss_f32(const float* x, const float* x_plus, const float* weight, const float* inertia,
+                        const float* mu_pair, const float* half, const float* kin, float dt, float eps,
+                        int64_t B, float* loss, float* force, int32_t* iters, float* grad,
+                        float* loss_sum, const int32_t* skip_flag, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int dpll_elbow_rollout_f64(const double* x0, const double* inertia, const double* mu_pair,
+                           const double* half, const double* kin, double dt, double eps, int64_t B,
+                           int32_t steps, double* traj, double* force, int32_t* iters, void* stream);
+int dpll_elbow_rollout_f32(const float* x0, const float* inertia, const float* mu_pair,
+                           const float* half, const float* kin, float dt, float eps, int64_t B,
+                           int32_t steps, float* traj, float* force, int32_t* iters, void* stream);
 
 /*
  * FP64 / FP32 FMA throughput micro-benchmark used by bench.py to measure the CUDA-core

@@ -2,6 +2,7 @@
 // container without a GPU.  TEST INFRASTRUCTURE ONLY: nothing in the package loads this.
 #include "../../dair_pll_b200/csrc/cn_cube.cuh"
 #include "../../dair_pll_b200/csrc/cn_params.cuh"
+#include "../../dair_pll_b200/csrc/cn_elbow.cuh"
 #include <cstdint>
 using namespace cn;
 extern "C" {
@@ -67,6 +68,31 @@ int emul_theta_chain_f64(const double* theta, const double* g_inertia, double* i
     double s = 0;
     for (int i = 0; i < 10; ++i) s += g_inertia[i] * dout[i].d;
     grad_theta[t] = s;
+  }
+  return 0;
+}
+int emul_elbow_loss_f64(const double* x, const double* xp, const double* inertia, const double* mu,
+                        const double* half, const double* kin, double dt, double eps, int64_t B, double* loss,
+                        double* force, int32_t* iters, double* grad) {
+  ElbowParams<double> P;
+  elbow_params_init(P, inertia, mu, half, kin, dt, eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  for (int i = 0; i < EL_NPARAM; ++i) if (grad) grad[i] = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    int it;
+    loss[b] = elbow_loss_sample(P, cfg, x + 15 * b, xp + 15 * b, grad, force ? force + 24 * b : nullptr, &it);
+    if (iters) iters[b] = it;
+  }
+  return 0;
+}
+int emul_elbow_step_f64(const double* x, const double* inertia, const double* mu, const double* half,
+                        const double* kin, double dt, double eps, int64_t B, double* xn, double* force, int32_t* iters) {
+  ElbowParams<double> P;
+  elbow_params_init(P, inertia, mu, half, kin, dt, eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  for (int64_t b = 0; b < B; ++b) {
+    int it = elbow_step_sample(P, cfg, x + 15 * b, xn + 15 * b, force ? force + 24 * b : nullptr);
+    if (iters) iters[b] = it;
   }
   return 0;
 }

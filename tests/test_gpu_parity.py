@@ -251,3 +251,49 @@ def test_invalid_arguments_raise():
         ops.cube_loss_raw(x, x, p, p[:1], p[:3], 0.0068, 1e-3)
     with pytest.raises(TypeError):
         ops.cube_loss_raw(x.half(), x.half(), p.half(), p[:1].half(), p[:3].half(), 0.0068, 1e-3)
+
+
+ELBOW_CASES = ['elbow_nominal', 'elbow_perturbed']
+
+
+def _elbow_system(g, assets_dir):
+    s = MultibodyLearnableSystem({'elbow': os.path.join(assets_dir, 'elbow.urdf')}, float(g['dt']))
+    s.load_state_dict({
+        'multibody_terms.lagrangian_terms.inertial_parameters': torch.from_numpy(g['theta']),
+        'multibody_terms.contact_terms.friction_params': torch.from_numpy(g['friction_params']),
+        'multibody_terms.contact_terms.geometries.0.length_params': torch.from_numpy(g['half_lengths'][0]).reshape(1, 3),
+        'multibody_terms.contact_terms.geometries.1.length_params': torch.from_numpy(g['half_lengths'][1]).reshape(1, 3)})
+    return s.to(DEV)
+
+
+@pytest.mark.parametrize('name', ELBOW_CASES)
+def test_elbow_loss_gradients_and_rollout_match_reference_golden(name, assets_dir):
+    """Two-body articulated asset through the module API: losses, parameter gradients (theta of both
+    bodies, three friction parameters, both boxes' lengths), impulses and rollouts at 1e-9."""
+    g = load_golden(name)
+    s = _elbow_system(g, assets_dir)
+    assert s.space.n_x == 15
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    loss = s.contactnets_loss(x, None, xp)
+    loss.mean().backward()
+    l = loss.detach().cpu().numpy()
+    assert np.abs(l - g['loss']).max() < 1e-12
+    assert rel_err(l, g['loss'], 1e-9).max() < 1e-9
+    mt = s.multibody_terms
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), g['grad_friction']) < 1e-9
+    gl = np.stack([mt.contact_terms.geometries[i].length_params.grad.cpu().numpy().reshape(3) for i in range(2)])
+    assert max_rel_to_scale(gl, g['grad_length']) < 1e-9
+    inertia, mu, half, kin = (t.detach() for t in s._elbow_params(torch.float64, torch.device(DEV)))
+    _, _, _, force, iters = ops.elbow_loss_raw(x, xp, inertia, mu, half, kin, float(g['dt']), 1e-3, want_force=True,
+                                               want_iters=True)
+    scale = np.maximum(np.abs(g['force']).max(axis=1, keepdims=True), 1e-6)
+    assert (np.abs(force.cpu().numpy() - g['force']) / scale).max() < 1e-7
+    assert int(iters.max()) <= 60
+    x0 = torch.from_numpy(g['sim_x0']).to(DEV)
+    steps = g['sim_traj'].shape[1] - 1
+    with torch.no_grad():
+        traj, _ = s.simulate(x0.unsqueeze(-2), torch.zeros(x0.shape[0], 1, device=DEV), steps)
+    t = traj.cpu().numpy()
+    assert np.abs(t[:, 1] - g['sim_traj'][:, 1]).max() < 1e-9
+    assert np.abs(t - g['sim_traj']).max() < 1e-6

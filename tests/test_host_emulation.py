@@ -120,3 +120,52 @@ def test_device_parameter_preparation_and_chain_rule():
     lib.emul_theta_chain_f64(dptr(th), dptr(g.numpy().copy()), dptr(inertia), dptr(grad))
     assert np.allclose(inertia, vec.detach().numpy(), rtol=1e-13, atol=1e-18)
     assert np.allclose(grad, theta.grad.numpy().reshape(10), rtol=1e-11, atol=1e-16)
+
+
+ELBOW_KIN = np.array([-0.035, 0.06, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.035, 0.0, 0.0])   # joint origin, axis, box offsets
+
+
+def elbow_kernel_level_params(g):
+    inertia = co.theta_to_inertia_vector(torch.from_numpy(g['theta'])).reshape(20).numpy()
+    mu = np.abs(g['friction_params'])
+    mu_pair = np.array([2 * mu[2] * mu[0] / (mu[2] + mu[0]), 2 * mu[2] * mu[1] / (mu[2] + mu[1])])
+    return inertia, mu_pair, np.abs(g['half_lengths']).reshape(6).copy()
+
+
+def elbow_chain_to_leaves(g, grad28):
+    theta = torch.from_numpy(g['theta']).clone().requires_grad_()
+    fr = torch.from_numpy(g['friction_params']).clone().requires_grad_()
+    ln = torch.from_numpy(g['half_lengths']).clone().requires_grad_()
+    mu = fr.abs()
+    flat = torch.cat((co.theta_to_inertia_vector(theta).reshape(20),
+                      (2 * mu[2] * mu[0] / (mu[2] + mu[0])).reshape(1), (2 * mu[2] * mu[1] / (mu[2] + mu[1])).reshape(1),
+                      ln.abs().reshape(6)))
+    flat.backward(torch.from_numpy(np.asarray(grad28, dtype=np.float64)))
+    return theta.grad.numpy(), fr.grad.numpy(), ln.grad.numpy()
+
+
+@pytest.mark.parametrize('name', ['elbow_nominal', 'elbow_perturbed'])
+def test_elbow_device_math_matches_reference_golden(name):
+    g = load_golden(name)
+    lib = host_emulation_lib()
+    inertia, mu, half = elbow_kernel_level_params(g)
+    x, xp = np.ascontiguousarray(g['x']), np.ascontiguousarray(g['x_plus'])
+    B = x.shape[0]
+    loss, force, iters, grad = np.zeros(B), np.zeros((B, 24)), np.zeros(B, np.int32), np.zeros(28)
+    lib.emul_elbow_loss_f64(dptr(x), dptr(xp), dptr(inertia), dptr(mu), dptr(half), dptr(ELBOW_KIN),
+                            ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-3), ctypes.c_int64(B), dptr(loss),
+                            dptr(force), dptr(iters), dptr(grad))
+    assert np.abs(loss - g['loss']).max() < 1e-12
+    assert rel_err(loss, g['loss'], 1e-9).max() < 1e-9
+    scale = np.maximum(np.abs(g['force']).max(axis=1, keepdims=True), 1e-6)
+    assert (np.abs(force - g['force']) / scale).max() < 1e-7
+    gt, gf, gl = elbow_chain_to_leaves(g, grad / B)
+    assert max_rel_to_scale(gt, g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(gf, g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(gl, g['grad_length']) < 1e-9
+    x0 = np.ascontiguousarray(g['sim_x0'])
+    xn = np.zeros_like(x0)
+    lib.emul_elbow_step_f64(dptr(x0), dptr(inertia), dptr(mu), dptr(half), dptr(ELBOW_KIN),
+                            ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-4), ctypes.c_int64(x0.shape[0]),
+                            dptr(xn), None, None)
+    assert np.abs(xn - g['sim_traj'][:, 1]).max() < 1e-9
