@@ -205,16 +205,19 @@ CN_HD void elbow_mass_force(const ElbowParams<T>& P, const ElbowKin<T>& K, const
   }
 }
 
-// corners of both boxes: lever arms, hinge columns
+// witness points of both geometries: lever arms, hinge columns.  pts == nullptr: box corners (top-4 of
+// 8, geometry.py:162-202); otherwise pts[24] holds the 4 + 4 witness points in the geometry frames, as
+// produced by the learned support function (DeepSupportConvex.get_vertices, geometry.py:309-325).
 template <typename T>
-CN_HD void elbow_contacts(const ElbowParams<T>& P, ElbowKin<T>& K, ElbowProb<T>& S) {
+CN_HD void elbow_contacts(const ElbowParams<T>& P, ElbowKin<T>& K, ElbowProb<T>& S, const T* pts) {
   for (int b = 0; b < 2; ++b) {
     const T* R = K.R[b];
     const T d[3] = {-R[6], -R[7], -R[8]};
-    K.sel[b] = cube_select_corners(d, P.h[b]);
+    K.sel[b] = pts ? 0u : cube_select_corners(d, P.h[b]);
     for (int c = 0; c < 4; ++c) {
       T p[3], r[3];
-      for (int k = 0; k < 3; ++k) p[k] = P.off[b][k] + sgn_bit<T>(K.sel[b], c, k) * P.h[b][k];
+      for (int k = 0; k < 3; ++k)
+        p[k] = P.off[b][k] + (pts ? pts[3 * (4 * b + c) + k] : sgn_bit<T>(K.sel[b], c, k) * P.h[b][k]);
       rot3(R, p, r);
       const int cc = 4 * b + c;
       if (b == 0) {
@@ -395,7 +398,8 @@ CN_HD void elbow_to_world(const T* R1, const T* v, T* u) {   // state velocity -
 }
 
 template <typename T>
-CN_HD void elbow_loss_prologue(const ElbowParams<T>& P, const T* x, const T* xp, ElbowProb<T>& S, ElbowLossAux<T>& A) {
+CN_HD void elbow_loss_prologue(const ElbowParams<T>& P, const T* x, const T* xp, const T* pts, ElbowProb<T>& S,
+                               ElbowLossAux<T>& A) {
   elbow_kinematics(P, xp, A.K);
   A.pos_z = xp[6];
   T vold[7];
@@ -407,7 +411,7 @@ CN_HD void elbow_loss_prologue(const ElbowParams<T>& P, const T* x, const T* xp,
   chol_factor<T, 7>(A.LM, A.LMinv);
   chol_solve<T, 7>(A.LM, A.LMinv, F, A.acc);
   for (int i = 0; i < 7; ++i) A.dv[i] = A.vp[i] - (vold[i] + P.dt * A.acc[i]);
-  elbow_contacts(P, A.K, S);
+  elbow_contacts(P, A.K, S, pts);
   T pen = T(0);
   for (int c = 0; c < EL_NC; ++c) {
     const T mu = P.mu[c >> 2];
@@ -435,7 +439,7 @@ CN_HD void elbow_loss_prologue(const ElbowParams<T>& P, const T* x, const T* xp,
 // grad layout: [inertia1 10 | inertia2 10 | mu 2 | half1 3 | half2 3]; force_out: [n(8); (tx,ty)(8)]
 template <typename T>
 CN_HD T elbow_loss_epilogue(const ElbowParams<T>& P, const ElbowProb<T>& S, const ElbowLossAux<T>& A, const T* u,
-                            T* grad, T* force_out) {
+                            T* grad, T* force_out, T* grad_pts) {
   T f[24], z[7] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
   T qf = T(0), ff = T(0), fmax = T(0);
   for (int c = 0; c < EL_NC; ++c) {
@@ -456,6 +460,7 @@ CN_HD T elbow_loss_epilogue(const ElbowParams<T>& P, const ElbowProb<T>& S, cons
   }
   if (!(fmax <= T(1e3))) {
     if (force_out) for (int i = 0; i < 24; ++i) force_out[i] = T(0);
+    if (grad_pts) for (int i = 0; i < 24; ++i) grad_pts[i] = T(0);
     return T(0);
   }
   if (force_out)
@@ -548,29 +553,34 @@ CN_HD T elbow_loss_epilogue(const ElbowParams<T>& P, const ElbowProb<T>& S, cons
     cross3(ftB, ObB, p1); cross3(gtB, OvB, p2);
     const T phic = S.rho[3 * c + 2] + A.pos_z;
     const T phibar = (phic > T(0) ? fn : (phic < T(0) ? -fn : T(0))) - T(2) * t_max(-phic, T(0));
-    for (int k = 0; k < 3; ++k)
-      grad[22 + 3 * bi + k] += sgn_bit<T>(A.K.sel[bi], cl, k) * (p1[k] + p2[k] + phibar * R[6 + k]);
+    for (int k = 0; k < 3; ++k) {
+      const T pbar = p1[k] + p2[k] + phibar * R[6 + k];      // d loss / d (witness point, geometry frame)
+      if (grad_pts) grad_pts[3 * c + k] = pbar;
+      else grad[22 + 3 * bi + k] += sgn_bit<T>(A.K.sel[bi], cl, k) * pbar;
+    }
   }
   return loss;
 }
 
 template <typename T>
-CN_HD T elbow_loss_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, const T* x, const T* xp, T* grad,
-                          T* force_out, int* iters_out) {
+CN_HD T elbow_loss_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, const T* x, const T* xp, const T* pts,
+                          T* grad, T* force_out, T* grad_pts, int* iters_out) {
   ElbowProb<T> S;
   ElbowLossAux<T> A;
-  elbow_loss_prologue(P, x, xp, S, A);
+  elbow_loss_prologue(P, x, xp, pts, S, A);
   T u[7] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
   const int it = elbow_solve(P, S, cfg, u);
   if (iters_out) *iters_out = it;
-  return elbow_loss_epilogue(P, S, A, u, grad, force_out);
+  if (!grad && grad_pts) for (int i = 0; i < 24; ++i) grad_pts[i] = T(0);
+  return elbow_loss_epilogue(P, S, A, u, grad, force_out, grad ? grad_pts : (T*)nullptr);
 }
 
 // ---------------------------------------------------------------------------
 // learnable time step
 // ---------------------------------------------------------------------------
 template <typename T>
-CN_HD int elbow_step_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, const T* x, T* xn, T* force_out) {
+CN_HD int elbow_step_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, const T* x, const T* pts, T* xn,
+                            T* force_out) {
   ElbowProb<T> S;
   ElbowKin<T> K;
   elbow_kinematics(P, x, K);
@@ -581,7 +591,7 @@ CN_HD int elbow_step_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, co
   chol_factor<T, 7>(LM, LMinv);
   chol_solve<T, 7>(LM, LMinv, F, acc);
   for (int i = 0; i < 7; ++i) vm[i] = vW[i] + P.dt * acc[i];
-  elbow_contacts(P, K, S);
+  elbow_contacts(P, K, S, pts);
   const T inv_dt = T(1) / P.dt;
   for (int c = 0; c < EL_NC; ++c) {
     const T mu = P.mu[c >> 2];

@@ -430,7 +430,7 @@ __device__ __forceinline__ void load_elbow_params(cn::ElbowParams<T>& P, const I
   T in[20], m[2], h[6], kn[cn::EL_NKIN];
   for (int i = 0; i < 20; ++i) in[i] = T(inertia[i]);
   for (int i = 0; i < 2; ++i) m[i] = T(mu[i]);
-  for (int i = 0; i < 6; ++i) h[i] = T(half[i]);
+  for (int i = 0; i < 6; ++i) h[i] = half ? T(half[i]) : T(0);
   for (int i = 0; i < cn::EL_NKIN; ++i) kn[i] = T(kin[i]);
   cn::elbow_params_init(P, in, m, h, kn, dt, eps);
 }
@@ -439,9 +439,9 @@ template <typename T, typename IO>
 __global__ void __launch_bounds__(kLossThreads)
 elbow_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
                   const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half,
-                  const IO* __restrict__ kin, T dt, T eps, int64_t B, IO* __restrict__ loss, IO* __restrict__ force,
-                  int32_t* __restrict__ iters, T* __restrict__ partials, int want_grad,
-                  const int32_t* __restrict__ skip_flag) {
+                  const IO* __restrict__ kin, const IO* __restrict__ pts, T dt, T eps, int64_t B, IO* __restrict__ loss,
+                  IO* __restrict__ force, IO* __restrict__ grad_pts, int32_t* __restrict__ iters,
+                  T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag) {
   if (skip_flag && *skip_flag) return;
   cn::ElbowParams<T> P;
   load_elbow_params<T, IO>(P, inertia, mu, half, kin, dt, eps);
@@ -450,13 +450,16 @@ elbow_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO*
   for (int i = 0; i < kNAccE; ++i) acc[i] = T(0);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
-    T xs[15], xps[15], gs[DPLL_ELBOW_NPARAM], fo[24];
+    T xs[15], xps[15], gs[DPLL_ELBOW_NPARAM], fo[24], pt[24], gp[24];
     for (int i = 0; i < 15; ++i) { xs[i] = T(x[b * 15 + i]); xps[i] = T(xp[b * 15 + i]); }
+    if (pts) for (int i = 0; i < 24; ++i) pt[i] = T(pts[b * 24 + i]);
     for (int i = 0; i < DPLL_ELBOW_NPARAM; ++i) gs[i] = T(0);
     int it;
-    const T l = cn::elbow_loss_sample<T>(P, cfg, xs, xps, want_grad ? gs : nullptr, force ? fo : nullptr, &it);
+    const T l = cn::elbow_loss_sample<T>(P, cfg, xs, xps, pts ? pt : (const T*)nullptr, want_grad ? gs : (T*)nullptr,
+                                         force ? fo : (T*)nullptr, grad_pts ? gp : (T*)nullptr, &it);
     if (force) for (int i = 0; i < 24; ++i) force[b * 24 + i] = IO(fo[i]);
     const T w = weight ? T(weight[b]) : T(1);
+    if (grad_pts) for (int i = 0; i < 24; ++i) grad_pts[b * 24 + i] = IO(w * gp[i]);
     for (int i = 0; i < DPLL_ELBOW_NPARAM; ++i) acc[i] += w * gs[i];
     if (loss) loss[b] = IO(l);
     acc[DPLL_ELBOW_NPARAM] += l;
@@ -480,19 +483,20 @@ elbow_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO*
 template <typename T, typename IO>
 __global__ void __launch_bounds__(kLossThreads)
 elbow_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, const IO* __restrict__ mu,
-                     const IO* __restrict__ half, const IO* __restrict__ kin, T dt, T eps, int64_t B, int steps,
-                     IO* __restrict__ traj, IO* __restrict__ force, int32_t* __restrict__ iters) {
+                     const IO* __restrict__ half, const IO* __restrict__ kin, const IO* __restrict__ pts, T dt, T eps,
+                     int64_t B, int steps, IO* __restrict__ traj, IO* __restrict__ force, int32_t* __restrict__ iters) {
   cn::ElbowParams<T> P;
   load_elbow_params<T, IO>(P, inertia, mu, half, kin, dt, eps);
   const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
-    T xc[15], xn[15], fo[24];
+    T xc[15], xn[15], fo[24], pt[24];
     IO* out = traj + b * (int64_t)(steps + 1) * 15;
     for (int i = 0; i < 15; ++i) { xc[i] = T(x0[b * 15 + i]); out[i] = IO(xc[i]); }
+    if (pts) for (int i = 0; i < 24; ++i) pt[i] = T(pts[b * 24 + i]);
     int total = 0;
     for (int s = 0; s < steps; ++s) {
-      total += cn::elbow_step_sample<T>(P, cfg, xc, xn, force ? fo : nullptr);
+      total += cn::elbow_step_sample<T>(P, cfg, xc, pts ? pt : (const T*)nullptr, xn, force ? fo : (T*)nullptr);
       if (force) for (int i = 0; i < 24; ++i) force[(b * steps + s) * 24 + i] = IO(fo[i]);
       for (int i = 0; i < 15; ++i) { xc[i] = xn[i]; out[(int64_t)(s + 1) * 15 + i] = IO(xn[i]); }
     }
@@ -502,9 +506,10 @@ elbow_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, 
 
 template <typename T, typename IO>
 int launch_elbow_loss(const IO* x, const IO* xp, const IO* weight, const IO* inertia, const IO* mu, const IO* half,
-                      const IO* kin, T dt, T eps, int64_t B, IO* loss, IO* force, int32_t* iters, IO* grad, IO* loss_sum,
+                      const IO* kin, const IO* pts, T dt, T eps, int64_t B, IO* loss, IO* force, IO* grad_pts,
+                      int32_t* iters, IO* grad, IO* loss_sum,
                       const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
-  if (B < 0 || !inertia || !mu || !half || !kin) return DPLL_EINVAL;
+  if (B < 0 || !inertia || !mu || (!half && !pts) || !kin || (grad_pts && (!pts || !grad))) return DPLL_EINVAL;
   if (B > 0 && (!x || !xp)) return DPLL_EINVAL;
   const bool want_red = grad || loss_sum;
   if (want_red && (!workspace || workspace_bytes < dpll_workspace_bytes())) return DPLL_EWORKSPACE;
@@ -519,8 +524,8 @@ int launch_elbow_loss(const IO* x, const IO* xp, const IO* weight, const IO* ine
   int blocks = (int)(need < cap ? need : cap);
   if (blocks < 1) blocks = 1;
   T* partials = want_red ? static_cast<T*>(workspace) : nullptr;
-  elbow_loss_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, kin, dt, eps, B, loss, force,
-                                                           iters, partials, grad ? 1 : 0, skip_flag);
+  elbow_loss_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, kin, pts, dt, eps, B, loss,
+                                                           force, grad_pts, iters, partials, grad ? 1 : 0, skip_flag);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (want_red) {
@@ -533,9 +538,9 @@ int launch_elbow_loss(const IO* x, const IO* xp, const IO* weight, const IO* ine
 }
 
 template <typename T, typename IO>
-int launch_elbow_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO* half, const IO* kin, T dt, T eps,
-                         int64_t B, int32_t steps, IO* traj, IO* force, int32_t* iters, void* stream) {
-  if (B < 0 || steps < 0 || !inertia || !mu || !half || !kin) return DPLL_EINVAL;
+int launch_elbow_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO* half, const IO* kin, const IO* pts,
+                         T dt, T eps, int64_t B, int32_t steps, IO* traj, IO* force, int32_t* iters, void* stream) {
+  if (B < 0 || steps < 0 || !inertia || !mu || (!half && !pts) || !kin || (pts && steps > 1)) return DPLL_EINVAL;
   if (B > 0 && (!x0 || !traj)) return DPLL_EINVAL;
   if (B == 0) return DPLL_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -546,8 +551,8 @@ int launch_elbow_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO
   int64_t need = (B + kLossThreads - 1) / kLossThreads;
   int64_t cap = (int64_t)di.sms * per_sm;
   int blocks = (int)(need < cap ? need : cap);
-  elbow_rollout_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x0, inertia, mu, half, kin, dt, eps, B, steps, traj, force,
-                                                              iters);
+  elbow_rollout_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x0, inertia, mu, half, kin, pts, dt, eps, B, steps, traj,
+                                                              force, iters);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPLL_OK : (int)e;
 }
@@ -716,32 +721,32 @@ int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu
 }
 
 int dpll_elbow_loss_f64(const double* x, const double* x_plus, const double* weight, const double* inertia,
-                        const double* mu_pair, const double* half, const double* kin, double dt, double eps, int64_t B,
-                        double* loss, double* force, int32_t* iters, double* grad, double* loss_sum,
+                        const double* mu_pair, const double* half, const double* kin, const double* pts, double dt, double eps,
+                        int64_t B, double* loss, double* force, double* grad_pts, int32_t* iters, double* grad, double* loss_sum,
                         const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
-  return launch_elbow_loss<double, double>(x, x_plus, weight, inertia, mu_pair, half, kin, dt, eps, B, loss, force, iters,
-                                           grad, loss_sum, skip_flag, workspace, workspace_bytes, stream);
+  return launch_elbow_loss<double, double>(x, x_plus, weight, inertia, mu_pair, half, kin, pts, dt, eps, B, loss, force,
+                                           grad_pts, iters, grad, loss_sum, skip_flag, workspace, workspace_bytes, stream);
 }
 
 int dpll_elbow_loss_f32(const float* x, const float* x_plus, const float* weight, const float* inertia,
-                        const float* mu_pair, const float* half, const float* kin, float dt, float eps, int64_t B,
-                        float* loss, float* force, int32_t* iters, float* grad, float* loss_sum,
+                        const float* mu_pair, const float* half, const float* kin, const float* pts, float dt, float eps,
+                        int64_t B, float* loss, float* force, float* grad_pts, int32_t* iters, float* grad, float* loss_sum,
                         const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
-  return launch_elbow_loss<double, float>(x, x_plus, weight, inertia, mu_pair, half, kin, (double)dt, (double)eps, B, loss,
-                                          force, iters, grad, loss_sum, skip_flag, workspace, workspace_bytes, stream);
+  return launch_elbow_loss<double, float>(x, x_plus, weight, inertia, mu_pair, half, kin, pts, (double)dt, (double)eps, B,
+                                          loss, force, grad_pts, iters, grad, loss_sum, skip_flag, workspace, workspace_bytes, stream);
 }
 
 int dpll_elbow_rollout_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,
-                           const double* kin, double dt, double eps, int64_t B, int32_t steps, double* traj,
+                           const double* kin, const double* pts, double dt, double eps, int64_t B, int32_t steps, double* traj,
                            double* force, int32_t* iters, void* stream) {
-  return launch_elbow_rollout<double, double>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, force, iters,
+  return launch_elbow_rollout<double, double>(x0, inertia, mu_pair, half, kin, pts, dt, eps, B, steps, traj, force, iters,
                                               stream);
 }
 
 int dpll_elbow_rollout_f32(const float* x0, const float* inertia, const float* mu_pair, const float* half,
-                           const float* kin, float dt, float eps, int64_t B, int32_t steps, float* traj, float* force,
+                           const float* kin, const float* pts, float dt, float eps, int64_t B, int32_t steps, float* traj, float* force,
                            int32_t* iters, void* stream) {
-  return launch_elbow_rollout<double, float>(x0, inertia, mu_pair, half, kin, (double)dt, (double)eps, B, steps, traj,
+  return launch_elbow_rollout<double, float>(x0, inertia, mu_pair, half, kin, pts, (double)dt, (double)eps, B, steps, traj,
                                              force, iters, stream);
 }
 

@@ -1,0 +1,88 @@
+"""Homogeneous input-convex support-function network (learned convex geometry).
+
+Mirror of ``dair_pll/deep_support_function.py:125-266`` (``HomogeneousICNN``): same parameters
+(``hidden_weights`` / ``input_weights`` ParameterLists, ``output_weight``), same initialisation
+distributions, same ``forward`` semantics -- the support point of the shape in direction d is the
+input-Jacobian of f(d) = |w_out| . s(|W_h|^T s(W_d0^T d) + W_d1^T d), s = LeakyReLU(0.5), evaluated by
+the hand-written Jacobian recursion of ``:238-266``.
+
+Device path: :class:`ICNNSupport` is a ``torch.autograd.Function`` with an explicit forward and
+backward.  The work is GEMM-shaped with weights shared by the whole batch -- two
+(D x W x W) products forward, two backward -- and runs on cuBLAS DGEMM through ``torch.matmul``;
+only the activation masks are kept between the passes (no autograd graph of elementwise ops).
+A hand-written FP64 GEMM for this layer is future work; FP64 tensor cores on B200
+have the same peak as the CUDA cores, so the library GEMM is already the right roofline.
+Mesh extraction (``extract_mesh`` / ``extract_obj``, :19-122) is logging/export code and stays
+with the reference.  Depth is fixed at 2 (the reference's default, ``geometry.py:50``).
+"""
+import math
+from typing import List, Tuple
+
+import torch
+from torch import Tensor
+from torch.nn import Module, Parameter, ParameterList
+
+
+class ICNNSupport(torch.autograd.Function):
+    """p (D,3) = d f / d direction for directions d (D,3); differentiable w.r.t. the four weights."""
+
+    @staticmethod
+    def forward(ctx, d, Wd0, Wd1, Wh, wout, slope):
+        Wh_a, wo = Wh.abs(), wout.abs()
+        lin0 = d @ Wd0
+        m0 = torch.where(lin0 > 0, 1.0, slope).to(d.dtype)
+        lin1 = (lin0 * m0) @ Wh_a + d @ Wd1
+        m1 = torch.where(lin1 > 0, 1.0, slope).to(d.dtype)
+        a1 = wo * m1
+        a0 = (a1 @ Wh_a.t()) * m0
+        p = a1 @ Wd1.t() + a0 @ Wd0.t()
+        ctx.save_for_backward(Wd0, Wd1, Wh, wout, m0, a1, a0, m1)
+        return p
+
+    @staticmethod
+    def backward(ctx, gp):
+        Wd0, Wd1, Wh, wout, m0, a1, a0, m1 = ctx.saved_tensors
+        gp = gp.contiguous()
+        Wh_a = Wh.abs()
+        gWd1 = gp.t() @ a1
+        gWd0 = gp.t() @ a0
+        t = (gp @ Wd0) * m0                       # adjoint of (a1 |W_h|^T), masks are constants
+        ga1 = gp @ Wd1 + t @ Wh_a
+        gWh = torch.sign(Wh) * (t.t() @ a1)
+        gwout = torch.sign(wout) * (ga1 * m1).sum(0)
+        return None, gWd0, gWd1, gWh, gwout, None
+
+
+class HomogeneousICNN(Module):
+    """Positively homogeneous ICNN; ``forward(directions)`` returns support points (*, 3)."""
+
+    def __init__(self, depth: int, width: int, negative_slope: float = 0.5, scale=1.0) -> None:
+        assert 0.0 <= negative_slope < 1.0
+        if depth != 2:
+            raise NotImplementedError('the device path implements the reference default depth = 2')
+        super().__init__()
+        # same distributions as deep_support_function.py:166-186 (values are RNG dependent)
+        scale_hidden = 2 * (2.0 / (1 + negative_slope ** 2)) ** 0.5 / width
+        hidden = [Parameter(2 * (torch.rand((width, width), dtype=torch.float64) - 0.5) * scale_hidden)]
+        inputs = []
+        for layer in range(depth):
+            w = torch.empty((3, width), dtype=torch.float64)
+            torch.nn.init.kaiming_uniform_(w)
+            if layer > 0:
+                w = w * 2 ** (-0.5)
+            inputs.append(Parameter(w))
+        scale_out = float(scale) * 2 * (2.0 / (width * (1 + negative_slope ** 2))) ** 0.5
+        self.hidden_weights = ParameterList(hidden)
+        self.input_weights = ParameterList(inputs)
+        self.output_weight = Parameter(2 * (torch.rand(width, dtype=torch.float64) - 0.5) * scale_out)
+        self.negative_slope = negative_slope
+
+    def abs_weights(self) -> Tuple[List[Tensor], Tensor]:
+        return [w.abs() for w in self.hidden_weights], self.output_weight.abs()
+
+    def forward(self, directions: Tensor) -> Tensor:
+        shape = directions.shape
+        dt = directions.dtype
+        p = ICNNSupport.apply(directions.reshape(-1, 3), self.input_weights[0].to(dt), self.input_weights[1].to(dt),
+                              self.hidden_weights[0].to(dt), self.output_weight.to(dt), self.negative_slope)
+        return p.reshape(shape)

@@ -3,7 +3,8 @@
 The collision maths itself (top-k support points :162-202, plane-convex collision :553-582)
 runs inside the CUDA kernels; these modules own the ``nn.Parameter`` s with the reference's
 names and shapes so checkpoints interchange (``Box.length_params`` (1,3) :375-397).
-Polygon, Sphere and mesh-mesh collision are not reached by any configuration of the
+``DeepSupportConvex`` (:255-364) owns the learned support-function network and the fixed direction
+perturbations.  Polygon, Sphere and mesh-mesh collision are not reached by any configuration of the
 hot path and are not provided.
 """
 from typing import Dict
@@ -11,6 +12,8 @@ from typing import Dict
 import torch
 from torch import Tensor
 from torch.nn import Module, Parameter
+
+from dair_pll_b200.deep_support_function import HomogeneousICNN
 
 _TOTAL_ORDERING = ['Plane', 'Polygon', 'Box', 'Sphere', 'DeepSupportConvex']  # geometry.py:46
 
@@ -49,3 +52,30 @@ class Box(CollisionGeometry):
 
     def scalars(self) -> Dict[str, float]:
         return {f'len_{ax}': 2 * v.item() for ax, v in zip('xyz', self.get_half_lengths().reshape(-1))}
+
+
+class DeepSupportConvex(CollisionGeometry):
+    """Convex shape represented by its learned support function (geometry.py:255-325): the witness
+    points against a plane are the network's support points in ``n_query`` directions -- the support
+    direction itself plus ``n_query - 1`` randomly perturbed copies, fixed at construction."""
+
+    def __init__(self, vertices: Tensor, n_query: int = 4, depth: int = 2, width: int = 256,
+                 perturbation: float = 0.4) -> None:
+        super().__init__()
+        self.n_query = n_query
+        vertices = vertices.to(torch.float64)
+        length_scale = (vertices.max(dim=0).values - vertices.min(dim=0).values).norm() / 2
+        self.network = HomogeneousICNN(depth, width, scale=length_scale.item())
+        # plain attribute in the reference (not in state_dict); a non-persistent buffer follows .to(device)
+        self.register_buffer('perturbations', torch.cat((
+            torch.zeros((1, 3), dtype=torch.float64),
+            perturbation * (torch.rand((n_query - 1, 3), dtype=torch.float64) - 0.5))), persistent=False)
+
+    def get_vertices(self, directions: Tensor) -> Tensor:
+        """(*, 3) support directions -> (*, n_query, 3) support points (geometry.py:309-325)."""
+        perturbed = directions.unsqueeze(-2) + self.perturbations.to(directions.dtype)
+        perturbed = perturbed / perturbed.norm(dim=-1, keepdim=True)
+        return self.network(perturbed)
+
+    def scalars(self) -> Dict[str, float]:
+        return {}

@@ -71,7 +71,23 @@ class MultibodyLearnableSystem(System):
         joint = spec.joints[0]
         kin = torch.tensor([*joint.origin, *joint.axis, *spec.geometries[0].offset, *spec.geometries[1].offset],
                            dtype=dtype, device=device)
-        return inertia.reshape(20), mu.reshape(2), torch.cat(half), kin
+        return inertia.reshape(20), mu.reshape(2), (torch.cat(half) if half else None), kin
+
+    def _elbow_witness_points(self, q: Tensor) -> Tensor:
+        """(B, 8) configurations -> (B, 8, 3) witness points of the two learned geometries against the
+        ground: support direction of geometry i = minus the third row of its world rotation
+        (geometry.py:560-567), then ``DeepSupportConvex.get_vertices`` (:309-325)."""
+        spec = self.multibody_terms.spec
+        w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        s = 2.0 / (w * w + x * x + y * y + z * z)
+        row = torch.stack((s * (x * z - w * y), s * (y * z + w * x), 1 - s * (x * x + y * y)), -1)   # R1[2, :]
+        axis = torch.tensor(spec.joints[0].axis, dtype=q.dtype, device=q.device)
+        th = q[:, 7:8]
+        # third row of R2 = R1 Rot(axis, th):  r Rot = r cos + (r x a) sin + a (a.r)(1 - cos)
+        row2 = row * torch.cos(th) + torch.linalg.cross(row, axis.expand_as(row)) * torch.sin(th) \
+            + axis * (row @ axis)[:, None] * (1 - torch.cos(th))
+        geoms = self.multibody_terms.contact_terms.geometries
+        return torch.cat((geoms[0].get_vertices(-row), geoms[1].get_vertices(-row2)), -2)
 
     # -- ContactNets loss --------------------------------------------------
     def contactnets_loss(self, x: Tensor, u: Tensor, x_plus: Tensor, loss_pool=None) -> Tensor:
@@ -88,8 +104,12 @@ class MultibodyLearnableSystem(System):
                 ct.geometries[0].length_params.to(x.dtype), float(self.dt), LOSS_EPS)
         elif self._kind() == 'elbow':
             inertia, mu, half, kin = self._elbow_params(x.dtype, x.device)
-            loss = ops.ElbowContactNetsLoss.apply(self._flat(x), self._flat(x_plus), inertia, mu, half, kin,
-                                                  float(self.dt), LOSS_EPS)
+            xf, xpf = self._flat(x), self._flat(x_plus)
+            if half is None:      # learned geometry: witness points from the support-function networks
+                pts = self._elbow_witness_points(xpf[:, :8])
+                loss = ops.ElbowContactNetsLossPts.apply(xf, xpf, inertia, mu, pts, kin, float(self.dt), LOSS_EPS)
+            else:
+                loss = ops.ElbowContactNetsLoss.apply(xf, xpf, inertia, mu, half, kin, float(self.dt), LOSS_EPS)
         else:
             raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r}')
         return loss.reshape(batch)
@@ -104,8 +124,20 @@ class MultibodyLearnableSystem(System):
                                        float(self.dt), steps, STEP_EPS)
         elif self._kind() == 'elbow':
             inertia, mu, half, kin = self._elbow_params(x_0.dtype, x_0.device)
-            traj, _ = ops.elbow_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(), kin,
-                                        float(self.dt), steps, STEP_EPS)
+            if half is None:
+                # learned geometry: witness points depend on the state, so the time loop stays on the
+                # host and every step is [support networks -> one-step kernel]
+                with torch.no_grad():
+                    xs = [self._flat(x_0)]
+                    for _ in range(steps):
+                        pts = self._elbow_witness_points(xs[-1][:, :8])
+                        one, _ = ops.elbow_rollout(xs[-1], inertia.detach(), mu.detach(), None, kin, float(self.dt), 1,
+                                                   STEP_EPS, pts=pts)
+                        xs.append(one[:, 1])
+                    traj = torch.stack(xs, 1)
+            else:
+                traj, _ = ops.elbow_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(), kin,
+                                            float(self.dt), steps, STEP_EPS)
         else:
             raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r}')
         return traj.reshape(batch + (steps + 1, self.space.n_x))

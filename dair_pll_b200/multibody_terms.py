@@ -15,7 +15,7 @@ import torch
 from torch import Tensor
 from torch.nn import Module, ModuleList, Parameter
 
-from dair_pll_b200.geometry import Box, Plane
+from dair_pll_b200.geometry import Box, DeepSupportConvex, Plane
 from dair_pll_b200.inertia import InertialParameterConverter
 from dair_pll_b200.system_spec import SystemSpec
 
@@ -48,8 +48,10 @@ class ContactTerms(Module):
                 geoms.append(Box(torch.tensor(g.half_lengths, dtype=torch.float64), 4))
             elif g.kind == 'plane':
                 geoms.append(Plane())
+            elif g.kind == 'mesh':
+                geoms.append(DeepSupportConvex(g.mesh_vertices()))
             else:
-                raise NotImplementedError(f'geometry kind {g.kind!r} (mesh support: DeepSupportConvex)')
+                raise NotImplementedError(f'geometry kind {g.kind!r}')
         self.geometries = ModuleList(geoms)
         self.friction_params = Parameter(torch.tensor([g.mu for g in spec.geometries], dtype=torch.float64),
                                          requires_grad=True)
@@ -68,8 +70,11 @@ class ContactTerms(Module):
         return 2 * mu_a * mu_b / (mu_a + mu_b)
 
     def half_lengths(self) -> List[Tensor]:
-        """|length_params| (3,) of each pair's body geometry, in pair order."""
+        """|length_params| (3,) of each pair's body geometry, in pair order (boxes only)."""
         return [self.geometries[int(b)].get_half_lengths().reshape(3) for b in self.collision_candidates[1]]
+
+    def has_learned_geometry(self) -> bool:
+        return any(isinstance(g, DeepSupportConvex) for g in self.geometries)
 
 
 class MultibodyTerms(Module):
@@ -89,6 +94,8 @@ class MultibodyTerms(Module):
         """Callable-level parameters in the kernels' dtype, differentiable w.r.t. the leaves."""
         inertia = self.lagrangian_terms.inertia_vector().to(dtype)
         mu = self.contact_terms.pair_friction().to(dtype)
+        if self.contact_terms.has_learned_geometry():
+            return inertia, mu, []
         half = [h.to(dtype) for h in self.contact_terms.half_lengths()]
         return inertia, mu, half
 

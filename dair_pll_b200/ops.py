@@ -208,19 +208,28 @@ def cube_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, dt:
     return traj, force
 
 
-def elbow_loss_raw(x: Tensor, x_plus: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, kin: Tensor, dt: float,
-                   eps: float, weight: Optional[Tensor] = None, want_grad: bool = True, want_force: bool = False,
-                   want_iters: bool = False, want_loss: bool = True, skip_flag: Optional[Tensor] = None,
-                   grad_out: Optional[Tensor] = None):
-    """Direct call of ``dpll_elbow_loss_*``.  x, x_plus (B,15); inertia (20), mu_pair (2), half (6), kin (12).
-    Returns (loss (B,) | None, grad (28,) | None, loss_sum (1,), force (B,24) | None, iters (B,) | None)."""
-    dtype = _check_inputs(x, x_plus, inertia, mu_pair, half, kin)
+def elbow_loss_raw(x: Tensor, x_plus: Tensor, inertia: Tensor, mu_pair: Tensor, half: Optional[Tensor], kin: Tensor,
+                   dt: float, eps: float, weight: Optional[Tensor] = None, want_grad: bool = True,
+                   want_force: bool = False, want_iters: bool = False, want_loss: bool = True,
+                   skip_flag: Optional[Tensor] = None, grad_out: Optional[Tensor] = None,
+                   pts: Optional[Tensor] = None, want_grad_pts: bool = False):
+    """Direct call of ``dpll_elbow_loss_*``.  x, x_plus (B,15); inertia (20), mu_pair (2), half (6) or
+    witness points pts (B,8,3), kin (12).  Returns (loss (B,) | None, grad (28,) | None, loss_sum (1,),
+    force (B,24) | None, iters (B,) | None[, grad_pts (B,8,3)])."""
+    dtype = _check_inputs(x, x_plus, inertia, mu_pair, kin, *([half] if half is not None else []),
+                          *([pts] if pts is not None else []))
     x, x_plus = x.contiguous(), x_plus.contiguous()
-    inertia, mu_pair, half, kin = inertia.contiguous(), mu_pair.contiguous(), half.contiguous(), kin.contiguous()
+    inertia, mu_pair, kin = inertia.contiguous(), mu_pair.contiguous(), kin.contiguous()
+    half = half.contiguous() if half is not None else None
+    pts = pts.contiguous() if pts is not None else None
     if x.dim() != 2 or x.shape[1] != 15 or x_plus.shape != x.shape:
         raise ValueError(f'expected (B,15) states, got {tuple(x.shape)} / {tuple(x_plus.shape)}')
-    if inertia.numel() != 20 or mu_pair.numel() != 2 or half.numel() != 6 or kin.numel() != 12:
+    if inertia.numel() != 20 or mu_pair.numel() != 2 or kin.numel() != 12 or (half is not None and half.numel() != 6):
         raise ValueError('elbow parameters must be inertia (20), mu_pair (2), half (6), kin (12)')
+    if half is None and pts is None:
+        raise ValueError('either half lengths (boxes) or witness points (learned geometry) are required')
+    if pts is not None and tuple(pts.shape) != (x.shape[0], 8, 3):
+        raise ValueError(f'pts must be (B,8,3), got {tuple(pts.shape)}')
     B = x.shape[0]
     dev = x.device
     loss = torch.empty(B, dtype=dtype, device=dev) if want_loss else None
@@ -231,12 +240,15 @@ def elbow_loss_raw(x: Tensor, x_plus: Tensor, inertia: Tensor, mu_pair: Tensor, 
     if weight is not None:
         weight = weight.to(dtype).contiguous()
     ws = _workspace(dev)
+    grad_pts = torch.zeros((B, 8, 3), dtype=dtype, device=dev) if (want_grad_pts and want_grad) else None
     fn = getattr(_lib.load(), 'dpll_elbow_loss_' + _SUFFIX[dtype])
     with torch.cuda.device(dev):
-        rc = fn(_ptr(x), _ptr(x_plus), _ptr(weight), _ptr(inertia), _ptr(mu_pair), _ptr(half), _ptr(kin), dt, eps, B,
-                _ptr(loss), _ptr(force), _ptr(iters), _ptr(grad), _ptr(loss_sum), _ptr(skip_flag), _ptr(ws), ws.numel(),
-                _stream())
+        rc = fn(_ptr(x), _ptr(x_plus), _ptr(weight), _ptr(inertia), _ptr(mu_pair), _ptr(half), _ptr(kin), _ptr(pts),
+                dt, eps, B, _ptr(loss), _ptr(force), _ptr(grad_pts), _ptr(iters), _ptr(grad), _ptr(loss_sum),
+                _ptr(skip_flag), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, 'dpll_elbow_loss')
+    if want_grad_pts:
+        return loss, grad, loss_sum, force, iters, grad_pts
     return loss, grad, loss_sum, force, iters
 
 
@@ -274,10 +286,50 @@ class ElbowContactNetsLoss(torch.autograd.Function):
         return (None, None, g[0:20].reshape(s_in), g[20:22].reshape(s_mu), g[22:28].reshape(s_h), None, None, None)
 
 
-def elbow_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, kin: Tensor, dt: float, steps: int,
-                  eps: float = 1e-4, want_force: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
-    """(B,15) -> trajectory (B, steps+1, 15) through ``dpll_elbow_rollout_*`` (no autograd)."""
-    dtype = _check_inputs(x0, inertia, mu_pair, half, kin)
+class ElbowContactNetsLossPts(torch.autograd.Function):
+    """ContactNets loss of the elbow with LEARNED geometry: the 4 + 4 witness points ``pts`` (B,8,3) come
+    from the support-function networks (``DeepSupportConvex.get_vertices``).  Differentiable w.r.t.
+    inertia (20), mu_pair (2) and ``pts``; the per-sample d loss_b / d pts[b] is produced by the forward
+    launch and scaled by the upstream gradient (exact for any upstream weights)."""
+
+    @staticmethod
+    def forward(ctx, x, x_plus, inertia, mu_pair, pts, kin, dt, eps):
+        need = any(ctx.needs_input_grad[2:5])
+        out = elbow_loss_raw(x, x_plus, inertia, mu_pair, None, kin, dt, eps, want_grad=need, pts=pts,
+                             want_grad_pts=True)
+        loss, grad, gpts = out[0], out[1], out[5]
+        ctx.dt, ctx.eps = dt, eps
+        ctx.shapes = (inertia.shape, mu_pair.shape)
+        if need:
+            ctx.save_for_backward(grad, gpts, x, x_plus, inertia, mu_pair, pts, kin)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        grad, gpts, x, x_plus, inertia, mu_pair, pts, kin = ctx.saved_tensors
+        if grad_loss.numel() == 0:
+            g = torch.zeros_like(grad)
+        elif grad_loss.dim() == 1 and grad_loss.stride(0) == 0:
+            g = grad * grad_loss[0]
+        else:
+            grad_loss = grad_loss.contiguous()
+            lo, hi = torch.aminmax(grad_loss)
+            uniform = lo == hi
+            gw = torch.zeros_like(grad)
+            elbow_loss_raw(x, x_plus, inertia, mu_pair, None, kin, ctx.dt, ctx.eps, weight=grad_loss, want_grad=True,
+                           want_loss=False, skip_flag=uniform.to(torch.int32), grad_out=gw, pts=pts)
+            g = torch.where(uniform, grad * lo, gw)
+        s_in, s_mu = ctx.shapes
+        return (None, None, g[0:20].reshape(s_in), g[20:22].reshape(s_mu), gpts * grad_loss.reshape(-1, 1, 1),
+                None, None, None)
+
+
+def elbow_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Optional[Tensor], kin: Tensor, dt: float,
+                  steps: int, eps: float = 1e-4, want_force: bool = False,
+                  pts: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """(B,15) -> trajectory (B, steps+1, 15) through ``dpll_elbow_rollout_*`` (no autograd).  With witness
+    points ``pts`` (B,8,3) of a learned geometry only a single step is allowed."""
+    dtype = _check_inputs(x0, inertia, mu_pair, kin)
     x0 = x0.contiguous()
     if x0.dim() != 2 or x0.shape[1] != 15:
         raise ValueError(f'expected (B,15) states, got {tuple(x0.shape)}')
@@ -286,8 +338,10 @@ def elbow_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, ki
     force = torch.empty((B, steps, 24), dtype=dtype, device=x0.device) if want_force else None
     fn = getattr(_lib.load(), 'dpll_elbow_rollout_' + _SUFFIX[dtype])
     with torch.cuda.device(x0.device):
-        rc = fn(_ptr(x0), _ptr(inertia.contiguous()), _ptr(mu_pair.contiguous()), _ptr(half.contiguous()),
-                _ptr(kin.contiguous()), dt, eps, B, steps, _ptr(traj), _ptr(force), None, _stream())
+        rc = fn(_ptr(x0), _ptr(inertia.contiguous()), _ptr(mu_pair.contiguous()),
+                _ptr(half.contiguous() if half is not None else None), _ptr(kin.contiguous()),
+                _ptr(pts.contiguous() if pts is not None else None), dt, eps, B, steps, _ptr(traj), _ptr(force), None,
+                _stream())
     _lib.check(rc, 'dpll_elbow_rollout')
     return traj, force
 

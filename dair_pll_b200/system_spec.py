@@ -55,6 +55,17 @@ class GeometrySpec:
     mesh_file: Optional[str] = None
     mu: float = 1.0
 
+    def mesh_vertices(self) -> torch.Tensor:
+        """Vertices of the Wavefront .obj (only ``v x y z`` records are needed: the reference uses them
+        for the initial length scale of the support-function network, geometry.py:303-305)."""
+        verts = []
+        with open(self.mesh_file) as fh:
+            for line in fh:
+                parts = line.split()
+                if len(parts) >= 4 and parts[0] == 'v':
+                    verts.append([float(v) for v in parts[1:4]])
+        return torch.tensor(verts, dtype=torch.float64)
+
 
 @dataclass
 class JointSpec:

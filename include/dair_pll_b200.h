@@ -149,24 +149,33 @@ int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu
  * d/d half (6)].  Same reference spans as the cube entry points; the articulated M(q), F(q,v) and
  * geometry Jacobians are the closed forms of what multibody_terms.py:114-157, 267-319 derive
  * symbolically.  One sample per thread in this version.
+ *
+ * Learned (mesh) geometry: `pts` (B, 8, 3), nullable.  When given, the 4 + 4 witness points of the two
+ * geometries (geometry frames) are taken from it instead of the box corners -- they are the outputs of
+ * DeepSupportConvex.get_vertices (geometry.py:309-325; the ICNN of deep_support_function.py:238-266 is
+ * evaluated by the caller) -- `half` may then be NULL, and `grad_pts` (B, 8, 3), nullable, receives
+ * w_b * d loss_b / d pts[b] for the caller's network backward (grad[22..27] stay zero).  The rollout
+ * accepts `pts` only for steps <= 1 (witness points depend on the state).
  */
 int dpll_elbow_loss_f64(const double* x, const double* x_plus, const double* weight,
                         const double* inertia, const double* mu_pair, const double* half,
-                        const double* kin, double dt, double eps, int64_t B, double* loss,
-                        double* force, int32_t* iters, double* grad, double* loss_sum,
-                        const int32_t* skip_flag, void* workspace, size_t workspace_bytes,
-                        void* stream);
-int dpll_elbow_loss_f32(const float* x, const float* x_plus, const float* weight, const float* inertia,
-                        const float* mu_pair, const float* half, const float* kin, float dt, float eps,
-                        int64_t B, float* loss, float* force, int32_t* iters, float* grad,
-                        float* loss_sum, const int32_t* skip_flag, void* workspace,
+                        const double* kin, const double* pts, double dt, double eps, int64_t B,
+                        double* loss, double* force, double* grad_pts, int32_t* iters, double* grad,
+                        double* loss_sum, const int32_t* skip_flag, void* workspace,
                         size_t workspace_bytes, void* stream);
+int dpll_elbow_loss_f32(const float* x, const float* x_plus, const float* weight, const float* inertia,
+                        const float* mu_pair, const float* half, const float* kin, const float* pts,
+                        float dt, float eps, int64_t B, float* loss, float* force, float* grad_pts,
+                        int32_t* iters, float* grad, float* loss_sum, const int32_t* skip_flag,
+                        void* workspace, size_t workspace_bytes, void* stream);
 int dpll_elbow_rollout_f64(const double* x0, const double* inertia, const double* mu_pair,
-                           const double* half, const double* kin, double dt, double eps, int64_t B,
-                           int32_t steps, double* traj, double* force, int32_t* iters, void* stream);
+                           const double* half, const double* kin, const double* pts, double dt,
+                           double eps, int64_t B, int32_t steps, double* traj, double* force,
+                           int32_t* iters, void* stream);
 int dpll_elbow_rollout_f32(const float* x0, const float* inertia, const float* mu_pair,
-                           const float* half, const float* kin, float dt, float eps, int64_t B,
-                           int32_t steps, float* traj, float* force, int32_t* iters, void* stream);
+                           const float* half, const float* kin, const float* pts, float dt, float eps,
+                           int64_t B, int32_t steps, float* traj, float* force, int32_t* iters,
+                           void* stream);
 
 /*
  * FP64 / FP32 FMA throughput micro-benchmark used by bench.py to measure the CUDA-core

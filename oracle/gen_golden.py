@@ -142,6 +142,53 @@ def elbow_case(name, x, x_plus, pi_cm, friction, half, sim_states, rollout_steps
     print(name, 'B', x.shape[0], 'mean loss %.12e' % loss.mean().item(), 'size %.1f KB' % (os.path.getsize(path) / 1e3))
 
 
+def box_vertices(half):
+    return torch.tensor([[sx * half[0], sy * half[1], sz * half[2]] for sx in (-1., 1.) for sy in (-1., 1.)
+                         for sz in (-1., 1.)], dtype=torch.float64)
+
+
+def elbow_mesh_case(name, x, pi_cm, friction, width, sim_n, rollout_steps):
+    """contactnets_elbow_mesh.urdf: both links carry a DeepSupportConvex (learned support function)."""
+    verts = [box_vertices(synthetic_half()) for _ in range(2)]
+    system = ref_shim.build_reference_system('elbow', DT, pi_cm, friction, None, mesh_vertices=verts,
+                                             mesh_width=width, mesh_seed=5)
+    mt = system.multibody_terms
+    u = torch.zeros(x.shape[:-1] + (0,))
+    with torch.no_grad():
+        xn, _ = system.integrator.step(x, torch.zeros(x.shape[0], 1))
+    from dair_pll_b200 import synthetic as syn
+    x_plus = syn.perturb_next_state(xn, seed=31, n_q=8)
+    loss = system.contactnets_loss(x, u, x_plus)
+    loss.mean().backward()
+    out = dict(dt=np.float64(DT), x=x.numpy(), x_plus=x_plus.numpy(), pi_cm=pi_cm.numpy(),
+               friction_params=friction.numpy(), theta=mt.lagrangian_terms.inertial_parameters.detach().numpy(),
+               loss=loss.detach().numpy(),
+               grad_theta=mt.lagrangian_terms.inertial_parameters.grad.numpy(),
+               grad_friction=mt.contact_terms.friction_params.grad.numpy())
+    for gi in range(2):
+        net = mt.contact_terms.geometries[gi].network
+        out[f'net{gi}_Wd0'] = net.input_weights[0].detach().numpy()
+        out[f'net{gi}_Wd1'] = net.input_weights[1].detach().numpy()
+        out[f'net{gi}_Wh'] = net.hidden_weights[0].detach().numpy()
+        out[f'net{gi}_wout'] = net.output_weight.detach().numpy()
+        out[f'net{gi}_perturbations'] = mt.contact_terms.geometries[gi].perturbations.numpy()
+        out[f'net{gi}_grad_Wd0'] = net.input_weights[0].grad.numpy()
+        out[f'net{gi}_grad_Wd1'] = net.input_weights[1].grad.numpy()
+        out[f'net{gi}_grad_Wh'] = net.hidden_weights[0].grad.numpy()
+        out[f'net{gi}_grad_wout'] = net.output_weight.grad.numpy()
+    with torch.no_grad():
+        traj, _ = system.simulate(x[:sim_n].unsqueeze(-2), torch.zeros(sim_n, 1), rollout_steps)
+    out.update(sim_x0=x[:sim_n].numpy(), sim_traj=traj.numpy())
+    path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')
+    np.savez_compressed(path, **out)
+    print(name, 'B', x.shape[0], 'mean loss %.12e' % loss.mean().item(), 'size %.1f KB' % (os.path.getsize(path) / 1e3))
+
+
+def synthetic_half():
+    from dair_pll_b200 import synthetic as syn
+    return syn.ELBOW_HALF
+
+
 def main():
     assert ref_shim.available(), 'needs the reference tree'
     ref_shim.import_reference()
@@ -180,6 +227,9 @@ def main():
             xn, _ = system.integrator.step(xe, torch.zeros(xe.shape[0], 1))
         xpe = synthetic.perturb_next_state(xn, seed=seed + 1, n_q=8)
         elbow_case(name, xe, xpe, pi_e, fr_e, half_e, xe[:48], 4)
+    # (5) elbow with learned (ICNN) geometry, width 64 to keep the fixture small
+    pi_e, fr_e, _ = synthetic.elbow_learnables_perturbed(1)
+    elbow_mesh_case('elbow_mesh_w64', synthetic.elbow_states(192, seed=17), pi_e, fr_e, 64, 32, 3)
 
 
 if __name__ == '__main__':

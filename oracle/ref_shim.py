@@ -66,7 +66,7 @@ def import_reference():
 
 
 def build_reference_system(kind: str, dt: float, pi_cm: torch.Tensor, friction: torch.Tensor,
-                           half_lengths, solver=None):
+                           half_lengths, solver=None, mesh_vertices=None, mesh_width: int = 256, mesh_seed: int = 0):
     """Reference ``MultibodyLearnableSystem`` for ``kind`` in {'cube','elbow'}.
 
     Args:
@@ -102,7 +102,17 @@ def build_reference_system(kind: str, dt: float, pi_cm: torch.Tensor, friction: 
     ct.geometry_translations = calls.geometry_translations
     ct.geometry_spatial_jacobians = calls.geometry_spatial_jacobians
     n_body_geoms = len(tree.geometry_body) - 1
-    geoms = [Box(torch.as_tensor(h, dtype=torch.float64), 4) for h in half_lengths] + [Plane()]
+    if mesh_vertices is not None:
+        # the reference's own DeepSupportConvex (geometry.py:255-325): random ICNN initialisation and
+        # random direction perturbations, made reproducible by seeding
+        from dair_pll.geometry import DeepSupportConvex
+        torch.manual_seed(mesh_seed)
+        geoms = [DeepSupportConvex(torch.as_tensor(v, dtype=torch.float64), width=mesh_width) for v in mesh_vertices] \
+            + [Plane()]
+        for geo in geoms[:-1]:
+            geo.perturbations = geo.perturbations.double()
+    else:
+        geoms = [Box(torch.as_tensor(h, dtype=torch.float64), 4) for h in half_lengths] + [Plane()]
     assert len(geoms) == n_body_geoms + 1
     ct.geometries = ModuleList(geoms)
     ct.friction_params = Parameter(friction.double().clone())

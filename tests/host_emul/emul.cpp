@@ -80,7 +80,8 @@ int emul_elbow_loss_f64(const double* x, const double* xp, const double* inertia
   for (int i = 0; i < EL_NPARAM; ++i) if (grad) grad[i] = 0;
   for (int64_t b = 0; b < B; ++b) {
     int it;
-    loss[b] = elbow_loss_sample(P, cfg, x + 15 * b, xp + 15 * b, grad, force ? force + 24 * b : nullptr, &it);
+    loss[b] = elbow_loss_sample(P, cfg, x + 15 * b, xp + 15 * b, (const double*)nullptr, grad,
+                                force ? force + 24 * b : nullptr, (double*)nullptr, &it);
     if (iters) iters[b] = it;
   }
   return 0;
@@ -91,7 +92,7 @@ int emul_elbow_step_f64(const double* x, const double* inertia, const double* mu
   elbow_params_init(P, inertia, mu, half, kin, dt, eps);
   SolverCfg<double> cfg = default_cfg<double>();
   for (int64_t b = 0; b < B; ++b) {
-    int it = elbow_step_sample(P, cfg, x + 15 * b, xn + 15 * b, force ? force + 24 * b : nullptr);
+    int it = elbow_step_sample(P, cfg, x + 15 * b, (const double*)nullptr, xn + 15 * b, force ? force + 24 * b : nullptr);
     if (iters) iters[b] = it;
   }
   return 0;

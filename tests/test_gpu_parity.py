@@ -297,3 +297,49 @@ def test_elbow_loss_gradients_and_rollout_match_reference_golden(name, assets_di
     t = traj.cpu().numpy()
     assert np.abs(t[:, 1] - g['sim_traj'][:, 1]).max() < 1e-9
     assert np.abs(t - g['sim_traj']).max() < 1e-6
+
+
+def _mesh_system(g, assets_dir, width):
+    from dair_pll_b200.deep_support_function import HomogeneousICNN
+    s = MultibodyLearnableSystem({'elbow': os.path.join(assets_dir, 'elbow_mesh.urdf')}, float(g['dt']))
+    geoms = s.multibody_terms.contact_terms.geometries
+    sd = {'multibody_terms.lagrangian_terms.inertial_parameters': torch.from_numpy(g['theta']),
+          'multibody_terms.contact_terms.friction_params': torch.from_numpy(g['friction_params'])}
+    for gi in range(2):
+        geoms[gi].network = HomogeneousICNN(2, width)
+        geoms[gi].perturbations = torch.from_numpy(g[f'net{gi}_perturbations'])
+        pre = f'multibody_terms.contact_terms.geometries.{gi}.network.'
+        sd.update({pre + 'input_weights.0': torch.from_numpy(g[f'net{gi}_Wd0']),
+                   pre + 'input_weights.1': torch.from_numpy(g[f'net{gi}_Wd1']),
+                   pre + 'hidden_weights.0': torch.from_numpy(g[f'net{gi}_Wh']),
+                   pre + 'output_weight': torch.from_numpy(g[f'net{gi}_wout'])})
+    s.load_state_dict(sd)
+    return s.to(DEV)
+
+
+def test_elbow_learned_geometry_matches_reference_golden(assets_dir):
+    """Elbow with DeepSupportConvex geometry (config 3's system, network width 64 in the fixture): loss,
+    inertia / friction gradients, the gradients of every ICNN weight tensor, and one-step rollouts."""
+    g = load_golden('elbow_mesh_w64')
+    s = _mesh_system(g, assets_dir, 64)
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    loss = s.contactnets_loss(x, None, xp)
+    loss.mean().backward()
+    l = loss.detach().cpu().numpy()
+    assert np.abs(l - g['loss']).max() < 1e-12
+    assert rel_err(l, g['loss'], 1e-9).max() < 1e-9
+    mt = s.multibody_terms
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), g['grad_friction']) < 1e-9
+    for gi in range(2):
+        net = mt.contact_terms.geometries[gi].network
+        for k, p in (('Wd0', net.input_weights[0]), ('Wd1', net.input_weights[1]), ('Wh', net.hidden_weights[0]),
+                     ('wout', net.output_weight)):
+            assert max_rel_to_scale(p.grad.cpu().numpy(), g[f'net{gi}_grad_{k}']) < 1e-9, (gi, k)
+    x0 = torch.from_numpy(g['sim_x0']).to(DEV)
+    steps = g['sim_traj'].shape[1] - 1
+    with torch.no_grad():
+        traj, _ = s.simulate(x0.unsqueeze(-2), torch.zeros(x0.shape[0], 1, device=DEV), steps)
+    t = traj.cpu().numpy()
+    assert np.abs(t[:, 1] - g['sim_traj'][:, 1]).max() < 1e-9
+    assert np.abs(t - g['sim_traj']).max() < 1e-6

@@ -175,3 +175,32 @@ def test_restated_callables_satisfy_the_power_balance(tree, n_q, seed):
     Vdot = (potential(flow(h)) - potential(flow(-h))) / (2 * h)
     power = (v * F).sum(-1) + 0.5 * (v * (Mdot @ v[..., None])[..., 0]).sum(-1) + Vdot
     assert power.abs().max().item() < 1e-7 * (v * F).sum(-1).abs().max().item()
+
+
+def _mesh_oracle_params(g, requires_grad=True):
+    nets = []
+    for gi in range(2):
+        nets.append({k: torch.from_numpy(g[f'net{gi}_{k}']).clone() for k in ('Wd0', 'Wd1', 'Wh', 'wout', 'perturbations')})
+    P = co.OracleParams(torch.from_numpy(g['theta']).clone(), torch.from_numpy(g['friction_params']).clone(), [], nets)
+    if requires_grad:
+        P.requires_grad_()
+    return P
+
+
+def test_elbow_with_learned_geometry_matches_reference_python():
+    """contactnets_elbow_mesh: DeepSupportConvex + HomogeneousICNN witness points (reference code ran the
+    networks); loss, inertia/friction gradients and the gradients of all four weight tensors of both nets."""
+    g = load_golden('elbow_mesh_w64')
+    P = _mesh_oracle_params(g)
+    x, xp = torch.from_numpy(g['x']), torch.from_numpy(g['x_plus'])
+    loss = co.contactnets_loss(ELBOW_CALLS, P, x, xp, float(g['dt']))
+    loss.mean().backward()
+    assert np.abs(loss.detach().numpy() - g['loss']).max() < 1e-13
+    assert max_rel_to_scale(P.inertial_parameters.grad.numpy(), g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(P.friction_params.grad.numpy(), g['grad_friction']) < 1e-9
+    for gi in range(2):
+        for k in ('Wd0', 'Wd1', 'Wh', 'wout'):
+            assert max_rel_to_scale(P.icnn[gi][k].grad.numpy(), g[f'net{gi}_grad_{k}']) < 1e-9, (gi, k)
+    with torch.no_grad():
+        traj = co.simulate(ELBOW_CALLS, P, torch.from_numpy(g['sim_x0']), float(g['dt']), g['sim_traj'].shape[1] - 1)
+    assert np.abs(traj.numpy()[:, 1] - g['sim_traj'][:, 1]).max() < 1e-9
