@@ -171,12 +171,21 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
   int64_t next = lo;
 
   for (int s = lane; s < kWfSlots; s += 32) { pool->q_done[s] = (uint8_t)s; pool->sample[s] = -1; }
-  int n_act = 0, n_done = kWfSlots, n_ls = 0, h_act = 0, h_done = 0, h_ls = 0;
+  int n_act = 0, n_done = kWfSlots, n_ls = 0, h_act = 0, h_done = 0, h_ls = 0, prev_phase = 0;
   __syncwarp();
 
   while (true) {
     int phase;   // 0 = PE, 1 = N, 2 = L
-    if (n_done >= 32) phase = 0;
+    // Drain mode (input exhausted): the remaining samples' Newton chains are the critical path of the
+    // warp, so N and L simply alternate (width no longer matters) and the finished samples are
+    // finalised in full-width PE batches at the very end.
+    const bool drain = next >= hi;
+    if (drain) {
+      if (n_ls > 0 && (n_act == 0 || prev_phase == 1)) phase = 2;
+      else if (n_act > 0) phase = 1;
+      else if (n_done > 0) phase = 0;
+      else break;
+    } else if (n_done >= 32) phase = 0;
     else if (n_act >= 32) phase = 1;
     else if (n_ls >= 32) phase = 2;
     else if (n_act > 0 && n_act >= n_ls && n_act >= n_done) phase = 1;
@@ -294,6 +303,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
       else if (on && more) pool->q_done[(h_done + n_done + __popc(m_keep & lt_mask)) % kWfSlots] = (uint8_t)slot;
       n_act += __popc(m_act); n_done += __popc(m_keep);
     }
+    prev_phase = phase;
     __syncwarp();
   }
 
