@@ -6,10 +6,10 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libdair_pll_b200.so')
-SOURCES = ['cn_kernels.cu']
-HEADERS = ['cn_common.cuh', 'cn_cube.cuh', 'cn_params.cuh', 'cn_elbow.cuh', os.path.join('..', '..', 'include', 'dair_pll_b200.h')]
+SOURCES = ['cn_kernels.cu', 'cn_tangent.cu']
+HEADERS = ['cn_common.cuh', 'cn_cube.cuh', 'cn_params.cuh', 'cn_elbow.cuh', 'cn_dual.cuh', 'cn_cube_tangent.cuh', os.path.join('..', '..', 'include', 'dair_pll_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-shared', '-Xcompiler', '-fPIC']
+              '-Xcompiler', '-fPIC']
 
 
 def _nvcc() -> str:
@@ -31,13 +31,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile ``csrc/*.cu`` into ``dair_pll_b200/libdair_pll_b200.so`` (cross-compiles without a GPU)."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-        ['-o', LIB_PATH] + [os.path.join(CSRC, f) for f in SOURCES]
-    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(proc.stderr)
+    # translation units are compiled in parallel (the dual-number one is slow), then linked
+    objdir = os.path.join(_HERE, 'build')
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace('.cu', '.o'))
+        cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', '-o', obj, os.path.join(CSRC, src)]
+        procs.append((cmd, obj, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    objs = []
+    for cmd, obj, proc in procs:
+        out, err = proc.communicate()
+        if verbose:
+            sys.stderr.write(err)
+        if proc.returncode != 0:
+            raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + out + err)
+        objs.append(obj)
+    link = [_nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB_PATH] + objs
+    proc = subprocess.run(link, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
+        raise RuntimeError('link failed:\n' + ' '.join(link) + '\n' + proc.stdout + proc.stderr)
     return LIB_PATH
 
 

@@ -1,0 +1,43 @@
+// Forward-mode derivative of the learnable time step (the backward of forward_dynamics / sim_step /
+// VelocityIntegrator.step that the reference gets from autograd through sappy,
+// multibody_learnable_system.py:293-304; integrator.py:153-162): the step code of cn_cube.cuh is
+// instantiated on dual numbers (cn_dual.cuh) carrying ONE tangent, and the rollout is run once per
+// direction -- 27 directions:
+//   0..13  callable-level parameters [inertia 10 | mu_pair 1 | half 3],   14..26  the 13 coordinates of x0 --
+// contracting the tangent of every x_s with the upstream gradient on the fly.  One (sample,
+// direction) pair per thread: 27x the forward work, but no tape, constant memory in the number of
+// steps, and parallelism even for the small batches of the prediction loss.
+#pragma once
+#include "cn_cube.cuh"
+#include "cn_dual.cuh"
+
+namespace cn {
+
+constexpr int CUBE_NTAN = 27;
+
+// xbar: upstream gradient w.r.t. traj[1..steps] (steps x 13, row s = step s+1).
+// Returns sum_s xbar_s . d x_s / d (direction `dir`).
+template <typename B>
+CN_HD B cube_rollout_tangent(const B* inertia, const B* mu, const B* half, B dt, B eps, const B* x0, int steps,
+                             const B* xbar, int dir) {
+  typedef DualN<B, 1> D;
+  D din[10], dmu[1], dh[3];
+  for (int i = 0; i < 10; ++i) { din[i] = D(inertia[i]); if (dir == i) din[i].d[0] = B(1); }
+  dmu[0] = D(mu[0]); if (dir == 10) dmu[0].d[0] = B(1);
+  for (int i = 0; i < 3; ++i) { dh[i] = D(half[i]); if (dir == 11 + i) dh[i].d[0] = B(1); }
+  CubeParams<D> P;
+  cube_params_init<D>(P, din, dmu, dh, D(dt), D(eps));
+  const SolverCfg<B> c0 = default_cfg<B>();
+  SolverCfg<D> cfg;
+  cfg.tol_rel = D(c0.tol_rel); cfg.tol_stall = D(c0.tol_stall); cfg.ls_c = D(c0.ls_c); cfg.max_iter = c0.max_iter;
+  D x[13], xn[13];
+  for (int i = 0; i < 13; ++i) { x[i] = D(x0[i]); if (dir == 14 + i) x[i].d[0] = B(1); }
+  B g = B(0);
+  for (int s = 0; s < steps; ++s) {
+    cube_step_sample<D>(P, cfg, x, xn, (D*)nullptr);
+    for (int i = 0; i < 13; ++i) { g += xbar[s * 13 + i] * xn[i].d[0]; x[i] = xn[i]; }
+  }
+  return g;
+}
+
+}  // namespace cn

@@ -120,8 +120,12 @@ class MultibodyLearnableSystem(System):
         batch = x_0.shape[:-1]
         if self._kind() == 'cube':
             inertia, mu, half = self._cube_params(x_0.dtype)
-            traj, _ = ops.cube_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(),
-                                       float(self.dt), steps, STEP_EPS)
+            if torch.is_grad_enabled() and (x_0.requires_grad or inertia.requires_grad):
+                # differentiable path (prediction loss): backward through every step's QP
+                traj = ops.CubeRollout.apply(self._flat(x_0), inertia, mu, half, float(self.dt), steps, STEP_EPS)
+            else:
+                traj, _ = ops.cube_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(),
+                                           float(self.dt), steps, STEP_EPS)
         elif self._kind() == 'elbow':
             inertia, mu, half, kin = self._elbow_params(x_0.dtype, x_0.device)
             if half is None:

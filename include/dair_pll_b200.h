@@ -140,6 +140,20 @@ int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu
                           float* traj, float* force, int32_t* iters, void* stream);
 
 /*
+ * Backward of dpll_cube_rollout_f64 (the gradient the reference obtains by autograd through
+ * forward_dynamics and sappy's backward, multibody_learnable_system.py:293-304; used by the
+ * prediction loss, experiment.py:230-248, 292-320): given the upstream gradient xbar (B, steps, 13)
+ * w.r.t. traj[:, 1:], returns PER-SAMPLE gradients
+ *   gparams (B, 14) w.r.t. [inertia 10 | mu_pair 1 | half 3]   and   gx0 (B, 13) w.r.t. x0
+ * (sum gparams over B for the parameter gradient; add xbar of traj[:, 0] to gx0 yourself).
+ * Implemented by forward-mode differentiation of the step code (27 tangent directions); exact
+ * implicit differentiation of the QP at the converged solution.
+ */
+int dpll_cube_rollout_grad_f64(const double* x0, const double* inertia, const double* mu_pair,
+                               const double* half, double dt, double eps, int64_t B, int32_t steps,
+                               const double* xbar, double* gparams, double* gx0, void* stream);
+
+/*
  * The same two operations for the elbow (assets/contactnets_elbow.urdf: floating base + one
  * revolute child, two boxes, 2 x 4 contacts): states (B, 15) = [quat | pos | hinge angle | w_body |
  * v_world | hinge rate]; parameters inertia[20] (two bodies' 10-vectors), mu_pair[2] (ground-box1,

@@ -3,6 +3,7 @@
 #include "../../dair_pll_b200/csrc/cn_cube.cuh"
 #include "../../dair_pll_b200/csrc/cn_params.cuh"
 #include "../../dair_pll_b200/csrc/cn_elbow.cuh"
+#include "../../dair_pll_b200/csrc/cn_cube_tangent.cuh"
 #include <cstdint>
 using namespace cn;
 extern "C" {
@@ -95,6 +96,18 @@ int emul_elbow_step_f64(const double* x, const double* inertia, const double* mu
     int it = elbow_step_sample(P, cfg, x + 15 * b, (const double*)nullptr, xn + 15 * b, force ? force + 24 * b : nullptr);
     if (iters) iters[b] = it;
   }
+  return 0;
+}
+// tangent rollout: per-sample gradients of sum_s xbar_s . x_s w.r.t. the 14 callable-level parameters and x0
+int emul_cube_rollout_grad_f64(const double* x0, const double* inertia, const double* mu, const double* half,
+                               double dt, double eps, int64_t B, int steps, const double* xbar, double* gparams,
+                               double* gx0) {
+  for (int64_t b = 0; b < B; ++b)
+    for (int dir = 0; dir < CUBE_NTAN; ++dir) {
+      const double g = cube_rollout_tangent<double>(inertia, mu, half, dt, eps, x0 + 13 * b, steps,
+                                                    xbar + (int64_t)b * steps * 13, dir);
+      if (dir < 14) gparams[14 * b + dir] = g; else gx0[13 * b + dir - 14] = g;
+    }
   return 0;
 }
 }

@@ -343,3 +343,31 @@ def test_elbow_learned_geometry_matches_reference_golden(assets_dir):
     t = traj.cpu().numpy()
     assert np.abs(t[:, 1] - g['sim_traj'][:, 1]).max() < 1e-9
     assert np.abs(t - g['sim_traj']).max() < 1e-6
+
+
+def test_rollout_backward_matches_oracle_autograd(assets_dir):
+    """Prediction-loss path: gradients of a multi-step rollout w.r.t. every learnable
+    parameter and the initial state, through the module API, against autograd through the CPU oracle
+    (implicit differentiation of each step's QP)."""
+    from oracle import contactnets_oracle as co
+    from oracle.callables import CUBE_TREE, TreeCallables
+    g = load_golden('cube_real_perturbed')
+    s = _system(g, assets_dir)
+    x0 = torch.from_numpy(g['sim_x0'][:32]).to(DEV).requires_grad_()
+    steps = 3
+    target = torch.from_numpy(g['sim_traj'][:32, 1:steps + 1]).to(DEV) + 0.01
+    traj, _ = s.simulate(x0.unsqueeze(-2), torch.zeros(32, 1, device=DEV), steps)
+    loss = ((traj[:, 1:] - target) ** 2).sum()
+    loss.backward()
+    # oracle
+    P = co.OracleParams(torch.from_numpy(g['theta']).clone(), torch.from_numpy(g['friction_params']).clone(),
+                        [torch.from_numpy(g['half_lengths']).clone().reshape(1, 3)]).requires_grad_()
+    x0o = torch.from_numpy(g['sim_x0'][:32]).clone().requires_grad_()
+    tro = co.simulate(TreeCallables(CUBE_TREE), P, x0o, float(g['dt']), steps)
+    ((tro[:, 1:] - target.cpu()) ** 2).sum().backward()
+    assert np.abs(traj.detach().cpu().numpy() - tro.detach().numpy()).max() < 1e-8
+    mt = s.multibody_terms
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), P.inertial_parameters.grad.numpy()) < 1e-6
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), P.friction_params.grad.numpy()) < 1e-6
+    assert max_rel_to_scale(mt.contact_terms.geometries[0].length_params.grad.cpu().numpy(), P.length_params[0].grad.numpy()) < 1e-6
+    assert max_rel_to_scale(x0.grad.cpu().numpy(), x0o.grad.numpy()) < 1e-6

@@ -169,3 +169,38 @@ def test_elbow_device_math_matches_reference_golden(name):
                             ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-4), ctypes.c_int64(x0.shape[0]),
                             dptr(xn), None, None)
     assert np.abs(xn - g['sim_traj'][:, 1]).max() < 1e-9
+
+
+def test_step_tangents_match_oracle_autograd():
+    """Backward of the learnable time step (K7): dual-number tangents of a 3-step rollout, contracted
+    with a random upstream gradient, against autograd through the oracle (implicit differentiation of
+    the QP as sappy's backward would provide, multibody_learnable_system.py:293-304)."""
+    lib = host_emulation_lib()
+    g = load_golden('cube_real_perturbed')
+    inertia, mu, half = kernel_level_params(g)
+    # states near / in contact so the QP is active
+    x0 = np.ascontiguousarray(g['sim_x0'][:24])
+    B, steps = x0.shape[0], 3
+    rng = np.random.default_rng(0)
+    xbar = rng.standard_normal((B, steps, 13))
+    gparams, gx0 = np.zeros((B, 14)), np.zeros((B, 13))
+    lib.emul_cube_rollout_grad_f64(dptr(x0), dptr(inertia), dptr(mu), dptr(half), ctypes.c_double(float(g['dt'])),
+                                   ctypes.c_double(1e-4), ctypes.c_int64(B), ctypes.c_int(steps), dptr(xbar),
+                                   dptr(gparams), dptr(gx0))
+    # oracle: autograd through the same rollout, gradients w.r.t. the callable-level parameters and x0
+    calls = TreeCallables(CUBE_TREE)
+    inertia_t = torch.from_numpy(inertia.copy()).reshape(1, 10).requires_grad_()
+    mu_t = torch.from_numpy(mu.copy()).requires_grad_()
+    half_t = torch.from_numpy(half.copy()).requires_grad_()
+    x0_t = torch.from_numpy(x0.copy()).requires_grad_()
+    orig = co.theta_to_inertia_vector
+    co.theta_to_inertia_vector = lambda th: inertia_t
+    try:
+        P = co.OracleParams(torch.zeros(1, 10, dtype=torch.float64), torch.stack((mu_t[0], mu_t[0])), [half_t.reshape(1, 3)])
+        tr = co.simulate(calls, P, x0_t, float(g['dt']), steps)
+    finally:
+        co.theta_to_inertia_vector = orig
+    (tr[:, 1:] * torch.from_numpy(xbar)).sum().backward()
+    ref_params = np.concatenate((inertia_t.grad.numpy().reshape(10), mu_t.grad.numpy(), half_t.grad.numpy()))
+    assert max_rel_to_scale(gparams.sum(0), ref_params) < 1e-6
+    assert max_rel_to_scale(gx0, x0_t.grad.numpy()) < 1e-6
