@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument('--impl', choices=['b200', 'reference'], default='b200')
     ap.add_argument('--cpu-sample', type=int, default=65536, help='samples in the CPU baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the other BASELINE.json configs')
     ap.add_argument('--variant', type=int, default=0, help='0 = wavefront loss kernel, 1 = one sample per thread')
     return ap.parse_args()
 
@@ -123,6 +124,68 @@ def make_batch(system, batch, seed, device, dtype):
         traj, _ = system.simulate(x.unsqueeze(-2), torch.zeros(batch, 1, device=device), 1)
     xp = synthetic.perturb_next_state(traj[:, 1], seed=seed + 7919)
     return x.to(dtype).contiguous(), xp.to(dtype).contiguous()
+
+
+def _time_gpu(fn, device, reps, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(device)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        fn()
+    e.record()
+    torch.cuda.synchronize(device)
+    return s.elapsed_time(e) / reps
+
+
+def secondary_configs(device):
+    """The other BASELINE.json configs, measured through the public API on device-resident inputs
+    (CUDA events; context for the headline number, not part of it)."""
+    from dair_pll_b200 import synthetic
+    from dair_pll_b200.multibody_learnable_system import MultibodyLearnableSystem
+    out = {}
+    # config 1: cube loss + backward at B = 65,536, fp64 and the fp32 variant
+    system = make_system(device, torch.float64)
+    x, xp = make_batch(system, 65536, 11, device, torch.float64)
+
+    def cube_step(xx, xxp):
+        for p in system.parameters():
+            p.grad = None
+        system.contactnets_loss(xx, None, xxp).mean().backward()
+    ms = _time_gpu(lambda: cube_step(x, xp), device, 10)
+    out['cube_loss_backward_B65536_f64'] = {'ms': ms, 'samples_per_s': 65536 / ms * 1e3}
+    xf, xpf = x.float(), xp.float()
+    ms = _time_gpu(lambda: cube_step(xf, xpf), device, 10)
+    out['cube_loss_backward_B65536_f32_storage'] = {'ms': ms, 'samples_per_s': 65536 / ms * 1e3}
+    # config 4: rollout, 4,096 cube tosses x 80 steps
+    x0 = synthetic.cube_states(4096, seed=5, device=device)
+    carry = torch.zeros(4096, 1, device=device)
+
+    def roll():
+        with torch.no_grad():
+            system.simulate(x0.unsqueeze(-2), carry, 80)
+    ms = _time_gpu(roll, device, 5)
+    out['cube_rollout_4096x80_f64'] = {'ms': ms, 'steps_per_s': 4096 * 80 / ms * 1e3}
+    # config 3: elbow with learned (ICNN, width 256) geometry, loss + backward at B = 262,144
+    torch.manual_seed(0)
+    elbow = MultibodyLearnableSystem({'elbow': os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow_mesh.urdf')}, DT).to(device)
+    Be = 262144
+    xe = synthetic.elbow_states(Be, seed=3, device=device)
+    with torch.no_grad():
+        te, _ = elbow.simulate(xe.unsqueeze(-2), torch.zeros(Be, 1, device=device), 1)
+    xpe = synthetic.perturb_next_state(te[:, 1], seed=4, n_q=8)
+
+    def elbow_step():
+        for p in elbow.parameters():
+            p.grad = None
+        elbow.contactnets_loss(xe, None, xpe).mean().backward()
+    ms = _time_gpu(elbow_step, device, 3, warmup=1)
+    out['elbow_mesh_loss_backward_B262144_f64'] = {
+        'ms': ms, 'samples_per_s': Be / ms * 1e3,
+        'note': 'support-function networks (4 DGEMMs of 2.1M x 256 x 256) run on cuBLAS via torch.matmul; '
+                'elbow loss kernel is the one-sample-per-thread version'}
+    return out
 
 
 def cpu_reference_step(batch, threads):
@@ -304,6 +367,10 @@ def main():
                         'sample': f'{Bc} cube state pairs per step x 3 steps, oracle port (batched fp64 torch + C cone-QP '
                                   f'solver, {threads} threads), same generator/parameters'}
 
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = secondary_configs(device)
+
     line = {
         'metric': METRIC + (' fp64' if dtype == torch.float64 else ' fp32'),
         'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -328,6 +395,7 @@ def main():
                              'bytes_per_sample': BYTES_PER_SAMPLE[dtype]}},
         'cpu_baseline': cpu_baseline,
         'clocks': clocks,
+        'secondary': secondary,
     }
     print(json.dumps(line))
     if world > 1:
