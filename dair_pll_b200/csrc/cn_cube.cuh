@@ -701,4 +701,63 @@ CN_HD int cube_step_sample(const CubeParams<T>& P, const SolverCfg<T>& cfg, cons
   return it;
 }
 
+// ---------------------------------------------------------------------------
+// Dense dynamics terms in the reference's own coordinates and ordering, for callers of
+// MultibodyTerms.forward (multibody_terms.py:584-609): M (6x6), J (12x6) = [J_n (4 rows) ; mu J_t
+// (x,y interleaved per contact, 8 rows)] (:401-426), phi (4), contact-free acceleration (6) and the
+// Delassus operator D = J M^-1 J^T (12x12).  Contacts by ascending box-vertex index.  State
+// coordinates: v = [w_body ; v_world], so the point Jacobian of corner p is [-R S(p), I3].
+// ---------------------------------------------------------------------------
+template <typename T>
+CN_HD void cube_terms_sample(const CubeParams<T>& P, const T* q, const T* v, T* M, T* J, T* phi, T* acc, T* D) {
+  T R[9], store[33];
+  CubeProb<T> S{store, 1};
+  uint32_t sel;
+  cube_geometry<T, 1>(P, q, R, sel, S);
+  cube_free_accel(P, R, v, acc, acc + 3);
+  // M = [[Io, m S(c) R^T], [-m R S(c), m I]]
+  const T Sc[9] = {T(0), -P.c[2], P.c[1], P.c[2], T(0), -P.c[0], -P.c[1], P.c[0], T(0)};
+  for (int i = 0; i < 36; ++i) M[i] = T(0);
+  M[0] = P.Io[0]; M[7] = P.Io[1]; M[14] = P.Io[2];
+  M[1] = M[6] = P.Io[3]; M[2] = M[12] = P.Io[4]; M[8] = M[13] = P.Io[5];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      T b = T(0);                                   // (S(c) R^T)_{ij} = sum_k Sc[i][k] R[j][k]
+      for (int k = 0; k < 3; ++k) b += Sc[3 * i + k] * R[3 * j + k];
+      M[6 * i + 3 + j] = P.m * b;
+      M[6 * (3 + j) + i] = P.m * b;
+    }
+  for (int i = 0; i < 3; ++i) M[6 * (3 + i) + 3 + i] = P.m;
+  for (int c = 0; c < CUBE_NC; ++c) {
+    const T rho[3] = {S.rho(3 * c), S.rho(3 * c + 1), S.rho(3 * c + 2)};   // R p_c
+    phi[c] = rho[2] + q[6];
+    // -R S(p) = -S(R p) R = -S(rho) R : row i = -(rho x R-columns)...  use (-S(rho) R)_{ij} = -(S(rho) R)_{ij}
+    T E[9];
+    for (int j = 0; j < 3; ++j) {
+      const T col[3] = {R[j], R[3 + j], R[6 + j]};
+      T cr[3];
+      cross3(rho, col, cr);
+      for (int i = 0; i < 3; ++i) E[3 * i + j] = -cr[i];
+    }
+    for (int j = 0; j < 3; ++j) {
+      J[6 * c + j] = E[6 + j];                               // normal row: z
+      J[6 * (4 + 2 * c) + j] = P.mu * E[j];                  // tangential x
+      J[6 * (4 + 2 * c + 1) + j] = P.mu * E[3 + j];          // tangential y
+      J[6 * c + 3 + j] = j == 2 ? T(1) : T(0);
+      J[6 * (4 + 2 * c) + 3 + j] = j == 0 ? P.mu : T(0);
+      J[6 * (4 + 2 * c + 1) + 3 + j] = j == 1 ? P.mu : T(0);
+    }
+  }
+  if (D) {
+    T W[72];                                          // M^-1 J^T, column r = M^-1 (row r of J)
+    for (int r = 0; r < 12; ++r) cube_minv(P, R, J + 6 * r, J + 6 * r + 3, W + 6 * r, W + 6 * r + 3);
+    for (int a = 0; a < 12; ++a)
+      for (int b = 0; b < 12; ++b) {
+        T s = T(0);
+        for (int k = 0; k < 6; ++k) s += J[6 * a + k] * W[6 * b + k];
+        D[12 * a + b] = s;
+      }
+  }
+}
+
 }  // namespace cn

@@ -429,6 +429,27 @@ cube_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, c
   }
 }
 
+// Dense terms export (MultibodyTerms.forward, multibody_terms.py:584-609): one sample per thread.
+template <typename T, typename IO>
+__global__ void __launch_bounds__(kLossThreads)
+cube_terms_kernel(const IO* __restrict__ q, const IO* __restrict__ v, const IO* __restrict__ inertia,
+                  const IO* __restrict__ mu, const IO* __restrict__ half, int64_t B, IO* __restrict__ M,
+                  IO* __restrict__ J, IO* __restrict__ phi, IO* __restrict__ acc, IO* __restrict__ D) {
+  cn::CubeParams<T> P;
+  load_cube_params<T, IO>(P, inertia, mu, half, T(1), T(1));
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  T qs[7], vs[6], Mo[36], Jo[72], po[4], ao[6], Do[144];
+  for (int i = 0; i < 7; ++i) qs[i] = T(q[b * 7 + i]);
+  for (int i = 0; i < 6; ++i) vs[i] = T(v[b * 6 + i]);
+  cn::cube_terms_sample<T>(P, qs, vs, Mo, Jo, po, ao, D ? Do : (T*)nullptr);
+  for (int i = 0; i < 36; ++i) M[b * 36 + i] = IO(Mo[i]);
+  for (int i = 0; i < 72; ++i) J[b * 72 + i] = IO(Jo[i]);
+  for (int i = 0; i < 4; ++i) phi[b * 4 + i] = IO(po[i]);
+  for (int i = 0; i < 6; ++i) acc[b * 6 + i] = IO(ao[i]);
+  if (D) for (int i = 0; i < 144; ++i) D[b * 144 + i] = IO(Do[i]);
+}
+
 // ---------------------------------------------------------------------------
 // Elbow (floating base + hinge, 8 contacts): one sample per thread, problem in thread-local arrays.
 // ---------------------------------------------------------------------------
@@ -728,6 +749,19 @@ int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu
                           void* stream) {
   return launch_cube_rollout<double, float>(x0, inertia, mu_pair, half, (double)dt, (double)eps, B, steps, traj, force,
                                             iters, stream);
+}
+
+int dpll_cube_terms_f64(const double* q, const double* v, const double* inertia, const double* mu_pair,
+                        const double* half, int64_t B, double* M, double* J, double* phi, double* acc, double* delassus,
+                        void* stream) {
+  if (B < 0 || !inertia || !mu_pair || !half) return DPLL_EINVAL;
+  if (B > 0 && (!q || !v || !M || !J || !phi || !acc)) return DPLL_EINVAL;
+  if (B == 0) return DPLL_OK;
+  const int blocks = (int)((B + kLossThreads - 1) / kLossThreads);
+  cube_terms_kernel<double, double><<<blocks, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      q, v, inertia, mu_pair, half, B, M, J, phi, acc, delassus);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPLL_OK : (int)e;
 }
 
 int dpll_elbow_loss_f64(const double* x, const double* x_plus, const double* weight, const double* inertia,

@@ -99,6 +99,21 @@ class MultibodyTerms(Module):
         half = [h.to(dtype) for h in self.contact_terms.half_lengths()]
         return inertia, mu, half
 
+    def forward(self, q: Tensor, v: Tensor, u: Tensor = None):
+        """(delassus, M, J, phi, non_contact_acceleration) as ``MultibodyTerms.forward`` of the reference
+        (multibody_terms.py:584-609), evaluated by the terms kernel (cube, float64, no autograd; contacts
+        ordered by box-vertex index).  The loss and step kernels do not go through these matrices."""
+        from dair_pll_b200 import ops
+        del u
+        if self.spec.kind != 'cube':
+            raise NotImplementedError('dense terms export is provided for the cube')
+        batch = q.shape[:-1]
+        inertia, mu, half = self.kernel_parameters(q.dtype)
+        D, M, J, phi, acc = ops.cube_terms(q.reshape(-1, 7), v.reshape(-1, 6), inertia.detach().reshape(10),
+                                           mu.detach().reshape(1), half[0].detach())
+        return (D.reshape(batch + (12, 12)), M.reshape(batch + (6, 6)), J.reshape(batch + (12, 6)),
+                phi.reshape(batch + (4,)), acc.reshape(batch + (6,)))
+
     def scalars_and_meshes(self):
         """Summary scalars per body (multibody_terms.py:536-582); no meshes for box geometries."""
         scalars = {}

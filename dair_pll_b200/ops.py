@@ -381,6 +381,27 @@ class CubeRollout(torch.autograd.Function):
                 g[11:14].reshape(half.shape).to(half.dtype), None, None, None)
 
 
+def cube_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor):
+    """``dpll_cube_terms_f64``: (delassus (B,12,12), M (B,6,6), J (B,12,6), phi (B,4), acc (B,6)) in the order
+    ``MultibodyTerms.forward`` returns them (multibody_terms.py:584-609).  fp64 only, no autograd."""
+    _check_inputs(q, v, inertia, mu_pair, half)
+    if q.dtype != torch.float64:
+        raise TypeError('cube_terms is provided in float64')
+    q, v = q.contiguous(), v.contiguous()
+    B, dev = q.shape[0], q.device
+    M = torch.empty((B, 6, 6), dtype=q.dtype, device=dev)
+    J = torch.empty((B, 12, 6), dtype=q.dtype, device=dev)
+    phi = torch.empty((B, 4), dtype=q.dtype, device=dev)
+    acc = torch.empty((B, 6), dtype=q.dtype, device=dev)
+    D = torch.empty((B, 12, 12), dtype=q.dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().dpll_cube_terms_f64(_ptr(q), _ptr(v), _ptr(inertia.contiguous()), _ptr(mu_pair.contiguous()),
+                                             _ptr(half.contiguous()), B, _ptr(M), _ptr(J), _ptr(phi), _ptr(acc),
+                                             _ptr(D), _stream())
+    _lib.check(rc, 'dpll_cube_terms')
+    return D, M, J, phi, acc
+
+
 def fma_peak(dtype: torch.dtype, device: torch.device, blocks: int, iters: int) -> float:
     """Measured FMA throughput (FLOP/s) of the CUDA cores for ``dtype`` -- roofline denominator."""
     out = torch.empty(blocks * 256, dtype=dtype, device=device)

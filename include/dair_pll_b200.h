@@ -140,6 +140,17 @@ int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu
                           float* traj, float* force, int32_t* iters, void* stream);
 
 /*
+ * Dense dynamics terms of the cube in the reference's coordinates and ordering, for callers of
+ * MultibodyTerms.forward (dair_pll/multibody_terms.py:584-609; LagrangianTerms.forward :214-237,
+ * ContactTerms.forward :428-521): q (B,7), v (B,6) -> M (B,6,6), J (B,12,6) = [J_n ; mu J_t interleaved]
+ * (:401-426), phi (B,4), contact-free acceleration (B,6), delassus (B,12,12) (nullable).  Contacts by
+ * ascending box-vertex index.  (The loss / step kernels never form these matrices.)
+ */
+int dpll_cube_terms_f64(const double* q, const double* v, const double* inertia, const double* mu_pair,
+                        const double* half, int64_t B, double* M, double* J, double* phi, double* acc,
+                        double* delassus, void* stream);
+
+/*
  * Backward of dpll_cube_rollout_f64 (the gradient the reference obtains by autograd through
  * forward_dynamics and sappy's backward, multibody_learnable_system.py:293-304; used by the
  * prediction loss, experiment.py:230-248, 292-320): given the upstream gradient xbar (B, steps, 13)

@@ -371,3 +371,83 @@ def test_rollout_backward_matches_oracle_autograd(assets_dir):
     assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), P.friction_params.grad.numpy()) < 1e-6
     assert max_rel_to_scale(mt.contact_terms.geometries[0].length_params.grad.cpu().numpy(), P.length_params[0].grad.numpy()) < 1e-6
     assert max_rel_to_scale(x0.grad.cpu().numpy(), x0o.grad.numpy()) < 1e-6
+
+
+def test_edge_cases_match_oracle():
+    """Edge cases of the domain: axis-aligned cube resting flat (ties between the four bottom corners
+    and degenerate top-k), zero velocities (zero sliding speed: the |.| and sqrt branches), deep
+    penetration, far-away flight, and a non-unit quaternion (Drake normalises the rotation)."""
+    from oracle import contactnets_oracle as co
+    from oracle.callables import CUBE_TREE, TreeCallables
+    calls = TreeCallables(CUBE_TREE)
+    pi, fr, half = synthetic.cube_learnables_perturbed(4)
+    P = co.OracleParams(co.pi_cm_to_theta(pi), fr, [half.reshape(1, 3)])
+    h = half.numpy()
+    rows = [
+        [1, 0, 0, 0, 0, 0, h[2], 0, 0, 0, 0, 0, 0],                 # flat on the ground, at rest
+        [1, 0, 0, 0, 0, 0, h[2] - 0.004, 0, 0, 0, 0.3, 0, -0.5],    # flat, penetrating, sliding in x
+        [1, 0, 0, 0, 0, 0, 5.0, 1, 2, 3, 0, 0, 0],                  # far away, spinning
+        [2, 0, 0, 0, 0, 0, h[2] + 1e-4, 0, 0, 0, 0, 0, -0.2],       # non-unit quaternion (norm 2)
+        [0.7071067811865476, 0.7071067811865476, 0, 0, 0, 0, h[1] + 1e-3, 0, 0, 0.5, 0.2, -0.1, -0.3],  # on a side face
+        [0.9, 0.1, 0.3, 0.2, 0.1, -0.2, 0.03, 3, -2, 1, 0.5, 0.5, -1.5],   # deep penetration, tumbling
+    ]
+    x = torch.tensor(rows, dtype=torch.float64)
+    with torch.no_grad():
+        xp = co.sim_step(calls, P, x, 0.0068)
+        xp2 = xp.clone()
+        xp2[:, 7:] += 0.05                                           # perturbed observations
+    g = dict(theta=P.inertial_parameters.numpy(), friction_params=fr.numpy(), half_lengths=half.numpy())
+    inertia, mu, hl = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    for target in (xp, xp2):
+        lo = co.contactnets_loss(calls, P, x, target, 0.0068).numpy()
+        l, _, _, _, it = ops.cube_loss_raw(x.to(DEV), target.to(DEV), inertia, mu, hl, 0.0068, 1e-3, want_iters=True)
+        assert np.abs(l.cpu().numpy() - lo).max() < 1e-11 * max(1.0, np.abs(lo).max())
+    traj, _ = ops.cube_rollout(x.to(DEV), inertia, mu, hl, 0.0068, 1)
+    assert np.abs(traj[:, 1].cpu().numpy() - xp.numpy()).max() < 1e-8
+
+
+def test_solver_failure_mask_zeroes_loss_and_gradient():
+    """multibody_learnable_system.py:186-192: samples whose impulse exceeds 1e3 (or is not finite) get
+    force := 0 and constant := 0, i.e. loss 0 and no gradient.  A 1e5 m/s velocity jump forces that."""
+    g = load_golden('cube_synthetic')
+    inertia, mu, half = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    x = torch.from_numpy(g['x'][:64]).to(DEV)
+    xp = torch.from_numpy(g['x_plus'][:64]).to(DEV).clone()
+    ref = ops.cube_loss_raw(x, xp, inertia, mu, half, float(g['dt']), 1e-3, want_force=True)
+    bad = xp.clone()
+    bad[::4, 12] = 1e5                        # absurd upward velocity with the corners on the ground
+    bad[::4, 6] = 0.05
+    bad[1::8, 9] = float('nan')               # non-finite observation
+    out = ops.cube_loss_raw(x, bad, inertia, mu, half, float(g['dt']), 1e-3, want_force=True)
+    masked = torch.zeros(64, dtype=torch.bool, device=DEV)
+    masked[::4] = True
+    masked[1::8] = True
+    assert (out[0][masked] == 0).all() and (out[3][masked] == 0).all()
+    assert torch.equal(out[0][~masked], ref[0][~masked])
+    assert torch.isfinite(out[1]).all()
+    # gradient = sum over the unmasked samples only
+    keep = ops.cube_loss_raw(x[~masked], xp[~masked], inertia, mu, half, float(g['dt']), 1e-3)
+    assert max_rel_to_scale(out[1].cpu().numpy(), keep[1].cpu().numpy()) < 1e-11
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_dense_terms_match_reference_golden(name, assets_dir):
+    """MultibodyTerms.forward: M, M^-1 F and phi against the reference-code goldens; J and the Delassus
+    operator against the oracle (same canonical contact order)."""
+    from oracle import contactnets_oracle as co
+    from oracle.callables import CUBE_TREE, TreeCallables
+    g = load_golden(name)
+    s = _system(g, assets_dir)
+    xp = torch.from_numpy(g['x_plus']).to(DEV)
+    D, M, J, phi, acc = s.multibody_terms(xp[:, :7], xp[:, 7:], None)
+    assert np.abs(M.cpu().numpy() - g['terms_M']).max() < 1e-15
+    assert np.abs(acc.cpu().numpy() - g['terms_acc']).max() < 1e-10 * max(1.0, np.abs(g['terms_acc']).max())
+    assert np.abs(np.sort(phi.cpu().numpy(), -1) - g['terms_phi_sorted']).max() < 1e-15
+    P = co.OracleParams(torch.from_numpy(g['theta']), torch.from_numpy(g['friction_params']),
+                        [torch.from_numpy(g['half_lengths']).reshape(1, 3)])
+    with torch.no_grad():
+        Mo, Jo, phio, _ = co.multibody_terms(TreeCallables(CUBE_TREE), P, xp.cpu()[:, :7], xp.cpu()[:, 7:])
+        Do = Jo @ torch.linalg.solve(Mo, Jo.transpose(-1, -2))
+    assert np.abs(J.cpu().numpy() - Jo.numpy()).max() < 1e-14
+    assert np.abs(phi.cpu().numpy() - phio.numpy()).max() < 1e-15
+    assert np.abs(D.cpu().numpy() - Do.numpy()).max() < 1e-10 * np.abs(Do.numpy()).max()

@@ -204,3 +204,29 @@ def test_step_tangents_match_oracle_autograd():
     ref_params = np.concatenate((inertia_t.grad.numpy().reshape(10), mu_t.grad.numpy(), half_t.grad.numpy()))
     assert max_rel_to_scale(gparams.sum(0), ref_params) < 1e-6
     assert max_rel_to_scale(gx0, x0_t.grad.numpy()) < 1e-6
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_device_dense_terms_match_reference_golden(name):
+    """MultibodyTerms.forward outputs (M, M^-1 F, phi from the reference's code; J, Delassus from the oracle)."""
+    g = load_golden(name)
+    lib = host_emulation_lib()
+    inertia, mu, half = kernel_level_params(g)
+    xp = g['x_plus']
+    B = xp.shape[0]
+    q, v = np.ascontiguousarray(xp[:, :7]), np.ascontiguousarray(xp[:, 7:])
+    M, J, phi = np.zeros((B, 6, 6)), np.zeros((B, 12, 6)), np.zeros((B, 4))
+    acc, D = np.zeros((B, 6)), np.zeros((B, 12, 12))
+    lib.emul_cube_terms_f64(dptr(q), dptr(v), dptr(inertia), dptr(mu), dptr(half), ctypes.c_int64(B), dptr(M),
+                            dptr(J), dptr(phi), dptr(acc), dptr(D))
+    assert np.abs(M - g['terms_M']).max() < 1e-15
+    assert np.abs(acc - g['terms_acc']).max() < 1e-10 * max(1.0, np.abs(g['terms_acc']).max())
+    assert np.abs(np.sort(phi, -1) - g['terms_phi_sorted']).max() < 1e-15
+    P = co.OracleParams(torch.from_numpy(g['theta']), torch.from_numpy(g['friction_params']),
+                        [torch.from_numpy(g['half_lengths']).reshape(1, 3)])
+    with torch.no_grad():
+        Mo, Jo, phio, _ = co.multibody_terms(TreeCallables(CUBE_TREE), P, torch.from_numpy(q), torch.from_numpy(v))
+        Do = Jo @ torch.linalg.solve(Mo, Jo.transpose(-1, -2))
+    assert np.abs(J - Jo.numpy()).max() < 1e-14
+    assert np.abs(phi - phio.numpy()).max() < 1e-15
+    assert np.abs(D - Do.numpy()).max() < 1e-10 * np.abs(Do.numpy()).max()
