@@ -389,6 +389,91 @@ CN_HD void cube_line_search(const CubeParams<T>& P, const CubeProb<T>& S, const 
   d0 = T(0);
 }
 
+// Line-search state of the unified Newton visit below (one bracket on the pending direction).
+template <typename T> struct CubeTrial {
+  T alpha, lo, hi;   // u = u0 + alpha d is the tentative point; phi' < 0 at lo, > 0 at hi
+};
+
+// One schedulable Newton VISIT for the wavefront kernel: exactly one gradient/Hessian evaluation,
+// no inner loop.  Differs from cube_newton_step + cube_line_search only in how a rejected step is
+// searched: the safeguarded Newton iteration on phi'(alpha) takes ONE trial per visit, using the
+// gradient and the curvature d^T H d of the full evaluation at the trial point (phi'' exactly), so
+// every lane of a warp runs the same code and there is no separate line-search queue.  A gradient
+// below cfg.tol_final (quadratic regime: the next step lands at rounding level) takes the step and
+// finishes without the confirming evaluation.
+//   it: bits 0-7 Newton directions taken, 8-15 trials on the pending direction (0xff = forced
+//   accept), 16+ rounding-floor counter.  Returns NEWTON_DONE or NEWTON_CONTINUE.
+template <typename T, int UNR>
+CN_HD int cube_newton_visit(const CubeParams<T>& P, const CubeProb<T>& S, const SolverCfg<T>& cfg, T* u, T* d,
+                            T& d0, T& best_res2, CubeTrial<T>& tr, int& it) {
+  T g[6], H[36], res2, scale2;
+  CN_STAT_UNIT();
+  cube_eval<T, true, UNR>(P, S, u, g, H, res2, scale2);
+  if (cube_converged(cfg, res2, scale2)) return NEWTON_DONE;
+  if (res2 <= cfg.tol_stall * cfg.tol_stall * scale2 && !(res2 < T(0.25) * best_res2)) {
+    it += 1 << 16;
+    if ((it >> 16) >= 3) return NEWTON_DONE;
+  } else if (res2 < best_res2 || best_res2 < T(0)) {
+    it &= 0xffff;
+  }
+  if (res2 < best_res2 || best_res2 < T(0)) best_res2 = res2;
+  const int trials = (it >> 8) & 0xff;
+  if (d0 < T(0) && trials != 0xff) {
+    T d1 = T(0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d1 += g[i] * d[i];
+    const T thresh = -cfg.ls_c * d0;
+    // the full step is accepted one-sidedly (still descending is fine); interior trials on |phi'|
+    const bool accept = trials == 0 ? (d1 <= thresh) : (t_abs(d1) <= thresh);
+    if (!accept) {
+      if (d1 < T(0)) tr.lo = tr.alpha; else tr.hi = tr.alpha;
+      T d2 = T(0);                                  // phi''(alpha) = d^T H d (lower triangle of H is filled)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        T row = T(0);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) row += H[j <= i ? 6 * i + j : 6 * j + i] * d[j];
+        d2 += d[i] * row;
+      }
+      T an = tr.alpha - d1 / d2;
+      if (!(an > tr.lo && an < tr.hi)) an = T(0.5) * (tr.lo + tr.hi);
+      int nt = trials + 1;
+      if (tr.hi - tr.lo <= T(4) * eps_of<T>() * tr.hi || nt >= 7) {   // budget spent: keep a point with phi' <= 0
+        an = tr.lo > T(0) ? tr.lo : an;
+        nt = 0xff;
+      }
+      const T step = an - tr.alpha;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) u[i] += step * d[i];
+      tr.alpha = an;
+      it = (it & ~0xff00) | (nt << 8);
+      return NEWTON_CONTINUE;
+    }
+  }
+  if ((it & 0xff) >= cfg.max_iter) return NEWTON_DONE;
+  block_solve6_neg<T>(H, g, d);
+  T dd = T(0);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { dd += g[i] * d[i]; u[i] += d[i]; }
+  d0 = dd < T(0) ? dd : T(0);
+  tr.alpha = T(1); tr.lo = T(0); tr.hi = T(1);
+  it = (it & ~0xff00) + 1;
+  if (res2 <= cfg.tol_final * cfg.tol_final * scale2) return NEWTON_DONE;
+  return NEWTON_CONTINUE;
+}
+
+// The visit-by-visit solve (what the wavefront kernel runs, per lane).
+template <typename T, int UNR>
+CN_HD int cube_solve_visits(const CubeParams<T>& P, const CubeProb<T>& S, const SolverCfg<T>& cfg, T* u) {
+  int it = 0;
+  if (!cube_trivially_solved<T, UNR>(S)) {
+    T d[6], d0 = T(0), best = T(-1);
+    CubeTrial<T> tr{T(1), T(0), T(1)};
+    while (cube_newton_visit<T, UNR>(P, S, cfg, u, d, d0, best, tr, it) != NEWTON_DONE) {}
+  }
+  return it & 0xff;
+}
+
 // Newton solve from u (in: start point, out: optimum).  Returns iterations.
 template <typename T, int UNR>
 CN_HD int cube_solve(const CubeParams<T>& P, const CubeProb<T>& S, const SolverCfg<T>& cfg, T* u) {

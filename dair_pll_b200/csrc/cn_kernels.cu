@@ -135,13 +135,13 @@ cube_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* 
 constexpr int kWfUnr = CN_WF_UNR;   // unroll factor of the per-contact loops inside the Newton step
 constexpr int kWfSlots = 64;
 constexpr int kWfWarps = 4;
-constexpr int kWfFields = 47;   // IW 6 | mcW 3 | rho 12 | q 12 | u 6 | prev_res2 1 | d 6 | d0 1
+constexpr int kWfFields = 50;   // IW 6 | mcW 3 | rho 12 | q 12 | u 6 | best_res2 1 | d 6 | d0 1 | alpha, lo, hi
 
 template <typename T> struct WfWarpPool {
   T field[kWfFields][kWfSlots];
   int32_t sample[kWfSlots];     // offset of the slot's sample in the warp's range; -1 = empty
   int32_t iters[kWfSlots];
-  uint8_t q_act[kWfSlots], q_done[kWfSlots], q_ls[kWfSlots];
+  uint8_t q_act[kWfSlots], q_done[kWfSlots];
 };
 
 template <typename T, typename IO>
@@ -171,47 +171,24 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
   int64_t next = lo;
 
   for (int s = lane; s < kWfSlots; s += 32) { pool->q_done[s] = (uint8_t)s; pool->sample[s] = -1; }
-  int n_act = 0, n_done = kWfSlots, n_ls = 0, h_act = 0, h_done = 0, h_ls = 0, prev_phase = 0;
+  int n_act = 0, n_done = kWfSlots, h_act = 0, h_done = 0;
   __syncwarp();
 
   while (true) {
-    int phase;   // 0 = PE, 1 = N, 2 = L
-    // Drain mode (input exhausted): the remaining samples' Newton chains are the critical path of the
-    // warp, so N and L simply alternate (width no longer matters) and the finished samples are
-    // finalised in full-width PE batches at the very end.
+    int phase;   // 0 = PE, 1 = N
+    // Slots are conserved while input remains (active + done = kWfSlots), so one of the two queues
+    // always holds a full warp's worth.  Once the input is exhausted (drain) the remaining samples'
+    // Newton chains are the critical path: N runs at whatever width is left and the finished samples
+    // are finalised in full-width PE batches at the very end.
     const bool drain = next >= hi;
     if (drain) {
-      if (n_ls > 0 && (n_act == 0 || prev_phase == 1)) phase = 2;
-      else if (n_act > 0) phase = 1;
+      if (n_act > 0) phase = 1;
       else if (n_done > 0) phase = 0;
       else break;
     } else if (n_done >= 32) phase = 0;
-    else if (n_act >= 32) phase = 1;
-    else if (n_ls >= 32) phase = 2;
-    else if (n_act > 0 && n_act >= n_ls && n_act >= n_done) phase = 1;
-    else if (n_ls > 0 && n_ls >= n_done) phase = 2;
-    else if (n_done > 0) phase = 0;
-    else break;
+    else phase = 1;
 
-    if (phase == 2) {
-      const int k = n_ls < 32 ? n_ls : 32;
-      const bool on = lane < k;
-      int slot = 0;
-      if (on) {
-        slot = pool->q_ls[(h_ls + lane) % kWfSlots];
-        const cn::CubeProb<T> S{&pool->field[0][slot], kWfSlots};
-        T u[6], d[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { u[i] = pool->field[33 + i][slot]; d[i] = pool->field[40 + i][slot]; }
-        T d0 = pool->field[46][slot];
-        cn::cube_line_search<T, 1>(P, S, cfg, u, d, d0);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = u[i];
-        pool->field[46][slot] = d0;
-        pool->q_act[(h_act + n_act + lane) % kWfSlots] = (uint8_t)slot;
-      }
-      h_ls = (h_ls + k) % kWfSlots; n_ls -= k; n_act += k;
-    } else if (phase == 1) {
+    if (phase == 1) {
       const int k = n_act < 32 ? n_act : 32;
       const bool on = lane < k;
       int st = -1;
@@ -223,24 +200,22 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
 #pragma unroll
         for (int i = 0; i < 6; ++i) { u[i] = pool->field[33 + i][slot]; d[i] = pool->field[40 + i][slot]; }
         T best = pool->field[39][slot], d0 = pool->field[46][slot];
+        cn::CubeTrial<T> tr{pool->field[47][slot], pool->field[48][slot], pool->field[49][slot]};
         int it = pool->iters[slot];
-        st = cn::cube_newton_step<T, kWfUnr>(P, S, cfg, u, d, d0, best, it);
+        st = cn::cube_newton_visit<T, kWfUnr>(P, S, cfg, u, d, d0, best, tr, it);
         pool->iters[slot] = it;
         pool->field[39][slot] = best;
-        if (st == cn::NEWTON_CONTINUE) {       // (LINESEARCH leaves u, d, d0 as they were)
 #pragma unroll
-          for (int i = 0; i < 6; ++i) { pool->field[33 + i][slot] = u[i]; pool->field[40 + i][slot] = d[i]; }
-          pool->field[46][slot] = d0;
-        }
+        for (int i = 0; i < 6; ++i) { pool->field[33 + i][slot] = u[i]; pool->field[40 + i][slot] = d[i]; }
+        pool->field[46][slot] = d0;
+        pool->field[47][slot] = tr.alpha; pool->field[48][slot] = tr.lo; pool->field[49][slot] = tr.hi;
       }
       const unsigned m_done = __ballot_sync(0xffffffffu, st == cn::NEWTON_DONE);
       const unsigned m_act = __ballot_sync(0xffffffffu, st == cn::NEWTON_CONTINUE);
-      const unsigned m_ls = __ballot_sync(0xffffffffu, st == cn::NEWTON_LINESEARCH);
       h_act = (h_act + k) % kWfSlots; n_act -= k;
       if (st == cn::NEWTON_DONE) pool->q_done[(h_done + n_done + __popc(m_done & lt_mask)) % kWfSlots] = (uint8_t)slot;
       else if (st == cn::NEWTON_CONTINUE) pool->q_act[(h_act + n_act + __popc(m_act & lt_mask)) % kWfSlots] = (uint8_t)slot;
-      else if (st == cn::NEWTON_LINESEARCH) pool->q_ls[(h_ls + n_ls + __popc(m_ls & lt_mask)) % kWfSlots] = (uint8_t)slot;
-      n_done += __popc(m_done); n_act += __popc(m_act); n_ls += __popc(m_ls);
+      n_done += __popc(m_done); n_act += __popc(m_act);
     } else {
       const int k = n_done < 32 ? n_done : 32;
       const bool on = lane < k;
@@ -282,7 +257,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
           for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] += w * gs[i];
           if (loss) loss[b] = IO(l);
           acc[14] += l;
-          if (iters) iters[b] = fresh ? 0 : (pool->iters[slot] & 0xffff);
+          if (iters) iters[b] = fresh ? 0 : (pool->iters[slot] & 0xff);
           pool->sample[slot] = -1;
         } else {
 #pragma unroll
@@ -303,7 +278,6 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
       else if (on && more) pool->q_done[(h_done + n_done + __popc(m_keep & lt_mask)) % kWfSlots] = (uint8_t)slot;
       n_act += __popc(m_act); n_done += __popc(m_keep);
     }
-    prev_phase = phase;
     __syncwarp();
   }
 
