@@ -599,7 +599,9 @@ CN_HD void rigid_body_inertia_adjoint(T m, const T* c, const T* R, const T* w, T
 
 // Loss value at the optimum u and (if grad != nullptr) += d loss / d [inertia(10), mu, half(3)].
 // force_out (nullable): reference order [n(4); (tx,ty)(4)].
-template <typename T, int UNR>
+// PARK: pass 1 overwrites the slot's q_c (dead after q.f) with the force f_c so that pass 2 reads it back
+// instead of re-evaluating the cone projection (the wavefront kernel; S is consumed).
+template <typename T, int UNR, bool PARK = false>
 CN_HD T cube_loss_epilogue(const CubeParams<T>& P, const CubeProb<T>& S, const CubeLossAux<T>& A, const T* u,
                            T* grad, T* force_out) {
   const T* R = A.R;
@@ -620,6 +622,10 @@ CN_HD T cube_loss_epilogue(const CubeParams<T>& P, const CubeProb<T>& S, const C
       qf += S.q(3 * c + i) * f[i]; ff += f[i] * f[i];
       const T af = t_abs(f[i]);
       fmax = (af > fmax || af != af) ? af : fmax;     // NaN-propagating max
+    }
+    if (PARK) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) S.q(3 * c + i) = f[i];
     }
     if (force_out) { force_out[c] = f[2]; force_out[4 + 2 * c] = f[0]; force_out[4 + 2 * c + 1] = f[1]; }
   }
@@ -662,8 +668,13 @@ CN_HD T cube_loss_epilogue(const CubeParams<T>& P, const CubeProb<T>& S, const C
 #pragma unroll UNR
   for (int cidx = 0; cidx < CUBE_NC; ++cidx) {
     T rho[3], r[3], f[3];
-    cube_contact_residual(P, S, cidx, u, rho, r);
-    cone_eval<T, false>(r, P.inv_eps, P.mu, f, (T*)nullptr);
+    if (PARK) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { rho[i] = S.rho(3 * cidx + i); f[i] = S.q(3 * cidx + i); }
+    } else {
+      cube_contact_residual(P, S, cidx, u, rho, r);
+      cone_eval<T, false>(r, P.inv_eps, P.mu, f, (T*)nullptr);
+    }
     T eb[3], ev[3];
     cross3(bW, rho, eb); cross3(wW, rho, ev);
 #pragma unroll

@@ -247,7 +247,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
 #pragma unroll
           for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
           T fo[12];
-          const T l = cn::cube_loss_epilogue<T, 1>(P, S, A, u, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr);
+          const T l = cn::cube_loss_epilogue<T, 1, true>(P, S, A, u, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr);
           if (force) {
 #pragma unroll
             for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(fo[i]);
