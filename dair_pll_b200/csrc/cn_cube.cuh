@@ -273,30 +273,6 @@ CN_HD void cube_eval(const CubeParams<T>& P, const CubeProb<T>& S, const T* u, T
   scale2 = t_max(a2, b2);
 }
 
-// 1-D derivative phi'(alpha) (and curvature) along u + alpha d, expressed with the trial point
-// u1 = u + d:  r_c(alpha) = r_c(u1) - (1 - alpha) D_mu J_c d.
-template <typename T, int UNR>
-CN_HD void cube_line(const CubeParams<T>& P, const CubeProb<T>& S, const T* u1, const T* d, T uMd, T dMd, T alpha,
-                     T& d1, T& d2) {
-  d1 = uMd + alpha * dMd;
-  d2 = dMd;
-  const T back = T(1) - alpha;
-#pragma unroll UNR
-  for (int c = 0; c < CUBE_NC; ++c) {
-    T rho[3], r[3], e[3], f[3], K[6];
-    cube_contact_residual(P, S, c, u1, rho, r);
-    cross3(d, rho, e);
-    e[0] = P.mu * (e[0] + d[3]); e[1] = P.mu * (e[1] + d[4]); e[2] = e[2] + d[5];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) r[j] -= back * e[j];
-    // e is already D_mu-scaled, so the plain G/eps is wanted: evaluate with mu = 1
-    cone_eval<T, true>(r, P.inv_eps, T(1), f, K);
-    d1 -= e[0] * f[0] + e[1] * f[1] + e[2] * f[2];
-    d2 += e[0] * (K[0] * e[0] + K[1] * e[1] + K[2] * e[2]) + e[1] * (K[1] * e[0] + K[3] * e[1] + K[4] * e[2]) +
-          e[2] * (K[2] * e[0] + K[4] * e[1] + K[5] * e[2]);
-  }
-}
-
 // True iff u = 0 is already optimal: every contact's y = -q/eps lies in the polar cone, so
 // all forces vanish and the gradient M*0 - J^T 0 is exactly zero (free flight).
 template <typename T, int UNR> CN_HD bool cube_trivially_solved(const CubeProb<T>& S) {
@@ -313,93 +289,24 @@ template <typename T> CN_HD bool cube_converged(const SolverCfg<T>& cfg, T res2,
   return !(res2 > cfg.tol_rel * cfg.tol_rel * scale2);   // also true for NaN
 }
 
-// One schedulable Newton step (the wavefront kernel runs one per lane per trip).  Each step is ONE
-// gradient/Hessian evaluation: the full step u <- u + d taken by the previous call is accepted
-// or rejected here, lazily, from the gradient at the new point (phi'(1) = g(u).d <= ls_c |phi'(0)|),
-// which the evaluation for the next direction provides anyway.  State: u (current, possibly
-// tentative point), d / d0 = phi'(0) of the pending step (d0 = 0: nothing pending), prev_res2, it.
-//   NEWTON_DONE        sample finished (converged / rounding floor / iteration cap), u final;
-//                      `it & 0xffff` = Newton directions taken
-//   NEWTON_CONTINUE    a new full step has been taken tentatively (u, d, d0 updated)
-//   NEWTON_LINESEARCH  the pending step overshoots: run cube_line_search (kept out of this
-//                      function so the wavefront kernel can run line searches as their own phase)
-enum { NEWTON_DONE = 0, NEWTON_CONTINUE = 1, NEWTON_LINESEARCH = 2 };
-
-template <typename T, int UNR>
-CN_HD int cube_newton_step(const CubeParams<T>& P, const CubeProb<T>& S, const SolverCfg<T>& cfg, T* u, T* d,
-                           T& d0, T& best_res2, int& it) {
-  T g[6], H[36], res2, scale2;
-  CN_STAT_UNIT();
-  cube_eval<T, true, UNR>(P, S, u, g, H, res2, scale2);
-  // a point with a negligible gradient is optimal (strong convexity), accepted step or not
-  if (cube_converged(cfg, res2, scale2)) return NEWTON_DONE;
-  // rounding floor: close to the optimum Newton contracts the residual quadratically, so three
-  // consecutive evaluations without a 4x reduction of the best residual mean the floor of this
-  // sample's conditioning has been reached (`it` carries the counter in its high bits)
-  if (res2 <= cfg.tol_stall * cfg.tol_stall * scale2 && !(res2 < T(0.25) * best_res2)) {
-    it += 1 << 16;
-    if ((it >> 16) >= 3) return NEWTON_DONE;
-  } else if (res2 < best_res2 || best_res2 < T(0)) {
-    it &= 0xffff;
-  }
-  if (res2 < best_res2 || best_res2 < T(0)) best_res2 = res2;
-  if (d0 < T(0)) {
-    T d1 = T(0);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) d1 += g[i] * d[i];
-    if (!(d1 <= -cfg.ls_c * d0)) return NEWTON_LINESEARCH;
-  }
-  if ((it & 0xffff) >= cfg.max_iter) return NEWTON_DONE;
-  block_solve6_neg<T>(H, g, d);
-  T dd = T(0);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) { dd += g[i] * d[i]; u[i] += d[i]; }
-  d0 = dd < T(0) ? dd : T(0);     // a non-descent direction (rounding at the floor) is simply accepted
-  ++it;
-  return NEWTON_CONTINUE;
-}
-
-// Derivative-based line search for a rejected full step: u holds the tentative point u0 + d.
-// Safeguarded Newton on phi'(alpha) over (0,1) until |phi'(alpha)| <= ls_c |phi'(0)|;
-// u <- u0 + alpha d, d0 <- 0 (nothing pending).
-template <typename T, int UNR>
-CN_HD void cube_line_search(const CubeParams<T>& P, const CubeProb<T>& S, const SolverCfg<T>& cfg, T* u,
-                            const T* d, T& d0) {
-  const T thresh = -cfg.ls_c * d0;
-  T Md[6], uMd = T(0), dMd = T(0);
-  cube_mass_mul(P, S, d, Md);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) { uMd += (u[i] - d[i]) * Md[i]; dMd += d[i] * Md[i]; }
-  T lo = T(0), hi = T(1), alpha = T(1), da, ha;
-  for (int ls = 0; ls < 8; ++ls) {
-    cube_line<T, UNR>(P, S, u, d, uMd, dMd, alpha, da, ha);
-    CN_STAT_LS();
-    if (ls > 0) {
-      if (t_abs(da) <= thresh) break;
-      if (da < T(0)) lo = alpha; else hi = alpha;
-    }
-    T an = alpha - da / ha;                         // Newton step on phi' (first from alpha = 1)
-    if (!(an > lo && an < hi)) an = T(0.5) * (lo + hi);
-    if (hi - lo <= T(4) * eps_of<T>() * hi) { alpha = lo > T(0) ? lo : an; break; }
-    alpha = (ls == 7 && lo > T(0)) ? lo : an;      // evaluation budget spent: keep a point with phi' <= 0
-  }
-  const T back = T(1) - alpha;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) u[i] -= back * d[i];
-  d0 = T(0);
-}
+enum { NEWTON_DONE = 0, NEWTON_CONTINUE = 1 };
 
 // Line-search state of the unified Newton visit below (one bracket on the pending direction).
 template <typename T> struct CubeTrial {
   T alpha, lo, hi;   // u = u0 + alpha d is the tentative point; phi' < 0 at lo, > 0 at hi
 };
 
-// One schedulable Newton VISIT for the wavefront kernel: exactly one gradient/Hessian evaluation,
-// no inner loop.  Differs from cube_newton_step + cube_line_search only in how a rejected step is
-// searched: the safeguarded Newton iteration on phi'(alpha) takes ONE trial per visit, using the
-// gradient and the curvature d^T H d of the full evaluation at the trial point (phi'' exactly), so
-// every lane of a warp runs the same code and there is no separate line-search queue.  A gradient
-// below cfg.tol_final (quadratic regime: the next step lands at rounding level) takes the step and
+// One Newton VISIT = exactly one gradient/Hessian evaluation, no inner loop (the unit the wavefront
+// kernel schedules; the per-thread kernels simply loop over visits).  State: u (current, possibly
+// tentative point u0 + alpha d), d / d0 = phi'(0) of the pending direction (d0 = 0: nothing pending),
+// the bracket tr, best_res2, it.  The step taken by the previous visit is accepted or rejected
+// lazily from the gradient at the new point, which the evaluation for the next direction provides
+// anyway: the full step one-sidedly (phi'(1) <= ls_c |phi'(0)|), an interior trial on
+// |phi'(alpha)| <= ls_c |phi'(0)|.  A rejected point moves the bracket and the next trial is one
+// safeguarded Newton iteration on phi'(alpha), with phi'' = d^T H d exact from this evaluation.
+// Stops: scaled gradient below tol_rel; three evaluations without a 4x reduction of the best residual
+// below tol_stall (rounding floor of the sample's conditioning); iteration cap.  A gradient below
+// cfg.tol_final (quadratic regime: the next step lands at rounding level) takes the step and
 // finishes without the confirming evaluation.
 //   it: bits 0-7 Newton directions taken, 8-15 trials on the pending direction (0xff = forced
 //   accept), 16+ rounding-floor counter.  Returns NEWTON_DONE or NEWTON_CONTINUE.
@@ -462,31 +369,20 @@ CN_HD int cube_newton_visit(const CubeParams<T>& P, const CubeProb<T>& S, const 
   return NEWTON_CONTINUE;
 }
 
-// The visit-by-visit solve (what the wavefront kernel runs, per lane).
+// Newton solve from u (in: start point -- zero, or the previous step's solution as a warm start;
+// out: optimum).  Returns the number of Newton directions taken.
 template <typename T, int UNR>
-CN_HD int cube_solve_visits(const CubeParams<T>& P, const CubeProb<T>& S, const SolverCfg<T>& cfg, T* u) {
+CN_HD int cube_solve(const CubeParams<T>& P, const CubeProb<T>& S, const SolverCfg<T>& cfg, T* u) {
   int it = 0;
-  if (!cube_trivially_solved<T, UNR>(S)) {
+  if (cube_trivially_solved<T, UNR>(S)) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) u[i] = T(0);
+  } else {
     T d[6], d0 = T(0), best = T(-1);
     CubeTrial<T> tr{T(1), T(0), T(1)};
     while (cube_newton_visit<T, UNR>(P, S, cfg, u, d, d0, best, tr, it) != NEWTON_DONE) {}
   }
   return it & 0xff;
-}
-
-// Newton solve from u (in: start point, out: optimum).  Returns iterations.
-template <typename T, int UNR>
-CN_HD int cube_solve(const CubeParams<T>& P, const CubeProb<T>& S, const SolverCfg<T>& cfg, T* u) {
-  int it = 0;
-  if (!cube_trivially_solved<T, UNR>(S)) {
-    T d[6], d0 = T(0), best = T(-1);
-    while (true) {
-      const int st = cube_newton_step<T, UNR>(P, S, cfg, u, d, d0, best, it);
-      if (st == NEWTON_DONE) break;
-      if (st == NEWTON_LINESEARCH) cube_line_search<T, UNR>(P, S, cfg, u, d, d0);
-    }
-  }
-  return it & 0xffff;
 }
 
 // ---------------------------------------------------------------------------
@@ -785,15 +681,24 @@ CN_HD void cube_step_epilogue(const CubeParams<T>& P, const CubeProb<T>& S, cons
   for (int i = 0; i < 6; ++i) xn[7 + i] = vn[i];
 }
 
+// warm (nullable, in/out): the contact velocity change u of the toss's previous step as the start
+// point of this step's solve (the optimum is unique, so only the iteration count depends on it).
 template <typename T>
-CN_HD int cube_step_sample(const CubeParams<T>& P, const SolverCfg<T>& cfg, const T* x, T* xn, T* force_out) {
+CN_HD int cube_step_sample(const CubeParams<T>& P, const SolverCfg<T>& cfg, const T* x, T* xn, T* force_out,
+                           T* warm = nullptr) {
   T store[CUBE_PROB_FIELDS];
   const CubeProb<T> S{store, 1};
   CubeStepAux<T> A;
   cube_step_prologue<T, 4>(P, x, S, A);
-  T u[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  T u[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) u[i] = warm ? warm[i] : T(0);
   const int it = cube_solve<T, 4>(P, S, cfg, u);
   cube_step_epilogue<T, 4>(P, S, A, x, u, xn, force_out);
+  if (warm) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) warm[i] = u[i];
+  }
   return it;
 }
 

@@ -291,26 +291,6 @@ CN_HD void elbow_eval(const ElbowParams<T>& P, const ElbowProb<T>& S, const T* u
   scale2 = t_max(a2, b2);
 }
 
-template <typename T>
-CN_HD void elbow_line(const ElbowParams<T>& P, const ElbowProb<T>& S, const T* u1, const T* d, T uMd, T dMd, T alpha,
-                      T& d1, T& d2) {
-  d1 = uMd + alpha * dMd;
-  d2 = dMd;
-  const T back = T(1) - alpha;
-  for (int c = 0; c < EL_NC; ++c) {
-    const T mu = P.mu[c >> 2];
-    T r[3], e[3], f[3], K[6];
-    elbow_residual(P, S, c, u1, r);
-    elbow_point_vel(S, c, d, e);
-    e[0] *= mu; e[1] *= mu;
-    for (int j = 0; j < 3; ++j) r[j] -= back * e[j];
-    cone_eval<T, true>(r, P.inv_eps, T(1), f, K);
-    d1 -= e[0] * f[0] + e[1] * f[1] + e[2] * f[2];
-    d2 += e[0] * (K[0] * e[0] + K[1] * e[1] + K[2] * e[2]) + e[1] * (K[1] * e[0] + K[3] * e[1] + K[4] * e[2]) +
-          e[2] * (K[2] * e[0] + K[4] * e[1] + K[5] * e[2]);
-  }
-}
-
 template <typename T> CN_HD bool elbow_trivially_solved(const ElbowProb<T>& S) {
   bool open = true;
   for (int c = 0; c < EL_NC; ++c) {
@@ -320,12 +300,15 @@ template <typename T> CN_HD bool elbow_trivially_solved(const ElbowProb<T>& S) {
   return open;
 }
 
-// Newton solve (same algorithm as cube_newton_step / cube_line_search, n_v = 7, Cholesky solve)
+// Newton solve: the same visit scheme as cube_newton_visit (one gradient/Hessian evaluation per
+// visit; rejected steps are searched by safeguarded Newton trials on phi'(alpha) that reuse the full
+// evaluation), n_v = 7, Cholesky solve.
 template <typename T>
 CN_HD int elbow_solve(const ElbowParams<T>& P, const ElbowProb<T>& S, const SolverCfg<T>& cfg, T* u) {
   int it = 0;
   if (elbow_trivially_solved(S)) return 0;
   T d[7], d0 = T(0), best = T(-1);
+  T alpha = T(1), lo = T(0), hi = T(1);
   while (true) {
     T g[7], H[49], res2, scale2;
     elbow_eval<T, true>(P, S, u, g, H, res2, scale2);
@@ -337,37 +320,35 @@ CN_HD int elbow_solve(const ElbowParams<T>& P, const ElbowProb<T>& S, const Solv
       it &= 0xffff;
     }
     if (res2 < best || best < T(0)) best = res2;
-    if (d0 < T(0)) {
+    const int trials = (it >> 8) & 0xff;
+    if (d0 < T(0) && trials != 0xff) {
       T d1 = T(0);
       for (int i = 0; i < 7; ++i) d1 += g[i] * d[i];
-      if (!(d1 <= -cfg.ls_c * d0)) {
-        // line search along the pending step (u holds u0 + d)
-        const T thresh = -cfg.ls_c * d0;
-        T uMd = T(0), dMd = T(0);
+      const T thresh = -cfg.ls_c * d0;
+      const bool accept = trials == 0 ? (d1 <= thresh) : (t_abs(d1) <= thresh);
+      if (!accept) {
+        if (d1 < T(0)) lo = alpha; else hi = alpha;
+        T d2 = T(0);
         for (int i = 0; i < 7; ++i) {
-          T s = T(0);
-          for (int j = 0; j < 7; ++j) s += S.M[7 * i + j] * d[j];
-          uMd += (u[i] - d[i]) * s; dMd += d[i] * s;
+          T row = T(0);
+          for (int j = 0; j < 7; ++j) row += H[j <= i ? 7 * i + j : 7 * j + i] * d[j];
+          d2 += d[i] * row;
         }
-        T lo = T(0), hi = T(1), alpha = T(1), da, ha;
-        for (int ls = 0; ls < 8; ++ls) {
-          elbow_line(P, S, u, d, uMd, dMd, alpha, da, ha);
-          if (ls > 0) {
-            if (t_abs(da) <= thresh) break;
-            if (da < T(0)) lo = alpha; else hi = alpha;
-          }
-          T an = alpha - da / ha;
-          if (!(an > lo && an < hi)) an = T(0.5) * (lo + hi);
-          if (hi - lo <= T(4) * eps_of<T>() * hi) { alpha = lo > T(0) ? lo : an; break; }
-          alpha = (ls == 7 && lo > T(0)) ? lo : an;
+        T an = alpha - d1 / d2;
+        if (!(an > lo && an < hi)) an = T(0.5) * (lo + hi);
+        int nt = trials + 1;
+        if (hi - lo <= T(4) * eps_of<T>() * hi || nt >= 7) {
+          an = lo > T(0) ? lo : an;
+          nt = 0xff;
         }
-        const T back = T(1) - alpha;
-        for (int i = 0; i < 7; ++i) u[i] -= back * d[i];
-        d0 = T(0);
+        const T step = an - alpha;
+        for (int i = 0; i < 7; ++i) u[i] += step * d[i];
+        alpha = an;
+        it = (it & ~0xff00) | (nt << 8);
         continue;
       }
     }
-    if ((it & 0xffff) >= cfg.max_iter) break;
+    if ((it & 0xff) >= cfg.max_iter) break;
     T inv_diag[7], ng[7];
     chol_factor<T, 7>(H, inv_diag);
     for (int i = 0; i < 7; ++i) ng[i] = -g[i];
@@ -375,9 +356,11 @@ CN_HD int elbow_solve(const ElbowParams<T>& P, const ElbowProb<T>& S, const Solv
     T dd = T(0);
     for (int i = 0; i < 7; ++i) { dd += g[i] * d[i]; u[i] += d[i]; }
     d0 = dd < T(0) ? dd : T(0);
-    ++it;
+    alpha = T(1); lo = T(0); hi = T(1);
+    it = (it & ~0xff00) + 1;
+    if (res2 <= cfg.tol_final * cfg.tol_final * scale2) break;
   }
-  return it & 0xffff;
+  return it & 0xff;
 }
 
 // ---------------------------------------------------------------------------

@@ -390,8 +390,9 @@ cube_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, c
 #pragma unroll
     for (int i = 0; i < 13; ++i) { xc[i] = T(x0[b * 13 + i]); out[i] = IO(xc[i]); }
     int total = 0;
+    T warm[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
     for (int s = 0; s < steps; ++s) {
-      total += cn::cube_step_sample<T>(P, cfg, xc, xn, force ? fo : nullptr);
+      total += cn::cube_step_sample<T>(P, cfg, xc, xn, force ? fo : nullptr, warm);
       if (force) {
 #pragma unroll
         for (int i = 0; i < 12; ++i) force[(b * steps + s) * 12 + i] = IO(fo[i]);

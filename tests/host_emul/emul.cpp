@@ -21,26 +21,6 @@ int emul_cube_loss_f64(const double* x, const double* xp, const double* inertia,
   }
   return 0;
 }
-// the wavefront kernel's per-lane solve (one evaluation per visit, no separate line search)
-int emul_cube_loss_visits_f64(const double* x, const double* xp, const double* inertia, const double* mu,
-                              const double* half, double dt, double eps, int64_t B, double* loss, double* force,
-                              int32_t* iters, double* grad) {
-  CubeParams<double> P;
-  cube_params_init(P, inertia, mu, half, dt, eps);
-  SolverCfg<double> cfg = default_cfg<double>();
-  for (int i = 0; i < CUBE_NPARAM; ++i) if (grad) grad[i] = 0;
-  for (int64_t b = 0; b < B; ++b) {
-    double store[CUBE_PROB_FIELDS];
-    const CubeProb<double> S{store, 1};
-    CubeLossAux<double> A;
-    cube_loss_prologue<double, 1>(P, x + 13 * b, xp + 13 * b, S, A);
-    double u[6] = {0, 0, 0, 0, 0, 0};
-    const int it = cube_solve_visits<double, 1>(P, S, cfg, u);
-    loss[b] = cube_loss_epilogue<double, 1>(P, S, A, u, grad, force ? force + 12 * b : nullptr);
-    if (iters) iters[b] = it;
-  }
-  return 0;
-}
 // fp32 variant = fp32 storage, fp64 arithmetic (as the kernels: T = double, IO = float)
 int emul_cube_loss_f32(const float* x, const float* xp, const float* inertia, const float* mu,
                        const float* half, float dt, float eps, int64_t B, float* loss, float* force,

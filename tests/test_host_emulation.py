@@ -16,7 +16,7 @@ from tests.util import dptr, host_emulation_lib, kernel_level_params, load_golde
 CASES = ['cube_real_nominal', 'cube_real_perturbed', 'cube_synthetic']
 
 
-def emul_loss(g, dtype=np.float64, visits=False):
+def emul_loss(g, dtype=np.float64):
     lib = host_emulation_lib()
     inertia, mu, half = kernel_level_params(g)
     x = np.ascontiguousarray(g['x'], dtype=dtype)
@@ -26,8 +26,6 @@ def emul_loss(g, dtype=np.float64, visits=False):
     iters, grad = np.zeros(B, np.int32), np.zeros(14, dtype)
     ct = ctypes.c_double if dtype == np.float64 else ctypes.c_float
     fn = lib.emul_cube_loss_f64 if dtype == np.float64 else lib.emul_cube_loss_f32
-    if visits:
-        fn = lib.emul_cube_loss_visits_f64
     fn(dptr(x), dptr(xp), dptr(inertia.astype(dtype)), dptr(mu.astype(dtype)), dptr(half.astype(dtype)),
        ct(float(g['dt'])), ct(1e-3), ctypes.c_int64(B), dptr(loss), dptr(force), dptr(iters), dptr(grad))
     return loss, force, iters, grad
@@ -47,13 +45,10 @@ def chain_to_leaves(g, grad14):
     return theta.grad.numpy(), fr.grad.numpy(), ln.grad.numpy()
 
 
-@pytest.mark.parametrize('visits', [False, True], ids=['step+linesearch', 'visits'])
 @pytest.mark.parametrize('name', CASES)
-def test_device_math_fp64_matches_reference_golden(name, visits):
-    """Both per-sample solver drivers: Newton step + derivative line search (simple kernels, rollout) and
-    the one-evaluation-per-visit form the wavefront loss kernel schedules."""
+def test_device_math_fp64_matches_reference_golden(name):
     g = load_golden(name)
-    loss, force, iters, grad = emul_loss(g, visits=visits)
+    loss, force, iters, grad = emul_loss(g)
     B = loss.shape[0]
     assert np.abs(loss - g['loss']).max() < 1e-13
     assert rel_err(loss, g['loss'], 1e-9).max() < 1e-9            # north_star: 1e-9 relative, fp64
