@@ -379,12 +379,18 @@ template <typename T, typename IO>
 __global__ void __launch_bounds__(kLossThreads)
 cube_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, const IO* __restrict__ mu,
                     const IO* __restrict__ half, T dt, T eps, int64_t B, int steps, IO* __restrict__ traj,
-                    IO* __restrict__ force, int32_t* __restrict__ iters) {
+                    IO* __restrict__ force, int32_t* __restrict__ iters, int lanes_per_warp) {
+  // A toss is a sequential chain of `steps` solves whose lengths differ per toss, and a warp advances
+  // at the pace of its slowest lane: small batches are therefore spread thinly (lanes_per_warp < 32
+  // tosses per warp) so that every SM sub-partition holds warps and each waits for few neighbours.
+  const int lane = threadIdx.x & 31;
+  if (lane >= lanes_per_warp) return;
   cn::CubeParams<T> P;
   load_cube_params<T, IO>(P, inertia, mu, half, dt, eps);
   const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t stride = (((int64_t)gridDim.x * blockDim.x) >> 5) * lanes_per_warp;
+  for (int64_t b = warp * lanes_per_warp + lane; b < B; b += stride) {
     T xc[13], xn[13], fo[12];
     IO* out = traj + b * (int64_t)(steps + 1) * 13;
 #pragma unroll
@@ -650,11 +656,16 @@ int launch_cube_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO*
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_rollout_kernel<T, IO>, kLossThreads, 0);
   if (per_sm < 1) per_sm = 1;
-  int64_t need = (B + kLossThreads - 1) / kLossThreads;
-  int64_t cap = (int64_t)di.sms * per_sm;
-  int blocks = (int)(need < cap ? need : cap);
+  const int64_t cap = (int64_t)di.sms * per_sm;                      // resident blocks
+  const int64_t warps = cap * (kLossThreads / 32);
+  int lpw = (int)((B + warps - 1) / warps);                          // tosses per warp when spread over all of them
+  if (lpw < 1) lpw = 1;
+  if (lpw > 32) lpw = 32;
+  const int64_t per_block = (int64_t)lpw * (kLossThreads / 32);
+  const int64_t need = (B + per_block - 1) / per_block;
+  const int blocks = (int)(need < cap ? need : cap);
   cube_rollout_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x0, inertia, mu, half, dt, eps, B, steps, traj, force,
-                                                          iters);
+                                                          iters, lpw);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPLL_OK : (int)e;
 }
