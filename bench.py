@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument('--cpu-sample', type=int, default=65536, help='samples in the CPU baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='skip the other BASELINE.json configs')
+    ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of the CUDA-graph replay')
     ap.add_argument('--variant', type=int, default=0, help='0 = wavefront loss kernel, 1 = one sample per thread')
     return ap.parse_args()
 
@@ -149,15 +150,19 @@ def secondary_configs(device):
     system = make_system(device, torch.float64)
     x, xp = make_batch(system, 65536, 11, device, torch.float64)
 
+    from dair_pll_b200 import parallel
+    reducer = parallel.GradientAllReduce(list(system.parameters()), device, 1)
+
     def cube_step(xx, xxp):
-        for p in system.parameters():
-            p.grad = None
-        system.contactnets_loss(xx, None, xxp).mean().backward()
-    ms = _time_gpu(lambda: cube_step(x, xp), device, 10)
-    out['cube_loss_backward_B65536_f64'] = {'ms': ms, 'samples_per_s': 65536 / ms * 1e3}
-    xf, xpf = x.float(), xp.float()
-    ms = _time_gpu(lambda: cube_step(xf, xpf), device, 10)
-    out['cube_loss_backward_B65536_f32_storage'] = {'ms': ms, 'samples_per_s': 65536 / ms * 1e3}
+        reducer.zero()
+        mean = system.contactnets_loss(xx, None, xxp).mean()
+        mean.backward()
+        return reducer(mean)
+    for name, (xx, xxp) in {'f64': (x, xp), 'f32_storage': (x.float(), xp.float())}.items():
+        ms_eager = _time_gpu(lambda: cube_step(xx, xxp), device, 10)
+        graphed = parallel.GraphedStep(lambda: cube_step(xx, xxp), device)
+        ms = _time_gpu(graphed, device, 20)
+        out[f'cube_loss_backward_B65536_{name}'] = {'ms': ms, 'samples_per_s': 65536 / ms * 1e3, 'eager_ms': ms_eager}
     # config 4: rollout, 4,096 cube tosses x 80 steps
     x0 = synthetic.cube_states(4096, seed=5, device=device)
     carry = torch.zeros(4096, 1, device=device)
@@ -303,7 +308,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_step = timed(step_resident, args.steps, max(args.warmup, 3))
+    ms_eager = timed(step_resident, args.steps, max(args.warmup, 3))
+    if args.no_graph:
+        ms_step = ms_eager
+    else:
+        # the same step, captured once into a CUDA graph and replayed (parallel.GraphedStep)
+        graphed = parallel.GraphedStep(step_resident, device)
+        ms_step = timed(graphed, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
     value = world * B / (ms_step * 1e-3)
 
@@ -379,7 +390,9 @@ def main():
         'config': {'workload': f'cube_contactnets_loss_backward_B{B}_per_gpu', 'batch_per_gpu': B,
                    'global_batch': world * B, 'dt': DT, 'eps': 1e-3, 'parallelism': f'dp{world}',
                    'l2_policy': f'inputs larger than L2 ({2 * B * 13 * x.element_size() / 1e6:.0f} MB per step vs 126 MB)',
-                   'mean_newton_iters': mean_iters},
+                   'mean_newton_iters': mean_iters,
+                   'step': 'eager launches' if args.no_graph else 'CUDA graph replay of the public-API step',
+                   'eager_ms_per_step': ms_eager},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h},
         'gpu_launches': 6 * args.steps,   # per step: prepare + loss/backward + reduce/chain, and the same three

@@ -7,7 +7,7 @@ all-reduce moves a flat buffer [d/d theta (n_b x 10), d/d friction (n_g), d/d le
 (15 doubles for the cube).  Parameter ``.grad`` tensors are views into that buffer, so autograd
 accumulates straight into the NCCL send buffer and nothing is packed or copied per step.
 """
-from typing import List, Optional
+from typing import Callable, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -61,6 +61,32 @@ class GradientAllReduce:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.mul_(1.0 / self.world)
         return self.flat
+
+
+class GraphedStep:
+    """One training step (forward, backward, gradient all-reduce) captured into a CUDA graph and replayed.
+
+    A step over device-resident data is one long kernel plus a dozen microsecond-sized launches (parameter
+    preparation, fixed-order reduction, ``mean`` and its backward, the NCCL all-reduce); replaying them as a
+    graph removes the Python/launch overhead between them, which is what bounds small batches.  ``fn`` must be
+    free of host synchronisation and must write its results into the same tensors on every call (the
+    ``GradientAllReduce`` flat buffer does).  The kernels take the capturing stream through the C ABI."""
+
+    def __init__(self, fn: Callable[[], Tensor], device: torch.device, warmup: int = 3) -> None:
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+
+    def __call__(self) -> Tensor:
+        self.graph.replay()
+        return self.out
 
 
 class HostBatchPipeline:
