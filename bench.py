@@ -277,12 +277,16 @@ def main():
     params = [p for p in system.parameters()]
     reducer = parallel.GradientAllReduce(params, device, world)
 
-    def step_resident():
+    def step_local():
         reducer.zero()
         loss = system.contactnets_loss(x, u, xp)
         mean = loss.mean()
         mean.backward()
-        return reducer(mean)          # all-reduce(sum)/world of [grads..., loss]; returns flat device buffer
+        return reducer.stage(mean)    # flat device buffer [grads..., loss] of this rank
+
+    def step_resident():
+        step_local()
+        return reducer.reduce()       # ONE all-reduce(sum)/world over NCCL
 
     def barrier():
         if world > 1:
@@ -313,8 +317,12 @@ def main():
         ms_step = ms_eager
     else:
         # the same step, captured once into a CUDA graph and replayed (parallel.GraphedStep)
-        graphed = parallel.GraphedStep(step_resident, device)
-        ms_step = timed(graphed, args.steps, max(args.warmup, 3))
+        graphed = parallel.GraphedStep(step_local, device)
+
+        def step_graphed():
+            graphed()
+            return reducer.reduce()
+        ms_step = timed(step_graphed, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
     value = world * B / (ms_step * 1e-3)
 
@@ -391,7 +399,7 @@ def main():
                    'global_batch': world * B, 'dt': DT, 'eps': 1e-3, 'parallelism': f'dp{world}',
                    'l2_policy': f'inputs larger than L2 ({2 * B * 13 * x.element_size() / 1e6:.0f} MB per step vs 126 MB)',
                    'mean_newton_iters': mean_iters,
-                   'step': 'eager launches' if args.no_graph else 'CUDA graph replay of the public-API step',
+                   'step': 'eager launches' if args.no_graph else 'CUDA graph replay of the public-API step (rank-local part) + NCCL all-reduce',
                    'eager_ms_per_step': ms_eager},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h},

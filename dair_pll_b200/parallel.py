@@ -53,24 +53,35 @@ class GradientAllReduce:
                 p.grad = g
             off += p.numel()
 
-    def __call__(self, local_mean_loss: Tensor) -> Tensor:
-        """Averages gradients (already in ``flat``) and the loss over ranks; returns ``flat``."""
+    def stage(self, local_mean_loss: Tensor) -> Tensor:
+        """Local half: makes sure the gradients live in ``flat`` and appends this rank's mean loss."""
         self.rebind()
         self.flat[-1:].copy_(local_mean_loss.detach().reshape(1))
+        return self.flat
+
+    def reduce(self) -> Tensor:
+        """Collective half: ONE all-reduce of ``flat`` (sum / world) over NCCL (gloo in the CPU tests)."""
         if self.world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.mul_(1.0 / self.world)
         return self.flat
 
+    def __call__(self, local_mean_loss: Tensor) -> Tensor:
+        """Averages gradients (already in ``flat``) and the loss over ranks; returns ``flat``."""
+        self.stage(local_mean_loss)
+        return self.reduce()
+
 
 class GraphedStep:
-    """One training step (forward, backward, gradient all-reduce) captured into a CUDA graph and replayed.
+    """The rank-local part of a training step (forward, backward, staging of the flat gradient buffer)
+    captured into a CUDA graph and replayed.
 
     A step over device-resident data is one long kernel plus a dozen microsecond-sized launches (parameter
-    preparation, fixed-order reduction, ``mean`` and its backward, the NCCL all-reduce); replaying them as a
-    graph removes the Python/launch overhead between them, which is what bounds small batches.  ``fn`` must be
-    free of host synchronisation and must write its results into the same tensors on every call (the
-    ``GradientAllReduce`` flat buffer does).  The kernels take the capturing stream through the C ABI."""
+    preparation, fixed-order reduction, ``mean`` and its backward); replaying them as a graph removes the
+    Python/launch overhead between them, which is what bounds small batches.  ``fn`` must be free of host
+    synchronisation and of collectives (the NCCL all-reduce is issued after the replay, on the same stream)
+    and must write its results into the same tensors on every call (``GradientAllReduce.stage`` does).  The
+    kernels take the capturing stream through the C ABI."""
 
     def __init__(self, fn: Callable[[], Tensor], device: torch.device, warmup: int = 3) -> None:
         side = torch.cuda.Stream(device=device)
