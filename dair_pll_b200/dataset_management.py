@@ -1,0 +1,102 @@
+"""Training slices resident on the device.
+
+The reference keeps a Python list of per-index tensor slices and feeds it through a
+``torch.utils.data.DataLoader`` (dataset_management.py:17-67); at ~1e9 samples/s that loader is the
+bottleneck.  Here every trajectory is sliced once with the same index arithmetic
+(``add_slices_from_trajectory``, dataset_management.py:43-59) into two dense device tensors, and an
+epoch is one on-device permutation plus gathers, so batches never touch the host.
+
+On-disk format of the reference: one ``torch.save``d ``(T, n_x)`` float64 tensor per trajectory,
+named ``<index>.pt`` (file_utils.py:16,168-176).
+"""
+import os
+from dataclasses import dataclass
+from typing import Iterator, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+
+@dataclass
+class TrajectorySliceConfig:
+    """Same fields and checks as the reference's ``data_config.TrajectorySliceConfig`` (data_config.py:5-19)."""
+    t_skip: int = 0
+    t_history: int = 1
+    t_prediction: int = 1
+
+    def __post_init__(self):
+        assert self.t_skip + 1 >= self.t_history
+        assert self.t_history >= 1
+        assert self.t_prediction >= 1
+
+
+class DeviceTrajectorySliceDataset:
+    """(previous states, future states) transition pairs of a set of trajectories, as two dense tensors
+    ``(N, t_history, n_x)`` and ``(N, t_prediction, n_x)`` on ``device``; indexable like the reference's
+    ``TrajectorySliceDataset`` and iterable in shuffled device batches."""
+
+    def __init__(self, config: TrajectorySliceConfig, device: torch.device = torch.device('cpu'),
+                 dtype: torch.dtype = torch.float64) -> None:
+        self.config = config
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self._previous: List[Tensor] = []
+        self._future: List[Tensor] = []
+        self._dense: Optional[Tuple[Tensor, Tensor]] = None
+
+    def add_slices_from_trajectory(self, trajectory: Tensor) -> None:
+        """``trajectory``: (T, n_x).  Slice i predicts from time index ``t_skip + i``
+        (dataset_management.py:49-59): previous = traj[idx+1-t_history : idx+1], future = traj[idx+1 : idx+1+t_prediction]."""
+        cfg = self.config
+        T = trajectory.shape[0]
+        first, last = cfg.t_skip, T - cfg.t_prediction
+        assert first <= last
+        if last == first:
+            return
+        traj = trajectory.to(device=self.device, dtype=self.dtype)
+        # unfold gives (windows, n_x, window) views: window w starts at time index w
+        prev = traj.unfold(0, cfg.t_history, 1)[first + 1 - cfg.t_history:last + 1 - cfg.t_history]
+        fut = traj.unfold(0, cfg.t_prediction, 1)[first + 1:last + 1]
+        self._previous.append(prev.transpose(1, 2).contiguous())
+        self._future.append(fut.transpose(1, 2).contiguous())
+        self._dense = None
+
+    def add_trajectories_from_directory(self, trajectory_dir: str, indices: Optional[List[int]] = None) -> int:
+        """Loads ``<index>.pt`` trajectories (all whole-number-named files when ``indices`` is None)."""
+        if indices is None:
+            indices = sorted(int(f[:-3]) for f in os.listdir(trajectory_dir) if f.endswith('.pt') and f[:-3].isdigit())
+        for i in indices:
+            self.add_slices_from_trajectory(torch.load(os.path.join(trajectory_dir, f'{i}.pt'), map_location='cpu'))
+        return len(indices)
+
+    def tensors(self) -> Tuple[Tensor, Tensor]:
+        """(previous (N, t_history, n_x), future (N, t_prediction, n_x)), device-resident."""
+        if self._dense is None:
+            if not self._previous:
+                raise ValueError('empty dataset')
+            self._dense = (torch.cat(self._previous, 0), torch.cat(self._future, 0))
+            self._previous, self._future = [self._dense[0]], [self._dense[1]]
+        return self._dense
+
+    def __len__(self) -> int:
+        return sum(p.shape[0] for p in self._previous)
+
+    def __getitem__(self, idx) -> Tuple[Tensor, Tensor]:
+        prev, fut = self.tensors()
+        return prev[idx], fut[idx]
+
+    def batches(self, batch_size: int, shuffle: bool = True, generator: Optional[torch.Generator] = None,
+                drop_last: bool = False) -> Iterator[Tuple[Tensor, Tensor]]:
+        """One epoch: a permutation drawn on the device and one gather per batch."""
+        prev, fut = self.tensors()
+        n = prev.shape[0]
+        order = torch.randperm(n, device=self.device, generator=generator) if shuffle else None
+        for lo in range(0, n, batch_size):
+            hi = min(lo + batch_size, n)
+            if drop_last and hi - lo < batch_size:
+                return
+            if order is None:
+                yield prev[lo:hi], fut[lo:hi]
+            else:
+                idx = order[lo:hi]
+                yield prev.index_select(0, idx), fut.index_select(0, idx)

@@ -105,3 +105,32 @@ def test_library_exports_every_declared_symbol():
     lib.dpll_workspace_bytes.restype = ctypes.c_size_t
     assert lib.dpll_version() >= 100
     assert lib.dpll_workspace_bytes() >= 14 * 8
+
+
+def test_device_slice_dataset_matches_reference_slicing(tmp_path):
+    """Same (previous, future) pairs, in the same order, as the reference's per-index loop
+    (dataset_management.py:43-59), from the reference's on-disk format (<index>.pt, file_utils.py:173-176)."""
+    from dair_pll_b200.dataset_management import DeviceTrajectorySliceDataset, TrajectorySliceConfig
+    gen = torch.Generator().manual_seed(0)
+    trajs = [torch.randn(T, 13, generator=gen, dtype=torch.float64) for T in (9, 4, 17)]
+    for i, t in enumerate(trajs):
+        torch.save(t, tmp_path / f'{i}.pt')
+    (tmp_path / 'notes.txt').write_text('ignored')
+    for cfg in (TrajectorySliceConfig(), TrajectorySliceConfig(t_skip=2, t_history=3, t_prediction=2)):
+        ds = DeviceTrajectorySliceDataset(cfg)
+        assert ds.add_trajectories_from_directory(str(tmp_path)) == 3
+        prev_ref, fut_ref = [], []
+        for tr in trajs:                               # the reference's loop, restated
+            for index in range(cfg.t_skip, tr.shape[0] - cfg.t_prediction):
+                prev_ref.append(tr[index + 1 - cfg.t_history:index + 1])
+                fut_ref.append(tr[index + 1:index + 1 + cfg.t_prediction])
+        assert len(ds) == len(prev_ref)
+        prev, fut = ds.tensors()
+        assert torch.equal(prev, torch.stack(prev_ref)) and torch.equal(fut, torch.stack(fut_ref))
+        p5, f5 = ds[5]
+        assert torch.equal(p5, prev_ref[5]) and torch.equal(f5, fut_ref[5])
+        seen = torch.cat([p[:, -1, 0] for p, _ in ds.batches(7, generator=torch.Generator().manual_seed(1))])
+        assert seen.shape[0] == len(ds) and torch.equal(seen.sort().values, prev[:, -1, 0].sort().values)
+        assert sum(p.shape[0] for p, _ in ds.batches(7, drop_last=True)) == (len(ds) // 7) * 7
+    with pytest.raises(AssertionError):
+        TrajectorySliceConfig(t_skip=0, t_history=2)
