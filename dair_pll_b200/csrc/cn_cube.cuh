@@ -342,7 +342,7 @@ CN_HD int cube_newton_visit(const CubeParams<T>& P, const CubeProb<T>& S, const 
         for (int j = 0; j < 6; ++j) row += H[j <= i ? 6 * i + j : 6 * j + i] * d[j];
         d2 += d[i] * row;
       }
-      T an = tr.alpha - d1 / d2;
+      T an = tr.alpha - d1 * t_rcp(d2);
       if (!(an > tr.lo && an < tr.hi)) an = T(0.5) * (tr.lo + tr.hi);
       int nt = trials + 1;
       if (tr.hi - tr.lo <= T(4) * eps_of<T>() * tr.hi || nt >= 7) {   // budget spent: keep a point with phi' <= 0
@@ -424,7 +424,8 @@ CN_HD void cube_loss_prologue(const CubeParams<T>& P, const T* x, const T* xp, c
 #pragma unroll
     for (int i = 0; i < 3; ++i) { ed[i] += dvW[3 + i]; ev[i] += vW[3 + i]; }
     const T sx = P.mu * ev[0], sy = P.mu * ev[1];
-    const T speed = t_sqrt(sx * sx + sy * sy);
+    const T speed2 = sx * sx + sy * sy;
+    const T speed = speed2 > T(0) ? speed2 * t_rsqrt(speed2) : T(0);
     const T phic = rho[2] + A.pos_z;
     S.q(3 * c) = -P.mu * ed[0] + P.dt * sx;                       // :158-161
     S.q(3 * c + 1) = -P.mu * ed[1] + P.dt * sy;
@@ -577,8 +578,9 @@ CN_HD T cube_loss_epilogue(const CubeParams<T>& P, const CubeProb<T>& S, const C
     for (int i = 0; i < 3; ++i) { eb[i] += b[3 + i]; ev[i] += A.vp[3 + i]; }
     const T ftx = f[0], fty = f[1], fn = f[2];
     const T sx = P.mu * ev[0], sy = P.mu * ev[1];
-    const T speed = t_sqrt(sx * sx + sy * sy);
-    const T ux = speed > T(0) ? sx / speed : T(0), uy = speed > T(0) ? sy / speed : T(0);
+    const T speed2 = sx * sx + sy * sy;
+    const T sinv = speed2 > T(0) ? t_rsqrt(speed2) : T(0);
+    const T ux = sx * sinv, uy = sy * sinv;
     const T gx = P.dt * (fn * ux + ftx), gy = P.dt * (fn * uy + fty);
     gmu += ftx * eb[0] + fty * eb[1] + gx * ev[0] + gy * ev[1];
     const T ft[3] = {P.mu * ftx, P.mu * fty, fn};
