@@ -425,7 +425,7 @@ CN_HD void cube_loss_prologue(const CubeParams<T>& P, const T* x, const T* xp, c
     for (int i = 0; i < 3; ++i) { ed[i] += dvW[3 + i]; ev[i] += vW[3 + i]; }
     const T sx = P.mu * ev[0], sy = P.mu * ev[1];
     const T speed2 = sx * sx + sy * sy;
-    const T speed = speed2 > T(0) ? speed2 * t_rsqrt(speed2) : T(0);
+    const T speed = speed2 * t_rsqrt(t_max(speed2, t_tiny<T>()));
     const T phic = rho[2] + A.pos_z;
     S.q(3 * c) = -P.mu * ed[0] + P.dt * sx;                       // :158-161
     S.q(3 * c + 1) = -P.mu * ed[1] + P.dt * sy;
@@ -579,7 +579,7 @@ CN_HD T cube_loss_epilogue(const CubeParams<T>& P, const CubeProb<T>& S, const C
     const T ftx = f[0], fty = f[1], fn = f[2];
     const T sx = P.mu * ev[0], sy = P.mu * ev[1];
     const T speed2 = sx * sx + sy * sy;
-    const T sinv = speed2 > T(0) ? t_rsqrt(speed2) : T(0);
+    const T sinv = t_rsqrt(t_max(speed2, t_tiny<T>()));            // speed 0: sx = sy = 0, so ux = uy = 0
     const T ux = sx * sinv, uy = sy * sinv;
     const T gx = P.dt * (fn * ux + ftx), gy = P.dt * (fn * uy + fty);
     gmu += ftx * eb[0] + fty * eb[1] + gx * ev[0] + gy * ev[1];

@@ -402,7 +402,8 @@ CN_HD void elbow_loss_prologue(const ElbowParams<T>& P, const T* x, const T* xp,
     elbow_point_vel(S, c, A.dv, ed);
     elbow_point_vel(S, c, A.vp, ev);
     const T sx = mu * ev[0], sy = mu * ev[1];
-    const T speed = t_sqrt(sx * sx + sy * sy);
+    const T speed2 = sx * sx + sy * sy;
+    const T speed = speed2 * t_rsqrt(t_max(speed2, t_tiny<T>()));
     const T phic = S.rho[3 * c + 2] + A.pos_z;
     S.q[3 * c] = -mu * ed[0] + P.dt * sx;
     S.q[3 * c + 1] = -mu * ed[1] + P.dt * sy;
@@ -519,8 +520,8 @@ CN_HD T elbow_loss_epilogue(const ElbowParams<T>& P, const ElbowProb<T>& S, cons
     elbow_point_vel(S, c, A.vp, ev);
     const T ftx = f[3 * c], fty = f[3 * c + 1], fn = f[3 * c + 2];
     const T sx = mu * ev[0], sy = mu * ev[1];
-    const T speed = t_sqrt(sx * sx + sy * sy);
-    const T ux = speed > T(0) ? sx / speed : T(0), uy = speed > T(0) ? sy / speed : T(0);
+    const T sinv = t_rsqrt(t_max(sx * sx + sy * sy, t_tiny<T>()));
+    const T ux = sx * sinv, uy = sy * sinv;
     const T gx = P.dt * (fn * ux + ftx), gy = P.dt * (fn * uy + fty);
     grad[20 + bi] += ftx * eb[0] + fty * eb[1] + gx * ev[0] + gy * ev[1];
     const T ft[3] = {mu * ftx, mu * fty, fn};

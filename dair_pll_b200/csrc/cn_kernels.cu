@@ -133,6 +133,10 @@ cube_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* 
 #define CN_WF_UNR 1
 #endif
 constexpr int kWfUnr = CN_WF_UNR;   // unroll factor of the per-contact loops inside the Newton step
+#ifndef CN_WF_UNR_PE
+#define CN_WF_UNR_PE 1
+#endif
+constexpr int kWfUnrPE = CN_WF_UNR_PE;   // ... and inside the prologue / epilogue
 constexpr int kWfSlots = 64;
 constexpr int kWfWarps = 4;
 constexpr int kWfFields = 50;   // IW 6 | mcW 3 | rho 12 | q 12 | u 6 | best_res2 1 | d 6 | d0 1 | alpha, lo, hi
@@ -237,8 +241,8 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
         for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * 13 + i]); xps[i] = T(xp[b * 13 + i]); }
         const cn::CubeProb<T> S{&pool->field[0][slot], kWfSlots};
         cn::CubeLossAux<T> A;
-        cn::cube_loss_prologue<T, 1>(P, xs, xps, S, A);      // (re)builds IW, mcW, rho, q in the slot
-        const bool finished = !fresh || cn::cube_trivially_solved<T, 1>(S);
+        cn::cube_loss_prologue<T, kWfUnrPE>(P, xs, xps, S, A);      // (re)builds IW, mcW, rho, q in the slot
+        const bool finished = !fresh || cn::cube_trivially_solved<T, kWfUnrPE>(S);
         if (finished) {
           T u[6];
 #pragma unroll
@@ -247,7 +251,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
 #pragma unroll
           for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
           T fo[12];
-          const T l = cn::cube_loss_epilogue<T, 1, true>(P, S, A, u, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr);
+          const T l = cn::cube_loss_epilogue<T, kWfUnrPE, true>(P, S, A, u, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr);
           if (force) {
 #pragma unroll
             for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(fo[i]);
