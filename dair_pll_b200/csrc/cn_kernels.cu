@@ -275,6 +275,17 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
       }
       next += n_new;
       const bool more = next < hi;                       // empty slots are only kept while input remains
+#ifndef CN_NO_PREFETCH
+      // the rows the next PE visit will read (a few Newton visits from now): pull them into L2
+      if (next + lane < hi) {
+        const char* px = reinterpret_cast<const char*>(x + (next + lane) * 13);
+        const char* pp = reinterpret_cast<const char*>(xp + (next + lane) * 13);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(px));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(px + 13 * sizeof(IO) - 1));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 13 * sizeof(IO) - 1));
+      }
+#endif
       const unsigned m_act = __ballot_sync(0xffffffffu, to_active);
       const unsigned m_keep = __ballot_sync(0xffffffffu, on && !to_active && more);
       h_done = (h_done + k) % kWfSlots; n_done -= k;
