@@ -28,29 +28,30 @@ class ICNNSupport(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, d, Wd0, Wd1, Wh, wout, slope):
+        # deep_support_function.py:251-264 with hj = |w_out| * m1 folded into the small matrices, so the only
+        # (D x width) intermediates are the two slope masks and a0
         Wh_a, wo = Wh.abs(), wout.abs()
         lin0 = d @ Wd0
         m0 = torch.where(lin0 > 0, 1.0, slope).to(d.dtype)
-        lin1 = (lin0 * m0) @ Wh_a + d @ Wd1
+        lin1 = torch.addmm(d @ Wd1, lin0.mul_(m0), Wh_a)
         m1 = torch.where(lin1 > 0, 1.0, slope).to(d.dtype)
-        a1 = wo * m1
-        a0 = (a1 @ Wh_a.t()) * m0
-        p = a1 @ Wd1.t() + a0 @ Wd0.t()
-        ctx.save_for_backward(Wd0, Wd1, Wh, wout, m0, a1, a0, m1)
+        a0 = (m1 @ (wo[:, None] * Wh_a.t())).mul_(m0)
+        p = torch.addmm(m1 @ (wo[:, None] * Wd1.t()), a0, Wd0.t())
+        ctx.save_for_backward(Wd0, Wd1, Wh, wout, m0, m1, a0)
         return p
 
     @staticmethod
     def backward(ctx, gp):
-        Wd0, Wd1, Wh, wout, m0, a1, a0, m1 = ctx.saved_tensors
+        Wd0, Wd1, Wh, wout, m0, m1, a0 = ctx.saved_tensors
         gp = gp.contiguous()
-        Wh_a = Wh.abs()
-        gWd1 = gp.t() @ a1
+        Wh_a, wo = Wh.abs(), wout.abs()
+        g1 = gp.t() @ m1                          # (3, width): d/dW_d1 before the |w_out| column scale
         gWd0 = gp.t() @ a0
-        t = (gp @ Wd0) * m0                       # adjoint of (a1 |W_h|^T), masks are constants
-        ga1 = gp @ Wd1 + t @ Wh_a
-        gWh = torch.sign(Wh) * (t.t() @ a1)
-        gwout = torch.sign(wout) * (ga1 * m1).sum(0)
-        return None, gWd0, gWd1, gWh, gwout, None
+        t = (gp @ Wd0).mul_(m0)                   # adjoint of (hj |W_h|^T); the masks are constants
+        G = t.t() @ m1                            # (width, width): d/d|W_h| before the column scale
+        # p is linear in |w_out|_j through column j of hj only: no third (D x width x width) product
+        gwout = torch.sign(wout) * ((Wd1 * g1).sum(0) + (Wh_a * G).sum(0))
+        return None, gWd0, g1 * wo, torch.sign(Wh) * (G * wo), gwout, None
 
 
 class HomogeneousICNN(Module):

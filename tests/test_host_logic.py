@@ -134,3 +134,26 @@ def test_device_slice_dataset_matches_reference_slicing(tmp_path):
         assert sum(p.shape[0] for p, _ in ds.batches(7, drop_last=True)) == (len(ds) // 7) * 7
     with pytest.raises(AssertionError):
         TrajectorySliceConfig(t_skip=0, t_history=2)
+
+
+def test_icnn_support_function_backward_matches_autograd_of_the_oracle():
+    """The product's explicit forward/backward of the support network (three width x width products, the output
+    weight's gradient from homogeneity) against autograd through the oracle restatement of
+    deep_support_function.py:238-266, for all four weights (signed weights, so |.| and sign() are exercised)."""
+    from dair_pll_b200.deep_support_function import ICNNSupport
+    torch.manual_seed(3)
+    W = 48
+    ws = [torch.randn(3, W, dtype=torch.float64), torch.randn(3, W, dtype=torch.float64),
+          torch.randn(W, W, dtype=torch.float64) / W, torch.randn(W, dtype=torch.float64)]
+    d = torch.randn(301, 3, dtype=torch.float64)
+    d = d / d.norm(dim=-1, keepdim=True)
+    gp = torch.randn(301, 3, dtype=torch.float64)
+    a = [w.clone().requires_grad_() for w in ws]
+    p = ICNNSupport.apply(d, a[0], a[1], a[2], a[3], 0.5)
+    (p * gp).sum().backward()
+    b = [w.clone().requires_grad_() for w in ws]
+    po = co.icnn_support(dict(Wd0=b[0], Wd1=b[1], Wh=b[2], wout=b[3]), d)
+    (po * gp).sum().backward()
+    assert torch.allclose(p, po, rtol=1e-12, atol=1e-13)
+    for x, y in zip(a, b):
+        assert torch.allclose(x.grad, y.grad, rtol=1e-10, atol=1e-12)
