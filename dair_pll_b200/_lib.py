@@ -33,6 +33,11 @@ EXPORTS = {
     'dpll_elbow_loss_f32': ([_c_void_p] * 8 + [_f32, _f32, _i64] + [_c_void_p] * 7 + [_c_void_p, _sz, _c_void_p], ctypes.c_int),
     'dpll_elbow_rollout_f64': ([_c_void_p] * 6 + [_f64, _f64, _i64, _i32] + [_c_void_p] * 4, ctypes.c_int),
     'dpll_elbow_rollout_f32': ([_c_void_p] * 6 + [_f32, _f32, _i64, _i32] + [_c_void_p] * 4, ctypes.c_int),
+    'dpll_icnn_input_f64': ([_c_void_p, _c_void_p, _i64, _i32, _f64, _c_void_p, _c_void_p], ctypes.c_int),
+    'dpll_icnn_mask_f64': ([_c_void_p, _i64, _f64, _c_void_p], ctypes.c_int),
+    'dpll_icnn_output_f64': ([_c_void_p] * 5 + [_i64, _i32, _f64, _c_void_p, _c_void_p], ctypes.c_int),
+    'dpll_icnn_backward_blocks': ([_i64], ctypes.c_int),
+    'dpll_icnn_backward_f64': ([_c_void_p] * 5 + [_i64, _i32, _f64, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     'dpll_fma_peak_f64': ([_c_void_p, _i32, _i64, _c_void_p], ctypes.c_int),
     'dpll_fma_peak_f32': ([_c_void_p, _i32, _i64, _c_void_p], ctypes.c_int),
 }

@@ -30,6 +30,14 @@ class ICNNSupport(torch.autograd.Function):
     def forward(ctx, d, Wd0, Wd1, Wh, wout, slope):
         # deep_support_function.py:251-264 with hj = |w_out| * m1 folded into the small matrices, so the only
         # (D x width) intermediates are the two slope masks and a0
+        if d.is_cuda and d.dtype == torch.float64:
+            # fused memory-bound layers (csrc/cn_icnn.cu) around the FP64 GEMMs
+            from dair_pll_b200 import ops
+            p, h0aug, m1, a0 = ops.icnn_support_forward(d, Wd0, Wd1, Wh, wout, float(slope))
+            ctx.save_for_backward(Wd0, Wd1, Wh, wout, h0aug, m1, a0)
+            ctx.fused, ctx.slope = True, float(slope)
+            return p
+        ctx.fused = False
         Wh_a, wo = Wh.abs(), wout.abs()
         lin0 = d @ Wd0
         m0 = torch.where(lin0 > 0, 1.0, slope).to(d.dtype)
@@ -45,10 +53,14 @@ class ICNNSupport(torch.autograd.Function):
         Wd0, Wd1, Wh, wout, m0, m1, a0 = ctx.saved_tensors
         gp = gp.contiguous()
         Wh_a, wo = Wh.abs(), wout.abs()
-        g1 = gp.t() @ m1                          # (3, width): d/dW_d1 before the |w_out| column scale
-        gWd0 = gp.t() @ a0
-        t = (gp @ Wd0).mul_(m0)                   # adjoint of (hj |W_h|^T); the masks are constants
-        G = t.t() @ m1                            # (width, width): d/d|W_h| before the column scale
+        if ctx.fused:
+            from dair_pll_b200 import ops
+            g1, gWd0, G = ops.icnn_support_backward(gp, m0, m1, a0, Wd0, ctx.slope)     # m0 slot holds h0aug
+        else:
+            g1 = gp.t() @ m1                          # (3, width): d/dW_d1 before the |w_out| column scale
+            gWd0 = gp.t() @ a0
+            t = (gp @ Wd0).mul_(m0)                   # adjoint of (hj |W_h|^T); the masks are constants
+            G = t.t() @ m1                            # (width, width): d/d|W_h| before the column scale
         # p is linear in |w_out|_j through column j of hj only: no third (D x width x width) product
         gwout = torch.sign(wout) * ((Wd1 * g1).sum(0) + (Wh_a * G).sum(0))
         return None, gWd0, g1 * wo, torch.sign(Wh) * (G * wo), gwout, None

@@ -402,6 +402,50 @@ def cube_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Ten
     return D, M, J, phi, acc
 
 
+def icnn_support_forward(d: Tensor, Wd0: Tensor, Wd1: Tensor, Wh: Tensor, wout: Tensor, slope: float):
+    """Support points p (D,3) of the depth-2 homogeneous ICNN for unit directions d (D,3), float64, CUDA:
+    the ``dpll_icnn_*`` kernels around two FP64 GEMMs.  Returns (p, h0aug, m1, a0) -- the last three are what
+    the backward needs."""
+    _check_inputs(d, Wd0, Wd1, Wh, wout)
+    if d.dtype != torch.float64:
+        raise TypeError('the support-network kernels are provided in float64')
+    lib = _lib.load()
+    d, Wd0 = d.contiguous(), Wd0.contiguous()
+    D, W = d.shape[0], Wd0.shape[1]
+    dev = d.device
+    Wh_a, wo = Wh.abs(), wout.abs()
+    h0aug = torch.empty((D, W + 8), dtype=d.dtype, device=dev)
+    W_aug = torch.cat((Wh_a, Wd1, torch.zeros((5, W), dtype=d.dtype, device=dev)), 0)
+    V1 = (Wd1 * wo).contiguous()
+    p = torch.empty((D, 3), dtype=d.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dpll_icnn_input_f64(_ptr(d), _ptr(Wd0), D, W, slope, _ptr(h0aug), _stream()), 'dpll_icnn_input')
+        m1 = h0aug @ W_aug                                   # z1 = h0 |Wh| + d Wd1
+        _lib.check(lib.dpll_icnn_mask_f64(_ptr(m1), m1.numel(), slope, _stream()), 'dpll_icnn_mask')
+        a0 = m1 @ (wo[:, None] * Wh_a.t())                   # T, turned into a0 in place below
+        _lib.check(lib.dpll_icnn_output_f64(_ptr(a0), _ptr(h0aug), _ptr(m1), _ptr(Wd0), _ptr(V1), D, W, slope, _ptr(p),
+                                            _stream()), 'dpll_icnn_output')
+    return p, h0aug, m1, a0
+
+
+def icnn_support_backward(gp: Tensor, h0aug: Tensor, m1: Tensor, a0: Tensor, Wd0: Tensor, slope: float):
+    """Returns (g1 = gp^T m1 (3,W), gWd0 = gp^T a0 (3,W), G = t^T m1 (W,W)) with t = (gp Wd0) o m0."""
+    _check_inputs(gp, h0aug, m1, a0, Wd0)
+    lib = _lib.load()
+    gp, Wd0 = gp.contiguous(), Wd0.contiguous()
+    D, W = m1.shape
+    dev = gp.device
+    blocks = lib.dpll_icnn_backward_blocks(D)
+    t = torch.empty((D, W), dtype=gp.dtype, device=dev)
+    part = torch.empty((blocks, 6, W), dtype=gp.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dpll_icnn_backward_f64(_ptr(gp), _ptr(h0aug), _ptr(m1), _ptr(a0), _ptr(Wd0), D, W, slope, _ptr(t),
+                                              _ptr(part), _stream()), 'dpll_icnn_backward')
+        sums = part.sum(0)
+        G = t.t() @ m1
+    return sums[:3], sums[3:], G
+
+
 def fma_peak(dtype: torch.dtype, device: torch.device, blocks: int, iters: int) -> float:
     """Measured FMA throughput (FLOP/s) of the CUDA cores for ``dtype`` -- roofline denominator."""
     out = torch.empty(blocks * 256, dtype=dtype, device=device)

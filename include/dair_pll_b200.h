@@ -140,6 +140,27 @@ int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu
                           float* traj, float* force, int32_t* iters, void* stream);
 
 /*
+ * Support-function network of learned geometries (HomogeneousICNN.forward, dair_pll/deep_support_function.py:238-266,
+ * called from DeepSupportConvex.get_vertices, dair_pll/geometry.py:309-325): the memory-bound layers around the
+ * three (D x W) x (W x W) products, which the caller runs as FP64 library GEMMs.  D direction rows, width W,
+ * LeakyReLU slope `slope`; row-major arrays; weights Wd0, Wd1 (3, W).
+ *   dpll_icnn_input_f64     h0aug (D, W+8) = [lrelu(d Wd0) | d | 0]      (so that z1 = h0aug [|Wh| ; Wd1 ; 0])
+ *   dpll_icnn_mask_f64      z (n) -> slope mask of z, in place            (m1 from z1)
+ *   dpll_icnn_output_f64    T (D, W) = m1 (|wout| * |Wh|^T) -> a0 = T o m0 in place;  p (D, 3) = m1 V1^T + a0 Wd0^T,
+ *                           V1 = |wout| * Wd1 (3, W): the support points
+ *   dpll_icnn_backward_f64  cotangent gp (D, 3): t (D, W) = (gp Wd0) o m0 and per-block partial sums
+ *                           part (dpll_icnn_backward_blocks(D), 6, W) of gp^T m1 (rows 0-2) and gp^T a0 (rows 3-5)
+ */
+int dpll_icnn_input_f64(const double* d, const double* Wd0, int64_t D, int32_t W, double slope, double* h0aug,
+                        void* stream);
+int dpll_icnn_mask_f64(double* z, int64_t n, double slope, void* stream);
+int dpll_icnn_output_f64(double* T, const double* h0aug, const double* m1, const double* Wd0, const double* V1, int64_t D,
+                         int32_t W, double slope, double* p, void* stream);
+int dpll_icnn_backward_blocks(int64_t D);
+int dpll_icnn_backward_f64(const double* gp, const double* h0aug, const double* m1, const double* a0, const double* Wd0,
+                           int64_t D, int32_t W, double slope, double* t, double* part, void* stream);
+
+/*
  * Dense dynamics terms of the cube in the reference's coordinates and ordering, for callers of
  * MultibodyTerms.forward (dair_pll/multibody_terms.py:584-609; LagrangianTerms.forward :214-237,
  * ContactTerms.forward :428-521): q (B,7), v (B,6) -> M (B,6,6), J (B,12,6) = [J_n ; mu J_t interleaved]

@@ -451,3 +451,28 @@ def test_dense_terms_match_reference_golden(name, assets_dir):
     assert np.abs(J.cpu().numpy() - Jo.numpy()).max() < 1e-14
     assert np.abs(phi.cpu().numpy() - phio.numpy()).max() < 1e-15
     assert np.abs(D.cpu().numpy() - Do.numpy()).max() < 1e-10 * np.abs(Do.numpy()).max()
+
+
+@pytest.mark.parametrize('width,rows', [(64, 1000), (256, 4099)])
+def test_support_network_kernels_match_oracle_autograd(width, rows):
+    """The fused support-network layers (dpll_icnn_*: input layer, slope masks, output contraction, weight-gradient
+    reductions) + library GEMMs against autograd through the oracle's restatement of
+    deep_support_function.py:238-266: support points and the gradients of all four weights."""
+    from dair_pll_b200.deep_support_function import ICNNSupport
+    from oracle import contactnets_oracle as co
+    torch.manual_seed(width)
+    ws = [torch.randn(3, width, dtype=torch.float64), torch.randn(3, width, dtype=torch.float64),
+          torch.randn(width, width, dtype=torch.float64) / width, torch.randn(width, dtype=torch.float64)]
+    d = torch.randn(rows, 3, dtype=torch.float64)
+    d = d / d.norm(dim=-1, keepdim=True)
+    gp = torch.randn(rows, 3, dtype=torch.float64)
+    a = [w.clone().to(DEV).requires_grad_() for w in ws]
+    p = ICNNSupport.apply(d.to(DEV), a[0], a[1], a[2], a[3], 0.5)
+    (p * gp.to(DEV)).sum().backward()
+    b = [w.clone().requires_grad_() for w in ws]
+    po = co.icnn_support(dict(Wd0=b[0], Wd1=b[1], Wh=b[2], wout=b[3]), d)
+    (po * gp).sum().backward()
+    assert torch.allclose(p.cpu(), po, rtol=1e-11, atol=1e-12)
+    for x, y in zip(a, b):
+        scale = y.grad.abs().max()
+        assert (x.grad.cpu() - y.grad).abs().max() <= 1e-10 * scale
