@@ -333,7 +333,6 @@ __global__ void reduce_partials_kernel(const T* __restrict__ partials, int nbloc
 }
 
 // ---- leaf-level parameter preparation / chain rule (cube: theta 10, friction 2 [box, ground], length 3) ----
-constexpr int kNLeaf = 15;
 
 template <typename T, typename IO>
 __global__ void cube_prep_kernel(const IO* __restrict__ theta, const IO* __restrict__ friction,

@@ -476,3 +476,26 @@ def test_support_network_kernels_match_oracle_autograd(width, rows):
     for x, y in zip(a, b):
         scale = y.grad.abs().max()
         assert (x.grad.cpu() - y.grad).abs().max() <= 1e-10 * scale
+
+
+def test_graphed_step_replays_the_eager_step(assets_dir):
+    """parallel.GraphedStep: the captured forward + backward + staging of the flat gradient buffer gives the same
+    numbers as eager launches, replay after replay, also after the inputs are overwritten in place."""
+    from dair_pll_b200 import parallel
+    g = load_golden('cube_synthetic')
+    s = _system(g, assets_dir)
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    reducer = parallel.GradientAllReduce(list(s.parameters()), DEV, 1)
+
+    def step():
+        reducer.zero()
+        mean = s.contactnets_loss(x, None, xp).mean()
+        mean.backward()
+        return reducer.stage(mean)
+    eager = step().clone()
+    graphed = parallel.GraphedStep(step, DEV)
+    for _ in range(3):
+        assert torch.equal(graphed(), eager)
+    x.copy_(x.flip(0)), xp.copy_(xp.flip(0))             # same multiset of pairs, new contents at the captured addresses
+    flipped = graphed().clone()
+    assert torch.allclose(flipped, eager, rtol=1e-12, atol=1e-18) and torch.equal(step(), flipped)
