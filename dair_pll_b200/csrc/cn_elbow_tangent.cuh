@@ -1,0 +1,42 @@
+// Forward-mode derivative of the learnable time step of the two-body (elbow) system: the step code of
+// cn_elbow.cuh instantiated on dual numbers carrying one tangent, as cn_cube_tangent.cuh does for the
+// cube.  43 directions:
+//   0..27  callable-level parameters [inertia 2x10 | mu_pair 2 | half 2x3],   28..42  the 15 coordinates of x0.
+// Box geometries only (witness points of a learned geometry depend on the state through the caller's
+// networks, so that rollout is stepped on the host).
+#pragma once
+#include "cn_elbow.cuh"
+#include "cn_dual.cuh"
+
+namespace cn {
+
+constexpr int ELBOW_NTAN = 43;
+constexpr int ELBOW_NPARAM_TAN = 28;
+
+// xbar: upstream gradient w.r.t. traj[1..steps] (steps x 15).  Returns sum_s xbar_s . d x_s / d (direction).
+template <typename B>
+CN_HD B elbow_rollout_tangent(const B* inertia, const B* mu, const B* half, const B* kin, B dt, B eps, const B* x0,
+                              int steps, const B* xbar, int dir) {
+  typedef DualN<B, 1> D;
+  D din[20], dmu[2], dh[6], dkin[12];
+  for (int i = 0; i < 20; ++i) { din[i] = D(inertia[i]); if (dir == i) din[i].d[0] = B(1); }
+  for (int i = 0; i < 2; ++i) { dmu[i] = D(mu[i]); if (dir == 20 + i) dmu[i].d[0] = B(1); }
+  for (int i = 0; i < 6; ++i) { dh[i] = D(half[i]); if (dir == 22 + i) dh[i].d[0] = B(1); }
+  for (int i = 0; i < 12; ++i) dkin[i] = D(kin[i]);
+  ElbowParams<D> P;
+  elbow_params_init<D>(P, din, dmu, dh, dkin, D(dt), D(eps));
+  const SolverCfg<B> c0 = default_cfg<B>();
+  SolverCfg<D> cfg;
+  cfg.tol_rel = D(c0.tol_rel); cfg.tol_stall = D(c0.tol_stall); cfg.ls_c = D(c0.ls_c); cfg.max_iter = c0.max_iter;
+  cfg.tol_final = D(c0.tol_final);
+  D x[15], xn[15];
+  for (int i = 0; i < 15; ++i) { x[i] = D(x0[i]); if (dir == ELBOW_NPARAM_TAN + i) x[i].d[0] = B(1); }
+  B g = B(0);
+  for (int s = 0; s < steps; ++s) {
+    elbow_step_sample<D>(P, cfg, x, (const D*)nullptr, xn, (D*)nullptr);
+    for (int i = 0; i < 15; ++i) { g += xbar[s * 15 + i] * xn[i].d[0]; x[i] = xn[i]; }
+  }
+  return g;
+}
+
+}  // namespace cn

@@ -510,12 +510,16 @@ template <typename T, typename IO>
 __global__ void __launch_bounds__(kLossThreads)
 elbow_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, const IO* __restrict__ mu,
                      const IO* __restrict__ half, const IO* __restrict__ kin, const IO* __restrict__ pts, T dt, T eps,
-                     int64_t B, int steps, IO* __restrict__ traj, IO* __restrict__ force, int32_t* __restrict__ iters) {
+                     int64_t B, int steps, IO* __restrict__ traj, IO* __restrict__ force, int32_t* __restrict__ iters,
+                     int lanes_per_warp) {
+  const int lane = threadIdx.x & 31;              // small batches are spread thinly, as in cube_rollout_kernel
+  if (lane >= lanes_per_warp) return;
   cn::ElbowParams<T> P;
   load_elbow_params<T, IO>(P, inertia, mu, half, kin, dt, eps);
   const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t stride = (((int64_t)gridDim.x * blockDim.x) >> 5) * lanes_per_warp;
+  for (int64_t b = warp * lanes_per_warp + lane; b < B; b += stride) {
     T xc[15], xn[15], fo[24], pt[24];
     IO* out = traj + b * (int64_t)(steps + 1) * 15;
     for (int i = 0; i < 15; ++i) { xc[i] = T(x0[b * 15 + i]); out[i] = IO(xc[i]); }
@@ -574,11 +578,16 @@ int launch_elbow_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, elbow_rollout_kernel<T, IO>, kLossThreads, 0);
   if (per_sm < 1) per_sm = 1;
-  int64_t need = (B + kLossThreads - 1) / kLossThreads;
-  int64_t cap = (int64_t)di.sms * per_sm;
-  int blocks = (int)(need < cap ? need : cap);
+  const int64_t cap = (int64_t)di.sms * per_sm;
+  const int64_t warps = cap * (kLossThreads / 32);
+  int lpw = (int)((B + warps - 1) / warps);
+  if (lpw < 1) lpw = 1;
+  if (lpw > 32) lpw = 32;
+  const int64_t per_block = (int64_t)lpw * (kLossThreads / 32);
+  const int64_t need = (B + per_block - 1) / per_block;
+  const int blocks = (int)(need < cap ? need : cap);
   elbow_rollout_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x0, inertia, mu, half, kin, pts, dt, eps, B, steps, traj,
-                                                              force, iters);
+                                                              force, iters, lpw);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPLL_OK : (int)e;
 }

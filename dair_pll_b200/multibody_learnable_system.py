@@ -139,6 +139,8 @@ class MultibodyLearnableSystem(System):
                                                    STEP_EPS, pts=pts)
                         xs.append(one[:, 1])
                     traj = torch.stack(xs, 1)
+            elif torch.is_grad_enabled() and (x_0.requires_grad or inertia.requires_grad):
+                traj = ops.ElbowRollout.apply(self._flat(x_0), inertia, mu, half, kin, float(self.dt), steps, STEP_EPS)
             else:
                 traj, _ = ops.elbow_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(), kin,
                                             float(self.dt), steps, STEP_EPS)

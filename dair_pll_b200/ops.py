@@ -381,6 +381,38 @@ class CubeRollout(torch.autograd.Function):
                 g[11:14].reshape(half.shape).to(half.dtype), None, None, None)
 
 
+class ElbowRollout(torch.autograd.Function):
+    """Differentiable rollout of the learnable two-body (elbow) system with box geometries: traj (B, steps+1, 15).
+    Backward = ``dpll_elbow_rollout_grad_f64`` (forward-mode tangents, 43 directions per toss)."""
+
+    @staticmethod
+    def forward(ctx, x0, inertia, mu_pair, half, kin, dt, steps, eps):
+        traj, _ = elbow_rollout(x0, inertia, mu_pair, half, kin, dt, steps, eps)
+        ctx.dt, ctx.steps, ctx.eps = dt, steps, eps
+        ctx.save_for_backward(x0, inertia, mu_pair, half, kin)
+        return traj
+
+    @staticmethod
+    def backward(ctx, gtraj):
+        x0, inertia, mu_pair, half, kin = ctx.saved_tensors
+        B, steps = x0.shape[0], ctx.steps
+        f64 = torch.float64
+        xbar = gtraj[:, 1:, :].to(f64).contiguous()
+        gparams = torch.zeros((B, 28), dtype=f64, device=x0.device)
+        gx0 = torch.zeros((B, 15), dtype=f64, device=x0.device)
+        if B > 0 and steps > 0:
+            a = [t.detach().to(f64).contiguous() for t in (x0, inertia, mu_pair, half, kin)]
+            with torch.cuda.device(x0.device):
+                rc = _lib.load().dpll_elbow_rollout_grad_f64(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(a[4]),
+                                                             ctx.dt, ctx.eps, B, steps, _ptr(xbar), _ptr(gparams),
+                                                             _ptr(gx0), _stream())
+            _lib.check(rc, 'dpll_elbow_rollout_grad')
+        g = gparams.sum(0)
+        gx = (gx0 + gtraj[:, 0, :].to(f64)).to(x0.dtype)
+        return (gx, g[0:20].reshape(inertia.shape).to(inertia.dtype), g[20:22].reshape(mu_pair.shape).to(mu_pair.dtype),
+                g[22:28].reshape(half.shape).to(half.dtype), None, None, None, None)
+
+
 def cube_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor):
     """``dpll_cube_terms_f64``: (delassus (B,12,12), M (B,6,6), J (B,12,6), phi (B,4), acc (B,6)) in the order
     ``MultibodyTerms.forward`` returns them (multibody_terms.py:584-609).  fp64 only, no autograd."""

@@ -186,6 +186,14 @@ int dpll_cube_rollout_grad_f64(const double* x0, const double* inertia, const do
                                const double* xbar, double* gparams, double* gx0, void* stream);
 
 /*
+ * The same backward for the two-body (elbow) system with box geometries: gparams (B, 28) =
+ * [d/d inertia (20) | d/d mu_pair (2) | d/d half (6)], gx0 (B, 15).  43 tangent directions per toss.
+ */
+int dpll_elbow_rollout_grad_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,
+                                const double* kin, double dt, double eps, int64_t B, int32_t steps, const double* xbar,
+                                double* gparams, double* gx0, void* stream);
+
+/*
  * The same two operations for the elbow (assets/contactnets_elbow.urdf: floating base + one
  * revolute child, two boxes, 2 x 4 contacts): states (B, 15) = [quat | pos | hinge angle | w_body |
  * v_world | hinge rate]; parameters inertia[20] (two bodies' 10-vectors), mu_pair[2] (ground-box1,

@@ -4,6 +4,7 @@
 #include "../../dair_pll_b200/csrc/cn_params.cuh"
 #include "../../dair_pll_b200/csrc/cn_elbow.cuh"
 #include "../../dair_pll_b200/csrc/cn_cube_tangent.cuh"
+#include "../../dair_pll_b200/csrc/cn_elbow_tangent.cuh"
 #include <cstdint>
 using namespace cn;
 extern "C" {
@@ -115,6 +116,17 @@ int emul_cube_rollout_grad_f64(const double* x0, const double* inertia, const do
       const double g = cube_rollout_tangent<double>(inertia, mu, half, dt, eps, x0 + 13 * b, steps,
                                                     xbar + (int64_t)b * steps * 13, dir);
       if (dir < 14) gparams[14 * b + dir] = g; else gx0[13 * b + dir - 14] = g;
+    }
+  return 0;
+}
+int emul_elbow_rollout_grad_f64(const double* x0, const double* inertia, const double* mu, const double* half,
+                                const double* kin, double dt, double eps, int64_t B, int steps, const double* xbar,
+                                double* gparams, double* gx0) {
+  for (int64_t b = 0; b < B; ++b)
+    for (int dir = 0; dir < ELBOW_NTAN; ++dir) {
+      const double g = elbow_rollout_tangent<double>(inertia, mu, half, kin, dt, eps, x0 + 15 * b, steps,
+                                                     xbar + (int64_t)b * steps * 15, dir);
+      if (dir < ELBOW_NPARAM_TAN) gparams[ELBOW_NPARAM_TAN * b + dir] = g; else gx0[15 * b + dir - ELBOW_NPARAM_TAN] = g;
     }
   return 0;
 }

@@ -499,3 +499,30 @@ def test_graphed_step_replays_the_eager_step(assets_dir):
     x.copy_(x.flip(0)), xp.copy_(xp.flip(0))             # same multiset of pairs, new contents at the captured addresses
     flipped = graphed().clone()
     assert torch.allclose(flipped, eager, rtol=1e-12, atol=1e-18) and torch.equal(step(), flipped)
+
+
+def test_elbow_rollout_backward_matches_oracle_autograd(assets_dir):
+    """Prediction-loss path for the two-body system: gradients of a 2-step rollout w.r.t. theta of both bodies,
+    the three friction parameters, both boxes' lengths and the initial state, through the module API, against
+    autograd through the CPU oracle."""
+    from oracle import contactnets_oracle as co
+    from oracle.callables import ELBOW_TREE, TreeCallables
+    from tests.util import oracle_params_from_golden
+    g = load_golden('elbow_perturbed')
+    s = _elbow_system(g, assets_dir)
+    n, steps = 16, 2
+    x0 = torch.from_numpy(g['sim_x0'][:n]).to(DEV).requires_grad_()
+    target = torch.from_numpy(g['sim_traj'][:n, 1:steps + 1]).to(DEV) + 0.01
+    traj, _ = s.simulate(x0.unsqueeze(-2), torch.zeros(n, 1, device=DEV), steps)
+    ((traj[:, 1:] - target) ** 2).sum().backward()
+    P = oracle_params_from_golden(g)
+    x0o = torch.from_numpy(g['sim_x0'][:n]).clone().requires_grad_()
+    tro = co.simulate(TreeCallables(ELBOW_TREE), P, x0o, float(g['dt']), steps)
+    ((tro[:, 1:] - target.cpu()) ** 2).sum().backward()
+    assert np.abs(traj.detach().cpu().numpy() - tro.detach().numpy()).max() < 1e-8
+    mt = s.multibody_terms
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), P.inertial_parameters.grad.numpy()) < 1e-6
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), P.friction_params.grad.numpy()) < 1e-6
+    gl = np.stack([mt.contact_terms.geometries[i].length_params.grad.cpu().numpy().reshape(3) for i in range(2)])
+    assert max_rel_to_scale(gl, np.stack([p.grad.numpy().reshape(3) for p in P.length_params])) < 1e-6
+    assert max_rel_to_scale(x0.grad.cpu().numpy(), x0o.grad.numpy()) < 1e-6

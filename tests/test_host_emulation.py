@@ -230,3 +230,30 @@ def test_device_dense_terms_match_reference_golden(name):
     assert np.abs(J - Jo.numpy()).max() < 1e-14
     assert np.abs(phi - phio.numpy()).max() < 1e-15
     assert np.abs(D - Do.numpy()).max() < 1e-10 * np.abs(Do.numpy()).max()
+
+
+def test_elbow_step_tangents_match_oracle_autograd():
+    """Backward of the learnable time step of the two-body system: dual-number tangents of a 2-step rollout
+    (43 directions), chained to the leaf parameters, against autograd through the oracle."""
+    from oracle.callables import ELBOW_TREE
+    from tests.util import oracle_params_from_golden
+    lib = host_emulation_lib()
+    g = load_golden('elbow_perturbed')
+    inertia, mu, half = elbow_kernel_level_params(g)
+    x0 = np.ascontiguousarray(g['sim_x0'][:12])
+    B, steps = x0.shape[0], 2
+    rng = np.random.default_rng(1)
+    xbar = rng.standard_normal((B, steps, 15))
+    gparams, gx0 = np.zeros((B, 28)), np.zeros((B, 15))
+    lib.emul_elbow_rollout_grad_f64(dptr(x0), dptr(inertia), dptr(mu), dptr(half), dptr(ELBOW_KIN),
+                                    ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-4), ctypes.c_int64(B),
+                                    ctypes.c_int(steps), dptr(xbar), dptr(gparams), dptr(gx0))
+    P = oracle_params_from_golden(g)
+    x0_t = torch.from_numpy(x0.copy()).requires_grad_()
+    tr = co.simulate(TreeCallables(ELBOW_TREE), P, x0_t, float(g['dt']), steps)
+    (tr[:, 1:] * torch.from_numpy(xbar)).sum().backward()
+    gt, gf, gl = elbow_chain_to_leaves(g, gparams.sum(0))
+    assert max_rel_to_scale(gx0, x0_t.grad.numpy()) < 1e-6
+    assert max_rel_to_scale(gt, P.inertial_parameters.grad.numpy()) < 1e-6
+    assert max_rel_to_scale(gf, P.friction_params.grad.numpy()) < 1e-6
+    assert max_rel_to_scale(gl, np.stack([p.grad.numpy().reshape(3) for p in P.length_params])) < 1e-6
