@@ -214,6 +214,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
         pool->field[46][slot] = d0;
         pool->field[47][slot] = tr.alpha; pool->field[48][slot] = tr.lo; pool->field[49][slot] = tr.hi;
       }
+      __syncwarp();          // ring entries read above may be overwritten below (queue full): order the accesses
       const unsigned m_done = __ballot_sync(0xffffffffu, st == cn::NEWTON_DONE);
       const unsigned m_act = __ballot_sync(0xffffffffu, st == cn::NEWTON_CONTINUE);
       h_act = (h_act + k) % kWfSlots; n_act -= k;
@@ -286,6 +287,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
         asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 13 * sizeof(IO) - 1));
       }
 #endif
+      __syncwarp();
       const unsigned m_act = __ballot_sync(0xffffffffu, to_active);
       const unsigned m_keep = __ballot_sync(0xffffffffu, on && !to_active && more);
       h_done = (h_done + k) % kWfSlots; n_done -= k;
