@@ -133,6 +133,9 @@ cube_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* 
 #define CN_WF_UNR 1
 #endif
 constexpr int kWfUnr = CN_WF_UNR;   // unroll factor of the per-contact loops inside the Newton step
+#ifndef CN_WF_TRIAGE
+#define CN_WF_TRIAGE 1                 // 1: free-flight samples are finalised by the register-only triage phase
+#endif
 #ifndef CN_WF_UNR_PE
 #define CN_WF_UNR_PE 1
 #endif
@@ -146,6 +149,7 @@ template <typename T> struct WfWarpPool {
   int32_t sample[kWfSlots];     // offset of the slot's sample in the warp's range; -1 = empty
   int32_t iters[kWfSlots];
   uint8_t q_act[kWfSlots], q_done[kWfSlots];
+  int32_t q_in[kWfSlots];       // offsets of triaged samples that need the solver, waiting for a slot
 };
 
 template <typename T, typename IO>
@@ -175,24 +179,69 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
   int64_t next = lo;
 
   for (int s = lane; s < kWfSlots; s += 32) { pool->q_done[s] = (uint8_t)s; pool->sample[s] = -1; }
-  int n_act = 0, n_done = kWfSlots, h_act = 0, h_done = 0;
+  int n_act = 0, n_done = kWfSlots, h_act = 0, h_done = 0, n_in = 0, h_in = 0;
   __syncwarp();
 
   while (true) {
-    int phase;   // 0 = PE, 1 = N
+    int phase;   // 0 = PE, 1 = N, 2 = T (triage)
     // Slots are conserved while input remains (active + done = kWfSlots), so one of the two queues
     // always holds a full warp's worth.  Once the input is exhausted (drain) the remaining samples'
     // Newton chains are the critical path: N runs at whatever width is left and the finished samples
     // are finalised in full-width PE batches at the very end.
-    const bool drain = next >= hi;
-    if (drain) {
+    const bool drain = next >= hi && n_in == 0;
+    if (CN_WF_TRIAGE && next < hi && n_in < 32) phase = 2;     // keep a warp's worth of solver samples queued
+    else if (drain) {
       if (n_act > 0) phase = 1;
       else if (n_done > 0) phase = 0;
       else break;
     } else if (n_done >= 32) phase = 0;
     else phase = 1;
 
-    if (phase == 1) {
+    if (phase == 2) {
+      // T: the next 32 input samples, in registers only.  Free flight (u = 0, f = 0 optimal) is finalised
+      // here at a third of the generic cost; the others wait in q_in for a slot.
+      const int64_t left = hi - next;
+      const int cnt = left < 32 ? (int)left : 32;
+      bool queue = false;
+      const int64_t b = next + lane;
+      if (lane < cnt) {
+        T xs[13], xps[13];
+#pragma unroll
+        for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * 13 + i]); xps[i] = T(xp[b * 13 + i]); }
+        T gs[DPLL_CUBE_NPARAM];
+#pragma unroll
+        for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
+        T l = T(0);
+        if (cn::cube_loss_free_flight<T>(P, xs, xps, want_grad ? gs : (T*)nullptr, &l)) {
+          if (force) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(0);
+          }
+          const T w = weight ? T(weight[b]) : T(1);
+#pragma unroll
+          for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] += w * gs[i];
+          if (loss) loss[b] = IO(l);
+          acc[14] += l;
+          if (iters) iters[b] = 0;
+        } else {
+          queue = true;
+        }
+      }
+      const unsigned m_q = __ballot_sync(0xffffffffu, queue);
+      if (queue) pool->q_in[(h_in + n_in + __popc(m_q & lt_mask)) % kWfSlots] = (int32_t)(b - lo);
+      n_in += __popc(m_q);
+      next += cnt;
+#ifndef CN_NO_PREFETCH
+      if (next + lane < hi) {       // the rows of the next triage visit: pull them into L2
+        const char* px = reinterpret_cast<const char*>(x + (next + lane) * 13);
+        const char* pp = reinterpret_cast<const char*>(xp + (next + lane) * 13);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(px));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(px + 13 * sizeof(IO) - 1));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 13 * sizeof(IO) - 1));
+      }
+#endif
+    } else if (phase == 1) {
       const int k = n_act < 32 ? n_act : 32;
       const bool on = lane < k;
       int st = -1;
@@ -228,22 +277,30 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
       if (on) { slot = pool->q_done[(h_done + lane) % kWfSlots]; old = pool->sample[slot]; }
       // empty slots take the next input samples, in lane order
       const unsigned m_empty = __ballot_sync(0xffffffffu, on && old < 0);
-      const int64_t left = hi - next;
       const int n_empty = __popc(m_empty);
+#if CN_WF_TRIAGE
+      const int n_new = n_in < n_empty ? n_in : n_empty;       // triaged samples waiting for a slot
+#else
+      const int64_t left = hi - next;
       const int n_new = left < n_empty ? (int)left : n_empty;
+#endif
       const int my_rank = __popc(m_empty & lt_mask);
       const bool fresh = on && old < 0 && my_rank < n_new;
       const bool work = fresh || (on && old >= 0);
       bool to_active = false;
       if (work) {
+#if CN_WF_TRIAGE
+        const int64_t b = lo + (fresh ? pool->q_in[(h_in + my_rank) % kWfSlots] : old);
+#else
         const int64_t b = fresh ? next + my_rank : lo + old;
+#endif
         T xs[13], xps[13];
 #pragma unroll
         for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * 13 + i]); xps[i] = T(xp[b * 13 + i]); }
         const cn::CubeProb<T> S{&pool->field[0][slot], kWfSlots};
         cn::CubeLossAux<T> A;
         cn::cube_loss_prologue<T, kWfUnrPE>(P, xs, xps, S, A);      // (re)builds IW, mcW, rho, q in the slot
-        const bool finished = !fresh || cn::cube_trivially_solved<T, kWfUnrPE>(S);
+        const bool finished = !fresh || (!CN_WF_TRIAGE && cn::cube_trivially_solved<T, kWfUnrPE>(S));
         if (finished) {
           T u[6];
 #pragma unroll
@@ -274,9 +331,14 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
           to_active = true;
         }
       }
+#if CN_WF_TRIAGE
+      h_in = (h_in + n_new) % kWfSlots; n_in -= n_new;
+      const bool more = next < hi || n_in > 0;           // empty slots are only kept while input remains
+#else
       next += n_new;
       const bool more = next < hi;                       // empty slots are only kept while input remains
-#ifndef CN_NO_PREFETCH
+#endif
+#if !defined(CN_NO_PREFETCH) && !CN_WF_TRIAGE
       // the rows the next PE visit will read (a few Newton visits from now): pull them into L2
       if (next + lane < hi) {
         const char* px = reinterpret_cast<const char*>(x + (next + lane) * 13);

@@ -22,6 +22,20 @@ int emul_cube_loss_f64(const double* x, const double* xp, const double* inertia,
   }
   return 0;
 }
+// free-flight fast path (triage phase of the wavefront kernel): flags[b] = 1 where it applies
+int emul_cube_loss_free_f64(const double* x, const double* xp, const double* inertia, const double* mu,
+                            const double* half, double dt, double eps, int64_t B, double* loss, int32_t* flags,
+                            double* grad) {
+  CubeParams<double> P;
+  cube_params_init(P, inertia, mu, half, dt, eps);
+  for (int i = 0; i < CUBE_NPARAM; ++i) grad[i] = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    double l = 0;
+    flags[b] = cube_loss_free_flight<double>(P, x + 13 * b, xp + 13 * b, grad, &l) ? 1 : 0;
+    loss[b] = l;
+  }
+  return 0;
+}
 // fp32 variant = fp32 storage, fp64 arithmetic (as the kernels: T = double, IO = float)
 int emul_cube_loss_f32(const float* x, const float* xp, const float* inertia, const float* mu,
                        const float* half, float dt, float eps, int64_t B, float* loss, float* force,

@@ -257,3 +257,37 @@ def test_elbow_step_tangents_match_oracle_autograd():
     assert max_rel_to_scale(gt, P.inertial_parameters.grad.numpy()) < 1e-6
     assert max_rel_to_scale(gf, P.friction_params.grad.numpy()) < 1e-6
     assert max_rel_to_scale(gl, np.stack([p.grad.numpy().reshape(3) for p in P.length_params])) < 1e-6
+
+
+def test_free_flight_fast_path_equals_the_generic_path():
+    """The triage phase's register-only evaluation of free-flight samples: it fires exactly on the samples
+    whose solve is trivial (0 iterations, zero forces) and gives the generic path's loss and gradient."""
+    from dair_pll_b200 import synthetic
+    lib = host_emulation_lib()
+    g = load_golden('cube_synthetic')
+    inertia, mu, half = kernel_level_params(g)
+    x = synthetic.cube_states(4000, seed=3).numpy().copy()
+    xp = np.zeros_like(x)
+    lib.emul_cube_step_f64(dptr(x), dptr(inertia), dptr(mu), dptr(half), ctypes.c_double(float(g['dt'])),
+                           ctypes.c_double(1e-4), ctypes.c_int64(x.shape[0]), dptr(xp), None, None)
+    xp = synthetic.perturb_next_state(torch.from_numpy(xp), seed=4).numpy().copy()
+    xp[:50, 6] -= 0.2                                     # some deep penetrations: flight test must still be exact
+    B = x.shape[0]
+    loss_f, flags, grad_f = np.zeros(B), np.zeros(B, np.int32), np.zeros(14)
+    lib.emul_cube_loss_free_f64(dptr(x), dptr(xp), dptr(inertia), dptr(mu), dptr(half), ctypes.c_double(float(g['dt'])),
+                                ctypes.c_double(1e-3), ctypes.c_int64(B), dptr(loss_f), dptr(flags), dptr(grad_f))
+    free = flags == 1
+    assert 0.3 < free.mean() < 0.95
+    # generic path on the same samples
+    loss, force, iters, grad = np.zeros(B), np.zeros((B, 12)), np.zeros(B, np.int32), np.zeros(14)
+    lib.emul_cube_loss_f64(dptr(x), dptr(xp), dptr(inertia), dptr(mu), dptr(half), ctypes.c_double(float(g['dt'])),
+                           ctypes.c_double(1e-3), ctypes.c_int64(B), dptr(loss), dptr(force), dptr(iters), dptr(grad))
+    assert np.array_equal(free, (iters == 0) & (np.abs(force).max(1) == 0))
+    assert np.abs(loss_f[free] - loss[free]).max() <= 1e-14 * np.abs(loss[free]).max()
+    xs, xps = np.ascontiguousarray(x[free]), np.ascontiguousarray(xp[free])
+    n = xs.shape[0]
+    l2, f2, i2, grad_g = np.zeros(n), np.zeros((n, 12)), np.zeros(n, np.int32), np.zeros(14)
+    lib.emul_cube_loss_f64(dptr(xs), dptr(xps), dptr(inertia), dptr(mu), dptr(half), ctypes.c_double(float(g['dt'])),
+                           ctypes.c_double(1e-3), ctypes.c_int64(n), dptr(l2), dptr(f2), dptr(i2), dptr(grad_g))
+    assert np.abs(grad_f - grad_g).max() <= 1e-12 * np.abs(grad_g).max()
+    assert np.abs(grad_g[11:]).max() > 0                  # the penetration term is exercised
