@@ -133,9 +133,6 @@ cube_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* 
 #define CN_WF_UNR 1
 #endif
 constexpr int kWfUnr = CN_WF_UNR;   // unroll factor of the per-contact loops inside the Newton step
-#ifndef CN_WF_TRIAGE
-#define CN_WF_TRIAGE 1                 // 1: free-flight samples are finalised by the register-only triage phase
-#endif
 #ifndef CN_WF_UNR_PE
 #define CN_WF_UNR_PE 1
 #endif
@@ -189,7 +186,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
     // Newton chains are the critical path: N runs at whatever width is left and the finished samples
     // are finalised in full-width PE batches at the very end.
     const bool drain = next >= hi && n_in == 0;
-    if (CN_WF_TRIAGE && next < hi && n_in < 32) phase = 2;     // keep a warp's worth of solver samples queued
+    if (next < hi && n_in < 32) phase = 2;     // keep a warp's worth of solver samples queued
     else if (drain) {
       if (n_act > 0) phase = 1;
       else if (n_done > 0) phase = 0;
@@ -271,84 +268,66 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
       else if (st == cn::NEWTON_CONTINUE) pool->q_act[(h_act + n_act + __popc(m_act & lt_mask)) % kWfSlots] = (uint8_t)slot;
       n_done += __popc(m_done); n_act += __popc(m_act);
     } else {
+      // PE: up to 32 slots of the done queue, two passes over ONE code instance of the prologue.  Pass 0
+      // finalises the finished samples (problem rebuilt from x, x+; loss + envelope backward; outputs) and
+      // their slots become empty; pass 1 gives the batch's empty slots the next triaged samples (problem
+      // built and parked) and sends them to the active queue -- so in steady state both passes run 32 wide.
       const int k = n_done < 32 ? n_done : 32;
       const bool on = lane < k;
       int slot = 0, old = -1;
       if (on) { slot = pool->q_done[(h_done + lane) % kWfSlots]; old = pool->sample[slot]; }
-      // empty slots take the next input samples, in lane order
-      const unsigned m_empty = __ballot_sync(0xffffffffu, on && old < 0);
-      const int n_empty = __popc(m_empty);
-#if CN_WF_TRIAGE
-      const int n_new = n_in < n_empty ? n_in : n_empty;       // triaged samples waiting for a slot
-#else
-      const int64_t left = hi - next;
-      const int n_new = left < n_empty ? (int)left : n_empty;
-#endif
-      const int my_rank = __popc(m_empty & lt_mask);
-      const bool fresh = on && old < 0 && my_rank < n_new;
-      const bool work = fresh || (on && old >= 0);
       bool to_active = false;
-      if (work) {
-#if CN_WF_TRIAGE
-        const int64_t b = lo + (fresh ? pool->q_in[(h_in + my_rank) % kWfSlots] : old);
-#else
-        const int64_t b = fresh ? next + my_rank : lo + old;
-#endif
-        T xs[13], xps[13];
-#pragma unroll
-        for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * 13 + i]); xps[i] = T(xp[b * 13 + i]); }
-        const cn::CubeProb<T> S{&pool->field[0][slot], kWfSlots};
-        cn::CubeLossAux<T> A;
-        cn::cube_loss_prologue<T, kWfUnrPE>(P, xs, xps, S, A);      // (re)builds IW, mcW, rho, q in the slot
-        const bool finished = !fresh || (!CN_WF_TRIAGE && cn::cube_trivially_solved<T, kWfUnrPE>(S));
-        if (finished) {
-          T u[6];
-#pragma unroll
-          for (int i = 0; i < 6; ++i) u[i] = fresh ? T(0) : pool->field[33 + i][slot];
-          T gs[DPLL_CUBE_NPARAM];
-#pragma unroll
-          for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
-          T fo[12];
-          const T l = cn::cube_loss_epilogue<T, kWfUnrPE, true>(P, S, A, u, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr);
-          if (force) {
-#pragma unroll
-            for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(fo[i]);
-          }
-          const T w = weight ? T(weight[b]) : T(1);
-#pragma unroll
-          for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] += w * gs[i];
-          if (loss) loss[b] = IO(l);
-          acc[14] += l;
-          if (iters) iters[b] = fresh ? 0 : (pool->iters[slot] & 0xff);
-          pool->sample[slot] = -1;
+      int n_new = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 0) {
+          if (!__any_sync(0xffffffffu, on && old >= 0)) continue;
         } else {
+          n_new = n_in < k ? n_in : k;                     // after pass 0 every slot of the batch is empty
+          if (n_new == 0) break;
+        }
+        const bool work = pass == 0 ? (on && old >= 0) : (lane < n_new);
+        if (work) {
+          const int64_t b = lo + (pass == 0 ? old : pool->q_in[(h_in + lane) % kWfSlots]);
+          T xs[13], xps[13];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = T(0);
-          pool->field[39][slot] = T(-1);
-          pool->field[46][slot] = T(0);
-          pool->sample[slot] = (int32_t)(b - lo);
-          pool->iters[slot] = 0;
-          to_active = true;
+          for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * 13 + i]); xps[i] = T(xp[b * 13 + i]); }
+          const cn::CubeProb<T> S{&pool->field[0][slot], kWfSlots};
+          cn::CubeLossAux<T> A;
+          cn::cube_loss_prologue<T, kWfUnrPE>(P, xs, xps, S, A);      // (re)builds IW, mcW, rho, q in the slot
+          if (pass == 0) {
+            T u[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) u[i] = pool->field[33 + i][slot];
+            T gs[DPLL_CUBE_NPARAM];
+#pragma unroll
+            for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
+            T fo[12];
+            const T l = cn::cube_loss_epilogue<T, kWfUnrPE, true>(P, S, A, u, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr);
+            if (force) {
+#pragma unroll
+              for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(fo[i]);
+            }
+            const T w = weight ? T(weight[b]) : T(1);
+#pragma unroll
+            for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] += w * gs[i];
+            if (loss) loss[b] = IO(l);
+            acc[14] += l;
+            if (iters) iters[b] = pool->iters[slot] & 0xff;
+            pool->sample[slot] = -1;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = T(0);
+            pool->field[39][slot] = T(-1);
+            pool->field[46][slot] = T(0);
+            pool->sample[slot] = (int32_t)(b - lo);
+            pool->iters[slot] = 0;
+            to_active = true;
+          }
         }
       }
-#if CN_WF_TRIAGE
       h_in = (h_in + n_new) % kWfSlots; n_in -= n_new;
-      const bool more = next < hi || n_in > 0;           // empty slots are only kept while input remains
-#else
-      next += n_new;
-      const bool more = next < hi;                       // empty slots are only kept while input remains
-#endif
-#if !defined(CN_NO_PREFETCH) && !CN_WF_TRIAGE
-      // the rows the next PE visit will read (a few Newton visits from now): pull them into L2
-      if (next + lane < hi) {
-        const char* px = reinterpret_cast<const char*>(x + (next + lane) * 13);
-        const char* pp = reinterpret_cast<const char*>(xp + (next + lane) * 13);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(px));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(px + 13 * sizeof(IO) - 1));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 13 * sizeof(IO) - 1));
-      }
-#endif
+      const bool more = next < hi || n_in > 0;             // empty slots are only kept while input remains
       __syncwarp();
       const unsigned m_act = __ballot_sync(0xffffffffu, to_active);
       const unsigned m_keep = __ballot_sync(0xffffffffu, on && !to_active && more);
