@@ -108,26 +108,23 @@ cube_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* 
 // ---------------------------------------------------------------------------
 // Wavefront variant of the loss kernel.
 //
-// The Newton solve needs 0 .. ~30 iterations depending on the sample (most free-flight
-// samples need none), so one-sample-per-thread leaves ~80% of the lanes idle (ncu:
-// 5.8 active threads per instruction, profiles/).  Here each WARP owns a pool of kWfSlots
-// sample slots in shared memory and three ring-buffer queues, and runs warp-uniform phases,
-// each processing up to 32 slots at full width:
-//   N   one Newton step for 32 slots whose sample is not yet converged ("active" queue)
-//   L   the derivative line search for 32 slots whose full Newton step overshot (~14% of the
-//       steps; kept out of N so that N has no data-dependent loop)
-//   PE  for 32 slots of the "done" queue: a slot holding a finished sample is finalised
-//       (problem rebuilt from x, x+ -> loss + envelope backward -> outputs) and becomes
-//       empty; an empty slot receives the next input sample (problem built and parked in
-//       the slot; if it is already optimal at u = 0 -- free flight -- it is finalised on the
-//       spot).  One code instance of the prologue serves both cases.
-// Slots are conserved (active + linesearch + done = kWfSlots until the input runs out), so the
-// fullest queue always holds >= 22 entries and in practice ~32.  The phase choice
-// depends only on warp-uniform counters; there is no divergence between phases and the
-// per-sample arithmetic is the same code as the simple kernel.  Samples are assigned to
-// warps statically (contiguous ranges), which keeps the gradient reduction deterministic.
-// The hot loop is kept small (rolled per-contact loops over the shared-memory slot) because
-// warps of one SM sit in different phases and share the instruction cache.
+// A solve needs 0 .. ~45 Newton visits depending on the sample (free-flight samples need none), so
+// one-sample-per-thread leaves ~80% of the lanes idle (ncu: 5.8 active threads per instruction,
+// profiles/).  Here each WARP owns a pool of kWfSlots sample slots in shared memory, two ring queues of
+// slots (active / done) and a FIFO of sample indices, and runs warp-uniform phases over 32 samples:
+//   T   triage of the next 32 input samples in registers: free flight (u = 0, f = 0 optimal) is finalised
+//       on the spot by cube_loss_free_flight; the others queue their index for a slot
+//   N   one Newton visit (one gradient/Hessian evaluation, cube_newton_visit) for 32 active slots
+//   PE  for 32 slots of the done queue: pass 0 finalises the finished samples (problem rebuilt from
+//       x, x+ -> loss + envelope backward -> outputs), pass 1 refills the emptied slots with triaged
+//       samples (problem built and parked in the slot).  One code instance of the prologue serves both.
+// Slots are conserved (active + done = kWfSlots until the input runs out), so one of the two queues
+// always holds a full warp's worth: phases run 32 wide until the warp drains.  The phase choice depends
+// only on warp-uniform counters; there is no divergence between phases and the per-sample arithmetic is
+// the same code as the simple kernel.  Samples are assigned to warps statically (contiguous ranges),
+// which keeps the gradient reduction deterministic.  The hot loops are kept small (rolled per-contact
+// loops over the shared-memory slot) because warps of one SM sit in different phases and share the
+// instruction cache.
 // ---------------------------------------------------------------------------
 #ifndef CN_WF_UNR
 #define CN_WF_UNR 1
