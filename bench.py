@@ -402,8 +402,8 @@ def main():
                    'eager_ms_per_step': ms_eager},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h},
-        'gpu_launches': 6 * args.steps,   # per step: prepare + loss/backward + reduce/chain, and the same three
-                                          # (device-side skipped) launches issued by autograd's backward
+        'gpu_launches': 3 * args.steps,   # per step: parameter preparation + loss/backward + reduce/chain rule
+                                          # (loss.mean() and its backward reuse that launch, ops.BatchLoss)
         'roofline': {'bound': 'fp64_cuda_core' if dtype == torch.float64 else 'fp32_cuda_core',
                      'achieved': achieved_tflops, 'peak': peak_flops / 1e12, 'unit': 'TFLOP/s',
                      'frac': achieved_tflops / (peak_flops / 1e12), 'traffic': traffic,

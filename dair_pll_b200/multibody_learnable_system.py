@@ -99,9 +99,12 @@ class MultibodyLearnableSystem(System):
             lt, ct = self.multibody_terms.lagrangian_terms, self.multibody_terms.contact_terms
             # the learnable leaves go straight to the library (parameter preparation, multibody_terms.py:230-231,
             # 466-471, geometry.py:394-397, and its chain rule run on the device)
-            loss = ops.CubeContactNetsLossLeaf.apply(
-                self._flat(x), self._flat(x_plus), lt.inertial_parameters.to(x.dtype), ct.friction_params.to(x.dtype),
-                ct.geometries[0].length_params.to(x.dtype), float(self.dt), LOSS_EPS)
+            leaves = (lt.inertial_parameters.to(x.dtype), ct.friction_params.to(x.dtype),
+                      ct.geometries[0].length_params.to(x.dtype))
+            loss, loss_sum, grad = ops.CubeContactNetsLossLeaf.apply(self._flat(x), self._flat(x_plus), *leaves,
+                                                                     float(self.dt), LOSS_EPS)
+            # loss.mean() / loss.sum() (drake_experiment.py:222-223) then come from this launch's own reduction
+            return ops.batch_loss(loss.reshape(batch), loss_sum, grad, leaves)
         elif self._kind() == 'elbow':
             inertia, mu, half, kin = self._elbow_params(x.dtype, x.device)
             xf, xpf = self._flat(x), self._flat(x_plus)

@@ -164,15 +164,19 @@ class CubeContactNetsLossLeaf(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, x_plus, theta, friction, length, dt, eps):
         need = any(ctx.needs_input_grad[2:5])
-        loss, grad, _ = cube_loss_leaf_raw(x, x_plus, theta, friction, length, dt, eps, want_grad=need)
+        loss, grad, loss_sum = cube_loss_leaf_raw(x, x_plus, theta, friction, length, dt, eps, want_grad=need)
         ctx.dt, ctx.eps = dt, eps
         ctx.shapes = (theta.shape, friction.shape, length.shape)
         if need:
             ctx.save_for_backward(grad, x, x_plus, theta, friction, length)
-        return loss
+        else:
+            grad = torch.zeros(15, dtype=loss.dtype, device=loss.device)
+        # the launch's own sum of losses and summed parameter gradient, for BatchLoss.mean() / .sum()
+        ctx.mark_non_differentiable(loss_sum, grad)
+        return loss, loss_sum, grad
 
     @staticmethod
-    def backward(ctx, grad_loss):
+    def backward(ctx, grad_loss, _g_sum, _g_grad):
         grad, x, x_plus, theta, friction, length = ctx.saved_tensors
         if grad_loss.numel() == 0:
             g = torch.zeros_like(grad)
@@ -188,6 +192,66 @@ class CubeContactNetsLossLeaf(torch.autograd.Function):
             g = torch.where(uniform, grad * lo, gw)
         s_t, s_f, s_l = ctx.shapes
         return (None, None, g[0:10].reshape(s_t), g[10:12].reshape(s_f), g[12:15].reshape(s_l), None, None)
+
+
+class _FusedReduction(torch.autograd.Function):
+    """``mean()`` / ``sum()`` of a batch loss taken from the kernel launch that produced it: the value is the
+    launch's own sum of losses, the backward scales the launch's fused parameter gradient -- no reduction
+    over the (B,) loss, no (B,) upstream gradient, no second launch."""
+
+    @staticmethod
+    def forward(ctx, loss_sum, grad, scale, *leaves):
+        ctx.save_for_backward(grad)
+        ctx.scale = scale
+        ctx.shapes = [l.shape for l in leaves]
+        return (loss_sum * scale).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        gg = grad * (g * ctx.scale)
+        outs, off = [], 0
+        for shape in ctx.shapes:
+            n = 1
+            for s in shape:
+                n *= s
+            outs.append(gg[off:off + n].reshape(shape))
+            off += n
+        return (None, None, None, *outs)
+
+
+_INPLACE_DUNDERS = {'__iadd__', '__isub__', '__imul__', '__itruediv__', '__ifloordiv__', '__ipow__', '__imod__',
+                    '__setitem__'}
+
+
+class BatchLoss(torch.Tensor):
+    """The (*,) loss tensor the module returns: an ordinary tensor whose argument-free ``mean()`` / ``sum()``
+    -- what the reference's training loop applies to it (drake_experiment.py:222-223) -- come from the launch
+    that produced the losses (:class:`_FusedReduction`).  Every other operation behaves as on a plain tensor
+    (and returns plain tensors); in-place modification switches the shortcut off."""
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        name = getattr(func, '__name__', '')
+        self = args[0] if args else None
+        fused = getattr(self, '_dpll_fused', None) if isinstance(self, BatchLoss) else None
+        if fused is not None and name in ('mean', 'sum') and len(args) == 1 and not kwargs:
+            loss_sum, grad, leaves = fused
+            n = self.numel()
+            scale = (1.0 / n if n > 0 else float('nan')) if name == 'mean' else 1.0
+            return _FusedReduction.apply(loss_sum, grad, scale, *leaves)
+        if fused is not None and (name in _INPLACE_DUNDERS or (name.endswith('_') and not name.endswith('__'))):
+            self._dpll_fused = None
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*args, **kwargs)
+
+
+def batch_loss(loss: Tensor, loss_sum: Tensor, grad: Tensor, leaves) -> Tensor:
+    """Wraps the per-sample loss with the launch's sum and fused gradient (see :class:`BatchLoss`)."""
+    out = loss.as_subclass(BatchLoss)
+    out._dpll_fused = (loss_sum, grad, tuple(leaves))
+    return out
 
 
 def cube_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, dt: float, steps: int,

@@ -526,3 +526,33 @@ def test_elbow_rollout_backward_matches_oracle_autograd(assets_dir):
     gl = np.stack([mt.contact_terms.geometries[i].length_params.grad.cpu().numpy().reshape(3) for i in range(2)])
     assert max_rel_to_scale(gl, np.stack([p.grad.numpy().reshape(3) for p in P.length_params])) < 1e-6
     assert max_rel_to_scale(x0.grad.cpu().numpy(), x0o.grad.numpy()) < 1e-6
+
+
+def test_batch_loss_mean_and_sum_shortcuts_equal_the_generic_reductions(assets_dir):
+    """``contactnets_loss(...).mean()`` / ``.sum()`` come from the launch's own reduction and fused gradient
+    (ops.BatchLoss); they must equal the generic torch reductions over the per-sample loss and their autograd
+    backward (second, weighted launch), and in-place edits must switch the shortcut off."""
+    g = load_golden('cube_real_perturbed')
+    s = _system(g, assets_dir)
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    params = list(s.parameters())
+
+    def grads_of(reduce):
+        for p in params:
+            p.grad = None
+        out = reduce(s.contactnets_loss(x, None, xp))
+        out.backward()
+        return out.detach().clone(), [p.grad.clone() for p in params]
+    for fused, generic in ((lambda l: l.mean(), lambda l: torch.mean(l.as_subclass(torch.Tensor))),
+                           (lambda l: l.sum(), lambda l: (l * 1.0).sum())):
+        vf, gf = grads_of(fused)
+        vg, gg = grads_of(generic)
+        assert abs(vf.item() - vg.item()) <= 1e-13 * abs(vg.item())
+        for a, b in zip(gf, gg):
+            assert torch.allclose(a, b, rtol=1e-11, atol=1e-16)
+    loss = s.contactnets_loss(x, None, xp)
+    assert type(loss * 2.0) is torch.Tensor and loss.shape == (x.shape[0],)
+    with torch.no_grad():
+        ref = loss.mean().item()
+        loss.mul_(3.0)
+        assert abs(loss.mean().item() - 3.0 * ref) <= 1e-12 * abs(ref)
