@@ -556,3 +556,29 @@ def test_batch_loss_mean_and_sum_shortcuts_equal_the_generic_reductions(assets_d
         ref = loss.mean().item()
         loss.mul_(3.0)
         assert abs(loss.mean().item() - 3.0 * ref) <= 1e-12 * abs(ref)
+
+
+def test_scheduler_boundary_batch_sizes_agree_with_the_simple_kernel():
+    """Batch sizes at the seams of the wavefront scheduler -- fewer samples than warps, exactly / one off a full
+    triage visit per warp, one off a full slot pool per warp -- give the per-sample results of the
+    one-sample-per-thread kernel: every sample is finalised exactly once and none is lost in a queue."""
+    g = load_golden('cube_synthetic')
+    inertia, mu, half = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    warps = 148 * 2 * 4
+    sizes = [1, 5, 32, 63, warps - 1, warps + 7, 32 * warps - 1, 32 * warps, 32 * warps + 1, 64 * warps + 33, 96 * warps - 5]
+    nmax = max(sizes)
+    x = synthetic.cube_states(nmax, seed=41, device=DEV)
+    traj, _ = ops.cube_rollout(x, inertia, mu, half, 0.0068, 1)
+    xp = synthetic.perturb_next_state(traj[:, 1], seed=42)
+    try:
+        ops.set_loss_variant(1)
+        ref = ops.cube_loss_raw(x, xp, inertia, mu, half, 0.0068, 1e-3, want_iters=True)
+    finally:
+        ops.set_loss_variant(0)
+    ref_loss = ref[0].cpu().numpy()
+    for n in sizes:
+        loss, grad, total, _, iters = ops.cube_loss_raw(x[:n], xp[:n], inertia, mu, half, 0.0068, 1e-3, want_iters=True)
+        l = loss.cpu().numpy()
+        assert rel_err(l, ref_loss[:n], 1e-9).max() < 1e-10, n
+        assert abs(total.item() - l.sum()) <= 1e-11 * abs(l.sum()), n
+        assert int(iters.min()) >= 0 and int(iters.max()) <= 100, n
