@@ -242,7 +242,9 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC + ' fp64', 'value': value, 'unit': 'samples/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'cube_contactnets_loss_backward_B{B}_cpu', 'batch_per_step': B, 'dt': DT},
+        'config': {'workload': f'cube_contactnets_loss_backward_B{args.batch}_per_gpu', 'batch_per_gpu': args.batch,
+                   'dt': DT, 'eps': 1e-3, 'cpu_sample_per_step': B,
+                   'note': 'same workload as the GPU arm; each CPU step is a bounded sample of it'},
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
