@@ -134,6 +134,10 @@ constexpr int kWfUnr = CN_WF_UNR;   // unroll factor of the per-contact loops in
 #define CN_WF_UNR_PE 1
 #endif
 constexpr int kWfUnrPE = CN_WF_UNR_PE;   // ... and inside the prologue / epilogue
+#ifndef CN_WF_MIN_PER_WARP
+#define CN_WF_MIN_PER_WARP 128
+#endif
+constexpr int kWfMinPerWarp = CN_WF_MIN_PER_WARP;   // fewest samples a warp should get before more warps are used
 constexpr int kWfSlots = 64;
 constexpr int kWfWarps = 4;
 constexpr int kWfFields = 50;   // IW 6 | mcW 3 | rho 12 | q 12 | u 6 | best_res2 1 | d 6 | d0 1 | alpha, lo, hi
@@ -676,7 +680,9 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_wf_kernel<T, IO>, kWfWarps * 32, smem);
     if (per_sm < 1) per_sm = 1;
-    int64_t need = (B + kWfWarps * 32 - 1) / (kWfWarps * 32);
+    // A warp needs a few hundred samples to keep its pool full; with fewer, every SM would run many
+    // mostly-empty warps at the issue rate of full ones.  Small batches therefore use fewer warps.
+    int64_t need = (B + kWfWarps * kWfMinPerWarp - 1) / (kWfWarps * kWfMinPerWarp);
     int64_t cap = (int64_t)di.sms * per_sm;
     if (cap > kMaxBlocks) cap = kMaxBlocks;
     blocks = (int)(need < cap ? need : cap);
