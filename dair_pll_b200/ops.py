@@ -542,17 +542,20 @@ def icnn_support_backward(gp: Tensor, h0aug: Tensor, m1: Tensor, a0: Tensor, Wd0
     return sums[:3], sums[3:], G
 
 
-def fma_peak(dtype: torch.dtype, device: torch.device, blocks: int, iters: int) -> float:
-    """Measured FMA throughput (FLOP/s) of the CUDA cores for ``dtype`` -- roofline denominator."""
+def fma_peak(dtype: torch.dtype, device: torch.device, blocks: int, iters: int, reps: int = 5) -> float:
+    """Measured FMA throughput (FLOP/s) of the CUDA cores for ``dtype`` -- roofline denominator.  Best of
+    ``reps`` runs (a peak: a run disturbed by clock ramp-up would understate the denominator)."""
     out = torch.empty(blocks * 256, dtype=dtype, device=device)
     fn = getattr(_lib.load(), 'dpll_fma_peak_' + _SUFFIX[dtype])
+    best = float('inf')
     with torch.cuda.device(device):
-        _lib.check(fn(_ptr(out), blocks, 1000, _stream()), 'dpll_fma_peak')   # warm-up
+        _lib.check(fn(_ptr(out), blocks, iters // 4 + 1, _stream()), 'dpll_fma_peak')   # warm-up
         torch.cuda.synchronize(device)
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        _lib.check(fn(_ptr(out), blocks, iters, _stream()), 'dpll_fma_peak')
-        stop.record()
-        torch.cuda.synchronize(device)
-    ms = start.elapsed_time(stop)
-    return blocks * 256 * iters * 16 * 2 / (ms * 1e-3)
+        for _ in range(max(1, reps)):
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            _lib.check(fn(_ptr(out), blocks, iters, _stream()), 'dpll_fma_peak')
+            stop.record()
+            torch.cuda.synchronize(device)
+            best = min(best, start.elapsed_time(stop))
+    return blocks * 256 * iters * 16 * 2 / (best * 1e-3)
