@@ -62,8 +62,11 @@ class GradientAllReduce:
     def reduce(self) -> Tensor:
         """Collective half: ONE all-reduce of ``flat`` (sum / world) over NCCL (gloo in the CPU tests)."""
         if self.world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.mul_(1.0 / self.world)
+            if dist.get_backend(self.group) == 'nccl':
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)     # one kernel: sum / world
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.mul_(1.0 / self.world)
         return self.flat
 
     def __call__(self, local_mean_loss: Tensor) -> Tensor:
