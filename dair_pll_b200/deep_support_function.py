@@ -30,7 +30,7 @@ class ICNNSupport(torch.autograd.Function):
     def forward(ctx, d, Wd0, Wd1, Wh, wout, slope):
         # deep_support_function.py:251-264 with hj = |w_out| * m1 folded into the small matrices, so the only
         # (D x width) intermediates are the two slope masks and a0
-        if d.is_cuda and d.dtype == torch.float64:
+        if d.is_cuda:
             # fused memory-bound layers (csrc/cn_icnn.cu) around the FP64 GEMMs
             from dair_pll_b200 import ops
             p, h0aug, m1, a0 = ops.icnn_support_forward(d, Wd0, Wd1, Wh, wout, float(slope))
@@ -95,7 +95,9 @@ class HomogeneousICNN(Module):
 
     def forward(self, directions: Tensor) -> Tensor:
         shape = directions.shape
-        dt = directions.dtype
-        p = ICNNSupport.apply(directions.reshape(-1, 3), self.input_weights[0].to(dt), self.input_weights[1].to(dt),
+        # CUDA tensors always take the kernel path (float64 arithmetic, as the fp32 variant of the loss kernels);
+        # CPU tensors run the same algebra in torch -- host mirror for CPU-only checks, never used by the CUDA path
+        dt = torch.float64 if directions.is_cuda else directions.dtype
+        p = ICNNSupport.apply(directions.reshape(-1, 3).to(dt), self.input_weights[0].to(dt), self.input_weights[1].to(dt),
                               self.hidden_weights[0].to(dt), self.output_weight.to(dt), self.negative_slope)
-        return p.reshape(shape)
+        return p.reshape(shape).to(directions.dtype)
