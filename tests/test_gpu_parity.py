@@ -82,13 +82,14 @@ def test_rollout_matches_reference_golden(name, assets_dir):
     assert torch.allclose(x1, traj[:, 1], atol=1e-14, rtol=0)
 
 
-def test_matches_cpu_oracle_on_random_inputs():
+@pytest.mark.parametrize('n', [2048, 150000])        # a partly filled pool per warp / every warp in steady state
+def test_matches_cpu_oracle_on_random_inputs(n):
     from oracle import contactnets_oracle as co
     from oracle.callables import CUBE_TREE, TreeCallables
     calls = TreeCallables(CUBE_TREE)
     pi, fr, half = synthetic.cube_learnables_perturbed(5)
     P = co.OracleParams(co.pi_cm_to_theta(pi), fr, [half.reshape(1, 3)]).requires_grad_()
-    x = synthetic.cube_states(2048, seed=21)
+    x = synthetic.cube_states(n, seed=21)
     with torch.no_grad():
         xp = synthetic.perturb_next_state(co.sim_step(calls, P, x, 0.0068), seed=22)
     loss_o = co.contactnets_loss(calls, P, x, xp, 0.0068)
