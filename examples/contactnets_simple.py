@@ -50,13 +50,17 @@ def parameter_report(system) -> dict:
 
 
 def run(epochs: int = 100, n_pop: int = N_POP, batch_size: int = 256, lr: float = 1e-3, seed: int = 0,
-        perturbation: float = 0.3, device: str = 'cuda:0', verbose: bool = True) -> dict:
+        perturbation: float = 0.3, device: str = 'cuda:0', verbose: bool = True, contactnets: bool = True,
+        t_prediction: int = 1) -> dict:
+    """``contactnets=False`` trains on the prediction loss instead (experiment.py:292-320: mean squared velocity
+    error of the ``t_prediction``-step rollout from the last past state), differentiating through every step's
+    QP (``simulate`` -> ``dpll_cube_rollout_grad_f64``)."""
     dev = torch.device(device)
     truth = MultibodyLearnableSystem({'cube': CUBE_URDF}, DT).to(dev)
     x0 = sample_initial_states(truth, n_pop, seed, dev)
     with torch.no_grad():
         trajectories, _ = truth.simulate(x0.unsqueeze(-2), torch.zeros(n_pop, 1, device=dev), TRAJECTORY_LENGTH)
-    data = DeviceTrajectorySliceDataset(TrajectorySliceConfig(), dev)
+    data = DeviceTrajectorySliceDataset(TrajectorySliceConfig(t_prediction=1 if contactnets else t_prediction), dev)
     for traj in trajectories:
         data.add_slices_from_trajectory(traj)
 
@@ -85,8 +89,13 @@ def run(epochs: int = 100, n_pop: int = N_POP, batch_size: int = 256, lr: float 
         total, count = 0.0, 0
         for x_past, x_future in data.batches(batch_size, generator=gen):
             optimizer.zero_grad(set_to_none=True)
-            # the experiment's loss callback (drake_experiment.py:202-224)
-            loss = learned.contactnets_loss(x_past[:, -1, :], None, x_future[:, 0, :]).mean()
+            if contactnets:     # the experiment's loss callback (drake_experiment.py:202-224)
+                loss = learned.contactnets_loss(x_past[:, -1, :], None, x_future[:, 0, :]).mean()
+            else:               # experiment.prediction_loss (experiment.py:292-320)
+                steps = x_future.shape[1]
+                predicted, _ = learned.simulate(x_past[:, -1:, :], torch.zeros(x_past.shape[0], 1, device=dev), steps)
+                space = learned.space
+                loss = ((space.v(predicted[:, 1:, :]) - space.v(x_future)) ** 2).sum() / space.v(x_future).numel()
             loss.backward()
             optimizer.step()
             total += loss.detach() * x_past.shape[0]
@@ -105,8 +114,11 @@ if __name__ == '__main__':
     ap.add_argument('--batch-size', type=int, default=256)
     ap.add_argument('--lr', type=float, default=1e-3)
     ap.add_argument('--perturbation', type=float, default=0.3)
+    ap.add_argument('--prediction', action='store_true', help='prediction loss instead of the ContactNets loss')
+    ap.add_argument('--t-prediction', type=int, default=1)
     a = ap.parse_args()
-    out = run(a.epochs, a.n_pop, a.batch_size, a.lr, perturbation=a.perturbation)
+    out = run(a.epochs, a.n_pop, a.batch_size, a.lr, perturbation=a.perturbation, contactnets=not a.prediction,
+              t_prediction=a.t_prediction)
     print(f"{out['pairs']} pairs, {a.epochs} epochs in {out['seconds']:.1f} s")
     print('truth  ', out['truth'])
     print('learned', out['learned'])

@@ -597,6 +597,10 @@ def test_contactnets_training_example_recovers_geometry():
     out = mod.run(epochs=40, n_pop=64, batch_size=1024, lr=3e-3, seed=0, perturbation=0.3, verbose=False)
     h = out['history']
     assert h[-1] < 0.5 * h[0]
+    # the prediction loss (experiment.py:292-320) through the differentiable 2-step rollout learns as well
+    pred = mod.run(epochs=15, n_pop=32, batch_size=1024, lr=3e-3, seed=0, perturbation=0.3, verbose=False,
+                   contactnets=False, t_prediction=2)
+    assert pred['history'][-1] < 0.5 * pred['history'][0]
     truth = out['truth']['half_lengths']
     err0 = max(abs(a - b) for a, b in zip(out['initial']['half_lengths'], truth))
     err = max(abs(a - b) for a, b in zip(out['learned']['half_lengths'], truth))
