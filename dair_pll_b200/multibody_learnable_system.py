@@ -8,6 +8,7 @@ interchange, experiment.py:530-538), same attributes (``space``, ``integrator``,
 (:104-197), ``forward_dynamics`` (:199-304) and the integrator loop runs in CUDA kernels
 through ``dair_pll_b200.ops``; inputs must be CUDA tensors -- there is no CPU path.
 """
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -161,6 +162,50 @@ class MultibodyLearnableSystem(System):
         """``Integrator.partial_step`` callback (:306-313)."""
         q, v = self.space.q_v(x)
         return self.forward_dynamics(q, v, x.new_zeros(x.shape[:-1] + (0,))), carry
+
+    def generate_updated_urdfs(self) -> Dict[str, str]:
+        """Writes the current parameterisation back into copies of the initial URDFs (same basenames, in
+        ``output_urdfs_dir``) and returns their paths, as the reference's method of the same name
+        (multibody_learnable_system.py:82-102; urdf_utils.represent_multibody_terms_as_urdfs): per link the
+        mass, centre of mass and inertia about it; per box collision geometry its size and friction
+        coefficient.  Host side only.  Learned mesh geometries keep their original ``<mesh>`` element."""
+        import xml.etree.ElementTree as ET
+        assert self.output_urdfs_dir is not None
+        os.makedirs(self.output_urdfs_dir, exist_ok=True)
+        mt = self.multibody_terms
+        pi_cm = mt.lagrangian_terms.pi_cm().detach().cpu().double()
+        mu = mt.contact_terms.get_friction_coefficients().detach().cpu().double()
+        fmt = lambda vals: ' '.join(repr(float(v)) for v in vals)      # noqa: E731
+        new_urdfs = {}
+        for name, old_path in self.init_urdfs.items():
+            tree = ET.parse(old_path)
+            gi = 0
+            for bi, link in enumerate(tree.getroot().findall('link')):
+                pi = pi_cm[bi]
+                m = float(pi[0])
+                inertial = link.find('inertial')
+                inertial.find('mass').set('value', repr(m))
+                origin = inertial.find('origin')
+                if origin is None:
+                    origin = ET.SubElement(inertial, 'origin')
+                origin.set('xyz', fmt(pi[1:4] / m))
+                origin.set('rpy', '0 0 0')
+                ine = inertial.find('inertia')
+                for key, val in zip(('ixx', 'iyy', 'izz', 'ixy', 'ixz', 'iyz'), pi[4:10]):
+                    ine.set(key, repr(float(val)))
+                for col in link.findall('collision'):
+                    geometry = mt.contact_terms.geometries[gi]
+                    box = col.find('geometry').find('box')
+                    if box is not None:
+                        box.set('size', fmt(2 * geometry.get_half_lengths().detach().cpu().double().reshape(3)))
+                    for prox in col.iter():
+                        if prox.tag.endswith('mu_static') or prox.tag.endswith('mu_dynamic'):
+                            prox.set('value', repr(float(mu[gi])))
+                    gi += 1
+            new_path = os.path.join(self.output_urdfs_dir, os.path.basename(old_path))
+            tree.write(new_path, xml_declaration=True, encoding='utf-8')
+            new_urdfs[name] = new_path
+        return new_urdfs
 
     def summary(self, statistics: Dict) -> SystemSummary:
         del statistics

@@ -157,3 +157,35 @@ def test_icnn_support_function_backward_matches_autograd_of_the_oracle():
     assert torch.allclose(p, po, rtol=1e-12, atol=1e-13)
     for x, y in zip(a, b):
         assert torch.allclose(x.grad, y.grad, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize('asset', ['cube.urdf', 'elbow.urdf'])
+def test_generate_updated_urdfs_round_trip(asset, tmp_path):
+    """multibody_learnable_system.py:82-102: the learned parameterisation written back into the URDF is read back
+    to the same inertial, geometric and friction parameters (host logic; no GPU)."""
+    urdf = os.path.join(ROOT, 'dair_pll_b200', 'assets', asset)
+    s = MultibodyLearnableSystem({'sys': urdf}, 0.0068, output_urdfs_dir=str(tmp_path))
+    gen = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        mt = s.multibody_terms
+        pi = mt.lagrangian_terms.pi_cm().clone()
+        pi[:, 0] *= 1.2
+        pi[:, 1:4] += 0.003 * pi[:, :1] * torch.randn(pi[:, 1:4].shape, generator=gen, dtype=pi.dtype)
+        pi[:, 4:7] *= 1.1
+        pi[:, 7:] += 1e-5
+        mt.lagrangian_terms.inertial_parameters.copy_(IPC.pi_cm_to_theta(pi))
+        mt.contact_terms.friction_params.mul_(0.8)
+        for g in mt.contact_terms.geometries:
+            if hasattr(g, 'length_params'):
+                g.length_params.mul_(torch.tensor([[1.1, 0.9, 1.05]], dtype=g.length_params.dtype))
+    paths = s.generate_updated_urdfs()
+    assert os.path.basename(paths['sys']) == asset and os.path.dirname(paths['sys']) == str(tmp_path)
+    s2 = MultibodyLearnableSystem(paths, 0.0068)
+    a, b = s.multibody_terms, s2.multibody_terms
+    assert torch.allclose(a.lagrangian_terms.pi_cm(), b.lagrangian_terms.pi_cm(), rtol=1e-12, atol=1e-15)
+    n_body_geoms = len(a.contact_terms.geometries) - 1
+    assert torch.allclose(a.contact_terms.friction_params[:n_body_geoms].abs(),
+                          b.contact_terms.friction_params[:n_body_geoms].abs(), rtol=1e-12)
+    for ga, gb in zip(a.contact_terms.geometries, b.contact_terms.geometries):
+        if hasattr(ga, 'length_params'):
+            assert torch.allclose(ga.length_params.abs(), gb.length_params.abs(), rtol=1e-12)
