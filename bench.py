@@ -356,7 +356,8 @@ def main():
     flops_per_sample = F0_CUBE + FIT_CUBE * mean_iters
     achieved_tflops = B * flops_per_sample / (ms_kernel * 1e-3) / 1e12
     sms = torch.cuda.get_device_properties(device).multi_processor_count
-    peak_flops = ops.fma_peak(dtype, device, sms * 8, 200000 if dtype == torch.float64 else 400000)
+    # the arithmetic is fp64 for both storage types (the fp32 variant is fp32 STORAGE), so is the roofline
+    peak_flops = ops.fma_peak(torch.float64, device, sms * 8, 200000)
     hbm_gbs = B * BYTES_PER_SAMPLE[dtype] / (ms_kernel * 1e-3) / 1e9
     peaks = {}
     try:
@@ -395,18 +396,18 @@ def main():
         'metric': METRIC + (' fp64' if dtype == torch.float64 else ' fp32'),
         'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': args.dtype, 'data': 'synthetic',
+        'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'cube_contactnets_loss_backward_B{B}_per_gpu', 'batch_per_gpu': B,
                    'global_batch': world * B, 'dt': DT, 'eps': 1e-3, 'parallelism': f'dp{world}',
                    'l2_policy': f'inputs larger than L2 ({2 * B * 13 * x.element_size() / 1e6:.0f} MB per step vs 126 MB)',
-                   'mean_newton_iters': mean_iters,
+                   'mean_newton_iters': mean_iters, 'storage': args.dtype,
                    'step': 'eager launches' if args.no_graph else 'CUDA graph replay of the public-API step (rank-local part) + NCCL all-reduce',
                    'eager_ms_per_step': ms_eager},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h},
         'gpu_launches': 3 * args.steps,   # per step: parameter preparation + loss/backward + reduce/chain rule
                                           # (loss.mean() and its backward reuse that launch, ops.BatchLoss)
-        'roofline': {'bound': 'fp64_cuda_core' if dtype == torch.float64 else 'fp32_cuda_core',
+        'roofline': {'bound': 'fp64_cuda_core',
                      'achieved': achieved_tflops, 'peak': peak_flops / 1e12, 'unit': 'TFLOP/s',
                      'frac': achieved_tflops / (peak_flops / 1e12), 'traffic': traffic,
                      'algorithmic_bytes': B * BYTES_PER_SAMPLE[dtype],
