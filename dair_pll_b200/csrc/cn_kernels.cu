@@ -155,7 +155,11 @@ __global__ void __launch_bounds__(kWfWarps * 32)
 cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
                     const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half, T dt,
                     T eps, int64_t B, IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
-                    T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag) {
+                    T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag,
+                    unsigned long long* __restrict__ dyn_counter) {
+  // dyn_counter != nullptr (variant 2): warps take their triage chunks of 32 samples from a global counter instead
+  // of a static range -- removes the load imbalance between warps, but the assignment of samples to warps (and
+  // with it the rounding of the gradient sums) then depends on timing.
   if (skip_flag && *skip_flag) return;
   extern __shared__ __align__(16) unsigned char wf_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -172,9 +176,9 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
   // static contiguous sample range of this warp
   const int64_t gw = (int64_t)blockIdx.x * kWfWarps + warp, W = (int64_t)gridDim.x * kWfWarps;
   const int64_t base = B / W, rem = B % W;
-  const int64_t lo = gw * base + (gw < rem ? gw : rem);
-  const int64_t hi = lo + base + (gw < rem ? 1 : 0);
-  int64_t next = lo;
+  const int64_t lo = dyn_counter ? 0 : gw * base + (gw < rem ? gw : rem);
+  const int64_t hi = dyn_counter ? B : lo + base + (gw < rem ? 1 : 0);
+  int64_t next = lo;               // static: next unread sample of the range; dynamic: B once the counter ran out
 
   for (int s = lane; s < kWfSlots; s += 32) { pool->q_done[s] = (uint8_t)s; pool->sample[s] = -1; }
   int n_act = 0, n_done = kWfSlots, h_act = 0, h_done = 0, n_in = 0, h_in = 0;
@@ -198,10 +202,17 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
     if (phase == 2) {
       // T: the next 32 input samples, in registers only.  Free flight (u = 0, f = 0 optimal) is finalised
       // here at a third of the generic cost; the others wait in q_in for a slot.
-      const int64_t left = hi - next;
+      int64_t first = next;
+      if (dyn_counter) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(dyn_counter, 32ull);
+        first = (int64_t)__shfl_sync(0xffffffffu, t, 0);
+        if (first >= B) first = B;
+      }
+      const int64_t left = hi - first;
       const int cnt = left < 32 ? (int)left : 32;
       bool queue = false;
-      const int64_t b = next + lane;
+      const int64_t b = first + lane;
       if (lane < cnt) {
         T xs[13], xps[13];
 #pragma unroll
@@ -228,9 +239,9 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
       const unsigned m_q = __ballot_sync(0xffffffffu, queue);
       if (queue) pool->q_in[(h_in + n_in + __popc(m_q & lt_mask)) % kWfSlots] = (int32_t)(b - lo);
       n_in += __popc(m_q);
-      next += cnt;
+      next = dyn_counter ? (cnt < 32 ? B : lo) : next + cnt;
 #ifndef CN_NO_PREFETCH
-      if (next + lane < hi) {       // the rows of the next triage visit: pull them into L2
+      if (!dyn_counter && next + lane < hi) {       // the rows of the next triage visit: pull them into L2
         const char* px = reinterpret_cast<const char*>(x + (next + lane) * 13);
         const char* pp = reinterpret_cast<const char*>(xp + (next + lane) * 13);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(px));
@@ -672,7 +683,7 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
     inertia = params; mu = params + 10; half = params + 11;
   }
   int blocks;
-  if (variant == 0) {
+  if (variant == 0 || variant == 2) {
     // wavefront kernel: persistent, one resident set of blocks
     const size_t smem = sizeof(WfWarpPool<T>) * kWfWarps;
     cudaError_t ea = cudaFuncSetAttribute(cube_loss_wf_kernel<T, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -687,8 +698,15 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
     if (cap > kMaxBlocks) cap = kMaxBlocks;
     blocks = (int)(need < cap ? need : cap);
     if (blocks < 1) blocks = 1;
+    unsigned long long* dyn = nullptr;
+    if (variant == 2) {
+      if (!workspace || workspace_bytes < dpll_workspace_bytes()) return DPLL_EWORKSPACE;
+      dyn = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + dpll_workspace_bytes() - sizeof(double));
+      cudaError_t em = cudaMemsetAsync(dyn, 0, sizeof(unsigned long long), st);
+      if (em != cudaSuccess) return (int)em;
+    }
     cube_loss_wf_kernel<T, IO><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss,
-                                                               force, iters, partials, grad ? 1 : 0, skip_flag);
+                                                               force, iters, partials, grad ? 1 : 0, skip_flag, dyn);
   } else {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_kernel<T, IO>, kLossThreads, 0);
@@ -743,10 +761,11 @@ int launch_cube_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO*
 
 extern "C" {
 
-// Kernel variant selector for A/B measurements (0 = wavefront [default], 1 = one sample per thread).
+// Kernel variant selector for A/B measurements (0 = wavefront, static ranges [default, deterministic];
+// 1 = one sample per thread; 2 = wavefront with dynamic sample distribution [not bitwise reproducible]).
 static int g_loss_variant = 0;
 int dpll_set_loss_variant(int variant) {
-  if (variant < 0 || variant > 1) return DPLL_EINVAL;
+  if (variant < 0 || variant > 2) return DPLL_EINVAL;
   g_loss_variant = variant;
   return DPLL_OK;
 }

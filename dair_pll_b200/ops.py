@@ -34,7 +34,9 @@ def _workspace(device: torch.device) -> Tensor:
 
 
 def set_loss_variant(variant: int) -> None:
-    """0 = warp-level wavefront kernel (default), 1 = one sample per thread (A/B measurements)."""
+    """0 = warp-level wavefront kernel, static sample ranges (default; bitwise reproducible), 1 = one sample per
+    thread (A/B measurements), 2 = wavefront kernel with dynamic sample distribution (faster by the load imbalance,
+    gradient sums reproducible only to rounding)."""
     _lib.check(_lib.load().dpll_set_loss_variant(variant), 'dpll_set_loss_variant')
 
 

@@ -605,3 +605,23 @@ def test_contactnets_training_example_recovers_geometry():
     err0 = max(abs(a - b) for a, b in zip(out['initial']['half_lengths'], truth))
     err = max(abs(a - b) for a, b in zip(out['learned']['half_lengths'], truth))
     assert err0 > 2e-3 and err < 0.4 * err0
+
+
+def test_dynamic_distribution_variant_agrees_to_rounding():
+    """Variant 2 (warps draw their triage chunks from a global counter): same per-sample results, gradient sums equal
+    up to the rounding of a different summation order; sizes around the chunk and pool seams."""
+    g = load_golden('cube_synthetic')
+    inertia, mu, half = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    x = synthetic.cube_states(200001, seed=51, device=DEV)
+    traj, _ = ops.cube_rollout(x, inertia, mu, half, 0.0068, 1)
+    xp = synthetic.perturb_next_state(traj[:, 1], seed=52)
+    for n in (1, 31, 32, 33, 4097, 200001):
+        a = ops.cube_loss_raw(x[:n], xp[:n], inertia, mu, half, 0.0068, 1e-3, want_force=True, want_iters=True)
+        try:
+            ops.set_loss_variant(2)
+            b = ops.cube_loss_raw(x[:n], xp[:n], inertia, mu, half, 0.0068, 1e-3, want_force=True, want_iters=True)
+        finally:
+            ops.set_loss_variant(0)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4]), n
+        assert max_rel_to_scale(a[1].cpu().numpy(), b[1].cpu().numpy()) < 1e-12, n
+        assert abs(a[2].item() - b[2].item()) <= 1e-12 * abs(a[2].item()), n
