@@ -150,7 +150,7 @@ template <typename T> struct WfWarpPool {
   int32_t q_in[kWfSlots];       // offsets of triaged samples that need the solver, waiting for a slot
 };
 
-template <typename T, typename IO>
+template <typename T, typename IO, int UNR>
 __global__ void __launch_bounds__(kWfWarps * 32)
 cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
                     const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half, T dt,
@@ -264,7 +264,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
         T best = pool->field[39][slot], d0 = pool->field[46][slot];
         cn::CubeTrial<T> tr{pool->field[47][slot], pool->field[48][slot], pool->field[49][slot]};
         int it = pool->iters[slot];
-        st = cn::cube_newton_visit<T, kWfUnr>(P, S, cfg, u, d, d0, best, tr, it);
+        st = cn::cube_newton_visit<T, UNR>(P, S, cfg, u, d, d0, best, tr, it);
         pool->iters[slot] = it;
         pool->field[39][slot] = best;
 #pragma unroll
@@ -686,10 +686,12 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
   if (variant == 0 || variant == 2) {
     // wavefront kernel: persistent, one resident set of blocks
     const size_t smem = sizeof(WfWarpPool<T>) * kWfWarps;
-    cudaError_t ea = cudaFuncSetAttribute(cube_loss_wf_kernel<T, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ea = cudaFuncSetAttribute(cube_loss_wf_kernel<T, IO, kWfUnr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ea == cudaSuccess)
+      ea = cudaFuncSetAttribute(cube_loss_wf_kernel<T, IO, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ea != cudaSuccess) return (int)ea;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_wf_kernel<T, IO>, kWfWarps * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_wf_kernel<T, IO, kWfUnr>, kWfWarps * 32, smem);
     if (per_sm < 1) per_sm = 1;
     // A warp needs a few hundred samples to keep its pool full; with fewer, every SM would run many
     // mostly-empty warps at the issue rate of full ones.  Small batches therefore use fewer warps.
@@ -705,8 +707,17 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
       cudaError_t em = cudaMemsetAsync(dyn, 0, sizeof(unsigned long long), st);
       if (em != cudaSuccess) return (int)em;
     }
-    cube_loss_wf_kernel<T, IO><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss,
-                                                               force, iters, partials, grad ? 1 : 0, skip_flag, dyn);
+    // Up to ~256 samples per warp the launch is a few long Newton chains per warp (latency-bound): the
+    // instance with the per-contact loop of the Newton visit unrolled overlaps the four contacts (measured -8% at
+    // 65,536 pairs, -5% at 262,144).  Larger batches keep every warp's pool full and run the rolled instance,
+    // which is smaller in the instruction cache (the unrolled one is +5% at 1M pairs, +15% at 4M).
+    if (B <= cap * kWfWarps * 256)
+      cube_loss_wf_kernel<T, IO, 4><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss,
+                                                                    force, iters, partials, grad ? 1 : 0, skip_flag, dyn);
+    else
+      cube_loss_wf_kernel<T, IO, kWfUnr><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B,
+                                                                         loss, force, iters, partials, grad ? 1 : 0,
+                                                                         skip_flag, dyn);
   } else {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_kernel<T, IO>, kLossThreads, 0);
