@@ -188,7 +188,7 @@ def secondary_configs(device):
     ms = _time_gpu(elbow_step, device, 3, warmup=1)
     out['elbow_mesh_loss_backward_B262144_f64'] = {
         'ms': ms, 'samples_per_s': Be / ms * 1e3,
-        'note': 'support-function networks: three (1.05M x 256 x 256) FP64 products per network on cuBLAS (torch.matmul) with the memory-bound layers fused in the dpll_icnn_* kernels; elbow loss kernel is one sample per thread'}
+        'note': 'support-function networks: three (1.05M x 256 x 256) FP64 products per network on cuBLAS (torch.matmul) with the memory-bound layers fused in the dpll_icnn_* kernels; elbow loss kernel with warp-level triage / solve passes'}
     return out
 
 

@@ -559,6 +559,23 @@ CN_HD T elbow_loss_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, cons
   return elbow_loss_epilogue(P, S, A, u, grad, force_out, grad ? grad_pts : (T*)nullptr);
 }
 
+// The same loss path for the two-phase kernel: `solve` = false is the triage pass -- a sample that needs the solver
+// is left untouched (returns false); `solve` = true runs the full path.  One code instance serves both passes.
+template <typename T>
+CN_HD bool elbow_loss_sample_phase(const ElbowParams<T>& P, const SolverCfg<T>& cfg, bool solve, const T* x, const T* xp,
+                                   const T* pts, T* grad, T* force_out, T* grad_pts, int* iters_out, T* loss_out) {
+  ElbowProb<T> S;
+  ElbowLossAux<T> A;
+  elbow_loss_prologue(P, x, xp, pts, S, A);
+  if (!solve && !elbow_trivially_solved(S)) return false;
+  T u[7] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
+  const int it = elbow_solve(P, S, cfg, u);            // returns at once for a trivially solved sample
+  if (iters_out) *iters_out = it;
+  if (!grad && grad_pts) for (int i = 0; i < 24; ++i) grad_pts[i] = T(0);
+  *loss_out = elbow_loss_epilogue(P, S, A, u, grad, force_out, grad ? grad_pts : (T*)nullptr);
+  return true;
+}
+
 // ---------------------------------------------------------------------------
 // learnable time step
 // ---------------------------------------------------------------------------
