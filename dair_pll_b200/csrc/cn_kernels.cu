@@ -801,11 +801,11 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
       cudaError_t em = cudaMemsetAsync(dyn, 0, sizeof(unsigned long long), st);
       if (em != cudaSuccess) return (int)em;
     }
-    // Up to ~400 samples per warp (crossover measured at ~440) the launch is a few long Newton chains per warp: the
+    // Up to ~320 samples per warp (crossover measured around 400) the launch is a few long Newton chains per warp: the
     // instance with the per-contact loop of the Newton visit unrolled overlaps the four contacts (measured -8% at
     // 65,536 pairs, -5% at 262,144).  Larger batches keep every warp's pool full and run the rolled instance,
     // which is smaller in the instruction cache (the unrolled one is +5% at 1M pairs, +15% at 4M).
-    if (B <= cap * kWfWarps * 400)
+    if (B <= cap * kWfWarps * 320)
       cube_loss_wf_kernel<T, IO, 4><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss,
                                                                     force, iters, partials, grad ? 1 : 0, skip_flag, dyn);
     else
