@@ -75,11 +75,18 @@ template <typename T> struct ElbowKin {
   uint32_t sel[2];
 };
 
+// View of the per-sample quantities that stay fixed during the Newton solve: element k of the 121-field record
+// at p[k * s].  s = 1 over a local array; s = block size over a thread-interleaved shared-memory array (the
+// two-phase loss kernel: the record is read on every Newton visit, and as a per-thread local array it
+// overflows L1 -- ncu: 41% of the stall samples on local loads).
+constexpr int ELBOW_PROB_FIELDS = 121;
 template <typename T> struct ElbowProb {
-  T M[49];       // world-twist mass matrix (full, symmetric)
-  T rho[24];     // lever arms from origin 1, world
-  T hc[24];      // hinge columns (0 for body-1 contacts)
-  T q[24];       // QP linear term, sappy order per contact
+  T* p;
+  int s;
+  CN_HD T& M(int i) const { return p[i * s]; }            // world-twist mass matrix (7x7, full, symmetric)
+  CN_HD T& rho(int k) const { return p[(49 + k) * s]; }   // lever arms from origin 1, world, 3 per contact
+  CN_HD T& hc(int k) const { return p[(73 + k) * s]; }    // hinge columns (0 for body-1 contacts)
+  CN_HD T& q(int k) const { return p[(97 + k) * s]; }     // QP linear term, sappy order per contact
 };
 
 // rotation about a unit axis by angle th (Rodrigues), row-major
@@ -209,7 +216,7 @@ CN_HD void elbow_mass_force(const ElbowParams<T>& P, const ElbowKin<T>& K, const
 // 8, geometry.py:162-202); otherwise pts[24] holds the 4 + 4 witness points in the geometry frames, as
 // produced by the learned support function (DeepSupportConvex.get_vertices, geometry.py:309-325).
 template <typename T>
-CN_HD void elbow_contacts(const ElbowParams<T>& P, ElbowKin<T>& K, ElbowProb<T>& S, const T* pts) {
+CN_HD void elbow_contacts(const ElbowParams<T>& P, ElbowKin<T>& K, const ElbowProb<T>& S, const T* pts) {
   for (int b = 0; b < 2; ++b) {
     const T* R = K.R[b];
     const T d[3] = {-R[6], -R[7], -R[8]};
@@ -221,11 +228,11 @@ CN_HD void elbow_contacts(const ElbowParams<T>& P, ElbowKin<T>& K, ElbowProb<T>&
       rot3(R, p, r);
       const int cc = 4 * b + c;
       if (b == 0) {
-        for (int i = 0; i < 3; ++i) { S.rho[3 * cc + i] = r[i]; S.hc[3 * cc + i] = T(0); }
+        for (int i = 0; i < 3; ++i) { S.rho(3 * cc + i) = r[i]; S.hc(3 * cc + i) = T(0); }
       } else {
         T ar[3];
         cross3(K.aW, r, ar);
-        for (int i = 0; i < 3; ++i) { S.rho[3 * cc + i] = K.rJ[i] + r[i]; S.hc[3 * cc + i] = ar[i]; }
+        for (int i = 0; i < 3; ++i) { S.rho(3 * cc + i) = K.rJ[i] + r[i]; S.hc(3 * cc + i) = ar[i]; }
       }
     }
   }
@@ -233,15 +240,16 @@ CN_HD void elbow_contacts(const ElbowParams<T>& P, ElbowKin<T>& K, ElbowProb<T>&
 
 // contact-point velocity of contact c for world twist u (7): e = u_w x rho + u_v + h thetadot
 template <typename T> CN_HD void elbow_point_vel(const ElbowProb<T>& S, int c, const T* u, T* e) {
-  cross3(u, S.rho + 3 * c, e);
-  for (int i = 0; i < 3; ++i) e[i] += u[3 + i] + S.hc[3 * c + i] * u[6];
+  const T rho[3] = {S.rho(3 * c), S.rho(3 * c + 1), S.rho(3 * c + 2)};
+  cross3(u, rho, e);
+  for (int i = 0; i < 3; ++i) e[i] += u[3 + i] + S.hc(3 * c + i) * u[6];
 }
 
 template <typename T> CN_HD void elbow_residual(const ElbowParams<T>& P, const ElbowProb<T>& S, int c, const T* u, T* r) {
   T e[3];
   elbow_point_vel(S, c, u, e);
   const T mu = P.mu[c >> 2];
-  r[0] = mu * e[0] + S.q[3 * c]; r[1] = mu * e[1] + S.q[3 * c + 1]; r[2] = e[2] + S.q[3 * c + 2];
+  r[0] = mu * e[0] + S.q(3 * c); r[1] = mu * e[1] + S.q(3 * c + 1); r[2] = e[2] + S.q(3 * c + 2);
 }
 
 template <typename T, bool WANT_H>
@@ -249,18 +257,18 @@ CN_HD void elbow_eval(const ElbowParams<T>& P, const ElbowProb<T>& S, const T* u
   T Mu[7], z[7];
   for (int i = 0; i < 7; ++i) {
     T s = T(0);
-    for (int j = 0; j < 7; ++j) s += S.M[7 * i + j] * u[j];
+    for (int j = 0; j < 7; ++j) s += S.M(7 * i + j) * u[j];
     Mu[i] = s; z[i] = T(0);
   }
-  if (WANT_H) for (int i = 0; i < 49; ++i) H[i] = S.M[i];
+  if (WANT_H) for (int i = 0; i < 49; ++i) H[i] = S.M(i);
   for (int c = 0; c < EL_NC; ++c) {
     const T mu = P.mu[c >> 2];
     T r[3], f[3], K[6];
     elbow_residual(P, S, c, u, r);
     cone_eval<T, WANT_H>(r, P.inv_eps, mu, f, K);
     const T ft[3] = {mu * f[0], mu * f[1], f[2]};
-    const T* rho = S.rho + 3 * c;
-    const T* hc = S.hc + 3 * c;
+    const T rho[3] = {S.rho(3 * c), S.rho(3 * c + 1), S.rho(3 * c + 2)};
+    const T hc[3] = {S.hc(3 * c), S.hc(3 * c + 1), S.hc(3 * c + 2)};
     T tq[3];
     cross3(rho, ft, tq);
     for (int i = 0; i < 3; ++i) { z[i] += tq[i]; z[3 + i] += ft[i]; }
@@ -294,7 +302,7 @@ CN_HD void elbow_eval(const ElbowParams<T>& P, const ElbowProb<T>& S, const T* u
 template <typename T> CN_HD bool elbow_trivially_solved(const ElbowProb<T>& S) {
   bool open = true;
   for (int c = 0; c < EL_NC; ++c) {
-    const T q0 = S.q[3 * c], q1 = S.q[3 * c + 1], qn = S.q[3 * c + 2];
+    const T q0 = S.q(3 * c), q1 = S.q(3 * c + 1), qn = S.q(3 * c + 2);
     open = open && (qn >= T(0)) && (q0 * q0 + q1 * q1 <= qn * qn);
   }
   return open;
@@ -381,7 +389,7 @@ CN_HD void elbow_to_world(const T* R1, const T* v, T* u) {   // state velocity -
 }
 
 template <typename T>
-CN_HD void elbow_loss_prologue(const ElbowParams<T>& P, const T* x, const T* xp, const T* pts, ElbowProb<T>& S,
+CN_HD void elbow_loss_prologue(const ElbowParams<T>& P, const T* x, const T* xp, const T* pts, const ElbowProb<T>& S,
                                ElbowLossAux<T>& A) {
   elbow_kinematics(P, xp, A.K);
   A.pos_z = xp[6];
@@ -389,8 +397,8 @@ CN_HD void elbow_loss_prologue(const ElbowParams<T>& P, const T* x, const T* xp,
   elbow_to_world(A.K.R[0], xp + 8, A.vp);
   elbow_to_world(A.K.R[0], x + 8, vold);           // same frame map as the reference: v and v+ are both state coordinates
   T F[7];
-  elbow_mass_force(P, A.K, A.vp, S.M, F, A.b2);
-  for (int i = 0; i < 49; ++i) A.LM[i] = S.M[i];
+  elbow_mass_force(P, A.K, A.vp, A.LM, F, A.b2);       // M into LM, copied to the record before LM is factorised
+  for (int i = 0; i < 49; ++i) S.M(i) = A.LM[i];
   chol_factor<T, 7>(A.LM, A.LMinv);
   chol_solve<T, 7>(A.LM, A.LMinv, F, A.acc);
   for (int i = 0; i < 7; ++i) A.dv[i] = A.vp[i] - (vold[i] + P.dt * A.acc[i]);
@@ -404,17 +412,17 @@ CN_HD void elbow_loss_prologue(const ElbowParams<T>& P, const T* x, const T* xp,
     const T sx = mu * ev[0], sy = mu * ev[1];
     const T speed2 = sx * sx + sy * sy;
     const T speed = speed2 * t_rsqrt(t_max(speed2, t_tiny<T>()));
-    const T phic = S.rho[3 * c + 2] + A.pos_z;
-    S.q[3 * c] = -mu * ed[0] + P.dt * sx;
-    S.q[3 * c + 1] = -mu * ed[1] + P.dt * sy;
-    S.q[3 * c + 2] = -ed[2] + t_abs(phic) + P.dt * speed;
+    const T phic = S.rho(3 * c + 2) + A.pos_z;
+    S.q(3 * c) = -mu * ed[0] + P.dt * sx;
+    S.q(3 * c + 1) = -mu * ed[1] + P.dt * sy;
+    S.q(3 * c + 2) = -ed[2] + t_abs(phic) + P.dt * speed;
     const T pneg = t_max(-phic, T(0));
     pen += pneg * pneg;
   }
   T e = T(0);
   for (int i = 0; i < 7; ++i) {
     T s = T(0);
-    for (int j = 0; j < 7; ++j) s += S.M[7 * i + j] * A.dv[j];
+    for (int j = 0; j < 7; ++j) s += S.M(7 * i + j) * A.dv[j];
     e += A.dv[i] * s;
   }
   A.konst = T(0.5) * e + pen;
@@ -433,14 +441,16 @@ CN_HD T elbow_loss_epilogue(const ElbowParams<T>& P, const ElbowProb<T>& S, cons
     cone_eval<T, false>(r, P.inv_eps, mu, f + 3 * c, (T*)nullptr);
     const T ft[3] = {mu * f[3 * c], mu * f[3 * c + 1], f[3 * c + 2]};
     T tq[3];
-    cross3(S.rho + 3 * c, ft, tq);
+    const T rho[3] = {S.rho(3 * c), S.rho(3 * c + 1), S.rho(3 * c + 2)};
+    cross3(rho, ft, tq);
     for (int i = 0; i < 3; ++i) {
       z[i] += tq[i]; z[3 + i] += ft[i];
-      qf += S.q[3 * c + i] * f[3 * c + i]; ff += f[3 * c + i] * f[3 * c + i];
+      qf += S.q(3 * c + i) * f[3 * c + i]; ff += f[3 * c + i] * f[3 * c + i];
       const T af = t_abs(f[3 * c + i]);
       fmax = (af > fmax || af != af) ? af : fmax;
     }
-    z[6] += dot3(S.hc + 3 * c, ft);
+    const T hc[3] = {S.hc(3 * c), S.hc(3 * c + 1), S.hc(3 * c + 2)};
+    z[6] += dot3(hc, ft);
   }
   if (!(fmax <= T(1e3))) {
     if (force_out) for (int i = 0; i < 24; ++i) force_out[i] = T(0);
@@ -535,7 +545,7 @@ CN_HD T elbow_loss_epilogue(const ElbowParams<T>& P, const ElbowProb<T>& S, cons
     T ftB[3], gtB[3], ObB[3], OvB[3], p1[3], p2[3];
     rot3t(R, ft, ftB); rot3t(R, gt, gtB); rot3t(R, Ob, ObB); rot3t(R, Ov, OvB);
     cross3(ftB, ObB, p1); cross3(gtB, OvB, p2);
-    const T phic = S.rho[3 * c + 2] + A.pos_z;
+    const T phic = S.rho(3 * c + 2) + A.pos_z;
     const T phibar = (phic > T(0) ? fn : (phic < T(0) ? -fn : T(0))) - T(2) * t_max(-phic, T(0));
     for (int k = 0; k < 3; ++k) {
       const T pbar = p1[k] + p2[k] + phibar * R[6 + k];      // d loss / d (witness point, geometry frame)
@@ -549,7 +559,8 @@ CN_HD T elbow_loss_epilogue(const ElbowParams<T>& P, const ElbowProb<T>& S, cons
 template <typename T>
 CN_HD T elbow_loss_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, const T* x, const T* xp, const T* pts,
                           T* grad, T* force_out, T* grad_pts, int* iters_out) {
-  ElbowProb<T> S;
+  T store[ELBOW_PROB_FIELDS];
+  const ElbowProb<T> S{store, 1};
   ElbowLossAux<T> A;
   elbow_loss_prologue(P, x, xp, pts, S, A);
   T u[7] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
@@ -562,9 +573,9 @@ CN_HD T elbow_loss_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, cons
 // The same loss path for the two-phase kernel: `solve` = false is the triage pass -- a sample that needs the solver
 // is left untouched (returns false); `solve` = true runs the full path.  One code instance serves both passes.
 template <typename T>
-CN_HD bool elbow_loss_sample_phase(const ElbowParams<T>& P, const SolverCfg<T>& cfg, bool solve, const T* x, const T* xp,
-                                   const T* pts, T* grad, T* force_out, T* grad_pts, int* iters_out, T* loss_out) {
-  ElbowProb<T> S;
+CN_HD bool elbow_loss_sample_phase(const ElbowParams<T>& P, const SolverCfg<T>& cfg, bool solve, const ElbowProb<T>& S,
+                                   const T* x, const T* xp, const T* pts, T* grad, T* force_out, T* grad_pts,
+                                   int* iters_out, T* loss_out) {
   ElbowLossAux<T> A;
   elbow_loss_prologue(P, x, xp, pts, S, A);
   if (!solve && !elbow_trivially_solved(S)) return false;
@@ -582,13 +593,14 @@ CN_HD bool elbow_loss_sample_phase(const ElbowParams<T>& P, const SolverCfg<T>& 
 template <typename T>
 CN_HD int elbow_step_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, const T* x, const T* pts, T* xn,
                             T* force_out) {
-  ElbowProb<T> S;
+  T store[ELBOW_PROB_FIELDS];
+  const ElbowProb<T> S{store, 1};
   ElbowKin<T> K;
   elbow_kinematics(P, x, K);
   T vW[7], F[7], LM[49], LMinv[7], acc[7], vm[7];
   elbow_to_world(K.R[0], x + 8, vW);
-  elbow_mass_force(P, K, vW, S.M, F, (T*)nullptr);
-  for (int i = 0; i < 49; ++i) LM[i] = S.M[i];
+  elbow_mass_force(P, K, vW, LM, F, (T*)nullptr);
+  for (int i = 0; i < 49; ++i) S.M(i) = LM[i];
   chol_factor<T, 7>(LM, LMinv);
   chol_solve<T, 7>(LM, LMinv, F, acc);
   for (int i = 0; i < 7; ++i) vm[i] = vW[i] + P.dt * acc[i];
@@ -598,9 +610,9 @@ CN_HD int elbow_step_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, co
     const T mu = P.mu[c >> 2];
     T e[3];
     elbow_point_vel(S, c, vm, e);
-    S.q[3 * c] = mu * e[0];
-    S.q[3 * c + 1] = mu * e[1];
-    S.q[3 * c + 2] = e[2] + (S.rho[3 * c + 2] + x[6]) * inv_dt;
+    S.q(3 * c) = mu * e[0];
+    S.q(3 * c + 1) = mu * e[1];
+    S.q(3 * c + 2) = e[2] + (S.rho(3 * c + 2) + x[6]) * inv_dt;
   }
   T u[7] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
   const int it = elbow_solve(P, S, cfg, u);

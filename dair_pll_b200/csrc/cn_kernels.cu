@@ -611,7 +611,9 @@ elbow_loss_2p_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const 
       for (int i = 0; i < DPLL_ELBOW_NPARAM; ++i) gs[i] = T(0);
       int it = 0;
       T l = T(0);
-      const bool done = cn::elbow_loss_sample_phase<T>(P, cfg, solve, xs, xps, pts ? pt : (const T*)nullptr,
+      T store[cn::ELBOW_PROB_FIELDS];        // problem record (measured: thread-interleaved shared memory at 6 warps
+      const cn::ElbowProb<T> S{store, 1};     // per SM is 1.6x slower than this local array at 8 warps per SM)
+      const bool done = cn::elbow_loss_sample_phase<T>(P, cfg, solve, S, xs, xps, pts ? pt : (const T*)nullptr,
                                                        want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr,
                                                        grad_pts ? gp : (T*)nullptr, &it, &l);
       if (done) {
