@@ -324,6 +324,12 @@ def main():
             graphed()
             return reducer.reduce()
         ms_step = timed(step_graphed, args.steps, max(args.warmup, 3))
+    # the timed region lasts ~10 ms, shorter than one nvidia-smi query: keep the same step running (untimed) for
+    # about half a second so that the clock / throttle samples are taken under this load
+    load_fn = step_resident if args.no_graph else step_graphed
+    for _ in range(max(1, min(5000, int(500.0 / ms_step)))):      # same count on every rank (ms_step is the max over ranks)
+        load_fn()
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
     value = world * B / (ms_step * 1e-3)
 
