@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--batch', type=int, default=1 << 20, help='samples per GPU per step')
+    ap.add_argument('--batch', type=int, default=1 << 20, help='samples per step: global (strong scaling) or per GPU (weak)')
     ap.add_argument('--dtype', choices=['f64', 'f32'], default='f64')
     ap.add_argument('--impl', choices=['b200', 'reference'], default='b200')
     ap.add_argument('--cpu-sample', type=int, default=65536, help='samples in the CPU baseline step')
@@ -47,6 +47,13 @@ def parse_args():
     ap.add_argument('--no-secondary', action='store_true', help='skip the other BASELINE.json configs')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of the CUDA-graph replay')
     ap.add_argument('--variant', type=int, default=0, help='0 = wavefront loss kernel, 1 = one sample per thread')
+    ap.add_argument('--scaling', choices=['strong', 'weak'], default=None,
+                    help='strong: --batch is the GLOBAL batch, sharded over the ranks (default for N > 1); '
+                         'weak: --batch pairs per GPU (default for N = 1)')
+    ap.add_argument('--allreduce', choices=['peer', 'nccl'], default='peer',
+                    help='gradient exchange: in-kernel peer-memory all-reduce (default) or NCCL after the step')
+    ap.add_argument('--order', choices=['cost', 'natural'], default='cost',
+                    help='batch order: by decreasing Newton count of the previous pass (default) or generator order')
     return ap.parse_args()
 
 
@@ -140,29 +147,81 @@ def _time_gpu(fn, device, reps, warmup=2):
     return s.elapsed_time(e) / reps
 
 
-def secondary_configs(device):
+def _roofline(flops, ms, peak_flops, extra=None):
+    out = {'bound': 'fp64_cuda_core', 'achieved': flops / (ms * 1e-3) / 1e12, 'peak': peak_flops / 1e12, 'unit': 'TFLOP/s',
+           'frac': flops / (ms * 1e-3) / peak_flops, 'kernel_ms': ms}
+    if extra:
+        out.update(extra)
+    return out
+
+
+def secondary_configs(device, peak_flops):
     """The other BASELINE.json configs, measured through the public API on device-resident inputs
-    (CUDA events; context for the headline number, not part of it)."""
-    from dair_pll_b200 import synthetic
+    (CUDA events; context for the headline number, not part of it).  Every entry carries the roofline of
+    its dominant kernel by the survey's algorithmic FLOP model and the mean
+    Newton count the model is evaluated at."""
+    import numpy as np
+    from dair_pll_b200 import ops, synthetic
     from dair_pll_b200.multibody_learnable_system import MultibodyLearnableSystem
     out = {}
-    # config 1: cube loss + backward at B = 65,536, fp64 and the fp32 variant
     system = make_system(device, torch.float64)
+    params = list(system.parameters())
+    lt, ct = system.multibody_terms.lagrangian_terms, system.multibody_terms.contact_terms
+
+    def leaves(dtype):
+        return [t.detach().to(dtype) for t in (lt.inertial_parameters, ct.friction_params, ct.geometries[0].length_params)]
+
+    def cube_entry(xx, xxp, ordered):
+        """graph-replayed public-API step + kernel-only roofline on one batch"""
+        from dair_pll_b200 import parallel
+        system.dynamic_schedule = ordered
+        if ordered:
+            it = ops.cube_loss_leaf_dp_raw(xx, xxp, *leaves(xx.dtype), DT, 1e-3, want_iters=True)[4]
+            idx = torch.argsort(it, descending=True, stable=True)
+            xx, xxp = xx.index_select(0, idx).contiguous(), xxp.index_select(0, idx).contiguous()
+
+        def step():
+            for p in params:
+                p.grad = None
+            mean = system.contactnets_loss(xx, None, xxp).mean()
+            mean.backward()
+            return mean
+        ms_eager = _time_gpu(step, device, 10)
+        graphed = parallel.GraphedStep(step, device)
+        n = xx.shape[0]
+        ms = _time_gpu(graphed, device, max(20, int(100.0 / max(ms_eager, 0.05))))
+        flags = ops.LOSS_DYNAMIC if ordered else 0
+        it = ops.cube_loss_leaf_dp_raw(xx, xxp, *leaves(xx.dtype), DT, 1e-3, flags=flags, want_iters=True)[4]
+        mean_it = it.double().mean().item()
+        ms_k = _time_gpu(lambda: ops.cube_loss_leaf_dp_raw(xx, xxp, *leaves(xx.dtype), DT, 1e-3, flags=flags), device,
+                         max(20, int(100.0 / max(ms_eager, 0.05))))
+        system.dynamic_schedule = False
+        return {'ms': ms, 'samples_per_s': n / ms * 1e3, 'eager_ms': ms_eager, 'mean_newton_iters': mean_it,
+                'order': 'cost' if ordered else 'natural',
+                'roofline': _roofline(n * (F0_CUBE + FIT_CUBE * mean_it), ms_k, peak_flops,
+                                      {'kernel': 'cube_loss_wf_kernel', 'flops_per_sample': F0_CUBE + FIT_CUBE * mean_it})}
+
+    # config 2: cube loss + backward at B = 65,536, fp64 and the fp32 variant (fp32 storage, fp64 arithmetic)
     x, xp = make_batch(system, 65536, 11, device, torch.float64)
-
-    from dair_pll_b200 import parallel
-    reducer = parallel.GradientAllReduce(list(system.parameters()), device, 1)
-
-    def cube_step(xx, xxp):
-        reducer.zero()
-        mean = system.contactnets_loss(xx, None, xxp).mean()
-        mean.backward()
-        return reducer(mean)
     for name, (xx, xxp) in {'f64': (x, xp), 'f32_storage': (x.float(), xp.float())}.items():
-        ms_eager = _time_gpu(lambda: cube_step(xx, xxp), device, 10)
-        graphed = parallel.GraphedStep(lambda: cube_step(xx, xxp), device)
-        ms = _time_gpu(graphed, device, 20)
-        out[f'cube_loss_backward_B65536_{name}'] = {'ms': ms, 'samples_per_s': 65536 / ms * 1e3, 'eager_ms': ms_eager}
+        for ordered in (False, True):
+            out[f'cube_loss_backward_B65536_{name}_{"cost" if ordered else "natural"}_order'] = cube_entry(xx, xxp, ordered)
+    # the real contact distribution: the reference's recorded tosses (assets/contactnets_cube, 478 consecutive pairs
+    # kept as a test fixture), tiled to the headline batch size, nominal URDF parameters
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'cube_real_nominal.npz'))
+    reps = (1 << 20) // g['x'].shape[0] + 1
+    perm = torch.randperm(reps * g['x'].shape[0], generator=torch.Generator().manual_seed(0))[:1 << 20]
+    xr = torch.from_numpy(np.tile(g['x'], (reps, 1)))[perm].to(device).contiguous()
+    xpr = torch.from_numpy(np.tile(g['x_plus'], (reps, 1)))[perm].to(device).contiguous()
+    saved = {k: v.detach().clone() for k, v in system.state_dict().items()}
+    system.load_state_dict({
+        'multibody_terms.lagrangian_terms.inertial_parameters': torch.from_numpy(g['theta']).to(device),
+        'multibody_terms.contact_terms.friction_params': torch.from_numpy(g['friction_params']).to(device),
+        'multibody_terms.contact_terms.geometries.0.length_params': torch.from_numpy(g['half_lengths']).reshape(1, 3).to(device)})
+    for ordered in (False, True):
+        out[f'cube_real_tiled_B1048576_f64_{"cost" if ordered else "natural"}_order'] = cube_entry(xr, xpr, ordered)
+    system.load_state_dict(saved)
+
     # config 4: rollout, 4,096 cube tosses x 80 steps
     x0 = synthetic.cube_states(4096, seed=5, device=device)
     carry = torch.zeros(4096, 1, device=device)
@@ -170,25 +229,72 @@ def secondary_configs(device):
     def roll():
         with torch.no_grad():
             system.simulate(x0.unsqueeze(-2), carry, 80)
-    ms = _time_gpu(roll, device, 5)
-    out['cube_rollout_4096x80_f64'] = {'ms': ms, 'steps_per_s': 4096 * 80 / ms * 1e3}
-    # config 3: elbow with learned (ICNN, width 256) geometry, loss + backward at B = 262,144
-    torch.manual_seed(0)
-    elbow = MultibodyLearnableSystem({'elbow': os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow_mesh.urdf')}, DT).to(device)
+    ms = _time_gpu(roll, device, 10)
+    inertia, mu, half = (t.detach() for t in system._cube_params(torch.float64))
+    it_total = torch.empty(4096, dtype=torch.int32, device=device)
+    ops.cube_rollout(x0, inertia, mu, half, DT, 80, 1e-4, iters_out=it_total)
+    mean_it = it_total.double().mean().item() / 80
+    out['cube_rollout_4096x80_f64'] = {
+        'ms': ms, 'steps_per_s': 4096 * 80 / ms * 1e3, 'mean_newton_iters_per_step': mean_it,
+        'roofline': _roofline(4096 * 80 * (1600.0 + FIT_CUBE * mean_it + 150.0), ms, peak_flops,
+                              {'kernel': 'cube_rollout_kernel', 'flops_per_step': 1600.0 + FIT_CUBE * mean_it + 150.0,
+                               'note': '4,096 sequential chains of 80 dependent steps: latency-bound (a lone toss advances at '
+                                       '~20 us per step); 65,536 tosses reach 4.5x this rate'})}
+    # prediction loss: rollout + backward through every step's QP (K7)
+    x0g = x0[:4096].clone().requires_grad_()
+    target = torch.zeros(4096, 81, 13, device=device, dtype=torch.float64)
+
+    def pred_step():
+        for p in params:
+            p.grad = None
+        x0g.grad = None
+        traj, _ = system.simulate(x0g.unsqueeze(-2), carry, 80)
+        ((traj - target) ** 2).mean().backward()
+    ms = _time_gpu(pred_step, device, 3, warmup=1)
+    out['cube_prediction_loss_4096x80_f64'] = {'ms': ms, 'steps_per_s': 4096 * 80 / ms * 1e3,
+                                               'note': 'forward rollout + backward through every step (dpll_cube_rollout_grad_f64)'}
+    # elbow (two bodies, 8 contacts) with box geometries, loss + backward at B = 262,144
+    FO_EL, FIT_EL = 12000.0, 4700.0
+    ebox = MultibodyLearnableSystem({'elbow': os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow.urdf')}, DT).to(device)
     Be = 262144
     xe = synthetic.elbow_states(Be, seed=3, device=device)
     with torch.no_grad():
-        te, _ = elbow.simulate(xe.unsqueeze(-2), torch.zeros(Be, 1, device=device), 1)
+        te, _ = ebox.simulate(xe.unsqueeze(-2), torch.zeros(Be, 1, device=device), 1)
     xpe = synthetic.perturb_next_state(te[:, 1], seed=4, n_q=8)
+
+    def ebox_step():
+        for p in ebox.parameters():
+            p.grad = None
+        ebox.contactnets_loss(xe, None, xpe).mean().backward()
+    ms = _time_gpu(ebox_step, device, 10)
+    ine, mue, halfe, kin = ebox._elbow_params(torch.float64, device)
+    raw = ops.elbow_loss_raw(xe, xpe, ine.detach(), mue.detach(), halfe.detach(), kin, DT, 1e-3, want_iters=True)
+    mean_it = raw[4].double().mean().item()
+    ms_k = _time_gpu(lambda: ops.elbow_loss_raw(xe, xpe, ine.detach(), mue.detach(), halfe.detach(), kin, DT, 1e-3),
+                     device, 10)
+    out['elbow_box_loss_backward_B262144_f64'] = {
+        'ms': ms, 'samples_per_s': Be / ms * 1e3, 'mean_newton_iters': mean_it,
+        'roofline': _roofline(Be * (FO_EL + FIT_EL * mean_it), ms_k, peak_flops,
+                              {'kernel': 'elbow_loss kernel', 'flops_per_sample': FO_EL + FIT_EL * mean_it})}
+    # config 3: elbow with learned (ICNN, width 256) geometry, loss + backward at B = 262,144
+    torch.manual_seed(0)
+    elbow = MultibodyLearnableSystem({'elbow': os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow_mesh.urdf')}, DT).to(device)
+    with torch.no_grad():
+        te, _ = elbow.simulate(xe.unsqueeze(-2), torch.zeros(Be, 1, device=device), 1)
+    xpm = synthetic.perturb_next_state(te[:, 1], seed=4, n_q=8)
 
     def elbow_step():
         for p in elbow.parameters():
             p.grad = None
-        elbow.contactnets_loss(xe, None, xpe).mean().backward()
+        elbow.contactnets_loss(xe, None, xpm).mean().backward()
     ms = _time_gpu(elbow_step, device, 3, warmup=1)
+    ICNN_FLOPS = 4.28e6
     out['elbow_mesh_loss_backward_B262144_f64'] = {
         'ms': ms, 'samples_per_s': Be / ms * 1e3,
-        'note': 'support-function networks: three (1.05M x 256 x 256) FP64 products per network on cuBLAS (torch.matmul) with the memory-bound layers fused in the dpll_icnn_* kernels; elbow loss kernel with warp-level triage / solve passes'}
+        'roofline': _roofline(Be * (ICNN_FLOPS + FO_EL + FIT_EL * mean_it), ms, peak_flops,
+                              {'kernel': 'support-function networks (FP64 GEMMs + dpll_icnn_* layers) + elbow loss kernel',
+                               'flops_per_sample': ICNN_FLOPS + FO_EL + FIT_EL * mean_it,
+                               'note': 'whole step, not one kernel; Newton count taken from the box-geometry batch'})}
     return out
 
 
@@ -237,12 +343,15 @@ def run_reference(args):
     warmup = max(1, min(args.warmup, 2))
     sec = time_cpu(step, steps, warmup)
     value = B / sec
+    scaling = args.scaling or ('strong' if args.gpus > 1 else 'weak')
+    workload = (f'cube_contactnets_loss_backward_B{args.batch}_global' if scaling == 'strong'
+                else f'cube_contactnets_loss_backward_B{args.batch}_per_gpu')
     sample = f'{B} cube state pairs per step (same generator/parameters as the GPU arm), {steps} steps'
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC + ' fp64', 'value': value, 'unit': 'samples/s', 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': scaling,
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'cube_contactnets_loss_backward_B{args.batch}_per_gpu', 'batch_per_gpu': args.batch,
+        'config': {'workload': workload, 'batch': args.batch,
                    'dt': DT, 'eps': 1e-3, 'cpu_sample_per_step': B,
                    'note': 'same workload as the GPU arm; each CPU step is a bounded sample of it'},
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': threads, 'kind': 'port', 'sample': sample},
@@ -270,95 +379,172 @@ def main():
     dtype = torch.float64 if args.dtype == 'f64' else torch.float32
     from dair_pll_b200 import ops, parallel
     ops.set_loss_variant(args.variant)
-
+    scaling = args.scaling or ('strong' if world > 1 else 'weak')
     system = make_system(device, dtype)
-    B = args.batch
-    x, xp = make_batch(system, B, seed=rank, device=device, dtype=dtype)
-    u = torch.zeros(B, 0, device=device, dtype=dtype)
+
+    # ---- the batch ------------------------------------------------------------------------------------------
+    # strong scaling (BASELINE.json config 5): ONE global batch of args.batch pairs, the same for every N, each
+    # rank evaluating its share; weak scaling: args.batch pairs per rank (rank r draws seed r).
+    if scaling == 'strong':
+        Bg = args.batch
+        xg, xpg = make_batch(system, Bg, seed=0, device=device, dtype=dtype)
+    else:
+        Bg = args.batch * world
+        xg, xpg = make_batch(system, args.batch, seed=rank, device=device, dtype=dtype)
+    # cost hints = the Newton counts of a previous pass over the same pairs (what a training loop has from its
+    # last epoch; dataset_management.DeviceTrajectorySliceDataset.update_costs), computed OUTSIDE the timed region
+    system.record_newton_iters = True
+    with torch.no_grad():
+        hint = system.contactnets_loss(xg, None, xpg).newton_iters.reshape(-1)
+    system.record_newton_iters = False
+
+    def shard(order):
+        if scaling == 'strong':
+            if order == 'cost':      # dealt round-robin from the cost-ordered global batch: equally expensive shards
+                idx = torch.argsort(hint, descending=True, stable=True)[rank::world]
+            else:
+                lo, hi = parallel.shard_bounds(Bg, world, rank)
+                idx = torch.arange(lo, hi, device=device)
+        else:
+            idx = torch.argsort(hint, descending=True, stable=True) if order == 'cost' else None
+        if idx is None:
+            return xg, xpg
+        return xg.index_select(0, idx).contiguous(), xpg.index_select(0, idx).contiguous()
+
+    comm = None
+    if world > 1 and args.allreduce == 'peer':
+        comm = parallel.PeerComm(device)
     params = [p for p in system.parameters()]
-    reducer = parallel.GradientAllReduce(params, device, world)
-
-    def step_local():
-        reducer.zero()
-        loss = system.contactnets_loss(x, u, xp)
-        mean = loss.mean()
-        mean.backward()
-        return reducer.stage(mean)    # flat device buffer [grads..., loss] of this rank
-
-    def step_resident():
-        step_local()
-        return reducer.reduce()       # ONE all-reduce(sum)/world over NCCL
+    reducer = parallel.GradientAllReduce(params, device, world) if (world > 1 and comm is None) else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, min_ms=0.0):
+        """Mean ms per call of fn over repetitions of `steps` calls lasting at least min_ms in total (device
+        time, CUDA events, max over ranks).  Returns (ms per step, number of timed steps)."""
         for _ in range(warmup):
             fn()
         barrier()
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        for _ in range(steps):
-            fn()
-        stop.record()
-        barrier()
-        ms = torch.tensor([start.elapsed_time(stop)], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item() / steps
+        reps, total_ms, total_steps = 1, 0.0, 0
+        while True:
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            for _ in range(reps * steps):
+                fn()
+            stop.record()
+            barrier()
+            ms = torch.tensor([start.elapsed_time(stop)], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            total_ms += ms.item()
+            total_steps += reps * steps
+            if total_ms >= min_ms:
+                return total_ms / total_steps, total_steps
+            # the same repetition count on every rank: derived from the all-reduced time
+            reps = max(1, min(100000, int((min_ms - total_ms) / max(ms.item() / (reps * steps), 1e-3) / steps) + 1))
 
-    # ---- device-resident throughput (value) ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms_eager = timed(step_resident, args.steps, max(args.warmup, 3))
-    if args.no_graph:
-        ms_step = ms_eager
-    else:
-        # the same step, captured once into a CUDA graph and replayed (parallel.GraphedStep)
+    def make_step(order):
+        """The public-API step on this rank's shard: loss.mean().backward() -> (global) mean loss + param.grad."""
+        x, xp = shard(order)
+        u = torch.zeros(x.shape[0], 0, device=device, dtype=dtype)
+        system.dynamic_schedule = order == 'cost'
+        system.data_parallel = comm
+
+        def step_local():
+            if reducer is not None:
+                reducer.zero()
+            else:
+                for p in params:
+                    p.grad = None
+            mean = system.contactnets_loss(x, u, xp).mean()
+            mean.backward()
+            return reducer.stage(mean) if reducer is not None else mean
+
+        def step_eager():
+            out = step_local()
+            return reducer.reduce() if reducer is not None else out
+        if args.no_graph:
+            return step_eager, step_eager, x, xp
+        # with the in-kernel exchange the WHOLE step is one CUDA graph; with NCCL the all-reduce follows the replay
         graphed = parallel.GraphedStep(step_local, device)
 
         def step_graphed():
-            graphed()
-            return reducer.reduce()
-        ms_step = timed(step_graphed, args.steps, max(args.warmup, 3))
-    # the timed region lasts ~10 ms, shorter than one nvidia-smi query: keep the same step running (untimed) for
-    # about half a second so that the clock / throttle samples are taken under this load
-    load_fn = step_resident if args.no_graph else step_graphed
-    for _ in range(max(1, min(5000, int(500.0 / ms_step)))):      # same count on every rank (ms_step is the max over ranks)
-        load_fn()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    value = world * B / (ms_step * 1e-3)
+            out = graphed()
+            return reducer.reduce() if reducer is not None else out
+        return step_graphed, step_eager, x, xp
 
-    # ---- end to end through the public API with HOST buffers ----
+    # ---- device-resident throughput (value): both batch orders, the configured one is the headline ----------
+    orders = {}
+    sampler = ClockSampler(local_rank)
+    for order in (['natural', 'cost'] if args.order == 'cost' else ['cost', 'natural']):   # headline order last
+        step, step_eager, x, xp = make_step(order)
+        ms_eager, _ = timed(step_eager, args.steps, max(args.warmup, 3))
+        headline = order == args.order
+        if headline and rank == 0:
+            sampler.start()
+        ms_step, n_timed = timed(step, args.steps, max(args.warmup, 3), min_ms=1000.0 if headline else 200.0)
+        if headline:
+            clocks = sampler.stop() if rank == 0 else None
+        orders[order] = {'ms_per_step': ms_step, 'value': Bg / (ms_step * 1e-3), 'eager_ms_per_step': ms_eager,
+                         'timed_steps': n_timed}
+    if comm is not None:
+        comm.check()
+    ms_step, value = orders[args.order]['ms_per_step'], orders[args.order]['value']
+    B = x.shape[0]                       # this rank's samples per step (headline order: built last)
+
+    # ---- end to end through the public API with HOST buffers ------------------------------------------------
     xh, xph = x.cpu().pin_memory(), xp.cpu().pin_memory()
+    system.data_parallel = None          # chunks are summed locally; ONE exchange per step follows
     loader = parallel.HostBatchPipeline(system, device, dtype, B)
-    out_host = torch.empty(reducer.numel, dtype=torch.float64).pin_memory()
+    n_flat = sum(p.numel() for p in params) + 1
+    out_host = torch.empty(n_flat, dtype=torch.float64).pin_memory()
 
     def step_e2e():
-        reducer.zero()
-        mean = loader.loss_mean_from_host(xh, xph)
+        for p in params:
+            p.grad = None
+        total = loader.loss_sum_from_host(xh, xph)
+        mean = total / Bg
         mean.backward()
-        flat = reducer(mean)
+        flat = torch.cat([p.grad.reshape(-1) for p in params] + [mean.detach().reshape(1)])
+        if comm is not None:
+            flat = comm.all_reduce_sum(flat)
+        elif world > 1:
+            dist.all_reduce(flat)
         out_host.copy_(flat, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the user reads the loss / gradients on the host
-    ms_e2e = timed(step_e2e, max(3, args.steps // 2), 3)
-    e2e_value = world * B / (ms_e2e * 1e-3)
+    ms_e2e, _ = timed(step_e2e, max(3, args.steps // 2), 3, min_ms=300.0)
+    e2e_value = Bg / (ms_e2e * 1e-3)
     h2d = 2 * B * 13 * x.element_size()
     d2h = out_host.numel() * 8
 
-    # ---- kernel-only timing for the roofline (CUDA events around the raw launch) ----
-    inertia, mu, half = system._cube_params(dtype)
-    inertia, mu, half = inertia.detach(), mu.detach(), half.detach()
-    _, _, _, _, iters = ops.cube_loss_raw(x, xp, inertia, mu, half, DT, 1e-3, want_iters=True)
+    # ---- the reference's own call pattern: x = x_past[..., -1, :], x_plus = x_future[..., 0, :] views --------
+    strided = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        past = torch.stack((x, x), 1)                # (B, 2, 13): t_history = 2, the loss reads the last
+        fut = torch.stack((xp, xp), 1)
+        xv, xpv = past[..., -1, :], fut[..., 0, :]
+
+        def step_views():
+            for p in params:
+                p.grad = None
+            system.contactnets_loss(xv, None, xpv).mean().backward()
+        ms_views, _ = timed(step_views, args.steps, 3)
+        strided = {'ms_per_step_eager': ms_views, 'contiguous_eager_ms_per_step': orders[args.order]['eager_ms_per_step'],
+                   'note': 'row strides go through the ABI (dpll_cube_loss_leaf_dp_*): no .contiguous() copy'}
+
+    # ---- kernel-only timing for the roofline (CUDA events around the raw launch) ----------------------------
+    lt, ct = system.multibody_terms.lagrangian_terms, system.multibody_terms.contact_terms
+    leaves = [t.detach().to(dtype) for t in (lt.inertial_parameters, ct.friction_params, ct.geometries[0].length_params)]
+    flags = ops.LOSS_DYNAMIC if args.order == 'cost' else 0
+    iters = ops.cube_loss_leaf_dp_raw(x, xp, *leaves, DT, 1e-3, flags=flags, want_iters=True)[4]
     mean_iters = iters.double().mean().item()
 
     def kernel_only():
-        ops.cube_loss_raw(x, xp, inertia, mu, half, DT, 1e-3)
-    ms_kernel = timed(kernel_only, args.steps, 3)
+        ops.cube_loss_leaf_dp_raw(x, xp, *leaves, DT, 1e-3, flags=flags)
+    ms_kernel, _ = timed(kernel_only, args.steps, 3, min_ms=200.0)
     flops_per_sample = F0_CUBE + FIT_CUBE * mean_iters
     achieved_tflops = B * flops_per_sample / (ms_kernel * 1e-3) / 1e12
     sms = torch.cuda.get_device_properties(device).multi_processor_count
@@ -373,8 +559,8 @@ def main():
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
-        key = f"cube_loss_wf_kernel_{args.dtype}_B{B}"
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')))
+        key = f"cube_loss_wf_kernel_{args.dtype}_B{B}_{args.order}"
         if args.variant == 0 and key in tr:
             traffic = tr[key]['dram_bytes_read'] + tr[key]['dram_bytes_write']     # one ncu --set full capture, per launch
     except (OSError, ValueError, KeyError):
@@ -382,6 +568,7 @@ def main():
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -396,23 +583,39 @@ def main():
 
     secondary = None
     if world == 1 and not args.no_secondary:
-        secondary = secondary_configs(device)
+        system.dynamic_schedule, system.data_parallel = False, None
+        secondary = secondary_configs(device, peak_flops)
+        secondary['reference_call_pattern_strided_views'] = strided
 
+    exchange = ('in-kernel peer-memory all-reduce (dpll_comm, NVLink P2P stores + flags) inside the reduction kernel'
+                if comm is not None else ('NCCL all-reduce after the graph replay' if world > 1 else 'none (1 GPU)'))
+    workload = (f'cube_contactnets_loss_backward_B{Bg}_global' if scaling == 'strong'
+                else f'cube_contactnets_loss_backward_B{args.batch}_per_gpu')
     line = {
         'metric': METRIC + (' fp64' if dtype == torch.float64 else ' fp32'),
         'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'cube_contactnets_loss_backward_B{B}_per_gpu', 'batch_per_gpu': B,
-                   'global_batch': world * B, 'dt': DT, 'eps': 1e-3, 'parallelism': f'dp{world}',
-                   'l2_policy': f'inputs larger than L2 ({2 * B * 13 * x.element_size() / 1e6:.0f} MB per step vs 126 MB)',
+        'config': {'workload': workload, 'batch_per_gpu': B, 'global_batch': Bg, 'dt': DT, 'eps': 1e-3,
+                   'parallelism': f'dp{world}',
+                   'l2_policy': (f'inputs larger than L2 ({2 * B * 13 * x.element_size() / 1e6:.0f} MB per step vs 126 MB)'
+                                 if 2 * B * 13 * x.element_size() > 126e6 else
+                                 f'inputs of {2 * B * 13 * x.element_size() / 1e6:.0f} MB per step fit the 126 MB L2 at this shard '
+                                 'size: the kernel is FP64-bound (HBM fraction below), so residency does not change the time'),
                    'mean_newton_iters': mean_iters, 'storage': args.dtype,
-                   'step': 'eager launches' if args.no_graph else 'CUDA graph replay of the public-API step (rank-local part) + NCCL all-reduce',
-                   'eager_ms_per_step': ms_eager},
+                   'order': (args.order + ': batch handed to the kernel by decreasing Newton count of the previous pass '
+                             '(cost hints as a training loop has them from its last epoch, computed outside the timed '
+                             'region), warps draw chunks in batch order' if args.order == 'cost' else
+                             'natural: generator order, static sample ranges per warp'),
+                   'by_order': orders,
+                   'timed_steps': orders[args.order]['timed_steps'],
+                   'exchange': exchange,
+                   'step': 'eager launches' if args.no_graph else 'CUDA graph replay of the public-API step',
+                   'eager_ms_per_step': orders[args.order]['eager_ms_per_step']},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h},
-        'gpu_launches': 3 * args.steps,   # per step: parameter preparation + loss/backward + reduce/chain rule
-                                          # (loss.mean() and its backward reuse that launch, ops.BatchLoss)
+        'gpu_launches': 3 * orders[args.order]['timed_steps'],   # per step: parameter preparation + loss/backward +
+                                                                  # reduce/chain rule(/exchange)
         'roofline': {'bound': 'fp64_cuda_core',
                      'achieved': achieved_tflops, 'peak': peak_flops / 1e12, 'unit': 'TFLOP/s',
                      'frac': achieved_tflops / (peak_flops / 1e12), 'traffic': traffic,
@@ -428,6 +631,7 @@ def main():
     }
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -9,6 +9,7 @@ import os
 from dair_pll_b200 import build as _build
 
 _LIB = None
+ABI_VERSION = 200        # DPLL_VERSION of include/dair_pll_b200.h this binding was written against
 
 _c_void_p = ctypes.c_void_p
 _i64, _i32, _f64, _f32, _sz = ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_float, ctypes.c_size_t
@@ -39,6 +40,17 @@ EXPORTS = {
     'dpll_icnn_output_f64': ([_c_void_p] * 5 + [_i64, _i32, _f64, _c_void_p, _c_void_p], ctypes.c_int),
     'dpll_icnn_backward_blocks': ([_i64], ctypes.c_int),
     'dpll_icnn_backward_f64': ([_c_void_p] * 5 + [_i64, _i32, _f64, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    'dpll_cube_loss_leaf_dp_f64': ([_c_void_p, _i64, _c_void_p, _i64] + [_c_void_p] * 3 + [_f64, _f64, _i64, _i32] +
+                                   [_c_void_p] * 6 + [_c_void_p, _sz, _c_void_p], ctypes.c_int),
+    'dpll_cube_loss_leaf_dp_f32': ([_c_void_p, _i64, _c_void_p, _i64] + [_c_void_p] * 3 + [_f32, _f32, _i64, _i32] +
+                                   [_c_void_p] * 6 + [_c_void_p, _sz, _c_void_p], ctypes.c_int),
+    'dpll_comm_handle_bytes': ([], _sz),
+    'dpll_comm_create': ([_i32, _i32, ctypes.POINTER(_c_void_p), _c_void_p], ctypes.c_int),
+    'dpll_comm_connect': ([_c_void_p, _c_void_p], ctypes.c_int),
+    'dpll_comm_destroy': ([_c_void_p], ctypes.c_int),
+    'dpll_comm_device_state': ([_c_void_p], _c_void_p),
+    'dpll_comm_error': ([_c_void_p], ctypes.c_int),
+    'dpll_comm_allreduce_f64': ([_c_void_p, _c_void_p, _i32, _f64, _c_void_p], ctypes.c_int),
     'dpll_fma_peak_f64': ([_c_void_p, _i32, _i64, _c_void_p], ctypes.c_int),
     'dpll_fma_peak_f32': ([_c_void_p, _i32, _i64, _c_void_p], ctypes.c_int),
 }
@@ -58,11 +70,17 @@ def load() -> ctypes.CDLL:
             raise RuntimeError(
                 f'{path} not found: build it with `python -m dair_pll_b200.build` '
                 '(nvcc, sm_100a). dair_pll_b200 has no CPU or PyTorch fallback.')
+        if path == _build.LIB_PATH and _build.sources_present() and _build.is_stale():
+            # argtypes are positional: a library older than its sources could take shifted pointers
+            raise RuntimeError(f'{path} is older than csrc/ or include/: rebuild it with `python -m dair_pll_b200.build`')
         lib = ctypes.CDLL(path)
         for name, (argtypes, restype) in EXPORTS.items():
             fn = getattr(lib, name)      # AttributeError if the symbol is missing
             fn.argtypes = argtypes
             fn.restype = restype
+        version = lib.dpll_version()
+        if version != ABI_VERSION:
+            raise RuntimeError(f'{path} reports ABI version {version}, this binding expects {ABI_VERSION}: rebuild it')
         _LIB = lib
     return _LIB
 
@@ -72,4 +90,6 @@ def check(rc: int, what: str) -> None:
         return
     if rc > 0:
         raise RuntimeError(f'{what}: CUDA error {rc}')
+    if rc == -3:
+        raise RuntimeError(f'{what}: a peer rank did not arrive at the gradient exchange (timeout)')
     raise RuntimeError(f'{what}: argument error {rc} (see include/dair_pll_b200.h)')

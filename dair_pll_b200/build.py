@@ -6,8 +6,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libdair_pll_b200.so')
-SOURCES = ['cn_kernels.cu', 'cn_tangent.cu', 'cn_tangent_elbow.cu', 'cn_icnn.cu']
-HEADERS = ['cn_common.cuh', 'cn_cube.cuh', 'cn_params.cuh', 'cn_elbow.cuh', 'cn_dual.cuh', 'cn_cube_tangent.cuh', 'cn_elbow_tangent.cuh', os.path.join('..', '..', 'include', 'dair_pll_b200.h')]
+SOURCES = ['cn_kernels.cu', 'cn_tangent.cu', 'cn_tangent_elbow.cu', 'cn_icnn.cu', 'cn_comm.cu']
+HEADERS = ['cn_common.cuh', 'cn_cube.cuh', 'cn_params.cuh', 'cn_elbow.cuh', 'cn_dual.cuh', 'cn_cube_tangent.cuh', 'cn_elbow_tangent.cuh', 'cn_comm.cuh', os.path.join('..', '..', 'include', 'dair_pll_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']
 
@@ -19,12 +19,29 @@ def _nvcc() -> str:
     return 'nvcc'
 
 
+HASH_PATH = LIB_PATH + '.hash'
+
+
+def sources_present() -> bool:
+    return all(os.path.exists(os.path.join(CSRC, f)) for f in SOURCES)
+
+
+def source_hash() -> str:
+    """Content hash of everything the library is compiled from (robust to copies that reset mtimes)."""
+    import hashlib
+    h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+    for f in sorted(SOURCES + HEADERS):
+        with open(os.path.join(CSRC, f), 'rb') as fh:
+            h.update(f.encode() + b'\0' + fh.read())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    """True if the library is missing or was built from other sources than the ones present."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    built = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > built for d in deps)
+    with open(HASH_PATH) as fh:
+        return fh.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -51,6 +68,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     proc = subprocess.run(link, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError('link failed:\n' + ' '.join(link) + '\n' + proc.stdout + proc.stderr)
+    with open(HASH_PATH, 'w') as fh:
+        fh.write(source_hash() + '\n')
     return LIB_PATH
 
 

@@ -316,7 +316,14 @@ CN_HD int cube_newton_visit(const CubeParams<T>& P, const CubeProb<T>& S, const 
   T g[6], H[36], res2, scale2;
   CN_STAT_UNIT();
   cube_eval<T, true, UNR>(P, S, u, g, H, res2, scale2);
-  if (cube_converged(cfg, res2, scale2)) return NEWTON_DONE;
+  if (cube_converged(cfg, res2, scale2)) {
+    if (cfg.polish && res2 == res2) {
+      block_solve6_neg<T>(H, g, d);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) u[i] += d[i];
+    }
+    return NEWTON_DONE;
+  }
   if (res2 <= cfg.tol_stall * cfg.tol_stall * scale2 && !(res2 < T(0.25) * best_res2)) {
     it += 1 << 16;
     if ((it >> 16) >= 3) return NEWTON_DONE;

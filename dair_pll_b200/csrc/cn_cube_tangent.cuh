@@ -30,7 +30,8 @@ CN_HD B cube_rollout_tangent(const B* inertia, const B* mu, const B* half, B dt,
   const SolverCfg<B> c0 = default_cfg<B>();
   SolverCfg<D> cfg;
   cfg.tol_rel = D(c0.tol_rel); cfg.tol_stall = D(c0.tol_stall); cfg.ls_c = D(c0.ls_c); cfg.max_iter = c0.max_iter;
-  cfg.tol_final = D(c0.tol_final);
+  cfg.tol_final = D(0);      // no early finish: every solve ends with the polishing step at the converged point,
+  cfg.polish = true;         // whose tangent is the exact implicit derivative of the QP solution
   D x[13], xn[13];
   for (int i = 0; i < 13; ++i) { x[i] = D(x0[i]); if (dir == 14 + i) x[i].d[0] = B(1); }
   B g = B(0);

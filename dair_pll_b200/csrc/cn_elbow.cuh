@@ -320,7 +320,16 @@ CN_HD int elbow_solve(const ElbowParams<T>& P, const ElbowProb<T>& S, const Solv
   while (true) {
     T g[7], H[49], res2, scale2;
     elbow_eval<T, true>(P, S, u, g, H, res2, scale2);
-    if (cube_converged(cfg, res2, scale2)) break;
+    if (cube_converged(cfg, res2, scale2)) {
+      if (cfg.polish && res2 == res2) {             // dual arithmetic: the step at u* carries the implicit derivative
+        T inv_diag[7], ng[7];
+        chol_factor<T, 7>(H, inv_diag);
+        for (int i = 0; i < 7; ++i) ng[i] = -g[i];
+        chol_solve<T, 7>(H, inv_diag, ng, d);
+        for (int i = 0; i < 7; ++i) u[i] += d[i];
+      }
+      break;
+    }
     if (res2 <= cfg.tol_stall * cfg.tol_stall * scale2 && !(res2 < T(0.25) * best)) {
       it += 1 << 16;
       if ((it >> 16) >= 3) break;

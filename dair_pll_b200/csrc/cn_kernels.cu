@@ -11,6 +11,7 @@
 #include "cn_cube.cuh"
 #include "cn_params.cuh"
 #include "cn_elbow.cuh"
+#include "cn_comm.cuh"
 
 namespace {
 
@@ -59,7 +60,8 @@ cube_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* 
                  const IO* __restrict__ inertia,
                  const IO* __restrict__ mu, const IO* __restrict__ half, T dt, T eps, int64_t B,
                  IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
-                 T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag) {
+                 T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag, int64_t ldx,
+                 int64_t ldxp) {
   if (skip_flag && *skip_flag) return;
   cn::CubeParams<T> P;
   load_cube_params<T, IO>(P, inertia, mu, half, dt, eps);
@@ -71,7 +73,7 @@ cube_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* 
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
     T xs[13], xps[13];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * 13 + i]); xps[i] = T(xp[b * 13 + i]); }
+    for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * ldx + i]); xps[i] = T(xp[b * ldxp + i]); }
     int it;
     T gs[DPLL_CUBE_NPARAM], fo[12];
 #pragma unroll
@@ -156,7 +158,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
                     const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half, T dt,
                     T eps, int64_t B, IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
                     T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag,
-                    unsigned long long* __restrict__ dyn_counter) {
+                    unsigned long long* __restrict__ dyn_counter, int64_t ldx, int64_t ldxp) {
   // dyn_counter != nullptr (variant 2): warps take their triage chunks of 32 samples from a global counter instead
   // of a static range -- removes the load imbalance between warps, but the assignment of samples to warps (and
   // with it the rounding of the gradient sums) then depends on timing.
@@ -216,7 +218,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
       if (lane < cnt) {
         T xs[13], xps[13];
 #pragma unroll
-        for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * 13 + i]); xps[i] = T(xp[b * 13 + i]); }
+        for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * ldx + i]); xps[i] = T(xp[b * ldxp + i]); }
         T gs[DPLL_CUBE_NPARAM];
 #pragma unroll
         for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
@@ -242,8 +244,8 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
       next = dyn_counter ? (cnt < 32 ? B : lo) : next + cnt;
 #ifndef CN_NO_PREFETCH
       if (!dyn_counter && next + lane < hi) {       // the rows of the next triage visit: pull them into L2
-        const char* px = reinterpret_cast<const char*>(x + (next + lane) * 13);
-        const char* pp = reinterpret_cast<const char*>(xp + (next + lane) * 13);
+        const char* px = reinterpret_cast<const char*>(x + (next + lane) * ldx);
+        const char* pp = reinterpret_cast<const char*>(xp + (next + lane) * ldxp);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(px));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(px + 13 * sizeof(IO) - 1));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
@@ -303,7 +305,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
           const int64_t b = lo + (pass == 0 ? old : pool->q_in[(h_in + lane) % kWfSlots]);
           T xs[13], xps[13];
 #pragma unroll
-          for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * 13 + i]); xps[i] = T(xp[b * 13 + i]); }
+          for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * ldx + i]); xps[i] = T(xp[b * ldxp + i]); }
           const cn::CubeProb<T> S{&pool->field[0][slot], kWfSlots};
           cn::CubeLossAux<T> A;
           cn::cube_loss_prologue<T, kWfUnrPE>(P, xs, xps, S, A);      // (re)builds IW, mcW, rho, q in the slot
@@ -407,13 +409,20 @@ __global__ void cube_prep_kernel(const IO* __restrict__ theta, const IO* __restr
 
 // Sums the per-block partials (fixed order) and pushes the callable-level gradient through the
 // parameter preparation: grad_leaf = [d/d theta (10) | d/d friction (2) | d/d length (3)].
+// Data-parallel step (comm != nullptr): the same block then performs the step's only exchange itself --
+// [grad_leaf 15 | loss sum | sample count] is pushed into every peer's buffer over NVLink and the world's rows
+// are summed in rank order (cn_comm.cuh), so no host-launched collective follows the kernel.  `sums` (17) /
+// `means` (16) receive the (global) sums and the sums divided by the sample count; `local_out` (16, nullable)
+// keeps this rank's own [grad_leaf | loss sum].
 template <typename T, typename IO>
 __global__ void reduce_partials_leaf_kernel(const T* __restrict__ partials, int nblocks, const IO* __restrict__ theta,
                                             const IO* __restrict__ friction, const IO* __restrict__ length,
                                             IO* __restrict__ grad_leaf, IO* __restrict__ loss_sum,
-                                            const int32_t* __restrict__ skip_flag) {
+                                            const int32_t* __restrict__ skip_flag, cn::CommDev* comm, double count,
+                                            IO* __restrict__ sums, IO* __restrict__ means, IO* __restrict__ local_out) {
   if (skip_flag && *skip_flag) return;
   __shared__ T g[kNAcc];
+  __shared__ double o[cn::COMM_MAX_ELEMS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (w < kNAcc) {
     T s = T(0);
@@ -423,25 +432,34 @@ __global__ void reduce_partials_leaf_kernel(const T* __restrict__ partials, int 
   }
   __syncthreads();
   const int t = threadIdx.x;
-  if (t < 10 && grad_leaf) {
+  if (t < 10) {
     cn::Dual<T> th[10], out[10];
     for (int i = 0; i < 10; ++i) th[i] = cn::Dual<T>(T(theta[i]), i == t ? T(1) : T(0));
     cn::theta_to_inertia_vector<cn::Dual<T>>(th, out);
     T s = T(0);
     for (int i = 0; i < 10; ++i) s += g[i] * out[i].d;
-    grad_leaf[t] = IO(s);
-  } else if (t == 10 && grad_leaf) {
+    o[t] = (double)s;
+  } else if (t == 10) {
     const T fa = T(friction[0]), fb = T(friction[1]);
     const T a = cn::t_abs(fa), b = cn::t_abs(fb), den = (a + b) * (a + b);
     const T sa = fa > T(0) ? T(1) : (fa < T(0) ? T(-1) : T(0)), sb = fb > T(0) ? T(1) : (fb < T(0) ? T(-1) : T(0));
-    grad_leaf[10] = IO(g[10] * (T(2) * b * b / den) * sa);
-    grad_leaf[11] = IO(g[10] * (T(2) * a * a / den) * sb);
-  } else if (t >= 11 && t < 14 && grad_leaf) {
+    o[10] = (double)(g[10] * (T(2) * b * b / den) * sa);
+    o[11] = (double)(g[10] * (T(2) * a * a / den) * sb);
+  } else if (t >= 11 && t < 14) {
     const T l = T(length[t - 11]);
-    grad_leaf[12 + (t - 11)] = IO(g[t] * (l > T(0) ? T(1) : (l < T(0) ? T(-1) : T(0))));
-  } else if (t == 14 && loss_sum) {
-    *loss_sum = IO(g[14]);
+    o[12 + (t - 11)] = (double)(g[t] * (l > T(0) ? T(1) : (l < T(0) ? T(-1) : T(0))));
+  } else if (t == 14) {
+    o[15] = (double)g[14];
+  } else if (t == 15) {
+    o[16] = count;
   }
+  __syncthreads();
+  if (local_out && t < 16) local_out[t] = IO(o[t]);
+  if (comm) cn::comm_allreduce_block(comm, o, 17);
+  if (t < 15 && grad_leaf) grad_leaf[t] = IO(o[t]);
+  else if (t == 15 && loss_sum) *loss_sum = IO(o[15]);
+  if (sums && t < 17) sums[t] = IO(o[t]);                    // [grad_leaf 15 | loss sum | sample count]
+  if (means && t < 16) means[t] = IO(o[t] / o[16]);          // the same per sample: loss.mean() and its gradient
 }
 
 template <typename T, typename IO>
@@ -763,11 +781,16 @@ template <typename T, typename IO>
 int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, const IO* inertia, const IO* mu,
                      const IO* half, const IO* theta, const IO* friction, const IO* length, T dt, T eps, int64_t B,
                      IO* loss, IO* force, int32_t* iters, IO* grad, IO* loss_sum,
-                     const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
+                     const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream, int flags = 0,
+                     cn::CommDev* comm = nullptr, IO* sums = nullptr, IO* means = nullptr, IO* local_out = nullptr,
+                     int64_t ldx = 13, int64_t ldxp = 13) {
   const bool leaf = theta != nullptr;
+  if (ldx < 13 || ldxp < 13) return DPLL_EINVAL;
+  if (flags & DPLL_LOSS_DYNAMIC) variant = 2;
+  if (comm && (!leaf || skip_flag)) return DPLL_EINVAL;   // the exchange lives in the leaf reduction and is unconditional
   if (B < 0 || (leaf ? (!friction || !length) : (!inertia || !mu || !half))) return DPLL_EINVAL;
   if (B > 0 && (!x || !xp)) return DPLL_EINVAL;
-  const bool want_red = grad || loss_sum;
+  const bool want_red = grad || loss_sum || comm || sums || means;
   if ((want_red || leaf) && (!workspace || workspace_bytes < dpll_workspace_bytes())) return DPLL_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DeviceInfo di = device_info();
@@ -809,11 +832,12 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
     // which is smaller in the instruction cache (the unrolled one is +5% at 1M pairs, +15% at 4M).
     if (B <= cap * kWfWarps * 320)
       cube_loss_wf_kernel<T, IO, 4><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss,
-                                                                    force, iters, partials, grad ? 1 : 0, skip_flag, dyn);
+                                                                    force, iters, partials, (grad || sums || means) ? 1 : 0, skip_flag, dyn, ldx, ldxp);
     else
       cube_loss_wf_kernel<T, IO, kWfUnr><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B,
-                                                                         loss, force, iters, partials, grad ? 1 : 0,
-                                                                         skip_flag, dyn);
+                                                                         loss, force, iters, partials,
+                                                                         (grad || sums || means) ? 1 : 0, skip_flag, dyn, ldx,
+                                                                         ldxp);
   } else {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_kernel<T, IO>, kLossThreads, 0);
@@ -824,13 +848,14 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
     blocks = (int)(need < cap ? need : cap);
     if (blocks < 1) blocks = 1;
     cube_loss_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss, force,
-                                                         iters, partials, grad ? 1 : 0, skip_flag);
+                                                         iters, partials, (grad || sums || means) ? 1 : 0, skip_flag, ldx, ldxp);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (want_red) {
     if (leaf) reduce_partials_leaf_kernel<T, IO><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, theta, friction, length, grad,
-                                                                     loss_sum, skip_flag);
+                                                                     loss_sum, skip_flag, comm, (double)B, sums, means,
+                                                                     local_out);
     else reduce_partials_kernel<T, IO, kNAcc, DPLL_CUBE_NPARAM><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, grad, loss_sum,
                                                                                         skip_flag);
     e = cudaGetLastError();
@@ -877,7 +902,7 @@ int dpll_set_loss_variant(int variant) {
   return DPLL_OK;
 }
 
-int dpll_version(void) { return 100; }
+int dpll_version(void) { return DPLL_VERSION; }
 
 size_t dpll_workspace_bytes(void) { return ((size_t)kMaxBlocks * 32 + 16) * sizeof(double); }
 
@@ -917,6 +942,30 @@ int dpll_cube_loss_leaf_f32(const float* x, const float* x_plus, const float* we
   return launch_cube_loss<double, float>(g_loss_variant, x, x_plus, weight, nullptr, nullptr, nullptr, theta, friction,
                                          length, (double)dt, (double)eps, B, loss, force, iters, grad_leaf, loss_sum,
                                          skip_flag, workspace, workspace_bytes, stream);
+}
+
+int dpll_cube_loss_leaf_dp_f64(const double* x, int64_t x_row_stride, const double* x_plus, int64_t xp_row_stride,
+                               const double* theta, const double* friction, const double* length, double dt, double eps,
+                               int64_t B, int32_t flags, void* comm, double* loss, int32_t* iters, double* sums,
+                               double* means, double* local, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!theta || (!sums && !means)) return DPLL_EINVAL;
+  return launch_cube_loss<double, double>(g_loss_variant, x, x_plus, nullptr, nullptr, nullptr, nullptr, theta, friction, length,
+                                          dt, eps, B, loss, nullptr, iters, nullptr, nullptr, nullptr, workspace,
+                                          workspace_bytes, stream, flags,
+                                          static_cast<cn::CommDev*>(dpll_comm_device_state(comm)), sums, means, local,
+                                          x_row_stride, xp_row_stride);
+}
+
+int dpll_cube_loss_leaf_dp_f32(const float* x, int64_t x_row_stride, const float* x_plus, int64_t xp_row_stride,
+                               const float* theta, const float* friction, const float* length, float dt, float eps,
+                               int64_t B, int32_t flags, void* comm, float* loss, int32_t* iters, float* sums,
+                               float* means, float* local, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!theta || (!sums && !means)) return DPLL_EINVAL;
+  return launch_cube_loss<double, float>(g_loss_variant, x, x_plus, nullptr, nullptr, nullptr, nullptr, theta, friction, length,
+                                         (double)dt, (double)eps, B, loss, nullptr, iters, nullptr, nullptr, nullptr,
+                                         workspace, workspace_bytes, stream, flags,
+                                         static_cast<cn::CommDev*>(dpll_comm_device_state(comm)), sums, means, local,
+                                         x_row_stride, xp_row_stride);
 }
 
 int dpll_cube_rollout_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,

@@ -43,6 +43,7 @@ class DeviceTrajectorySliceDataset:
         self._previous: List[Tensor] = []
         self._future: List[Tensor] = []
         self._dense: Optional[Tuple[Tensor, Tensor]] = None
+        self._cost: Optional[Tensor] = None      # (N,) int32 per-slice cost hint (last epoch's Newton counts)
 
     def add_slices_from_trajectory(self, trajectory: Tensor) -> None:
         """``trajectory``: (T, n_x).  Slice i predicts from time index ``t_skip + i``
@@ -60,6 +61,7 @@ class DeviceTrajectorySliceDataset:
         self._previous.append(prev.transpose(1, 2).contiguous())
         self._future.append(fut.transpose(1, 2).contiguous())
         self._dense = None
+        self._cost = None
 
     def add_trajectories_from_directory(self, trajectory_dir: str, indices: Optional[List[int]] = None) -> int:
         """Loads ``<index>.pt`` trajectories (all whole-number-named files when ``indices`` is None)."""
@@ -85,9 +87,39 @@ class DeviceTrajectorySliceDataset:
         prev, fut = self.tensors()
         return prev[idx], fut[idx]
 
+    # -- cost hints -------------------------------------------------------------------------------------
+    # The loss kernel's run time per sample is its Newton count (0 for free flight, up to ~45), and training
+    # revisits the same slices every epoch while the parameters move slowly: last epoch's counts predict this
+    # epoch's.  A batch handed to the kernel in order of decreasing cost (with ``system.dynamic_schedule``)
+    # starts its longest solves first and ends on the cheap samples, which removes the serial tail of the
+    # launch.  The hint only orders the batch; results do not depend on it.
+    def update_costs(self, indices: Optional[Tensor], newton_iters: Tensor) -> None:
+        """Records ``BatchLoss.newton_iters`` of the slices ``indices`` (None: all slices, in storage order)."""
+        n = len(self)
+        if self._cost is None:
+            self._cost = torch.zeros(n, dtype=torch.int32, device=self.device)
+        it = newton_iters.reshape(-1).to(device=self.device, dtype=torch.int32)
+        if indices is None:
+            assert it.numel() == n
+            self._cost.copy_(it)
+        else:
+            self._cost[indices.reshape(-1).to(self.device)] = it
+
+    def cost_order(self, indices: Optional[Tensor] = None, rank: int = 0, world: int = 1) -> Tensor:
+        """Slice indices (of ``indices``, default all) by decreasing cost hint (stable), dealt round-robin to the
+        ranks of a data-parallel step so that every shard is itself ordered and equally expensive."""
+        if indices is None:
+            indices = torch.arange(len(self), device=self.device)
+        if self._cost is not None:
+            indices = indices[torch.argsort(self._cost[indices], descending=True, stable=True)]
+        return indices[rank::world]
+
     def batches(self, batch_size: int, shuffle: bool = True, generator: Optional[torch.Generator] = None,
-                drop_last: bool = False) -> Iterator[Tuple[Tensor, Tensor]]:
-        """One epoch: a permutation drawn on the device and one gather per batch."""
+                drop_last: bool = False, cost_ordered: bool = False, return_indices: bool = False,
+                rank: int = 0, world: int = 1) -> Iterator[Tuple[Tensor, ...]]:
+        """One epoch: a permutation drawn on the device and one gather per batch.  ``cost_ordered``: every batch
+        is handed out by decreasing cost hint (see above); ``rank`` / ``world``: this rank's share of every batch;
+        ``return_indices``: also yield the slice indices (to feed ``update_costs``)."""
         prev, fut = self.tensors()
         n = prev.shape[0]
         order = torch.randperm(n, device=self.device, generator=generator) if shuffle else None
@@ -95,8 +127,13 @@ class DeviceTrajectorySliceDataset:
             hi = min(lo + batch_size, n)
             if drop_last and hi - lo < batch_size:
                 return
-            if order is None:
-                yield prev[lo:hi], fut[lo:hi]
+            if order is None and not cost_ordered and world == 1:
+                out = (prev[lo:hi], fut[lo:hi])
+                idx = None
             else:
-                idx = order[lo:hi]
-                yield prev.index_select(0, idx), fut.index_select(0, idx)
+                idx = order[lo:hi] if order is not None else torch.arange(lo, hi, device=self.device)
+                idx = self.cost_order(idx, rank, world) if cost_ordered else idx[rank::world]
+                out = (prev.index_select(0, idx), fut.index_select(0, idx))
+            if return_indices:
+                out = out + (idx if idx is not None else torch.arange(lo, hi, device=self.device),)
+            yield out

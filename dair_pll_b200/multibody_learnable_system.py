@@ -54,6 +54,11 @@ class MultibodyLearnableSystem(System):
         self.dt = dt
         self.set_carry_sampler(lambda: torch.Tensor([False]))
         self.max_batch_dim = 1
+        # Extensions of the reference API (all off by default -> the reference's semantics):
+        self.data_parallel = None        # parallel.PeerComm: loss.mean()/.sum() and gradients cover all ranks
+        self.dynamic_schedule = False    # warps draw sample chunks in batch order (cost-ordered batches)
+        self.record_newton_iters = False  # BatchLoss.newton_iters: per-sample cost hint for the data set
+        self._kin_cache = {}
 
     # -- helpers ---------------------------------------------------------
     def _kind(self) -> str:
@@ -66,23 +71,32 @@ class MultibodyLearnableSystem(System):
         inertia, mu, half = self.multibody_terms.kernel_parameters(dtype)
         return inertia.reshape(10), mu.reshape(1), half[0]
 
+    def _elbow_kin(self, dtype: torch.dtype, device: torch.device):
+        """URDF constants [joint origin | joint axis | box offsets] and the axis alone, created once per
+        (dtype, device): no host->device copy (= host synchronisation) inside a step, so the elbow step can be
+        captured into a CUDA graph like the cube's."""
+        key = (dtype, str(device))
+        if key not in self._kin_cache:
+            spec = self.multibody_terms.spec
+            joint = spec.joints[0]
+            kin = torch.tensor([*joint.origin, *joint.axis, *spec.geometries[0].offset, *spec.geometries[1].offset],
+                               dtype=dtype, device=device)
+            self._kin_cache[key] = (kin, kin[3:6].clone())
+        return self._kin_cache[key]
+
     def _elbow_params(self, dtype: torch.dtype, device: torch.device):
         inertia, mu, half = self.multibody_terms.kernel_parameters(dtype)
-        spec = self.multibody_terms.spec
-        joint = spec.joints[0]
-        kin = torch.tensor([*joint.origin, *joint.axis, *spec.geometries[0].offset, *spec.geometries[1].offset],
-                           dtype=dtype, device=device)
+        kin, _ = self._elbow_kin(dtype, device)
         return inertia.reshape(20), mu.reshape(2), (torch.cat(half) if half else None), kin
 
     def _elbow_witness_points(self, q: Tensor) -> Tensor:
         """(B, 8) configurations -> (B, 8, 3) witness points of the two learned geometries against the
         ground: support direction of geometry i = minus the third row of its world rotation
         (geometry.py:560-567), then ``DeepSupportConvex.get_vertices`` (:309-325)."""
-        spec = self.multibody_terms.spec
         w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
         s = 2.0 / (w * w + x * x + y * y + z * z)
         row = torch.stack((s * (x * z - w * y), s * (y * z + w * x), 1 - s * (x * x + y * y)), -1)   # R1[2, :]
-        axis = torch.tensor(spec.joints[0].axis, dtype=q.dtype, device=q.device)
+        _, axis = self._elbow_kin(q.dtype, q.device)
         th = q[:, 7:8]
         # third row of R2 = R1 Rot(axis, th):  r Rot = r cos + (r x a) sin + a (a.r)(1 - cos)
         row2 = row * torch.cos(th) + torch.linalg.cross(row, axis.expand_as(row)) * torch.sin(th) \
@@ -102,11 +116,17 @@ class MultibodyLearnableSystem(System):
             # 466-471, geometry.py:394-397, and its chain rule run on the device)
             leaves = (lt.inertial_parameters.to(x.dtype), ct.friction_params.to(x.dtype),
                       ct.geometries[0].length_params.to(x.dtype))
-            loss, loss_sum, grad = ops.CubeContactNetsLossLeaf.apply(self._flat(x), self._flat(x_plus), *leaves,
-                                                                     float(self.dt), LOSS_EPS)
+            flags = ops.LOSS_DYNAMIC if self.dynamic_schedule else 0
+            loss, sums, means, iters = ops.CubeContactNetsLossLeaf.apply(
+                self._flat(x), self._flat(x_plus), *leaves, float(self.dt), LOSS_EPS, flags, self.data_parallel,
+                self.record_newton_iters)
             # loss.mean() / loss.sum() (drake_experiment.py:222-223) then come from this launch's own reduction
-            return ops.batch_loss(loss.reshape(batch), loss_sum, grad, leaves)
+            return ops.batch_loss(loss.reshape(batch), sums, means, 15, leaves,
+                                  iters.reshape(batch) if self.record_newton_iters else None)
         elif self._kind() == 'elbow':
+            if self.data_parallel is not None:
+                raise NotImplementedError('the in-kernel gradient exchange is provided for the cube; use '
+                                          'parallel.GradientAllReduce (NCCL) for this system')
             inertia, mu, half, kin = self._elbow_params(x.dtype, x.device)
             xf, xpf = self._flat(x), self._flat(x_plus)
             if half is None:      # learned geometry: witness points from the support-function networks
@@ -124,7 +144,7 @@ class MultibodyLearnableSystem(System):
         batch = x_0.shape[:-1]
         if self._kind() == 'cube':
             inertia, mu, half = self._cube_params(x_0.dtype)
-            if torch.is_grad_enabled() and (x_0.requires_grad or inertia.requires_grad):
+            if torch.is_grad_enabled() and any(t.requires_grad for t in (x_0, inertia, mu, half)):
                 # differentiable path (prediction loss): backward through every step's QP
                 traj = ops.CubeRollout.apply(self._flat(x_0), inertia, mu, half, float(self.dt), steps, STEP_EPS)
             else:
@@ -135,6 +155,11 @@ class MultibodyLearnableSystem(System):
             if half is None:
                 # learned geometry: witness points depend on the state, so the time loop stays on the
                 # host and every step is [support networks -> one-step kernel]
+                if torch.is_grad_enabled() and (x_0.requires_grad or
+                                                any(p.requires_grad for p in self.multibody_terms.parameters())):
+                    raise NotImplementedError(
+                        'the rollout with learned (support-function) geometry has no backward: evaluate it under '
+                        'torch.no_grad(), or train the geometry with contactnets_loss')
                 with torch.no_grad():
                     xs = [self._flat(x_0)]
                     for _ in range(steps):
@@ -143,7 +168,7 @@ class MultibodyLearnableSystem(System):
                                                    STEP_EPS, pts=pts)
                         xs.append(one[:, 1])
                     traj = torch.stack(xs, 1)
-            elif torch.is_grad_enabled() and (x_0.requires_grad or inertia.requires_grad):
+            elif torch.is_grad_enabled() and any(t.requires_grad for t in (x_0, inertia, mu, half)):
                 traj = ops.ElbowRollout.apply(self._flat(x_0), inertia, mu, half, kin, float(self.dt), steps, STEP_EPS)
             else:
                 traj, _ = ops.elbow_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(), kin,

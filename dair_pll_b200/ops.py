@@ -128,6 +128,21 @@ class CubeContactNetsLoss(torch.autograd.Function):
         return (None, None, g[0:10].reshape(s_in), g[10:11].reshape(s_mu), g[11:14].reshape(s_h), None, None)
 
 
+LOSS_DYNAMIC = 1     # DPLL_LOSS_DYNAMIC (include/dair_pll_b200.h)
+
+
+def _rows(t: Tensor, n_x: int):
+    """(B, n_x) tensor -> (tensor, row stride in elements); rows must be contiguous, their spacing is free (so
+    the training loop's ``x_past[..., -1, :]`` views, drake_experiment.py:217-218, are read in place)."""
+    if t.dim() != 2 or t.shape[1] != n_x:
+        raise ValueError(f'expected (B,{n_x}) states, got {tuple(t.shape)}')
+    if t.shape[0] > 1 and (t.stride(1) != 1 or t.stride(0) < n_x):
+        t = t.contiguous()
+    elif t.shape[0] <= 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else n_x)
+
+
 def cube_loss_leaf_raw(x: Tensor, x_plus: Tensor, theta: Tensor, friction: Tensor, length: Tensor, dt: float,
                        eps: float, weight: Optional[Tensor] = None, want_grad: bool = True, want_loss: bool = True,
                        skip_flag: Optional[Tensor] = None, grad_out: Optional[Tensor] = None):
@@ -157,29 +172,65 @@ def cube_loss_leaf_raw(x: Tensor, x_plus: Tensor, theta: Tensor, friction: Tenso
     return loss, grad, loss_sum
 
 
+def cube_loss_leaf_dp_raw(x: Tensor, x_plus: Tensor, theta: Tensor, friction: Tensor, length: Tensor, dt: float,
+                          eps: float, flags: int = 0, comm=None, want_loss: bool = True, want_iters: bool = False):
+    """Direct call of ``dpll_cube_loss_leaf_dp_*`` (the training-loop / data-parallel form).  x, x_plus: (B,13)
+    with any row stride.  ``comm``: a :class:`dair_pll_b200.parallel.PeerComm` or None.  Returns
+    (loss (B,) | None, sums (17,) = [grad_leaf 15 | loss sum | count], means (16,), local (16,), iters | None);
+    with a communicator ``sums`` / ``means`` cover all ranks, ``local`` is this rank's share."""
+    dtype = _check_inputs(x, x_plus, theta, friction, length)
+    x, ldx = _rows(x, 13)
+    x_plus, ldxp = _rows(x_plus, 13)
+    if x_plus.shape != x.shape:
+        raise ValueError(f'x {tuple(x.shape)} and x_plus {tuple(x_plus.shape)} differ')
+    theta, friction, length = theta.contiguous(), friction.contiguous(), length.contiguous()
+    if theta.numel() != 10 or friction.numel() != 2 or length.numel() != 3:
+        raise ValueError('cube leaves must be theta (10), friction_params (2), length_params (3)')
+    B, dev = x.shape[0], x.device
+    loss = torch.empty(B, dtype=dtype, device=dev) if want_loss else None
+    iters = torch.empty(B, dtype=torch.int32, device=dev) if want_iters else None
+    out = torch.empty(49, dtype=dtype, device=dev)
+    sums, means, local = out[0:17], out[17:33], out[33:49]
+    ws = _workspace(dev)
+    fn = getattr(_lib.load(), 'dpll_cube_loss_leaf_dp_' + _SUFFIX[dtype])
+    with torch.cuda.device(dev):
+        rc = fn(_ptr(x), ldx, _ptr(x_plus), ldxp, _ptr(theta), _ptr(friction), _ptr(length), dt, eps, B, flags,
+                comm.handle if comm is not None else None, _ptr(loss), _ptr(iters), _ptr(sums), _ptr(means),
+                _ptr(local), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, 'dpll_cube_loss_leaf_dp')
+    return loss, sums, means, local, iters
+
+
 class CubeContactNetsLossLeaf(torch.autograd.Function):
     """ContactNets loss of the cube as a function of the module's learnable LEAVES: parameter
-    preparation and its chain rule run inside the CUDA library (``dpll_cube_loss_leaf_*``), so
+    preparation and its chain rule run inside the CUDA library (``dpll_cube_loss_leaf_dp_*``), so
     forward + backward is three kernel launches and no PyTorch glue.  Same backward protocol as
-    :class:`CubeContactNetsLoss` (fused gradient from the forward launch; device-side skip flag)."""
+    :class:`CubeContactNetsLoss` (fused gradient from the forward launch; device-side skip flag).
+
+    With a communicator (data-parallel step) the gradient this Function returns is the SUM over ranks of every
+    rank's vector-Jacobian product -- i.e. the gradient of the sum over ranks of each rank's scalar objective --
+    identical bits on every rank.  For ``mean()`` / ``sum()`` of the returned :class:`BatchLoss` the exchange
+    happens inside the forward launch's reduction kernel; a general upstream gradient is summed with the
+    stand-alone peer all-reduce."""
 
     @staticmethod
-    def forward(ctx, x, x_plus, theta, friction, length, dt, eps):
-        need = any(ctx.needs_input_grad[2:5])
-        loss, grad, loss_sum = cube_loss_leaf_raw(x, x_plus, theta, friction, length, dt, eps, want_grad=need)
-        ctx.dt, ctx.eps = dt, eps
+    def forward(ctx, x, x_plus, theta, friction, length, dt, eps, flags, comm, want_iters):
+        loss, sums, means, local, iters = cube_loss_leaf_dp_raw(x, x_plus, theta, friction, length, dt, eps,
+                                                               flags=flags, comm=comm, want_iters=want_iters)
+        ctx.dt, ctx.eps, ctx.comm = dt, eps, comm
         ctx.shapes = (theta.shape, friction.shape, length.shape)
-        if need:
-            ctx.save_for_backward(grad, x, x_plus, theta, friction, length)
-        else:
-            grad = torch.zeros(15, dtype=loss.dtype, device=loss.device)
-        # the launch's own sum of losses and summed parameter gradient, for BatchLoss.mean() / .sum()
-        ctx.mark_non_differentiable(loss_sum, grad)
-        return loss, loss_sum, grad
+        if any(ctx.needs_input_grad[2:5]):
+            ctx.save_for_backward(local, x, x_plus, theta, friction, length)
+        if iters is None:
+            iters = torch.empty(0, dtype=torch.int32, device=loss.device)
+        # the launch's own (global) sums and means, for BatchLoss.mean() / .sum()
+        ctx.mark_non_differentiable(sums, means, iters)
+        return loss, sums, means, iters
 
     @staticmethod
-    def backward(ctx, grad_loss, _g_sum, _g_grad):
-        grad, x, x_plus, theta, friction, length = ctx.saved_tensors
+    def backward(ctx, grad_loss, _g_sums, _g_means, _g_iters):
+        local, x, x_plus, theta, friction, length = ctx.saved_tensors
+        grad = local[:15]
         if grad_loss.numel() == 0:
             g = torch.zeros_like(grad)
         elif grad_loss.dim() == 1 and grad_loss.stride(0) == 0:
@@ -192,26 +243,30 @@ class CubeContactNetsLossLeaf(torch.autograd.Function):
             cube_loss_leaf_raw(x, x_plus, theta, friction, length, ctx.dt, ctx.eps, weight=grad_loss, want_grad=True,
                                want_loss=False, skip_flag=uniform.to(torch.int32), grad_out=gw)
             g = torch.where(uniform, grad * lo, gw)
+        if ctx.comm is not None:
+            g = ctx.comm.all_reduce_sum(g)
         s_t, s_f, s_l = ctx.shapes
-        return (None, None, g[0:10].reshape(s_t), g[10:12].reshape(s_f), g[12:15].reshape(s_l), None, None)
+        return (None, None, g[0:10].reshape(s_t), g[10:12].reshape(s_f), g[12:15].reshape(s_l), None, None, None, None,
+                None)
 
 
 class _FusedReduction(torch.autograd.Function):
-    """``mean()`` / ``sum()`` of a batch loss taken from the kernel launch that produced it: the value is the
-    launch's own sum of losses, the backward scales the launch's fused parameter gradient -- no reduction
-    over the (B,) loss, no (B,) upstream gradient, no second launch."""
+    """``mean()`` / ``sum()`` of a batch loss taken from the kernel launch that produced it: ``vec`` is the
+    launch's [parameter gradient (n) | loss] already summed (or averaged) over the batch -- and over the ranks of
+    a data-parallel step --, so the value is a copy of its last element and the backward one scale: no reduction
+    over the (B,) loss, no (B,) upstream gradient, no second launch, no collective."""
 
     @staticmethod
-    def forward(ctx, loss_sum, grad, scale, *leaves):
-        ctx.save_for_backward(grad)
-        ctx.scale = scale
+    def forward(ctx, vec, n, *leaves):
+        ctx.save_for_backward(vec)
+        ctx.n = n
         ctx.shapes = [l.shape for l in leaves]
-        return (loss_sum * scale).reshape(())
+        return vec[n].clone()
 
     @staticmethod
     def backward(ctx, g):
-        (grad,) = ctx.saved_tensors
-        gg = grad * (g * ctx.scale)
+        (vec,) = ctx.saved_tensors
+        gg = vec[:ctx.n] * g
         outs, off = [], 0
         for shape in ctx.shapes:
             n = 1
@@ -219,7 +274,7 @@ class _FusedReduction(torch.autograd.Function):
                 n *= s
             outs.append(gg[off:off + n].reshape(shape))
             off += n
-        return (None, None, None, *outs)
+        return (None, None, *outs)
 
 
 _INPLACE_DUNDERS = {'__iadd__', '__isub__', '__imul__', '__itruediv__', '__ifloordiv__', '__ipow__', '__imod__',
@@ -239,26 +294,28 @@ class BatchLoss(torch.Tensor):
         self = args[0] if args else None
         fused = getattr(self, '_dpll_fused', None) if isinstance(self, BatchLoss) else None
         if fused is not None and name in ('mean', 'sum') and len(args) == 1 and not kwargs:
-            loss_sum, grad, leaves = fused
-            n = self.numel()
-            scale = (1.0 / n if n > 0 else float('nan')) if name == 'mean' else 1.0
-            return _FusedReduction.apply(loss_sum, grad, scale, *leaves)
+            sums, means, n, leaves = fused
+            return _FusedReduction.apply(means if name == 'mean' else sums, n, *leaves)
         if fused is not None and (name in _INPLACE_DUNDERS or (name.endswith('_') and not name.endswith('__'))):
             self._dpll_fused = None
         with torch._C.DisableTorchFunctionSubclass():
             return func(*args, **kwargs)
 
 
-def batch_loss(loss: Tensor, loss_sum: Tensor, grad: Tensor, leaves) -> Tensor:
-    """Wraps the per-sample loss with the launch's sum and fused gradient (see :class:`BatchLoss`)."""
+def batch_loss(loss: Tensor, sums: Tensor, means: Tensor, n: int, leaves, iters: Optional[Tensor] = None) -> Tensor:
+    """Wraps the per-sample loss with the launch's [gradient (n) | loss] sums and means (see :class:`BatchLoss`);
+    ``newton_iters`` (B,) int32, when recorded, is the cost hint the data set orders its batches by."""
     out = loss.as_subclass(BatchLoss)
-    out._dpll_fused = (loss_sum, grad, tuple(leaves))
+    out._dpll_fused = (sums, means, n, tuple(leaves))
+    out.newton_iters = iters
     return out
 
 
 def cube_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, dt: float, steps: int,
-                 eps: float = 1e-4, want_force: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
-    """(B,13) -> trajectory (B, steps+1, 13) through ``dpll_cube_rollout_*`` (no autograd)."""
+                 eps: float = 1e-4, want_force: bool = False,
+                 iters_out: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """(B,13) -> trajectory (B, steps+1, 13) through ``dpll_cube_rollout_*`` (no autograd).  ``iters_out``
+    (B,) int32, optional: total Newton iterations of every toss."""
     dtype = _check_inputs(x0, inertia, mu_pair, half)
     x0 = x0.contiguous()
     if x0.dim() != 2 or x0.shape[1] != 13:
@@ -269,7 +326,7 @@ def cube_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, dt:
     fn = getattr(_lib.load(), 'dpll_cube_rollout_' + _SUFFIX[dtype])
     with torch.cuda.device(x0.device):
         rc = fn(_ptr(x0), _ptr(inertia.contiguous()), _ptr(mu_pair.contiguous()), _ptr(half.contiguous()),
-                dt, eps, B, steps, _ptr(traj), _ptr(force), None, _stream())
+                dt, eps, B, steps, _ptr(traj), _ptr(force), _ptr(iters_out), _stream())
     _lib.check(rc, 'dpll_cube_rollout')
     return traj, force
 

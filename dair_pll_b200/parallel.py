@@ -21,6 +21,64 @@ def shard_bounds(n: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class PeerComm:
+    """Communicator of the in-kernel gradient exchange (``dpll_comm_*``, csrc/cn_comm.cuh): every rank owns a
+    small buffer in its HBM that all peers map through CUDA IPC, and the reduction kernel of the loss launch
+    pushes its [gradient | loss sum | count] row into every peer's buffer over NVLink and sums the world's
+    rows -- the data-parallel step issues no NCCL collective.  ``torch.distributed`` (any backend) is used
+    once, here, to hand the IPC handles around.
+
+    Attach it with ``system.data_parallel = PeerComm(device)``: ``loss.mean()`` / ``loss.sum()`` of the returned
+    batch loss and the parameter gradients then cover the samples of all ranks (identical bits on every rank).
+    One communicator serves one stream at a time; every rank must make the same sequence of calls."""
+
+    def __init__(self, device: torch.device, group: Optional[dist.ProcessGroup] = None) -> None:
+        import ctypes
+        from dair_pll_b200 import _lib
+        self._lib = _lib
+        lib = _lib.load()
+        self.device = device
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        nbytes = lib.dpll_comm_handle_bytes()
+        mine = ctypes.create_string_buffer(nbytes)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.dpll_comm_create(self.rank, self.world, ctypes.byref(handle), mine), 'dpll_comm_create')
+            self.handle = handle
+            if self.world > 1:
+                gathered = [None] * self.world
+                dist.all_gather_object(gathered, bytes(mine.raw), group=group)
+                blob = ctypes.create_string_buffer(b''.join(gathered), nbytes * self.world)
+            else:
+                blob = mine
+            _lib.check(lib.dpll_comm_connect(self.handle, blob), 'dpll_comm_connect')
+        if self.world > 1:
+            dist.barrier(group=group)        # every rank has mapped every buffer before the first exchange
+
+    def all_reduce_sum(self, t: Tensor, scale: float = 1.0) -> Tensor:
+        """Stand-alone exchange of up to 32 doubles (one tiny kernel, no NCCL): returns scale * sum over ranks."""
+        buf = t.detach().to(torch.float64).contiguous().clone()
+        with torch.cuda.device(self.device):
+            rc = self._lib.load().dpll_comm_allreduce_f64(self.handle, buf.data_ptr(), buf.numel(), float(scale),
+                                                          torch.cuda.current_stream().cuda_stream)
+        self._lib.check(rc, 'dpll_comm_allreduce')
+        return buf.to(t.dtype).view_as(t)
+
+    def check(self) -> None:
+        """Host-side check (synchronises): raises if an exchange timed out waiting for a peer."""
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.load().dpll_comm_error(self.handle), 'dpll_comm')
+
+    def close(self) -> None:
+        if self.handle is not None:
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize(self.device)
+                self._lib.load().dpll_comm_destroy(self.handle)
+            self.handle = None
+
+
 class GradientAllReduce:
     """Flat gradient buffer shared with the parameters' ``.grad`` + mean all-reduce over ranks."""
 
@@ -119,6 +177,9 @@ class HostBatchPipeline:
         self.events = [torch.cuda.Event() for _ in range(chunks)]
 
     def loss_mean_from_host(self, x_host: Tensor, xp_host: Tensor) -> Tensor:
+        return self.loss_sum_from_host(x_host, xp_host) / x_host.shape[0]
+
+    def loss_sum_from_host(self, x_host: Tensor, xp_host: Tensor) -> Tensor:
         B = x_host.shape[0]
         assert B <= self.x_dev.shape[0]
         main = torch.cuda.current_stream(self.device)
@@ -136,4 +197,4 @@ class HostBatchPipeline:
             main.wait_event(self.events[c])
             part = self.system.contactnets_loss(self.x_dev[lo:hi], None, self.xp_dev[lo:hi]).sum()
             total = part if total is None else total + part
-        return total / B
+        return total

@@ -159,10 +159,14 @@ class SystemSpec:
             if jo is not None and any(abs(a) > 0 for a in _floats(jo.get('rpy'), 3)):
                 raise NotImplementedError('rotated joint frames are not supported')
             axis = joint.find('axis')
+            ax = _floats(axis.get('xyz') if axis is not None else '1 0 0', 3)
+            norm = sum(a * a for a in ax) ** 0.5
+            if norm == 0:
+                raise ValueError(f'joint {joint.get("name")} has a zero axis')
             joints.append(JointSpec(names.index(joint.find('parent').get('link')),
                                     names.index(joint.find('child').get('link')),
                                     _floats(jo.get('xyz') if jo is not None else None, 3),
-                                    _floats(axis.get('xyz') if axis is not None else '1 0 0', 3)))
+                                    tuple(a / norm for a in ax)))        # Drake normalises the axis on parsing
         if len(bodies) == 1 and not joints:
             kind = 'cube'
         elif len(bodies) == 2 and len(joints) == 1 and joints[0].parent == 0 and joints[0].child == 1:
@@ -171,6 +175,19 @@ class SystemSpec:
             raise NotImplementedError(
                 'kernels are specialised for a single floating body or a floating body with one '
                 'revolute child; arbitrary trees need the symbolic path (SURVEY.md section 8(f) N2)')
+        if kind == 'cube':
+            if len(geometries) != 1:
+                raise NotImplementedError('the single-body kernels take exactly one collision geometry')
+            if geometries[0].kind != 'box':
+                raise NotImplementedError('the single-body kernels take a <box> collision geometry')
+            if any(abs(o) > 0 for o in geometries[0].offset):
+                raise NotImplementedError('a collision frame offset from the link origin is not supported for a single '
+                                          'floating body (the two-body kernels take offsets)')
+        else:
+            if len(geometries) != 2 or [g.body for g in geometries] != [0, 1]:
+                raise NotImplementedError('the two-body kernels take one collision geometry per link')
+        if len({g.kind for g in geometries}) > 1:
+            raise NotImplementedError('mixed box / mesh collision geometries in one system are not supported')
         ground = len(geometries)
         geometries.append(GeometrySpec(-1, 'plane', (0., 0., 0.), None, None, 1.0))
         pairs = [(ground, g) for g in range(ground)]

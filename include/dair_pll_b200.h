@@ -12,7 +12,9 @@
  *    row-major.  The library never allocates or frees; scratch is passed in
  *    (`workspace`, at least dpll_workspace_bytes() bytes, 16-byte aligned).
  *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and
- *    performs no host synchronisation.  Calls are re-entrant; there is no global state.
+ *    performs no host synchronisation.  Compute calls are re-entrant.  Mutable library state: the
+ *    A/B selector dpll_set_loss_variant (process-wide, measurement only) and the communicator
+ *    objects of the data-parallel exchange (dpll_comm_*, one stream at a time each).
  *  - Return value: 0 on success, a positive cudaError_t value if a launch failed, a
  *    negative DPLL_E* value for argument errors.  Numerical failure of a sample's QP
  *    is NOT an error: as in the reference (multibody_learnable_system.py:186-192) that
@@ -40,6 +42,9 @@ extern "C" {
 #define DPLL_OK 0
 #define DPLL_EINVAL (-1)     /* null pointer / negative size */
 #define DPLL_EWORKSPACE (-2) /* workspace too small */
+#define DPLL_ECOMM (-3)      /* a peer did not arrive within the exchange's timeout */
+
+#define DPLL_VERSION 200     /* bumped with every change of a signature below; the binding checks it */
 
 #define DPLL_CUBE_NX 13
 #define DPLL_CUBE_NC 4
@@ -53,8 +58,11 @@ extern "C" {
 int dpll_version(void);
 
 /* Selects the loss-kernel implementation, for A/B measurement only: 0 = warp-level wavefront
- * scheduler (default), 1 = one sample per thread.  Both produce bitwise-identical per-sample
- * losses.  Process-wide setting (the single piece of mutable library state). */
+ * scheduler with static sample ranges (default; gradient sums bitwise reproducible), 1 = one sample
+ * per thread, 2 = wavefront scheduler whose warps draw 32-sample chunks from a global counter (as
+ * DPLL_LOSS_DYNAMIC below).  All three produce bitwise-identical PER-SAMPLE losses and forces; the
+ * summed gradient of variant 2 depends on the chunk-to-warp assignment and is reproducible to
+ * rounding only.  Process-wide setting. */
 int dpll_set_loss_variant(int variant);
 
 /* Bytes of device scratch any entry point below may need. */
@@ -117,6 +125,54 @@ int dpll_cube_loss_leaf_f32(const float* x, const float* x_plus, const float* we
                             float eps, int64_t B, float* loss, float* force, int32_t* iters,
                             float* grad_leaf, float* loss_sum, const int32_t* skip_flag,
                             void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The data-parallel / training-loop form of dpll_cube_loss_leaf_*: what one rank of the sharded step
+ * (the reference has no distributed code) calls on its B samples.
+ *   x_row_stride, xp_row_stride : distance in ELEMENTS between consecutive rows of x / x_plus (>= 13), so the
+ *       training loop's views x_past[..., -1, :] / x_future[..., 0, :] (drake_experiment.py:217-218) are read in
+ *       place instead of being copied first
+ *   flags : DPLL_LOSS_DYNAMIC -- warps draw their 32-sample chunks from a global counter instead of a static
+ *       range.  Chunks are handed out in batch order, so a batch ordered by decreasing expected Newton count
+ *       (last epoch's `iters`, dataset_management.DeviceTrajectorySliceDataset) starts its longest solves first
+ *       and ends with the cheap samples: no serial tail.  Per-sample outputs are unaffected; the summed
+ *       gradient is reproducible to rounding only.
+ *   comm  : nullable communicator (dpll_comm_create).  When given, the reduction kernel exchanges
+ *       [grad_leaf 15 | loss sum | B] with every peer over NVLink itself and the outputs are the sums over
+ *       ranks, bitwise identical on every rank; every rank of the communicator must make the call.
+ *   sums  : (17) nullable; [d(sum_b loss_b)/d leaves (15) | sum_b loss_b | number of samples summed]
+ *   means : (16) nullable; sums[0..15] / sums[16]: loss.mean() (drake_experiment.py:222-223) and its gradient
+ *   local : (16) nullable; this rank's own [grad_leaf 15 | loss sum] (before the exchange)
+ * No `weight`, `force` or `skip_flag`: this is the loss.mean()/loss.sum() training path.
+ */
+#define DPLL_LOSS_DYNAMIC 1
+int dpll_cube_loss_leaf_dp_f64(const double* x, int64_t x_row_stride, const double* x_plus, int64_t xp_row_stride,
+                               const double* theta, const double* friction, const double* length, double dt,
+                               double eps, int64_t B, int32_t flags, void* comm, double* loss, int32_t* iters,
+                               double* sums, double* means, double* local, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int dpll_cube_loss_leaf_dp_f32(const float* x, int64_t x_row_stride, const float* x_plus, int64_t xp_row_stride,
+                               const float* theta, const float* friction, const float* length, float dt, float eps,
+                               int64_t B, int32_t flags, void* comm, float* loss, int32_t* iters, float* sums,
+                               float* means, float* local, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Data-parallel exchange over peer memory.  One communicator per rank (= per process and GPU); `create`
+ * allocates the rank's exchange buffer (the only allocation this library ever makes) and returns its CUDA IPC
+ * handle (dpll_comm_handle_bytes() bytes, HOST memory); the caller gathers all ranks' handles by any means
+ * (torch.distributed.all_gather_object in dair_pll_b200/parallel.py) and passes them, in rank order, to
+ * `connect`, which maps the peers' buffers (NVLink / NVSwitch P2P).  The kernels then all-reduce up to 32
+ * doubles by direct peer stores + flags (csrc/cn_comm.cuh): no NCCL launch on the step's critical path.  A
+ * peer that never arrives is reported by dpll_comm_error (DPLL_ECOMM) after a 4 s device-side timeout
+ * instead of hanging the GPU.  dpll_comm_allreduce_f64: the stand-alone form, buf[i] <- scale * sum over ranks.
+ */
+size_t dpll_comm_handle_bytes(void);
+int dpll_comm_create(int32_t rank, int32_t world, void** comm_out, void* handle_out);
+int dpll_comm_connect(void* comm, const void* handles);
+int dpll_comm_destroy(void* comm);
+void* dpll_comm_device_state(void* comm);
+int dpll_comm_error(void* comm);
+int dpll_comm_allreduce_f64(void* comm, double* buf, int32_t n, double scale, void* stream);
 
 /*
  * Learnable time stepping for the cube: `steps` applications of
@@ -202,7 +258,7 @@ int dpll_elbow_rollout_grad_f64(const double* x0, const double* inertia, const d
  * of box 1 then box 2, each by ascending vertex index.  grad[28] = [d/d inertia (20) | d/d mu_pair (2) |
  * d/d half (6)].  Same reference spans as the cube entry points; the articulated M(q), F(q,v) and
  * geometry Jacobians are the closed forms of what multibody_terms.py:114-157, 267-319 derive
- * symbolically.  One sample per thread in this version.
+ * symbolically.
  *
  * Learned (mesh) geometry: `pts` (B, 8, 3), nullable.  When given, the 4 + 4 witness points of the two
  * geometries (geometry frames) are taken from it instead of the box corners -- they are the outputs of

@@ -1,0 +1,326 @@
+"""GPU, round 2: the regions round 1 left untested -- the bench batch itself against the oracle, the elbow at
+scale and in the fp32 variant, long rollouts, the training-loop entry point (row strides, cost-ordered dynamic
+scheduling, in-kernel exchange at world size 1), the device data set against the reference class's outputs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from dair_pll_b200 import ops, synthetic  # noqa: E402
+from dair_pll_b200.multibody_learnable_system import MultibodyLearnableSystem  # noqa: E402
+from tests.util import kernel_level_params, load_golden, max_rel_to_scale, rel_err  # noqa: E402
+
+DEV = 'cuda:0'
+DT = 0.0068
+
+
+def _leaf_grads(system):
+    mt = system.multibody_terms
+    out = [mt.lagrangian_terms.inertial_parameters.grad, mt.contact_terms.friction_params.grad]
+    out += [g.length_params.grad for g in mt.contact_terms.geometries if hasattr(g, 'length_params')]
+    return [t.detach().cpu().numpy().copy() for t in out]
+
+
+def test_bench_batch_subset_matches_oracle():
+    """The headline workload itself: bench.py's 1,048,576-pair batch (same generator, seed and parameters) goes
+    through the public API once; a random 16,384-sample subset of its per-sample losses, and the parameter
+    gradient of that subset, are compared with the CPU oracle at 1e-9 (north_star)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import contactnets_oracle as co
+    from oracle.callables import CUBE_TREE, TreeCallables
+    system = bench.make_system(torch.device(DEV), torch.float64)
+    x, xp = bench.make_batch(system, 1 << 20, seed=0, device=torch.device(DEV), dtype=torch.float64)
+    loss = system.contactnets_loss(x, None, xp).detach()
+    idx = torch.randperm(1 << 20, generator=torch.Generator().manual_seed(123))[:16384].to(DEV)
+    xs, xps = x[idx].contiguous(), xp[idx].contiguous()
+    sub = system.contactnets_loss(xs, None, xps)
+    assert torch.equal(sub.detach(), loss[idx])                  # per-sample results do not depend on the batch
+    sub.sum().backward()
+    mt = system.multibody_terms
+    P = co.OracleParams(mt.lagrangian_terms.inertial_parameters.detach().cpu().clone(),
+                        mt.contact_terms.friction_params.detach().cpu().clone(),
+                        [mt.contact_terms.geometries[0].length_params.detach().cpu().clone()]).requires_grad_()
+    lo = co.contactnets_loss(TreeCallables(CUBE_TREE), P, xs.cpu(), xps.cpu(), DT)
+    lo.sum().backward()
+    assert rel_err(sub.detach().cpu().numpy(), lo.detach().numpy(), 1e-9).max() < 1e-9
+    gt, gf, gl = _leaf_grads(system)
+    assert max_rel_to_scale(gt, P.inertial_parameters.grad.numpy()) < 1e-9
+    assert max_rel_to_scale(gf, P.friction_params.grad.numpy()) < 1e-9
+    assert max_rel_to_scale(gl, P.length_params[0].grad.numpy()) < 1e-9
+
+
+def _elbow_random(n, assets_dir, seed):
+    from dair_pll_b200.inertia import InertialParameterConverter as IPC
+    pi, fr, half = synthetic.elbow_learnables_perturbed(seed)
+    s = MultibodyLearnableSystem({'elbow': os.path.join(assets_dir, 'elbow.urdf')}, DT)
+    s.load_state_dict({
+        'multibody_terms.lagrangian_terms.inertial_parameters': IPC.pi_cm_to_theta(pi),
+        'multibody_terms.contact_terms.friction_params': fr,
+        'multibody_terms.contact_terms.geometries.0.length_params': half[0].reshape(1, 3),
+        'multibody_terms.contact_terms.geometries.1.length_params': half[1].reshape(1, 3)})
+    s = s.to(DEV)
+    x = synthetic.elbow_states(n, seed=seed + 10, device=DEV)
+    with torch.no_grad():
+        traj, _ = s.simulate(x.unsqueeze(-2), torch.zeros(n, 1, device=DEV), 1)
+    xp = synthetic.perturb_next_state(traj[:, 1], seed=seed + 11, n_q=8)
+    return s, (pi, fr, half), x, xp, traj
+
+
+def test_elbow_matches_cpu_oracle_on_random_inputs(assets_dir):
+    """Two-body system at scale: 65,536 random state pairs (all contact regimes of both boxes) -- per-sample
+    losses, every parameter gradient and the one-step next states against the CPU oracle at 1e-9."""
+    from oracle import contactnets_oracle as co
+    from oracle.callables import ELBOW_TREE, TreeCallables
+    n = 65536
+    s, (pi, fr, half), x, xp, traj = _elbow_random(n, assets_dir, 1)
+    loss = s.contactnets_loss(x, None, xp)
+    loss.sum().backward()
+    calls = TreeCallables(ELBOW_TREE)
+    P = co.OracleParams(co.pi_cm_to_theta(pi), fr.clone(), [h.reshape(1, 3).clone() for h in half]).requires_grad_()
+    lo = co.contactnets_loss(calls, P, x.cpu(), xp.cpu(), DT)
+    lo.sum().backward()
+    assert rel_err(loss.detach().cpu().numpy(), lo.detach().numpy(), 1e-9).max() < 1e-9
+    g = _leaf_grads(s)
+    assert max_rel_to_scale(g[0], P.inertial_parameters.grad.numpy()) < 1e-9
+    assert max_rel_to_scale(g[1], P.friction_params.grad.numpy()) < 1e-9
+    assert max_rel_to_scale(np.stack([a.reshape(3) for a in g[2:]]),
+                            np.stack([p.grad.numpy().reshape(3) for p in P.length_params])) < 1e-9
+    with torch.no_grad():
+        step_o = co.sim_step(calls, P, x[:8192].cpu(), DT)
+    assert np.abs(traj[:8192, 1].cpu().numpy() - step_o.numpy()).max() < 1e-9
+
+
+def test_elbow_fp32_variant(assets_dir):
+    """fp32 variant of the two-body entry points (dpll_elbow_loss_f32 / dpll_elbow_rollout_f32: fp32 storage, fp64
+    arithmetic): losses, gradients and next states within 1e-4 (north_star) of the fp64 results."""
+    n = 8192
+    s, _, x, xp, traj = _elbow_random(n, assets_dir, 2)
+    loss64 = s.contactnets_loss(x, None, xp)
+    loss64.mean().backward()
+    g64 = _leaf_grads(s)
+    for p in s.parameters():
+        p.grad = None
+    loss32 = s.contactnets_loss(x.float(), None, xp.float())
+    assert loss32.dtype == torch.float32
+    loss32.mean().backward()
+    g32 = _leaf_grads(s)
+    l64, l32 = loss64.detach().cpu().numpy(), loss32.detach().cpu().numpy().astype(np.float64)
+    assert np.abs(l32 - l64).max() < 1e-4 * max(np.abs(l64).max(), 1e-3)
+    assert abs(l32.mean() - l64.mean()) < 1e-4 * abs(l64.mean())
+    for a, b in zip(g32, g64):
+        assert max_rel_to_scale(a, b) < 1e-4
+    with torch.no_grad():
+        t32, _ = s.simulate(x.float().unsqueeze(-2), torch.zeros(n, 1, device=DEV), 1)
+    assert t32.dtype == torch.float32
+    ref = traj[:, 1].cpu().numpy()
+    assert np.abs(t32[:, 1].cpu().numpy() - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_elbow_learned_geometry_width_256_matches_oracle(assets_dir):
+    """Config 3's system as configured (support networks of width 256, reference initialisation): loss and the
+    gradients of inertia, friction and all network weights against autograd through the CPU oracle."""
+    from oracle import contactnets_oracle as co
+    from oracle.callables import ELBOW_TREE, TreeCallables
+    torch.manual_seed(0)
+    s = MultibodyLearnableSystem({'elbow': os.path.join(assets_dir, 'elbow_mesh.urdf')}, DT).to(DEV)
+    n = 2048
+    x = synthetic.elbow_states(n, seed=31, device=DEV)
+    with torch.no_grad():
+        traj, _ = s.simulate(x.unsqueeze(-2), torch.zeros(n, 1, device=DEV), 1)
+    xp = synthetic.perturb_next_state(traj[:, 1], seed=32, n_q=8)
+    loss = s.contactnets_loss(x, None, xp)
+    loss.sum().backward()
+    mt = s.multibody_terms
+    nets = []
+    for gi in range(2):
+        geom = mt.contact_terms.geometries[gi]
+        net = geom.network
+        nets.append(dict(Wd0=net.input_weights[0].detach().cpu().clone().requires_grad_(),
+                         Wd1=net.input_weights[1].detach().cpu().clone().requires_grad_(),
+                         Wh=net.hidden_weights[0].detach().cpu().clone().requires_grad_(),
+                         wout=net.output_weight.detach().cpu().clone().requires_grad_(),
+                         perturbations=geom.perturbations.detach().cpu().clone()))
+    P = co.OracleParams(mt.lagrangian_terms.inertial_parameters.detach().cpu().clone(),
+                        mt.contact_terms.friction_params.detach().cpu().clone(), [], icnn=nets).requires_grad_()
+    lo = co.contactnets_loss(TreeCallables(ELBOW_TREE), P, x.cpu(), xp.cpu(), DT)
+    lo.sum().backward()
+    assert rel_err(loss.detach().cpu().numpy(), lo.detach().numpy(), 1e-9).max() < 1e-9
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), P.inertial_parameters.grad.numpy()) < 1e-9
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), P.friction_params.grad.numpy()) < 1e-9
+    for gi in range(2):
+        net = mt.contact_terms.geometries[gi].network
+        for k, p in (('Wd0', net.input_weights[0]), ('Wd1', net.input_weights[1]), ('Wh', net.hidden_weights[0]),
+                     ('wout', net.output_weight)):
+            assert max_rel_to_scale(p.grad.cpu().numpy(), nets[gi][k].grad.numpy()) < 1e-9, (gi, k)
+
+
+def test_long_rollout_matches_oracle_with_growth_bound(assets_dir):
+    """Config 4's horizon: 256 tosses x 80 steps (the example's initial-condition sampler, contactnets_simple.py:56-63)
+    against the CPU oracle's own 80-step simulation.  Each step is held to 1e-9; over a trajectory the difference
+    may grow through contact events (a toss has a handful of impacts; measured sensitivity of an impact step to
+    its input is <= ~30x), so the whole trajectory is held to 1e-9 * 30^k with k the impacts seen -- stated here
+    as: median over tosses <= 1e-9, maximum <= 1e-5 -- and one-step agreement is re-checked ALONG the
+    trajectory by stepping the oracle from the kernel's own states."""
+    from oracle import contactnets_oracle as co
+    from oracle.callables import CUBE_TREE, TreeCallables
+    g = load_golden('cube_real_nominal')
+    s = MultibodyLearnableSystem({'cube': os.path.join(assets_dir, 'cube.urdf')}, DT).to(DEV)
+    n, steps = 256, 80
+    gen = torch.Generator().manual_seed(7)
+    x0 = torch.tensor([1., 0., 0., 0., 0., 0., 0.21, 0., 0., 0., 0., 0., -.075], dtype=torch.float64).repeat(n, 1)
+    x0[:, 7:] += 0.1 * (2 * torch.rand(n, 6, generator=gen, dtype=torch.float64) - 1) * torch.tensor([30., 30, 30, 10, 10, 10])
+    quat = x0[:, :4] + 0.3 * torch.randn(n, 4, generator=gen, dtype=torch.float64)
+    x0[:, :4] = quat / quat.norm(dim=-1, keepdim=True)
+    with torch.no_grad():
+        traj, _ = s.simulate(x0.to(DEV).unsqueeze(-2), torch.zeros(n, 1, device=DEV), steps)
+    mt = s.multibody_terms
+    P = co.OracleParams(mt.lagrangian_terms.inertial_parameters.detach().cpu(), mt.contact_terms.friction_params.detach().cpu(),
+                        [mt.contact_terms.geometries[0].length_params.detach().cpu()])
+    calls = TreeCallables(CUBE_TREE)
+    with torch.no_grad():
+        tro = co.simulate(calls, P, x0, DT, steps)
+    t = traj.cpu()
+    assert (t[:, -1, 6] < 0.2).all()                         # the tosses did come down and hit the ground
+    err = (t - tro).abs().amax(dim=(1, 2))
+    assert err.median().item() < 1e-9 and err.max().item() < 1e-5
+    # one-step parity along the kernel's own trajectory (no accumulation): every 8th state of every toss
+    xs = t[:, 0:steps:8].reshape(-1, 13)
+    with torch.no_grad():
+        nxt = co.sim_step(calls, P, xs, DT)
+    assert (nxt - t[:, 1:steps + 1:8].reshape(-1, 13)).abs().max().item() < 1e-9
+    del g
+
+
+def test_tiled_real_data_matches_reference_golden(assets_dir):
+    """The reference's recorded tosses (478 consecutive real pairs, 83% in contact) tiled 512 times: every tile's
+    per-sample losses are the golden ones and the gradient of the mean is the golden gradient."""
+    g = load_golden('cube_real_nominal')
+    s = MultibodyLearnableSystem({'cube': os.path.join(assets_dir, 'cube.urdf')}, float(g['dt']))
+    s.load_state_dict({
+        'multibody_terms.lagrangian_terms.inertial_parameters': torch.from_numpy(g['theta']),
+        'multibody_terms.contact_terms.friction_params': torch.from_numpy(g['friction_params']),
+        'multibody_terms.contact_terms.geometries.0.length_params': torch.from_numpy(g['half_lengths']).reshape(1, 3)})
+    s = s.to(DEV)
+    k = 512
+    x = torch.from_numpy(np.tile(g['x'], (k, 1))).to(DEV)
+    xp = torch.from_numpy(np.tile(g['x_plus'], (k, 1))).to(DEV)
+    loss = s.contactnets_loss(x, None, xp)
+    loss.mean().backward()
+    l = loss.detach().cpu().numpy().reshape(k, -1)
+    assert np.abs(l - g['loss'][None]).max() < 1e-13
+    gt, gf, gl = _leaf_grads(s)
+    assert max_rel_to_scale(gt, g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(gf, g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(gl, g['grad_length']) < 1e-9
+
+
+def test_training_entry_point_strides_order_and_exchange(assets_dir):
+    """dpll_cube_loss_leaf_dp_*: (1) row-strided views (the reference's x_past[..., -1, :]) give the bits of the
+    contiguous call; (2) a cost-ordered batch with dynamic chunk scheduling gives the same per-sample losses and
+    the same sums to rounding; (3) a world-size-1 communicator is the identity; (4) means = sums / count."""
+    from dair_pll_b200 import parallel
+    g = load_golden('cube_synthetic')
+    theta = torch.from_numpy(g['theta']).to(DEV)
+    fr = torch.from_numpy(g['friction_params']).to(DEV)
+    ln = torch.from_numpy(g['half_lengths']).reshape(1, 3).to(DEV)
+    inertia, mu, half = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    n = 300001
+    x = synthetic.cube_states(n, seed=61, device=DEV)
+    traj, _ = ops.cube_rollout(x, inertia, mu, half, DT, 1)
+    xp = synthetic.perturb_next_state(traj[:, 1], seed=62)
+    base = ops.cube_loss_leaf_dp_raw(x, xp, theta, fr, ln, DT, 1e-3, want_iters=True)
+    loss, sums, means, local, iters = base
+    assert sums[16].item() == n and torch.equal(local, sums[:16])
+    assert torch.allclose(means, sums[:16] / n, rtol=1e-15, atol=0)
+    old = ops.cube_loss_leaf_raw(x, xp, theta, fr, ln, DT, 1e-3)
+    assert torch.equal(old[0], loss) and torch.equal(old[1], sums[:15]) and torch.equal(old[2], sums[15:16])
+    # (1) strided rows
+    past, fut = torch.stack((x, x + 1.0), 1), torch.stack((xp, xp - 1.0), 1)
+    xv, xpv = past[:, 0, :], fut[:, 0, :]
+    assert not xv.is_contiguous()
+    st = ops.cube_loss_leaf_dp_raw(xv, xpv, theta, fr, ln, DT, 1e-3)
+    assert torch.equal(st[0], loss) and torch.equal(st[1], sums)
+    # (2) cost order + dynamic scheduling
+    order = torch.argsort(iters, descending=True, stable=True)
+    xo, xpo = x[order].contiguous(), xp[order].contiguous()
+    dyn = ops.cube_loss_leaf_dp_raw(xo, xpo, theta, fr, ln, DT, 1e-3, flags=ops.LOSS_DYNAMIC, want_iters=True)
+    assert torch.equal(dyn[0], loss[order]) and torch.equal(dyn[4], iters[order])
+    assert max_rel_to_scale(dyn[1].cpu().numpy(), sums.cpu().numpy()) < 1e-12
+    for m in (1, 31, 32, 33, 4097):
+        a = ops.cube_loss_leaf_dp_raw(xo[:m], xpo[:m], theta, fr, ln, DT, 1e-3, flags=ops.LOSS_DYNAMIC)
+        b = ops.cube_loss_leaf_dp_raw(xo[:m], xpo[:m], theta, fr, ln, DT, 1e-3)
+        assert torch.equal(a[0], b[0]) and max_rel_to_scale(a[1].cpu().numpy(), b[1].cpu().numpy()) < 1e-12, m
+    # (3) communicator of one rank
+    comm = parallel.PeerComm(torch.device(DEV))
+    try:
+        for _ in range(3):                                   # epochs advance, buffers alternate
+            c = ops.cube_loss_leaf_dp_raw(x, xp, theta, fr, ln, DT, 1e-3, comm=comm)
+            assert torch.equal(c[1], sums) and torch.equal(c[2], means) and torch.equal(c[3], local)
+        v = torch.arange(15, dtype=torch.float64, device=DEV)
+        assert torch.equal(comm.all_reduce_sum(v, 0.5), v * 0.5)
+        comm.check()
+    finally:
+        comm.close()
+    # module API: the options change nothing but the schedule
+    s = MultibodyLearnableSystem({'cube': os.path.join(assets_dir, 'cube.urdf')}, DT)
+    s.load_state_dict({
+        'multibody_terms.lagrangian_terms.inertial_parameters': torch.from_numpy(g['theta']),
+        'multibody_terms.contact_terms.friction_params': torch.from_numpy(g['friction_params']),
+        'multibody_terms.contact_terms.geometries.0.length_params': torch.from_numpy(g['half_lengths']).reshape(1, 3)})
+    s = s.to(DEV)
+    s.record_newton_iters = True
+    l0 = s.contactnets_loss(xv, None, xpv)
+    assert torch.equal(l0.newton_iters, iters)
+    l0.mean().backward()
+    g0 = _leaf_grads(s)
+    for p in s.parameters():
+        p.grad = None
+    s.dynamic_schedule = True
+    l1 = s.contactnets_loss(xo, None, xpo)
+    l1.mean().backward()
+    assert abs(l1.mean().item() - l0.mean().item()) <= 1e-13 * abs(l0.mean().item())
+    for a, b in zip(_leaf_grads(s), g0):
+        assert max_rel_to_scale(a, b) < 1e-12
+
+
+def test_device_dataset_matches_reference_fixture_on_the_gpu():
+    """the device-resident slice data set holds exactly the (previous, future) pairs the reference's
+    TrajectorySliceDataset produced (fixture generated by the reference's own class, oracle/gen_golden_dataset.py),
+    and cost-ordered batches feed the loss without leaving the device."""
+    from dair_pll_b200.dataset_management import DeviceTrajectorySliceDataset, TrajectorySliceConfig
+    g = load_golden('dataset_slices')
+    trajs = [torch.from_numpy(g[f'traj{i}']) for i in range(int(g['n_traj']))]
+    for c, (skip, hist, pred) in enumerate(g['configs']):
+        ds = DeviceTrajectorySliceDataset(TrajectorySliceConfig(t_skip=int(skip), t_history=int(hist), t_prediction=int(pred)),
+                                          device=torch.device(DEV))
+        for t in trajs:
+            ds.add_slices_from_trajectory(t)
+        prev, fut = ds.tensors()
+        assert prev.is_cuda and torch.equal(prev.cpu(), torch.from_numpy(g[f'previous{c}']))
+        assert torch.equal(fut.cpu(), torch.from_numpy(g[f'future{c}']))
+    # an epoch through the loss: hints recorded from the first pass order the second
+    ds = DeviceTrajectorySliceDataset(TrajectorySliceConfig(t_skip=1, t_history=2, t_prediction=1), device=torch.device(DEV))
+    for t in trajs:
+        ds.add_slices_from_trajectory(t)
+    s = MultibodyLearnableSystem({'cube': os.path.join(ROOT, 'dair_pll_b200', 'assets', 'cube.urdf')}, DT).to(DEV)
+    s.record_newton_iters = True
+    total = 0.0
+    for prev, fut, idx in ds.batches(16, shuffle=True, generator=torch.Generator(device=DEV).manual_seed(0), return_indices=True):
+        loss = s.contactnets_loss(prev[..., -1, :], None, fut[..., 0, :])
+        ds.update_costs(idx, loss.newton_iters)
+        total += loss.sum().item()
+    s.dynamic_schedule = True
+    total2, costs = 0.0, []
+    for prev, fut, idx in ds.batches(16, shuffle=True, generator=torch.Generator(device=DEV).manual_seed(1), cost_ordered=True,
+                                     return_indices=True):
+        loss = s.contactnets_loss(prev[..., -1, :], None, fut[..., 0, :])
+        costs.append(loss.newton_iters.cpu())
+        total2 += loss.sum().item()
+    assert abs(total - total2) <= 1e-12 * abs(total)
+    assert all(torch.equal(c, c.sort(descending=True).values) for c in costs)

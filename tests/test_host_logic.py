@@ -189,3 +189,93 @@ def test_generate_updated_urdfs_round_trip(asset, tmp_path):
     for ga, gb in zip(a.contact_terms.geometries, b.contact_terms.geometries):
         if hasattr(ga, 'length_params'):
             assert torch.allclose(ga.length_params.abs(), gb.length_params.abs(), rtol=1e-12)
+
+
+def test_device_slice_dataset_matches_the_reference_class_fixture():
+    """tests/golden/dataset_slices.npz holds the outputs of the REFERENCE's own TrajectorySliceDataset
+    (dair_pll/dataset_management.py:17-67, run through oracle/ref_shim.py by oracle/gen_golden_dataset.py) on three
+    recorded tosses for four slice configurations: same pairs, same order, bit for bit."""
+    from dair_pll_b200.dataset_management import DeviceTrajectorySliceDataset, TrajectorySliceConfig
+    from tests.util import load_golden
+    g = load_golden('dataset_slices')
+    trajs = [torch.from_numpy(g[f'traj{i}']) for i in range(int(g['n_traj']))]
+    for c, (skip, hist, pred) in enumerate(g['configs']):
+        ds = DeviceTrajectorySliceDataset(TrajectorySliceConfig(t_skip=int(skip), t_history=int(hist), t_prediction=int(pred)))
+        for t in trajs:
+            ds.add_slices_from_trajectory(t)
+        prev, fut = ds.tensors()
+        assert torch.equal(prev, torch.from_numpy(g[f'previous{c}'])), c
+        assert torch.equal(fut, torch.from_numpy(g[f'future{c}'])), c
+
+
+def test_cost_ordered_batches_cover_each_slice_once_and_deal_equal_shards():
+    """DeviceTrajectorySliceDataset cost hints: every batch is handed out by decreasing hint, dealt round-robin to the
+    ranks, so each rank's share is itself ordered, shares differ by at most one slice and their costs by at most
+    the largest single hint; together the shares are exactly the batch."""
+    from dair_pll_b200.dataset_management import DeviceTrajectorySliceDataset, TrajectorySliceConfig
+    gen = torch.Generator().manual_seed(5)
+    ds = DeviceTrajectorySliceDataset(TrajectorySliceConfig())
+    for T in (40, 23, 61):
+        ds.add_slices_from_trajectory(torch.randn(T, 13, generator=gen, dtype=torch.float64))
+    n = len(ds)
+    cost = torch.randint(0, 40, (n,), generator=gen, dtype=torch.int32)
+    ds.update_costs(None, cost)
+    ds.update_costs(torch.tensor([3, 5]), torch.tensor([99, 98], dtype=torch.int32))
+    cost[3], cost[5] = 99, 98
+    world = 3
+    for batch_size in (n, 32):
+        seen = []
+        for lo in range(0, n, batch_size):
+            pass
+        shares = [list(ds.batches(batch_size, shuffle=True, generator=torch.Generator().manual_seed(9), cost_ordered=True,
+                                  return_indices=True, rank=r, world=world)) for r in range(world)]
+        for b in range(len(shares[0])):
+            idx = [shares[r][b][2] for r in range(world)]
+            sizes = [i.numel() for i in idx]
+            assert max(sizes) - min(sizes) <= 1
+            for r in range(world):
+                c = cost[idx[r]]
+                assert torch.equal(c, c.sort(descending=True).values)               # each share is ordered
+                prev, fut = ds.tensors()
+                assert torch.equal(shares[r][b][0], prev[idx[r]]) and torch.equal(shares[r][b][1], fut[idx[r]])
+            tot = [int(cost[i].sum()) for i in idx]
+            assert max(tot) - min(tot) <= int(cost.max())
+            seen.append(torch.cat(idx))
+        allidx = torch.cat(seen)
+        assert allidx.numel() == n and torch.equal(allidx.sort().values, torch.arange(n))
+    # the first batch of the whole-set order starts with the most expensive slices
+    first = next(iter(ds.batches(n, shuffle=False, cost_ordered=True, return_indices=True)))[2]
+    assert first[0].item() == 3 and first[1].item() == 5
+
+
+def test_peer_allreduce_protocol_model():
+    """tests/host_emul/comm_model.cpp: a thread-per-rank model of the in-kernel all-reduce protocol
+    (csrc/cn_comm.cuh: monotone flags, two alternating data rows, rank-ordered sums) never reads a row of the wrong
+    epoch, for 2 / 4 / 8 ranks drifting at random."""
+    import subprocess
+    import tempfile
+    out = os.path.join(tempfile.gettempdir(), f'dpll_comm_model_{os.getuid()}.so')
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-pthread', '-o', out,
+                           os.path.join(ROOT, 'tests', 'host_emul', 'comm_model.cpp')])
+    lib = ctypes.CDLL(out)
+    for world in (2, 4, 8):
+        assert lib.comm_model_run(world, 5000, 17, world) == 0
+
+
+def test_urdf_ingestion_rejects_what_the_kernels_do_not_model(tmp_path):
+    """Models the kernels would silently mis-simulate are refused at construction: a single floating box whose
+    collision frame is offset from the link origin, and a joint axis is normalised as Drake does on parsing."""
+    from dair_pll_b200.system_spec import SystemSpec
+    cube = open(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'cube.urdf')).read()
+    assert '<collision>' in cube
+    shifted = cube.replace('<collision>', '<collision>\n      <origin xyz="0.01 0 0" rpy="0 0 0"/>', 1)
+    p = tmp_path / 'shifted.urdf'
+    p.write_text(shifted)
+    with pytest.raises(NotImplementedError):
+        SystemSpec.from_urdf(str(p))
+    elbow = open(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow.urdf')).read()
+    assert 'xyz="0 1 0"' in elbow
+    p2 = tmp_path / 'axis.urdf'
+    p2.write_text(elbow.replace('<axis xyz="0 1 0"', '<axis xyz="0 2 0"', 1))
+    spec = SystemSpec.from_urdf(str(p2))
+    assert spec.joints[0].axis == (0.0, 1.0, 0.0)
