@@ -18,6 +18,9 @@ namespace {
 constexpr int kLossThreads = 128;
 constexpr int kNAcc = 16;            // 14 parameter gradients + loss sum + pad
 constexpr int kMaxBlocks = 148 * 16; // upper bound used to size the workspace
+// workspace: [per-block partials kMaxBlocks x 32 doubles | 16 prepared parameters | chunk counter of the dynamic schedule]
+constexpr size_t kWsQueueOffset = ((size_t)kMaxBlocks * 32 + 16) * sizeof(double);
+constexpr size_t kWsQueueBytes = 2 * sizeof(unsigned long long);
 
 struct DeviceInfo { int sms; int device; };
 inline DeviceInfo device_info() {
@@ -159,9 +162,12 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
                     T eps, int64_t B, IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
                     T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag,
                     unsigned long long* __restrict__ dyn_counter, int64_t ldx, int64_t ldxp) {
-  // dyn_counter != nullptr (variant 2): warps take their triage chunks of 32 samples from a global counter instead
-  // of a static range -- removes the load imbalance between warps, but the assignment of samples to warps (and
-  // with it the rounding of the gradient sums) then depends on timing.
+  // dyn_counter != nullptr (DPLL_LOSS_DYNAMIC / variant 2): warps take their triage chunks of 32 samples from a
+  // global counter, in batch order, instead of a static range -- removes the load imbalance between warps and
+  // lets a cost-ordered batch start its longest solves first, but the assignment of samples to warps (and with it
+  // the rounding of the gradient sums) then depends on timing.  (Measured and dropped: a two-ended queue in which
+  // the second block of every SM consumes the batch from its cheap end, so that no two warps of long chains share
+  // an SM sub-partition -- 0.427 vs 0.398 ms at 1,048,576 pairs, 0.143 vs 0.129 ms at 131,072.)
   if (skip_flag && *skip_flag) return;
   extern __shared__ __align__(16) unsigned char wf_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -241,7 +247,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
       const unsigned m_q = __ballot_sync(0xffffffffu, queue);
       if (queue) pool->q_in[(h_in + n_in + __popc(m_q & lt_mask)) % kWfSlots] = (int32_t)(b - lo);
       n_in += __popc(m_q);
-      next = dyn_counter ? (cnt < 32 ? B : lo) : next + cnt;
+      next = dyn_counter ? (first >= B ? B : lo) : next + cnt;
 #ifndef CN_NO_PREFETCH
       if (!dyn_counter && next + lane < hi) {       // the rows of the next triage visit: pull them into L2
         const char* px = reinterpret_cast<const char*>(x + (next + lane) * ldx);
@@ -822,8 +828,8 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
     unsigned long long* dyn = nullptr;
     if (variant == 2) {
       if (!workspace || workspace_bytes < dpll_workspace_bytes()) return DPLL_EWORKSPACE;
-      dyn = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + dpll_workspace_bytes() - sizeof(double));
-      cudaError_t em = cudaMemsetAsync(dyn, 0, sizeof(unsigned long long), st);
+      dyn = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + kWsQueueOffset);
+      cudaError_t em = cudaMemsetAsync(dyn, 0, kWsQueueBytes, st);
       if (em != cudaSuccess) return (int)em;
     }
     // Up to ~320 samples per warp (crossover measured around 400) the launch is a few long Newton chains per warp: the
@@ -904,7 +910,7 @@ int dpll_set_loss_variant(int variant) {
 
 int dpll_version(void) { return DPLL_VERSION; }
 
-size_t dpll_workspace_bytes(void) { return ((size_t)kMaxBlocks * 32 + 16) * sizeof(double); }
+size_t dpll_workspace_bytes(void) { return kWsQueueOffset + kWsQueueBytes; }
 
 int dpll_cube_loss_f64(const double* x, const double* x_plus, const double* weight, const double* inertia,
                        const double* mu_pair, const double* half, double dt, double eps, int64_t B, double* loss,

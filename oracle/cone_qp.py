@@ -155,7 +155,10 @@ class OracleSAPSolver:
         self.nthreads = nthreads
         self.last_iters = None
 
-    def apply(self, J: Tensor, q: Tensor, eps: float) -> Tensor:
+    def apply(self, J: Tensor, q: Tensor, eps: float, return_primal: bool = False) -> Tensor:
+        """f (..., k), as sappy.  ``return_primal``: return the primal optimum w = J^T f (..., n_v) instead -- the
+        same differentiable Newton correction, for callers that evaluate M^-1 J^T f as L^-T w (the better
+        conditioned form of the same quantity: f = Pi(-(J w + q)/eps) amplifies rounding in w by 1/eps)."""
         batch = q.shape[:-1]
         k, nv = J.shape[-2], J.shape[-1]
         A = J.reshape((-1, k, nv))
@@ -175,6 +178,8 @@ class OracleSAPSolver:
             w = w0 - torch.linalg.solve(H, grad[..., None])[..., 0]
         else:
             w = w0
+        if return_primal:
+            return w.reshape(batch + (nv,))
         y = -((A @ w[..., None])[..., 0] + qq) / eps
         f = project_lorentz_sappy(y)
         return f.reshape(batch + (k,))

@@ -228,15 +228,29 @@ def contactnets_loss(calls: TreeCallables, params: OracleParams, x: Tensor, x_pl
     return (loss, f) if return_force else loss
 
 
+PRIMAL_UPDATE = False   # see forward_dynamics
+
+
 def forward_dynamics(calls: TreeCallables, params: OracleParams, q: Tensor, v: Tensor, dt: float,
                      solver: Optional[OracleSAPSolver] = None, return_force: bool = False):
-    """Next velocity (multibody_learnable_system.py:199-304; the 1e6 contact filter is a no-op)."""
+    """Next velocity (multibody_learnable_system.py:199-304; the 1e6 contact filter is a no-op).
+
+    ``PRIMAL_UPDATE`` (module switch, default off = the reference's form): evaluate the same update as
+    v- + L^-T w with w = A^T f the primal optimum of the QP (A = J L^-T, L L^T = M, so M^-1 J^T f = L^-T A^T f).
+    Identical in exact arithmetic; in floating point the reference's form loses ~cond(Q) eps ~ 1e-9 of the
+    DERIVATIVES (f = Pi(-(A w + q)/eps) amplifies the rounding of w by 1/eps = 1e4), which is the resolution limit
+    of any comparison against it.  Tests use the switch to show that a ~2e-9 disagreement with the reference
+    form is that rounding and not an error of the kernels."""
     solver = solver or OracleSAPSolver()
     M, J, phi, acc = multibody_terms(calls, params, q, v)
     n_c = phi.shape[-1]
     v_minus = v + dt * acc
     q_full = (J @ v_minus[..., None])[..., 0] + torch.cat((phi, torch.zeros_like(phi).repeat_interleave(2, -1)), -1) / dt
     A = _to_sappy(_whiten(M, J), n_c, -2)
+    if PRIMAL_UPDATE and not return_force:
+        w = solver.apply(A, _to_sappy(q_full, n_c, -1), STEP_EPS, return_primal=True)
+        L = torch.linalg.cholesky(M)
+        return v_minus + torch.linalg.solve_triangular(L.transpose(-1, -2), w[..., None], upper=True)[..., 0]
     f = _from_sappy(solver.apply(A, _to_sappy(q_full, n_c, -1), STEP_EPS), n_c)
     v_next = v_minus + torch.linalg.solve(M, (J.transpose(-1, -2) @ f[..., None]))[..., 0]
     return (v_next, f) if return_force else v_next
