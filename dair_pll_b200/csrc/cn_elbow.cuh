@@ -654,4 +654,82 @@ CN_HD int elbow_step_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, co
   return it;
 }
 
+// ---------------------------------------------------------------------------
+// Dense dynamics terms of the two-body system in the reference's own coordinates and ordering, for callers of
+// MultibodyTerms.forward (multibody_terms.py:584-609): M (7x7), J (24x7) = [J_n (8 rows) ; mu J_t (x,y interleaved
+// per contact, 16 rows)] (:401-426), phi (8), contact-free acceleration (7), Delassus operator D = J M^-1 J^T
+// (24x24).  Contacts: box 1 then box 2, each by ascending vertex index.  State velocity v = [w_body1 ; v_world ;
+// hinge rate] = T^T u^ with T = blkdiag(R1, I3, 1) (orthogonal), so M = T^T M^ T, J = J^ T, a = T^T a^.
+// ---------------------------------------------------------------------------
+template <typename T>
+CN_HD void elbow_terms_sample(const ElbowParams<T>& P, const T* q, const T* v, T* M, T* J, T* phi, T* acc, T* D) {
+  T store[ELBOW_PROB_FIELDS];
+  const ElbowProb<T> S{store, 1};
+  ElbowKin<T> K;
+  elbow_kinematics(P, q, K);
+  T vW[7], F[7], MW[49], LM[49], LMinv[7], aW[7];
+  elbow_to_world(K.R[0], v, vW);
+  elbow_mass_force(P, K, vW, MW, F, (T*)nullptr);
+  for (int i = 0; i < 49; ++i) LM[i] = MW[i];
+  chol_factor<T, 7>(LM, LMinv);
+  chol_solve<T, 7>(LM, LMinv, F, aW);
+  const T* R = K.R[0];
+  rot3t(R, aW, acc);
+  for (int i = 3; i < 7; ++i) acc[i] = aW[i];
+  // M = T^T M^ T: rotate the angular rows and columns into body-1 coordinates
+  T tmp[49];
+  for (int i = 0; i < 7; ++i) {                       // tmp = M^ T  (columns 0..2 rotated)
+    const T* row = MW + 7 * i;
+    for (int j = 0; j < 3; ++j) tmp[7 * i + j] = row[0] * R[j] + row[1] * R[3 + j] + row[2] * R[6 + j];
+    for (int j = 3; j < 7; ++j) tmp[7 * i + j] = row[j];
+  }
+  for (int j = 0; j < 7; ++j) {                       // M = T^T tmp  (rows 0..2 rotated)
+    for (int i = 0; i < 3; ++i) M[7 * i + j] = R[i] * tmp[j] + R[3 + i] * tmp[7 + j] + R[6 + i] * tmp[14 + j];
+    for (int i = 3; i < 7; ++i) M[7 * i + j] = tmp[7 * i + j];
+  }
+  elbow_contacts(P, K, S, (const T*)nullptr);
+  for (int c = 0; c < EL_NC; ++c) {
+    const T mu = P.mu[c >> 2];
+    const T rho[3] = {S.rho(3 * c), S.rho(3 * c + 1), S.rho(3 * c + 2)};
+    phi[c] = rho[2] + q[6];
+    // world rows of J^_c = [-S(rho), I3, h]; angular block in state coordinates: (-S(rho)) R1
+    T E[9];
+    for (int j = 0; j < 3; ++j) {
+      const T col[3] = {R[j], R[3 + j], R[6 + j]};
+      T cr[3];
+      cross3(rho, col, cr);
+      for (int i = 0; i < 3; ++i) E[3 * i + j] = -cr[i];
+    }
+    T* jn = J + 7 * c;
+    T* jx = J + 7 * (EL_NC + 2 * c);
+    T* jy = J + 7 * (EL_NC + 2 * c + 1);
+    for (int j = 0; j < 3; ++j) {
+      jn[j] = E[6 + j]; jx[j] = mu * E[j]; jy[j] = mu * E[3 + j];
+      jn[3 + j] = j == 2 ? T(1) : T(0);
+      jx[3 + j] = j == 0 ? mu : T(0);
+      jy[3 + j] = j == 1 ? mu : T(0);
+    }
+    jn[6] = S.hc(3 * c + 2); jx[6] = mu * S.hc(3 * c); jy[6] = mu * S.hc(3 * c + 1);
+  }
+  if (D) {
+    // D = J M^-1 J^T with M = L L^T (Cholesky of the state-coordinate M): W = L^-1 J^T, D = W^T W
+    T LS[49], LSinv[7], W[7 * EL_K];
+    for (int i = 0; i < 49; ++i) LS[i] = M[i];
+    chol_factor<T, 7>(LS, LSinv);
+    for (int r = 0; r < EL_K; ++r)
+      for (int i = 0; i < 7; ++i) {
+        T s = J[7 * r + i];
+        for (int m = 0; m < i; ++m) s -= LS[7 * i + m] * W[EL_K * m + r];
+        W[EL_K * i + r] = s * LSinv[i];
+      }
+    for (int a = 0; a < EL_K; ++a)
+      for (int b = 0; b <= a; ++b) {
+        T s = T(0);
+        for (int k = 0; k < 7; ++k) s += W[EL_K * k + a] * W[EL_K * k + b];
+        D[EL_K * a + b] = s;
+        D[EL_K * b + a] = s;
+      }
+  }
+}
+
 }  // namespace cn

@@ -700,6 +700,29 @@ elbow_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, 
   }
 }
 
+// Dense terms export for the two-body system (MultibodyTerms.forward, multibody_terms.py:584-609).  One sample per
+// thread; the 24x24 Delassus block makes it 6.9 KB written per sample -- an HBM-bound export for callers that ask
+// for the matrices (the loss / step kernels never form them).
+template <typename T, typename IO>
+__global__ void __launch_bounds__(64)
+elbow_terms_kernel(const IO* __restrict__ q, const IO* __restrict__ v, const IO* __restrict__ inertia,
+                   const IO* __restrict__ mu, const IO* __restrict__ half, const IO* __restrict__ kin, int64_t B,
+                   IO* __restrict__ M, IO* __restrict__ J, IO* __restrict__ phi, IO* __restrict__ acc, IO* __restrict__ D) {
+  cn::ElbowParams<T> P;
+  load_elbow_params<T, IO>(P, inertia, mu, half, kin, T(1), T(1));
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  T qs[8], vs[7], Mo[49], Jo[168], po[8], ao[7];
+  for (int i = 0; i < 8; ++i) qs[i] = T(q[b * 8 + i]);
+  for (int i = 0; i < 7; ++i) vs[i] = T(v[b * 7 + i]);
+  T* Do = D ? reinterpret_cast<T*>(D + b * 576) : (T*)nullptr;        // T == IO here: assembled in place
+  cn::elbow_terms_sample<T>(P, qs, vs, Mo, Jo, po, ao, Do);
+  for (int i = 0; i < 49; ++i) M[b * 49 + i] = IO(Mo[i]);
+  for (int i = 0; i < 168; ++i) J[b * 168 + i] = IO(Jo[i]);
+  for (int i = 0; i < 8; ++i) phi[b * 8 + i] = IO(po[i]);
+  for (int i = 0; i < 7; ++i) acc[b * 7 + i] = IO(ao[i]);
+}
+
 template <typename T, typename IO>
 int launch_elbow_loss(int variant, const IO* x, const IO* xp, const IO* weight, const IO* inertia, const IO* mu, const IO* half,
                       const IO* kin, const IO* pts, T dt, T eps, int64_t B, IO* loss, IO* force, IO* grad_pts,
@@ -996,6 +1019,19 @@ int dpll_cube_terms_f64(const double* q, const double* v, const double* inertia,
   const int blocks = (int)((B + kLossThreads - 1) / kLossThreads);
   cube_terms_kernel<double, double><<<blocks, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       q, v, inertia, mu_pair, half, B, M, J, phi, acc, delassus);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPLL_OK : (int)e;
+}
+
+int dpll_elbow_terms_f64(const double* q, const double* v, const double* inertia, const double* mu_pair,
+                         const double* half, const double* kin, int64_t B, double* M, double* J, double* phi, double* acc,
+                         double* delassus, void* stream) {
+  if (B < 0 || !inertia || !mu_pair || !half || !kin) return DPLL_EINVAL;
+  if (B > 0 && (!q || !v || !M || !J || !phi || !acc)) return DPLL_EINVAL;
+  if (B == 0) return DPLL_OK;
+  const int blocks = (int)((B + 63) / 64);
+  elbow_terms_kernel<double, double><<<blocks, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      q, v, inertia, mu_pair, half, kin, B, M, J, phi, acc, delassus);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPLL_OK : (int)e;
 }

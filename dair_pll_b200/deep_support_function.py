@@ -8,10 +8,8 @@ the hand-written Jacobian recursion of ``:238-266``.
 
 Device path: :class:`ICNNSupport` is a ``torch.autograd.Function`` with an explicit forward and
 backward.  The work is GEMM-shaped with weights shared by the whole batch -- two
-(D x W x W) products forward, two backward -- and runs on cuBLAS DGEMM through ``torch.matmul``;
+(D x W x W) products forward, one backward -- which run as FP64 library GEMMs between the fused layers;
 only the activation masks are kept between the passes (no autograd graph of elementwise ops).
-A hand-written FP64 GEMM for this layer is future work; FP64 tensor cores on B200
-have the same peak as the CUDA cores, so the library GEMM is already the right roofline.
 Mesh extraction (``extract_mesh`` / ``extract_obj``, :19-122) is logging/export code and stays
 with the reference.  Depth is fixed at 2 (the reference's default, ``geometry.py:50``).
 """
@@ -23,47 +21,37 @@ from torch import Tensor
 from torch.nn import Module, Parameter, ParameterList
 
 
+def icnn_weight_gradients(Wd1: Tensor, Wh: Tensor, wout: Tensor, g1: Tensor, gWd0: Tensor, G: Tensor):
+    """Chain rule from the three reductions the backward kernels produce -- g1 = gp^T m1 (3,W), gWd0 = gp^T a0 (3,W),
+    G = t^T m1 (W,W) with t = (gp Wd0) o m0 -- to the gradients of (Wd0, Wd1, Wh, wout).  p is linear in |w_out|_j
+    through column j of hj = |w_out| o m1 only, so d/d w_out needs no third (D x W x W) product."""
+    Wh_a, wo = Wh.abs(), wout.abs()
+    gwout = torch.sign(wout) * ((Wd1 * g1).sum(0) + (Wh_a * G).sum(0))
+    return gWd0, g1 * wo, torch.sign(Wh) * (G * wo), gwout
+
+
 class ICNNSupport(torch.autograd.Function):
-    """p (D,3) = d f / d direction for directions d (D,3); differentiable w.r.t. the four weights."""
+    """p (D,3) = d f / d direction for directions d (D,3); differentiable w.r.t. the four weights.  CUDA only:
+    the fused memory-bound layers of csrc/cn_icnn.cu around FP64 GEMMs (there is no CPU path)."""
 
     @staticmethod
     def forward(ctx, d, Wd0, Wd1, Wh, wout, slope):
         # deep_support_function.py:251-264 with hj = |w_out| * m1 folded into the small matrices, so the only
         # (D x width) intermediates are the two slope masks and a0
-        if d.is_cuda:
-            # fused memory-bound layers (csrc/cn_icnn.cu) around the FP64 GEMMs
-            from dair_pll_b200 import ops
-            p, h0aug, m1, a0 = ops.icnn_support_forward(d, Wd0, Wd1, Wh, wout, float(slope))
-            ctx.save_for_backward(Wd0, Wd1, Wh, wout, h0aug, m1, a0)
-            ctx.fused, ctx.slope = True, float(slope)
-            return p
-        ctx.fused = False
-        Wh_a, wo = Wh.abs(), wout.abs()
-        lin0 = d @ Wd0
-        m0 = torch.where(lin0 > 0, 1.0, slope).to(d.dtype)
-        lin1 = torch.addmm(d @ Wd1, lin0.mul_(m0), Wh_a)
-        m1 = torch.where(lin1 > 0, 1.0, slope).to(d.dtype)
-        a0 = (m1 @ (wo[:, None] * Wh_a.t())).mul_(m0)
-        p = torch.addmm(m1 @ (wo[:, None] * Wd1.t()), a0, Wd0.t())
-        ctx.save_for_backward(Wd0, Wd1, Wh, wout, m0, m1, a0)
+        if not d.is_cuda:
+            raise RuntimeError('dair_pll_b200 has no CPU path: support-function networks are evaluated on a CUDA device')
+        from dair_pll_b200 import ops
+        p, h0aug, m1, a0 = ops.icnn_support_forward(d, Wd0, Wd1, Wh, wout, float(slope))
+        ctx.save_for_backward(Wd0, Wd1, Wh, wout, h0aug, m1, a0)
+        ctx.slope = float(slope)
         return p
 
     @staticmethod
     def backward(ctx, gp):
-        Wd0, Wd1, Wh, wout, m0, m1, a0 = ctx.saved_tensors
-        gp = gp.contiguous()
-        Wh_a, wo = Wh.abs(), wout.abs()
-        if ctx.fused:
-            from dair_pll_b200 import ops
-            g1, gWd0, G = ops.icnn_support_backward(gp, m0, m1, a0, Wd0, ctx.slope)     # m0 slot holds h0aug
-        else:
-            g1 = gp.t() @ m1                          # (3, width): d/dW_d1 before the |w_out| column scale
-            gWd0 = gp.t() @ a0
-            t = (gp @ Wd0).mul_(m0)                   # adjoint of (hj |W_h|^T); the masks are constants
-            G = t.t() @ m1                            # (width, width): d/d|W_h| before the column scale
-        # p is linear in |w_out|_j through column j of hj only: no third (D x width x width) product
-        gwout = torch.sign(wout) * ((Wd1 * g1).sum(0) + (Wh_a * G).sum(0))
-        return None, gWd0, g1 * wo, torch.sign(Wh) * (G * wo), gwout, None
+        from dair_pll_b200 import ops
+        Wd0, Wd1, Wh, wout, h0aug, m1, a0 = ctx.saved_tensors
+        g1, gWd0, G = ops.icnn_support_backward(gp.contiguous(), h0aug, m1, a0, Wd0, ctx.slope)
+        return (None,) + icnn_weight_gradients(Wd1, Wh, wout, g1, gWd0, G) + (None,)
 
 
 class HomogeneousICNN(Module):
@@ -95,9 +83,8 @@ class HomogeneousICNN(Module):
 
     def forward(self, directions: Tensor) -> Tensor:
         shape = directions.shape
-        # CUDA tensors always take the kernel path (float64 arithmetic, as the fp32 variant of the loss kernels);
-        # CPU tensors run the same algebra in torch -- host mirror for CPU-only checks, never used by the CUDA path
-        dt = torch.float64 if directions.is_cuda else directions.dtype
+        # float64 arithmetic whatever the storage type (as the fp32 variant of the loss kernels)
+        dt = torch.float64
         p = ICNNSupport.apply(directions.reshape(-1, 3).to(dt), self.input_weights[0].to(dt), self.input_weights[1].to(dt),
                               self.hidden_weights[0].to(dt), self.output_weight.to(dt), self.negative_slope)
         return p.reshape(shape).to(directions.dtype)

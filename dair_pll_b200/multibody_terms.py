@@ -101,18 +101,29 @@ class MultibodyTerms(Module):
 
     def forward(self, q: Tensor, v: Tensor, u: Tensor = None):
         """(delassus, M, J, phi, non_contact_acceleration) as ``MultibodyTerms.forward`` of the reference
-        (multibody_terms.py:584-609), evaluated by the terms kernel (cube, float64, no autograd; contacts
-        ordered by box-vertex index).  The loss and step kernels do not go through these matrices."""
+        (multibody_terms.py:584-609), evaluated by the terms kernels (float64, no autograd; contacts
+        ordered by geometry, then box-vertex index).  The loss and step kernels do not go through these matrices."""
         from dair_pll_b200 import ops
         del u
-        if self.spec.kind != 'cube':
-            raise NotImplementedError('dense terms export is provided for the cube')
         batch = q.shape[:-1]
         inertia, mu, half = self.kernel_parameters(q.dtype)
-        D, M, J, phi, acc = ops.cube_terms(q.reshape(-1, 7), v.reshape(-1, 6), inertia.detach().reshape(10),
-                                           mu.detach().reshape(1), half[0].detach())
-        return (D.reshape(batch + (12, 12)), M.reshape(batch + (6, 6)), J.reshape(batch + (12, 6)),
-                phi.reshape(batch + (4,)), acc.reshape(batch + (6,)))
+        if self.spec.kind == 'cube':
+            D, M, J, phi, acc = ops.cube_terms(q.reshape(-1, 7), v.reshape(-1, 6), inertia.detach().reshape(10),
+                                               mu.detach().reshape(1), half[0].detach())
+        elif self.spec.kind == 'elbow':
+            if not half:
+                raise NotImplementedError('dense terms export is provided for box geometries (witness points of a '
+                                          'learned geometry come from the support-function networks)')
+            joint = self.spec.joints[0]
+            kin = torch.tensor([*joint.origin, *joint.axis, *self.spec.geometries[0].offset,
+                                *self.spec.geometries[1].offset], dtype=q.dtype, device=q.device)
+            D, M, J, phi, acc = ops.elbow_terms(q.reshape(-1, 8), v.reshape(-1, 7), inertia.detach().reshape(20),
+                                                mu.detach().reshape(2), torch.cat(half).detach(), kin)
+        else:
+            raise NotImplementedError(f'no kernel specialisation for system kind {self.spec.kind!r}')
+        n_v, k, n_c = M.shape[-1], J.shape[-2], phi.shape[-1]
+        return (D.reshape(batch + (k, k)), M.reshape(batch + (n_v, n_v)), J.reshape(batch + (k, n_v)),
+                phi.reshape(batch + (n_c,)), acc.reshape(batch + (n_v,)))
 
     def scalars_and_meshes(self):
         """Summary scalars per body (multibody_terms.py:536-582); no meshes for box geometries."""

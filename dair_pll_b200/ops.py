@@ -557,6 +557,27 @@ def cube_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Ten
     return D, M, J, phi, acc
 
 
+def elbow_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, kin: Tensor):
+    """``dpll_elbow_terms_f64``: (delassus (B,24,24), M (B,7,7), J (B,24,7), phi (B,8), acc (B,7)) in the order
+    ``MultibodyTerms.forward`` returns them (multibody_terms.py:584-609).  fp64 only, no autograd."""
+    _check_inputs(q, v, inertia, mu_pair, half, kin)
+    if q.dtype != torch.float64:
+        raise TypeError('elbow_terms is provided in float64')
+    q, v = q.contiguous(), v.contiguous()
+    B, dev = q.shape[0], q.device
+    M = torch.empty((B, 7, 7), dtype=q.dtype, device=dev)
+    J = torch.empty((B, 24, 7), dtype=q.dtype, device=dev)
+    phi = torch.empty((B, 8), dtype=q.dtype, device=dev)
+    acc = torch.empty((B, 7), dtype=q.dtype, device=dev)
+    D = torch.empty((B, 24, 24), dtype=q.dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().dpll_elbow_terms_f64(_ptr(q), _ptr(v), _ptr(inertia.contiguous()), _ptr(mu_pair.contiguous()),
+                                              _ptr(half.contiguous()), _ptr(kin.contiguous()), B, _ptr(M), _ptr(J),
+                                              _ptr(phi), _ptr(acc), _ptr(D), _stream())
+    _lib.check(rc, 'dpll_elbow_terms')
+    return D, M, J, phi, acc
+
+
 def icnn_support_forward(d: Tensor, Wd0: Tensor, Wd1: Tensor, Wh: Tensor, wout: Tensor, slope: float):
     """Support points p (D,3) of the depth-2 homogeneous ICNN for unit directions d (D,3), float64, CUDA:
     the ``dpll_icnn_*`` kernels around two FP64 GEMMs.  Returns (p, h0aug, m1, a0) -- the last three are what
@@ -592,7 +613,7 @@ def icnn_support_backward(gp: Tensor, h0aug: Tensor, m1: Tensor, a0: Tensor, Wd0
     dev = gp.device
     blocks = lib.dpll_icnn_backward_blocks(D)
     t = torch.empty((D, W), dtype=gp.dtype, device=dev)
-    part = torch.empty((blocks, 6, W), dtype=gp.dtype, device=dev)
+    part = torch.zeros((max(blocks, 1), 6, W), dtype=gp.dtype, device=dev)   # zeros: D == 0 launches nothing
     with torch.cuda.device(dev):
         _lib.check(lib.dpll_icnn_backward_f64(_ptr(gp), _ptr(h0aug), _ptr(m1), _ptr(a0), _ptr(Wd0), D, W, slope, _ptr(t),
                                               _ptr(part), _stream()), 'dpll_icnn_backward')

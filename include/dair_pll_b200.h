@@ -228,6 +228,15 @@ int dpll_cube_terms_f64(const double* q, const double* v, const double* inertia,
                         double* delassus, void* stream);
 
 /*
+ * The same export for the two-body (elbow) system with box geometries: q (B,8), v (B,7) -> M (B,7,7), J (B,24,7),
+ * phi (B,8), contact-free acceleration (B,7), delassus (B,24,24) (nullable).  Contacts of box 1 then box 2, each by
+ * ascending vertex index; J rows [normals (8) ; mu (x, y) interleaved per contact (16)].
+ */
+int dpll_elbow_terms_f64(const double* q, const double* v, const double* inertia, const double* mu_pair,
+                         const double* half, const double* kin, int64_t B, double* M, double* J, double* phi,
+                         double* acc, double* delassus, void* stream);
+
+/*
  * Backward of dpll_cube_rollout_f64 (the gradient the reference obtains by autograd through
  * forward_dynamics and sappy's backward, multibody_learnable_system.py:293-304; used by the
  * prediction loss, experiment.py:230-248, 292-320): given the upstream gradient xbar (B, steps, 13)

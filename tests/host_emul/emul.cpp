@@ -79,6 +79,14 @@ int emul_cube_terms_f64(const double* q, const double* v, const double* inertia,
     cube_terms_sample<double>(P, q + 7 * b, v + 6 * b, M + 36 * b, J + 72 * b, phi + 4 * b, acc + 6 * b, D + 144 * b);
   return 0;
 }
+int emul_elbow_terms_f64(const double* q, const double* v, const double* inertia, const double* mu, const double* half,
+                         const double* kin, int64_t B, double* M, double* J, double* phi, double* acc, double* D) {
+  ElbowParams<double> P;
+  elbow_params_init(P, inertia, mu, half, kin, 1.0, 1.0);
+  for (int64_t b = 0; b < B; ++b)
+    elbow_terms_sample<double>(P, q + 8 * b, v + 7 * b, M + 49 * b, J + 168 * b, phi + 8 * b, acc + 7 * b, D + 576 * b);
+  return 0;
+}
 // theta -> inertia vector and the reverse-direction product g^T J via dual numbers (as the reduce kernel does)
 int emul_theta_chain_f64(const double* theta, const double* g_inertia, double* inertia, double* grad_theta) {
   double th[10], out[10];

@@ -42,6 +42,7 @@ def _worker(rank, world, port, out):
     full.mean().backward()
     ref = [p.grad.clone() for p in s.parameters()]
     ref_mean = full.mean().item()
+    del full                                   # no autograd graph may outlive its step (CUDA graph capture below)
     lo, hi = parallel.shard_bounds(n, world, rank)
     s.data_parallel = comm
     params = list(s.parameters())
@@ -52,8 +53,8 @@ def _worker(rank, world, port, out):
         mean = s.contactnets_loss(x[lo:hi], None, xp[lo:hi]).mean()
         mean.backward()
         return mean
-    mean = step()
-    assert abs(mean.item() - ref_mean) <= 1e-13 * abs(ref_mean)
+    mean = step().item()
+    assert abs(mean - ref_mean) <= 1e-13 * abs(ref_mean)
     for p, r in zip(params, ref):
         assert torch.allclose(p.grad, r, rtol=1e-12, atol=1e-18)
     # general upstream gradient: summed over ranks by the stand-alone exchange
@@ -69,12 +70,13 @@ def _worker(rank, world, port, out):
     for a, p in zip(gw, params):
         assert torch.allclose(a, p.grad, rtol=1e-11, atol=1e-18)
     s.data_parallel = comm
+    torch.cuda.synchronize(dev)
     # (3) the whole step, exchange included, as ONE CUDA graph
     graphed = parallel.GraphedStep(step, dev)
     for _ in range(20):
         m = graphed()
     assert abs(m.item() - ref_mean) <= 1e-13 * abs(ref_mean)
-    flat = torch.cat([p.grad.reshape(-1) for p in params] + [m.reshape(1)]).cpu()
+    flat = torch.cat([p.grad.reshape(-1) for p in params] + [m.detach().reshape(1)]).cpu()
     gathered = [None] * world
     dist.all_gather_object(gathered, flat)
     assert all(torch.equal(g, gathered[0]) for g in gathered)      # identical bits on every rank

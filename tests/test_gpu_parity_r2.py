@@ -324,3 +324,32 @@ def test_device_dataset_matches_reference_fixture_on_the_gpu():
         total2 += loss.sum().item()
     assert abs(total - total2) <= 1e-12 * abs(total)
     assert all(torch.equal(c, c.sort(descending=True).values) for c in costs)
+
+
+@pytest.mark.parametrize('name', ['elbow_nominal', 'elbow_perturbed'])
+def test_elbow_dense_terms_match_oracle(name, assets_dir):
+    """MultibodyTerms.forward for the two-body system (multibody_terms.py:584-609; dpll_elbow_terms_f64): the
+    (delassus, M, J, phi, acceleration) tuple against the oracle's tree code at the golden states."""
+    from oracle import contactnets_oracle as co
+    from oracle.callables import ELBOW_TREE, TreeCallables
+    from tests.util import oracle_params_from_golden
+    g = load_golden(name)
+    s = MultibodyLearnableSystem({'elbow': os.path.join(assets_dir, 'elbow.urdf')}, float(g['dt']))
+    s.load_state_dict({
+        'multibody_terms.lagrangian_terms.inertial_parameters': torch.from_numpy(g['theta']),
+        'multibody_terms.contact_terms.friction_params': torch.from_numpy(g['friction_params']),
+        'multibody_terms.contact_terms.geometries.0.length_params': torch.from_numpy(g['half_lengths'][0]).reshape(1, 3),
+        'multibody_terms.contact_terms.geometries.1.length_params': torch.from_numpy(g['half_lengths'][1]).reshape(1, 3)})
+    s = s.to(DEV)
+    xp = torch.from_numpy(g['x_plus']).to(DEV)
+    D, M, J, phi, acc = s.multibody_terms(xp[:, :8], xp[:, 8:], None)
+    assert D.shape[1:] == (24, 24) and M.shape[1:] == (7, 7) and J.shape[1:] == (24, 7) and phi.shape[1:] == (8,)
+    P = oracle_params_from_golden(g, requires_grad=False)
+    with torch.no_grad():
+        Mo, Jo, phio, acco = co.multibody_terms(TreeCallables(ELBOW_TREE), P, xp.cpu()[:, :8], xp.cpu()[:, 8:])
+        Do = Jo @ torch.linalg.solve(Mo, Jo.transpose(-1, -2))
+    assert np.abs(M.cpu().numpy() - Mo.numpy()).max() < 1e-14 * max(1.0, np.abs(Mo.numpy()).max())
+    assert np.abs(J.cpu().numpy() - Jo.numpy()).max() < 1e-13
+    assert np.abs(phi.cpu().numpy() - phio.numpy()).max() < 1e-14
+    assert np.abs(acc.cpu().numpy() - acco.numpy()).max() < 1e-9 * max(1.0, np.abs(acco.numpy()).max())
+    assert np.abs(D.cpu().numpy() - Do.numpy()).max() < 1e-9 * np.abs(Do.numpy()).max()

@@ -291,3 +291,30 @@ def test_free_flight_fast_path_equals_the_generic_path():
                            ctypes.c_double(1e-3), ctypes.c_int64(n), dptr(l2), dptr(f2), dptr(i2), dptr(grad_g))
     assert np.abs(grad_f - grad_g).max() <= 1e-12 * np.abs(grad_g).max()
     assert np.abs(grad_g[11:]).max() > 0                  # the penetration term is exercised
+
+
+@pytest.mark.parametrize('name', ['elbow_nominal', 'elbow_perturbed'])
+def test_elbow_dense_terms_match_oracle(name):
+    """MultibodyTerms.forward for the two-body system (dpll_elbow_terms_f64's per-sample code): M, J, phi, the
+    contact-free acceleration and the Delassus operator against the oracle's tree code at the golden states."""
+    from oracle.callables import ELBOW_TREE
+    from tests.util import oracle_params_from_golden
+    g = load_golden(name)
+    lib = host_emulation_lib()
+    inertia, mu, half = elbow_kernel_level_params(g)
+    xp = g['x_plus']
+    B = xp.shape[0]
+    q, v = np.ascontiguousarray(xp[:, :8]), np.ascontiguousarray(xp[:, 8:])
+    M, J, phi = np.zeros((B, 7, 7)), np.zeros((B, 24, 7)), np.zeros((B, 8))
+    acc, D = np.zeros((B, 7)), np.zeros((B, 24, 24))
+    lib.emul_elbow_terms_f64(dptr(q), dptr(v), dptr(inertia), dptr(mu), dptr(half), dptr(ELBOW_KIN), ctypes.c_int64(B),
+                             dptr(M), dptr(J), dptr(phi), dptr(acc), dptr(D))
+    P = oracle_params_from_golden(g, requires_grad=False)
+    with torch.no_grad():
+        Mo, Jo, phio, acco = co.multibody_terms(TreeCallables(ELBOW_TREE), P, torch.from_numpy(q), torch.from_numpy(v))
+        Do = Jo @ torch.linalg.solve(Mo, Jo.transpose(-1, -2))
+    assert np.abs(M - Mo.numpy()).max() < 1e-14 * max(1.0, np.abs(Mo.numpy()).max())
+    assert np.abs(J - Jo.numpy()).max() < 1e-13
+    assert np.abs(phi - phio.numpy()).max() < 1e-14
+    assert np.abs(acc - acco.numpy()).max() < 1e-9 * max(1.0, np.abs(acco.numpy()).max())
+    assert np.abs(D - Do.numpy()).max() < 1e-9 * np.abs(Do.numpy()).max()

@@ -136,27 +136,35 @@ def test_device_slice_dataset_matches_reference_slicing(tmp_path):
         TrajectorySliceConfig(t_skip=0, t_history=2)
 
 
-def test_icnn_support_function_backward_matches_autograd_of_the_oracle():
-    """The product's explicit forward/backward of the support network (three width x width products, the output
-    weight's gradient from homogeneity) against autograd through the oracle restatement of
-    deep_support_function.py:238-266, for all four weights (signed weights, so |.| and sign() are exercised)."""
-    from dair_pll_b200.deep_support_function import ICNNSupport
+def test_icnn_weight_gradient_chain_rule_matches_autograd_of_the_oracle():
+    """The host half of the support network's backward (deep_support_function.icnn_weight_gradients: the chain rule
+    from the three reductions the backward kernels produce, the output weight's gradient from homogeneity) against
+    autograd through the oracle restatement of deep_support_function.py:238-266, for all four weights (signed
+    weights, so |.| and sign() are exercised).  The reductions themselves are formed here in torch -- on the GPU
+    they come from the dpll_icnn_* kernels (tests/test_gpu_parity.py)."""
+    from dair_pll_b200.deep_support_function import icnn_weight_gradients
     torch.manual_seed(3)
     W = 48
-    ws = [torch.randn(3, W, dtype=torch.float64), torch.randn(3, W, dtype=torch.float64),
-          torch.randn(W, W, dtype=torch.float64) / W, torch.randn(W, dtype=torch.float64)]
+    Wd0, Wd1, Wh, wout = (torch.randn(3, W, dtype=torch.float64), torch.randn(3, W, dtype=torch.float64),
+                          torch.randn(W, W, dtype=torch.float64) / W, torch.randn(W, dtype=torch.float64))
     d = torch.randn(301, 3, dtype=torch.float64)
     d = d / d.norm(dim=-1, keepdim=True)
     gp = torch.randn(301, 3, dtype=torch.float64)
-    a = [w.clone().requires_grad_() for w in ws]
-    p = ICNNSupport.apply(d, a[0], a[1], a[2], a[3], 0.5)
-    (p * gp).sum().backward()
-    b = [w.clone().requires_grad_() for w in ws]
+    # what the kernels hand over (SURVEY.md A.6)
+    lin0 = d @ Wd0
+    m0 = torch.where(lin0 > 0, 1.0, 0.5).double()
+    m1 = torch.where((lin0 * m0) @ Wh.abs() + d @ Wd1 > 0, 1.0, 0.5).double()
+    a0 = (m1 @ (wout.abs()[:, None] * Wh.abs().t())) * m0
+    g1, gWd0, G = gp.t() @ m1, gp.t() @ a0, ((gp @ Wd0) * m0).t() @ m1
+    got = icnn_weight_gradients(Wd1, Wh, wout, g1, gWd0, G)
+    b = [w.clone().requires_grad_() for w in (Wd0, Wd1, Wh, wout)]
     po = co.icnn_support(dict(Wd0=b[0], Wd1=b[1], Wh=b[2], wout=b[3]), d)
     (po * gp).sum().backward()
-    assert torch.allclose(p, po, rtol=1e-12, atol=1e-13)
-    for x, y in zip(a, b):
-        assert torch.allclose(x.grad, y.grad, rtol=1e-10, atol=1e-12)
+    for x, y in zip(got, b):
+        assert torch.allclose(x, y.grad, rtol=1e-10, atol=1e-12)
+    with pytest.raises(RuntimeError):                 # the product has no CPU path
+        from dair_pll_b200.deep_support_function import ICNNSupport
+        ICNNSupport.apply(d, Wd0, Wd1, Wh, wout, 0.5)
 
 
 @pytest.mark.parametrize('asset', ['cube.urdf', 'elbow.urdf'])
