@@ -472,7 +472,7 @@ template <typename T, typename IO>
 __global__ void __launch_bounds__(kLossThreads)
 cube_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, const IO* __restrict__ mu,
                     const IO* __restrict__ half, T dt, T eps, int64_t B, int steps, IO* __restrict__ traj,
-                    IO* __restrict__ force, int32_t* __restrict__ iters, int lanes_per_warp) {
+                    IO* __restrict__ force, int32_t* __restrict__ iters, int lanes_per_warp, IO* __restrict__ usol) {
   // A toss is a sequential chain of `steps` solves whose lengths differ per toss, and a warp advances
   // at the pace of its slowest lane: small batches are therefore spread thinly (lanes_per_warp < 32
   // tosses per warp) so that every SM sub-partition holds warps and each waits for few neighbours.
@@ -492,6 +492,10 @@ cube_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, c
     T warm[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
     for (int s = 0; s < steps; ++s) {
       total += cn::cube_step_sample<T>(P, cfg, xc, xn, force ? fo : nullptr, warm);
+      if (usol) {                      // the step's QP optimum, for the reverse-mode backward (cn_cube_adjoint.cuh)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) usol[(b * steps + s) * 6 + i] = IO(warm[i]);
+      }
       if (force) {
 #pragma unroll
         for (int i = 0; i < 12; ++i) force[(b * steps + s) * 12 + i] = IO(fo[i]);
@@ -895,7 +899,7 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
 
 template <typename T, typename IO>
 int launch_cube_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO* half, T dt, T eps, int64_t B,
-                        int32_t steps, IO* traj, IO* force, int32_t* iters, void* stream) {
+                        int32_t steps, IO* traj, IO* force, int32_t* iters, void* stream, IO* usol = nullptr) {
   if (B < 0 || steps < 0 || !inertia || !mu || !half) return DPLL_EINVAL;
   if (B > 0 && (!x0 || !traj)) return DPLL_EINVAL;
   if (B == 0) return DPLL_OK;
@@ -913,7 +917,7 @@ int launch_cube_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO*
   const int64_t need = (B + per_block - 1) / per_block;
   const int blocks = (int)(need < cap ? need : cap);
   cube_rollout_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x0, inertia, mu, half, dt, eps, B, steps, traj, force,
-                                                          iters, lpw);
+                                                          iters, lpw, usol);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPLL_OK : (int)e;
 }
@@ -1001,6 +1005,14 @@ int dpll_cube_rollout_f64(const double* x0, const double* inertia, const double*
                           double dt, double eps, int64_t B, int32_t steps, double* traj, double* force,
                           int32_t* iters, void* stream) {
   return launch_cube_rollout<double, double>(x0, inertia, mu_pair, half, dt, eps, B, steps, traj, force, iters, stream);
+}
+
+int dpll_cube_rollout_saved_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,
+                                double dt, double eps, int64_t B, int32_t steps, double* traj, double* usol,
+                                void* stream) {
+  if (B > 0 && steps > 0 && !usol) return DPLL_EINVAL;
+  return launch_cube_rollout<double, double>(x0, inertia, mu_pair, half, dt, eps, B, steps, traj, nullptr, nullptr, stream,
+                                             usol);
 }
 
 int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu_pair, const float* half, float dt,

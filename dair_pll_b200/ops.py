@@ -471,21 +471,32 @@ def elbow_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Optional[T
 
 class CubeRollout(torch.autograd.Function):
     """Differentiable rollout of the learnable cube system: traj (B, steps+1, 13) from x0 (B, 13).
-    Backward = ``dpll_cube_rollout_grad_f64`` (forward-mode tangents of every step, exact implicit
-    differentiation of the QP), giving gradients w.r.t. the callable-level parameters and x0 -- what the
-    reference gets from autograd through ``forward_dynamics`` and sappy's backward
-    (multibody_learnable_system.py:293-304) for the prediction loss (experiment.py:230-248)."""
+    Forward = ``dpll_cube_rollout_saved_f64`` (keeps every step's QP optimum); backward =
+    ``dpll_cube_rollout_backward_f64``, the reverse-mode adjoint: one 6x6 SPD solve per step (implicit
+    differentiation of the QP) walking each trajectory backwards -- gradients w.r.t. the callable-level parameters
+    and x0, what the reference gets from autograd through ``forward_dynamics`` and sappy's backward
+    (multibody_learnable_system.py:293-304) for the prediction loss (experiment.py:230-248).  ``forward_mode=True``
+    selects the dual-number backward ``dpll_cube_rollout_grad_f64`` instead (27 tangent rollouts per toss; the
+    independent check of the adjoint)."""
 
     @staticmethod
-    def forward(ctx, x0, inertia, mu_pair, half, dt, steps, eps):
-        traj, _ = cube_rollout(x0, inertia, mu_pair, half, dt, steps, eps)
-        ctx.dt, ctx.steps, ctx.eps = dt, steps, eps
-        ctx.save_for_backward(x0, inertia, mu_pair, half)
-        return traj
+    def forward(ctx, x0, inertia, mu_pair, half, dt, steps, eps, forward_mode=False):
+        f64 = torch.float64
+        B = x0.shape[0]
+        a = [t.detach().to(f64).contiguous() for t in (x0, inertia, mu_pair, half)]
+        traj = torch.empty((B, steps + 1, 13), dtype=f64, device=x0.device)
+        usol = torch.empty((B, steps, 6), dtype=f64, device=x0.device)
+        with torch.cuda.device(x0.device):
+            rc = _lib.load().dpll_cube_rollout_saved_f64(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), dt, eps, B, steps,
+                                                         _ptr(traj), _ptr(usol), _stream())
+        _lib.check(rc, 'dpll_cube_rollout_saved')
+        ctx.dt, ctx.steps, ctx.eps, ctx.forward_mode = dt, steps, eps, forward_mode
+        ctx.save_for_backward(x0, inertia, mu_pair, half, traj, usol)
+        return traj.to(x0.dtype)
 
     @staticmethod
     def backward(ctx, gtraj):
-        x0, inertia, mu_pair, half = ctx.saved_tensors
+        x0, inertia, mu_pair, half, traj, usol = ctx.saved_tensors
         B, steps = x0.shape[0], ctx.steps
         f64 = torch.float64
         xbar = gtraj[:, 1:, :].to(f64).contiguous()
@@ -493,15 +504,21 @@ class CubeRollout(torch.autograd.Function):
         gx0 = torch.zeros((B, 13), dtype=f64, device=x0.device)
         if B > 0 and steps > 0:
             args = [t.detach().to(f64).contiguous() for t in (x0, inertia, mu_pair, half)]
+            lib = _lib.load()
             with torch.cuda.device(x0.device):
-                rc = _lib.load().dpll_cube_rollout_grad_f64(_ptr(args[0]), _ptr(args[1]), _ptr(args[2]), _ptr(args[3]),
-                                                            ctx.dt, ctx.eps, B, steps, _ptr(xbar), _ptr(gparams),
-                                                            _ptr(gx0), _stream())
-            _lib.check(rc, 'dpll_cube_rollout_grad')
+                if ctx.forward_mode:
+                    rc = lib.dpll_cube_rollout_grad_f64(_ptr(args[0]), _ptr(args[1]), _ptr(args[2]), _ptr(args[3]),
+                                                        ctx.dt, ctx.eps, B, steps, _ptr(xbar), _ptr(gparams), _ptr(gx0),
+                                                        _stream())
+                else:
+                    rc = lib.dpll_cube_rollout_backward_f64(_ptr(traj), _ptr(usol), _ptr(args[1]), _ptr(args[2]),
+                                                            _ptr(args[3]), ctx.dt, ctx.eps, B, steps, _ptr(xbar),
+                                                            _ptr(gparams), _ptr(gx0), _stream())
+            _lib.check(rc, 'dpll_cube_rollout_backward')
         g = gparams.sum(0)
         gx = (gx0 + gtraj[:, 0, :].to(f64)).to(x0.dtype)
         return (gx, g[0:10].reshape(inertia.shape).to(inertia.dtype), g[10:11].reshape(mu_pair.shape).to(mu_pair.dtype),
-                g[11:14].reshape(half.shape).to(half.dtype), None, None, None)
+                g[11:14].reshape(half.shape).to(half.dtype), None, None, None, None)
 
 
 class ElbowRollout(torch.autograd.Function):

@@ -251,6 +251,26 @@ int dpll_cube_rollout_grad_f64(const double* x0, const double* inertia, const do
                                const double* xbar, double* gparams, double* gx0, void* stream);
 
 /*
+ * Reverse-mode form of the same backward ("adjoint solve n_v x n_v"): the forward rollout keeps every
+ * step's QP optimum,
+ *   dpll_cube_rollout_saved_f64   as dpll_cube_rollout_f64, plus usol (B, steps, 6): the optimum u* of every step's
+ *                                 cone QP (world-frame twist; v+ = v- + u*)
+ * and the backward walks each trajectory once, last step first: per step one evaluation of the Newton Hessian at
+ * u*, ONE 6x6 SPD (Cholesky) solve -- implicit differentiation of the QP -- and the hand-derived adjoints of the
+ * step's remaining lines (csrc/cn_cube_adjoint.cuh).
+ *   dpll_cube_rollout_backward_f64   traj (B, steps+1, 13), usol (B, steps, 6), xbar (B, steps, 13) w.r.t. traj[:, 1:]
+ *                                    -> gparams (B, 14), gx0 (B, 13), exactly as dpll_cube_rollout_grad_f64
+ * About the arithmetic of three Newton visits per step instead of 27 dual-number rollouts; agrees with the
+ * forward-mode entry point to 1e-10 (tests), which is kept as the independent check.
+ */
+int dpll_cube_rollout_saved_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,
+                                double dt, double eps, int64_t B, int32_t steps, double* traj, double* usol,
+                                void* stream);
+int dpll_cube_rollout_backward_f64(const double* traj, const double* usol, const double* inertia,
+                                   const double* mu_pair, const double* half, double dt, double eps, int64_t B,
+                                   int32_t steps, const double* xbar, double* gparams, double* gx0, void* stream);
+
+/*
  * The same backward for the two-body (elbow) system with box geometries: gparams (B, 28) =
  * [d/d inertia (20) | d/d mu_pair (2) | d/d half (6)], gx0 (B, 15).  43 tangent directions per toss.
  */

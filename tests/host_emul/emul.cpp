@@ -5,6 +5,8 @@
 #include "../../dair_pll_b200/csrc/cn_elbow.cuh"
 #include "../../dair_pll_b200/csrc/cn_cube_tangent.cuh"
 #include "../../dair_pll_b200/csrc/cn_elbow_tangent.cuh"
+#include "../../dair_pll_b200/csrc/cn_cube_adjoint.cuh"
+#include <vector>
 #include <cstdint>
 using namespace cn;
 extern "C" {
@@ -139,6 +141,28 @@ int emul_cube_rollout_grad_f64(const double* x0, const double* inertia, const do
                                                     xbar + (int64_t)b * steps * 13, dir);
       if (dir < 14) gparams[14 * b + dir] = g; else gx0[13 * b + dir - 14] = g;
     }
+  return 0;
+}
+// reverse-mode rollout backward (cn_cube_adjoint.cuh): forward rollout keeping the states and the QP optima, then the
+// adjoint sweep; same outputs as emul_cube_rollout_grad_f64
+int emul_cube_rollout_backward_f64(const double* x0, const double* inertia, const double* mu, const double* half,
+                                   double dt, double eps, int64_t B, int steps, const double* xbar, double* gparams,
+                                   double* gx0) {
+  CubeParams<double> P;
+  cube_params_init(P, inertia, mu, half, dt, eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  // (the plain forward solve: its optima are converged to rounding, measured: no difference with a polishing step)
+  std::vector<double> traj((steps + 1) * 13), usol(steps * 6);
+  for (int64_t b = 0; b < B; ++b) {
+    for (int i = 0; i < 13; ++i) traj[i] = x0[13 * b + i];
+    double warm[6] = {0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < steps; ++s) {
+      cube_step_sample<double>(P, cfg, &traj[13 * s], &traj[13 * (s + 1)], (double*)nullptr, warm);
+      for (int i = 0; i < 6; ++i) usol[6 * s + i] = warm[i];
+    }
+    cube_rollout_backward_sample<double>(P, traj.data(), usol.data(), xbar + (int64_t)b * steps * 13, steps,
+                                         gparams + 14 * b, gx0 + 13 * b);
+  }
   return 0;
 }
 int emul_elbow_rollout_grad_f64(const double* x0, const double* inertia, const double* mu, const double* half,

@@ -353,3 +353,35 @@ def test_elbow_dense_terms_match_oracle(name, assets_dir):
     assert np.abs(phi.cpu().numpy() - phio.numpy()).max() < 1e-14
     assert np.abs(acc.cpu().numpy() - acco.numpy()).max() < 1e-9 * max(1.0, np.abs(acco.numpy()).max())
     assert np.abs(D.cpu().numpy() - Do.numpy()).max() < 1e-9 * np.abs(Do.numpy()).max()
+
+
+def test_reverse_mode_rollout_backward_matches_forward_mode(assets_dir):
+    """K7: dpll_cube_rollout_backward_f64 (reverse-mode adjoint, one 6x6 solve per step) against
+    dpll_cube_rollout_grad_f64 (27 dual-number rollouts per toss) through the autograd Function, 256 tosses x 24
+    steps from the example's initial-condition sampler: every gradient to 1e-10; and the module API
+    (``simulate`` under autograd) uses the reverse-mode path."""
+    g = load_golden('cube_real_perturbed')
+    inertia, mu, half = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    n, steps = 256, 24
+    gen = torch.Generator().manual_seed(3)
+    x0 = torch.tensor([1., 0., 0., 0., 0., 0., 0.12, 0., 0., 0., 0., 0., -.4], dtype=torch.float64).repeat(n, 1)
+    x0[:, 7:] += (2 * torch.rand(n, 6, generator=gen, dtype=torch.float64) - 1) * torch.tensor([3., 3, 3, 1, 1, 1])
+    quat = x0[:, :4] + 0.3 * torch.randn(n, 4, generator=gen, dtype=torch.float64)
+    x0[:, :4] = quat / quat.norm(dim=-1, keepdim=True)
+    w = torch.randn(n, steps + 1, 13, generator=gen, dtype=torch.float64).to(DEV)
+    grads = []
+    for forward_mode in (True, False):
+        leaves = [t.clone().requires_grad_() for t in (x0.to(DEV), inertia, mu, half)]
+        traj = ops.CubeRollout.apply(leaves[0], leaves[1], leaves[2], leaves[3], DT, steps, 1e-4, forward_mode)
+        (traj * w).sum().backward()
+        grads.append([t.grad.cpu().numpy() for t in leaves])
+        assert (traj[:, -1, 6] < 0.11).any()                      # tosses reach the ground within the horizon
+    for a, b in zip(grads[1], grads[0]):
+        assert max_rel_to_scale(a, b) < 1e-10
+    s = MultibodyLearnableSystem({'cube': os.path.join(assets_dir, 'cube.urdf')}, DT).to(DEV)
+    xs = x0[:32].to(DEV).requires_grad_()
+    traj, _ = s.simulate(xs.unsqueeze(-2), torch.zeros(32, 1, device=DEV), 6)
+    assert traj.grad_fn is not None and 'CubeRollout' in type(traj.grad_fn).__name__
+    traj.sum().backward()
+    assert xs.grad is not None and torch.isfinite(xs.grad).all()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in s.parameters())

@@ -318,3 +318,30 @@ def test_elbow_dense_terms_match_oracle(name):
     assert np.abs(phi - phio.numpy()).max() < 1e-14
     assert np.abs(acc - acco.numpy()).max() < 1e-9 * max(1.0, np.abs(acco.numpy()).max())
     assert np.abs(D - Do.numpy()).max() < 1e-9 * np.abs(Do.numpy()).max()
+
+
+@pytest.mark.parametrize('steps', [1, 12])
+def test_reverse_mode_step_adjoint_matches_forward_mode_tangents(steps):
+    """K7 (cn_cube_adjoint.cuh): the hand-derived reverse-mode backward of the learnable step -- implicit
+    differentiation of the QP by one 6x6 Cholesky solve per step plus the adjoints of the step's other lines --
+    against the dual-number tangents of the same step code (27 forward-mode rollouts per toss), on real tosses
+    in and around contact: parameter and initial-state gradients to 1e-10."""
+    lib = host_emulation_lib()
+    g = load_golden('cube_real_perturbed')
+    inertia, mu, half = kernel_level_params(g)
+    x0 = np.ascontiguousarray(g['sim_x0'])
+    n = x0.shape[0]
+    xbar = np.random.default_rng(steps).standard_normal((n, steps, 13))
+    out = []
+    for fn in (lib.emul_cube_rollout_grad_f64, lib.emul_cube_rollout_backward_f64):
+        gp, gx = np.zeros((n, 14)), np.zeros((n, 13))
+        fn(dptr(x0), dptr(inertia), dptr(mu), dptr(half), ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-4),
+           ctypes.c_int64(n), ctypes.c_int(steps), dptr(xbar), dptr(gp), dptr(gx))
+        out.append((gp, gx))
+    (gp_f, gx_f), (gp_r, gx_r) = out
+    assert np.abs(gp_f).max() > 0 and np.abs(gx_f).max() > 0
+    for a, b in ((gp_r, gp_f), (gx_r, gx_f)):
+        per_sample = np.abs(a - b).max(1) / np.maximum(np.abs(b).max(1), 1e-300)
+        assert per_sample.max() < 1e-9                            # every toss on its own
+    assert max_rel_to_scale(gp_r.sum(0), gp_f.sum(0)) < 1e-10     # the parameter gradient of the batch
+    assert max_rel_to_scale(gx_r, gx_f) < 1e-10
