@@ -13,6 +13,13 @@
 #include "cn_elbow.cuh"
 #include "cn_comm.cuh"
 
+// wavefront kernel of the two-body system (cn_elbow_wf.cu)
+template <typename T, typename IO>
+int launch_elbow_loss_wf(const IO* x, const IO* xp, const IO* weight, const IO* inertia, const IO* mu, const IO* half,
+                         const IO* kin, const IO* pts, T dt, T eps, int64_t B, IO* loss, IO* force, IO* grad_pts,
+                         int32_t* iters, T* partials, int want_grad, const int32_t* skip_flag, int sms, cudaStream_t st,
+                         int* err);
+
 namespace {
 
 constexpr int kLossThreads = 128;
@@ -738,26 +745,36 @@ int launch_elbow_loss(int variant, const IO* x, const IO* xp, const IO* weight, 
   if (want_red && (!workspace || workspace_bytes < dpll_workspace_bytes())) return DPLL_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DeviceInfo di = device_info();
-  const bool two_phase = variant != 1;            // 1 = one sample per thread (A/B measurements)
-  int per_sm = 0;
-  if (two_phase) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, elbow_loss_2p_kernel<T, IO>, kLossThreads, 0);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, elbow_loss_kernel<T, IO>, kLossThreads, 0);
-  if (per_sm < 1) per_sm = 1;
-  // two-phase: a warp wants a few solve passes' worth of samples (>= 128) to fill its lanes
-  const int64_t per_block = two_phase ? (int64_t)(kLossThreads / 32) * 128 : kLossThreads;
-  int64_t need = (B + per_block - 1) / per_block;
-  int64_t cap = (int64_t)di.sms * per_sm;
-  if (cap > kMaxBlocks) cap = kMaxBlocks;
-  int blocks = (int)(need < cap ? need : cap);
-  if (blocks < 1) blocks = 1;
   T* partials = want_red ? static_cast<T*>(workspace) : nullptr;
-  if (two_phase)
-    elbow_loss_2p_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, kin, pts, dt, eps, B,
-                                                                loss, force, grad_pts, iters, partials, grad ? 1 : 0,
-                                                                skip_flag);
-  else
-    elbow_loss_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, kin, pts, dt, eps, B, loss,
-                                                             force, grad_pts, iters, partials, grad ? 1 : 0, skip_flag);
+  int blocks;
+  if (variant == 0) {
+    // wavefront kernel (default): per-visit scheduling over shared-memory records
+    int err = DPLL_OK;
+    blocks = ::launch_elbow_loss_wf<T, IO>(x, xp, weight, inertia, mu, half, kin, pts, dt, eps, B, loss, force, grad_pts,
+                                         iters, partials, grad ? 1 : 0, skip_flag, di.sms, st, &err);
+    if (err != DPLL_OK) return err;
+  } else {
+    const bool two_phase = variant != 1;          // 1 = one sample per thread, 2 = triage / solve passes (A/B measurements)
+    int per_sm = 0;
+    if (two_phase) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, elbow_loss_2p_kernel<T, IO>, kLossThreads, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, elbow_loss_kernel<T, IO>, kLossThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    // two-phase: a warp wants a few solve passes' worth of samples (>= 128) to fill its lanes
+    const int64_t per_block = two_phase ? (int64_t)(kLossThreads / 32) * 128 : kLossThreads;
+    int64_t need = (B + per_block - 1) / per_block;
+    int64_t cap = (int64_t)di.sms * per_sm;
+    if (cap > kMaxBlocks) cap = kMaxBlocks;
+    blocks = (int)(need < cap ? need : cap);
+    if (blocks < 1) blocks = 1;
+    if (two_phase)
+      elbow_loss_2p_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, kin, pts, dt, eps, B,
+                                                                  loss, force, grad_pts, iters, partials, grad ? 1 : 0,
+                                                                  skip_flag);
+    else
+      elbow_loss_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x, xp, weight, inertia, mu, half, kin, pts, dt, eps, B,
+                                                               loss, force, grad_pts, iters, partials, grad ? 1 : 0,
+                                                               skip_flag);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (want_red) {

@@ -133,7 +133,10 @@ class MultibodyLearnableSystem(System):
                 pts = self._elbow_witness_points(xpf[:, :8])
                 loss = ops.ElbowContactNetsLossPts.apply(xf, xpf, inertia, mu, pts, kin, float(self.dt), LOSS_EPS)
             else:
-                loss = ops.ElbowContactNetsLoss.apply(xf, xpf, inertia, mu, half, kin, float(self.dt), LOSS_EPS)
+                loss, sums, means = ops.ElbowContactNetsLoss.apply(xf, xpf, inertia, mu, half, kin, float(self.dt),
+                                                                   LOSS_EPS)
+                # mean() / sum() of the result reuse the launch's own reduction and fused gradient (ops.BatchLoss)
+                return ops.batch_loss(loss.reshape(batch), sums, means, 28, (inertia, mu, half))
         else:
             raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r}')
         return loss.reshape(batch)

@@ -378,20 +378,26 @@ def elbow_loss_raw(x: Tensor, x_plus: Tensor, inertia: Tensor, mu_pair: Tensor, 
 class ElbowContactNetsLoss(torch.autograd.Function):
     """ContactNets loss of the elbow (floating base + hinge, two boxes); differentiable w.r.t. the
     callable-level parameters (two inertia 10-vectors, two pair frictions, two half-length triples).
-    Same fused-backward protocol as :class:`CubeContactNetsLoss`."""
+    Same fused-backward protocol as :class:`CubeContactNetsLoss`; also returns the launch's
+    [gradient (28) | loss] sums and means for :class:`BatchLoss`."""
 
     @staticmethod
     def forward(ctx, x, x_plus, inertia, mu_pair, half, kin, dt, eps):
         need = any(ctx.needs_input_grad[2:5])
-        loss, grad, _, _, _ = elbow_loss_raw(x, x_plus, inertia, mu_pair, half, kin, dt, eps, want_grad=need)
+        loss, grad, loss_sum, _, _ = elbow_loss_raw(x, x_plus, inertia, mu_pair, half, kin, dt, eps, want_grad=need)
         ctx.dt, ctx.eps = dt, eps
         ctx.shapes = (inertia.shape, mu_pair.shape, half.shape)
         if need:
             ctx.save_for_backward(grad, x, x_plus, inertia, mu_pair, half, kin)
-        return loss
+        else:
+            grad = torch.zeros(28, dtype=loss.dtype, device=loss.device)
+        sums = torch.cat((grad, loss_sum))
+        means = sums / max(loss.numel(), 1) if loss.numel() > 0 else sums * float('nan')
+        ctx.mark_non_differentiable(sums, means)
+        return loss, sums, means
 
     @staticmethod
-    def backward(ctx, grad_loss):
+    def backward(ctx, grad_loss, _g_sums, _g_means):
         grad, x, x_plus, inertia, mu_pair, half, kin = ctx.saved_tensors
         if grad_loss.numel() == 0:
             g = torch.zeros_like(grad)

@@ -6,6 +6,7 @@
 #include "../../dair_pll_b200/csrc/cn_cube_tangent.cuh"
 #include "../../dair_pll_b200/csrc/cn_elbow_tangent.cuh"
 #include "../../dair_pll_b200/csrc/cn_cube_adjoint.cuh"
+#include "../../dair_pll_b200/csrc/cn_elbow_wf.cuh"
 #include <vector>
 #include <cstdint>
 using namespace cn;
@@ -116,6 +117,23 @@ int emul_elbow_loss_f64(const double* x, const double* xp, const double* inertia
     int it;
     loss[b] = elbow_loss_sample(P, cfg, x + 15 * b, xp + 15 * b, (const double*)nullptr, grad,
                                 force ? force + 24 * b : nullptr, (double*)nullptr, &it);
+    if (iters) iters[b] = it;
+  }
+  return 0;
+}
+// the closed-form (composite body + hinge column) formulation the wavefront kernel runs (cn_elbow_wf.cuh)
+int emul_elbow_loss_wf_f64(const double* x, const double* xp, const double* inertia, const double* mu,
+                           const double* half, const double* kin, const double* pts, double dt, double eps, int64_t B,
+                           double* loss, double* force, int32_t* iters, double* grad, double* grad_pts) {
+  ElbowParams<double> P;
+  double h0[6] = {0, 0, 0, 0, 0, 0};
+  elbow_params_init(P, inertia, mu, half ? half : h0, kin, dt, eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  for (int i = 0; i < EL_NPARAM; ++i) if (grad) grad[i] = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    int it;
+    loss[b] = elbow_loss_sample_wf<double>(P, cfg, x + 15 * b, xp + 15 * b, pts ? pts + 24 * b : nullptr, grad,
+                                           force ? force + 24 * b : nullptr, grad_pts ? grad_pts + 24 * b : nullptr, &it);
     if (iters) iters[b] = it;
   }
   return 0;
