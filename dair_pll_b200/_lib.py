@@ -36,6 +36,8 @@ EXPORTS = {
     'dpll_elbow_rollout_grad_f64': ([_c_void_p] * 5 + [_f64, _f64, _i64, _i32] + [_c_void_p] * 4, ctypes.c_int),
     'dpll_elbow_loss_f64': ([_c_void_p] * 8 + [_f64, _f64, _i64] + [_c_void_p] * 7 + [_c_void_p, _sz, _c_void_p], ctypes.c_int),
     'dpll_elbow_loss_f32': ([_c_void_p] * 8 + [_f32, _f32, _i64] + [_c_void_p] * 7 + [_c_void_p, _sz, _c_void_p], ctypes.c_int),
+    'dpll_elbow_loss_ex_f64': ([_c_void_p] * 8 + [_f64, _f64, _i64, _i32] + [_c_void_p] * 7 + [_c_void_p, _sz, _c_void_p], ctypes.c_int),
+    'dpll_elbow_loss_ex_f32': ([_c_void_p] * 8 + [_f32, _f32, _i64, _i32] + [_c_void_p] * 7 + [_c_void_p, _sz, _c_void_p], ctypes.c_int),
     'dpll_elbow_rollout_f64': ([_c_void_p] * 6 + [_f64, _f64, _i64, _i32] + [_c_void_p] * 4, ctypes.c_int),
     'dpll_elbow_rollout_f32': ([_c_void_p] * 6 + [_f32, _f32, _i64, _i32] + [_c_void_p] * 4, ctypes.c_int),
     'dpll_icnn_input_f64': ([_c_void_p, _c_void_p, _i64, _i32, _f64, _c_void_p, _c_void_p], ctypes.c_int),

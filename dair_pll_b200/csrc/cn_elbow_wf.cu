@@ -41,6 +41,43 @@ template <typename T> __device__ __forceinline__ T ew_warp_sum(T v) {
   return v;
 }
 
+// Warp reduce-scatter of 32 per-lane values: on return lane l holds sum over lanes of v[bitrev5(l)]... precisely, the
+// value index owned by a lane is built from its lane bits stage by stage (bit 4 first): after the stage with offset
+// o the lane keeps the half of its remaining values selected by (lane & o).  31 shuffle-adds per lane instead of
+// 32 x 5; all array indices are compile-time constants (registers).  Deterministic (fixed tree).
+template <typename T> __device__ __forceinline__ T ew_reduce_scatter32(T* v, int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 16;
+    const T keep = up ? v[i + 16] : v[i], give = up ? v[i] : v[i + 16];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 8;
+    const T keep = up ? v[i + 8] : v[i], give = up ? v[i] : v[i + 8];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 4;
+    const T keep = up ? v[i + 4] : v[i], give = up ? v[i] : v[i + 4];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 2;
+    const T keep = up ? v[i + 2] : v[i], give = up ? v[i] : v[i + 2];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+  }
+  {
+    const bool up = lane & 1;
+    const T keep = up ? v[1] : v[0], give = up ? v[0] : v[1];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, give, 1);
+  }
+  return v[0];      // lane l owns value index (l & 16) + (l & 8) + (l & 4) + (l & 2) + (l & 1) = l
+}
+
 template <typename T, typename IO>
 __device__ __forceinline__ void ew_load_params(cn::ElbowParams<T>& P, const IO* inertia, const IO* mu, const IO* half,
                                                const IO* kin, T dt, T eps) {
@@ -59,7 +96,9 @@ elbow_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const 
                      const IO* __restrict__ kin, const IO* __restrict__ pts, T dt, T eps, int64_t B,
                      IO* __restrict__ loss, IO* __restrict__ force, IO* __restrict__ grad_pts,
                      int32_t* __restrict__ iters, T* __restrict__ partials, int want_grad,
-                     const int32_t* __restrict__ skip_flag) {
+                     const int32_t* __restrict__ skip_flag, unsigned long long* __restrict__ dyn_counter) {
+  // dyn_counter != nullptr (DPLL_LOSS_DYNAMIC): warps draw their 32-sample chunks from a global counter, in batch
+  // order (cost-ordered batches: uniform chunks, longest solves first), as cube_loss_wf_kernel does.
   if (skip_flag && *skip_flag) return;
   extern __shared__ __align__(16) unsigned char ew_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -69,14 +108,14 @@ elbow_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const 
   cn::ElbowParams<T> P;
   ew_load_params<T, IO>(P, inertia, mu, half, kin, dt, eps);
   const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
-  T acc[kEwNAcc];
-#pragma unroll
-  for (int i = 0; i < kEwNAcc; ++i) acc[i] = T(0);
+  // Accumulators: lane l owns accumulator l ([0, 28) parameter gradients, 28 = loss sum); every finalising phase
+  // reduce-scatters its 32 lanes' contributions (ew_reduce_scatter32), so one register replaces 29 per thread.
+  T acc_lane = T(0);
 
   const int64_t gw = (int64_t)blockIdx.x * kEwWarps + warp, W = (int64_t)gridDim.x * kEwWarps;
   const int64_t base = B / W, rem = B % W;
-  const int64_t lo = gw * base + (gw < rem ? gw : rem);
-  const int64_t hi = lo + base + (gw < rem ? 1 : 0);
+  const int64_t lo = dyn_counter ? 0 : gw * base + (gw < rem ? gw : rem);
+  const int64_t hi = dyn_counter ? B : lo + base + (gw < rem ? 1 : 0);
   int64_t next = lo;
 
   for (int s = lane; s < kEwSlots; s += 32) { pool->q_done[s] = (uint8_t)s; pool->sample[s] = -1; }
@@ -95,18 +134,24 @@ elbow_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const 
     else phase = 1;
 
     if (phase == 2) {
-      const int64_t first = next;
+      int64_t first = next;
+      if (dyn_counter) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(dyn_counter, 32ull);
+        first = (int64_t)__shfl_sync(0xffffffffu, t, 0);
+        if (first >= B) first = B;
+      }
       const int64_t left = hi - first;
       const int cnt = left < 32 ? (int)left : 32;
       bool queue = false;
       const int64_t b = first + lane;
+      T gs[kEwNAcc];
+#pragma unroll
+      for (int i = 0; i < kEwNAcc; ++i) gs[i] = T(0);
       if (lane < cnt) {
         T xs[15], xps[15];
 #pragma unroll
         for (int i = 0; i < 15; ++i) { xs[i] = T(x[b * 15 + i]); xps[i] = T(xp[b * 15 + i]); }
-        T gs[DPLL_ELBOW_NPARAM];
-#pragma unroll
-        for (int i = 0; i < DPLL_ELBOW_NPARAM; ++i) gs[i] = T(0);
         T l = T(0);
         const T w = weight ? T(weight[b]) : T(1);
         if (cn::elbow_loss_free_flight<T, IO>(P, xs, xps, pts ? pts + b * 24 : (const IO*)nullptr,
@@ -117,18 +162,19 @@ elbow_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const 
             for (int i = 0; i < 24; ++i) force[b * 24 + i] = IO(0);
           }
 #pragma unroll
-          for (int i = 0; i < DPLL_ELBOW_NPARAM; ++i) acc[i] += w * gs[i];
+          for (int i = 0; i < DPLL_ELBOW_NPARAM; ++i) gs[i] *= w;
           if (loss) loss[b] = IO(l);
-          acc[DPLL_ELBOW_NPARAM] += l;
+          gs[DPLL_ELBOW_NPARAM] = l;
           if (iters) iters[b] = 0;
         } else {
           queue = true;
         }
       }
+      acc_lane += ew_reduce_scatter32(gs, lane);
       const unsigned m_q = __ballot_sync(0xffffffffu, queue);
       if (queue) pool->q_in[(h_in + n_in + __popc(m_q & lt_mask)) % kEwQin] = (int32_t)(b - lo);
       n_in += __popc(m_q);
-      next += cnt;
+      next = dyn_counter ? (first >= B ? B : lo) : next + cnt;
     } else if (phase == 1) {
       const int k = n_act < 32 ? n_act : 32;
       const bool on = lane < k;
@@ -174,6 +220,9 @@ elbow_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const 
           if (n_new == 0) break;
         }
         const bool work = pass == 0 ? (on && old >= 0) : (lane < n_new);
+        T gs[kEwNAcc];
+#pragma unroll
+        for (int i = 0; i < kEwNAcc; ++i) gs[i] = T(0);
         if (work) {
           const int64_t b = lo + (pass == 0 ? old : pool->q_in[(h_in + lane) % kEwQin]);
           T xs[15], xps[15];
@@ -187,17 +236,14 @@ elbow_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const 
             T u[7];
 #pragma unroll
             for (int i = 0; i < 7; ++i) u[i] = pool->field[77 + i][slot];
-            T gs[DPLL_ELBOW_NPARAM];
-#pragma unroll
-            for (int i = 0; i < DPLL_ELBOW_NPARAM; ++i) gs[i] = T(0);
             const T w = weight ? T(weight[b]) : T(1);
             const T l = cn::elbow_loss_epilogue_wf<T, IO>(P, S, E, A, u, want_grad ? gs : (T*)nullptr,
                                                           force ? force + b * 24 : (IO*)nullptr,
                                                           grad_pts ? grad_pts + b * 24 : (IO*)nullptr, w);
 #pragma unroll
-            for (int i = 0; i < DPLL_ELBOW_NPARAM; ++i) acc[i] += w * gs[i];
+            for (int i = 0; i < DPLL_ELBOW_NPARAM; ++i) gs[i] *= w;
             if (loss) loss[b] = IO(l);
-            acc[DPLL_ELBOW_NPARAM] += l;
+            gs[DPLL_ELBOW_NPARAM] = l;
             if (iters) iters[b] = pool->iters[slot] & 0xff;
             pool->sample[slot] = -1;
           } else {
@@ -210,6 +256,7 @@ elbow_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const 
             to_active = true;
           }
         }
+        if (pass == 0) acc_lane += ew_reduce_scatter32(gs, lane);
       }
       h_in = (h_in + n_new) % kEwQin; n_in -= n_new;
       const bool more = next < hi || n_in > 0;
@@ -226,14 +273,7 @@ elbow_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const 
 
   if (!partials) return;
   __shared__ T red[kEwWarps][kEwNAcc];
-#pragma unroll 1
-  for (int i = 0; i < kEwNAcc; ++i) {
-    T v = T(0);
-#pragma unroll
-    for (int j = 0; j < kEwNAcc; ++j) v = (j == i) ? acc[j] : v;
-    const T s = ew_warp_sum(v);
-    if (lane == 0) red[warp][i] = s;
-  }
+  red[warp][lane] = acc_lane;
   __syncthreads();
   if (threadIdx.x < kEwNAcc) {
     T s = T(0);
@@ -251,7 +291,7 @@ template <typename T, typename IO>
 int launch_elbow_loss_wf(const IO* x, const IO* xp, const IO* weight, const IO* inertia, const IO* mu, const IO* half,
                          const IO* kin, const IO* pts, T dt, T eps, int64_t B, IO* loss, IO* force, IO* grad_pts,
                          int32_t* iters, T* partials, int want_grad, const int32_t* skip_flag, int sms, cudaStream_t st,
-                         int* err) {
+                         int* err, unsigned long long* dyn) {
   const size_t smem = sizeof(EwWarpPool<T>) * kEwWarps;
   cudaError_t ea = cudaFuncSetAttribute(elbow_loss_wf_kernel<T, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ea != cudaSuccess) { *err = (int)ea; return 0; }
@@ -265,7 +305,7 @@ int launch_elbow_loss_wf(const IO* x, const IO* xp, const IO* weight, const IO* 
   if (blocks < 1) blocks = 1;
   elbow_loss_wf_kernel<T, IO><<<blocks, kEwWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, kin, pts, dt, eps, B,
                                                                    loss, force, grad_pts, iters, partials, want_grad,
-                                                                   skip_flag);
+                                                                   skip_flag, dyn);
   cudaError_t e = cudaGetLastError();
   *err = e == cudaSuccess ? DPLL_OK : (int)e;
   return blocks;
@@ -274,8 +314,8 @@ int launch_elbow_loss_wf(const IO* x, const IO* xp, const IO* weight, const IO* 
 template int launch_elbow_loss_wf<double, double>(const double*, const double*, const double*, const double*, const double*,
                                                   const double*, const double*, const double*, double, double, int64_t,
                                                   double*, double*, double*, int32_t*, double*, int, const int32_t*, int,
-                                                  cudaStream_t, int*);
+                                                  cudaStream_t, int*, unsigned long long*);
 template int launch_elbow_loss_wf<double, float>(const float*, const float*, const float*, const float*, const float*,
                                                  const float*, const float*, const float*, double, double, int64_t, float*,
                                                  float*, float*, int32_t*, double*, int, const int32_t*, int, cudaStream_t,
-                                                 int*);
+                                                 int*, unsigned long long*);

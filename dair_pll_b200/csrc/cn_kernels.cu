@@ -18,7 +18,7 @@ template <typename T, typename IO>
 int launch_elbow_loss_wf(const IO* x, const IO* xp, const IO* weight, const IO* inertia, const IO* mu, const IO* half,
                          const IO* kin, const IO* pts, T dt, T eps, int64_t B, IO* loss, IO* force, IO* grad_pts,
                          int32_t* iters, T* partials, int want_grad, const int32_t* skip_flag, int sms, cudaStream_t st,
-                         int* err);
+                         int* err, unsigned long long* dyn);
 
 namespace {
 
@@ -738,7 +738,7 @@ template <typename T, typename IO>
 int launch_elbow_loss(int variant, const IO* x, const IO* xp, const IO* weight, const IO* inertia, const IO* mu, const IO* half,
                       const IO* kin, const IO* pts, T dt, T eps, int64_t B, IO* loss, IO* force, IO* grad_pts,
                       int32_t* iters, IO* grad, IO* loss_sum,
-                      const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
+                      const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream, int flags = 0) {
   if (B < 0 || !inertia || !mu || (!half && !pts) || !kin || (grad_pts && (!pts || !grad))) return DPLL_EINVAL;
   if (B > 0 && (!x || !xp)) return DPLL_EINVAL;
   const bool want_red = grad || loss_sum;
@@ -750,8 +750,15 @@ int launch_elbow_loss(int variant, const IO* x, const IO* xp, const IO* weight, 
   if (variant == 0) {
     // wavefront kernel (default): per-visit scheduling over shared-memory records
     int err = DPLL_OK;
+    unsigned long long* dyn = nullptr;
+    if (flags & DPLL_LOSS_DYNAMIC) {
+      if (!workspace || workspace_bytes < dpll_workspace_bytes()) return DPLL_EWORKSPACE;
+      dyn = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + kWsQueueOffset);
+      cudaError_t em = cudaMemsetAsync(dyn, 0, kWsQueueBytes, st);
+      if (em != cudaSuccess) return (int)em;
+    }
     blocks = ::launch_elbow_loss_wf<T, IO>(x, xp, weight, inertia, mu, half, kin, pts, dt, eps, B, loss, force, grad_pts,
-                                         iters, partials, grad ? 1 : 0, skip_flag, di.sms, st, &err);
+                                         iters, partials, grad ? 1 : 0, skip_flag, di.sms, st, &err, dyn);
     if (err != DPLL_OK) return err;
   } else {
     const bool two_phase = variant != 1;          // 1 = one sample per thread, 2 = triage / solve passes (A/B measurements)
@@ -1071,6 +1078,26 @@ int dpll_elbow_loss_f64(const double* x, const double* x_plus, const double* wei
                         const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream) {
   return launch_elbow_loss<double, double>(g_loss_variant, x, x_plus, weight, inertia, mu_pair, half, kin, pts, dt, eps, B, loss, force,
                                            grad_pts, iters, grad, loss_sum, skip_flag, workspace, workspace_bytes, stream);
+}
+
+int dpll_elbow_loss_ex_f64(const double* x, const double* x_plus, const double* weight, const double* inertia,
+                           const double* mu_pair, const double* half, const double* kin, const double* pts, double dt,
+                           double eps, int64_t B, int32_t flags, double* loss, double* force, double* grad_pts,
+                           int32_t* iters, double* grad, double* loss_sum, const int32_t* skip_flag, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return launch_elbow_loss<double, double>(g_loss_variant == 2 ? 2 : (g_loss_variant == 1 ? 1 : 0), x, x_plus, weight, inertia,
+                                           mu_pair, half, kin, pts, dt, eps, B, loss, force, grad_pts, iters, grad, loss_sum,
+                                           skip_flag, workspace, workspace_bytes, stream, flags);
+}
+
+int dpll_elbow_loss_ex_f32(const float* x, const float* x_plus, const float* weight, const float* inertia,
+                           const float* mu_pair, const float* half, const float* kin, const float* pts, float dt, float eps,
+                           int64_t B, int32_t flags, float* loss, float* force, float* grad_pts, int32_t* iters, float* grad,
+                           float* loss_sum, const int32_t* skip_flag, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  return launch_elbow_loss<double, float>(g_loss_variant == 2 ? 2 : (g_loss_variant == 1 ? 1 : 0), x, x_plus, weight, inertia,
+                                          mu_pair, half, kin, pts, (double)dt, (double)eps, B, loss, force, grad_pts, iters,
+                                          grad, loss_sum, skip_flag, workspace, workspace_bytes, stream, flags);
 }
 
 int dpll_elbow_loss_f32(const float* x, const float* x_plus, const float* weight, const float* inertia,

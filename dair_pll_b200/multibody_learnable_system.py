@@ -133,10 +133,12 @@ class MultibodyLearnableSystem(System):
                 pts = self._elbow_witness_points(xpf[:, :8])
                 loss = ops.ElbowContactNetsLossPts.apply(xf, xpf, inertia, mu, pts, kin, float(self.dt), LOSS_EPS)
             else:
-                loss, sums, means = ops.ElbowContactNetsLoss.apply(xf, xpf, inertia, mu, half, kin, float(self.dt),
-                                                                   LOSS_EPS)
+                flags = ops.LOSS_DYNAMIC if self.dynamic_schedule else 0
+                loss, sums, means, iters = ops.ElbowContactNetsLoss.apply(xf, xpf, inertia, mu, half, kin, float(self.dt),
+                                                                          LOSS_EPS, flags, self.record_newton_iters)
                 # mean() / sum() of the result reuse the launch's own reduction and fused gradient (ops.BatchLoss)
-                return ops.batch_loss(loss.reshape(batch), sums, means, 28, (inertia, mu, half))
+                return ops.batch_loss(loss.reshape(batch), sums, means, 28, (inertia, mu, half),
+                                      iters.reshape(batch) if self.record_newton_iters else None)
         else:
             raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r}')
         return loss.reshape(batch)

@@ -335,8 +335,8 @@ def elbow_loss_raw(x: Tensor, x_plus: Tensor, inertia: Tensor, mu_pair: Tensor, 
                    dt: float, eps: float, weight: Optional[Tensor] = None, want_grad: bool = True,
                    want_force: bool = False, want_iters: bool = False, want_loss: bool = True,
                    skip_flag: Optional[Tensor] = None, grad_out: Optional[Tensor] = None,
-                   pts: Optional[Tensor] = None, want_grad_pts: bool = False):
-    """Direct call of ``dpll_elbow_loss_*``.  x, x_plus (B,15); inertia (20), mu_pair (2), half (6) or
+                   pts: Optional[Tensor] = None, want_grad_pts: bool = False, flags: int = 0):
+    """Direct call of ``dpll_elbow_loss_ex_*`` (``flags``: LOSS_DYNAMIC for cost-ordered batches).  x, x_plus (B,15); inertia (20), mu_pair (2), half (6) or
     witness points pts (B,8,3), kin (12).  Returns (loss (B,) | None, grad (28,) | None, loss_sum (1,),
     force (B,24) | None, iters (B,) | None[, grad_pts (B,8,3)])."""
     dtype = _check_inputs(x, x_plus, inertia, mu_pair, kin, *([half] if half is not None else []),
@@ -364,10 +364,10 @@ def elbow_loss_raw(x: Tensor, x_plus: Tensor, inertia: Tensor, mu_pair: Tensor, 
         weight = weight.to(dtype).contiguous()
     ws = _workspace(dev)
     grad_pts = torch.zeros((B, 8, 3), dtype=dtype, device=dev) if (want_grad_pts and want_grad) else None
-    fn = getattr(_lib.load(), 'dpll_elbow_loss_' + _SUFFIX[dtype])
+    fn = getattr(_lib.load(), 'dpll_elbow_loss_ex_' + _SUFFIX[dtype])
     with torch.cuda.device(dev):
         rc = fn(_ptr(x), _ptr(x_plus), _ptr(weight), _ptr(inertia), _ptr(mu_pair), _ptr(half), _ptr(kin), _ptr(pts),
-                dt, eps, B, _ptr(loss), _ptr(force), _ptr(grad_pts), _ptr(iters), _ptr(grad), _ptr(loss_sum),
+                dt, eps, B, flags, _ptr(loss), _ptr(force), _ptr(grad_pts), _ptr(iters), _ptr(grad), _ptr(loss_sum),
                 _ptr(skip_flag), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, 'dpll_elbow_loss')
     if want_grad_pts:
@@ -382,9 +382,10 @@ class ElbowContactNetsLoss(torch.autograd.Function):
     [gradient (28) | loss] sums and means for :class:`BatchLoss`."""
 
     @staticmethod
-    def forward(ctx, x, x_plus, inertia, mu_pair, half, kin, dt, eps):
+    def forward(ctx, x, x_plus, inertia, mu_pair, half, kin, dt, eps, flags=0, want_iters=False):
         need = any(ctx.needs_input_grad[2:5])
-        loss, grad, loss_sum, _, _ = elbow_loss_raw(x, x_plus, inertia, mu_pair, half, kin, dt, eps, want_grad=need)
+        loss, grad, loss_sum, _, iters = elbow_loss_raw(x, x_plus, inertia, mu_pair, half, kin, dt, eps, want_grad=need,
+                                                        want_iters=want_iters, flags=flags)
         ctx.dt, ctx.eps = dt, eps
         ctx.shapes = (inertia.shape, mu_pair.shape, half.shape)
         if need:
@@ -393,11 +394,13 @@ class ElbowContactNetsLoss(torch.autograd.Function):
             grad = torch.zeros(28, dtype=loss.dtype, device=loss.device)
         sums = torch.cat((grad, loss_sum))
         means = sums / max(loss.numel(), 1) if loss.numel() > 0 else sums * float('nan')
-        ctx.mark_non_differentiable(sums, means)
-        return loss, sums, means
+        if iters is None:
+            iters = torch.empty(0, dtype=torch.int32, device=loss.device)
+        ctx.mark_non_differentiable(sums, means, iters)
+        return loss, sums, means, iters
 
     @staticmethod
-    def backward(ctx, grad_loss, _g_sums, _g_means):
+    def backward(ctx, grad_loss, _g_sums, _g_means, _g_iters):
         grad, x, x_plus, inertia, mu_pair, half, kin = ctx.saved_tensors
         if grad_loss.numel() == 0:
             g = torch.zeros_like(grad)
@@ -412,7 +415,8 @@ class ElbowContactNetsLoss(torch.autograd.Function):
                            want_loss=False, skip_flag=uniform.to(torch.int32), grad_out=gw)
             g = torch.where(uniform, grad * lo, gw)
         s_in, s_mu, s_h = ctx.shapes
-        return (None, None, g[0:20].reshape(s_in), g[20:22].reshape(s_mu), g[22:28].reshape(s_h), None, None, None)
+        return (None, None, g[0:20].reshape(s_in), g[20:22].reshape(s_mu), g[22:28].reshape(s_h), None, None, None,
+                None, None)
 
 
 class ElbowContactNetsLossPts(torch.autograd.Function):

@@ -287,7 +287,8 @@ int dpll_elbow_rollout_grad_f64(const double* x0, const double* inertia, const d
  * of box 1 then box 2, each by ascending vertex index.  grad[28] = [d/d inertia (20) | d/d mu_pair (2) |
  * d/d half (6)].  Same reference spans as the cube entry points; the articulated M(q), F(q,v) and
  * geometry Jacobians are the closed forms of what multibody_terms.py:114-157, 267-319 derive
- * symbolically.
+ * symbolically.  The loss runs in a warp-level wavefront kernel like the cube's (csrc/cn_elbow_wf.cu: mass matrix
+ * as a composite body + hinge column, 96-double shared-memory records, one Newton visit per scheduling step).
  *
  * Learned (mesh) geometry: `pts` (B, 8, 3), nullable.  When given, the 4 + 4 witness points of the two
  * geometries (geometry frames) are taken from it instead of the box corners -- they are the outputs of
@@ -307,6 +308,18 @@ int dpll_elbow_loss_f32(const float* x, const float* x_plus, const float* weight
                         float dt, float eps, int64_t B, float* loss, float* force, float* grad_pts,
                         int32_t* iters, float* grad, float* loss_sum, const int32_t* skip_flag,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* The same with `flags` (DPLL_LOSS_DYNAMIC: 32-sample chunks handed to the warps in batch order, for cost-ordered
+ * batches -- see dpll_cube_loss_leaf_dp_*). */
+int dpll_elbow_loss_ex_f64(const double* x, const double* x_plus, const double* weight, const double* inertia,
+                           const double* mu_pair, const double* half, const double* kin, const double* pts,
+                           double dt, double eps, int64_t B, int32_t flags, double* loss, double* force,
+                           double* grad_pts, int32_t* iters, double* grad, double* loss_sum,
+                           const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream);
+int dpll_elbow_loss_ex_f32(const float* x, const float* x_plus, const float* weight, const float* inertia,
+                           const float* mu_pair, const float* half, const float* kin, const float* pts, float dt,
+                           float eps, int64_t B, int32_t flags, float* loss, float* force, float* grad_pts,
+                           int32_t* iters, float* grad, float* loss_sum, const int32_t* skip_flag,
+                           void* workspace, size_t workspace_bytes, void* stream);
 int dpll_elbow_rollout_f64(const double* x0, const double* inertia, const double* mu_pair,
                            const double* half, const double* kin, const double* pts, double dt,
                            double eps, int64_t B, int32_t steps, double* traj, double* force,

@@ -15,16 +15,22 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=1 << 20)
 ap.add_argument('--reps', type=int, default=4)
 ap.add_argument('--dtype', default='f64')
-ap.add_argument('--variant', type=int, default=0)
+ap.add_argument('--order', choices=['cost', 'natural'], default='cost')
 a = ap.parse_args()
-ops.set_loss_variant(a.variant)
 dev = torch.device('cuda', 0)
 dtype = torch.float64 if a.dtype == 'f64' else torch.float32
 system = bench.make_system(dev, dtype)
 x, xp = bench.make_batch(system, a.batch, 0, dev, dtype)
-inertia, mu, half = (t.detach() for t in system._cube_params(dtype))
+lt, ct = system.multibody_terms.lagrangian_terms, system.multibody_terms.contact_terms
+leaves = [t.detach().to(dtype) for t in (lt.inertial_parameters, ct.friction_params, ct.geometries[0].length_params)]
+flags = 0
+if a.order == 'cost':
+    it = ops.cube_loss_leaf_dp_raw(x, xp, *leaves, bench.DT, 1e-3, want_iters=True)[4]
+    idx = torch.argsort(it, descending=True, stable=True)
+    x, xp = x.index_select(0, idx).contiguous(), xp.index_select(0, idx).contiguous()
+    flags = ops.LOSS_DYNAMIC
 for _ in range(a.reps):
-    loss, grad, s, _, it = ops.cube_loss_raw(x, xp, inertia, mu, half, bench.DT, 1e-3, want_iters=True)
+    loss, sums, means, local, it = ops.cube_loss_leaf_dp_raw(x, xp, *leaves, bench.DT, 1e-3, flags=flags, want_iters=True)
 torch.cuda.synchronize()
-print('loss sum', s.item(), 'mean iters', it.double().mean().item(), 'max iters', it.max().item(),
+print('loss sum', sums[15].item(), 'mean iters', it.double().mean().item(), 'max iters', it.max().item(),
       'hist', torch.bincount(it)[:40].tolist())

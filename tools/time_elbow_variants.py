@@ -44,3 +44,17 @@ for B in (262144, 65536, 1048576):
         ref = out
         print(msg, flush=True)
     ops.set_loss_variant(0)
+    order = torch.argsort(ref[4], descending=True, stable=True)
+    xo, xpo = x[order].contiguous(), xp[order].contiguous()
+    for _ in range(2):
+        o2 = ops.elbow_loss_raw(xo, xpo, inertia, mu, hl, kin, 0.0068, 1e-3, flags=ops.LOSS_DYNAMIC)
+    torch.cuda.synchronize()
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st.record()
+    for _ in range(5):
+        ops.elbow_loss_raw(xo, xpo, inertia, mu, hl, kin, 0.0068, 1e-3, flags=ops.LOSS_DYNAMIC)
+    en.record()
+    torch.cuda.synchronize()
+    ms = st.elapsed_time(en) / 5
+    print(f'variant 0 cost order + dynamic B={B}: {ms:.3f} ms  {B / ms / 1e3:.2f} M samples/s  '
+          f'per-sample equal {torch.equal(o2[0], ref[0][order])}  grad rel {((o2[1] - ref[1]).abs().max() / ref[1].abs().max()).item():.2e}', flush=True)
