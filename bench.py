@@ -262,20 +262,28 @@ def secondary_configs(device, peak_flops):
         te, _ = ebox.simulate(xe.unsqueeze(-2), torch.zeros(Be, 1, device=device), 1)
     xpe = synthetic.perturb_next_state(te[:, 1], seed=4, n_q=8)
 
-    def ebox_step():
-        for p in ebox.parameters():
-            p.grad = None
-        ebox.contactnets_loss(xe, None, xpe).mean().backward()
-    ms = _time_gpu(ebox_step, device, 10)
+    params_e = list(ebox.parameters())
     ine, mue, halfe, kin = ebox._elbow_params(torch.float64, device)
-    raw = ops.elbow_loss_raw(xe, xpe, ine.detach(), mue.detach(), halfe.detach(), kin, DT, 1e-3, want_iters=True)
-    mean_it = raw[4].double().mean().item()
-    ms_k = _time_gpu(lambda: ops.elbow_loss_raw(xe, xpe, ine.detach(), mue.detach(), halfe.detach(), kin, DT, 1e-3),
-                     device, 10)
-    out['elbow_box_loss_backward_B262144_f64'] = {
-        'ms': ms, 'samples_per_s': Be / ms * 1e3, 'mean_newton_iters': mean_it,
-        'roofline': _roofline(Be * (FO_EL + FIT_EL * mean_it), ms_k, peak_flops,
-                              {'kernel': 'elbow_loss kernel', 'flops_per_sample': FO_EL + FIT_EL * mean_it})}
+    ine, mue, halfe = ine.detach(), mue.detach(), halfe.detach()
+    it_e = ops.elbow_loss_raw(xe, xpe, ine, mue, halfe, kin, DT, 1e-3, want_iters=True)[4]
+    mean_it = it_e.double().mean().item()
+    order_e = torch.argsort(it_e, descending=True, stable=True)
+    for ordered in (False, True):
+        xx, xxp = (xe.index_select(0, order_e).contiguous(), xpe.index_select(0, order_e).contiguous()) if ordered else (xe, xpe)
+        ebox.dynamic_schedule = ordered
+        flags = ops.LOSS_DYNAMIC if ordered else 0
+
+        def ebox_step():
+            for p in params_e:
+                p.grad = None
+            ebox.contactnets_loss(xx, None, xxp).mean().backward()
+        ms = _time_gpu(ebox_step, device, 20)
+        ms_k = _time_gpu(lambda: ops.elbow_loss_raw(xx, xxp, ine, mue, halfe, kin, DT, 1e-3, flags=flags), device, 20)
+        out[f'elbow_box_loss_backward_B262144_f64_{"cost" if ordered else "natural"}_order'] = {
+            'ms': ms, 'samples_per_s': Be / ms * 1e3, 'mean_newton_iters': mean_it, 'order': 'cost' if ordered else 'natural',
+            'roofline': _roofline(Be * (FO_EL + FIT_EL * mean_it), ms_k, peak_flops,
+                                  {'kernel': 'elbow_loss_wf_kernel', 'flops_per_sample': FO_EL + FIT_EL * mean_it})}
+    ebox.dynamic_schedule = False
     # config 3: elbow with learned (ICNN, width 256) geometry, loss + backward at B = 262,144
     torch.manual_seed(0)
     elbow = MultibodyLearnableSystem({'elbow': os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow_mesh.urdf')}, DT).to(device)
