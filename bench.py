@@ -339,7 +339,7 @@ def time_cpu(step, steps, warmup):
     return (time.perf_counter() - t0) / steps
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -363,13 +363,23 @@ def run_reference(args):
                    'dt': DT, 'eps': 1e-3, 'cpu_sample_per_step': B,
                    'note': 'same workload as the GPU arm; each CPU step is a bounded sample of it'},
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': threads, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), file=out, flush=True)
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else written to file descriptor 1 by this process or the
+    libraries it loads (NCCL prints its version banner there) is sent to stderr.  Returns a writer for the line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, 'w')
 
 
 def main():
     args = parse_args()
+    out = _claim_stdout()
     if args.impl == 'reference':
-        run_reference(args)
+        run_reference(args, out)
         return
     import torch.distributed as dist
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -637,7 +647,7 @@ def main():
         'clocks': clocks,
         'secondary': secondary,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
