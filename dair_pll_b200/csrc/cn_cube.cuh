@@ -786,6 +786,220 @@ CN_HD int cube_step_sample(const CubeParams<T>& P, const SolverCfg<T>& cfg, cons
 }
 
 // ---------------------------------------------------------------------------
+// The same single floating body with WITNESS POINTS instead of box corners: the contact set of any plane-convex
+// pair (GeometryCollider.collide_plane_convex, geometry.py:553-582) is "n_c <= 4 support points p_c of the shape in
+// the direction -R^T e_z", whatever the shape -- a Sphere's single point d r (geometry.py:415-456), the top-n_query
+// vertices of a Polygon (geometry.py:220-252, 162-202), the outputs of a support-function network.  The caller
+// evaluates the shape's support points (they are piecewise constant or linear in the shape parameters and carry
+// no state gradient) and gets d loss / d p_c back.  Contacts c >= n_c are switched off by a linear term deep in the
+// polar cone (zero force, zero curvature) and take no part in the loss.  Same reference spans as above.
+// ---------------------------------------------------------------------------
+template <typename T> CN_HD T contact_off() { return T(1e30); }
+
+template <typename T>
+CN_HD void body_geometry_pts(const CubeParams<T>& P, const T* quat, const T* pts, int n_c, T* R, const CubeProb<T>& S) {
+  quat_to_rot(quat, R);
+  T A[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const T r0 = R[3 * i], r1 = R[3 * i + 1], r2 = R[3 * i + 2];
+    A[3 * i + 0] = r0 * P.Io[0] + r1 * P.Io[3] + r2 * P.Io[4];
+    A[3 * i + 1] = r0 * P.Io[3] + r1 * P.Io[1] + r2 * P.Io[5];
+    A[3 * i + 2] = r0 * P.Io[4] + r1 * P.Io[5] + r2 * P.Io[2];
+  }
+  S.IW(0) = A[0] * R[0] + A[1] * R[1] + A[2] * R[2];
+  S.IW(1) = A[3] * R[3] + A[4] * R[4] + A[5] * R[5];
+  S.IW(2) = A[6] * R[6] + A[7] * R[7] + A[8] * R[8];
+  S.IW(3) = A[0] * R[3] + A[1] * R[4] + A[2] * R[5];
+  S.IW(4) = A[0] * R[6] + A[1] * R[7] + A[2] * R[8];
+  S.IW(5) = A[3] * R[6] + A[4] * R[7] + A[5] * R[8];
+  T cW[3];
+  rot3(R, P.c, cW);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.mcW(i) = P.m * cW[i];
+#pragma unroll
+  for (int c = 0; c < CUBE_NC; ++c) {
+    T r[3] = {T(0), T(0), T(0)};
+    if (c < n_c) rot3(R, pts + 3 * c, r);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) S.rho(3 * c + i) = r[i];
+  }
+}
+
+// loss (multibody_learnable_system.py:104-197) with witness points: grad11 += d loss / d [inertia 10 | mu];
+// grad_pts (12, written): d loss / d p_c (zero rows for c >= n_c); force_out (nullable, 12): reference order.
+template <typename T>
+CN_HD T body_loss_sample_pts(const CubeParams<T>& P, const SolverCfg<T>& cfg, const T* x, const T* xp, const T* pts,
+                             int n_c, T* grad11, T* grad_pts, T* force_out, int* iters_out) {
+  T store[CUBE_PROB_FIELDS];
+  const CubeProb<T> S{store, 1};
+  T R[9], vp[6], acc[6], dv[6];
+  body_geometry_pts(P, xp, pts, n_c, R, S);
+  const T pos_z = xp[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) vp[i] = xp[7 + i];
+  cube_free_accel(P, R, vp, acc, acc + 3);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) dv[i] = vp[i] - (x[7 + i] + P.dt * acc[i]);
+  T dvW[6], vW[6];
+  rot3(R, dv, dvW); rot3(R, vp, vW);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { dvW[3 + i] = dv[3 + i]; vW[3 + i] = vp[3 + i]; }
+  T pen = T(0);
+#pragma unroll
+  for (int c = 0; c < CUBE_NC; ++c) {
+    if (c < n_c) {
+      const T rho[3] = {S.rho(3 * c), S.rho(3 * c + 1), S.rho(3 * c + 2)};
+      T ed[3], ev[3];
+      cross3(dvW, rho, ed); cross3(vW, rho, ev);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { ed[i] += dvW[3 + i]; ev[i] += vW[3 + i]; }
+      const T sx = P.mu * ev[0], sy = P.mu * ev[1];
+      const T speed2 = sx * sx + sy * sy;
+      const T speed = speed2 * t_rsqrt(t_max(speed2, t_tiny<T>()));
+      const T phic = rho[2] + pos_z;
+      S.q(3 * c) = -P.mu * ed[0] + P.dt * sx;
+      S.q(3 * c + 1) = -P.mu * ed[1] + P.dt * sy;
+      S.q(3 * c + 2) = -ed[2] + t_abs(phic) + P.dt * speed;
+      const T pneg = t_max(-phic, T(0));
+      pen += pneg * pneg;
+    } else {
+      S.q(3 * c) = T(0); S.q(3 * c + 1) = T(0); S.q(3 * c + 2) = contact_off<T>();
+    }
+  }
+  T Mdv[6];
+  cube_mass_mul(P, S, dvW, Mdv);
+  T e = T(0);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) e += dvW[i] * Mdv[i];
+  const T konst = T(0.5) * e + pen;
+  T u[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  const int it = cube_solve<T, 4>(P, S, cfg, u);
+  if (iters_out) *iters_out = it;
+  // forces, loss
+  T zW[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, fs[12];
+  T qf = T(0), ff = T(0), fmax = T(0);
+#pragma unroll
+  for (int c = 0; c < CUBE_NC; ++c) {
+    T rho[3], r[3], f[3] = {T(0), T(0), T(0)};
+    if (c < n_c) {
+      cube_contact_residual(P, S, c, u, rho, r);
+      cone_eval<T, false>(r, P.inv_eps, P.mu, f, (T*)nullptr);
+      const T ft[3] = {P.mu * f[0], P.mu * f[1], f[2]};
+      T tq[3];
+      cross3(rho, ft, tq);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        zW[i] += tq[i]; zW[3 + i] += ft[i];
+        qf += S.q(3 * c + i) * f[i]; ff += f[i] * f[i];
+        const T af = t_abs(f[i]);
+        fmax = (af > fmax || af != af) ? af : fmax;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) fs[3 * c + i] = f[i];
+    if (force_out) { force_out[c] = f[2]; force_out[4 + 2 * c] = f[0]; force_out[4 + 2 * c + 1] = f[1]; }
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) grad_pts[i] = T(0);
+  if (!(fmax <= T(1e3))) {
+    if (force_out) for (int i = 0; i < 12; ++i) force_out[i] = T(0);
+    return T(0);
+  }
+  T z[6], y[6];
+  rot3t(R, zW, z);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) z[3 + i] = zW[3 + i];
+  cube_minv(P, R, z, z + 3, y, y + 3);
+  T zy = T(0);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) zy += z[i] * y[i];
+  const T loss = T(0.5) * zy + T(0.5) * P.eps * ff + qf + konst;
+  if (!grad11) return loss;
+  // envelope backward, as cube_loss_epilogue, with d/d p_c instead of d/d half lengths
+  T lam[6], b[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { b[i] = y[i] - dv[i]; lam[i] = P.dt * b[i]; }
+  T Kww[9], N[9], trvv = T(0);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      Kww[3 * i + j] = T(0.5) * (dv[i] * dv[j] - y[i] * y[j]) - lam[i] * acc[j];
+      N[3 * i + j] = (dv[i] * dv[3 + j] - y[i] * y[3 + j]) - lam[i] * acc[3 + j] - lam[3 + j] * acc[i];
+    }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) trvv += T(0.5) * (dv[3 + i] * dv[3 + i] - y[3 + i] * y[3 + i]) - lam[3 + i] * acc[3 + i];
+  rigid_body_inertia_adjoint<T>(P.m, P.c, R, vp, P.grav, Kww, N, trvv, lam, grad11);
+  T bW[3], wW[3];
+  rot3(R, b, bW); rot3(R, vp, wW);
+  T gmu = T(0);
+#pragma unroll
+  for (int c = 0; c < CUBE_NC; ++c) {
+    if (c < n_c) {
+      const T rho[3] = {S.rho(3 * c), S.rho(3 * c + 1), S.rho(3 * c + 2)};
+      const T ftx = fs[3 * c], fty = fs[3 * c + 1], fn = fs[3 * c + 2];
+      T eb[3], ev[3];
+      cross3(bW, rho, eb); cross3(wW, rho, ev);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { eb[i] += b[3 + i]; ev[i] += vp[3 + i]; }
+      const T sx = P.mu * ev[0], sy = P.mu * ev[1];
+      const T sinv = t_rsqrt(t_max(sx * sx + sy * sy, t_tiny<T>()));
+      const T ux = sx * sinv, uy = sy * sinv;
+      const T gx = P.dt * (fn * ux + ftx), gy = P.dt * (fn * uy + fty);
+      gmu += ftx * eb[0] + fty * eb[1] + gx * ev[0] + gy * ev[1];
+      const T ft[3] = {P.mu * ftx, P.mu * fty, fn};
+      const T gt[3] = {P.mu * gx, P.mu * gy, T(0)};
+      T ftB[3], gtB[3], p1[3], p2[3];
+      rot3t(R, ft, ftB); rot3t(R, gt, gtB);
+      cross3(ftB, b, p1); cross3(gtB, vp, p2);
+      const T phic = rho[2] + pos_z;
+      const T phibar = (phic > T(0) ? fn : (phic < T(0) ? -fn : T(0))) - T(2) * t_max(-phic, T(0));
+#pragma unroll
+      for (int k = 0; k < 3; ++k) grad_pts[3 * c + k] = p1[k] + p2[k] + phibar * R[6 + k];
+    }
+  }
+  grad11[10] += gmu;
+  return loss;
+}
+
+// learnable time step with witness points (forward_dynamics :260-304 + the Lie-group update)
+template <typename T>
+CN_HD int body_step_sample_pts(const CubeParams<T>& P, const SolverCfg<T>& cfg, const T* x, const T* pts, int n_c,
+                               T* xn, T* force_out) {
+  T store[CUBE_PROB_FIELDS];
+  const CubeProb<T> S{store, 1};
+  CubeStepAux<T> A;
+  A.sel = 0u;
+  body_geometry_pts(P, x, pts, n_c, A.R, S);
+  T acc[6], vmW[6];
+  cube_free_accel(P, A.R, x + 7, acc, acc + 3);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) A.vm[i] = x[7 + i] + P.dt * acc[i];
+  rot3(A.R, A.vm, vmW);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) vmW[3 + i] = A.vm[3 + i];
+  const T inv_dt = T(1) / P.dt;
+#pragma unroll
+  for (int c = 0; c < CUBE_NC; ++c) {
+    if (c < n_c) {
+      const T rho[3] = {S.rho(3 * c), S.rho(3 * c + 1), S.rho(3 * c + 2)};
+      T e[3];
+      cross3(vmW, rho, e);
+      S.q(3 * c) = P.mu * (e[0] + vmW[3]);
+      S.q(3 * c + 1) = P.mu * (e[1] + vmW[4]);
+      S.q(3 * c + 2) = (e[2] + vmW[5]) + (rho[2] + x[6]) * inv_dt;
+    } else {
+      S.q(3 * c) = T(0); S.q(3 * c + 1) = T(0); S.q(3 * c + 2) = contact_off<T>();
+    }
+  }
+  T u[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  const int it = cube_solve<T, 4>(P, S, cfg, u);
+  cube_step_epilogue<T, 4>(P, S, A, x, u, xn, force_out);
+  return it;
+}
+
+// ---------------------------------------------------------------------------
 // Dense dynamics terms in the reference's own coordinates and ordering, for callers of
 // MultibodyTerms.forward (multibody_terms.py:584-609): M (6x6), J (12x6) = [J_n (4 rows) ; mu J_t
 // (x,y interleaved per contact, 8 rows)] (:401-426), phi (4), contact-free acceleration (6) and the

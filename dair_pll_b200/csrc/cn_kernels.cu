@@ -514,6 +514,100 @@ cube_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, c
   }
 }
 
+// Single floating body with caller-supplied witness points (Sphere / Polygon / any plane-convex pair,
+// cn_cube.cuh:body_loss_sample_pts): one sample per thread.  Accumulators: [0, 11) d/d [inertia | mu], 11 = loss sum.
+template <typename T, typename IO>
+__global__ void __launch_bounds__(kLossThreads)
+body_pts_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
+                     const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ pts, int n_c, T dt,
+                     T eps, int64_t B, IO* __restrict__ loss, IO* __restrict__ force, IO* __restrict__ grad_pts,
+                     int32_t* __restrict__ iters, T* __restrict__ partials, int want_grad) {
+  cn::CubeParams<T> P;
+  {
+    T in[10], m[1], h[3] = {T(0), T(0), T(0)};
+#pragma unroll
+    for (int i = 0; i < 10; ++i) in[i] = T(inertia[i]);
+    m[0] = T(mu[0]);
+    cn::cube_params_init(P, in, m, h, dt, eps);
+  }
+  const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
+  T acc[kNAcc];
+#pragma unroll
+  for (int i = 0; i < kNAcc; ++i) acc[i] = T(0);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
+    T xs[13], xps[13], pt[12], gs[11], gp[12], fo[12];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * 13 + i]); xps[i] = T(xp[b * 13 + i]); }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) pt[i] = T(pts[b * 12 + i]);
+#pragma unroll
+    for (int i = 0; i < 11; ++i) gs[i] = T(0);
+    int it;
+    const T l = cn::body_loss_sample_pts<T>(P, cfg, xs, xps, pt, n_c, want_grad ? gs : (T*)nullptr, gp,
+                                            force ? fo : (T*)nullptr, &it);
+    const T w = weight ? T(weight[b]) : T(1);
+    if (force) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(fo[i]);
+    }
+    if (grad_pts) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) grad_pts[b * 12 + i] = IO(w * gp[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 11; ++i) acc[i] += w * gs[i];
+    if (loss) loss[b] = IO(l);
+    acc[11] += l;
+    if (iters) iters[b] = it;
+  }
+  if (!partials) return;
+  __shared__ T red[kLossThreads / 32][kNAcc];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kNAcc; ++i) {
+    const T s = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNAcc) {
+    T s = T(0);
+#pragma unroll
+    for (int w = 0; w < kLossThreads / 32; ++w) s += red[w][threadIdx.x];
+    partials[(int64_t)blockIdx.x * kNAcc + threadIdx.x] = s;
+  }
+}
+
+template <typename T, typename IO>
+__global__ void __launch_bounds__(kLossThreads)
+body_pts_step_kernel(const IO* __restrict__ x, const IO* __restrict__ inertia, const IO* __restrict__ mu,
+                     const IO* __restrict__ pts, int n_c, T dt, T eps, int64_t B, IO* __restrict__ xn,
+                     IO* __restrict__ force) {
+  cn::CubeParams<T> P;
+  {
+    T in[10], m[1], h[3] = {T(0), T(0), T(0)};
+#pragma unroll
+    for (int i = 0; i < 10; ++i) in[i] = T(inertia[i]);
+    m[0] = T(mu[0]);
+    cn::cube_params_init(P, in, m, h, dt, eps);
+  }
+  const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  T xs[13], pt[12], xo[13], fo[12];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) xs[i] = T(x[b * 13 + i]);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) pt[i] = T(pts[b * 12 + i]);
+  cn::body_step_sample_pts<T>(P, cfg, xs, pt, n_c, xo, force ? fo : (T*)nullptr);
+#pragma unroll
+  for (int i = 0; i < 13; ++i) xn[b * 13 + i] = IO(xo[i]);
+  if (force) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(fo[i]);
+  }
+}
+
 // Dense terms export (MultibodyTerms.forward, multibody_terms.py:584-609): one sample per thread.
 template <typename T, typename IO>
 __global__ void __launch_bounds__(kLossThreads)
@@ -1044,6 +1138,51 @@ int dpll_cube_rollout_f32(const float* x0, const float* inertia, const float* mu
                           void* stream) {
   return launch_cube_rollout<double, float>(x0, inertia, mu_pair, half, (double)dt, (double)eps, B, steps, traj, force,
                                             iters, stream);
+}
+
+int dpll_body_loss_pts_f64(const double* x, const double* x_plus, const double* weight, const double* inertia,
+                           const double* mu_pair, const double* pts, int32_t n_contacts, double dt, double eps, int64_t B,
+                           double* loss, double* force, double* grad_pts, int32_t* iters, double* grad, double* loss_sum,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || !inertia || !mu_pair || n_contacts < 1 || n_contacts > DPLL_CUBE_NC) return DPLL_EINVAL;
+  if (B > 0 && (!x || !x_plus || !pts)) return DPLL_EINVAL;
+  const bool want_red = grad || loss_sum;
+  if (want_red && (!workspace || workspace_bytes < dpll_workspace_bytes())) return DPLL_EWORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DeviceInfo di = device_info();
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, body_pts_loss_kernel<double, double>, kLossThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  int64_t need = (B + kLossThreads - 1) / kLossThreads;
+  int64_t cap = (int64_t)di.sms * per_sm;
+  if (cap > kMaxBlocks) cap = kMaxBlocks;
+  int blocks = (int)(need < cap ? need : cap);
+  if (blocks < 1) blocks = 1;
+  double* partials = want_red ? static_cast<double*>(workspace) : nullptr;
+  body_pts_loss_kernel<double, double><<<blocks, kLossThreads, 0, st>>>(x, x_plus, weight, inertia, mu_pair, pts, n_contacts,
+                                                                      dt, eps, B, loss, force, grad_pts, iters, partials,
+                                                                      grad ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (want_red) {
+    reduce_partials_kernel<double, double, kNAcc, 11><<<1, 32 * kNAcc, 0, st>>>(partials, blocks, grad, loss_sum, nullptr);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return DPLL_OK;
+}
+
+int dpll_body_step_pts_f64(const double* x, const double* inertia, const double* mu_pair, const double* pts,
+                           int32_t n_contacts, double dt, double eps, int64_t B, double* x_next, double* force,
+                           void* stream) {
+  if (B < 0 || !inertia || !mu_pair || n_contacts < 1 || n_contacts > DPLL_CUBE_NC) return DPLL_EINVAL;
+  if (B > 0 && (!x || !pts || !x_next)) return DPLL_EINVAL;
+  if (B == 0) return DPLL_OK;
+  const int blocks = (int)((B + kLossThreads - 1) / kLossThreads);
+  body_pts_step_kernel<double, double><<<blocks, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, inertia, mu_pair, pts, n_contacts, dt, eps, B, x_next, force);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPLL_OK : (int)e;
 }
 
 int dpll_cube_terms_f64(const double* q, const double* v, const double* inertia, const double* mu_pair,

@@ -4,8 +4,9 @@ The collision maths itself (top-k support points :162-202, plane-convex collisio
 runs inside the CUDA kernels; these modules own the ``nn.Parameter`` s with the reference's
 names and shapes so checkpoints interchange (``Box.length_params`` (1,3) :375-397).
 ``DeepSupportConvex`` (:255-364) owns the learned support-function network and the fixed direction
-perturbations.  Polygon, Sphere and mesh-mesh collision are not reached by any configuration of the
-hot path and are not provided.
+perturbations.  ``Sphere`` (:415-456) and ``Polygon`` (:220-252) evaluate their support points here (a scale /
+a top-k gather over a handful of vertices) and hand them to the witness-point kernels
+(``dpll_body_loss_pts_f64``).  Mesh-mesh collision (:584-643, fcl) is not provided.
 """
 from typing import Dict
 
@@ -52,6 +53,53 @@ class Box(CollisionGeometry):
 
     def scalars(self) -> Dict[str, float]:
         return {f'len_{ax}': 2 * v.item() for ax, v in zip('xyz', self.get_half_lengths().reshape(-1))}
+
+
+class Sphere(CollisionGeometry):
+    """Sphere by its support function (geometry.py:415-456): one witness point ``direction * |length_param|``."""
+    n_query = 1
+
+    def __init__(self, radius: Tensor) -> None:
+        super().__init__()
+        assert radius.numel() == 1
+        self.length_param = Parameter(radius.detach().clone().to(torch.float64).reshape(()), requires_grad=True)
+
+    def get_radius(self) -> Tensor:
+        return self.length_param.abs()
+
+    def support_points(self, directions: Tensor) -> Tensor:
+        """(*, 3) unit directions -> (*, 1, 3)."""
+        return (directions * self.get_radius().to(directions.dtype)).unsqueeze(-2)
+
+    def scalars(self) -> Dict[str, float]:
+        return {'radius': self.get_radius().item()}
+
+
+class Polygon(CollisionGeometry):
+    """Convex polytope given by its vertices (geometry.py:220-252): the witness points are the ``n_query``
+    vertices with the largest support in the query direction (geometry.py:162-202; returned by ascending vertex
+    index, the reference's order is unspecified)."""
+
+    def __init__(self, vertices: Tensor, n_query: int = 4) -> None:
+        super().__init__()
+        assert vertices.dim() == 2 and vertices.shape[1] == 3 and vertices.shape[0] >= n_query
+        self.n_query = n_query
+        self.vertices = Parameter(vertices.detach().clone().to(torch.float64), requires_grad=True)
+
+    def support_points(self, directions: Tensor) -> Tensor:
+        """(*, 3) directions -> (*, n_query, 3)."""
+        verts = self.vertices.to(directions.dtype)
+        dots = directions @ verts.t()
+        sel = torch.topk(dots, self.n_query, dim=-1, sorted=False).indices
+        sel, _ = torch.sort(sel, dim=-1)
+        return verts[sel]
+
+    def scalars(self) -> Dict[str, float]:
+        out = {}
+        for axis, values in zip('xyz', self.vertices.t()):
+            for i, v in enumerate(values):
+                out[f'v{i}_{axis}'] = v.item()
+        return out
 
 
 class DeepSupportConvex(CollisionGeometry):

@@ -69,7 +69,20 @@ class MultibodyLearnableSystem(System):
 
     def _cube_params(self, dtype: torch.dtype):
         inertia, mu, half = self.multibody_terms.kernel_parameters(dtype)
-        return inertia.reshape(10), mu.reshape(1), half[0]
+        return inertia.reshape(10), mu.reshape(1), (half[0] if half else None)
+
+    def _body_witness_points(self, quat: Tensor):
+        """(B,4) orientations -> ((B,4,3) witness points of the body geometry against the ground, n_contacts): the
+        shape's support points in the direction -R^T e_z (geometry.py:560-567), rows beyond n_query zero."""
+        geom = self.multibody_terms.contact_terms.geometries[0]
+        w, x, y, z = quat.unbind(-1)
+        s = 2.0 / (w * w + x * x + y * y + z * z)
+        d = -torch.stack((s * (x * z - w * y), s * (y * z + w * x), 1 - s * (x * x + y * y)), -1)
+        p = geom.support_points(d)
+        n_c = p.shape[-2]
+        if n_c < 4:
+            p = torch.cat((p, p.new_zeros(p.shape[:-2] + (4 - n_c, 3))), -2)
+        return p, n_c
 
     def _elbow_kin(self, dtype: torch.dtype, device: torch.device):
         """URDF constants [joint origin | joint axis | box offsets] and the axis alone, created once per
@@ -110,6 +123,13 @@ class MultibodyLearnableSystem(System):
         del u, loss_pool   # unactuated assets; the kernel needs no process pool
         assert x.shape[-1] == self.space.n_x and x_plus.shape == x.shape
         batch = x.shape[:-1]
+        if self._kind() == 'cube' and self.multibody_terms.contact_terms.has_witness_point_geometry():
+            # Sphere / Polygon: support points evaluated here, contact set handed to the witness-point kernel
+            inertia, mu, _ = self._cube_params(torch.float64)
+            xf, xpf = self._flat(x).to(torch.float64), self._flat(x_plus).to(torch.float64)
+            pts, n_c = self._body_witness_points(xpf[:, :4])
+            loss = ops.BodyWitnessPointLoss.apply(xf, xpf, inertia, mu, pts, n_c, float(self.dt), LOSS_EPS)
+            return loss.to(x.dtype).reshape(batch)
         if self._kind() == 'cube':
             lt, ct = self.multibody_terms.lagrangian_terms, self.multibody_terms.contact_terms
             # the learnable leaves go straight to the library (parameter preparation, multibody_terms.py:230-231,
@@ -147,6 +167,19 @@ class MultibodyLearnableSystem(System):
     def _rollout(self, x_0: Tensor, steps: int) -> Tensor:
         """(*, n_x) -> (*, steps+1, n_x)."""
         batch = x_0.shape[:-1]
+        if self._kind() == 'cube' and self.multibody_terms.contact_terms.has_witness_point_geometry():
+            # the witness points depend on the orientation: the time loop stays on the host, one step per launch
+            if torch.is_grad_enabled() and (x_0.requires_grad or any(p.requires_grad for p in self.multibody_terms.parameters())):
+                raise NotImplementedError('the rollout with Sphere / Polygon geometry has no backward: evaluate it under '
+                                          'torch.no_grad(), or train with contactnets_loss')
+            with torch.no_grad():
+                inertia, mu, _ = self._cube_params(torch.float64)
+                xs = [self._flat(x_0).to(torch.float64)]
+                for _ in range(steps):
+                    pts, n_c = self._body_witness_points(xs[-1][:, :4])
+                    xs.append(ops.body_step_pts(xs[-1], inertia, mu, pts, n_c, float(self.dt), STEP_EPS))
+                traj = torch.stack(xs, 1).to(x_0.dtype)
+            return traj.reshape(batch + (steps + 1, self.space.n_x))
         if self._kind() == 'cube':
             inertia, mu, half = self._cube_params(x_0.dtype)
             if torch.is_grad_enabled() and any(t.requires_grad for t in (x_0, inertia, mu, half)):

@@ -15,7 +15,7 @@ import torch
 from torch import Tensor
 from torch.nn import Module, ModuleList, Parameter
 
-from dair_pll_b200.geometry import Box, DeepSupportConvex, Plane
+from dair_pll_b200.geometry import Box, DeepSupportConvex, Plane, Polygon, Sphere
 from dair_pll_b200.inertia import InertialParameterConverter
 from dair_pll_b200.system_spec import SystemSpec
 
@@ -46,6 +46,8 @@ class ContactTerms(Module):
         for g in spec.geometries:
             if g.kind == 'box':
                 geoms.append(Box(torch.tensor(g.half_lengths, dtype=torch.float64), 4))
+            elif g.kind == 'sphere':
+                geoms.append(Sphere(torch.tensor(g.radius, dtype=torch.float64)))
             elif g.kind == 'plane':
                 geoms.append(Plane())
             elif g.kind == 'mesh':
@@ -76,6 +78,10 @@ class ContactTerms(Module):
     def has_learned_geometry(self) -> bool:
         return any(isinstance(g, DeepSupportConvex) for g in self.geometries)
 
+    def has_witness_point_geometry(self) -> bool:
+        """True if a body geometry is evaluated through its support points here (Sphere, Polygon)."""
+        return any(isinstance(g, (Sphere, Polygon)) for g in self.geometries)
+
 
 class MultibodyTerms(Module):
     """Container for the learnable dynamics parameters of a URDF system."""
@@ -94,7 +100,7 @@ class MultibodyTerms(Module):
         """Callable-level parameters in the kernels' dtype, differentiable w.r.t. the leaves."""
         inertia = self.lagrangian_terms.inertia_vector().to(dtype)
         mu = self.contact_terms.pair_friction().to(dtype)
-        if self.contact_terms.has_learned_geometry():
+        if self.contact_terms.has_learned_geometry() or self.contact_terms.has_witness_point_geometry():
             return inertia, mu, []
         half = [h.to(dtype) for h in self.contact_terms.half_lengths()]
         return inertia, mu, half

@@ -563,6 +563,70 @@ class ElbowRollout(torch.autograd.Function):
                 g[22:28].reshape(half.shape).to(half.dtype), None, None, None, None)
 
 
+class BodyWitnessPointLoss(torch.autograd.Function):
+    """ContactNets loss of a single floating body whose contact set is given by witness points ``pts`` (B,4,3)
+    (first ``n_contacts`` rows used) -- Sphere, Polygon, any plane-convex pair: ``dpll_body_loss_pts_f64``.
+    Differentiable w.r.t. inertia (10), mu_pair (1) and ``pts``; float64."""
+
+    @staticmethod
+    def forward(ctx, x, x_plus, inertia, mu_pair, pts, n_contacts, dt, eps):
+        _check_inputs(x, x_plus, inertia, mu_pair, pts)
+        if x.dtype != torch.float64:
+            raise TypeError('the witness-point kernels are provided in float64')
+        x, x_plus, pts = x.contiguous(), x_plus.contiguous(), pts.contiguous()
+        B, dev = x.shape[0], x.device
+        if tuple(pts.shape) != (B, 4, 3):
+            raise ValueError(f'pts must be (B,4,3), got {tuple(pts.shape)}')
+        loss = torch.empty(B, dtype=x.dtype, device=dev)
+        grad = torch.empty(11, dtype=x.dtype, device=dev)
+        loss_sum = torch.empty(1, dtype=x.dtype, device=dev)
+        gpts = torch.empty((B, 4, 3), dtype=x.dtype, device=dev)
+        ws = _workspace(dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().dpll_body_loss_pts_f64(_ptr(x), _ptr(x_plus), None, _ptr(inertia.contiguous()),
+                                                    _ptr(mu_pair.contiguous()), _ptr(pts), n_contacts, dt, eps, B,
+                                                    _ptr(loss), None, _ptr(gpts), None, _ptr(grad), _ptr(loss_sum),
+                                                    _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, 'dpll_body_loss_pts')
+        ctx.args = (n_contacts, dt, eps)
+        ctx.shapes = (inertia.shape, mu_pair.shape)
+        ctx.save_for_backward(grad, gpts, x, x_plus, inertia, mu_pair, pts)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        grad, gpts, x, x_plus, inertia, mu_pair, pts = ctx.saved_tensors
+        n_contacts, dt, eps = ctx.args
+        grad_loss = grad_loss.contiguous()
+        B, dev = x.shape[0], x.device
+        # general upstream weights: one weighted pass (these shapes are not on a benchmark configuration)
+        g = torch.zeros_like(grad)
+        if B > 0:
+            ws = _workspace(dev)
+            with torch.cuda.device(dev):
+                rc = _lib.load().dpll_body_loss_pts_f64(_ptr(x), _ptr(x_plus), _ptr(grad_loss), _ptr(inertia.contiguous()),
+                                                        _ptr(mu_pair.contiguous()), _ptr(pts), n_contacts, dt, eps, B,
+                                                        None, None, None, None, _ptr(g), None, _ptr(ws), ws.numel(),
+                                                        _stream())
+            _lib.check(rc, 'dpll_body_loss_pts')
+        s_in, s_mu = ctx.shapes
+        return (None, None, g[0:10].reshape(s_in), g[10:11].reshape(s_mu), gpts * grad_loss.reshape(-1, 1, 1), None, None,
+                None)
+
+
+def body_step_pts(x: Tensor, inertia: Tensor, mu_pair: Tensor, pts: Tensor, n_contacts: int, dt: float,
+                  eps: float = 1e-4) -> Tensor:
+    """One learnable time step (B,13) -> (B,13) of a single floating body with witness points (no autograd)."""
+    _check_inputs(x, inertia, mu_pair, pts)
+    x, pts = x.contiguous(), pts.contiguous()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().dpll_body_step_pts_f64(_ptr(x), _ptr(inertia.contiguous()), _ptr(mu_pair.contiguous()), _ptr(pts),
+                                                n_contacts, dt, eps, x.shape[0], _ptr(out), None, _stream())
+    _lib.check(rc, 'dpll_body_step_pts')
+    return out
+
+
 def cube_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor):
     """``dpll_cube_terms_f64``: (delassus (B,12,12), M (B,6,6), J (B,12,6), phi (B,4), acc (B,6)) in the order
     ``MultibodyTerms.forward`` returns them (multibody_terms.py:584-609).  fp64 only, no autograd."""

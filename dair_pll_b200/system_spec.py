@@ -49,11 +49,12 @@ class BodySpec:
 @dataclass
 class GeometrySpec:
     body: int                                   # index into bodies, -1 = world
-    kind: str                                   # 'box' | 'mesh' | 'plane'
+    kind: str                                   # 'box' | 'sphere' | 'mesh' | 'plane'
     offset: Tuple[float, float, float] = (0., 0., 0.)
     half_lengths: Optional[Tuple[float, float, float]] = None
     mesh_file: Optional[str] = None
     mu: float = 1.0
+    radius: Optional[float] = None
 
     def mesh_vertices(self) -> torch.Tensor:
         """Vertices of the Wavefront .obj (only ``v x y z`` records are needed: the reference uses them
@@ -139,8 +140,11 @@ class SystemSpec:
                     if prox.tag.endswith('mu_static'):
                         mu = float(prox.get('value'))
                 geom = col.find('geometry')
-                box, mesh = geom.find('box'), geom.find('mesh')
-                if box is not None:
+                box, mesh, sphere = geom.find('box'), geom.find('mesh'), geom.find('sphere')
+                if sphere is not None:
+                    geometries.append(GeometrySpec(len(bodies) - 1, 'sphere', offset, None, None, mu,
+                                                   float(sphere.get('radius'))))
+                elif box is not None:
                     size = _floats(box.get('size'), 3)
                     geometries.append(GeometrySpec(len(bodies) - 1, 'box', offset,
                                                    tuple(0.5 * s for s in size), None, mu))
@@ -150,7 +154,7 @@ class SystemSpec:
                         fname = os.path.join(os.path.dirname(os.path.abspath(path)), fname)
                     geometries.append(GeometrySpec(len(bodies) - 1, 'mesh', offset, None, fname, mu))
                 else:
-                    raise NotImplementedError('only <box> and <mesh> collision geometries are supported')
+                    raise NotImplementedError('only <box>, <sphere> and <mesh> collision geometries are supported')
         joints = []
         for joint in root.findall('joint'):
             if joint.get('type') not in ('continuous', 'revolute'):
@@ -178,8 +182,9 @@ class SystemSpec:
         if kind == 'cube':
             if len(geometries) != 1:
                 raise NotImplementedError('the single-body kernels take exactly one collision geometry')
-            if geometries[0].kind != 'box':
-                raise NotImplementedError('the single-body kernels take a <box> collision geometry')
+            if geometries[0].kind not in ('box', 'sphere'):
+                raise NotImplementedError('the single-body kernels take a <box> or <sphere> collision geometry '
+                                          '(a Polygon is set through the module API)')
             if any(abs(o) > 0 for o in geometries[0].offset):
                 raise NotImplementedError('a collision frame offset from the link origin is not supported for a single '
                                           'floating body (the two-body kernels take offsets)')

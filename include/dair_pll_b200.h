@@ -217,6 +217,24 @@ int dpll_icnn_backward_f64(const double* gp, const double* h0aug, const double* 
                            int64_t D, int32_t W, double slope, double* t, double* part, void* stream);
 
 /*
+ * A single floating body whose collision geometry is ANY convex shape against the ground plane
+ * (GeometryCollider.collide_plane_convex, dair_pll/geometry.py:553-582): the caller passes the shape's support
+ * points in the direction -R^T e_z -- Sphere: 1 point d r (geometry.py:415-456); Polygon: the top-n_query vertices
+ * (geometry.py:220-252, 162-202); Box / DeepSupportConvex likewise -- as pts (B, 4, 3) in the geometry frame, of
+ * which the first n_contacts (1..4) rows are used, and gets the loss, the gradient w.r.t. [inertia 10 | mu_pair]
+ * (grad, 11) and grad_pts (B, 4, 3) = w_b d loss_b / d pts[b] back (rows >= n_contacts zero).  One sample per
+ * thread (these shapes are not on a benchmark configuration; the box keeps its wavefront kernel).
+ * dpll_body_step_pts_f64: one learnable time step x -> x_next with the same contact set.
+ */
+int dpll_body_loss_pts_f64(const double* x, const double* x_plus, const double* weight, const double* inertia,
+                           const double* mu_pair, const double* pts, int32_t n_contacts, double dt, double eps,
+                           int64_t B, double* loss, double* force, double* grad_pts, int32_t* iters, double* grad,
+                           double* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
+int dpll_body_step_pts_f64(const double* x, const double* inertia, const double* mu_pair, const double* pts,
+                           int32_t n_contacts, double dt, double eps, int64_t B, double* x_next, double* force,
+                           void* stream);
+
+/*
  * Dense dynamics terms of the cube in the reference's coordinates and ordering, for callers of
  * MultibodyTerms.forward (dair_pll/multibody_terms.py:584-609; LagrangianTerms.forward :214-237,
  * ContactTerms.forward :428-521): q (B,7), v (B,6) -> M (B,6,6), J (B,12,6) = [J_n ; mu J_t interleaved]

@@ -66,7 +66,8 @@ def import_reference():
 
 
 def build_reference_system(kind: str, dt: float, pi_cm: torch.Tensor, friction: torch.Tensor,
-                           half_lengths, solver=None, mesh_vertices=None, mesh_width: int = 256, mesh_seed: int = 0):
+                           half_lengths, solver=None, mesh_vertices=None, mesh_width: int = 256, mesh_seed: int = 0,
+                           body_geometries=None):
     """Reference ``MultibodyLearnableSystem`` for ``kind`` in {'cube','elbow'}.
 
     Args:
@@ -102,7 +103,10 @@ def build_reference_system(kind: str, dt: float, pi_cm: torch.Tensor, friction: 
     ct.geometry_translations = calls.geometry_translations
     ct.geometry_spatial_jacobians = calls.geometry_spatial_jacobians
     n_body_geoms = len(tree.geometry_body) - 1
-    if mesh_vertices is not None:
+    if body_geometries is not None:
+        # caller-built reference geometry objects (Sphere, Polygon, ...), one per body geometry
+        geoms = list(body_geometries) + [Plane()]
+    elif mesh_vertices is not None:
         # the reference's own DeepSupportConvex (geometry.py:255-325): random ICNN initialisation and
         # random direction perturbations, made reproducible by seeding
         from dair_pll.geometry import DeepSupportConvex

@@ -82,6 +82,31 @@ int emul_cube_terms_f64(const double* q, const double* v, const double* inertia,
     cube_terms_sample<double>(P, q + 7 * b, v + 6 * b, M + 36 * b, J + 72 * b, phi + 4 * b, acc + 6 * b, D + 144 * b);
   return 0;
 }
+// single floating body with witness points (Sphere / Polygon / any plane-convex pair)
+int emul_body_loss_pts_f64(const double* x, const double* xp, const double* inertia, const double* mu, const double* pts,
+                           int n_c, double dt, double eps, int64_t B, double* loss, double* grad11, double* grad_pts) {
+  CubeParams<double> P;
+  double h[3] = {0, 0, 0};
+  cube_params_init(P, inertia, mu, h, dt, eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  for (int i = 0; i < 11; ++i) grad11[i] = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    int it;
+    loss[b] = body_loss_sample_pts<double>(P, cfg, x + 13 * b, xp + 13 * b, pts + 12 * b, n_c, grad11, grad_pts + 12 * b,
+                                           (double*)nullptr, &it);
+  }
+  return 0;
+}
+int emul_body_step_pts_f64(const double* x, const double* inertia, const double* mu, const double* pts, int n_c, double dt,
+                           double eps, int64_t B, double* xn) {
+  CubeParams<double> P;
+  double h[3] = {0, 0, 0};
+  cube_params_init(P, inertia, mu, h, dt, eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  for (int64_t b = 0; b < B; ++b)
+    body_step_sample_pts<double>(P, cfg, x + 13 * b, pts + 12 * b, n_c, xn + 13 * b, (double*)nullptr);
+  return 0;
+}
 int emul_elbow_terms_f64(const double* q, const double* v, const double* inertia, const double* mu, const double* half,
                          const double* kin, int64_t B, double* M, double* J, double* phi, double* acc, double* D) {
   ElbowParams<double> P;

@@ -385,3 +385,40 @@ def test_reverse_mode_rollout_backward_matches_forward_mode(assets_dir):
     traj.sum().backward()
     assert xs.grad is not None and torch.isfinite(xs.grad).all()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in s.parameters())
+
+
+@pytest.mark.parametrize('name', ['shape_sphere', 'shape_polygon'])
+def test_sphere_and_polygon_geometries_match_reference_golden(name, assets_dir):
+    """SURVEY 8(f) N4, plane-convex half: a floating body with the reference's Sphere (geometry.py:415-456) or Polygon
+    (:220-252) collision geometry through the module API -- the geometry module evaluates the support points, the
+    witness-point kernels (dpll_body_loss_pts_f64 / dpll_body_step_pts_f64) do the rest -- against goldens produced by
+    the reference's own classes: losses, gradients of theta / friction / radius or vertices, next states, at 1e-9."""
+    from dair_pll_b200.geometry import Polygon
+    g = load_golden(name)
+    s = MultibodyLearnableSystem({'body': os.path.join(assets_dir, 'sphere.urdf')}, float(g['dt']))
+    ct = s.multibody_terms.contact_terms
+    if name == 'shape_polygon':
+        ct.geometries[0] = Polygon(torch.from_numpy(g['shape_param']), 4)
+        leaf = lambda: ct.geometries[0].vertices            # noqa: E731
+    else:
+        with torch.no_grad():
+            ct.geometries[0].length_param.copy_(torch.from_numpy(g['shape_param']))
+        leaf = lambda: ct.geometries[0].length_param        # noqa: E731
+    with torch.no_grad():
+        s.multibody_terms.lagrangian_terms.inertial_parameters.copy_(torch.from_numpy(g['theta']))
+        ct.friction_params.copy_(torch.from_numpy(g['friction_params']))
+    s = s.to(DEV)
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    loss = s.contactnets_loss(x, None, xp)
+    loss.mean().backward()
+    l = loss.detach().cpu().numpy()
+    assert np.abs(l - g['loss']).max() < 1e-12
+    assert rel_err(l, g['loss'], 1e-9).max() < 1e-9
+    mt = s.multibody_terms
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(leaf().grad.cpu().numpy(), g['grad_shape_param']) < 1e-9
+    with torch.no_grad():
+        traj, _ = s.simulate(x.unsqueeze(-2), torch.zeros(x.shape[0], 1, device=DEV), 2)
+    assert np.abs(traj[:, 1].cpu().numpy() - g['x_next']).max() < 1e-9
+    assert torch.isfinite(traj).all()

@@ -345,3 +345,63 @@ def test_reverse_mode_step_adjoint_matches_forward_mode_tangents(steps):
         assert per_sample.max() < 1e-9                            # every toss on its own
     assert max_rel_to_scale(gp_r.sum(0), gp_f.sum(0)) < 1e-10     # the parameter gradient of the batch
     assert max_rel_to_scale(gx_r, gx_f) < 1e-10
+
+
+def _shape_case(name):
+    """golden + the product's geometry object and the witness points it yields on the CPU (torch ops)"""
+    from dair_pll_b200.geometry import Polygon, Sphere
+    g = load_golden(name)
+    p = torch.from_numpy(g['shape_param'])
+    geom = Sphere(p) if name == 'shape_sphere' else Polygon(p, 4)
+    return g, geom
+
+
+def _support_direction(quat):
+    w, x, y, z = quat.unbind(-1)
+    s = 2.0 / (w * w + x * x + y * y + z * z)
+    return -torch.stack((s * (x * z - w * y), s * (y * z + w * x), 1 - s * (x * x + y * y)), -1)
+
+
+@pytest.mark.parametrize('name', ['shape_sphere', 'shape_polygon'])
+def test_witness_point_device_math_matches_reference_golden(name):
+    """N4 (plane-convex contacts beyond the box): the witness-point loss / step code against goldens produced by the
+    REFERENCE's own Sphere and Polygon classes (oracle/gen_golden_shapes.py): losses, gradients of theta, friction
+    and the shape parameter (radius / vertices), and the one-step next state, at 1e-9."""
+    lib = host_emulation_lib()
+    g, geom = _shape_case(name)
+    theta = torch.from_numpy(g['theta']).clone().requires_grad_()
+    fr = torch.from_numpy(g['friction_params']).clone().requires_grad_()
+    inertia_t = co.theta_to_inertia_vector(theta).reshape(10)
+    m = fr.abs()
+    mu_t = (2 * m[0] * m[1] / (m[0] + m[1])).reshape(1)
+    x, xp = np.ascontiguousarray(g['x']), np.ascontiguousarray(g['x_plus'])
+    B = x.shape[0]
+
+    def witness(states):
+        p = geom.support_points(_support_direction(torch.from_numpy(states[:, :4])))
+        n_c = p.shape[-2]
+        full = torch.cat((p, p.new_zeros(B, 4 - n_c, 3)), -2) if n_c < 4 else p
+        return p, full, n_c
+    p, full, n_c = witness(xp)
+    pts = np.ascontiguousarray(full.detach().numpy())
+    loss, g11, gp = np.zeros(B), np.zeros(11), np.zeros((B, 4, 3))
+    inertia, mu = inertia_t.detach().numpy().copy(), mu_t.detach().numpy().copy()
+    lib.emul_body_loss_pts_f64(dptr(x), dptr(xp), dptr(inertia), dptr(mu), dptr(pts), ctypes.c_int(n_c),
+                               ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-3), ctypes.c_int64(B), dptr(loss),
+                               dptr(g11), dptr(gp))
+    assert np.abs(loss - g['loss']).max() < 1e-12
+    assert rel_err(loss, g['loss'], 1e-9).max() < 1e-9
+    # chain rule to the leaves (golden gradients are of loss.mean())
+    torch.cat((inertia_t, mu_t)).backward(torch.from_numpy(g11 / B))
+    p.backward(torch.from_numpy(gp[:, :n_c] / B))
+    shape_leaf = geom.length_param if name == 'shape_sphere' else geom.vertices
+    assert max_rel_to_scale(theta.grad.numpy(), g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(fr.grad.numpy(), g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(shape_leaf.grad.numpy(), g['grad_shape_param']) < 1e-9
+    # one learnable time step
+    _, full0, _ = witness(x)
+    pts0 = np.ascontiguousarray(full0.detach().numpy())
+    xn = np.zeros((B, 13))
+    lib.emul_body_step_pts_f64(dptr(x), dptr(inertia), dptr(mu), dptr(pts0), ctypes.c_int(n_c),
+                               ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-4), ctypes.c_int64(B), dptr(xn))
+    assert np.abs(xn - g['x_next']).max() < 1e-9
