@@ -276,11 +276,17 @@ def secondary_configs(device, peak_flops):
         def ebox_step():
             for p in params_e:
                 p.grad = None
-            ebox.contactnets_loss(xx, None, xxp).mean().backward()
-        ms = _time_gpu(ebox_step, device, 20)
+            mean = ebox.contactnets_loss(xx, None, xxp).mean()
+            mean.backward()
+            return mean
+        ms_eager_e = _time_gpu(ebox_step, device, 10)
+        from dair_pll_b200 import parallel
+        ms = _time_gpu(parallel.GraphedStep(ebox_step, device), device, 50)   # parameter preparation (theta -> inertia
+        # vectors, ~100 tiny torch kernels with their autograd) is host-bound when launched eagerly
         ms_k = _time_gpu(lambda: ops.elbow_loss_raw(xx, xxp, ine, mue, halfe, kin, DT, 1e-3, flags=flags), device, 20)
         out[f'elbow_box_loss_backward_B262144_f64_{"cost" if ordered else "natural"}_order'] = {
-            'ms': ms, 'samples_per_s': Be / ms * 1e3, 'mean_newton_iters': mean_it, 'order': 'cost' if ordered else 'natural',
+            'ms': ms, 'samples_per_s': Be / ms * 1e3, 'eager_ms': ms_eager_e, 'mean_newton_iters': mean_it,
+            'order': 'cost' if ordered else 'natural', 'step': 'CUDA graph replay of the public-API step',
             'roofline': _roofline(Be * (FO_EL + FIT_EL * mean_it), ms_k, peak_flops,
                                   {'kernel': 'elbow_loss_wf_kernel', 'flops_per_sample': FO_EL + FIT_EL * mean_it})}
     ebox.dynamic_schedule = False
