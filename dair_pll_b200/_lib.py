@@ -9,7 +9,7 @@ import os
 from dair_pll_b200 import build as _build
 
 _LIB = None
-ABI_VERSION = 200        # DPLL_VERSION of include/dair_pll_b200.h this binding was written against
+ABI_VERSION = 201        # DPLL_VERSION of include/dair_pll_b200.h this binding was written against
 
 _c_void_p = ctypes.c_void_p
 _i64, _i32, _f64, _f32, _sz = ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_float, ctypes.c_size_t
@@ -49,9 +49,9 @@ EXPORTS = {
     'dpll_icnn_backward_blocks': ([_i64], ctypes.c_int),
     'dpll_icnn_backward_f64': ([_c_void_p] * 5 + [_i64, _i32, _f64, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     'dpll_cube_loss_leaf_dp_f64': ([_c_void_p, _i64, _c_void_p, _i64] + [_c_void_p] * 3 + [_f64, _f64, _i64, _i32] +
-                                   [_c_void_p] * 6 + [_c_void_p, _sz, _c_void_p], ctypes.c_int),
+                                   [_c_void_p] * 8 + [_c_void_p, _sz, _c_void_p], ctypes.c_int),
     'dpll_cube_loss_leaf_dp_f32': ([_c_void_p, _i64, _c_void_p, _i64] + [_c_void_p] * 3 + [_f32, _f32, _i64, _i32] +
-                                   [_c_void_p] * 6 + [_c_void_p, _sz, _c_void_p], ctypes.c_int),
+                                   [_c_void_p] * 8 + [_c_void_p, _sz, _c_void_p], ctypes.c_int),
     'dpll_comm_handle_bytes': ([], _sz),
     'dpll_comm_create': ([_i32, _i32, ctypes.POINTER(_c_void_p), _c_void_p], ctypes.c_int),
     'dpll_comm_connect': ([_c_void_p, _c_void_p], ctypes.c_int),

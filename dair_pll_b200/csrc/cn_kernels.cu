@@ -168,7 +168,12 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
                     const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half, T dt,
                     T eps, int64_t B, IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
                     T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag,
-                    unsigned long long* __restrict__ dyn_counter, int64_t ldx, int64_t ldxp) {
+                    unsigned long long* __restrict__ dyn_counter, int64_t ldx, int64_t ldxp,
+                    const IO* __restrict__ u_init, IO* __restrict__ u_out) {
+  // u_init / u_out (nullable, (B, 6)): start point of every sample's Newton solve and its optimum (world-frame
+  // twist).  A training loop revisits the same pairs with slowly moving parameters: started from the previous
+  // epoch's optimum the solve takes a few visits instead of ~11 (the optimum is unique, so only the visit count
+  // depends on the start).
   // dyn_counter != nullptr (DPLL_LOSS_DYNAMIC / variant 2): warps take their triage chunks of 32 samples from a
   // global counter, in batch order, instead of a static range -- removes the load imbalance between warps and
   // lets a cost-ordered batch start its longest solves first, but the assignment of samples to warps (and with it
@@ -247,6 +252,10 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
           if (loss) loss[b] = IO(l);
           acc[14] += l;
           if (iters) iters[b] = 0;
+          if (u_out) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) u_out[b * 6 + i] = IO(0);
+          }
         } else {
           queue = true;
         }
@@ -341,10 +350,14 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
             if (loss) loss[b] = IO(l);
             acc[14] += l;
             if (iters) iters[b] = pool->iters[slot] & 0xff;
+            if (u_out) {
+#pragma unroll
+              for (int i = 0; i < 6; ++i) u_out[b * 6 + i] = IO(u[i]);
+            }
             pool->sample[slot] = -1;
           } else {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = T(0);
+            for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = u_init ? T(u_init[b * 6 + i]) : T(0);
             pool->field[39][slot] = T(-1);
             pool->field[46][slot] = T(0);
             pool->sample[slot] = (int32_t)(b - lo);
@@ -934,9 +947,10 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
                      IO* loss, IO* force, int32_t* iters, IO* grad, IO* loss_sum,
                      const int32_t* skip_flag, void* workspace, size_t workspace_bytes, void* stream, int flags = 0,
                      cn::CommDev* comm = nullptr, IO* sums = nullptr, IO* means = nullptr, IO* local_out = nullptr,
-                     int64_t ldx = 13, int64_t ldxp = 13) {
+                     int64_t ldx = 13, int64_t ldxp = 13, const IO* u_init = nullptr, IO* u_out = nullptr) {
   const bool leaf = theta != nullptr;
   if (ldx < 13 || ldxp < 13) return DPLL_EINVAL;
+  if ((u_init || u_out) && variant == 1) return DPLL_EINVAL;      // warm starts live in the wavefront kernel
   if (flags & DPLL_LOSS_DYNAMIC) variant = 2;
   if (comm && (!leaf || skip_flag)) return DPLL_EINVAL;   // the exchange lives in the leaf reduction and is unconditional
   if (B < 0 || (leaf ? (!friction || !length) : (!inertia || !mu || !half))) return DPLL_EINVAL;
@@ -983,12 +997,12 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
     // which is smaller in the instruction cache (the unrolled one is +5% at 1M pairs, +15% at 4M).
     if (B <= cap * kWfWarps * 320)
       cube_loss_wf_kernel<T, IO, 4><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B, loss,
-                                                                    force, iters, partials, (grad || sums || means) ? 1 : 0, skip_flag, dyn, ldx, ldxp);
+                                                                    force, iters, partials, (grad || sums || means) ? 1 : 0, skip_flag, dyn, ldx, ldxp, u_init, u_out);
     else
       cube_loss_wf_kernel<T, IO, kWfUnr><<<blocks, kWfWarps * 32, smem, st>>>(x, xp, weight, inertia, mu, half, dt, eps, B,
                                                                          loss, force, iters, partials,
                                                                          (grad || sums || means) ? 1 : 0, skip_flag, dyn, ldx,
-                                                                         ldxp);
+                                                                         ldxp, u_init, u_out);
   } else {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_kernel<T, IO>, kLossThreads, 0);
@@ -1097,26 +1111,28 @@ int dpll_cube_loss_leaf_f32(const float* x, const float* x_plus, const float* we
 
 int dpll_cube_loss_leaf_dp_f64(const double* x, int64_t x_row_stride, const double* x_plus, int64_t xp_row_stride,
                                const double* theta, const double* friction, const double* length, double dt, double eps,
-                               int64_t B, int32_t flags, void* comm, double* loss, int32_t* iters, double* sums,
-                               double* means, double* local, void* workspace, size_t workspace_bytes, void* stream) {
+                               int64_t B, int32_t flags, void* comm, const double* u_init, double* u_out, double* loss,
+                               int32_t* iters, double* sums, double* means, double* local, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   if (!theta || (!sums && !means)) return DPLL_EINVAL;
   return launch_cube_loss<double, double>(g_loss_variant, x, x_plus, nullptr, nullptr, nullptr, nullptr, theta, friction, length,
                                           dt, eps, B, loss, nullptr, iters, nullptr, nullptr, nullptr, workspace,
                                           workspace_bytes, stream, flags,
                                           static_cast<cn::CommDev*>(dpll_comm_device_state(comm)), sums, means, local,
-                                          x_row_stride, xp_row_stride);
+                                          x_row_stride, xp_row_stride, u_init, u_out);
 }
 
 int dpll_cube_loss_leaf_dp_f32(const float* x, int64_t x_row_stride, const float* x_plus, int64_t xp_row_stride,
                                const float* theta, const float* friction, const float* length, float dt, float eps,
-                               int64_t B, int32_t flags, void* comm, float* loss, int32_t* iters, float* sums,
-                               float* means, float* local, void* workspace, size_t workspace_bytes, void* stream) {
+                               int64_t B, int32_t flags, void* comm, const float* u_init, float* u_out, float* loss,
+                               int32_t* iters, float* sums, float* means, float* local, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   if (!theta || (!sums && !means)) return DPLL_EINVAL;
   return launch_cube_loss<double, float>(g_loss_variant, x, x_plus, nullptr, nullptr, nullptr, nullptr, theta, friction, length,
                                          (double)dt, (double)eps, B, loss, nullptr, iters, nullptr, nullptr, nullptr,
                                          workspace, workspace_bytes, stream, flags,
                                          static_cast<cn::CommDev*>(dpll_comm_device_state(comm)), sums, means, local,
-                                         x_row_stride, xp_row_stride);
+                                         x_row_stride, xp_row_stride, u_init, u_out);
 }
 
 int dpll_cube_rollout_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,

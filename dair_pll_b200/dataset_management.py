@@ -44,6 +44,7 @@ class DeviceTrajectorySliceDataset:
         self._future: List[Tensor] = []
         self._dense: Optional[Tuple[Tensor, Tensor]] = None
         self._cost: Optional[Tensor] = None      # (N,) int32 per-slice cost hint (last epoch's Newton counts)
+        self._usol: Optional[Tensor] = None      # (N, 6) last epoch's QP optima: next epoch's warm starts
 
     def add_slices_from_trajectory(self, trajectory: Tensor) -> None:
         """``trajectory``: (T, n_x).  Slice i predicts from time index ``t_skip + i``
@@ -62,6 +63,7 @@ class DeviceTrajectorySliceDataset:
         self._future.append(fut.transpose(1, 2).contiguous())
         self._dense = None
         self._cost = None
+        self._usol = None
 
     def add_trajectories_from_directory(self, trajectory_dir: str, indices: Optional[List[int]] = None) -> int:
         """Loads ``<index>.pt`` trajectories (all whole-number-named files when ``indices`` is None)."""
@@ -104,6 +106,25 @@ class DeviceTrajectorySliceDataset:
             self._cost.copy_(it)
         else:
             self._cost[indices.reshape(-1).to(self.device)] = it
+
+    def update_solutions(self, indices: Optional[Tensor], qp_solution: Tensor) -> None:
+        """Records ``BatchLoss.qp_solution`` (the cone QPs' optima) of the slices ``indices`` (None: all)."""
+        n = len(self)
+        if self._usol is None:
+            self._usol = torch.zeros((n, 6), dtype=self.dtype, device=self.device)
+        u = qp_solution.reshape(-1, 6).to(device=self.device, dtype=self.dtype)
+        if indices is None:
+            assert u.shape[0] == n
+            self._usol.copy_(u)
+        else:
+            self._usol[indices.reshape(-1).to(self.device)] = u
+
+    def warm_start(self, indices: Optional[Tensor] = None) -> Optional[Tensor]:
+        """(len(indices), 6) warm starts for ``system.qp_warm_start`` (zeros before the first epoch); None if no
+        solution has been recorded yet."""
+        if self._usol is None:
+            return None
+        return self._usol if indices is None else self._usol.index_select(0, indices.reshape(-1).to(self.device))
 
     def cost_order(self, indices: Optional[Tensor] = None, rank: int = 0, world: int = 1) -> Tensor:
         """Slice indices (of ``indices``, default all) by decreasing cost hint (stable), dealt round-robin to the

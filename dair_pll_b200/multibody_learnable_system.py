@@ -58,6 +58,9 @@ class MultibodyLearnableSystem(System):
         self.data_parallel = None        # parallel.PeerComm: loss.mean()/.sum() and gradients cover all ranks
         self.dynamic_schedule = False    # warps draw sample chunks in batch order (cost-ordered batches)
         self.record_newton_iters = False  # BatchLoss.newton_iters: per-sample cost hint for the data set
+        self.qp_warm_start = None        # (B, 6) contiguous start points of the next contactnets_loss call's solves
+                                         # (cube); with record_qp_solution it is overwritten in place by the optima
+        self.record_qp_solution = False  # BatchLoss.qp_solution (B, 6): the optima, next epoch's warm start
         self._kin_cache = {}
 
     # -- helpers ---------------------------------------------------------
@@ -137,12 +140,17 @@ class MultibodyLearnableSystem(System):
             leaves = (lt.inertial_parameters.to(x.dtype), ct.friction_params.to(x.dtype),
                       ct.geometries[0].length_params.to(x.dtype))
             flags = ops.LOSS_DYNAMIC if self.dynamic_schedule else 0
-            loss, sums, means, iters = ops.CubeContactNetsLossLeaf.apply(
+            warm, self.qp_warm_start = self.qp_warm_start, None          # consumed by this call
+            loss, sums, means, iters, usol = ops.CubeContactNetsLossLeaf.apply(
                 self._flat(x), self._flat(x_plus), *leaves, float(self.dt), LOSS_EPS, flags, self.data_parallel,
-                self.record_newton_iters)
+                self.record_newton_iters, warm.reshape(-1, 6) if warm is not None else None, self.record_qp_solution)
             # loss.mean() / loss.sum() (drake_experiment.py:222-223) then come from this launch's own reduction
-            return ops.batch_loss(loss.reshape(batch), sums, means, 15, leaves,
-                                  iters.reshape(batch) if self.record_newton_iters else None)
+            out = ops.batch_loss(loss.reshape(batch), sums, means, 15, leaves,
+                                 iters.reshape(batch) if self.record_newton_iters else None)
+            if self.record_qp_solution:
+                # with a warm start the optima were written back into the warm-start tensor itself
+                out.qp_solution = (warm if warm is not None else usol).reshape(batch + (6,))
+            return out
         elif self._kind() == 'elbow':
             if self.data_parallel is not None:
                 raise NotImplementedError('the in-kernel gradient exchange is provided for the cube; use '

@@ -173,11 +173,13 @@ def cube_loss_leaf_raw(x: Tensor, x_plus: Tensor, theta: Tensor, friction: Tenso
 
 
 def cube_loss_leaf_dp_raw(x: Tensor, x_plus: Tensor, theta: Tensor, friction: Tensor, length: Tensor, dt: float,
-                          eps: float, flags: int = 0, comm=None, want_loss: bool = True, want_iters: bool = False):
+                          eps: float, flags: int = 0, comm=None, want_loss: bool = True, want_iters: bool = False,
+                          u_init: Optional[Tensor] = None, want_u: bool = False):
     """Direct call of ``dpll_cube_loss_leaf_dp_*`` (the training-loop / data-parallel form).  x, x_plus: (B,13)
     with any row stride.  ``comm``: a :class:`dair_pll_b200.parallel.PeerComm` or None.  Returns
-    (loss (B,) | None, sums (17,) = [grad_leaf 15 | loss sum | count], means (16,), local (16,), iters | None);
-    with a communicator ``sums`` / ``means`` cover all ranks, ``local`` is this rank's share."""
+    (loss (B,) | None, sums (17,) = [grad_leaf 15 | loss sum | count], means (16,), local (16,), iters | None
+    [, u (B,6) if ``want_u``]); with a communicator ``sums`` / ``means`` cover all ranks, ``local`` is this rank's
+    share.  ``u_init`` (B,6): warm start of every sample's Newton solve (e.g. last epoch's ``u``)."""
     dtype = _check_inputs(x, x_plus, theta, friction, length)
     x, ldx = _rows(x, 13)
     x_plus, ldxp = _rows(x_plus, 13)
@@ -191,13 +193,22 @@ def cube_loss_leaf_dp_raw(x: Tensor, x_plus: Tensor, theta: Tensor, friction: Te
     iters = torch.empty(B, dtype=torch.int32, device=dev) if want_iters else None
     out = torch.empty(49, dtype=dtype, device=dev)
     sums, means, local = out[0:17], out[17:33], out[33:49]
+    if u_init is not None:
+        if tuple(u_init.shape) != (B, 6):
+            raise ValueError(f'u_init must be (B,6), got {tuple(u_init.shape)}')
+        u_init = u_init.to(dtype).contiguous()
+    # with a warm start the optima are written back IN PLACE (every sample reads its row before it writes it): a
+    # training loop keeps one (B, 6) buffer per batch and nothing is copied between epochs
+    u_out = (u_init if u_init is not None else torch.empty((B, 6), dtype=dtype, device=dev)) if want_u else None
     ws = _workspace(dev)
     fn = getattr(_lib.load(), 'dpll_cube_loss_leaf_dp_' + _SUFFIX[dtype])
     with torch.cuda.device(dev):
         rc = fn(_ptr(x), ldx, _ptr(x_plus), ldxp, _ptr(theta), _ptr(friction), _ptr(length), dt, eps, B, flags,
-                comm.handle if comm is not None else None, _ptr(loss), _ptr(iters), _ptr(sums), _ptr(means),
-                _ptr(local), _ptr(ws), ws.numel(), _stream())
+                comm.handle if comm is not None else None, _ptr(u_init), _ptr(u_out), _ptr(loss), _ptr(iters),
+                _ptr(sums), _ptr(means), _ptr(local), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, 'dpll_cube_loss_leaf_dp')
+    if want_u:
+        return loss, sums, means, local, iters, u_out
     return loss, sums, means, local, iters
 
 
@@ -214,9 +225,12 @@ class CubeContactNetsLossLeaf(torch.autograd.Function):
     stand-alone peer all-reduce."""
 
     @staticmethod
-    def forward(ctx, x, x_plus, theta, friction, length, dt, eps, flags, comm, want_iters):
-        loss, sums, means, local, iters = cube_loss_leaf_dp_raw(x, x_plus, theta, friction, length, dt, eps,
-                                                               flags=flags, comm=comm, want_iters=want_iters)
+    def forward(ctx, x, x_plus, theta, friction, length, dt, eps, flags, comm, want_iters, u_init=None, want_u=False):
+        out = cube_loss_leaf_dp_raw(x, x_plus, theta, friction, length, dt, eps, flags=flags, comm=comm,
+                                    want_iters=want_iters, u_init=u_init, want_u=want_u)
+        loss, sums, means, local, iters = out[:5]
+        # (a warm-start buffer is updated in place and not returned through autograd)
+        usol = out[5] if (want_u and u_init is None) else torch.empty(0, dtype=loss.dtype, device=loss.device)
         ctx.dt, ctx.eps, ctx.comm = dt, eps, comm
         ctx.shapes = (theta.shape, friction.shape, length.shape)
         if any(ctx.needs_input_grad[2:5]):
@@ -224,11 +238,11 @@ class CubeContactNetsLossLeaf(torch.autograd.Function):
         if iters is None:
             iters = torch.empty(0, dtype=torch.int32, device=loss.device)
         # the launch's own (global) sums and means, for BatchLoss.mean() / .sum()
-        ctx.mark_non_differentiable(sums, means, iters)
-        return loss, sums, means, iters
+        ctx.mark_non_differentiable(sums, means, iters, usol)
+        return loss, sums, means, iters, usol
 
     @staticmethod
-    def backward(ctx, grad_loss, _g_sums, _g_means, _g_iters):
+    def backward(ctx, grad_loss, _g_sums, _g_means, _g_iters, _g_u):
         local, x, x_plus, theta, friction, length = ctx.saved_tensors
         grad = local[:15]
         if grad_loss.numel() == 0:
@@ -247,7 +261,7 @@ class CubeContactNetsLossLeaf(torch.autograd.Function):
             g = ctx.comm.all_reduce_sum(g)
         s_t, s_f, s_l = ctx.shapes
         return (None, None, g[0:10].reshape(s_t), g[10:12].reshape(s_f), g[12:15].reshape(s_l), None, None, None, None,
-                None)
+                None, None, None)
 
 
 class _FusedReduction(torch.autograd.Function):
@@ -308,6 +322,7 @@ def batch_loss(loss: Tensor, sums: Tensor, means: Tensor, n: int, leaves, iters:
     out = loss.as_subclass(BatchLoss)
     out._dpll_fused = (sums, means, n, tuple(leaves))
     out.newton_iters = iters
+    out.qp_solution = None
     return out
 
 

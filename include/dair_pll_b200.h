@@ -44,7 +44,7 @@ extern "C" {
 #define DPLL_EWORKSPACE (-2) /* workspace too small */
 #define DPLL_ECOMM (-3)      /* a peer did not arrive within the exchange's timeout */
 
-#define DPLL_VERSION 200     /* bumped with every change of a signature below; the binding checks it */
+#define DPLL_VERSION 201     /* bumped with every change of a signature below; the binding checks it */
 
 #define DPLL_CUBE_NX 13
 #define DPLL_CUBE_NC 4
@@ -140,6 +140,10 @@ int dpll_cube_loss_leaf_f32(const float* x, const float* x_plus, const float* we
  *   comm  : nullable communicator (dpll_comm_create).  When given, the reduction kernel exchanges
  *       [grad_leaf 15 | loss sum | B] with every peer over NVLink itself and the outputs are the sums over
  *       ranks, bitwise identical on every rank; every rank of the communicator must make the call.
+ *   u_init, u_out : (B, 6) nullable; start point of every sample's Newton solve / its optimum u* (world-frame twist of
+ *       the impulse, M u* = J^T f).  The QP's optimum is unique, so the start changes only the number of Newton
+ *       visits: a training loop that keeps u* per pair (DeviceTrajectorySliceDataset.update_solutions) and hands it
+ *       back next epoch solves in a few visits instead of ~11.  u_out of a free-flight sample is 0.
  *   sums  : (17) nullable; [d(sum_b loss_b)/d leaves (15) | sum_b loss_b | number of samples summed]
  *   means : (16) nullable; sums[0..15] / sums[16]: loss.mean() (drake_experiment.py:222-223) and its gradient
  *   local : (16) nullable; this rank's own [grad_leaf 15 | loss sum] (before the exchange)
@@ -148,13 +152,14 @@ int dpll_cube_loss_leaf_f32(const float* x, const float* x_plus, const float* we
 #define DPLL_LOSS_DYNAMIC 1
 int dpll_cube_loss_leaf_dp_f64(const double* x, int64_t x_row_stride, const double* x_plus, int64_t xp_row_stride,
                                const double* theta, const double* friction, const double* length, double dt,
-                               double eps, int64_t B, int32_t flags, void* comm, double* loss, int32_t* iters,
-                               double* sums, double* means, double* local, void* workspace, size_t workspace_bytes,
-                               void* stream);
+                               double eps, int64_t B, int32_t flags, void* comm, const double* u_init, double* u_out,
+                               double* loss, int32_t* iters, double* sums, double* means, double* local,
+                               void* workspace, size_t workspace_bytes, void* stream);
 int dpll_cube_loss_leaf_dp_f32(const float* x, int64_t x_row_stride, const float* x_plus, int64_t xp_row_stride,
                                const float* theta, const float* friction, const float* length, float dt, float eps,
-                               int64_t B, int32_t flags, void* comm, float* loss, int32_t* iters, float* sums,
-                               float* means, float* local, void* workspace, size_t workspace_bytes, void* stream);
+                               int64_t B, int32_t flags, void* comm, const float* u_init, float* u_out, float* loss,
+                               int32_t* iters, float* sums, float* means, float* local, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /*
  * Data-parallel exchange over peer memory.  One communicator per rank (= per process and GPU); `create`

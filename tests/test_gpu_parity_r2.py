@@ -422,3 +422,48 @@ def test_sphere_and_polygon_geometries_match_reference_golden(name, assets_dir):
         traj, _ = s.simulate(x.unsqueeze(-2), torch.zeros(x.shape[0], 1, device=DEV), 2)
     assert np.abs(traj[:, 1].cpu().numpy() - g['x_next']).max() < 1e-9
     assert torch.isfinite(traj).all()
+
+
+def test_warm_started_solves_give_the_same_results_in_fewer_iterations(assets_dir):
+    """dpll_cube_loss_leaf_dp_* with u_init / u_out: started from the optima found with slightly different parameters
+    (a training loop's previous epoch) the solves reach the same losses and gradients (the QP's optimum is unique) in
+    fewer Newton iterations; through the module API the data set carries the solutions."""
+    from dair_pll_b200.dataset_management import DeviceTrajectorySliceDataset, TrajectorySliceConfig
+    g = load_golden('cube_synthetic')
+    theta = torch.from_numpy(g['theta']).to(DEV)
+    fr = torch.from_numpy(g['friction_params']).to(DEV)
+    ln = torch.from_numpy(g['half_lengths']).reshape(1, 3).to(DEV)
+    inertia, mu, half = (torch.from_numpy(a).to(DEV) for a in kernel_level_params(g))
+    n = 100003
+    x = synthetic.cube_states(n, seed=81, device=DEV)
+    traj, _ = ops.cube_rollout(x, inertia, mu, half, DT, 1)
+    xp = synthetic.perturb_next_state(traj[:, 1], seed=82)
+    cold = ops.cube_loss_leaf_dp_raw(x, xp, theta, fr, ln, DT, 1e-3, want_iters=True, want_u=True)
+    assert cold[5].shape == (n, 6) and (cold[5][cold[4] == 0] == 0).all()
+    # same parameters: already optimal -> no Newton direction is taken, bits of the loss unchanged to rounding
+    same = ops.cube_loss_leaf_dp_raw(x, xp, theta, fr, ln, DT, 1e-3, want_iters=True, u_init=cold[5], want_u=True)
+    assert int(same[4].max()) <= 1 and torch.allclose(same[0], cold[0], rtol=1e-12, atol=1e-18)
+    # moved parameters: same answers as a cold solve, far fewer iterations
+    theta2, fr2, ln2 = theta * 1.001, fr * 0.999, ln * 1.0005
+    ref = ops.cube_loss_leaf_dp_raw(x, xp, theta2, fr2, ln2, DT, 1e-3, want_iters=True)
+    warm = ops.cube_loss_leaf_dp_raw(x, xp, theta2, fr2, ln2, DT, 1e-3, want_iters=True, u_init=cold[5])
+    assert rel_err(warm[0].cpu().numpy(), ref[0].cpu().numpy(), 1e-9).max() < 1e-10
+    assert max_rel_to_scale(warm[1].cpu().numpy(), ref[1].cpu().numpy()) < 1e-11
+    assert warm[4].double().mean().item() < 0.6 * ref[4].double().mean().item()
+    # a bad start is only slower, never wrong
+    junk = ops.cube_loss_leaf_dp_raw(x, xp, theta2, fr2, ln2, DT, 1e-3, u_init=torch.randn(n, 6, dtype=torch.float64, device=DEV))
+    assert rel_err(junk[0].cpu().numpy(), ref[0].cpu().numpy(), 1e-9).max() < 1e-9
+    # module API + data set
+    ds = DeviceTrajectorySliceDataset(TrajectorySliceConfig(), device=torch.device(DEV))
+    ds.add_slices_from_trajectory(torch.stack((x[:5000], xp[:5000]), 1).reshape(-1, 13)[:2])   # placeholder trajectory
+    s = MultibodyLearnableSystem({'cube': os.path.join(assets_dir, 'cube.urdf')}, DT).to(DEV)
+    s.record_qp_solution = True
+    l0 = s.contactnets_loss(x[:5000], None, xp[:5000])
+    assert l0.qp_solution.shape == (5000, 6)
+    s.qp_warm_start = l0.qp_solution
+    s.record_newton_iters = True
+    l1 = s.contactnets_loss(x[:5000], None, xp[:5000])
+    assert s.qp_warm_start is None and int(l1.newton_iters.max()) <= 1
+    assert torch.allclose(l1.detach(), l0.detach(), rtol=1e-12, atol=1e-18)
+    ds.update_solutions(torch.tensor([0]), l0.qp_solution[:1])
+    assert ds.warm_start(torch.tensor([0])).shape == (1, 6)
