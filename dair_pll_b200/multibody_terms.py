@@ -58,6 +58,7 @@ class ContactTerms(Module):
         self.friction_params = Parameter(torch.tensor([g.mu for g in spec.geometries], dtype=torch.float64),
                                          requires_grad=True)
         # (2, n_pairs): row 0 = geometry a (Plane sorts first, geometry.py:46), row 1 = geometry b
+        self._pairs = [tuple(int(i) for i in pair) for pair in spec.collision_pairs]    # host copy: no device reads
         self.register_buffer('collision_candidates',
                              torch.tensor(spec.collision_pairs, dtype=torch.long).t().contiguous(),
                              persistent=False)
@@ -73,7 +74,7 @@ class ContactTerms(Module):
 
     def half_lengths(self) -> List[Tensor]:
         """|length_params| (3,) of each pair's body geometry, in pair order (boxes only)."""
-        return [self.geometries[int(b)].get_half_lengths().reshape(3) for b in self.collision_candidates[1]]
+        return [self.geometries[b].get_half_lengths().reshape(3) for _, b in self._pairs]
 
     def has_learned_geometry(self) -> bool:
         return any(isinstance(g, DeepSupportConvex) for g in self.geometries)
