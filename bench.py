@@ -230,43 +230,46 @@ def secondary_configs(device, peak_flops):
     it0 = ops.cube_loss_leaf_dp_raw(xt, xpt, *leaves(torch.float64), DT, 1e-3, want_iters=True)[4]
     order = torch.argsort(it0, descending=True, stable=True)
     xt, xpt = xt.index_select(0, order).contiguous(), xpt.index_select(0, order).contiguous()
-    opt = torch.optim.Adam(params, lr=1e-3)
     saved_t = {k: v.detach().clone() for k, v in system.state_dict().items()}
     system.dynamic_schedule = True
     train = {}
+    from dair_pll_b200 import parallel
     for mode in ('cold', 'warm'):
         system.load_state_dict(saved_t)
-        opt = torch.optim.Adam(params, lr=1e-3)
+        opt = torch.optim.Adam(params, lr=1e-3, capturable=True)
         usol = torch.zeros(1 << 20, 6, dtype=torch.float64, device=device)
         system.record_qp_solution = system.record_newton_iters = mode == 'warm'
-        counts = []
+        holder = {}
 
         def train_step():
             opt.zero_grad(set_to_none=True)
             if mode == 'warm':
                 system.qp_warm_start = usol
             loss = system.contactnets_loss(xt, None, xpt)
-            loss.mean().backward()
+            mean = loss.mean()
+            mean.backward()
             opt.step()
-            return loss
-        for _ in range(3):
-            train_step()
+            holder['iters'] = loss.newton_iters
+            return mean
+        graphed = parallel.GraphedStep(train_step, device)      # the whole iteration, optimiser included, as one graph
+        for _ in range(5):
+            graphed()
         torch.cuda.synchronize(device)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for _ in range(30):
-            last = train_step()
+        for _ in range(200):
+            graphed()
         s1.record()
         torch.cuda.synchronize(device)
-        ms_t = s0.elapsed_time(s1) / 30
+        ms_t = s0.elapsed_time(s1) / 200
         train[mode] = {'ms_per_step': ms_t, 'samples_per_s': (1 << 20) / ms_t * 1e3,
-                       'mean_newton_iters_last_step': (last.newton_iters.double().mean().item() if mode == 'warm' else
+                       'mean_newton_iters_last_step': (holder['iters'].double().mean().item() if mode == 'warm' else
                                                        it0.double().mean().item())}
     system.record_qp_solution = system.record_newton_iters = False
     system.dynamic_schedule = False
     system.load_state_dict(saved_t)
     out['cube_training_loop_adam_B1048576_f64'] = {
-        **train, 'note': 'loss.mean().backward() + Adam step per iteration, eager launches, cost-ordered batch; warm = every '
+        **train, 'note': 'loss.mean().backward() + Adam step per iteration (CUDA graph replay), cost-ordered batch; warm = every '
                          'solve starts from the previous step\'s optimum (in-place (B,6) buffer)'}
 
     # config 4: rollout, 4,096 cube tosses x 80 steps
