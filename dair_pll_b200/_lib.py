@@ -32,6 +32,9 @@ EXPORTS = {
     'dpll_body_loss_pts_f64': ([_c_void_p] * 6 + [_i32, _f64, _f64, _i64] + [_c_void_p] * 6 + [_c_void_p, _sz, _c_void_p],
                                ctypes.c_int),
     'dpll_body_step_pts_f64': ([_c_void_p] * 4 + [_i32, _f64, _f64, _i64] + [_c_void_p] * 3, ctypes.c_int),
+    'dpll_chain_loss_f64': ([_i32] + [_c_void_p] * 7 + [_f64, _f64, _i64] + [_c_void_p] * 5 + [_c_void_p, _sz, _c_void_p],
+                            ctypes.c_int),
+    'dpll_chain_rollout_f64': ([_i32] + [_c_void_p] * 5 + [_f64, _f64, _i64, _i32] + [_c_void_p] * 2, ctypes.c_int),
     'dpll_elbow_terms_f64': ([_c_void_p] * 6 + [_i64] + [_c_void_p] * 6, ctypes.c_int),
     'dpll_cube_rollout_grad_f64': ([_c_void_p] * 4 + [_f64, _f64, _i64, _i32] + [_c_void_p] * 4, ctypes.c_int),
     'dpll_cube_rollout_saved_f64': ([_c_void_p] * 4 + [_f64, _f64, _i64, _i32] + [_c_void_p] * 3, ctypes.c_int),

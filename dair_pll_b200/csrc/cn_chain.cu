@@ -1,0 +1,165 @@
+// Kernels of the generic floating-base serial chain (cn_chain.cuh; SURVEY.md section 8(f) N2, first slice): one sample
+// per thread, N = 2 .. 4 links.  The general path for models the specialised kernels do not cover.
+#include <cuda_runtime.h>
+
+#include "../../include/dair_pll_b200.h"
+#include "cn_chain.cuh"
+
+namespace {
+
+constexpr int kChThreads = 64;
+constexpr int kChNAcc = 64;                 // 14 N parameter gradients + loss sum (N <= 4: 57)
+constexpr int kChMaxBlocks = 148 * 8;       // partials fit the common workspace (dpll_workspace_bytes)
+
+template <typename T> __device__ __forceinline__ T ch_warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T, int N>
+__global__ void __launch_bounds__(kChThreads)
+chain_loss_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __restrict__ weight,
+                  const T* __restrict__ inertia, const T* __restrict__ mu, const T* __restrict__ half,
+                  const T* __restrict__ kin, T dt, T eps, int64_t B, T* __restrict__ loss, T* __restrict__ force,
+                  int32_t* __restrict__ iters, T* __restrict__ partials, int want_grad) {
+  constexpr int NX = 13 + 2 * (N - 1), NP = 14 * N, NF = 12 * N;
+  cn::ChainParams<T, N> P;
+  cn::chain_params_init<T, N>(P, inertia, mu, half, kin, dt, eps);
+  const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
+  T acc[NP + 1];
+  for (int i = 0; i <= NP; ++i) acc[i] = T(0);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
+    T xs[NX], xps[NX], gs[NP], fo[NF];
+    for (int i = 0; i < NX; ++i) { xs[i] = x[b * NX + i]; xps[i] = xp[b * NX + i]; }
+    for (int i = 0; i < NP; ++i) gs[i] = T(0);
+    int it;
+    const T l = cn::chain_loss_sample<T, N>(P, cfg, xs, xps, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr, &it);
+    if (force) for (int i = 0; i < NF; ++i) force[b * NF + i] = fo[i];
+    const T w = weight ? weight[b] : T(1);
+    for (int i = 0; i < NP; ++i) acc[i] += w * gs[i];
+    if (loss) loss[b] = l;
+    acc[NP] += l;
+    if (iters) iters[b] = it;
+  }
+  if (!partials) return;
+  __shared__ T red[kChThreads / 32][kChNAcc];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = 0; i <= NP; ++i) {
+    const T s = ch_warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x <= NP) {
+    T s = T(0);
+    for (int w = 0; w < kChThreads / 32; ++w) s += red[w][threadIdx.x];
+    partials[(int64_t)blockIdx.x * kChNAcc + threadIdx.x] = s;
+  }
+}
+
+template <typename T>
+__global__ void chain_reduce_kernel(const T* __restrict__ partials, int nblocks, int nparam, T* __restrict__ grad,
+                                    T* __restrict__ loss_sum) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int a = w; a <= nparam; a += blockDim.x >> 5) {
+    T s = T(0);
+    for (int b = lane; b < nblocks; b += 32) s += partials[(int64_t)b * kChNAcc + a];
+    s = ch_warp_sum(s);
+    if (lane == 0) {
+      if (a < nparam) { if (grad) grad[a] = s; }
+      else if (loss_sum) *loss_sum = s;
+    }
+  }
+}
+
+template <typename T, int N>
+__global__ void __launch_bounds__(kChThreads)
+chain_rollout_kernel(const T* __restrict__ x0, const T* __restrict__ inertia, const T* __restrict__ mu,
+                     const T* __restrict__ half, const T* __restrict__ kin, T dt, T eps, int64_t B, int steps,
+                     T* __restrict__ traj) {
+  constexpr int NX = 13 + 2 * (N - 1);
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  cn::ChainParams<T, N> P;
+  cn::chain_params_init<T, N>(P, inertia, mu, half, kin, dt, eps);
+  const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
+  T xc[NX], xn[NX];
+  T* out = traj + b * (int64_t)(steps + 1) * NX;
+  for (int i = 0; i < NX; ++i) { xc[i] = x0[b * NX + i]; out[i] = xc[i]; }
+  for (int s = 0; s < steps; ++s) {
+    cn::chain_step_sample<T, N>(P, cfg, xc, xn);
+    for (int i = 0; i < NX; ++i) { xc[i] = xn[i]; out[(int64_t)(s + 1) * NX + i] = xn[i]; }
+  }
+}
+
+template <int N>
+int launch_chain_loss(const double* x, const double* xp, const double* weight, const double* inertia, const double* mu,
+                      const double* half, const double* kin, double dt, double eps, int64_t B, double* loss, double* force,
+                      int32_t* iters, double* grad, double* loss_sum, void* workspace, size_t workspace_bytes,
+                      cudaStream_t st) {
+  const bool want_red = grad || loss_sum;
+  if (want_red && (!workspace || workspace_bytes < dpll_workspace_bytes())) return DPLL_EWORKSPACE;
+  int64_t need = (B + kChThreads - 1) / kChThreads;
+  int blocks = (int)(need < kChMaxBlocks ? need : kChMaxBlocks);
+  if (blocks < 1) blocks = 1;
+  double* partials = want_red ? static_cast<double*>(workspace) : nullptr;
+  chain_loss_kernel<double, N><<<blocks, kChThreads, 0, st>>>(x, xp, weight, inertia, mu, half, kin, dt, eps, B, loss, force,
+                                                             iters, partials, grad ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (want_red) {
+    chain_reduce_kernel<double><<<1, 512, 0, st>>>(partials, blocks, 14 * N, grad, loss_sum);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return DPLL_OK;
+}
+
+template <int N>
+int launch_chain_rollout(const double* x0, const double* inertia, const double* mu, const double* half, const double* kin,
+                         double dt, double eps, int64_t B, int steps, double* traj, cudaStream_t st) {
+  const int blocks = (int)((B + kChThreads - 1) / kChThreads);
+  chain_rollout_kernel<double, N><<<blocks, kChThreads, 0, st>>>(x0, inertia, mu, half, kin, dt, eps, B, steps, traj);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPLL_OK : (int)e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dpll_chain_loss_f64(int32_t n_links, const double* x, const double* x_plus, const double* weight, const double* inertia,
+                        const double* mu_pair, const double* half, const double* kin, double dt, double eps, int64_t B,
+                        double* loss, double* force, int32_t* iters, double* grad, double* loss_sum, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (B < 0 || !inertia || !mu_pair || !half || !kin) return DPLL_EINVAL;
+  if (B > 0 && (!x || !x_plus)) return DPLL_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (n_links) {
+    case 2: return launch_chain_loss<2>(x, x_plus, weight, inertia, mu_pair, half, kin, dt, eps, B, loss, force, iters, grad,
+                                        loss_sum, workspace, workspace_bytes, st);
+    case 3: return launch_chain_loss<3>(x, x_plus, weight, inertia, mu_pair, half, kin, dt, eps, B, loss, force, iters, grad,
+                                        loss_sum, workspace, workspace_bytes, st);
+    case 4: return launch_chain_loss<4>(x, x_plus, weight, inertia, mu_pair, half, kin, dt, eps, B, loss, force, iters, grad,
+                                        loss_sum, workspace, workspace_bytes, st);
+    default: return DPLL_EINVAL;
+  }
+}
+
+int dpll_chain_rollout_f64(int32_t n_links, const double* x0, const double* inertia, const double* mu_pair,
+                           const double* half, const double* kin, double dt, double eps, int64_t B, int32_t steps,
+                           double* traj, void* stream) {
+  if (B < 0 || steps < 0 || !inertia || !mu_pair || !half || !kin) return DPLL_EINVAL;
+  if (B > 0 && (!x0 || !traj)) return DPLL_EINVAL;
+  if (B == 0) return DPLL_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (n_links) {
+    case 2: return launch_chain_rollout<2>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, st);
+    case 3: return launch_chain_rollout<3>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, st);
+    case 4: return launch_chain_rollout<4>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, st);
+    default: return DPLL_EINVAL;
+  }
+}
+
+}  // extern "C"

@@ -105,6 +105,24 @@ class MultibodyLearnableSystem(System):
         kin, _ = self._elbow_kin(dtype, device)
         return inertia.reshape(20), mu.reshape(2), (torch.cat(half) if half else None), kin
 
+    def _chain_params(self, device: torch.device):
+        """Generic serial chain: (inertia (n*10), mu (n), half (n*3), kin (n*18), n), float64."""
+        inertia, mu, half = self.multibody_terms.kernel_parameters(torch.float64)
+        spec = self.multibody_terms.spec
+        n = len(spec.bodies)
+        key = ('chain', str(device))
+        if key not in self._kin_cache:
+            rows = []
+            for b in range(n):
+                if b == 0:
+                    rows += [0.] * 3 + [1., 0., 0., 0., 1., 0., 0., 0., 1.] + [0., 0., 1.]
+                else:
+                    j = spec.joints[b - 1]
+                    rows += [*j.origin, *j.rotation(), *j.axis]
+                rows += [*spec.geometries[b].offset]
+            self._kin_cache[key] = torch.tensor(rows, dtype=torch.float64, device=device)
+        return inertia.reshape(-1), mu.reshape(-1), torch.cat(half), self._kin_cache[key], n
+
     def _elbow_witness_points(self, q: Tensor) -> Tensor:
         """(B, 8) configurations -> (B, 8, 3) witness points of the two learned geometries against the
         ground: support direction of geometry i = minus the third row of its world rotation
@@ -167,6 +185,10 @@ class MultibodyLearnableSystem(System):
                 # mean() / sum() of the result reuse the launch's own reduction and fused gradient (ops.BatchLoss)
                 return ops.batch_loss(loss.reshape(batch), sums, means, 28, (inertia, mu, half),
                                       iters.reshape(batch) if self.record_newton_iters else None)
+        elif self._kind() == 'chain':
+            inertia, mu, half, kin, n = self._chain_params(x.device)
+            loss = ops.ChainContactNetsLoss.apply(self._flat(x).to(torch.float64), self._flat(x_plus).to(torch.float64),
+                                                  inertia, mu, half, kin, n, float(self.dt), LOSS_EPS).to(x.dtype)
         else:
             raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r}')
         return loss.reshape(batch)
@@ -219,6 +241,14 @@ class MultibodyLearnableSystem(System):
             else:
                 traj, _ = ops.elbow_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(), kin,
                                             float(self.dt), steps, STEP_EPS)
+        elif self._kind() == 'chain':
+            if torch.is_grad_enabled() and (x_0.requires_grad or any(p.requires_grad for p in self.multibody_terms.parameters())):
+                raise NotImplementedError('the generic chain rollout has no backward: evaluate it under torch.no_grad(), '
+                                          'or train with contactnets_loss')
+            with torch.no_grad():
+                inertia, mu, half, kin, n = self._chain_params(x_0.device)
+                traj = ops.chain_rollout(self._flat(x_0).to(torch.float64), inertia, mu, half, kin, n, float(self.dt),
+                                         steps, STEP_EPS).to(x_0.dtype)
         else:
             raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r}')
         return traj.reshape(batch + (steps + 1, self.space.n_x))

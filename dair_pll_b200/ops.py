@@ -642,6 +642,68 @@ def body_step_pts(x: Tensor, inertia: Tensor, mu_pair: Tensor, pts: Tensor, n_co
     return out
 
 
+class ChainContactNetsLoss(torch.autograd.Function):
+    """ContactNets loss of a generic floating-base serial chain of ``n`` links (``dpll_chain_loss_f64``,
+    csrc/cn_chain.cuh): differentiable w.r.t. inertia (n,10), mu_pair (n), half (n,3); float64."""
+
+    @staticmethod
+    def forward(ctx, x, x_plus, inertia, mu_pair, half, kin, n, dt, eps):
+        _check_inputs(x, x_plus, inertia, mu_pair, half, kin)
+        if x.dtype != torch.float64:
+            raise TypeError('the generic chain kernels are provided in float64')
+        n_x = 13 + 2 * (n - 1)
+        x, x_plus = x.contiguous(), x_plus.contiguous()
+        if x.dim() != 2 or x.shape[1] != n_x or x_plus.shape != x.shape:
+            raise ValueError(f'expected (B,{n_x}) states, got {tuple(x.shape)} / {tuple(x_plus.shape)}')
+        B, dev = x.shape[0], x.device
+        loss = torch.empty(B, dtype=x.dtype, device=dev)
+        ctx.args = (n, dt, eps)
+        ctx.shapes = (inertia.shape, mu_pair.shape, half.shape)
+        ctx.save_for_backward(x, x_plus, inertia, mu_pair, half, kin)
+        ws = _workspace(dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().dpll_chain_loss_f64(n, _ptr(x), _ptr(x_plus), None, _ptr(inertia.contiguous()),
+                                                 _ptr(mu_pair.contiguous()), _ptr(half.contiguous()), _ptr(kin.contiguous()),
+                                                 dt, eps, B, _ptr(loss), None, None, None, None, _ptr(ws), ws.numel(),
+                                                 _stream())
+        _lib.check(rc, 'dpll_chain_loss')
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        x, x_plus, inertia, mu_pair, half, kin = ctx.saved_tensors
+        n, dt, eps = ctx.args
+        B, dev = x.shape[0], x.device
+        g = torch.zeros(14 * n, dtype=x.dtype, device=dev)
+        if B > 0:
+            w = grad_loss.contiguous()
+            ws = _workspace(dev)
+            with torch.cuda.device(dev):
+                rc = _lib.load().dpll_chain_loss_f64(n, _ptr(x), _ptr(x_plus), _ptr(w), _ptr(inertia.contiguous()),
+                                                     _ptr(mu_pair.contiguous()), _ptr(half.contiguous()),
+                                                     _ptr(kin.contiguous()), dt, eps, B, None, None, None, _ptr(g), None,
+                                                     _ptr(ws), ws.numel(), _stream())
+            _lib.check(rc, 'dpll_chain_loss')
+        s_in, s_mu, s_h = ctx.shapes
+        return (None, None, g[:10 * n].reshape(s_in), g[10 * n:11 * n].reshape(s_mu), g[11 * n:].reshape(s_h), None, None,
+                None, None)
+
+
+def chain_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, kin: Tensor, n: int, dt: float,
+                  steps: int, eps: float = 1e-4) -> Tensor:
+    """(B, n_x) -> trajectory (B, steps+1, n_x) of a generic serial chain (``dpll_chain_rollout_f64``, no autograd)."""
+    _check_inputs(x0, inertia, mu_pair, half, kin)
+    x0 = x0.contiguous()
+    B = x0.shape[0]
+    traj = torch.empty((B, steps + 1, x0.shape[1]), dtype=x0.dtype, device=x0.device)
+    with torch.cuda.device(x0.device):
+        rc = _lib.load().dpll_chain_rollout_f64(n, _ptr(x0), _ptr(inertia.contiguous()), _ptr(mu_pair.contiguous()),
+                                                _ptr(half.contiguous()), _ptr(kin.contiguous()), dt, eps, B, steps,
+                                                _ptr(traj), _stream())
+    _lib.check(rc, 'dpll_chain_rollout')
+    return traj
+
+
 def cube_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor):
     """``dpll_cube_terms_f64``: (delassus (B,12,12), M (B,6,6), J (B,12,6), phi (B,4), acc (B,6)) in the order
     ``MultibodyTerms.forward`` returns them (multibody_terms.py:584-609).  fp64 only, no autograd."""

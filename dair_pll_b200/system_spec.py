@@ -74,11 +74,29 @@ class JointSpec:
     child: int
     origin: Tuple[float, float, float]
     axis: Tuple[float, float, float]
+    rpy: Tuple[float, float, float] = (0., 0., 0.)        # fixed rotation parent link -> joint frame
+
+    def rotation(self) -> Tuple[float, ...]:
+        """Row-major 3x3 of the URDF rotation R = Rz(yaw) Ry(pitch) Rx(roll)."""
+        return tuple(_rpy_matrix(self.rpy).reshape(-1).tolist())
+
+
+def _rpy_matrix(rpy) -> torch.Tensor:
+    r, p, y = (torch.tensor(float(v), dtype=torch.float64) for v in rpy)
+    cr, sr, cp, sp, cy, sy = torch.cos(r), torch.sin(r), torch.cos(p), torch.sin(p), torch.cos(y), torch.sin(y)
+    Rx = torch.stack((torch.stack((torch.ones(()).double(), torch.zeros(()).double(), torch.zeros(()).double())),
+                      torch.stack((torch.zeros(()).double(), cr, -sr)), torch.stack((torch.zeros(()).double(), sr, cr))))
+    Ry = torch.stack((torch.stack((cp, torch.zeros(()).double(), sp)),
+                      torch.stack((torch.zeros(()).double(), torch.ones(()).double(), torch.zeros(()).double())),
+                      torch.stack((-sp, torch.zeros(()).double(), cp))))
+    Rz = torch.stack((torch.stack((cy, -sy, torch.zeros(()).double())), torch.stack((sy, cy, torch.zeros(()).double())),
+                      torch.stack((torch.zeros(()).double(), torch.zeros(()).double(), torch.ones(()).double()))))
+    return Rz @ Ry @ Rx
 
 
 @dataclass
 class SystemSpec:
-    kind: str                                   # 'cube' (1 floating body) | 'elbow' (+1 hinge)
+    kind: str                                   # 'cube' (1 floating body) | 'elbow' (+1 hinge) | 'chain' (generic serial chain)
     bodies: List[BodySpec]
     joints: List[JointSpec]
     geometries: List[GeometrySpec]              # body geometries first, ground last
@@ -124,10 +142,16 @@ class SystemSpec:
                 raise NotImplementedError(f'link {link.get("name")} has no <inertial>')
             origin = inertial.find('origin')
             com = _floats(origin.get('xyz') if origin is not None else None, 3)
-            if origin is not None and any(abs(a) > 0 for a in _floats(origin.get('rpy'), 3)):
-                raise NotImplementedError('rotated inertial frames are not supported')
             ine = inertial.find('inertia')
             inertia_cm = tuple(float(ine.get(k)) for k in ('ixx', 'iyy', 'izz', 'ixy', 'ixz', 'iyz'))
+            irpy = _floats(origin.get('rpy'), 3) if origin is not None else (0., 0., 0.)
+            if any(abs(a) > 0 for a in irpy):
+                # a rotated inertial frame only re-expresses the constant inertia tensor: I_link = R I R^T (on the host)
+                xx, yy, zz, xy, xz, yz = inertia_cm
+                I = torch.tensor([[xx, xy, xz], [xy, yy, yz], [xz, yz, zz]], dtype=torch.float64)
+                R = _rpy_matrix(irpy)
+                I = R @ I @ R.t()
+                inertia_cm = (I[0, 0].item(), I[1, 1].item(), I[2, 2].item(), I[0, 1].item(), I[0, 2].item(), I[1, 2].item())
             names.append(link.get('name'))
             bodies.append(BodySpec(link.get('name'), float(inertial.find('mass').get('value')), com, inertia_cm))
             for col in link.findall('collision'):
@@ -160,8 +184,7 @@ class SystemSpec:
             if joint.get('type') not in ('continuous', 'revolute'):
                 raise NotImplementedError(f'joint type {joint.get("type")}')
             jo = joint.find('origin')
-            if jo is not None and any(abs(a) > 0 for a in _floats(jo.get('rpy'), 3)):
-                raise NotImplementedError('rotated joint frames are not supported')
+            jrpy = _floats(jo.get('rpy'), 3) if jo is not None else (0., 0., 0.)
             axis = joint.find('axis')
             ax = _floats(axis.get('xyz') if axis is not None else '1 0 0', 3)
             norm = sum(a * a for a in ax) ** 0.5
@@ -170,15 +193,19 @@ class SystemSpec:
             joints.append(JointSpec(names.index(joint.find('parent').get('link')),
                                     names.index(joint.find('child').get('link')),
                                     _floats(jo.get('xyz') if jo is not None else None, 3),
-                                    tuple(a / norm for a in ax)))        # Drake normalises the axis on parsing
+                                    tuple(a / norm for a in ax), jrpy))  # Drake normalises the axis on parsing
+        serial = len(joints) == len(bodies) - 1 and all(j.parent == k and j.child == k + 1 for k, j in enumerate(joints))
+        rotated = any(any(abs(a) > 0 for a in j.rpy) for j in joints)
         if len(bodies) == 1 and not joints:
             kind = 'cube'
-        elif len(bodies) == 2 and len(joints) == 1 and joints[0].parent == 0 and joints[0].child == 1:
-            kind = 'elbow'
+        elif len(bodies) == 2 and serial and not rotated:
+            kind = 'elbow'                      # the specialised two-body kernels
+        elif 2 <= len(bodies) <= 4 and serial:
+            kind = 'chain'                      # generic serial chain (csrc/cn_chain.cuh): rotated joint frames allowed
         else:
             raise NotImplementedError(
-                'kernels are specialised for a single floating body or a floating body with one '
-                'revolute child; arbitrary trees need the symbolic path (SURVEY.md section 8(f) N2)')
+                'kernels cover a single floating body, a floating body with one revolute child, and serial chains of '
+                'up to 4 links listed base to tip; branching trees need the symbolic path (SURVEY.md section 8(f) N2)')
         if kind == 'cube':
             if len(geometries) != 1:
                 raise NotImplementedError('the single-body kernels take exactly one collision geometry')
@@ -189,8 +216,10 @@ class SystemSpec:
                 raise NotImplementedError('a collision frame offset from the link origin is not supported for a single '
                                           'floating body (the two-body kernels take offsets)')
         else:
-            if len(geometries) != 2 or [g.body for g in geometries] != [0, 1]:
-                raise NotImplementedError('the two-body kernels take one collision geometry per link')
+            if [g.body for g in geometries] != list(range(len(bodies))):
+                raise NotImplementedError('the multi-link kernels take one collision geometry per link')
+            if kind == 'chain' and any(g.kind != 'box' for g in geometries):
+                raise NotImplementedError('the generic chain kernels take <box> collision geometries')
         if len({g.kind for g in geometries}) > 1:
             raise NotImplementedError('mixed box / mesh collision geometries in one system are not supported')
         ground = len(geometries)

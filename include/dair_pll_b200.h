@@ -353,6 +353,25 @@ int dpll_elbow_rollout_f32(const float* x0, const float* inertia, const float* m
                            void* stream);
 
 /*
+ * Generic floating-base serial chain (first slice): n_links = 2..4 rigid links joined by
+ * revolute joints, one box per link against the ground -- what the reference derives symbolically for any plant
+ * (multibody_terms.py:114-157, 267-319) evaluated by recursion over the links (csrc/cn_chain.cuh), for models the
+ * specialised cube / elbow kernels do not cover.  States (B, 13 + 2 (n-1)) = [quat | pos | joint angles | w_body |
+ * v_world | joint rates]; inertia (n, 10), mu_pair (n) (ground-link i), half (n, 3); kin (n, 18) per link =
+ * [joint origin in the parent link (3) | fixed rotation parent -> joint frame, row-major (9) | joint axis (3) | box
+ * offset in the link (3)] (row 0: only the box offset is used).  grad (14 n) = [d/d inertia (10 n) | d/d mu_pair (n) |
+ * d/d half (3 n)] of sum_b w_b loss_b; force (B, 12 n) = [normals (4 n) ; (tx, ty) (4 n)], links in order, contacts by
+ * ascending vertex index.  One sample per thread.  dpll_chain_rollout_f64: traj (B, steps+1, n_x).
+ */
+int dpll_chain_loss_f64(int32_t n_links, const double* x, const double* x_plus, const double* weight,
+                        const double* inertia, const double* mu_pair, const double* half, const double* kin,
+                        double dt, double eps, int64_t B, double* loss, double* force, int32_t* iters, double* grad,
+                        double* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
+int dpll_chain_rollout_f64(int32_t n_links, const double* x0, const double* inertia, const double* mu_pair,
+                           const double* half, const double* kin, double dt, double eps, int64_t B, int32_t steps,
+                           double* traj, void* stream);
+
+/*
  * FP64 / FP32 FMA throughput micro-benchmark used by bench.py to measure the CUDA-core
  * roofline denominator on the box it runs on (MEASURED_PEAKS.json carries no FP64
  * figure).  Launches `blocks` x 256 threads, each running `iters` x 16 independent FMAs

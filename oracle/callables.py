@@ -78,6 +78,16 @@ class TreeSpec:
     axis: List[Tuple[float, float, float]]
     geometry_body: List[int] = field(default_factory=list)
     geometry_offset: List[Tuple[float, float, float]] = field(default_factory=list)
+    joint_rpy: List[Tuple[float, float, float]] = field(default_factory=list)   # fixed rotation parent -> joint frame
+                                                                                # (URDF <origin rpy>); empty = none
+
+    def joint_rotation(self, i: int, dtype) -> Tensor:
+        """Fixed rotation of joint i's frame in its parent link (URDF convention R = Rz(yaw) Ry(pitch) Rx(roll))."""
+        if not self.joint_rpy:
+            return torch.eye(3, dtype=dtype)
+        r, p, y = (torch.tensor(v, dtype=dtype) for v in self.joint_rpy[i])
+        ex, ey, ez = (torch.tensor(v, dtype=dtype) for v in ((1., 0., 0.), (0., 1., 0.), (0., 0., 1.)))
+        return axis_rot(ez, y) @ axis_rot(ey, p) @ axis_rot(ex, r)
 
     @property
     def n_bodies(self) -> int:
@@ -104,6 +114,15 @@ ELBOW_TREE = TreeSpec(parent=[-1, 0], joint_origin=[(0., 0., 0.), (-0.035, 0.06,
                       axis=[(0., 0., 1.), (0., 1., 0.)],
                       geometry_body=[0, 1, -1],
                       geometry_offset=[(0., 0., 0.), (0.035, 0., 0.), (0., 0., 0.)])
+
+
+# a three-link chain with an off-axis, rotated second joint (tests of the generic chain kernels; not a reference asset)
+CHAIN3_TREE = TreeSpec(parent=[-1, 0, 1],
+                       joint_origin=[(0., 0., 0.), (-0.035, 0.06, 0.), (0.07, 0.01, -0.02)],
+                       axis=[(0., 0., 1.), (0., 1., 0.), (0.6, 0., 0.8)],
+                       geometry_body=[0, 1, 2, -1],
+                       geometry_offset=[(0., 0., 0.), (0.035, 0., 0.), (0.03, -0.01, 0.), (0., 0., 0.)],
+                       joint_rpy=[(0., 0., 0.), (0., 0., 0.), (0.3, -0.2, 0.5)])
 
 
 class TreeCallables:
@@ -135,7 +154,7 @@ class TreeCallables:
             p = tree.parent[i]
             a = torch.tensor(tree.axis[i], dtype=dt)
             pj = torch.tensor(tree.joint_origin[i], dtype=dt)
-            Rj = axis_rot(a, q[..., 6 + i])
+            Rj = tree.joint_rotation(i, dt) @ axis_rot(a, q[..., 6 + i])
             RjT = Rj.transpose(-1, -2)
             e = eye6[5 + i]
             R.append(R[p] @ Rj)

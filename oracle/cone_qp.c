@@ -34,8 +34,8 @@
 #include <omp.h>
 #endif
 
-#define MAXC 8
-#define MAXV 8
+#define MAXC 16
+#define MAXV 12
 #define MAXK (3 * MAXC)
 
 /* Projection of y=(t0,t1,n) onto L3 and (optionally) its Jacobian G (sym 3x3,

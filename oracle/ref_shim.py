@@ -88,7 +88,8 @@ def build_reference_system(kind: str, dt: float, pi_cm: torch.Tensor, friction: 
     from oracle.callables import TreeCallables, CUBE_TREE, ELBOW_TREE
     from oracle.cone_qp import OracleSAPSolver
 
-    tree = {'cube': CUBE_TREE, 'elbow': ELBOW_TREE}[kind]
+    from oracle.callables import CHAIN3_TREE
+    tree = kind if not isinstance(kind, str) else {'cube': CUBE_TREE, 'elbow': ELBOW_TREE, 'chain3': CHAIN3_TREE}[kind]
     calls = TreeCallables(tree)
 
     lt = LagrangianTerms.__new__(LagrangianTerms)

@@ -7,9 +7,37 @@
 #include "../../dair_pll_b200/csrc/cn_elbow_tangent.cuh"
 #include "../../dair_pll_b200/csrc/cn_cube_adjoint.cuh"
 #include "../../dair_pll_b200/csrc/cn_elbow_wf.cuh"
+#include "../../dair_pll_b200/csrc/cn_chain.cuh"
 #include <vector>
 #include <cstdint>
 using namespace cn;
+// generic serial chain (cn_chain.cuh), N = 2 or 3 links
+template <int N>
+static int chain_loss_emul(const double* x, const double* xp, const double* inertia, const double* mu, const double* half,
+                           const double* kin, double dt, double eps, int64_t B, double* loss, double* force, int32_t* iters,
+                           double* grad) {
+  ChainParams<double, N> P;
+  chain_params_init<double, N>(P, inertia, mu, half, kin, dt, eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  constexpr int NX = 13 + 2 * (N - 1);
+  for (int i = 0; i < 14 * N; ++i) grad[i] = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    int it;
+    loss[b] = chain_loss_sample<double, N>(P, cfg, x + NX * b, xp + NX * b, grad, force ? force + 12 * N * b : nullptr, &it);
+    if (iters) iters[b] = it;
+  }
+  return 0;
+}
+template <int N>
+static int chain_step_emul(const double* x, const double* inertia, const double* mu, const double* half, const double* kin,
+                           double dt, double eps, int64_t B, double* xn) {
+  ChainParams<double, N> P;
+  chain_params_init<double, N>(P, inertia, mu, half, kin, dt, eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  constexpr int NX = 13 + 2 * (N - 1);
+  for (int64_t b = 0; b < B; ++b) chain_step_sample<double, N>(P, cfg, x + NX * b, xn + NX * b);
+  return 0;
+}
 extern "C" {
 int emul_cube_loss_f64(const double* x, const double* xp, const double* inertia, const double* mu,
                        const double* half, double dt, double eps, int64_t B, double* loss, double* force,
@@ -81,6 +109,19 @@ int emul_cube_terms_f64(const double* q, const double* v, const double* inertia,
   for (int64_t b = 0; b < B; ++b)
     cube_terms_sample<double>(P, q + 7 * b, v + 6 * b, M + 36 * b, J + 72 * b, phi + 4 * b, acc + 6 * b, D + 144 * b);
   return 0;
+}
+int emul_chain_loss_f64(int n, const double* x, const double* xp, const double* inertia, const double* mu,
+                        const double* half, const double* kin, double dt, double eps, int64_t B, double* loss, double* force,
+                        int32_t* iters, double* grad) {
+  if (n == 2) return chain_loss_emul<2>(x, xp, inertia, mu, half, kin, dt, eps, B, loss, force, iters, grad);
+  if (n == 3) return chain_loss_emul<3>(x, xp, inertia, mu, half, kin, dt, eps, B, loss, force, iters, grad);
+  return -1;
+}
+int emul_chain_step_f64(int n, const double* x, const double* inertia, const double* mu, const double* half,
+                        const double* kin, double dt, double eps, int64_t B, double* xn) {
+  if (n == 2) return chain_step_emul<2>(x, inertia, mu, half, kin, dt, eps, B, xn);
+  if (n == 3) return chain_step_emul<3>(x, inertia, mu, half, kin, dt, eps, B, xn);
+  return -1;
 }
 // single floating body with witness points (Sphere / Polygon / any plane-convex pair)
 int emul_body_loss_pts_f64(const double* x, const double* xp, const double* inertia, const double* mu, const double* pts,

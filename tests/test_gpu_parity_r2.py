@@ -467,3 +467,65 @@ def test_warm_started_solves_give_the_same_results_in_fewer_iterations(assets_di
     assert torch.allclose(l1.detach(), l0.detach(), rtol=1e-12, atol=1e-18)
     ds.update_solutions(torch.tensor([0]), l0.qp_solution[:1])
     assert ds.warm_start(torch.tensor([0])).shape == (1, 6)
+
+
+def _chain_system(g, urdf, n):
+    s = MultibodyLearnableSystem({'chain': urdf}, float(g['dt']))
+    sd = {'multibody_terms.lagrangian_terms.inertial_parameters': torch.from_numpy(g['theta']),
+          'multibody_terms.contact_terms.friction_params': torch.from_numpy(g['friction_params'])}
+    for i in range(n):
+        sd[f'multibody_terms.contact_terms.geometries.{i}.length_params'] = torch.from_numpy(g['half_lengths'][i]).reshape(1, 3)
+    s.load_state_dict(sd)
+    return s.to(DEV)
+
+
+def test_generic_chain_three_links_matches_reference_golden(assets_dir):
+    """N2 first slice: a three-link URDF with a rotated, off-axis second joint goes URDF -> SystemSpec -> the generic
+    serial-chain kernels; losses, every parameter gradient and a time step against the reference's own
+    contactnets_loss / sim_step (tests/golden/chain3.npz, oracle/gen_golden_chain.py)."""
+    g = load_golden('chain3')
+    s = _chain_system(g, os.path.join(assets_dir, 'chain3.urdf'), 3)
+    assert s._kind() == 'chain' and s.space.n_x == 17
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    loss = s.contactnets_loss(x, None, xp)
+    loss.mean().backward()
+    l = loss.detach().cpu().numpy()
+    assert np.abs(l - g['loss']).max() < 1e-12
+    assert rel_err(l, g['loss'], 1e-9).max() < 1e-9
+    gt, gf, *gl = _leaf_grads(s)
+    assert max_rel_to_scale(gt, g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(gf, g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(np.stack([a.reshape(3) for a in gl]), g['grad_length']) < 1e-9
+    with torch.no_grad():
+        traj, _ = s.simulate(x.unsqueeze(-2), torch.zeros(x.shape[0], 1, device=DEV), 3)
+    t = traj.cpu().numpy()
+    assert np.abs(t[:, 1] - g['x_next']).max() < 1e-9
+    assert np.isfinite(t).all() and np.abs(np.linalg.norm(t[:, :, :4], axis=-1) - 1).max() < 1e-12
+    # the rollout is the step applied repeatedly
+    with torch.no_grad():
+        one, _ = s.simulate(traj[:, 1:2], torch.zeros(x.shape[0], 1, device=DEV), 1)
+    assert (one[:, 1] - traj[:, 2]).abs().max().item() < 1e-12
+    with pytest.raises(NotImplementedError):
+        s.simulate(x.unsqueeze(-2), torch.zeros(x.shape[0], 1, device=DEV), 1)     # no backward for the generic rollout
+
+
+@pytest.mark.parametrize('name', ['elbow_nominal', 'elbow_perturbed'])
+def test_generic_chain_two_links_reproduces_the_elbow_kernels(name, assets_dir):
+    """The generic recursion at N = 2 against the reference goldens of the elbow AND against the specialised kernels."""
+    g = load_golden(name)
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    s = _chain_system(g, os.path.join(assets_dir, 'elbow.urdf'), 2)
+    inertia, mu, half, kin = (t.detach() for t in s._elbow_params(torch.float64, torch.device(DEV)))
+    kin18 = torch.tensor([0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1, *kin[6:9].tolist(),
+                          *kin[0:3].tolist(), 1, 0, 0, 0, 1, 0, 0, 0, 1, *kin[3:6].tolist(), *kin[9:12].tolist()],
+                         dtype=torch.float64, device=DEV)
+    inertia.requires_grad_(); mu.requires_grad_(); half.requires_grad_()
+    loss = ops.ChainContactNetsLoss.apply(x, xp, inertia, mu, half, kin18, 2, float(g['dt']), 1e-3)
+    loss.sum().backward()
+    l = loss.detach().cpu().numpy()
+    assert rel_err(l, g['loss'], 1e-9).max() < 1e-9
+    ref_loss, ref_grad, _, _, _ = ops.elbow_loss_raw(x, xp, inertia.detach(), mu.detach(), half.detach(), kin,
+                                                     float(g['dt']), 1e-3)
+    assert rel_err(l, ref_loss.cpu().numpy(), 1e-9).max() < 1e-10
+    mine = torch.cat((inertia.grad.reshape(-1), mu.grad, half.grad.reshape(-1))).cpu().numpy()
+    assert max_rel_to_scale(mine, ref_grad.cpu().numpy()) < 1e-10

@@ -405,3 +405,95 @@ def test_witness_point_device_math_matches_reference_golden(name):
     lib.emul_body_step_pts_f64(dptr(x), dptr(inertia), dptr(mu), dptr(pts0), ctypes.c_int(n_c),
                                ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-4), ctypes.c_int64(B), dptr(xn))
     assert np.abs(xn - g['x_next']).max() < 1e-9
+
+
+# ---- generic serial chain (cn_chain.cuh) -----------------------------------------------------------
+
+def chain_kin_rows(tree):
+    """(n, 18) kinematic table of dpll_chain_*: [joint origin | fixed rotation row-major | axis | box offset]."""
+    rows = []
+    for b in range(tree.n_bodies):
+        Rfix = tree.joint_rotation(b, torch.float64).numpy().reshape(-1) if b > 0 else np.eye(3).reshape(-1)
+        rows.append(np.concatenate((tree.joint_origin[b], Rfix, tree.axis[b], tree.geometry_offset[b])))
+    return np.ascontiguousarray(np.stack(rows))
+
+
+def chain_kernel_level_params(g, n):
+    inertia = co.theta_to_inertia_vector(torch.from_numpy(g['theta'])).reshape(10 * n).numpy()
+    mu = np.abs(g['friction_params'])
+    mu_pair = np.array([2 * mu[n] * mu[i] / (mu[n] + mu[i]) for i in range(n)])
+    return inertia, mu_pair, np.abs(g['half_lengths']).reshape(3 * n).copy()
+
+
+def chain_grad_to_leaves(g, grad, n):
+    theta = torch.from_numpy(g['theta']).clone().requires_grad_()
+    fr = torch.from_numpy(g['friction_params']).clone().requires_grad_()
+    ln = torch.from_numpy(g['half_lengths']).clone().requires_grad_()
+    mu = fr.abs()
+    flat = torch.cat((co.theta_to_inertia_vector(theta).reshape(10 * n),
+                      torch.stack([2 * mu[n] * mu[i] / (mu[n] + mu[i]) for i in range(n)]), ln.abs().reshape(3 * n)))
+    flat.backward(torch.from_numpy(np.asarray(grad, dtype=np.float64)))
+    return theta.grad.numpy(), fr.grad.numpy(), ln.grad.numpy()
+
+
+def emul_chain_loss(n, g, kin, x, xp, eps=1e-3):
+    lib = host_emulation_lib()
+    inertia, mu, half = chain_kernel_level_params(g, n)
+    B = x.shape[0]
+    loss, force, iters, grad = np.zeros(B), np.zeros((B, 12 * n)), np.zeros(B, np.int32), np.zeros(14 * n)
+    rc = lib.emul_chain_loss_f64(ctypes.c_int(n), dptr(x), dptr(xp), dptr(inertia), dptr(mu), dptr(half), dptr(kin),
+                                 ctypes.c_double(float(g['dt'])), ctypes.c_double(eps), ctypes.c_int64(B), dptr(loss),
+                                 dptr(force), dptr(iters), dptr(grad))
+    assert rc == 0
+    return loss, force, iters, grad
+
+
+def test_chain3_device_math_matches_reference_golden():
+    """Three links, rotated off-axis second joint: loss, parameter gradients and one time step against the REFERENCE's
+    own contactnets_loss / sim_step run on oracle/callables.py:CHAIN3_TREE (oracle/gen_golden_chain.py)."""
+    from oracle.callables import CHAIN3_TREE
+    g = load_golden('chain3')
+    kin = chain_kin_rows(CHAIN3_TREE)
+    x, xp = np.ascontiguousarray(g['x']), np.ascontiguousarray(g['x_plus'])
+    B = x.shape[0]
+    loss, _, iters, grad = emul_chain_loss(3, g, kin, x, xp)
+    assert np.abs(loss - g['loss']).max() < 1e-12
+    assert rel_err(loss, g['loss'], 1e-9).max() < 1e-9
+    gt, gf, gl = chain_grad_to_leaves(g, grad / B, 3)
+    assert max_rel_to_scale(gt, g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(gf, g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(gl, g['grad_length']) < 1e-9
+    assert iters.max() <= 60
+    inertia, mu, half = chain_kernel_level_params(g, 3)
+    xn = np.zeros_like(x)
+    rc = host_emulation_lib().emul_chain_step_f64(ctypes.c_int(3), dptr(x), dptr(inertia), dptr(mu), dptr(half), dptr(kin),
+                                                  ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-4),
+                                                  ctypes.c_int64(B), dptr(xn))
+    assert rc == 0
+    assert np.abs(xn - g['x_next']).max() < 1e-9
+
+
+@pytest.mark.parametrize('name', ['elbow_nominal', 'elbow_perturbed'])
+def test_chain2_reproduces_the_elbow_goldens(name):
+    """The hand-derived two-body kernels are the N = 2 instance of the generic recursion: same reference goldens."""
+    from oracle.callables import ELBOW_TREE
+    g = load_golden(name)
+    kin = chain_kin_rows(ELBOW_TREE)
+    x, xp = np.ascontiguousarray(g['x']), np.ascontiguousarray(g['x_plus'])
+    B = x.shape[0]
+    loss, force, _, grad = emul_chain_loss(2, g, kin, x, xp)
+    assert np.abs(loss - g['loss']).max() < 1e-12
+    assert rel_err(loss, g['loss'], 1e-9).max() < 1e-9
+    scale = np.maximum(np.abs(g['force']).max(axis=1, keepdims=True), 1e-6)
+    assert (np.abs(force - g['force']) / scale).max() < 1e-7
+    gt, gf, gl = chain_grad_to_leaves(g, grad / B, 2)
+    assert max_rel_to_scale(gt, g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(gf, g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(gl, g['grad_length']) < 1e-9
+    inertia, mu, half = chain_kernel_level_params(g, 2)
+    x0 = np.ascontiguousarray(g['sim_x0'])
+    xn = np.zeros_like(x0)
+    host_emulation_lib().emul_chain_step_f64(ctypes.c_int(2), dptr(x0), dptr(inertia), dptr(mu), dptr(half), dptr(kin),
+                                             ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-4),
+                                             ctypes.c_int64(x0.shape[0]), dptr(xn))
+    assert np.abs(xn - g['sim_traj'][:, 1]).max() < 1e-9

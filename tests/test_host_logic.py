@@ -287,3 +287,24 @@ def test_urdf_ingestion_rejects_what_the_kernels_do_not_model(tmp_path):
     p2.write_text(elbow.replace('<axis xyz="0 1 0"', '<axis xyz="0 2 0"', 1))
     spec = SystemSpec.from_urdf(str(p2))
     assert spec.joints[0].axis == (0.0, 1.0, 0.0)
+
+
+def test_chain_spec_carries_rotated_joint_frames(assets_dir):
+    """N2 first slice: a three-link serial chain parses into the 'chain' kind; the kinematic table handed to
+    dpll_chain_* (joint origin | fixed joint-frame rotation | axis | box offset per link) equals the one the
+    oracle's tree code (oracle/callables.py:CHAIN3_TREE) is built from."""
+    from oracle.callables import CHAIN3_TREE
+    from tests.test_host_emulation import chain_kin_rows
+    s = MultibodyLearnableSystem({'chain3': os.path.join(assets_dir, 'chain3.urdf')}, 0.0068)
+    spec = s.multibody_terms.spec
+    assert (spec.kind, spec.n_q, spec.n_v, spec.n_x, spec.n_contacts) == ('chain', 9, 8, 17, 12)
+    assert spec.collision_pairs == [(3, 0), (3, 1), (3, 2)]
+    inertia, mu, half, kin, n = s._chain_params(torch.device('cpu'))
+    assert n == 3 and inertia.shape == (30,) and mu.shape == (3,) and half.shape == (9,)
+    assert np.allclose(kin.numpy().reshape(3, 18), chain_kin_rows(CHAIN3_TREE), rtol=0, atol=1e-15)
+    names = [k for k, _ in s.named_parameters()]
+    assert 'multibody_terms.contact_terms.geometries.2.length_params' in names
+    x = torch.zeros(2, 17, dtype=torch.float64)
+    x[:, 0] = 1
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        s.contactnets_loss(x, torch.zeros(2, 0), x)
