@@ -7,9 +7,9 @@ input-Jacobian of f(d) = |w_out| . s(|W_h|^T s(W_d0^T d) + W_d1^T d), s = LeakyR
 the hand-written Jacobian recursion of ``:238-266``.
 
 Device path: :class:`ICNNSupport` is a ``torch.autograd.Function`` with an explicit forward and
-backward.  The work is GEMM-shaped with weights shared by the whole batch -- two
-(D x W x W) products forward, one backward -- which run as FP64 library GEMMs between the fused layers;
-only the activation masks are kept between the passes (no autograd graph of elementwise ops).
+backward.  The forward over all D rows is one tensor-core kernel (csrc/cn_icnn_tc.cu: the layer
+Jacobians as exact int8 slice products on tcgen05, ``ops.icnn_support_points``); the backward visits only the rows
+with a non-zero cotangent.
 Mesh extraction (``extract_mesh`` / ``extract_obj``, :19-122) is logging/export code and stays
 with the reference.  Depth is fixed at 2 (the reference's default, ``geometry.py:50``).
 """
@@ -31,25 +31,32 @@ def icnn_weight_gradients(Wd1: Tensor, Wh: Tensor, wout: Tensor, g1: Tensor, gWd
 
 
 class ICNNSupport(torch.autograd.Function):
-    """p (D,3) = d f / d direction for directions d (D,3); differentiable w.r.t. the four weights.  CUDA only:
-    the fused memory-bound layers of csrc/cn_icnn.cu around FP64 GEMMs (there is no CPU path)."""
+    """p (D,3) = d f / d direction for directions d (D,3); differentiable w.r.t. the four weights.  CUDA only (there is
+    no CPU path).
+
+    Forward: every row (``ops.icnn_support_points``).  Nothing of size (D x width) is kept for the backward: a row whose
+    cotangent is exactly zero contributes exactly zero to every weight gradient, and in the ContactNets loss only the
+    witness points of contacts that carry force or penetrate have a non-zero cotangent (3.7% of the rows of the
+    config-3 batch, tools/exp_active_rows.py) -- so the backward gathers those rows, re-evaluates their activation
+    masks and runs the three reductions on them alone."""
 
     @staticmethod
     def forward(ctx, d, Wd0, Wd1, Wh, wout, slope):
-        # deep_support_function.py:251-264 with hj = |w_out| * m1 folded into the small matrices, so the only
-        # (D x width) intermediates are the two slope masks and a0
         if not d.is_cuda:
             raise RuntimeError('dair_pll_b200 has no CPU path: support-function networks are evaluated on a CUDA device')
         from dair_pll_b200 import ops
-        p, h0aug, m1, a0 = ops.icnn_support_forward(d, Wd0, Wd1, Wh, wout, float(slope))
-        ctx.save_for_backward(Wd0, Wd1, Wh, wout, h0aug, m1, a0)
+        ctx.save_for_backward(d, Wd0, Wd1, Wh, wout)
         ctx.slope = float(slope)
-        return p
+        return ops.icnn_support_points(d, Wd0, Wd1, Wh, wout, float(slope))
 
     @staticmethod
     def backward(ctx, gp):
         from dair_pll_b200 import ops
-        Wd0, Wd1, Wh, wout, h0aug, m1, a0 = ctx.saved_tensors
+        d, Wd0, Wd1, Wh, wout = ctx.saved_tensors
+        rows = torch.nonzero((gp != 0).any(-1)).reshape(-1)        # one host read (the row count sizes the launches)
+        if rows.numel() < gp.shape[0]:
+            d, gp = d.index_select(0, rows), gp.index_select(0, rows)
+        _, h0aug, m1, a0 = ops.icnn_support_forward(d, Wd0, Wd1, Wh, wout, ctx.slope)
         g1, gWd0, G = ops.icnn_support_backward(gp.contiguous(), h0aug, m1, a0, Wd0, ctx.slope)
         return (None,) + icnn_weight_gradients(Wd1, Wh, wout, g1, gWd0, G) + (None,)
 

@@ -746,6 +746,38 @@ def elbow_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Te
     return D, M, J, phi, acc
 
 
+def icnn_support_points(d: Tensor, Wd0: Tensor, Wd1: Tensor, Wh: Tensor, wout: Tensor, slope: float) -> Tensor:
+    """Support points p (D,3) for unit directions d (D,3), nothing kept for a backward (``ICNNSupport.forward``).
+    Width 256: the tensor-core kernel (``icnn_support_points_tc``); other widths: the FP64 layer path."""
+    if Wd0.shape[1] == ICNN_TC_WIDTH and not ICNN_FORCE_FP64_PATH:
+        return icnn_support_points_tc(d, Wd0, Wd1, Wh, wout, slope)
+    return icnn_support_forward(d, Wd0, Wd1, Wh, wout, slope)[0]
+
+
+def icnn_support_points_tc(d: Tensor, Wd0: Tensor, Wd1: Tensor, Wh: Tensor, wout: Tensor, slope: float) -> Tensor:
+    """``dpll_icnn_tc_prepare_f64`` + ``dpll_icnn_tc_support_f64``: support points (D,3) on the tensor cores."""
+    _check_inputs(d, Wd0, Wd1, Wh, wout)
+    if d.dtype != torch.float64:
+        raise TypeError('the support-network kernels are provided in float64')
+    lib = _lib.load()
+    d, Wd0, Wd1, Wh, wout = (t.contiguous() for t in (d, Wd0, Wd1, Wh, wout))
+    D, W = d.shape[0], Wd0.shape[1]
+    dev = d.device
+    image = torch.empty(lib.dpll_icnn_tc_image_bytes(), dtype=torch.uint8, device=dev)
+    consts = torch.empty(lib.dpll_icnn_tc_const_bytes() // 8, dtype=torch.float64, device=dev)
+    p = torch.empty((D, 3), dtype=d.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dpll_icnn_tc_prepare_f64(_ptr(Wd0), _ptr(Wd1), _ptr(Wh), _ptr(wout), W, slope, _ptr(image),
+                                                _ptr(consts), _stream()), 'dpll_icnn_tc_prepare')
+        _lib.check(lib.dpll_icnn_tc_support_f64(_ptr(d), D, _ptr(image), _ptr(consts), _ptr(Wh), W, slope, _ptr(p),
+                                                _stream()), 'dpll_icnn_tc_support')
+    return p
+
+
+ICNN_TC_WIDTH = 256
+ICNN_FORCE_FP64_PATH = False        # tests / A-B timing: route width-256 networks through the FP64 layer path too
+
+
 def icnn_support_forward(d: Tensor, Wd0: Tensor, Wd1: Tensor, Wh: Tensor, wout: Tensor, slope: float):
     """Support points p (D,3) of the depth-2 homogeneous ICNN for unit directions d (D,3), float64, CUDA:
     the ``dpll_icnn_*`` kernels around two FP64 GEMMs.  Returns (p, h0aug, m1, a0) -- the last three are what

@@ -222,6 +222,22 @@ int dpll_icnn_backward_f64(const double* gp, const double* h0aug, const double* 
                            int64_t D, int32_t W, double slope, double* t, double* part, void* stream);
 
 /*
+ * Support points on the tensor cores (csrc/cn_icnn_tc.cu; width W = 256 only): HomogeneousICNN.forward
+ * (deep_support_function.py:238-266) for all D direction rows in one kernel.  The layer Jacobian d z1 / d d is a
+ * (binary mask) x (constant matrix) product, evaluated exactly as int8 digit-plane products by tcgen05.mma with int32
+ * accumulators in tensor memory and rebuilt in fp64 per row (42-bit fixed point per weight column; rows whose
+ * pre-activation is within 1e-9 of zero are re-evaluated in plain fp64 before the mask is taken).  No (D x W) array
+ * exists in HBM.  dpll_icnn_tc_prepare_f64 turns the four weights into the digit-plane image (dpll_icnn_tc_image_bytes())
+ * and the epilogue constants (dpll_icnn_tc_const_bytes()); run it whenever the weights change.
+ */
+size_t dpll_icnn_tc_image_bytes(void);
+size_t dpll_icnn_tc_const_bytes(void);
+int dpll_icnn_tc_prepare_f64(const double* Wd0, const double* Wd1, const double* Wh, const double* wout, int32_t W,
+                             double slope, void* image, double* consts, void* stream);
+int dpll_icnn_tc_support_f64(const double* d, int64_t D, const void* image, const double* consts, const double* Wh,
+                             int32_t W, double slope, double* p, void* stream);
+
+/*
  * A single floating body whose collision geometry is ANY convex shape against the ground plane
  * (GeometryCollider.collide_plane_convex, dair_pll/geometry.py:553-582): the caller passes the shape's support
  * points in the direction -R^T e_z -- Sphere: 1 point d r (geometry.py:415-456); Polygon: the top-n_query vertices
