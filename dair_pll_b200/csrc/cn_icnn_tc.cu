@@ -1,16 +1,21 @@
 // Support points of the depth-2 homogeneous ICNN (HomogeneousICNN.forward, dair_pll/deep_support_function.py:238-266;
 // called per contact by DeepSupportConvex.get_vertices, geometry.py:309-325) for ALL direction rows of a batch in one
-// kernel on the sm_100a tensor cores: tcgen05.mma kind::i8 with int32 accumulators in TMEM, operands in shared memory,
-// one thread per direction row for the prologue (slope-mask bits of layer 0) and the epilogue (fp64 reconstruction of
-// the layer Jacobian, layer-1 mask, support point).  See cn_icnn_tc.cuh for the mathematics.
+// kernel on the sm_100a tensor cores: tcgen05.mma kind::i8 with int32 accumulators in TMEM.  See cn_icnn_tc.cuh for
+// the mathematics (layer Jacobian = binary mask x constant matrix, as exact int8 digit-plane products).
 //
-// Per CTA (128 threads, one per SM, persistent over 128-row tiles):
-//   A operand   the tile's mask bits as bytes, twice: values {0, 1} and {0, -128}; K-major, no swizzle (64 KB)
-//   B operand   digit planes of Q_k for a (chunk of 32 hidden units, k) unit: 6 planes x (32 x 256) int8 = 48 KB, copied
-//               from the prepared image (L2-resident, 1.18 MB) by cp.async.bulk into a two-deep ring
-//   TMEM        9 accumulators (3 k x 3 plane pairs) of 128 lanes x 32 columns
-//   per chunk   3 units x 6 planes x 8 k-steps = 144 MMAs (M 128, N 32, K 32), one commit, then the epilogue of the
-//               chunk's 32 hidden units straight out of TMEM (tcgen05.ld 32x32b)
+// One persistent CTA per SM, 128-row tiles, warp-specialised (320 threads):
+//   warps 0-7   prologue + epilogue.  Thread = (TMEM lane = direction row, column half).  Prologue: slope-mask bits of
+//               layer 0 as the two byte-valued A operands ({0, 1} and {0, -128}), written straight into TENSOR MEMORY
+//               (tcgen05.st; the MMA then takes A from TMEM and reads only the 1 KB B tile from shared memory -- with A
+//               in shared memory a 128 x 32 B re-read per MMA made the N = 32 products four times slower).  Epilogue:
+//               accumulators -> fp64 Jacobian (exact integer Horner) -> z1, layer-1 mask, support point, in registers.
+//   warp 8      producer: digit planes of one (chunk of 32 hidden units, input coordinate k) unit = 6 planes x (32 x 256)
+//               int8 = 48 KB per cp.async.bulk from the prepared image (L2-resident, 1.18 MB) into a 3-slot ring.
+//   warp 9      MMA issuer: 48 MMAs (M 128, N 32, K 32) per unit into that k's three accumulators; tcgen05.commit
+//               releases the ring slot and publishes the accumulators.
+// The three accumulator sets (one per k) are handed back by the epilogue as soon as they are in registers, so the
+// tensor pipe works on (chunk c, k+1 ...) while the CUDA cores finish (chunk c, k).
+// TMEM columns: [0, 64) A {0,1}; [64, 128) A {0,-128}; [128 + 96 k + 32 t, +32) accumulator t of coordinate k.
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -21,14 +26,18 @@ namespace {
 
 using namespace cn;
 
-constexpr int kThreads = 128;
+constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kThreads = kEpiThreads + 64;
 constexpr int kTileRows = 128;
-constexpr int kSmemA = kTileRows * TC_W;                  // 32 KB per copy
-constexpr int kOffAlo = 0, kOffAhi = kSmemA, kOffB = 2 * kSmemA, kOffC = kOffB + 2 * TC_UNIT_BYTES,
-              kOffBar = kOffC + TC_NCONST * 8, kSmemBytes = kOffBar + 64;
+constexpr int kSlots = 3;
+constexpr int kOffB = 0, kOffC = kOffB + kSlots * TC_UNIT_BYTES, kOffP = kOffC + TC_NCONST_SMEM * 8,
+              kOffBar = kOffP + 2 * kTileRows * 3 * 8, kSmemBytes = kOffBar + 128;
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColAlo = 0, kColAhi = 64, kColAcc = 128;
 // instruction descriptor, kind::i8: D s32 (2 << 4), A s8 (1 << 7), B s8 (1 << 10), both K-major, N >> 3 at 17, M >> 4 at 24
 constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// barrier indices
+constexpr int kBarFull = 0, kBarEmpty = kSlots, kBarAccFull = 2 * kSlots, kBarAccEmpty = 2 * kSlots + 3,
+              kBarAReady = 2 * kSlots + 6, kNumBars = 2 * kSlots + 7;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -38,7 +47,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// bounded spin (a protocol error must not hang the device): traps after ~2 s
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded spin (a protocol error must not hang the device): traps after a few seconds
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     uint32_t ok;
@@ -65,38 +77,55 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(2048u >> 4) << 32) |
          ((uint64_t)1 << 46);
 }
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n"
       "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+      "r"(tmem_a), "l"(bdesc), "r"(kIdesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// int32 -> double without the conversion unit: bits [2^52 + 2^31 + x] minus the constant (exact)
+__device__ __forceinline__ double i2d(int32_t x) {
+  return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;
+}
 
 // z1_i in plain fp64 for one row (the rare |z1| ~ 0 case, where a 42-bit Jacobian must not decide the mask)
-__device__ __noinline__ double exact_z1(const double* sC, const double* __restrict__ Wh, double dx, double dy, double dz,
-                                        double slope, int i) {
-  const double* W0 = sC + TC_C_WD0;
+__device__ __noinline__ double exact_z1(const double* sW0, const double* __restrict__ Wd1, const double* __restrict__ Wh,
+                                        double dx, double dy, double dz, double slope, int i) {
   double z = 0;
   for (int j = 0; j < TC_W; ++j) {
-    const double lin = dx * W0[j] + dy * W0[TC_W + j] + dz * W0[2 * TC_W + j];
+    const double lin = dx * sW0[j] + dy * sW0[TC_W + j] + dz * sW0[2 * TC_W + j];
     z += (lin > 0 ? lin : slope * lin) * fabs(Wh[j * TC_W + i]);
   }
-  const double* W1 = sC + TC_C_WD1;
-  return z + (dx * W1[i] + dy * W1[TC_W + i] + dz * W1[2 * TC_W + i]);
+  return z + (dx * Wd1[i] + dy * Wd1[TC_W + i] + dz * Wd1[2 * TC_W + i]);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -104,14 +133,17 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const uint8_t* __restric
                const double* __restrict__ Wh, double slope, double* __restrict__ p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   double* sC = reinterpret_cast<double*>(smem + kOffC);
+  double* sP = reinterpret_cast<double*>(smem + kOffP);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 48);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t sAlo = smem_u32(smem + kOffAlo), sAhi = smem_u32(smem + kOffAhi), sB = smem_u32(smem + kOffB);
-  const uint32_t bar_full0 = smem_u32(&bars[0]), bar_mma0 = smem_u32(&bars[2]), bar_chunk = smem_u32(&bars[4]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * kNumBars);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar = [bar0](int i) { return bar0 + 8u * (uint32_t)i; };
 
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    for (int s = 0; s < kSlots; ++s) { mbar_init(bar(kBarFull + s), 1); mbar_init(bar(kBarEmpty + s), 1); }
+    for (int k = 0; k < 3; ++k) { mbar_init(bar(kBarAccFull + k), 1); mbar_init(bar(kBarAccEmpty + k), kEpiWarps); }
+    mbar_init(bar(kBarAReady), kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -119,122 +151,149 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const uint8_t* __restric
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < TC_NCONST; i += kThreads) sC[i] = consts[i];
+  for (int i = tid; i < TC_NCONST_SMEM; i += kThreads) sC[i] = consts[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
-
   const int64_t ntiles = (D + kTileRows - 1) / kTileRows;
-  uint32_t gu = 0;          // units issued so far by this CTA (identical in every thread)
-  uint32_t chunks_done = 0;
-  if (tid == 0 && (int64_t)blockIdx.x < ntiles) {
-    mbar_expect_tx(bar_full0, TC_UNIT_BYTES);
-    bulk_g2s(sB, img, TC_UNIT_BYTES, bar_full0);
-  }
-  const double* W0 = sC + TC_C_WD0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t row = tile * kTileRows + tid;
-    const bool valid = row < D;
-    const bool last_tile = tile + gridDim.x >= ntiles;
-    double dx = 0, dy = 0, dz = 0;
-    if (valid) { dx = d[3 * row]; dy = d[3 * row + 1]; dz = d[3 * row + 2]; }
-    // ---- prologue: slope-mask bits of layer 0 as the two byte-valued A operands ----
-    {
-      uint8_t* a_lo = smem + kOffAlo + (tid >> 3) * 2048 + (tid & 7) * 16;
-      uint8_t* a_hi = smem + kOffAhi + (tid >> 3) * 2048 + (tid & 7) * 16;
-#pragma unroll 1
-      for (int jc = 0; jc < TC_W / 16; ++jc) {
-        uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const int j = jc * 16 + jj;
-          const double lin = dx * W0[j] + dy * W0[TC_W + j] + dz * W0[2 * TC_W + j];
-          w[jj >> 2] |= (lin > 0 ? 1u : 0u) << (8 * (jj & 3));
-        }
-        *reinterpret_cast<uint4*>(a_lo + jc * 128) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(a_hi + jc * 128) = make_uint4(w[0] << 7, w[1] << 7, w[2] << 7, w[3] << 7);
+  const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+  if (warp == kEpiWarps) {
+    // ===== producer =====
+    if (lane == 0) {
+      const uint32_t sB = smem_u32(smem + kOffB);
+      const int64_t total = my_tiles * TC_UNITS;
+      for (int64_t g = 0; g < total; ++g) {
+        const int s = (int)(g % kSlots);
+        const uint32_t use = (uint32_t)(g / kSlots);
+        if (use >= 1) mbar_wait(bar(kBarEmpty + s), (use - 1) & 1u);
+        mbar_expect_tx(bar(kBarFull + s), TC_UNIT_BYTES);
+        bulk_g2s(sB + (uint32_t)s * TC_UNIT_BYTES, img + (size_t)(g % TC_UNITS) * TC_UNIT_BYTES, TC_UNIT_BYTES, bar(kBarFull + s));
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    double p0 = 0, p1 = 0, p2 = 0;
+  } else if (warp == kEpiWarps + 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t sB = smem_u32(smem + kOffB);
+      int64_t g = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        mbar_wait(bar(kBarAReady), (uint32_t)it & 1u);
+        tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < TC_CHUNKS; ++c) {
-      if (tid == 0) {
+        for (int c = 0; c < TC_CHUNKS; ++c) {
 #pragma unroll 1
+          for (int k = 0; k < 3; ++k, ++g) {
+            const uint32_t n = (uint32_t)(it * TC_CHUNKS + c);       // uses of accumulator set k so far
+            if (n >= 1) { mbar_wait(bar(kBarAccEmpty + k), (n - 1) & 1u); tc_fence_after(); }
+            const int s = (int)(g % kSlots);
+            mbar_wait(bar(kBarFull + s), (uint32_t)(g / kSlots) & 1u);
+            tc_fence_after();
+            const uint32_t sBu = sB + (uint32_t)s * TC_UNIT_BYTES;
+#pragma unroll 1
+            for (int t = 0; t < TC_NACC; ++t) {
+              const uint32_t acc = tmem + kColAcc + (uint32_t)((k * TC_NACC + t) * TC_NC);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t a_base = tmem + (h == 0 ? kColAhi : kColAlo);
+                const uint32_t b_base = sBu + (uint32_t)((2 * t + h) * TC_SLICE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < TC_W / 32; ++ks)
+                  umma_i8_ts(acc, a_base + ks * 8, umma_desc(b_base + ks * 256), (h | ks) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(bar(kBarEmpty + s));
+            umma_commit(bar(kBarAccFull + k));
+          }
+        }
+      }
+    }
+  } else {
+    // ===== prologue + epilogue warps =====
+    const int quad = warp & 3, ch = warp >> 2;                 // TMEM lane quadrant, column half
+    const int r_in = quad * 32 + lane;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
+    const double* sW0 = sC + TC_C_WD0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t row = tile * kTileRows + r_in;
+      const bool valid = row < D;
+      double dx = 0, dy = 0, dz = 0;
+      if (valid) { dx = d[3 * row]; dy = d[3 * row + 1]; dz = d[3 * row + 2]; }
+      // ---- prologue: this thread's 128 mask bits of layer 0 (hidden units ch*128 ..) -> 32 words of A in TMEM ----
+      {
+        uint32_t w[32];
+#pragma unroll
+        for (int wi = 0; wi < 32; ++wi) {
+          uint32_t v = 0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int j = ch * 128 + wi * 4 + b;
+            const double lin = dx * sW0[j] + dy * sW0[TC_W + j] + dz * sW0[2 * TC_W + j];
+            v |= (lin > 0 ? 1u : 0u) << (8 * b);
+          }
+          w[wi] = v;
+        }
+        // (the previous tile's MMAs have all completed: its last accumulator set was awaited below)
+        tmem_st32(tmem_lane + kColAlo + (uint32_t)(ch * 32), w);
+#pragma unroll
+        for (int wi = 0; wi < 32; ++wi) w[wi] <<= 7;
+        tmem_st32(tmem_lane + kColAhi + (uint32_t)(ch * 32), w);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kBarAReady));
+      }
+      double p0 = 0, p1 = 0, p2 = 0;
+#pragma unroll 1
+      for (int c = 0; c < TC_CHUNKS; ++c) {
+        const uint32_t n = (uint32_t)(it * TC_CHUNKS + c);
+        double Y0[16], Y1[16];
+#pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const uint32_t b = gu & 1u;
-          mbar_wait(bar_full0 + 8 * b, (gu >> 1) & 1u);
+          int32_t a[TC_NACC][16];
+          mbar_wait(bar(kBarAccFull + k), n & 1u);
+          __syncwarp();
           tc_fence_after();
-          const uint32_t sBu = sB + b * TC_UNIT_BYTES;
-#pragma unroll 1
-          for (int t = 0; t < TC_NACC; ++t) {
-            const uint32_t acc = tmem + (uint32_t)((k * TC_NACC + t) * TC_NC);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t a_base = h == 0 ? sAhi : sAlo;
-              const uint32_t b_base = sBu + (uint32_t)((2 * t + h) * TC_SLICE_BYTES);
+          for (int t = 0; t < TC_NACC; ++t)
+            tmem_ld16(tmem_lane + kColAcc + (uint32_t)((k * TC_NACC + t) * TC_NC + ch * 16), a[t]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(kBarAccEmpty + k));     // the tensor pipe may overwrite this set
 #pragma unroll
-              for (int ks = 0; ks < TC_W / 32; ++ks)
-                umma_i8(acc, umma_desc(a_base + ks * 256), umma_desc(b_base + ks * 256), (h | ks) != 0 ? 1u : 0u);
+          for (int q = 0; q < 16; ++q) {
+            const int i = c * TC_NC + ch * 16 + q;
+            double v = i2d(a[0][q]);
+#pragma unroll
+            for (int t = 1; t < TC_NACC; ++t) v = fma(v, 16384.0, i2d(a[t][q]));
+            const double2 cb = *reinterpret_cast<const double2*>(sC + TC_C_COL + 8 * i + 2 * k);
+            const double y = fma(cb.x, v, cb.y);
+            if (k == 0) Y0[q] = y;
+            else if (k == 1) Y1[q] = y;
+            else {
+              double z = dx * Y0[q] + dy * Y1[q] + dz * y;
+              if (fabs(z) < sC[TC_C_COL + 8 * i + 6] && valid)
+                z = exact_z1(sW0, consts + TC_C_WD1, Wh, dx, dy, dz, slope, i);
+              const double m = z > 0 ? 1.0 : slope;
+              p0 = fma(m, Y0[q], p0);
+              p1 = fma(m, Y1[q], p1);
+              p2 = fma(m, y, p2);
             }
           }
-          umma_commit(bar_mma0 + 8 * b);
-          if (k == 2) umma_commit(bar_chunk);
-          // refill the other ring slot: its previous user (unit gu - 1) must have been read completely
-          if (gu >= 1) mbar_wait(bar_mma0 + 8 * (b ^ 1u), ((gu - 1) >> 1) & 1u);
-          const int next = (c * 3 + k + 1) % TC_UNITS;
-          if (!(last_tile && c == TC_CHUNKS - 1 && k == 2)) {
-            mbar_expect_tx(bar_full0 + 8 * (b ^ 1u), TC_UNIT_BYTES);
-            bulk_g2s(sB + (b ^ 1u) * TC_UNIT_BYTES, img + (size_t)next * TC_UNIT_BYTES, TC_UNIT_BYTES, bar_full0 + 8 * (b ^ 1u));
-          }
-          ++gu;
-        }
-      } else {
-        gu += 3;
-      }
-      __syncwarp();
-      mbar_wait(bar_chunk, chunks_done & 1u);
-      ++chunks_done;
-      __syncwarp();
-      tc_fence_after();
-      // ---- epilogue: Jacobian Y_k, z1, layer-1 mask, support point -- 8 hidden units per TMEM read ----
-#pragma unroll 1
-      for (int g = 0; g < TC_NC / 8; ++g) {
-        int32_t a[3 * TC_NACC][8];
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 3 * TC_NACC; ++q) tmem_ld8(tmem_lane + (uint32_t)(q * TC_NC + g * 8), a[q]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int i = c * TC_NC + g * 8 + q;
-          double Y[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            double v = (double)a[k * TC_NACC][q];
-#pragma unroll
-            for (int t = 1; t < TC_NACC; ++t) v = fma(v, 16384.0, (double)a[k * TC_NACC + t][q]);
-            Y[k] = fma(sC[TC_C_COEF + k * TC_W + i], v, sC[TC_C_BASE + k * TC_W + i]);
-          }
-          double z = dx * Y[0] + dy * Y[1] + dz * Y[2];
-          if (fabs(z) < sC[TC_C_ZTOL + i] && valid) z = exact_z1(sC, Wh, dx, dy, dz, slope, i);
-          const double m = z > 0 ? sC[TC_C_WO + i] : slope * sC[TC_C_WO + i];
-          p0 = fma(m, Y[0], p0);
-          p1 = fma(m, Y[1], p1);
-          p2 = fma(m, Y[2], p2);
         }
       }
-      tc_fence_before();
-      __syncthreads();          // TMEM accumulators (and, after the last chunk, the A operands) are free again
-      tc_fence_after();
+      // the two column halves of a row meet in shared memory
+      double* sPt = sP + (it & 1) * (kTileRows * 3);
+      if (ch == 1) { sPt[3 * r_in] = p0; sPt[3 * r_in + 1] = p1; sPt[3 * r_in + 2] = p2; }
+      epi_barrier();
+      if (ch == 0 && valid) {
+        p[3 * row] = p0 + sPt[3 * r_in];
+        p[3 * row + 1] = p1 + sPt[3 * r_in + 1];
+        p[3 * row + 2] = p2 + sPt[3 * r_in + 2];
+      }
     }
-    if (valid) { p[3 * row] = p0; p[3 * row + 1] = p1; p[3 * row + 2] = p2; }
   }
   tc_fence_before();
   __syncthreads();
@@ -250,6 +309,7 @@ icnn_tc_prepare_kernel(const double* __restrict__ Wd0, const double* __restrict_
   __shared__ double bc[3];
   const int i = blockIdx.x, j = threadIdx.x, lane = j & 31, w = j >> 5;
   const double wh = fabs(Wh[j * TC_W + i]);
+  const double wo = fabs(wout[i]);
   double abs_total = 0;
   for (int k = 0; k < 3; ++k) {
     const double q = Wd0[k * TC_W + j] * wh;
@@ -273,8 +333,8 @@ icnn_tc_prepare_kernel(const double* __restrict__ Wd0, const double* __restrict_
     tc_digits(q, e, dig);
     for (int s = 0; s < TC_NS; ++s) img[tc_image_offset(k, s, j, i)] = (uint8_t)dig[s];
     if (j == 0) {
-      consts[TC_C_BASE + k * TC_W + i] = Wd1[k * TC_W + i] + slope * bc[1];
-      consts[TC_C_COEF + k * TC_W + i] = (1.0 - slope) * ldexp(sigma, -(7 * TC_NS - 1));
+      consts[TC_C_COL + 8 * i + 2 * k] = wo * ((1.0 - slope) * ldexp(sigma, -(7 * TC_NS - 1)));
+      consts[TC_C_COL + 8 * i + 2 * k + 1] = wo * (Wd1[k * TC_W + i] + slope * bc[1]);
       consts[TC_C_WD0 + k * TC_W + i] = Wd0[k * TC_W + i];
       consts[TC_C_WD1 + k * TC_W + i] = Wd1[k * TC_W + i];
     }
@@ -282,8 +342,8 @@ icnn_tc_prepare_kernel(const double* __restrict__ Wd0, const double* __restrict_
     __syncthreads();
   }
   if (j == 0) {
-    consts[TC_C_WO + i] = fabs(wout[i]);
-    consts[TC_C_ZTOL + i] = TC_ZTOL_REL * abs_total;
+    consts[TC_C_COL + 8 * i + 6] = wo * (TC_ZTOL_REL * abs_total);
+    consts[TC_C_COL + 8 * i + 7] = 0.0;
   }
 }
 
