@@ -88,6 +88,20 @@ __device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uin
       "r"(tmem_a), "l"(bdesc), "r"(kIdesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
       : "memory");
 }
+// one lane of a converged warp (the compiler then issues the uniform-datapath instruction once, without a lane loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -160,51 +174,58 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const uint8_t* __restric
   const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
   if (warp == kEpiWarps) {
-    // ===== producer =====
-    if (lane == 0) {
-      const uint32_t sB = smem_u32(smem + kOffB);
-      const int64_t total = my_tiles * TC_UNITS;
-      for (int64_t g = 0; g < total; ++g) {
-        const int s = (int)(g % kSlots);
-        const uint32_t use = (uint32_t)(g / kSlots);
-        if (use >= 1) mbar_wait(bar(kBarEmpty + s), (use - 1) & 1u);
+    // ===== producer (whole warp runs the loop, one elected lane issues) =====
+    const uint32_t sB = smem_u32(smem + kOffB);
+    const int64_t total = my_tiles * TC_UNITS;
+    int s = 0, unit = 0;
+    uint32_t use = 0;
+    for (int64_t g = 0; g < total; ++g) {
+      if (use >= 1) mbar_wait(bar(kBarEmpty + s), (use - 1) & 1u);
+      if (elect_one()) {
         mbar_expect_tx(bar(kBarFull + s), TC_UNIT_BYTES);
-        bulk_g2s(sB + (uint32_t)s * TC_UNIT_BYTES, img + (size_t)(g % TC_UNITS) * TC_UNIT_BYTES, TC_UNIT_BYTES, bar(kBarFull + s));
+        bulk_g2s(sB + (uint32_t)s * TC_UNIT_BYTES, img + (size_t)unit * TC_UNIT_BYTES, TC_UNIT_BYTES, bar(kBarFull + s));
       }
+      __syncwarp();
+      if (++s == kSlots) { s = 0; ++use; }
+      if (++unit == TC_UNITS) unit = 0;
     }
   } else if (warp == kEpiWarps + 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t sB = smem_u32(smem + kOffB);
-      int64_t g = 0;
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        mbar_wait(bar(kBarAReady), (uint32_t)it & 1u);
-        tc_fence_after();
+    // ===== MMA issuer (whole warp runs the loop, one elected lane issues) =====
+    const uint32_t sB = smem_u32(smem + kOffB);
+    // descriptor of byte 0 of the ring: K-major, no swizzle, LBO 128 B, SBO 2048 B, version 1; +1 per 16 bytes
+    const uint64_t desc0 = umma_desc(sB);
+    int s = 0;
+    uint32_t use = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      mbar_wait(bar(kBarAReady), (uint32_t)it & 1u);
+      tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < TC_CHUNKS; ++c) {
+      for (int c = 0; c < TC_CHUNKS; ++c) {
+        const uint32_t n = (uint32_t)(it * TC_CHUNKS + c);       // uses of each accumulator set so far
 #pragma unroll 1
-          for (int k = 0; k < 3; ++k, ++g) {
-            const uint32_t n = (uint32_t)(it * TC_CHUNKS + c);       // uses of accumulator set k so far
-            if (n >= 1) { mbar_wait(bar(kBarAccEmpty + k), (n - 1) & 1u); tc_fence_after(); }
-            const int s = (int)(g % kSlots);
-            mbar_wait(bar(kBarFull + s), (uint32_t)(g / kSlots) & 1u);
-            tc_fence_after();
-            const uint32_t sBu = sB + (uint32_t)s * TC_UNIT_BYTES;
-#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+          if (n >= 1) mbar_wait(bar(kBarAccEmpty + k), (n - 1) & 1u);
+          mbar_wait(bar(kBarFull + s), use & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t desc_u = desc0 + (uint64_t)((uint32_t)s * (TC_UNIT_BYTES >> 4));
+#pragma unroll
             for (int t = 0; t < TC_NACC; ++t) {
               const uint32_t acc = tmem + kColAcc + (uint32_t)((k * TC_NACC + t) * TC_NC);
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const uint32_t a_base = tmem + (h == 0 ? kColAhi : kColAlo);
-                const uint32_t b_base = sBu + (uint32_t)((2 * t + h) * TC_SLICE_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < TC_W / 32; ++ks)
-                  umma_i8_ts(acc, a_base + ks * 8, umma_desc(b_base + ks * 256), (h | ks) != 0 ? 1u : 0u);
+                  umma_i8_ts(acc, a_base + ks * 8, desc_u + (uint64_t)(((2 * t + h) * TC_SLICE_BYTES + ks * 256) >> 4),
+                             (h | ks) != 0 ? 1u : 0u);
               }
             }
             umma_commit(bar(kBarEmpty + s));
             umma_commit(bar(kBarAccFull + k));
           }
+          __syncwarp();
+          if (++s == kSlots) { s = 0; ++use; }
         }
       }
     }
