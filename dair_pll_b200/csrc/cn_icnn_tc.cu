@@ -26,11 +26,16 @@ namespace {
 
 using namespace cn;
 
-constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kThreads = kEpiThreads + 64;
+#ifndef TC_SPLIT
+#define TC_SPLIT 4
+#endif
+constexpr int kSplit = TC_SPLIT;                     // threads per direction row (column groups of a chunk)
+constexpr int kCols = TC_NC / kSplit;              // hidden units per thread and unit
+constexpr int kEpiWarps = 4 * kSplit, kEpiThreads = kEpiWarps * 32, kThreads = kEpiThreads + 64;
 constexpr int kTileRows = 128;
 constexpr int kSlots = 3;
 constexpr int kOffB = 0, kOffC = kOffB + kSlots * TC_UNIT_BYTES, kOffP = kOffC + TC_NCONST_SMEM * 8,
-              kOffBar = kOffP + 2 * kTileRows * 3 * 8, kSmemBytes = kOffBar + 128;
+              kOffBar = kOffP + 2 * (kSplit - 1) * kTileRows * 3 * 8, kSmemBytes = kOffBar + 128;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColAlo = 0, kColAhi = 64, kColAcc = 128;
 // instruction descriptor, kind::i8: D s32 (2 << 4), A s8 (1 << 7), B s8 (1 << 10), both K-major, N >> 3 at 17, M >> 4 at 24
@@ -112,6 +117,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -126,9 +143,13 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
-// int32 -> double without the conversion unit: bits [2^52 + 2^31 + x] minus the constant (exact)
-__device__ __forceinline__ double i2d(int32_t x) {
-  return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;
+// sum_t acc_t 128^(2 (NACC-1-t)) as a double: integer Horner on the integer pipe (|result| < 2^51), then the 2^52 + 2^51
+// bias trick instead of the conversion unit (exact)
+__device__ __forceinline__ double horner_i2d(const int32_t* a) {
+  long long v = a[0];
+#pragma unroll
+  for (int t = 1; t < TC_NACC; ++t) v = v * 16384 + a[t];
+  return __longlong_as_double(v + 0x4338000000000000LL) - 6755399441055744.0;
 }
 
 // z1_i in plain fp64 for one row (the rare |z1| ~ 0 case, where a 42-bit Jacobian must not decide the mask)
@@ -231,35 +252,38 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const uint8_t* __restric
     }
   } else {
     // ===== prologue + epilogue warps =====
-    const int quad = warp & 3, ch = warp >> 2;                 // TMEM lane quadrant, column half
+    const int quad = warp & 3, ch = warp >> 2;                 // TMEM lane quadrant, column group
     const int r_in = quad * 32 + lane;
     const uint32_t tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
     const double* sW0 = sC + TC_C_WD0;
+    constexpr int kWords = 64 / kSplit;                        // words of each A copy written by this thread
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int64_t row = tile * kTileRows + r_in;
       const bool valid = row < D;
       double dx = 0, dy = 0, dz = 0;
       if (valid) { dx = d[3 * row]; dy = d[3 * row + 1]; dz = d[3 * row + 2]; }
-      // ---- prologue: this thread's 128 mask bits of layer 0 (hidden units ch*128 ..) -> 32 words of A in TMEM ----
+      // ---- prologue: this thread's mask bits of layer 0 (hidden units ch * 4 kWords ..) -> kWords words of A in TMEM ----
       {
-        uint32_t w[32];
+        uint32_t w[kWords];
 #pragma unroll
-        for (int wi = 0; wi < 32; ++wi) {
+        for (int wi = 0; wi < kWords; ++wi) {
           uint32_t v = 0;
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
-            const int j = ch * 128 + wi * 4 + b;
+            const int j = (ch * kWords + wi) * 4 + b;
             const double lin = dx * sW0[j] + dy * sW0[TC_W + j] + dz * sW0[2 * TC_W + j];
             v |= (lin > 0 ? 1u : 0u) << (8 * b);
           }
           w[wi] = v;
         }
         // (the previous tile's MMAs have all completed: its last accumulator set was awaited below)
-        tmem_st32(tmem_lane + kColAlo + (uint32_t)(ch * 32), w);
+        if constexpr (kWords == 32) tmem_st32(tmem_lane + kColAlo + (uint32_t)(ch * kWords), w);
+        else tmem_st16(tmem_lane + kColAlo + (uint32_t)(ch * kWords), w);
 #pragma unroll
-        for (int wi = 0; wi < 32; ++wi) w[wi] <<= 7;
-        tmem_st32(tmem_lane + kColAhi + (uint32_t)(ch * 32), w);
+        for (int wi = 0; wi < kWords; ++wi) w[wi] <<= 7;
+        if constexpr (kWords == 32) tmem_st32(tmem_lane + kColAhi + (uint32_t)(ch * kWords), w);
+        else tmem_st16(tmem_lane + kColAhi + (uint32_t)(ch * kWords), w);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
@@ -269,26 +293,30 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const uint8_t* __restric
 #pragma unroll 1
       for (int c = 0; c < TC_CHUNKS; ++c) {
         const uint32_t n = (uint32_t)(it * TC_CHUNKS + c);
-        double Y0[16], Y1[16];
+        double Y0[kCols], Y1[kCols];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          int32_t a[TC_NACC][16];
+          int32_t a[TC_NACC][kCols];
           mbar_wait(bar(kBarAccFull + k), n & 1u);
           __syncwarp();
           tc_fence_after();
 #pragma unroll
-          for (int t = 0; t < TC_NACC; ++t)
-            tmem_ld16(tmem_lane + kColAcc + (uint32_t)((k * TC_NACC + t) * TC_NC + ch * 16), a[t]);
+          for (int t = 0; t < TC_NACC; ++t) {
+            const uint32_t ta = tmem_lane + kColAcc + (uint32_t)((k * TC_NACC + t) * TC_NC + ch * kCols);
+            if constexpr (kCols == 16) tmem_ld16(ta, a[t]);
+            else tmem_ld8(ta, a[t]);
+          }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(kBarAccEmpty + k));     // the tensor pipe may overwrite this set
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int i = c * TC_NC + ch * 16 + q;
-            double v = i2d(a[0][q]);
+          for (int q = 0; q < kCols; ++q) {
+            const int i = c * TC_NC + ch * kCols + q;
+            int32_t aq[TC_NACC];
 #pragma unroll
-            for (int t = 1; t < TC_NACC; ++t) v = fma(v, 16384.0, i2d(a[t][q]));
+            for (int t = 0; t < TC_NACC; ++t) aq[t] = a[t][q];
+            const double v = horner_i2d(aq);
             const double2 cb = *reinterpret_cast<const double2*>(sC + TC_C_COL + 8 * i + 2 * k);
             const double y = fma(cb.x, v, cb.y);
             if (k == 0) Y0[q] = y;
@@ -305,14 +333,20 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const uint8_t* __restric
           }
         }
       }
-      // the two column halves of a row meet in shared memory
-      double* sPt = sP + (it & 1) * (kTileRows * 3);
-      if (ch == 1) { sPt[3 * r_in] = p0; sPt[3 * r_in + 1] = p1; sPt[3 * r_in + 2] = p2; }
+      // the column groups of a row meet in shared memory
+      double* sPt = sP + (it & 1) * ((kSplit - 1) * kTileRows * 3);
+      if (ch > 0) {
+        double* dst = sPt + ((ch - 1) * kTileRows + r_in) * 3;
+        dst[0] = p0; dst[1] = p1; dst[2] = p2;
+      }
       epi_barrier();
       if (ch == 0 && valid) {
-        p[3 * row] = p0 + sPt[3 * r_in];
-        p[3 * row + 1] = p1 + sPt[3 * r_in + 1];
-        p[3 * row + 2] = p2 + sPt[3 * r_in + 2];
+#pragma unroll
+        for (int o = 0; o < kSplit - 1; ++o) {
+          const double* src = sPt + (o * kTileRows + r_in) * 3;
+          p0 += src[0]; p1 += src[1]; p2 += src[2];
+        }
+        p[3 * row] = p0; p[3 * row + 1] = p1; p[3 * row + 2] = p2;
       }
     }
   }
