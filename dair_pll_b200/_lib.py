@@ -49,11 +49,17 @@ EXPORTS = {
     'dpll_icnn_input_f64': ([_c_void_p, _c_void_p, _i64, _i32, _f64, _c_void_p, _c_void_p], ctypes.c_int),
     'dpll_icnn_mask_f64': ([_c_void_p, _i64, _f64, _c_void_p], ctypes.c_int),
     'dpll_icnn_output_f64': ([_c_void_p] * 5 + [_i64, _i32, _f64, _c_void_p, _c_void_p], ctypes.c_int),
+    'dpll_elbow_support_directions_f64': ([_c_void_p, _i64] + [_c_void_p] * 3 + [_i32, _i64] + [_c_void_p] * 3, ctypes.c_int),
     'dpll_icnn_tc_image_bytes': ([], ctypes.c_size_t),
     'dpll_icnn_tc_const_bytes': ([], ctypes.c_size_t),
     'dpll_icnn_tc_prepare_f64': ([_c_void_p] * 4 + [_i32, _f64, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     'dpll_icnn_tc_support_f64': ([_c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _i32, _f64, _c_void_p, _c_void_p],
                                  ctypes.c_int),
+    'dpll_icnn_tc_bwd_partial_bytes': ([], ctypes.c_size_t),
+    'dpll_icnn_tc_bwd_planes': ([], ctypes.c_int32),
+    'dpll_icnn_tc_record_f64': ([_c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _f64, _c_void_p, _c_void_p,
+                                 _i64, _c_void_p], ctypes.c_int),
+    'dpll_icnn_tc_bwd_f64': ([_c_void_p] * 5 + [_i64, _f64] + [_c_void_p] * 5, ctypes.c_int),
     'dpll_icnn_backward_blocks': ([_i64], ctypes.c_int),
     'dpll_icnn_backward_f64': ([_c_void_p] * 5 + [_i64, _i32, _f64, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     'dpll_cube_loss_leaf_dp_f64': ([_c_void_p, _i64, _c_void_p, _i64] + [_c_void_p] * 3 + [_f64, _f64, _i64, _i32] +

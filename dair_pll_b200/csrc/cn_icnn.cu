@@ -106,6 +106,36 @@ __global__ void icnn_backward_kernel(const double* __restrict__ gp, const double
   }
 }
 
+// Support directions of the two elbow links against the ground (GeometryCollider.collide_plane_convex,
+// geometry.py:560-567: minus the third row of the link's world rotation) and their n_query perturbed, normalised copies
+// (DeepSupportConvex.get_vertices, geometry.py:309-325).  One thread per sample.
+__global__ void elbow_support_directions_kernel(const double* __restrict__ q, int64_t q_stride, const double* __restrict__ axis,
+                                                const double* __restrict__ pert0, const double* __restrict__ pert1, int nq,
+                                                int64_t B, double* __restrict__ dirs0, double* __restrict__ dirs1) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* qb = q + b * q_stride;
+  const double w = qb[0], x = qb[1], y = qb[2], z = qb[3], th = qb[7];
+  const double s = 2.0 / (w * w + x * x + y * y + z * z);
+  const double r[3] = {s * (x * z - w * y), s * (y * z + w * x), 1 - s * (x * x + y * y)};      // R1[2, :]
+  const double a[3] = {axis[0], axis[1], axis[2]};
+  // third row of R2 = R1 Rot(axis, th):  r Rot = r cos + (r x a) sin + a (a.r)(1 - cos)
+  const double c = cos(th), sn = sin(th), ar = r[0] * a[0] + r[1] * a[1] + r[2] * a[2];
+  const double rxa[3] = {r[1] * a[2] - r[2] * a[1], r[2] * a[0] - r[0] * a[2], r[0] * a[1] - r[1] * a[0]};
+  double r2[3];
+  for (int i = 0; i < 3; ++i) r2[i] = r[i] * c + rxa[i] * sn + a[i] * ar * (1 - c);
+  for (int g = 0; g < 2; ++g) {
+    const double* base = g == 0 ? r : r2;
+    const double* pert = g == 0 ? pert0 : pert1;
+    double* out = (g == 0 ? dirs0 : dirs1) + b * nq * 3;
+    for (int k = 0; k < nq; ++k) {
+      const double vx = -base[0] + pert[3 * k], vy = -base[1] + pert[3 * k + 1], vz = -base[2] + pert[3 * k + 2];
+      const double n = sqrt(vx * vx + vy * vy + vz * vz);
+      out[3 * k] = vx / n; out[3 * k + 1] = vy / n; out[3 * k + 2] = vz / n;
+    }
+  }
+}
+
 int grid_for(int64_t work, int per_block) {
   int64_t b = (work + per_block - 1) / per_block;
   return (int)(b < 1 ? 1 : (b > 2147483647LL ? 2147483647LL : b));
@@ -121,6 +151,18 @@ int dpll_icnn_input_f64(const double* d, const double* Wd0, int64_t D, int32_t W
   if (D == 0) return DPLL_OK;
   if (!d || !h0aug) return DPLL_EINVAL;
   icnn_input_kernel<<<grid_for(D, kRowsPerBlock), 288, 0, static_cast<cudaStream_t>(stream)>>>(d, Wd0, D, W, slope, h0aug);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPLL_OK : (int)e;
+}
+
+int dpll_elbow_support_directions_f64(const double* q, int64_t q_stride, const double* axis, const double* pert0,
+                                      const double* pert1, int32_t n_query, int64_t B, double* dirs0, double* dirs1,
+                                      void* stream) {
+  if (B < 0 || n_query <= 0 || q_stride < 8 || !axis || !pert0 || !pert1) return DPLL_EINVAL;
+  if (B == 0) return DPLL_OK;
+  if (!q || !dirs0 || !dirs1) return DPLL_EINVAL;
+  elbow_support_directions_kernel<<<grid_for(B, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      q, q_stride, axis, pert0, pert1, n_query, B, dirs0, dirs1);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPLL_OK : (int)e;
 }
@@ -148,7 +190,14 @@ int dpll_icnn_output_f64(double* T, const double* h0aug, const double* m1, const
   return e == cudaSuccess ? DPLL_OK : (int)e;
 }
 
-int dpll_icnn_backward_blocks(int64_t D) { return grid_for(D, 512); }
+// rows per block: 512 for large batches; small batches (the active rows of a step) still get ~4 blocks per SM
+static int backward_rows_per_block(int64_t D) {
+  int rows = 512;
+  while (rows > 32 && D / rows < 148 * 4) rows >>= 1;
+  return rows;
+}
+
+int dpll_icnn_backward_blocks(int64_t D) { return grid_for(D, backward_rows_per_block(D)); }
 
 int dpll_icnn_backward_f64(const double* gp, const double* h0aug, const double* m1, const double* a0, const double* Wd0,
                            int64_t D, int32_t W, double slope, double* t, double* part, void* stream) {
@@ -156,7 +205,7 @@ int dpll_icnn_backward_f64(const double* gp, const double* h0aug, const double* 
   if (D == 0) return DPLL_OK;
   if (!gp || !h0aug || !m1 || !a0 || !t || !part) return DPLL_EINVAL;
   icnn_backward_kernel<<<dpll_icnn_backward_blocks(D), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      gp, h0aug, m1, a0, Wd0, D, W, slope, 512, t, part);
+      gp, h0aug, m1, a0, Wd0, D, W, slope, backward_rows_per_block(D), t, part);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPLL_OK : (int)e;
 }

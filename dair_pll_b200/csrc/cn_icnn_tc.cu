@@ -163,9 +163,16 @@ __device__ __noinline__ double exact_z1(const double* sW0, const double* __restr
   return z + (dx * Wd1[i] + dy * Wd1[TC_W + i] + dz * Wd1[2 * TC_W + i]);
 }
 
+// RECORD = false: support points p of all D rows.  RECORD = true (the backward's first pass over the compacted active
+// rows): the row count comes from device memory (*n_ptr <= D, no host read), and instead of p the two layers' slope-mask
+// bits are written as TRANSPOSED byte matrices -- m0t[j][row] in {0x00, 0xFF}, m1t[i][row] in {0, 1}, row stride ldk --
+// the K-major operands of the weight-gradient kernel.
+template <bool RECORD>
 __global__ void __launch_bounds__(kThreads, 1)
-icnn_tc_kernel(const double* __restrict__ d, int64_t D, const uint8_t* __restrict__ img, const double* __restrict__ consts,
-               const double* __restrict__ Wh, double slope, double* __restrict__ p) {
+icnn_tc_kernel(const double* __restrict__ d, int64_t D, const int64_t* __restrict__ n_ptr, const uint8_t* __restrict__ img,
+               const double* __restrict__ consts, const double* __restrict__ Wh, double slope, double* __restrict__ p,
+               uint8_t* __restrict__ m0t, uint8_t* __restrict__ m1t, int64_t ldk) {
+  if (RECORD) { const int64_t n = *n_ptr; D = n < D ? n : D; }
   extern __shared__ __align__(1024) uint8_t smem[];
   double* sC = reinterpret_cast<double*>(smem + kOffC);
   double* sP = reinterpret_cast<double*>(smem + kOffP);
@@ -276,6 +283,11 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const uint8_t* __restric
             v |= (lin > 0 ? 1u : 0u) << (8 * b);
           }
           w[wi] = v;
+          if (RECORD) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              m0t[(int64_t)((ch * kWords + wi) * 4 + b) * ldk + row] = ((v >> (8 * b)) & 1u) ? 0xFF : 0x00;
+          }
         }
         // (the previous tile's MMAs have all completed: its last accumulator set was awaited below)
         if constexpr (kWords == 32) tmem_st32(tmem_lane + kColAlo + (uint32_t)(ch * kWords), w);
@@ -326,6 +338,7 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const uint8_t* __restric
               if (fabs(z) < sC[TC_C_COL + 8 * i + 6] && valid)
                 z = exact_z1(sW0, consts + TC_C_WD1, Wh, dx, dy, dz, slope, i);
               const double m = z > 0 ? 1.0 : slope;
+              if (RECORD) m1t[(int64_t)i * ldk + row] = z > 0 ? 1 : 0;
               p0 = fma(m, Y0[q], p0);
               p1 = fma(m, Y1[q], p1);
               p2 = fma(m, y, p2);
@@ -333,6 +346,7 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const uint8_t* __restric
           }
         }
       }
+      if (RECORD) continue;
       // the column groups of a row meet in shared memory
       double* sPt = sP + (it & 1) * ((kSplit - 1) * kTileRows * 3);
       if (ch > 0) {
@@ -402,6 +416,13 @@ icnn_tc_prepare_kernel(const double* __restrict__ Wd0, const double* __restrict_
   }
 }
 
+int sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
 }  // namespace
 
 extern "C" {
@@ -423,15 +444,29 @@ int dpll_icnn_tc_support_f64(const double* d, int64_t D, const void* image, cons
   if (W != cn::TC_W || D < 0 || !image || !consts || !Wh) return DPLL_EINVAL;
   if (D == 0) return DPLL_OK;
   if (!d || !p) return DPLL_EINVAL;
-  cudaError_t e = cudaFuncSetAttribute(icnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(icnn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (D + kTileRows - 1) / kTileRows;
+  const int sms = sm_count();
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  icnn_tc_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-      d, D, static_cast<const uint8_t*>(image), consts, Wh, slope, p);
+  icnn_tc_kernel<false><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+      d, D, nullptr, static_cast<const uint8_t*>(image), consts, Wh, slope, p, nullptr, nullptr, 0);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? DPLL_OK : (int)e;
+}
+
+int dpll_icnn_tc_record_f64(const double* d, int64_t capacity, const int64_t* n_rows, const void* image, const double* consts,
+                            const double* Wh, int32_t W, double slope, uint8_t* m0t, uint8_t* m1t, int64_t ldk, void* stream) {
+  if (W != cn::TC_W || capacity < 0 || !n_rows || !image || !consts || !Wh || (ldk & 127) || ldk < capacity) return DPLL_EINVAL;
+  if (capacity == 0) return DPLL_OK;
+  if (!d || !m0t || !m1t) return DPLL_EINVAL;
+  cudaError_t e = cudaFuncSetAttribute(icnn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t ntiles = (capacity + kTileRows - 1) / kTileRows;
+  const int sms = sm_count();
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  icnn_tc_kernel<true><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+      d, capacity, n_rows, static_cast<const uint8_t*>(image), consts, Wh, slope, nullptr, m0t, m1t, ldk);
   e = cudaGetLastError();
   return e == cudaSuccess ? DPLL_OK : (int)e;
 }

@@ -34,24 +34,41 @@ class ICNNSupport(torch.autograd.Function):
     """p (D,3) = d f / d direction for directions d (D,3); differentiable w.r.t. the four weights.  CUDA only (there is
     no CPU path).
 
-    Forward: every row (``ops.icnn_support_points``).  Nothing of size (D x width) is kept for the backward: a row whose
-    cotangent is exactly zero contributes exactly zero to every weight gradient, and in the ContactNets loss only the
-    witness points of contacts that carry force or penetrate have a non-zero cotangent (3.7% of the rows of the
-    config-3 batch, tools/exp_active_rows.py) -- so the backward gathers those rows, re-evaluates their activation
-    masks and runs the three reductions on them alone."""
+    Forward: every row.  Nothing of size (D x width) is kept for the backward: a row whose cotangent is exactly zero
+    contributes exactly zero to every weight gradient, and in the ContactNets loss only the witness points of contacts
+    that carry force or penetrate have a non-zero cotangent (3.7% of the rows of the config-3 batch,
+    tools/exp_active_rows.py) -- so the backward gathers those rows, re-evaluates their activation masks and runs the
+    reductions on them alone.  Width 256: both passes on the tensor cores (csrc/cn_icnn_tc.cu, cn_icnn_tc_bwd.cu), no host
+    read; other widths: the FP64 layer kernels of csrc/cn_icnn.cu around library GEMMs (one host read for the row count)."""
 
     @staticmethod
     def forward(ctx, d, Wd0, Wd1, Wh, wout, slope):
         if not d.is_cuda:
             raise RuntimeError('dair_pll_b200 has no CPU path: support-function networks are evaluated on a CUDA device')
         from dair_pll_b200 import ops
-        ctx.save_for_backward(d, Wd0, Wd1, Wh, wout)
         ctx.slope = float(slope)
-        return ops.icnn_support_points(d, Wd0, Wd1, Wh, wout, float(slope))
+        ctx.tensor_cores = Wd0.shape[1] == ops.ICNN_TC_WIDTH and not ops.ICNN_FORCE_FP64_PATH
+        if ctx.tensor_cores:
+            prepared = ops.icnn_tc_prepare(Wd0, Wd1, Wh, wout, ctx.slope)
+            ctx.save_for_backward(d, Wd0, Wd1, Wh, wout, *prepared)
+            return ops.icnn_support_points_tc(d, Wd0, Wd1, Wh, wout, ctx.slope, prepared)
+        ctx.save_for_backward(d, Wd0, Wd1, Wh, wout)
+        return ops.icnn_support_forward(d, Wd0, Wd1, Wh, wout, ctx.slope)[0]
 
     @staticmethod
     def backward(ctx, gp):
         from dair_pll_b200 import ops
+        if ctx.tensor_cores:
+            d, Wd0, Wd1, Wh, wout, image, consts = ctx.saved_tensors
+            s = ctx.slope
+            # no host read: compaction, mask re-evaluation and the (rows x W x W) contraction all take the live-row count
+            # from device memory, so the whole training step can be captured into a CUDA graph
+            C, R1, S = ops.icnn_support_backward_tc(d, gp.contiguous(), Wh, s, (image, consts))
+            Wh_a, wo = Wh.abs(), wout.abs()
+            g1 = s * S[:, None] + (1 - s) * R1                              # gp^T m1
+            G = (Wd0[:, :, None] * C).sum(0)                                # t^T m1, t = (gp Wd0) o m0
+            gWd0 = (C * (Wh_a * wo[None, :])[None]).sum(-1)                 # gp^T a0, a0 = (m1 (|wout| * |Wh|^T)) o m0
+            return (None,) + icnn_weight_gradients(Wd1, Wh, wout, g1, gWd0, G) + (None,)
         d, Wd0, Wd1, Wh, wout = ctx.saved_tensors
         rows = torch.nonzero((gp != 0).any(-1)).reshape(-1)        # one host read (the row count sizes the launches)
         if rows.numel() < gp.shape[0]:

@@ -127,15 +127,21 @@ class MultibodyLearnableSystem(System):
         """(B, 8) configurations -> (B, 8, 3) witness points of the two learned geometries against the
         ground: support direction of geometry i = minus the third row of its world rotation
         (geometry.py:560-567), then ``DeepSupportConvex.get_vertices`` (:309-325)."""
+        from dair_pll_b200.geometry import DeepSupportConvex
+        geoms = self.multibody_terms.contact_terms.geometries
+        _, axis = self._elbow_kin(q.dtype, q.device)
+        if q.is_cuda and q.dtype == torch.float64 and all(isinstance(g, DeepSupportConvex) for g in geoms[:2]) \
+                and geoms[0].n_query == geoms[1].n_query:
+            # one launch for both links' perturbed, normalised directions; the networks then evaluate them row by row
+            d0, d1 = ops.elbow_support_directions(q, axis, geoms[0].perturbations, geoms[1].perturbations)
+            return torch.cat((geoms[0].network(d0), geoms[1].network(d1)), -2)
         w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
         s = 2.0 / (w * w + x * x + y * y + z * z)
         row = torch.stack((s * (x * z - w * y), s * (y * z + w * x), 1 - s * (x * x + y * y)), -1)   # R1[2, :]
-        _, axis = self._elbow_kin(q.dtype, q.device)
         th = q[:, 7:8]
         # third row of R2 = R1 Rot(axis, th):  r Rot = r cos + (r x a) sin + a (a.r)(1 - cos)
         row2 = row * torch.cos(th) + torch.linalg.cross(row, axis.expand_as(row)) * torch.sin(th) \
             + axis * (row @ axis)[:, None] * (1 - torch.cos(th))
-        geoms = self.multibody_terms.contact_terms.geometries
         return torch.cat((geoms[0].get_vertices(-row), geoms[1].get_vertices(-row2)), -2)
 
     # -- ContactNets loss --------------------------------------------------

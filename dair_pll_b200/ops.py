@@ -746,6 +746,25 @@ def elbow_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Te
     return D, M, J, phi, acc
 
 
+def elbow_support_directions(q: Tensor, axis: Tensor, pert0: Tensor, pert1: Tensor):
+    """``dpll_elbow_support_directions_f64``: q (B, >= 8) rows (any row stride) -> the two links' perturbed, normalised
+    support directions (B, n_query, 3) each.  float64, no autograd (directions are data, geometry.py:309-325)."""
+    _check_inputs(q, axis, pert0, pert1)
+    if q.dtype != torch.float64:
+        raise TypeError('the support-network kernels are provided in float64')
+    if q.dim() != 2 or q.shape[1] < 8 or q.stride(1) != 1:
+        raise ValueError(f'expected (B, >= 8) configuration rows with unit column stride, got {tuple(q.shape)}')
+    B, nq = q.shape[0], pert0.shape[0]
+    d0 = torch.empty((B, nq, 3), dtype=q.dtype, device=q.device)
+    d1 = torch.empty((B, nq, 3), dtype=q.dtype, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = _lib.load().dpll_elbow_support_directions_f64(_ptr(q), q.stride(0) if B > 1 else q.shape[1], _ptr(axis.contiguous()),
+                                                           _ptr(pert0.contiguous()), _ptr(pert1.contiguous()), nq, B,
+                                                           _ptr(d0), _ptr(d1), _stream())
+    _lib.check(rc, 'dpll_elbow_support_directions')
+    return d0, d1
+
+
 def icnn_support_points(d: Tensor, Wd0: Tensor, Wd1: Tensor, Wh: Tensor, wout: Tensor, slope: float) -> Tensor:
     """Support points p (D,3) for unit directions d (D,3), nothing kept for a backward (``ICNNSupport.forward``).
     Width 256: the tensor-core kernel (``icnn_support_points_tc``); other widths: the FP64 layer path."""
@@ -754,24 +773,78 @@ def icnn_support_points(d: Tensor, Wd0: Tensor, Wd1: Tensor, Wh: Tensor, wout: T
     return icnn_support_forward(d, Wd0, Wd1, Wh, wout, slope)[0]
 
 
-def icnn_support_points_tc(d: Tensor, Wd0: Tensor, Wd1: Tensor, Wh: Tensor, wout: Tensor, slope: float) -> Tensor:
-    """``dpll_icnn_tc_prepare_f64`` + ``dpll_icnn_tc_support_f64``: support points (D,3) on the tensor cores."""
-    _check_inputs(d, Wd0, Wd1, Wh, wout)
-    if d.dtype != torch.float64:
+def icnn_tc_prepare(Wd0: Tensor, Wd1: Tensor, Wh: Tensor, wout: Tensor, slope: float):
+    """``dpll_icnn_tc_prepare_f64``: the four weights -> (digit-plane image, epilogue constants) of the tensor-core kernels."""
+    _check_inputs(Wd0, Wd1, Wh, wout)
+    if Wd0.dtype != torch.float64:
         raise TypeError('the support-network kernels are provided in float64')
     lib = _lib.load()
-    d, Wd0, Wd1, Wh, wout = (t.contiguous() for t in (d, Wd0, Wd1, Wh, wout))
-    D, W = d.shape[0], Wd0.shape[1]
-    dev = d.device
+    Wd0, Wd1, Wh, wout = (t.contiguous() for t in (Wd0, Wd1, Wh, wout))
+    dev = Wd0.device
     image = torch.empty(lib.dpll_icnn_tc_image_bytes(), dtype=torch.uint8, device=dev)
     consts = torch.empty(lib.dpll_icnn_tc_const_bytes() // 8, dtype=torch.float64, device=dev)
-    p = torch.empty((D, 3), dtype=d.dtype, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.dpll_icnn_tc_prepare_f64(_ptr(Wd0), _ptr(Wd1), _ptr(Wh), _ptr(wout), W, slope, _ptr(image),
+        _lib.check(lib.dpll_icnn_tc_prepare_f64(_ptr(Wd0), _ptr(Wd1), _ptr(Wh), _ptr(wout), Wd0.shape[1], slope, _ptr(image),
                                                 _ptr(consts), _stream()), 'dpll_icnn_tc_prepare')
-        _lib.check(lib.dpll_icnn_tc_support_f64(_ptr(d), D, _ptr(image), _ptr(consts), _ptr(Wh), W, slope, _ptr(p),
-                                                _stream()), 'dpll_icnn_tc_support')
+    return image, consts
+
+
+def icnn_support_points_tc(d: Tensor, Wd0: Tensor, Wd1: Tensor, Wh: Tensor, wout: Tensor, slope: float, prepared=None) -> Tensor:
+    """``dpll_icnn_tc_support_f64``: support points (D,3) on the tensor cores (``prepared`` = ``icnn_tc_prepare`` output)."""
+    _check_inputs(d, Wh)
+    if d.dtype != torch.float64:
+        raise TypeError('the support-network kernels are provided in float64')
+    image, consts = prepared if prepared is not None else icnn_tc_prepare(Wd0, Wd1, Wh, wout, slope)
+    d, Wh = d.contiguous(), Wh.contiguous()
+    D = d.shape[0]
+    p = torch.empty((D, 3), dtype=d.dtype, device=d.device)
+    with torch.cuda.device(d.device):
+        _lib.check(_lib.load().dpll_icnn_tc_support_f64(_ptr(d), D, _ptr(image), _ptr(consts), _ptr(Wh), Wh.shape[0], slope,
+                                                        _ptr(p), _stream()), 'dpll_icnn_tc_support')
     return p
+
+
+ICNN_TC_BWD_MAX_ROWS = 1 << 20       # rows per backward launch (int32 accumulators of the six row chunks)
+
+
+def icnn_support_backward_tc(d: Tensor, gp: Tensor, Wh: Tensor, slope: float, prepared):
+    """Weight-gradient reductions of the support network on the tensor cores, without a host read: the rows with a non-zero
+    cotangent are compacted on the device (``torch.nonzero_static``), their slope masks re-evaluated
+    (``dpll_icnn_tc_record_f64``) and contracted (``dpll_icnn_tc_bwd_f64``).  Returns (C (3,W,W), R1 (3,W), S (3)) with
+    C_k[j,i] = sum_r gp_k[r] m0[r,j] m1[r,i], R1_k[i] = sum_r gp_k[r] b1[r,i], S_k = sum_r gp_k[r]."""
+    _check_inputs(d, gp, Wh)
+    lib = _lib.load()
+    image, consts = prepared
+    W = Wh.shape[0]
+    dev = d.device
+    C = torch.zeros((3, W, W), dtype=torch.float64, device=dev)
+    R1 = torch.zeros((3, W), dtype=torch.float64, device=dev)
+    S = torch.zeros(3, dtype=torch.float64, device=dev)
+    Wh = Wh.contiguous()
+    for lo in range(0, d.shape[0], ICNN_TC_BWD_MAX_ROWS):
+        dd, gg = d[lo:lo + ICNN_TC_BWD_MAX_ROWS], gp[lo:lo + ICNN_TC_BWD_MAX_ROWS]
+        cap = dd.shape[0]
+        ldk = (cap + 127) // 128 * 128
+        live = (gg != 0).any(-1)
+        idx = torch.nonzero_static(live, size=cap, fill_value=0).reshape(-1)       # first n entries: the live rows, in order
+        n = live.sum().reshape(1)
+        d_act, g_act = dd.index_select(0, idx), gg.index_select(0, idx)
+        amax = gg.abs().amax(0)
+        m0t = torch.empty((W, ldk), dtype=torch.uint8, device=dev)
+        m1t = torch.empty((W, ldk), dtype=torch.uint8, device=dev)
+        planes = torch.empty((lib.dpll_icnn_tc_bwd_planes(), ldk), dtype=torch.int8, device=dev)
+        partial = torch.empty(lib.dpll_icnn_tc_bwd_partial_bytes() // 4, dtype=torch.int32, device=dev)
+        sums = torch.empty(6 * W + 3, dtype=torch.float64, device=dev)
+        Cb = torch.empty((3, W, W), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.dpll_icnn_tc_record_f64(_ptr(d_act), cap, _ptr(n), _ptr(image), _ptr(consts), _ptr(Wh), W, slope,
+                                                   _ptr(m0t), _ptr(m1t), ldk, _stream()), 'dpll_icnn_tc_record')
+            _lib.check(lib.dpll_icnn_tc_bwd_f64(_ptr(g_act), _ptr(n), _ptr(amax), _ptr(m0t), _ptr(m1t), ldk, slope, _ptr(planes),
+                                                _ptr(partial), _ptr(sums), _ptr(Cb), _stream()), 'dpll_icnn_tc_bwd')
+        C += Cb
+        R1 += sums[3 * W:6 * W].reshape(3, W)
+        S += sums[6 * W:]
+    return C, R1, S
 
 
 ICNN_TC_WIDTH = 256

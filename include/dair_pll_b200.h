@@ -222,6 +222,16 @@ int dpll_icnn_backward_f64(const double* gp, const double* h0aug, const double* 
                            int64_t D, int32_t W, double slope, double* t, double* part, void* stream);
 
 /*
+ * Support directions of the two elbow links against the ground -- minus the third row of each link's world rotation
+ * (GeometryCollider.collide_plane_convex, geometry.py:560-567) -- and their n_query perturbed, normalised copies
+ * (DeepSupportConvex.get_vertices, geometry.py:309-325): q rows of 8 configuration values at stride q_stride, axis (3),
+ * pert0 / pert1 (n_query, 3) the two geometries' fixed perturbations; dirs0 / dirs1 (B, n_query, 3).
+ */
+int dpll_elbow_support_directions_f64(const double* q, int64_t q_stride, const double* axis, const double* pert0,
+                                      const double* pert1, int32_t n_query, int64_t B, double* dirs0, double* dirs1,
+                                      void* stream);
+
+/*
  * Support points on the tensor cores (csrc/cn_icnn_tc.cu; width W = 256 only): HomogeneousICNN.forward
  * (deep_support_function.py:238-266) for all D direction rows in one kernel.  The layer Jacobian d z1 / d d is a
  * (binary mask) x (constant matrix) product, evaluated exactly as int8 digit-plane products by tcgen05.mma with int32
@@ -236,6 +246,28 @@ int dpll_icnn_tc_prepare_f64(const double* Wd0, const double* Wd1, const double*
                              double slope, void* image, double* consts, void* stream);
 int dpll_icnn_tc_support_f64(const double* d, int64_t D, const void* image, const double* consts, const double* Wh,
                              int32_t W, double slope, double* p, void* stream);
+
+/*
+ * Backward of the support-function network on the tensor cores (csrc/cn_icnn_tc_bwd.cu, W = 256), for the rows of a
+ * batch whose cotangent is non-zero, WITHOUT a host read: the caller compacts those rows (e.g. torch.nonzero_static) into
+ * the first *n_rows of `capacity` gathered rows and passes the count as a device scalar; every grid is fixed.
+ *   dpll_icnn_tc_record_f64   first pass over the gathered directions d (capacity, 3): the two layers' slope-mask bits as
+ *                             transposed byte matrices m0t[j][row] in {0x00, 0xFF}, m1t[i][row] in {0, 1}, row stride ldk
+ *                             (a multiple of 128, >= capacity); same kernel as dpll_icnn_tc_support_f64
+ *   dpll_icnn_tc_bwd_f64      gathered cotangent gp (capacity, 3), amax (3) = max |gp_k| -> C (3, W, W),
+ *                             C_k[j,i] = sum_r gp_k[r] m0[r,j] m1[r,i] (m = slope + (1 - slope) bit), and
+ *                             sums (6 W + 3) = [R0_k[j] = sum_r gp_k[r] b0[r,j] | R1_k[i] = sum_r gp_k[r] b1[r,i] | S_k = sum_r gp_k[r]].
+ *                             The (rows x W x W) contraction runs as exact int8 digit-plane products of the cotangent
+ *                             (56-bit fixed point per coordinate) against the mask bytes: tcgen05.mma M 128 N 256.
+ *                             Scratch: planes (dpll_icnn_tc_bwd_planes() * ldk bytes), partial (dpll_icnn_tc_bwd_partial_bytes()).
+ * All weight gradients then follow from C and sums by (W x W)-sized arithmetic (dair_pll_b200/deep_support_function.py).
+ */
+size_t dpll_icnn_tc_bwd_partial_bytes(void);
+int32_t dpll_icnn_tc_bwd_planes(void);
+int dpll_icnn_tc_record_f64(const double* d, int64_t capacity, const int64_t* n_rows, const void* image, const double* consts,
+                            const double* Wh, int32_t W, double slope, uint8_t* m0t, uint8_t* m1t, int64_t ldk, void* stream);
+int dpll_icnn_tc_bwd_f64(const double* gp, const int64_t* n_rows, const double* amax, const uint8_t* m0t, const uint8_t* m1t,
+                         int64_t ldk, double slope, int8_t* planes, int32_t* partial, double* sums, double* C, void* stream);
 
 /*
  * A single floating body whose collision geometry is ANY convex shape against the ground plane

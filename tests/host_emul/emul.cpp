@@ -8,6 +8,7 @@
 #include "../../dair_pll_b200/csrc/cn_cube_adjoint.cuh"
 #include "../../dair_pll_b200/csrc/cn_elbow_wf.cuh"
 #include "../../dair_pll_b200/csrc/cn_chain.cuh"
+#include "../../dair_pll_b200/csrc/cn_icnn_tc.cuh"
 #include <vector>
 #include <cstdint>
 using namespace cn;
@@ -39,6 +40,22 @@ static int chain_step_emul(const double* x, const double* inertia, const double*
   return 0;
 }
 extern "C" {
+// digit planes of the tensor-core support-point kernel (cn_icnn_tc.cuh): column of n weights -> digits, value the planes
+// stand for, image offsets
+int emul_tc_digits(const double* q, int n, int8_t* dig, double* rec, double* sigma_out) {
+  double cmax = 0;
+  for (int i = 0; i < n; ++i) cmax = std::fmax(cmax, std::fabs(q[i]));
+  int e;
+  *sigma_out = cn::tc_column_scale(cmax, &e);
+  for (int i = 0; i < n; ++i) {
+    cn::tc_digits(q[i], e, dig + cn::TC_NS * i);
+    rec[i] = cn::tc_reconstruct(dig + cn::TC_NS * i, e);
+  }
+  return cn::TC_NS;
+}
+int emul_tc_image_offset(int k, int s, int j, int i) { return cn::tc_image_offset(k, s, j, i); }
+int emul_tc_image_bytes() { return cn::TC_IMG_BYTES; }
+
 int emul_cube_loss_f64(const double* x, const double* xp, const double* inertia, const double* mu,
                        const double* half, double dt, double eps, int64_t B, double* loss, double* force,
                        int32_t* iters, double* grad) {

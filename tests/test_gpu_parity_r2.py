@@ -529,3 +529,84 @@ def test_generic_chain_two_links_reproduces_the_elbow_kernels(name, assets_dir):
     assert rel_err(l, ref_loss.cpu().numpy(), 1e-9).max() < 1e-10
     mine = torch.cat((inertia.grad.reshape(-1), mu.grad, half.grad.reshape(-1))).cpu().numpy()
     assert max_rel_to_scale(mine, ref_grad.cpu().numpy()) < 1e-10
+
+
+def _icnn_weights(width, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(3, width, generator=g, dtype=torch.float64), torch.randn(3, width, generator=g, dtype=torch.float64),
+            torch.randn(width, width, generator=g, dtype=torch.float64) / width, torch.randn(width, generator=g, dtype=torch.float64)]
+
+
+@pytest.mark.parametrize('slope', [0.5, 0.25, 0.0])
+def test_tensor_core_support_points_match_the_fp64_layer_path(slope):
+    """csrc/cn_icnn_tc.cu (int8 digit-plane products on tcgen05, fp64 reconstruction) against the FP64 layer path
+    (dpll_icnn_* + library GEMMs) and the oracle: empty, single-row, ragged and multi-tile batches, three slopes.
+    Tolerance 1e-11 of the point scale (the 42-bit Jacobian quantisation is below 1e-12)."""
+    from oracle import contactnets_oracle as co
+    ws = _icnn_weights(256, 5)
+    wd = [w.to(DEV) for w in ws]
+    for rows in (0, 1, 127, 128, 129, 20000):
+        d = torch.randn(rows, 3, generator=torch.Generator().manual_seed(rows), dtype=torch.float64)
+        d = d / d.norm(dim=-1, keepdim=True).clamp(min=1e-300)
+        got = ops.icnn_support_points_tc(d.to(DEV), *wd, slope)
+        assert got.shape == (rows, 3)
+        if rows == 0:
+            continue
+        ref = ops.icnn_support_forward(d.to(DEV), *wd, slope)[0]
+        scale = ref.abs().max().item()
+        assert (got - ref).abs().max().item() < 1e-11 * scale
+        if rows <= 129 and slope == 0.5:
+            po = co.icnn_support(dict(Wd0=ws[0], Wd1=ws[1], Wh=ws[2], wout=ws[3]), d)
+            assert (got.cpu() - po).abs().max().item() < 1e-11 * scale
+    # a zero direction row (what a padded tile sees) gives the zero point, not NaN
+    z = ops.icnn_support_points_tc(torch.zeros(3, 3, dtype=torch.float64, device=DEV), *wd, slope)
+    assert torch.isfinite(z).all()
+
+
+def test_support_network_backward_visits_only_rows_with_a_cotangent():
+    """ICNNSupport.backward gathers the rows whose cotangent is non-zero (3.7% of the rows of the config-3 batch) and
+    re-evaluates only those: the weight gradients equal autograd through the oracle with the same sparse cotangent;
+    an all-zero cotangent gives zero gradients."""
+    from dair_pll_b200.deep_support_function import ICNNSupport
+    from oracle import contactnets_oracle as co
+    ws = _icnn_weights(256, 9)
+    rows = 6000
+    g = torch.Generator().manual_seed(1)
+    d = torch.randn(rows, 3, generator=g, dtype=torch.float64)
+    d = d / d.norm(dim=-1, keepdim=True)
+    gp = torch.randn(rows, 3, generator=g, dtype=torch.float64)
+    gp[torch.rand(rows, generator=g) < 0.9] = 0
+    a = [w.clone().to(DEV).requires_grad_() for w in ws]
+    p = ICNNSupport.apply(d.to(DEV), a[0], a[1], a[2], a[3], 0.5)
+    (p * gp.to(DEV)).sum().backward()
+    b = [w.clone().requires_grad_() for w in ws]
+    po = co.icnn_support(dict(Wd0=b[0], Wd1=b[1], Wh=b[2], wout=b[3]), d)
+    (po * gp).sum().backward()
+    for x, y in zip(a, b):
+        assert (x.grad.cpu() - y.grad).abs().max() <= 1e-10 * y.grad.abs().max()
+    a2 = [w.clone().to(DEV).requires_grad_() for w in ws]
+    p2 = ICNNSupport.apply(d.to(DEV), a2[0], a2[1], a2[2], a2[3], 0.5)
+    (p2 * 0).sum().backward()
+    assert all((x.grad == 0).all() for x in a2)
+
+
+def test_elbow_support_directions_kernel_matches_the_tensor_formula(assets_dir):
+    """dpll_elbow_support_directions_f64 against the host formula it replaces (minus the third row of each link's
+    rotation, perturbed and normalised, geometry.py:309-325, 560-567), through a strided view of the state batch."""
+    torch.manual_seed(0)
+    s = MultibodyLearnableSystem({'elbow': os.path.join(assets_dir, 'elbow_mesh.urdf')}, DT).to(DEV)
+    x = synthetic.elbow_states(3001, seed=5, device=DEV)
+    q = x[:, :8]
+    geoms = s.multibody_terms.contact_terms.geometries
+    _, axis = s._elbow_kin(torch.float64, torch.device(DEV))
+    d0, d1 = ops.elbow_support_directions(q, axis, geoms[0].perturbations, geoms[1].perturbations)
+    w, xx, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    sc = 2.0 / (w * w + xx * xx + y * y + z * z)
+    row = torch.stack((sc * (xx * z - w * y), sc * (y * z + w * xx), 1 - sc * (xx * xx + y * y)), -1)
+    th = q[:, 7:8]
+    row2 = row * torch.cos(th) + torch.linalg.cross(row, axis.expand_as(row)) * torch.sin(th) \
+        + axis * (row @ axis)[:, None] * (1 - torch.cos(th))
+    for got, base, geom in ((d0, row, geoms[0]), (d1, row2, geoms[1])):
+        ref = -base.unsqueeze(-2) + geom.perturbations
+        ref = ref / ref.norm(dim=-1, keepdim=True)
+        assert (got - ref).abs().max().item() < 1e-14

@@ -497,3 +497,33 @@ def test_chain2_reproduces_the_elbow_goldens(name):
                                              ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-4),
                                              ctypes.c_int64(x0.shape[0]), dptr(xn))
     assert np.abs(xn - g['sim_traj'][:, 1]).max() < 1e-9
+
+
+def test_tensor_core_digit_planes_are_exact_to_42_bits():
+    """cn_icnn_tc.cuh: a weight column splits into TC_NS balanced base-128 int8 digits of a power-of-two column scale;
+    the planes stand for the weight to 2^-(7 NS) of that scale, the stored digits fit int8 with the -128 pairing
+    (|digit| <= 64), and the image offsets of all (k, plane, j, i) are a permutation of the image bytes."""
+    lib = host_emulation_lib()
+    lib.emul_tc_digits.restype = ctypes.c_int
+    rng = np.random.default_rng(0)
+    for scale in (1.0, 3.7e-5, 8.1e6):
+        q = rng.standard_normal(256) * scale
+        q[7] = 0.0
+        q[11] = np.abs(q).max() * (1 - 1e-16)        # right at the column maximum
+        dig = np.zeros(256 * 8, np.int8)
+        rec, sigma = np.zeros(256), np.zeros(1)
+        ns = lib.emul_tc_digits(dptr(q), 256, dptr(dig), dptr(rec), dptr(sigma))
+        assert ns == 6
+        s = sigma[0]
+        assert np.abs(q).max() < s <= 2 * np.abs(q).max() and np.log2(s) == np.round(np.log2(s))
+        assert np.abs(rec - q).max() <= 2.0 ** -(7 * ns) * s
+        assert np.abs(dig[:256 * ns].astype(np.int32)).max() <= 64
+    assert np.array_equal(lib.emul_tc_digits(dptr(np.zeros(4)), 4, dptr(dig), dptr(rec), dptr(sigma)) and rec[:4], np.zeros(4))
+    lib.emul_tc_image_offset.restype = ctypes.c_int
+    seen = np.zeros(lib.emul_tc_image_bytes(), np.int32)
+    for k in range(3):
+        for s_ in range(6):
+            for j in (0, 1, 15, 16, 17, 255):
+                for i in (0, 7, 8, 31, 32, 255):
+                    seen[lib.emul_tc_image_offset(k, s_, j, i)] += 1
+    assert seen.max() == 1 and seen.sum() == 3 * 6 * 36
