@@ -142,7 +142,9 @@ class GraphedStep:
     Python/launch overhead between them, which is what bounds small batches.  ``fn`` must be free of host
     synchronisation and of collectives (the NCCL all-reduce is issued after the replay, on the same stream)
     and must write its results into the same tensors on every call (``GradientAllReduce.stage`` does).  The
-    kernels take the capturing stream through the C ABI."""
+    kernels take the capturing stream through the C ABI.  Drop every result of earlier EAGER steps that still carries
+    an autograd graph before capturing: a live graph keeps the parameters' gradient accumulators, which stay bound to the
+    stream that step ran on, and autograd's end-of-backward stream synchronisation then fails inside the capture."""
 
     def __init__(self, fn: Callable[[], Tensor], device: torch.device, warmup: int = 3) -> None:
         side = torch.cuda.Stream(device=device)
