@@ -147,6 +147,16 @@ def _time_gpu(fn, device, reps, warmup=2):
     return s.elapsed_time(e) / reps
 
 
+def measured_bf16_tflops():
+    """Dense bf16 tensor throughput measured by the driver on this pool (MEASURED_PEAKS.json), else the profiling recipe's
+    nominal fallback."""
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['bf16_tflops'])
+    except (OSError, KeyError, ValueError):
+        return 2250.0
+
+
 def _roofline(flops, ms, peak_flops, extra=None):
     out = {'bound': 'fp64_cuda_core', 'achieved': flops / (ms * 1e-3) / 1e12, 'peak': peak_flops / 1e12, 'unit': 'TFLOP/s',
            'frac': flops / (ms * 1e-3) / peak_flops, 'kernel_ms': ms}
@@ -302,7 +312,9 @@ def secondary_configs(device, peak_flops):
         ((traj - target) ** 2).mean().backward()
     ms = _time_gpu(pred_step, device, 3, warmup=1)
     out['cube_prediction_loss_4096x80_f64'] = {'ms': ms, 'steps_per_s': 4096 * 80 / ms * 1e3,
-                                               'note': 'forward rollout + backward through every step (dpll_cube_rollout_grad_f64)'}
+                                               'note': 'forward rollout keeping every QP optimum + reverse-mode backward through every step '
+                                                       '(dpll_cube_rollout_saved_f64 / dpll_cube_rollout_backward_f64) + the torch MSE on the '
+                                                       'trajectory'}
     # elbow (two bodies, 8 contacts) with box geometries, loss + backward at B = 262,144
     FO_EL, FIT_EL = 12000.0, 4700.0
     ebox = MultibodyLearnableSystem({'elbow': os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow.urdf')}, DT).to(device)
@@ -347,18 +359,37 @@ def secondary_configs(device, peak_flops):
         te, _ = elbow.simulate(xe.unsqueeze(-2), torch.zeros(Be, 1, device=device), 1)
     xpm = synthetic.perturb_next_state(te[:, 1], seed=4, n_q=8)
 
+    params_m = list(elbow.parameters())
+
     def elbow_step():
-        for p in elbow.parameters():
+        for p in params_m:
             p.grad = None
-        elbow.contactnets_loss(xe, None, xpm).mean().backward()
-    ms = _time_gpu(elbow_step, device, 3, warmup=1)
-    ICNN_FLOPS = 4.28e6
+        loss = elbow.contactnets_loss(xe, None, xpm)
+        loss.mean().backward()
+        return loss.detach()       # (a live autograd graph of an eager step would break the later capture)
+    ms_eager_m = _time_gpu(elbow_step, device, 3, warmup=1)
+    ms = _time_gpu(parallel.GraphedStep(elbow_step, device), device, 10)
+    # dominant kernel: the support-point kernel of ONE network over its D = 4 B direction rows (two such launches per step)
+    net = elbow.multibody_terms.contact_terms.geometries[0].network
+    ws = [net.input_weights[0].detach(), net.input_weights[1].detach(), net.hidden_weights[0].detach(), net.output_weight.detach()]
+    Dm = 4 * Be
+    dirs = torch.randn(Dm, 3, dtype=torch.float64, device=device)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    prepared = ops.icnn_tc_prepare(*ws, net.negative_slope)
+    ms_k = _time_gpu(lambda: ops.icnn_support_points_tc(dirs, *ws, net.negative_slope, prepared), device, 10)
+    TC_OPS_PER_ROW = 2.0 * 3 * 6 * 256 * 256        # 3 input coordinates x 6 int8 digit planes x (256 x 256) MACs
+    int8_peak = 2.0 * measured_bf16_tflops() * 1e12
     out['elbow_mesh_loss_backward_B262144_f64'] = {
-        'ms': ms, 'samples_per_s': Be / ms * 1e3,
-        'roofline': _roofline(Be * (ICNN_FLOPS + FO_EL + FIT_EL * mean_it), ms, peak_flops,
-                              {'kernel': 'support-function networks (FP64 GEMMs + dpll_icnn_* layers) + elbow loss kernel',
-                               'flops_per_sample': ICNN_FLOPS + FO_EL + FIT_EL * mean_it,
-                               'note': 'whole step, not one kernel; Newton count taken from the box-geometry batch'})}
+        'ms': ms, 'samples_per_s': Be / ms * 1e3, 'eager_ms': ms_eager_m, 'step': 'CUDA graph replay of the public-API step',
+        'roofline': {'bound': 'tensor', 'kernel': 'icnn_tc_kernel (support points of one network, D = 1,048,576 rows; 2 launches '
+                                                  'per step)',
+                     'achieved': Dm * TC_OPS_PER_ROW / (ms_k * 1e-3) / 1e12, 'peak': int8_peak / 1e12, 'unit': 'TOP/s (int8)',
+                     'frac': Dm * TC_OPS_PER_ROW / (ms_k * 1e-3) / int8_peak, 'kernel_ms': ms_k,
+                     'ops_per_row': TC_OPS_PER_ROW,
+                     'peak_source': '2 x MEASURED_PEAKS.json bf16_tflops (tcgen05 kind::i8 issues at twice the bf16 rate; no '
+                                    'measured int8 figure exists)',
+                     'note': 'exact fp64 result from int8 digit-plane products; FP64-equivalent work of the replaced GEMMs: '
+                             '4.28e6 FLOP per sample'}}
     return out
 
 
@@ -576,19 +607,28 @@ def main():
     n_flat = sum(p.numel() for p in params) + 1
     out_host = torch.empty(n_flat, dtype=torch.float64).pin_memory()
 
-    def step_e2e():
-        for p in params:
-            p.grad = None
-        total = loader.loss_sum_from_host(xh, xph)
-        mean = total / Bg
-        mean.backward()
-        flat = torch.cat([p.grad.reshape(-1) for p in params] + [mean.detach().reshape(1)])
-        if comm is not None:
-            flat = comm.all_reduce_sum(flat)
-        elif world > 1:
+    if hasattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch'):
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)    # capture runs on a side stream by design
+    e2e_note = 'one CUDA graph: chunked H2D copies (side stream) + loss launches + backward + exchange + D2H'
+    if comm is not None or world == 1:
+        graphed_e2e = loader.capture_step(xh, xph, params, float(Bg), out_host, comm)
+
+        def step_e2e():
+            graphed_e2e()
+            torch.cuda.current_stream().synchronize()      # the user reads the loss / gradients on the host
+    else:
+        e2e_note = 'eager chunk launches + NCCL all-reduce'
+
+        def step_e2e():
+            for p in params:
+                p.grad = None
+            total = loader.loss_sum_from_host(xh, xph)
+            mean = total / Bg
+            mean.backward()
+            flat = torch.cat([p.grad.reshape(-1) for p in params] + [mean.detach().reshape(1)])
             dist.all_reduce(flat)
-        out_host.copy_(flat, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the user reads the loss / gradients on the host
+            out_host.copy_(flat, non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the user reads the loss / gradients on the host
     ms_e2e, _ = timed(step_e2e, max(3, args.steps // 2), 3, min_ms=300.0)
     e2e_value = Bg / (ms_e2e * 1e-3)
     h2d = 2 * B * 13 * x.element_size()
@@ -687,7 +727,7 @@ def main():
                    'step': 'eager launches' if args.no_graph else 'CUDA graph replay of the public-API step',
                    'eager_ms_per_step': orders[args.order]['eager_ms_per_step']},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h},
+                'd2h_bytes_per_step': d2h, 'step': e2e_note, 'chunks': loader.chunks},
         'gpu_launches': 3 * orders[args.order]['timed_steps'],   # per step: parameter preparation + loss/backward +
                                                                   # reduce/chain rule(/exchange)
         'roofline': {'bound': 'fp64_cuda_core',

@@ -66,6 +66,13 @@ class ContactTerms(Module):
     def get_friction_coefficients(self) -> Tensor:
         return self.friction_params.abs()
 
+    def pair_index32(self) -> Tensor:
+        """(2, n_pairs) int32 copy of ``collision_candidates`` on the parameters' device (created once per device)."""
+        dev = self.friction_params.device
+        if getattr(self, '_pair32', None) is None or self._pair32.device != dev:
+            self._pair32 = torch.tensor(list(zip(*self._pairs)), dtype=torch.int32, device=dev).reshape(2, -1).contiguous()
+        return self._pair32
+
     def pair_friction(self) -> Tensor:
         """(n_pairs,) combined coefficient 2 mu_a mu_b / (mu_a + mu_b) (multibody_terms.py:466-471)."""
         mu = self.get_friction_coefficients()
@@ -98,12 +105,24 @@ class MultibodyTerms(Module):
             for bi, b in enumerate(self.spec.bodies)}
 
     def kernel_parameters(self, dtype: torch.dtype) -> Tuple[Tensor, Tensor, List[Tensor]]:
-        """Callable-level parameters in the kernels' dtype, differentiable w.r.t. the leaves."""
-        inertia = self.lagrangian_terms.inertia_vector().to(dtype)
-        mu = self.contact_terms.pair_friction().to(dtype)
-        if self.contact_terms.has_learned_geometry() or self.contact_terms.has_witness_point_geometry():
+        """Callable-level parameters in the kernels' dtype, differentiable w.r.t. the leaves.  float64 on a CUDA device:
+        one launch (``ops.LeafPrepare``, and one more for the chain rule) instead of the elementwise PyTorch graph."""
+        lt, ct = self.lagrangian_terms, self.contact_terms
+        boxes = not (ct.has_learned_geometry() or ct.has_witness_point_geometry())
+        theta = lt.inertial_parameters
+        if theta.is_cuda and dtype == torch.float64 and theta.dtype == torch.float64:
+            from dair_pll_b200 import ops
+            if boxes:
+                length = torch.cat([ct.geometries[b].length_params.reshape(3) for _, b in ct._pairs])
+            else:
+                length = theta.new_empty(0)
+            inertia, mu, half = ops.LeafPrepare.apply(theta, ct.friction_params, ct.pair_index32(), length)
+            return inertia, mu, (list(half.reshape(-1, 3).unbind(0)) if boxes else [])
+        inertia = lt.inertia_vector().to(dtype)
+        mu = ct.pair_friction().to(dtype)
+        if not boxes:
             return inertia, mu, []
-        half = [h.to(dtype) for h in self.contact_terms.half_lengths()]
+        half = [h.to(dtype) for h in ct.half_lengths()]
         return inertia, mu, half
 
     def forward(self, q: Tensor, v: Tensor, u: Tensor = None):

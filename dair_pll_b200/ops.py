@@ -746,6 +746,48 @@ def elbow_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Te
     return D, M, J, phi, acc
 
 
+class LeafPrepare(torch.autograd.Function):
+    """Learnable leaves -> callable-level parameters, one launch each way (``dpll_leaf_prepare_f64`` /
+    ``dpll_leaf_backward_f64``, csrc/cn_leaf.cu): theta (n_bodies, 10) -> inertia (n_bodies, 10); friction_params
+    (n_geoms,) and the collision pairs' geometry indices (int32 (2, n_pairs)) -> pair friction (n_pairs,); length
+    parameters (n_len,) -> |.|.  Replaces ~100 elementwise PyTorch launches (and their autograd nodes) per step of the
+    systems that have no fused training entry point (two-body tree, generic chains).  float64, CUDA."""
+
+    @staticmethod
+    def forward(ctx, theta, friction, pairs, length):
+        _check_inputs(theta, friction, length)
+        if theta.dtype != torch.float64:
+            raise TypeError('dpll_leaf_prepare is provided in float64')
+        theta, friction, length = theta.contiguous(), friction.contiguous(), length.contiguous()
+        assert pairs.dtype == torch.int32 and pairs.is_cuda and pairs.is_contiguous() and pairs.shape[0] == 2
+        nb, npair, nlen = theta.shape[0], pairs.shape[1], length.numel()
+        inertia = torch.empty_like(theta)
+        mu = torch.empty(npair, dtype=theta.dtype, device=theta.device)
+        half = torch.empty(nlen, dtype=theta.dtype, device=theta.device)
+        with torch.cuda.device(theta.device):
+            rc = _lib.load().dpll_leaf_prepare_f64(_ptr(theta), nb, _ptr(friction), pairs.data_ptr(),
+                                                   pairs.data_ptr() + 4 * npair, npair, _ptr(length), nlen, _ptr(inertia),
+                                                   _ptr(mu), _ptr(half), _stream())
+        _lib.check(rc, 'dpll_leaf_prepare')
+        ctx.save_for_backward(theta, friction, pairs, length)
+        return inertia, mu, half
+
+    @staticmethod
+    def backward(ctx, g_inertia, g_mu, g_half):
+        theta, friction, pairs, length = ctx.saved_tensors
+        nb, npair, nlen = theta.shape[0], pairs.shape[1], length.numel()
+        g_theta, g_friction, g_length = torch.empty_like(theta), torch.empty_like(friction), torch.empty_like(length)
+        cont = lambda g: None if g is None else g.contiguous()      # noqa: E731
+        g_inertia, g_mu, g_half = cont(g_inertia), cont(g_mu), cont(g_half)
+        with torch.cuda.device(theta.device):
+            rc = _lib.load().dpll_leaf_backward_f64(_ptr(theta), nb, _ptr(friction), friction.numel(), pairs.data_ptr(),
+                                                    pairs.data_ptr() + 4 * npair, npair, _ptr(length), nlen, _ptr(g_inertia),
+                                                    _ptr(g_mu), _ptr(g_half), _ptr(g_theta), _ptr(g_friction),
+                                                    _ptr(g_length), _stream())
+        _lib.check(rc, 'dpll_leaf_backward')
+        return g_theta, g_friction, None, g_length
+
+
 def elbow_support_directions(q: Tensor, axis: Tensor, pert0: Tensor, pert1: Tensor):
     """``dpll_elbow_support_directions_f64``: q (B, >= 8) rows (any row stride) -> the two links' perturbed, normalised
     support directions (B, n_query, 3) each.  float64, no autograd (directions are data, geometry.py:309-325)."""

@@ -44,7 +44,7 @@ extern "C" {
 #define DPLL_EWORKSPACE (-2) /* workspace too small */
 #define DPLL_ECOMM (-3)      /* a peer did not arrive within the exchange's timeout */
 
-#define DPLL_VERSION 201     /* bumped with every change of a signature below; the binding checks it */
+#define DPLL_VERSION 202     /* bumped with every change of a signature below; the binding checks it */
 
 #define DPLL_CUBE_NX 13
 #define DPLL_CUBE_NC 4
@@ -418,6 +418,23 @@ int dpll_chain_loss_f64(int32_t n_links, const double* x, const double* x_plus, 
 int dpll_chain_rollout_f64(int32_t n_links, const double* x0, const double* inertia, const double* mu_pair,
                            const double* half, const double* kin, double dt, double eps, int64_t B, int32_t steps,
                            double* traj, void* stream);
+
+/*
+ * Parameter preparation of any system and its chain rule, one launch each (csrc/cn_leaf.cu): theta (n_bodies, 10)
+ * -> inertia (n_bodies, 10) = [m, c, I_cm / m] (inertia.py:205-234, 304-331, 376-382 as LagrangianTerms.forward applies
+ * them, multibody_terms.py:230-231); friction_params (n_geoms) -> mu_pair (n_pairs) = 2 |a| |b| / (|a| + |b|) for the
+ * pair's two geometry indices pair_a[p], pair_b[p] (multibody_terms.py:321-324, 466-471); length_params (n_len doubles)
+ * -> half = |length| (geometry.py:394-397).  dpll_leaf_backward_f64 maps the cotangents of (inertia, mu_pair, half)
+ * (any of them NULL = zero) to those of (theta, friction_params, length_params); d|v|/dv = 0 at v = 0.  The single
+ * floating box has the same maps fused into dpll_cube_loss_leaf_*.
+ */
+int dpll_leaf_prepare_f64(const double* theta, int32_t n_bodies, const double* friction, const int32_t* pair_a,
+                          const int32_t* pair_b, int32_t n_pairs, const double* length, int32_t n_len, double* inertia,
+                          double* mu_pair, double* half, void* stream);
+int dpll_leaf_backward_f64(const double* theta, int32_t n_bodies, const double* friction, int32_t n_geoms,
+                           const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs, const double* length, int32_t n_len,
+                           const double* g_inertia, const double* g_mu_pair, const double* g_half, double* g_theta,
+                           double* g_friction, double* g_length, void* stream);
 
 /*
  * FP64 / FP32 FMA throughput micro-benchmark used by bench.py to measure the CUDA-core

@@ -610,3 +610,37 @@ def test_elbow_support_directions_kernel_matches_the_tensor_formula(assets_dir):
         ref = -base.unsqueeze(-2) + geom.perturbations
         ref = ref / ref.norm(dim=-1, keepdim=True)
         assert (got - ref).abs().max().item() < 1e-14
+
+
+@pytest.mark.parametrize('name', ['cube', 'elbow', 'chain3'])
+def test_leaf_preparation_kernels_match_the_host_parameter_graph(name, assets_dir):
+    """dpll_leaf_prepare_f64 / dpll_leaf_backward_f64 (one launch each) against the PyTorch graph they replace --
+    theta -> [m, c, I_cm/m] (inertia.py:205-234, 304-331, 376-382), pairwise friction (multibody_terms.py:466-471),
+    |length_params| (geometry.py:394-397) -- values and the chain rule to the leaves, with perturbed (sign-mixed) leaves."""
+    s = MultibodyLearnableSystem({name: os.path.join(assets_dir, f'{name}.urdf')}, DT).to(DEV)
+    mt = s.multibody_terms
+    gen = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for p in mt.parameters():
+            p.mul_(1 + 0.2 * (torch.rand(p.shape, generator=gen, dtype=p.dtype) - 0.5).to(DEV))
+        mt.contact_terms.friction_params[0].neg_()               # |.| and its sign in the chain rule
+        mt.contact_terms.geometries[mt.contact_terms._pairs[0][1]].length_params[0, 1].neg_()
+    inertia, mu, half = mt.kernel_parameters(torch.float64)                         # the kernels
+    ref_in = mt.lagrangian_terms.inertia_vector()
+    ref_mu = mt.contact_terms.pair_friction()
+    ref_half = mt.contact_terms.half_lengths()
+    assert max_rel_to_scale(inertia.detach().cpu().numpy(), ref_in.detach().cpu().numpy()) < 1e-14
+    assert max_rel_to_scale(mu.detach().cpu().numpy(), ref_mu.detach().cpu().numpy()) < 1e-15
+    assert len(half) == len(ref_half)
+    wi, wm = torch.randn_like(ref_in), torch.randn_like(ref_mu)
+    wh = [torch.randn_like(h) for h in ref_half]
+    for h, r in zip(half, ref_half):
+        assert torch.equal(h.detach(), r.detach())
+    grads = []
+    for (a, b, c) in ((inertia, mu, half), (ref_in, ref_mu, ref_half)):
+        for p in mt.parameters():
+            p.grad = None
+        ((a * wi).sum() + (b * wm).sum() + sum((h * w).sum() for h, w in zip(c, wh))).backward()
+        grads.append(_leaf_grads(s))
+    for got, ref in zip(*grads):
+        assert max_rel_to_scale(got, ref) < 1e-13

@@ -16,7 +16,14 @@ WANT = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
         'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum', 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum',
         'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum', 'sm__cycles_active.avg',
-        'smsp__inst_executed_op_branch.sum', 'sm__inst_executed_pipe_fp64.sum']
+        'smsp__inst_executed_op_branch.sum', 'sm__inst_executed_pipe_fp64.sum',
+        # tensor-core kernels (tcgen05 / TMEM / bulk copies)
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_tmem.sum.pct_of_peak_sustained_active', 'sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'smsp__sass_inst_executed_op_tmem_ldt.sum', 'smsp__sass_inst_executed_op_tmem_stt.sum', 'lts__t_bytes.sum',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed']
 out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
