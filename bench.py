@@ -469,20 +469,29 @@ def main():
         run_reference(args, out)
         return
     import torch.distributed as dist
+    if hasattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch'):
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)    # graph capture runs on a side stream by design
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit('launch N>1 with torch.distributed.run --nproc-per-node N')
-    torch.cuda.set_device(local_rank)
-    device = torch.device('cuda', local_rank)
+    # N < visible GPUs: spread the ranks over the box (rank r -> GPU r * stride).  On the HGX boards of this pool four GPUs
+    # share one PCIe root (measured: ~105 GB/s of pinned host->device copies per group of four, 51 GB/s per GPU), so four
+    # ranks on GPUs 0-3 get half the end-to-end copy bandwidth of four ranks on GPUs 0, 2, 4, 6; NVLink is all-to-all.
+    visible = torch.cuda.device_count()
+    dev_index = local_rank * (visible // world) if (world > 1 and visible >= 2 * world) else local_rank
+    torch.cuda.set_device(dev_index)
+    device = torch.device('cuda', dev_index)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the single JSON line
         dist.init_process_group('nccl', device_id=device)
     dtype = torch.float64 if args.dtype == 'f64' else torch.float32
     from dair_pll_b200 import ops, parallel
+    # one process per GPU: keep each rank (and the pinned staging buffers it allocates) on its GPU's NUMA node
+    host_binding = parallel.bind_host_to_gpu(dev_index) if world > 1 else None
     ops.set_loss_variant(args.variant)
     scaling = args.scaling or ('strong' if world > 1 else 'weak')
     system = make_system(device, dtype)
@@ -551,41 +560,54 @@ def main():
             # the same repetition count on every rank: derived from the all-reduced time
             reps = max(1, min(100000, int((min_ms - total_ms) / max(ms.item() / (reps * steps), 1e-3) / steps) + 1))
 
+    L2_BYTES = 126e6
+
     def make_step(order):
-        """The public-API step on this rank's shard: loss.mean().backward() -> (global) mean loss + param.grad."""
+        """The public-API step on this rank's shard: loss.mean().backward() -> (global) mean loss + param.grad.
+        A shard that would fit the L2 (strong scaling, N > 1) is replicated into enough distinct buffers that consecutive
+        steps never read rows still resident from the previous ones: the steps cycle through > 2 L2 sizes of inputs."""
         x, xp = shard(order)
+        step_bytes = 2 * x.shape[0] * 13 * x.element_size()
+        copies = 1 if step_bytes > L2_BYTES else int(2.5 * L2_BYTES / step_bytes) + 1
+        bufs = [(x, xp)] + [(x.clone(), xp.clone()) for _ in range(copies - 1)]
         u = torch.zeros(x.shape[0], 0, device=device, dtype=dtype)
         system.dynamic_schedule = order == 'cost'
         system.data_parallel = comm
+        turn = {'eager': 0, 'graph': 0}
 
-        def step_local():
-            if reducer is not None:
-                reducer.zero()
-            else:
-                for p in params:
-                    p.grad = None
-            mean = system.contactnets_loss(x, u, xp).mean()
-            mean.backward()
-            return reducer.stage(mean) if reducer is not None else mean
+        def make_local(xx, xxp):
+            def step_local():
+                if reducer is not None:
+                    reducer.zero()
+                else:
+                    for p in params:
+                        p.grad = None
+                mean = system.contactnets_loss(xx, u, xxp).mean()
+                mean.backward()
+                return reducer.stage(mean) if reducer is not None else mean
+            return step_local
+        locals_ = [make_local(xx, xxp) for xx, xxp in bufs]
 
         def step_eager():
-            out = step_local()
+            turn['eager'] = (turn['eager'] + 1) % copies
+            out = locals_[turn['eager']]()
             return reducer.reduce() if reducer is not None else out
         if args.no_graph:
-            return step_eager, step_eager, x, xp
+            return step_eager, step_eager, x, xp, copies
         # with the in-kernel exchange the WHOLE step is one CUDA graph; with NCCL the all-reduce follows the replay
-        graphed = parallel.GraphedStep(step_local, device)
+        graphs = [parallel.GraphedStep(fn, device) for fn in locals_]
 
         def step_graphed():
-            out = graphed()
+            turn['graph'] = (turn['graph'] + 1) % copies
+            out = graphs[turn['graph']]()
             return reducer.reduce() if reducer is not None else out
-        return step_graphed, step_eager, x, xp
+        return step_graphed, step_eager, x, xp, copies
 
     # ---- device-resident throughput (value): both batch orders, the configured one is the headline ----------
     orders = {}
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(dev_index)
     for order in (['natural', 'cost'] if args.order == 'cost' else ['cost', 'natural']):   # headline order last
-        step, step_eager, x, xp = make_step(order)
+        step, step_eager, x, xp, input_copies = make_step(order)
         ms_eager, _ = timed(step_eager, args.steps, max(args.warmup, 3))
         headline = order == args.order
         if headline and rank == 0:
@@ -607,8 +629,6 @@ def main():
     n_flat = sum(p.numel() for p in params) + 1
     out_host = torch.empty(n_flat, dtype=torch.float64).pin_memory()
 
-    if hasattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch'):
-        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)    # capture runs on a side stream by design
     e2e_note = 'one CUDA graph: chunked H2D copies (side stream) + loss launches + backward + exchange + D2H'
     if comm is not None or world == 1:
         graphed_e2e = loader.capture_step(xh, xph, params, float(Bg), out_host, comm)
@@ -713,9 +733,10 @@ def main():
         'config': {'workload': workload, 'batch_per_gpu': B, 'global_batch': Bg, 'dt': DT, 'eps': 1e-3,
                    'parallelism': f'dp{world}',
                    'l2_policy': (f'inputs larger than L2 ({2 * B * 13 * x.element_size() / 1e6:.0f} MB per step vs 126 MB)'
-                                 if 2 * B * 13 * x.element_size() > 126e6 else
-                                 f'inputs of {2 * B * 13 * x.element_size() / 1e6:.0f} MB per step fit the 126 MB L2 at this shard '
-                                 'size: the kernel is FP64-bound (HBM fraction below), so residency does not change the time'),
+                                 if input_copies == 1 else
+                                 f'inputs of {2 * B * 13 * x.element_size() / 1e6:.0f} MB per step would fit the 126 MB L2: the steps '
+                                 f'cycle through {input_copies} distinct copies of the shard '
+                                 f'({input_copies * 2 * B * 13 * x.element_size() / 1e6:.0f} MB), one captured graph per copy'),
                    'mean_newton_iters': mean_iters, 'storage': args.dtype,
                    'order': (args.order + ': batch handed to the kernel by decreasing Newton count of the previous pass '
                              '(cost hints as a training loop has them from its last epoch, computed outside the timed '
@@ -727,7 +748,8 @@ def main():
                    'step': 'eager launches' if args.no_graph else 'CUDA graph replay of the public-API step',
                    'eager_ms_per_step': orders[args.order]['eager_ms_per_step']},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'step': e2e_note, 'chunks': loader.chunks},
+                'd2h_bytes_per_step': d2h, 'step': e2e_note, 'chunks': loader.chunks,
+                'host_binding': host_binding},
         'gpu_launches': 3 * orders[args.order]['timed_steps'],   # per step: parameter preparation + loss/backward +
                                                                   # reduce/chain rule(/exchange)
         'roofline': {'bound': 'fp64_cuda_core',

@@ -21,6 +21,24 @@ def shard_bounds(n: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def bind_host_to_gpu(device_index: int) -> Optional[str]:
+    """Pins the calling process to the CPUs of the NUMA node its GPU hangs off (NVML's ideal affinity), so that pinned
+    staging buffers allocated afterwards are first-touched in the memory next to that GPU's PCIe root.  With one process
+    per GPU the host->device copies of all ranks otherwise share whichever socket the processes happened to start on.
+    Returns a short description, or None if NVML is unavailable or the affinity cannot be set (containers with a
+    restricted cpuset): the step then simply runs unbound."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        import os
+        cpus = sorted(os.sched_getaffinity(0))
+        return f'{len(cpus)} cpus [{cpus[0]}..{cpus[-1]}]'
+    except Exception:      # noqa: BLE001 -- best effort by design
+        return None
+
+
 class PeerComm:
     """Communicator of the in-kernel gradient exchange (``dpll_comm_*``, csrc/cn_comm.cuh): every rank owns a
     small buffer in its HBM that all peers map through CUDA IPC, and the reduction kernel of the loss launch
