@@ -404,8 +404,22 @@ template <typename T> struct CubeLossAux {
   T vp[6];      // v+, state coordinates
   T pos_z;
   T konst;      // 1/2 dv^T M dv + sum max(-phi,0)^2   (:163-170)
+  T u0[6];      // start point of the Newton solve (world twist), see cube_loss_prologue
   uint32_t sel; // selected corners (sign bits)
 };
+
+// Start point of the loss QP's solve.  In the primal form every contact's residual is r_c(u) = D_mu J_c (u - dv) + s_c with
+// s_c = [dt mu v_t ; |phi| + dt |mu v_t|] inside the polar cone: u = dv (the measured velocity change, world twist) is always
+// feasible with zero forces, u = 0 minimises the kinetic term, and the optimum is (up to eps) the M-projection of 0 onto the
+// feasible set.  Along the segment u = (1 - a) dv the residual is the interpolation (1 - a) s_c + a q_c, so the a at which
+// contact c leaves the polar cone is the root of one quadratic; a_b = min_c a_c is where the segment leaves the feasible set.
+// Starting the Newton iteration at a = min(1, CN_LOSS_START_FACTOR a_b) instead of u = 0 (a = 1) puts it next to the
+// contacts that actually activate: measured on the bench batch 11.1 -> 7.4 evaluations per solve, on recorded tosses 8.5 ->
+// 7.6 (tools/exp_solver_trace.py; factors 3..9 are within 3% of each other, 1 -- the boundary itself -- gains nothing because
+// the curvature there is still M alone).  The optimum is unique, so only the iteration count changes.  0 disables it.
+#ifndef CN_LOSS_START_FACTOR
+#define CN_LOSS_START_FACTOR 7.0
+#endif
 
 template <typename T, int UNR>
 CN_HD void cube_loss_prologue(const CubeParams<T>& P, const T* x, const T* xp, const CubeProb<T>& S,
@@ -422,7 +436,7 @@ CN_HD void cube_loss_prologue(const CubeParams<T>& P, const T* x, const T* xp, c
   rot3(A.R, A.dv, dvW); rot3(A.R, A.vp, vW);
 #pragma unroll
   for (int i = 0; i < 3; ++i) { dvW[3 + i] = A.dv[3 + i]; vW[3 + i] = A.vp[3 + i]; }
-  T pen = T(0);
+  T pen = T(0), a_min = T(2);
 #pragma unroll UNR
   for (int c = 0; c < CUBE_NC; ++c) {
     const T rho[3] = {S.rho(3 * c), S.rho(3 * c + 1), S.rho(3 * c + 2)};
@@ -434,11 +448,28 @@ CN_HD void cube_loss_prologue(const CubeParams<T>& P, const T* x, const T* xp, c
     const T speed2 = sx * sx + sy * sy;
     const T speed = speed2 * t_rsqrt(t_max(speed2, t_tiny<T>()));
     const T phic = rho[2] + A.pos_z;
-    S.q(3 * c) = -P.mu * ed[0] + P.dt * sx;                       // :158-161
-    S.q(3 * c + 1) = -P.mu * ed[1] + P.dt * sy;
-    S.q(3 * c + 2) = -ed[2] + t_abs(phic) + P.dt * speed;
+    const T s0 = P.dt * sx, s1 = P.dt * sy, s2 = t_abs(phic) + P.dt * speed;
+    const T e0 = -P.mu * ed[0], e1 = -P.mu * ed[1], e2 = -ed[2];
+    S.q(3 * c) = e0 + s0;                                          // :158-161
+    S.q(3 * c + 1) = e1 + s1;
+    S.q(3 * c + 2) = e2 + s2;
     const T pneg = t_max(-phic, T(0));
     pen += pneg * pneg;
+    if (CN_LOSS_START_FACTOR > 0) {
+      // |s_t + a e_t|^2 = (s_n + a e_n)^2: smallest positive root, in the cancellation-free form -2 C / (B + sqrt(disc))
+      const T Aq = e0 * e0 + e1 * e1 - e2 * e2, Bq = T(2) * (s0 * e0 + s1 * e1 - s2 * e2);
+      const T Cq = t_min(s0 * s0 + s1 * s1 - s2 * s2, T(0));
+      const T disc = Bq * Bq - T(4) * Aq * Cq;
+      const T dpos = t_max(disc, T(0));
+      const T den = Bq + dpos * t_rsqrt(t_max(dpos, t_tiny<T>()));
+      const T a_c = (disc >= T(0) && den > T(0)) ? T(-2) * Cq * t_rcp(den) : T(2);
+      a_min = t_min(a_min, a_c);
+    }
+  }
+  {
+    const T a0 = t_min(T(CN_LOSS_START_FACTOR) * a_min, T(1));
+#pragma unroll
+    for (int i = 0; i < 6; ++i) A.u0[i] = (T(1) - a0) * dvW[i];
   }
   T Mdv[6];
   cube_mass_mul(P, S, dvW, Mdv);
@@ -688,7 +719,9 @@ CN_HD T cube_loss_sample(const CubeParams<T>& P, const SolverCfg<T>& cfg, const 
   const CubeProb<T> S{store, 1};
   CubeLossAux<T> A;
   cube_loss_prologue<T, 4>(P, x, xp, S, A);
-  T u[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  T u[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) u[i] = A.u0[i];
   const int it = cube_solve<T, 4>(P, S, cfg, u);
   if (iters_out) *iters_out = it;
   return cube_loss_epilogue<T, 4>(P, S, A, u, grad, force_out);

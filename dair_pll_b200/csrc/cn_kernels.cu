@@ -357,7 +357,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
             pool->sample[slot] = -1;
           } else {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = u_init ? T(u_init[b * 6 + i]) : T(0);
+            for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = u_init ? T(u_init[b * 6 + i]) : A.u0[i];
             pool->field[39][slot] = T(-1);
             pool->field[46][slot] = T(0);
             pool->sample[slot] = (int32_t)(b - lo);
