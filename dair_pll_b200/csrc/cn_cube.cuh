@@ -467,7 +467,7 @@ CN_HD void cube_loss_prologue(const CubeParams<T>& P, const T* x, const T* xp, c
     }
   }
   {
-    const T a0 = t_min(T(CN_LOSS_START_FACTOR) * a_min, T(1));
+    const T a0 = CN_LOSS_START_FACTOR > 0 ? t_min(T(CN_LOSS_START_FACTOR) * a_min, T(1)) : T(1);
 #pragma unroll
     for (int i = 0; i < 6; ++i) A.u0[i] = (T(1) - a0) * dvW[i];
   }

@@ -248,7 +248,7 @@ elbow_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const 
             pool->sample[slot] = -1;
           } else {
 #pragma unroll
-            for (int i = 0; i < 7; ++i) pool->field[77 + i][slot] = T(0);
+            for (int i = 0; i < 7; ++i) pool->field[77 + i][slot] = (T(1) - A.a_start) * A.dv[i];
             pool->field[91][slot] = T(-1);
             pool->field[92][slot] = T(0);
             pool->sample[slot] = (int32_t)(b - lo);

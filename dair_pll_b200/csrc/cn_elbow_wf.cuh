@@ -238,6 +238,7 @@ CN_HD void elbow_contact_geometry(const ElbowSetup<T>& E, int c, const T* p, T* 
 template <typename T> struct ElbowLossCore {
   T vp[7], dv[7], acc[7], b2[6];
   T pos_z, konst;
+  T a_start;    // start fraction of the Newton solve on the feasible segment u = (1 - a) dv (cube_loss_prologue, cn_cube.cuh)
   uint32_t sel0, sel1;
 };
 
@@ -284,7 +285,7 @@ template <typename T> CN_HD void point_vel7(const T* rho, const T* hcol, const T
 // q_c of the loss QP (:158-161) and the contact's penetration term
 template <typename T>
 CN_HD void elbow_loss_q(const ElbowParams<T>& P, const ElbowLossCore<T>& A, int c, const T* rho, const T* hcol, T* qc,
-                        T& pen) {
+                        T& pen, T& a_min) {
   const T mu = elbow_mu(P, c);
   T ed[3], ev[3];
   point_vel7(rho, hcol, A.dv, ed);
@@ -293,11 +294,23 @@ CN_HD void elbow_loss_q(const ElbowParams<T>& P, const ElbowLossCore<T>& A, int 
   const T speed2 = sx * sx + sy * sy;
   const T speed = speed2 * t_rsqrt(t_max(speed2, t_tiny<T>()));
   const T phic = rho[2] + A.pos_z;
-  qc[0] = -mu * ed[0] + P.dt * sx;
-  qc[1] = -mu * ed[1] + P.dt * sy;
-  qc[2] = -ed[2] + t_abs(phic) + P.dt * speed;
+  const T s0 = P.dt * sx, s1 = P.dt * sy, s2 = t_abs(phic) + P.dt * speed;
+  const T e0 = -mu * ed[0], e1 = -mu * ed[1], e2 = -ed[2];
+  qc[0] = e0 + s0;
+  qc[1] = e1 + s1;
+  qc[2] = e2 + s2;
   const T pneg = t_max(-phic, T(0));
   pen += pneg * pneg;
+  if (CN_LOSS_START_FACTOR > 0) {
+    // where this contact leaves the polar cone along u = (1 - a) dv (see cube_loss_prologue)
+    const T Aq = e0 * e0 + e1 * e1 - e2 * e2, Bq = T(2) * (s0 * e0 + s1 * e1 - s2 * e2);
+    const T Cq = t_min(s0 * s0 + s1 * s1 - s2 * s2, T(0));
+    const T disc = Bq * Bq - T(4) * Aq * Cq;
+    const T dpos = t_max(disc, T(0));
+    const T den = Bq + dpos * t_rsqrt(t_max(dpos, t_tiny<T>()));
+    const T a_c = (disc >= T(0) && den > T(0)) ? T(-2) * Cq * t_rcp(den) : T(2);
+    a_min = t_min(a_min, a_c);
+  }
 }
 
 // twist of link BI for world twist v7: [w (link body frame) ; v (world, link origin)]
@@ -427,13 +440,13 @@ CN_HD bool elbow_loss_free_flight(const ElbowParams<T>& P, const T* x, const T* 
   ElbowLossCore<T> A;
   elbow_loss_core(P, x, xp, pts != nullptr, E, A);
   bool open = true;
-  T pen = T(0);
+  T pen = T(0), a_unused = T(2);
 #pragma unroll 1
   for (int c = 0; c < EL_NC; ++c) {
     T p[3], rho[3], hcol[3], qc[3];
     elbow_witness(P, A.sel0, A.sel1, pts, c, p);
     elbow_contact_geometry(E, c, p, rho, hcol);
-    elbow_loss_q(P, A, c, rho, hcol, qc, pen);
+    elbow_loss_q(P, A, c, rho, hcol, qc, pen, a_unused);
     open = open && (qc[2] >= T(0)) && (qc[0] * qc[0] + qc[1] * qc[1] <= qc[2] * qc[2]);
   }
   if (!open) return false;
@@ -472,13 +485,13 @@ CN_HD void elbow_loss_prologue_wf(const ElbowParams<T>& P, const T* x, const T* 
 #pragma unroll
   for (int i = 0; i < 3; ++i) { S.mc(i) = E.mc[i]; S.hw(i) = E.hw[i]; S.hv(i) = E.hv[i]; }
   S.mt() = E.mt; S.ht() = E.ht;
-  T pen = T(0);
+  T pen = T(0), a_min = T(2);
 #pragma unroll 1
   for (int c = 0; c < EL_NC; ++c) {
     T p[3], rho[3], hcol[3], qc[3];
     elbow_witness(P, A.sel0, A.sel1, pts, c, p);
     elbow_contact_geometry(E, c, p, rho, hcol);
-    elbow_loss_q(P, A, c, rho, hcol, qc, pen);
+    elbow_loss_q(P, A, c, rho, hcol, qc, pen, a_min);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       S.rho(3 * c + i) = rho[i];
@@ -487,6 +500,7 @@ CN_HD void elbow_loss_prologue_wf(const ElbowParams<T>& P, const T* x, const T* 
     }
   }
   A.konst += pen;
+  A.a_start = CN_LOSS_START_FACTOR > 0 ? t_min(T(CN_LOSS_START_FACTOR) * a_min, T(1)) : T(1);
 }
 
 template <typename T> CN_HD void elbow_rec_contact(const ElbowRec<T>& S, int c, T* rho, T* hcol) {
@@ -751,7 +765,9 @@ CN_HD T elbow_loss_sample_wf(const ElbowParams<T>& P, const SolverCfg<T>& cfg, c
   ElbowSetup<T> E;
   ElbowLossCore<T> A;
   elbow_loss_prologue_wf<T, T>(P, x, xp, pts, S, E, A);
-  T u[7] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
+  T u[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) u[i] = (T(1) - A.a_start) * A.dv[i];
   int it = 0;
   T d[7], d0 = T(0), best = T(-1);
   CubeTrial<T> tr{T(1), T(0), T(1)};
