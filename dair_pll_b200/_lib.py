@@ -73,6 +73,7 @@ EXPORTS = {
     'dpll_comm_device_state': ([_c_void_p], _c_void_p),
     'dpll_comm_error': ([_c_void_p], ctypes.c_int),
     'dpll_comm_allreduce_f64': ([_c_void_p, _c_void_p, _i32, _f64, _c_void_p], ctypes.c_int),
+    'dpll_elbow_step_pts_grad_f64': ([_c_void_p] * 5 + [_f64, _f64, _i64] + [_c_void_p] * 5, ctypes.c_int),
     'dpll_leaf_prepare_f64': ([_c_void_p, _i32, _c_void_p, _c_void_p, _c_void_p, _i32, _c_void_p, _i32] + [_c_void_p] * 4, ctypes.c_int),
     'dpll_leaf_backward_f64': ([_c_void_p, _i32, _c_void_p, _i32, _c_void_p, _c_void_p, _i32, _c_void_p, _i32] + [_c_void_p] * 7,
                                ctypes.c_int),

@@ -40,4 +40,37 @@ CN_HD B elbow_rollout_tangent(const B* inertia, const B* mu, const B* half, cons
   return g;
 }
 
+// One learnable step with caller-supplied witness points (learned geometry): 61 directions
+//   0..19 inertia | 20..21 mu_pair | 22..45 the 8 x 3 witness-point coordinates | 46..60 the 15 coordinates of x.
+// Returns xbar . d x_next / d (direction).  The caller's networks make the points a function of the state and of their
+// weights; a piecewise-linear support function has piecewise-CONSTANT support points, so the chain through the
+// directions vanishes almost everywhere and the points' cotangent goes to the weights alone (ops.ElbowStepPts).
+constexpr int ELBOW_PTS_NTAN = 61;
+constexpr int ELBOW_PTS_NPARAM = 22;
+
+template <typename B>
+CN_HD B elbow_step_pts_tangent(const B* inertia, const B* mu, const B* kin, B dt, B eps, const B* x0, const B* pts,
+                               const B* xbar, int dir) {
+  typedef DualN<B, 1> D;
+  D din[20], dmu[2], dh[6], dkin[12], dp[24];
+  for (int i = 0; i < 20; ++i) { din[i] = D(inertia[i]); if (dir == i) din[i].d[0] = B(1); }
+  for (int i = 0; i < 2; ++i) { dmu[i] = D(mu[i]); if (dir == 20 + i) dmu[i].d[0] = B(1); }
+  for (int i = 0; i < 6; ++i) dh[i] = D(B(0));
+  for (int i = 0; i < 12; ++i) dkin[i] = D(kin[i]);
+  for (int i = 0; i < 24; ++i) { dp[i] = D(pts[i]); if (dir == ELBOW_PTS_NPARAM + i) dp[i].d[0] = B(1); }
+  ElbowParams<D> P;
+  elbow_params_init<D>(P, din, dmu, dh, dkin, D(dt), D(eps));
+  const SolverCfg<B> c0 = default_cfg<B>();
+  SolverCfg<D> cfg;
+  cfg.tol_rel = D(c0.tol_rel); cfg.tol_stall = D(c0.tol_stall); cfg.ls_c = D(c0.ls_c); cfg.max_iter = c0.max_iter;
+  cfg.tol_final = D(0);
+  cfg.polish = true;
+  D x[15], xn[15];
+  for (int i = 0; i < 15; ++i) { x[i] = D(x0[i]); if (dir == ELBOW_PTS_NPARAM + 24 + i) x[i].d[0] = B(1); }
+  elbow_step_sample<D>(P, cfg, x, dp, xn, (D*)nullptr);
+  B g = B(0);
+  for (int i = 0; i < 15; ++i) g += xbar[i] * xn[i].d[0];
+  return g;
+}
+
 }  // namespace cn

@@ -228,20 +228,26 @@ class MultibodyLearnableSystem(System):
             inertia, mu, half, kin = self._elbow_params(x_0.dtype, x_0.device)
             if half is None:
                 # learned geometry: witness points depend on the state, so the time loop stays on the
-                # host and every step is [support networks -> one-step kernel]
+                # host and every step is [support directions -> support networks -> one-step kernel]
                 if torch.is_grad_enabled() and (x_0.requires_grad or
                                                 any(p.requires_grad for p in self.multibody_terms.parameters())):
-                    raise NotImplementedError(
-                        'the rollout with learned (support-function) geometry has no backward: evaluate it under '
-                        'torch.no_grad(), or train the geometry with contactnets_loss')
-                with torch.no_grad():
+                    # differentiable (prediction loss trains the geometry): every step is an autograd node whose backward
+                    # is the 61-direction tangent kernel; the points' cotangents reach the network weights through
+                    # ICNNSupport (support points are piecewise constant in the direction: no chain through the state there)
                     xs = [self._flat(x_0)]
                     for _ in range(steps):
-                        pts = self._elbow_witness_points(xs[-1][:, :8])
-                        one, _ = ops.elbow_rollout(xs[-1], inertia.detach(), mu.detach(), None, kin, float(self.dt), 1,
-                                                   STEP_EPS, pts=pts)
-                        xs.append(one[:, 1])
+                        pts = self._elbow_witness_points(xs[-1][:, :8].detach())
+                        xs.append(ops.ElbowStepPts.apply(xs[-1], inertia, mu, pts, kin, float(self.dt), STEP_EPS))
                     traj = torch.stack(xs, 1)
+                else:
+                    with torch.no_grad():
+                        xs = [self._flat(x_0)]
+                        for _ in range(steps):
+                            pts = self._elbow_witness_points(xs[-1][:, :8])
+                            one, _ = ops.elbow_rollout(xs[-1], inertia.detach(), mu.detach(), None, kin, float(self.dt), 1,
+                                                       STEP_EPS, pts=pts)
+                            xs.append(one[:, 1])
+                        traj = torch.stack(xs, 1)
             elif torch.is_grad_enabled() and any(t.requires_grad for t in (x_0, inertia, mu, half)):
                 traj = ops.ElbowRollout.apply(self._flat(x_0), inertia, mu, half, kin, float(self.dt), steps, STEP_EPS)
             else:

@@ -578,6 +578,40 @@ class ElbowRollout(torch.autograd.Function):
                 g[22:28].reshape(half.shape).to(half.dtype), None, None, None, None)
 
 
+class ElbowStepPts(torch.autograd.Function):
+    """ONE differentiable learnable step of the two-body system with learned geometry: x (B,15), witness points pts
+    (B,8,3) of the support-function networks -> next state (B,15).  Backward = ``dpll_elbow_step_pts_grad_f64``
+    (61 forward-mode directions per sample): cotangents of x, inertia, mu_pair and of the points -- which autograd then
+    chains into the network weights through :class:`deep_support_function.ICNNSupport`."""
+
+    @staticmethod
+    def forward(ctx, x, inertia, mu_pair, pts, kin, dt, eps):
+        traj, _ = elbow_rollout(x, inertia, mu_pair, None, kin, dt, 1, eps, pts=pts)
+        ctx.dt, ctx.eps = dt, eps
+        ctx.save_for_backward(x, inertia, mu_pair, pts, kin)
+        return traj[:, 1]
+
+    @staticmethod
+    def backward(ctx, gnext):
+        x, inertia, mu_pair, pts, kin = ctx.saved_tensors
+        B = x.shape[0]
+        f64 = torch.float64
+        gparams = torch.zeros((B, 22), dtype=f64, device=x.device)
+        gpts = torch.zeros((B, 24), dtype=f64, device=x.device)
+        gx = torch.zeros((B, 15), dtype=f64, device=x.device)
+        if B > 0:
+            a = [t.detach().to(f64).contiguous() for t in (x, inertia, mu_pair, kin, pts)]
+            xbar = gnext.to(f64).contiguous()
+            with torch.cuda.device(x.device):
+                rc = _lib.load().dpll_elbow_step_pts_grad_f64(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(a[4]),
+                                                              ctx.dt, ctx.eps, B, _ptr(xbar), _ptr(gparams), _ptr(gpts),
+                                                              _ptr(gx), _stream())
+            _lib.check(rc, 'dpll_elbow_step_pts_grad')
+        g = gparams.sum(0)
+        return (gx.to(x.dtype), g[0:20].reshape(inertia.shape).to(inertia.dtype),
+                g[20:22].reshape(mu_pair.shape).to(mu_pair.dtype), gpts.reshape(pts.shape).to(pts.dtype), None, None, None)
+
+
 class BodyWitnessPointLoss(torch.autograd.Function):
     """ContactNets loss of a single floating body whose contact set is given by witness points ``pts`` (B,4,3)
     (first ``n_contacts`` rows used) -- Sphere, Polygon, any plane-convex pair: ``dpll_body_loss_pts_f64``.

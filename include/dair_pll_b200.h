@@ -350,6 +350,18 @@ int dpll_elbow_rollout_grad_f64(const double* x0, const double* inertia, const d
                                 double* gparams, double* gx0, void* stream);
 
 /*
+ * Backward of ONE learnable step of the two-body system with caller-supplied witness points pts (B, 8, 3) -- the learned
+ * (support-function) geometry, whose points depend on the state through the caller's networks, so the time loop of that
+ * rollout runs step by step (forward_dynamics multibody_learnable_system.py:199-304 with geometry.py:309-325): given
+ * xbar (B, 15) w.r.t. the next state, gparams (B, 22) = [d/d inertia (20) | d/d mu_pair (2)], gpts (B, 24) and
+ * gx (B, 15) w.r.t. the current state at fixed points.  Forward-mode tangents through the step code, 61 directions per
+ * sample, implicit derivative of the QP by the polishing Newton step.
+ */
+int dpll_elbow_step_pts_grad_f64(const double* x, const double* inertia, const double* mu_pair, const double* kin,
+                                 const double* pts, double dt, double eps, int64_t B, const double* xbar,
+                                 double* gparams, double* gpts, double* gx, void* stream);
+
+/*
  * The same two operations for the elbow (assets/contactnets_elbow.urdf: floating base + one
  * revolute child, two boxes, 2 x 4 contacts): states (B, 15) = [quat | pos | hinge angle | w_body |
  * v_world | hinge rate]; parameters inertia[20] (two bodies' 10-vectors), mu_pair[2] (ground-box1,

@@ -644,3 +644,50 @@ def test_leaf_preparation_kernels_match_the_host_parameter_graph(name, assets_di
         grads.append(_leaf_grads(s))
     for got, ref in zip(*grads):
         assert max_rel_to_scale(got, ref) < 1e-13
+
+
+def test_learned_geometry_rollout_is_differentiable_and_matches_oracle_autograd(assets_dir):
+    """Prediction-loss path with learned (support-function) geometry (multibody_learnable_system.py:293-304 through
+    geometry.py:309-325): a 3-step rollout of the two-body system with two width-256 networks through the module API --
+    trajectory, and the gradients of theta, friction, every network weight and the initial state -- against autograd
+    through the CPU oracle's simulate()."""
+    from oracle import contactnets_oracle as co
+    from oracle.callables import ELBOW_TREE, TreeCallables
+    torch.manual_seed(0)
+    s = MultibodyLearnableSystem({'elbow': os.path.join(assets_dir, 'elbow_mesh.urdf')}, DT).to(DEV)
+    n, steps = 24, 3
+    x0 = synthetic.elbow_states(n, seed=41, device=DEV).requires_grad_()
+    gen = torch.Generator().manual_seed(5)
+    target = torch.randn(n, steps, 15, generator=gen, dtype=torch.float64).to(DEV)
+    traj, _ = s.simulate(x0.unsqueeze(-2), torch.zeros(n, 1, device=DEV), steps)
+    ((traj[:, 1:] - target) ** 2).sum().backward()
+    mt = s.multibody_terms
+    nets = []
+    for gi in range(2):
+        geom = mt.contact_terms.geometries[gi]
+        net = geom.network
+        nets.append(dict(Wd0=net.input_weights[0].detach().cpu().clone().requires_grad_(),
+                         Wd1=net.input_weights[1].detach().cpu().clone().requires_grad_(),
+                         Wh=net.hidden_weights[0].detach().cpu().clone().requires_grad_(),
+                         wout=net.output_weight.detach().cpu().clone().requires_grad_(),
+                         perturbations=geom.perturbations.detach().cpu().clone()))
+    P = co.OracleParams(mt.lagrangian_terms.inertial_parameters.detach().cpu().clone(),
+                        mt.contact_terms.friction_params.detach().cpu().clone(), [], icnn=nets).requires_grad_()
+    x0o = x0.detach().cpu().clone().requires_grad_()
+    tro = co.simulate(TreeCallables(ELBOW_TREE), P, x0o, DT, steps)
+    ((tro[:, 1:] - target.cpu()) ** 2).sum().backward()
+    assert np.abs(traj.detach().cpu().numpy() - tro.detach().numpy()).max() < 1e-8
+    # tolerance: the reference form of the velocity update loses ~cond(Q) eps of the derivatives (DESIGN.md section 2)
+    tol = 1e-7
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), P.inertial_parameters.grad.numpy()) < tol
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), P.friction_params.grad.numpy()) < tol
+    assert max_rel_to_scale(x0.grad.cpu().numpy(), x0o.grad.numpy()) < tol
+    seen = 0
+    for gi in range(2):
+        net = mt.contact_terms.geometries[gi].network
+        for k, p in (('Wd0', net.input_weights[0]), ('Wd1', net.input_weights[1]), ('Wh', net.hidden_weights[0]),
+                     ('wout', net.output_weight)):
+            ref = nets[gi][k].grad.numpy()
+            assert max_rel_to_scale(p.grad.cpu().numpy(), ref) < tol, (gi, k)
+            seen += int(np.abs(ref).max() > 0)
+    assert seen >= 4          # the batch does train the geometry (contacts carry force during the rollout)
