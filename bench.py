@@ -200,7 +200,7 @@ def secondary_configs(device, peak_flops):
         graphed = parallel.GraphedStep(step, device)
         n = xx.shape[0]
         ms = _time_gpu(graphed, device, max(20, int(100.0 / max(ms_eager, 0.05))))
-        flags = ops.LOSS_DYNAMIC if ordered else 0
+        flags = (ops.LOSS_DYNAMIC | ops.LOSS_RACE) if ordered else 0
         it = ops.cube_loss_leaf_dp_raw(xx, xxp, *leaves(xx.dtype), DT, 1e-3, flags=flags, want_iters=True)[4]
         mean_it = it.double().mean().item()
         ms_k = _time_gpu(lambda: ops.cube_loss_leaf_dp_raw(xx, xxp, *leaves(xx.dtype), DT, 1e-3, flags=flags), device,
@@ -672,7 +672,7 @@ def main():
     # ---- kernel-only timing for the roofline (CUDA events around the raw launch) ----------------------------
     lt, ct = system.multibody_terms.lagrangian_terms, system.multibody_terms.contact_terms
     leaves = [t.detach().to(dtype) for t in (lt.inertial_parameters, ct.friction_params, ct.geometries[0].length_params)]
-    flags = ops.LOSS_DYNAMIC if args.order == 'cost' else 0
+    flags = (ops.LOSS_DYNAMIC | ops.LOSS_RACE) if args.order == 'cost' else 0
     iters = ops.cube_loss_leaf_dp_raw(x, xp, *leaves, DT, 1e-3, flags=flags, want_iters=True)[4]
     mean_iters = iters.double().mean().item()
 

@@ -404,7 +404,8 @@ template <typename T> struct CubeLossAux {
   T vp[6];      // v+, state coordinates
   T pos_z;
   T konst;      // 1/2 dv^T M dv + sum max(-phi,0)^2   (:163-170)
-  T u0[6];      // start point of the Newton solve (world twist), see cube_loss_prologue
+  T dvW[6];     // dv as a world twist: the always-feasible end of the start segment (cube_loss_start)
+  T a_min;      // fraction of the segment dv -> 0 at which the first contact leaves its polar cone
   uint32_t sel; // selected corners (sign bits)
 };
 
@@ -466,11 +467,9 @@ CN_HD void cube_loss_prologue(const CubeParams<T>& P, const T* x, const T* xp, c
       a_min = t_min(a_min, a_c);
     }
   }
-  {
-    const T a0 = CN_LOSS_START_FACTOR > 0 ? t_min(T(CN_LOSS_START_FACTOR) * a_min, T(1)) : T(1);
+  A.a_min = a_min;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) A.u0[i] = (T(1) - a0) * dvW[i];
-  }
+  for (int i = 0; i < 6; ++i) A.dvW[i] = dvW[i];
   T Mdv[6];
   cube_mass_mul(P, S, dvW, Mdv);
   T e = T(0);
@@ -480,6 +479,16 @@ CN_HD void cube_loss_prologue(const CubeParams<T>& P, const T* x, const T* xp, c
 }
 
 // vex(X) with <X, S(a)> = a . vex(X);  X row-major 3x3
+// Start point u = (1 - a) dv with a = min(1, factor a_min) (factor <= 0: a = 1, the round-1 start u = 0; factor < 0 is
+// reserved for callers that pass a fixed fraction through cube_loss_start_fraction).
+template <typename T> CN_HD void cube_loss_start_fraction(const CubeLossAux<T>& A, T a, T* u) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) u[i] = (T(1) - a) * A.dvW[i];
+}
+template <typename T> CN_HD void cube_loss_start(const CubeLossAux<T>& A, T factor, T* u) {
+  cube_loss_start_fraction<T>(A, factor > T(0) ? t_min(factor * A.a_min, T(1)) : T(1), u);
+}
+
 template <typename T> CN_HD void vex3(const T* X, T* o) {
   o[0] = X[7] - X[5]; o[1] = X[2] - X[6]; o[2] = X[3] - X[1];
 }
@@ -720,8 +729,7 @@ CN_HD T cube_loss_sample(const CubeParams<T>& P, const SolverCfg<T>& cfg, const 
   CubeLossAux<T> A;
   cube_loss_prologue<T, 4>(P, x, xp, S, A);
   T u[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) u[i] = A.u0[i];
+  cube_loss_start<T>(A, T(CN_LOSS_START_FACTOR), u);
   const int it = cube_solve<T, 4>(P, S, cfg, u);
   if (iters_out) *iters_out = it;
   return cube_loss_epilogue<T, 4>(P, S, A, u, grad, force_out);

@@ -57,6 +57,8 @@ class MultibodyLearnableSystem(System):
         # Extensions of the reference API (all off by default -> the reference's semantics):
         self.data_parallel = None        # parallel.PeerComm: loss.mean()/.sum() and gradients cover all ranks
         self.dynamic_schedule = False    # warps draw sample chunks in batch order (cost-ordered batches)
+        self.race_expensive_head = True  # with dynamic_schedule, small launches: the first B/64 samples of the (cost-ordered)
+                                         # batch are solved from eight start points at once, first to converge wins (cube)
         self.record_newton_iters = False  # BatchLoss.newton_iters: per-sample cost hint for the data set
         self.qp_warm_start = None        # (B, 6) contiguous start points of the next contactnets_loss call's solves
                                          # (cube); with record_qp_solution it is overwritten in place by the optima
@@ -163,7 +165,7 @@ class MultibodyLearnableSystem(System):
             # 466-471, geometry.py:394-397, and its chain rule run on the device)
             leaves = (lt.inertial_parameters.to(x.dtype), ct.friction_params.to(x.dtype),
                       ct.geometries[0].length_params.to(x.dtype))
-            flags = ops.LOSS_DYNAMIC if self.dynamic_schedule else 0
+            flags = (ops.LOSS_DYNAMIC | (ops.LOSS_RACE if self.race_expensive_head else 0)) if self.dynamic_schedule else 0
             warm, self.qp_warm_start = self.qp_warm_start, None          # consumed by this call
             loss, sums, means, iters, usol = ops.CubeContactNetsLossLeaf.apply(
                 self._flat(x), self._flat(x_plus), *leaves, float(self.dt), LOSS_EPS, flags, self.data_parallel,

@@ -129,6 +129,7 @@ class CubeContactNetsLoss(torch.autograd.Function):
 
 
 LOSS_DYNAMIC = 1     # DPLL_LOSS_DYNAMIC (include/dair_pll_b200.h)
+LOSS_RACE = 2        # DPLL_LOSS_RACE: the head of a cost-ordered batch is solved by the racing kernel (small launches)
 
 
 def _rows(t: Tensor, n_x: int):

@@ -691,3 +691,49 @@ def test_learned_geometry_rollout_is_differentiable_and_matches_oracle_autograd(
             assert max_rel_to_scale(p.grad.cpu().numpy(), ref) < tol, (gi, k)
             seen += int(np.abs(ref).max() > 0)
     assert seen >= 4          # the batch does train the geometry (contacts carry force during the rollout)
+
+
+def test_racing_kernel_for_the_expensive_head_gives_the_same_results(assets_dir):
+    """DPLL_LOSS_RACE: the first B/64 samples of a cost-ordered batch are solved from eight start points at once (first to
+    converge wins) on a second stream.  The optimum is unique, so per-sample losses, the summed loss and the leaf
+    gradients must equal the plain dynamic launch's to solver tolerance -- eagerly and replayed from a CUDA graph."""
+    import bench
+    from dair_pll_b200 import parallel
+    system = bench.make_system(torch.device(DEV), torch.float64)
+    x, xp = bench.make_batch(system, 65536, 123, torch.device(DEV), torch.float64)
+    lt, ct = system.multibody_terms.lagrangian_terms, system.multibody_terms.contact_terms
+    leaves = [t.detach() for t in (lt.inertial_parameters, ct.friction_params, ct.geometries[0].length_params)]
+    it = ops.cube_loss_leaf_dp_raw(x, xp, *leaves, DT, 1e-3, want_iters=True)[4]
+    order = torch.argsort(it, descending=True, stable=True)
+    xo, xpo = x.index_select(0, order).contiguous(), xp.index_select(0, order).contiguous()
+    ref = ops.cube_loss_leaf_dp_raw(xo, xpo, *leaves, DT, 1e-3, flags=ops.LOSS_DYNAMIC, want_iters=True)
+    got = ops.cube_loss_leaf_dp_raw(xo, xpo, *leaves, DT, 1e-3, flags=ops.LOSS_DYNAMIC | ops.LOSS_RACE, want_iters=True)
+    torch.cuda.synchronize()
+    head = 65536 // 64
+    scale = ref[0].abs().max().item()
+    assert (got[0] - ref[0]).abs().max().item() < 1e-11 * scale                  # per-sample losses
+    assert torch.equal(got[0][head:], ref[0][head:])                             # the wavefront part is the same computation
+    assert max_rel_to_scale(got[1].cpu().numpy(), ref[1].cpu().numpy()) < 1e-10  # [leaf gradients | loss sum | count]
+    assert int(got[4][:head].max()) < int(ref[4][:head].max())                   # the worst chain did get shorter
+    # public API + graph capture (fork / join of the second stream inside the capture)
+    system.dynamic_schedule = True
+    params = list(system.parameters())
+
+    def step():
+        for p in params:
+            p.grad = None
+        m = system.contactnets_loss(xo, None, xpo).mean()
+        m.backward()
+        return m.detach()
+    eager = step().clone()
+    g_eager = [p.grad.clone() for p in params]
+    graphed = parallel.GraphedStep(step, torch.device(DEV))
+    for _ in range(3):
+        out = graphed()
+    torch.cuda.synchronize()
+    assert abs(out.item() - eager.item()) < 1e-12 * abs(eager.item())
+    for p, g in zip(params, g_eager):
+        assert max_rel_to_scale(p.grad.cpu().numpy(), g.cpu().numpy()) < 1e-10
+    system.race_expensive_head = False
+    plain = step()
+    assert abs(plain.item() - eager.item()) < 1e-11 * abs(eager.item())

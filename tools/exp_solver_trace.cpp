@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
     if (cube_trivially_solved<double, 4>(S)) { hist[0]++; continue; }
     const bool zero = getenv("ZERO_START") != nullptr;      // the round-1 start point u = 0, for comparison
     double u[6], d[6], d0 = 0, best = -1; CubeTrial<double> tr{1, 0, 1}; int it = 0;
-    for (int i = 0; i < 6; ++i) u[i] = zero ? 0.0 : A.u0[i];
+    cube_loss_start<double>(A, zero ? 0.0 : (double)CN_LOSS_START_FACTOR, u);
     long v0 = g_visits;
     bool show = false;
     // dry run to get count
