@@ -6,8 +6,6 @@
 // sample.  Parameter gradients are accumulated per thread across a grid-stride loop and
 // reduced warp -> block -> grid in a fixed order (deterministic).
 #include <cuda_runtime.h>
-#include <cstdlib>
-#include <mutex>
 
 #include "../../include/dair_pll_b200.h"
 #include "cn_cube.cuh"
@@ -120,6 +118,109 @@ cube_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* 
 }
 
 // ---------------------------------------------------------------------------
+// Racing blocks for the EXPENSIVE head of a cost-ordered batch (DPLL_LOSS_RACE).
+//
+// A launch lasts at least as long as its longest Newton chain (~45 dependent visits of ~2.5 us on the bench batch), which
+// is all that is left of a small launch -- the strong-scaling shard of a data-parallel step.  How long a chain gets depends
+// on where it starts: over eight different start points on the feasible segment (cube_loss_start) the SHORTEST chain of the
+// worst sample is 26 visits instead of 47 (over the best four: 28), and only 92 of 39,016 solves still need 20 or more.
+// The optimum is unique, so any of them gives the same answer.  Here every sample of the head gets four (or eight) lanes,
+// one start point each; after every visit the group votes, the first lane to converge hands its solution to the group and
+// the group stops.  One lane per group then runs the ordinary epilogue.  The kernel runs beside the wavefront kernel (which
+// takes the rest of the batch) on a second stream; its partial sums go to rows of their own.  Measured (kernel time of a
+// shard of the cost-ordered 1M bench batch): 65,536 pairs 125 -> 83 us, 131,072 pairs 129 -> 106 us, 262,144 pairs 171 ->
+// 151 us; four lanes beat eight (the racing warps share the SM sub-partitions with the wavefront warps, and a visit of a
+// warp that shares its sub-partition takes 2.65 us instead of 2.0).
+// ---------------------------------------------------------------------------
+constexpr int kRaceThreads = 128;
+constexpr int kRaceLanes = 4;                          // start points per sample
+
+template <typename T, typename IO, int kRaceLanes>
+__device__ __forceinline__ void
+cube_loss_race_block(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
+                     const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half, T dt, T eps,
+                     int64_t H, IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
+                     T* __restrict__ partials, int want_grad, int64_t ldx, int64_t ldxp, IO* __restrict__ u_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int group = lane / kRaceLanes, v = lane % kRaceLanes;
+  const int64_t b = ((int64_t)blockIdx.x * (kRaceThreads / 32) + warp) * (32 / kRaceLanes) + group;
+  const bool valid = b < H;
+  cn::CubeParams<T> P;
+  load_cube_params<T, IO>(P, inertia, mu, half, dt, eps);
+  const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
+  T store[cn::CUBE_PROB_FIELDS];
+  const cn::CubeProb<T> S{store, 1};
+  cn::CubeLossAux<T> A;
+  T u[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, d[6], d0 = T(0), best = T(-1);
+  cn::CubeTrial<T> tr{T(1), T(0), T(1)};
+  int it = 0;
+  bool active = false;
+  if (valid) {
+    T xs[13], xps[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * ldx + i]); xps[i] = T(xp[b * ldxp + i]); }
+    cn::cube_loss_prologue<T, 4>(P, xs, xps, S, A);
+    if (!cn::cube_trivially_solved<T, 4>(S)) {
+      active = true;
+      // eight starts on the segment u = (1 - a) dv: multiples of the fraction at which the first contact activates
+      // (7 = the wavefront kernel's choice), the round-1 start u = 0, and a fixed fraction
+      const T factor = v == 0 ? T(CN_LOSS_START_FACTOR > 0 ? CN_LOSS_START_FACTOR : 7.0)
+                     : v == 1 ? T(2) : v == 2 ? T(60) : v == 4 ? T(4) : v == 5 ? T(25) : v == 6 ? T(12) : T(0);
+      if (v == 3) cn::cube_loss_start_fraction<T>(A, T(0.3), u);          // (lanes 0-3 are the best set of four)
+      else cn::cube_loss_start<T>(A, factor, u);
+    }
+  }
+  while (__any_sync(0xffffffffu, active)) {
+    int st = cn::NEWTON_CONTINUE;
+    if (active) st = cn::cube_newton_visit<T, 4>(P, S, cfg, u, d, d0, best, tr, it);
+    const unsigned fin = __ballot_sync(0xffffffffu, active && st == cn::NEWTON_DONE);
+    const unsigned gfin = (fin >> (group * kRaceLanes)) & ((1u << kRaceLanes) - 1u);
+    const int src = gfin ? group * kRaceLanes + (__ffs(gfin) - 1) : lane;      // the group's first finisher, else myself
+#pragma unroll
+    for (int i = 0; i < 6; ++i) u[i] = __shfl_sync(0xffffffffu, u[i], src);
+    it = __shfl_sync(0xffffffffu, it, src);
+    if (gfin) active = false;
+  }
+  T acc[kNAcc];
+#pragma unroll
+  for (int i = 0; i < kNAcc; ++i) acc[i] = T(0);
+  if (valid && v == 0) {
+    T gs[DPLL_CUBE_NPARAM], fo[12];
+#pragma unroll
+    for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
+    const T l = cn::cube_loss_epilogue<T, 4>(P, S, A, u, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr);
+    if (force) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(fo[i]);
+    }
+    const T w = weight ? T(weight[b]) : T(1);
+#pragma unroll
+    for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] = w * gs[i];
+    if (loss) loss[b] = IO(l);
+    acc[14] = l;
+    if (iters) iters[b] = it & 0xff;
+    if (u_out) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) u_out[b * 6 + i] = IO(u[i]);
+    }
+  }
+  if (!partials) return;
+  __shared__ T red[kRaceThreads / 32][kNAcc];
+#pragma unroll
+  for (int i = 0; i < kNAcc; ++i) {
+    const T sum = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = sum;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNAcc) {
+    T sum = T(0);
+#pragma unroll
+    for (int w = 0; w < kRaceThreads / 32; ++w) sum += red[w][threadIdx.x];
+    partials[(int64_t)blockIdx.x * kNAcc + threadIdx.x] = sum;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Wavefront variant of the loss kernel.
 //
 // A solve needs 0 .. ~45 Newton visits depending on the sample (free-flight samples need none), so
@@ -164,14 +265,14 @@ template <typename T> struct WfWarpPool {
   int32_t q_in[kWfSlots];       // offsets of triaged samples that need the solver, waiting for a slot
 };
 
-template <typename T, typename IO, int UNR>
+template <typename T, typename IO, int UNR, bool RACE = false>
 __global__ void __launch_bounds__(kWfWarps * 32)
 cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
                     const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half, T dt,
                     T eps, int64_t B, IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
                     T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag,
                     unsigned long long* __restrict__ dyn_counter, int64_t ldx, int64_t ldxp,
-                    const IO* __restrict__ u_init, IO* __restrict__ u_out) {
+                    const IO* __restrict__ u_init, IO* __restrict__ u_out, int race_blocks, int64_t head) {
   // u_init / u_out (nullable, (B, 6)): start point of every sample's Newton solve and its optimum (world-frame
   // twist).  A training loop revisits the same pairs with slowly moving parameters: started from the previous
   // epoch's optimum the solve takes a few visits instead of ~11 (the optimum is unique, so only the visit count
@@ -183,6 +284,22 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
   // the second block of every SM consumes the batch from its cheap end, so that no two warps of long chains share
   // an SM sub-partition -- 0.427 vs 0.398 ms at 1,048,576 pairs, 0.143 vs 0.129 ms at 131,072.)
   if (skip_flag && *skip_flag) return;
+  // DPLL_LOSS_RACE: blocks [0, race_blocks) race the first `head` samples (the expensive head of a cost-ordered batch),
+  // the others run the wavefront scheduler over the rest (a separate instantiation: the racing code costs
+  // registers -- 254 against 230 -- and instruction-cache space that launches without a raced head should not pay)
+  if (RACE && (int)blockIdx.x < race_blocks) {
+    cube_loss_race_block<T, IO, kRaceLanes>(x, xp, weight, inertia, mu, half, dt, eps, head, loss, force, iters, partials,
+                                            want_grad, ldx, ldxp, u_out);
+    return;
+  }
+  x += head * ldx; xp += head * ldxp; B -= head;
+  if (weight) weight += head;
+  if (loss) loss += head;
+  if (force) force += head * 12;
+  if (iters) iters += head;
+  if (u_init) u_init += head * 6;
+  if (u_out) u_out += head * 6;
+  const int wf_block = (int)blockIdx.x - race_blocks, wf_blocks = (int)gridDim.x - race_blocks;
   extern __shared__ __align__(16) unsigned char wf_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WfWarpPool<T>* pool = reinterpret_cast<WfWarpPool<T>*>(wf_smem) + warp;
@@ -196,7 +313,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
   for (int i = 0; i < kNAcc; ++i) acc[i] = T(0);
 
   // static contiguous sample range of this warp
-  const int64_t gw = (int64_t)blockIdx.x * kWfWarps + warp, W = (int64_t)gridDim.x * kWfWarps;
+  const int64_t gw = (int64_t)wf_block * kWfWarps + warp, W = (int64_t)wf_blocks * kWfWarps;
   const int64_t base = B / W, rem = B % W;
   const int64_t lo = dyn_counter ? 0 : gw * base + (gw < rem ? gw : rem);
   const int64_t hi = dyn_counter ? B : lo + base + (gw < rem ? 1 : 0);
@@ -399,110 +516,6 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
 #pragma unroll
     for (int w = 0; w < kWfWarps; ++w) s += red[w][threadIdx.x];
     partials[(int64_t)blockIdx.x * kNAcc + threadIdx.x] = s;
-  }
-}
-
-// ---------------------------------------------------------------------------
-// Racing kernel for the EXPENSIVE head of a cost-ordered batch (DPLL_LOSS_RACE).
-//
-// A launch lasts at least as long as its longest Newton chain (~45 dependent visits of ~2.5 us on the bench batch), which
-// is all that is left of a small launch -- the strong-scaling shard of a data-parallel step.  How long a chain gets depends
-// on where it starts: over eight different start points on the feasible segment (cube_loss_start) the SHORTEST chain of the
-// worst sample is 26 visits instead of 47 (over the best four: 28), and only 92 of 39,016 solves still need 20 or more.
-// The optimum is unique, so any of them gives the same answer.  Here every sample of the head gets four (or eight) lanes,
-// one start point each; after every visit the group votes, the first lane to converge hands its solution to the group and
-// the group stops.  One lane per group then runs the ordinary epilogue.  The kernel runs beside the wavefront kernel (which
-// takes the rest of the batch) on a second stream; its partial sums go to rows of their own.  Measured (kernel time of a
-// shard of the cost-ordered 1M bench batch): 65,536 pairs 125 -> 83 us, 131,072 pairs 129 -> 106 us, 262,144 pairs 171 ->
-// 151 us; four lanes beat eight (the racing warps share the SM sub-partitions with the wavefront warps, and a visit of a
-// warp that shares its sub-partition takes 2.65 us instead of 2.0).
-// ---------------------------------------------------------------------------
-constexpr int kRaceThreads = 128;
-
-template <typename T, typename IO, int kRaceLanes>    // kRaceLanes = start points per sample (4 or 8)
-__global__ void __launch_bounds__(kRaceThreads)
-cube_loss_race_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
-                      const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half, T dt, T eps,
-                      int64_t H, IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
-                      T* __restrict__ partials, int want_grad, const int32_t* __restrict__ skip_flag, int64_t ldx,
-                      int64_t ldxp, IO* __restrict__ u_out) {
-  if (skip_flag && *skip_flag) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int group = lane / kRaceLanes, v = lane % kRaceLanes;
-  const int64_t b = ((int64_t)blockIdx.x * (kRaceThreads / 32) + warp) * (32 / kRaceLanes) + group;
-  const bool valid = b < H;
-  cn::CubeParams<T> P;
-  load_cube_params<T, IO>(P, inertia, mu, half, dt, eps);
-  const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
-  T store[cn::CUBE_PROB_FIELDS];
-  const cn::CubeProb<T> S{store, 1};
-  cn::CubeLossAux<T> A;
-  T u[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, d[6], d0 = T(0), best = T(-1);
-  cn::CubeTrial<T> tr{T(1), T(0), T(1)};
-  int it = 0;
-  bool active = false;
-  if (valid) {
-    T xs[13], xps[13];
-#pragma unroll
-    for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * ldx + i]); xps[i] = T(xp[b * ldxp + i]); }
-    cn::cube_loss_prologue<T, 4>(P, xs, xps, S, A);
-    if (!cn::cube_trivially_solved<T, 4>(S)) {
-      active = true;
-      // eight starts on the segment u = (1 - a) dv: multiples of the fraction at which the first contact activates
-      // (7 = the wavefront kernel's choice), the round-1 start u = 0, and a fixed fraction
-      const T factor = v == 0 ? T(CN_LOSS_START_FACTOR > 0 ? CN_LOSS_START_FACTOR : 7.0)
-                     : v == 1 ? T(2) : v == 2 ? T(60) : v == 4 ? T(4) : v == 5 ? T(25) : v == 6 ? T(12) : T(0);
-      if (v == 3) cn::cube_loss_start_fraction<T>(A, T(0.3), u);          // (lanes 0-3 are the best set of four)
-      else cn::cube_loss_start<T>(A, factor, u);
-    }
-  }
-  while (__any_sync(0xffffffffu, active)) {
-    int st = cn::NEWTON_CONTINUE;
-    if (active) st = cn::cube_newton_visit<T, 4>(P, S, cfg, u, d, d0, best, tr, it);
-    const unsigned fin = __ballot_sync(0xffffffffu, active && st == cn::NEWTON_DONE);
-    const unsigned gfin = (fin >> (group * kRaceLanes)) & ((1u << kRaceLanes) - 1u);
-    const int src = gfin ? group * kRaceLanes + (__ffs(gfin) - 1) : lane;      // the group's first finisher, else myself
-#pragma unroll
-    for (int i = 0; i < 6; ++i) u[i] = __shfl_sync(0xffffffffu, u[i], src);
-    it = __shfl_sync(0xffffffffu, it, src);
-    if (gfin) active = false;
-  }
-  T acc[kNAcc];
-#pragma unroll
-  for (int i = 0; i < kNAcc; ++i) acc[i] = T(0);
-  if (valid && v == 0) {
-    T gs[DPLL_CUBE_NPARAM], fo[12];
-#pragma unroll
-    for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
-    const T l = cn::cube_loss_epilogue<T, 4>(P, S, A, u, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr);
-    if (force) {
-#pragma unroll
-      for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(fo[i]);
-    }
-    const T w = weight ? T(weight[b]) : T(1);
-#pragma unroll
-    for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] = w * gs[i];
-    if (loss) loss[b] = IO(l);
-    acc[14] = l;
-    if (iters) iters[b] = it & 0xff;
-    if (u_out) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) u_out[b * 6 + i] = IO(u[i]);
-    }
-  }
-  if (!partials) return;
-  __shared__ T red[kRaceThreads / 32][kNAcc];
-#pragma unroll
-  for (int i = 0; i < kNAcc; ++i) {
-    const T sum = warp_sum(acc[i]);
-    if (lane == 0) red[warp][i] = sum;
-  }
-  __syncthreads();
-  if (threadIdx.x < kNAcc) {
-    T sum = T(0);
-#pragma unroll
-    for (int w = 0; w < kRaceThreads / 32; ++w) sum += red[w][threadIdx.x];
-    partials[(int64_t)blockIdx.x * kNAcc + threadIdx.x] = sum;
   }
 }
 
@@ -1049,27 +1062,8 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int64_t iters) {
   out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-// second stream + fork / join events of the racing kernel, one set per device (created on first use, kept for the
-// process: creating them is not a stream operation, so it is allowed while another stream is being captured)
 constexpr int64_t kRaceMaxBatch = 300000;     // larger launches are bound by throughput, not by their longest chain
 constexpr int64_t kRaceMaxHead = 2048;
-struct RaceStreams { cudaStream_t side; cudaEvent_t fork, join; bool ok; };
-RaceStreams* race_streams(int device) {
-  static RaceStreams table[64] = {};
-  static std::mutex mu;
-  if (device < 0 || device >= 64) return nullptr;
-  std::lock_guard<std::mutex> lock(mu);
-  RaceStreams& r = table[device];
-  if (!r.ok) {
-    int lo_pri = 0, hi_pri = 0;
-    cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);       // the racing blocks should be placed first
-    if (cudaStreamCreateWithPriority(&r.side, cudaStreamNonBlocking, hi_pri) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&r.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    r.ok = true;
-  }
-  return &r;
-}
 
 template <typename T, typename IO>
 int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, const IO* inertia, const IO* mu,
@@ -1103,6 +1097,8 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
     cudaError_t ea = cudaFuncSetAttribute(cube_loss_wf_kernel<T, IO, kWfUnr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ea == cudaSuccess)
       ea = cudaFuncSetAttribute(cube_loss_wf_kernel<T, IO, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ea == cudaSuccess)
+      ea = cudaFuncSetAttribute(cube_loss_wf_kernel<T, IO, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ea != cudaSuccess) return (int)ea;
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_wf_kernel<T, IO, kWfUnr>, kWfWarps * 32, smem);
@@ -1125,66 +1121,32 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
     // instance with the per-contact loop of the Newton visit unrolled overlaps the four contacts (measured -8% at
     // 65,536 pairs, -5% at 262,144).  Larger batches keep every warp's pool full and run the rolled instance,
     // which is smaller in the instruction cache (the unrolled one is +5% at 1M pairs, +15% at 4M).
-    // DPLL_LOSS_RACE: the head of a cost-ordered batch goes to the racing kernel on a second stream (fork / join by events:
-    // also valid inside a stream capture), the wavefront kernel takes the rest.  Only for launches that leave room on the
-    // machine -- small shards, which are the ones bounded by their longest chain -- and only for cold solves.
+    // DPLL_LOSS_RACE: the head of a cost-ordered batch goes to racing blocks at the front of the same grid, the wavefront
+    // blocks take the rest.  Only for launches bounded by their longest chain (small shards), and only for cold solves.
     int64_t head = 0;
-    int race_lanes = 8;
-    RaceStreams* rs = nullptr;
-    static const int64_t env_maxb = getenv("DPLL_RACE_MAXB") ? atoll(getenv("DPLL_RACE_MAXB")) : kRaceMaxBatch;
-    if ((flags & DPLL_LOSS_RACE) && variant == 2 && !u_init && B >= 4096 && B <= env_maxb) {
-      static const int env_div = getenv("DPLL_RACE_DIV") ? atoi(getenv("DPLL_RACE_DIV")) : 64;        // tuning knobs
-      static const int env_lanes = getenv("DPLL_RACE_LANES") ? atoi(getenv("DPLL_RACE_LANES")) : 4;
-      static const int env_max = getenv("DPLL_RACE_MAX") ? atoi(getenv("DPLL_RACE_MAX")) : (int)kRaceMaxHead;
-      race_lanes = env_lanes == 4 ? 4 : 8;
-      head = B / (env_div > 0 ? env_div : 64);
-      if (head > env_max) head = env_max;
-      head -= head % (kRaceThreads / race_lanes);
-      rs = race_streams(di.device);
-      if (!rs) head = 0;
-    }
-    if (head > 0) {
-      const int kRacePerBlock = kRaceThreads / race_lanes;
-      const int race_blocks = (int)(head / kRacePerBlock);
-      // an SM holds two wavefront blocks, or one and a racing block: leave the racing blocks their share
+    int race_blocks = 0;
+    const bool small = B <= cap * kWfWarps * 320;
+    if ((flags & DPLL_LOSS_RACE) && variant == 2 && small && !u_init && B >= 4096 && B <= kRaceMaxBatch) {
+      head = B / 64;
+      if (head > kRaceMaxHead) head = kRaceMaxHead;
+      head -= head % (kRaceThreads / kRaceLanes);
+      race_blocks = (int)(head / (kRaceThreads / kRaceLanes));
+      // an SM holds two blocks: leave the racing blocks their share of the resident set
       if (blocks > cap - race_blocks) blocks = (int)(cap - race_blocks > 1 ? cap - race_blocks : 1);
-      cudaError_t er = cudaEventRecord(rs->fork, st);
-      if (er == cudaSuccess) er = cudaStreamWaitEvent(rs->side, rs->fork, 0);
-      if (er != cudaSuccess) return (int)er;
-      if (race_lanes == 8)
-        cube_loss_race_kernel<T, IO, 8><<<race_blocks, kRaceThreads, 0, rs->side>>>(
-            x, xp, weight, inertia, mu, half, dt, eps, head, loss, force, iters,
-            partials ? partials + (size_t)blocks * kNAcc : nullptr, (grad || sums || means) ? 1 : 0, skip_flag, ldx, ldxp, u_out);
-      else
-        cube_loss_race_kernel<T, IO, 4><<<race_blocks, kRaceThreads, 0, rs->side>>>(
-            x, xp, weight, inertia, mu, half, dt, eps, head, loss, force, iters,
-            partials ? partials + (size_t)blocks * kNAcc : nullptr, (grad || sums || means) ? 1 : 0, skip_flag, ldx, ldxp, u_out);
-      er = cudaGetLastError();
-      if (er == cudaSuccess) er = cudaEventRecord(rs->join, rs->side);
-      if (er != cudaSuccess) return (int)er;
-      race_rows = race_blocks;
     }
-    const IO* xm = x + head * ldx;
-    const IO* xpm = xp + head * ldxp;
-    const IO* wm = weight ? weight + head : nullptr;
-    IO* lossm = loss ? loss + head : nullptr;
-    IO* forcem = force ? force + head * 12 : nullptr;
-    int32_t* itersm = iters ? iters + head : nullptr;
-    const IO* uim = u_init ? u_init + head * 6 : nullptr;
-    IO* uom = u_out ? u_out + head * 6 : nullptr;
-    const int64_t Bm = B - head;
-    if (B <= cap * kWfWarps * 320)
-      cube_loss_wf_kernel<T, IO, 4><<<blocks, kWfWarps * 32, smem, st>>>(xm, xpm, wm, inertia, mu, half, dt, eps, Bm, lossm,
-                                                                    forcem, itersm, partials, (grad || sums || means) ? 1 : 0, skip_flag, dyn, ldx, ldxp, uim, uom);
+    if (race_blocks > 0)
+      cube_loss_wf_kernel<T, IO, 4, true><<<race_blocks + blocks, kWfWarps * 32, smem, st>>>(
+          x, xp, weight, inertia, mu, half, dt, eps, B, loss, force, iters, partials, (grad || sums || means) ? 1 : 0,
+          skip_flag, dyn, ldx, ldxp, u_init, u_out, race_blocks, head);
+    else if (small)
+      cube_loss_wf_kernel<T, IO, 4><<<blocks, kWfWarps * 32, smem, st>>>(
+          x, xp, weight, inertia, mu, half, dt, eps, B, loss, force, iters, partials, (grad || sums || means) ? 1 : 0,
+          skip_flag, dyn, ldx, ldxp, u_init, u_out, 0, 0);
     else
-      cube_loss_wf_kernel<T, IO, kWfUnr><<<blocks, kWfWarps * 32, smem, st>>>(xm, xpm, wm, inertia, mu, half, dt, eps, Bm,
-                                                                         lossm, forcem, itersm, partials,
-                                                                         (grad || sums || means) ? 1 : 0, skip_flag, dyn, ldx,
-                                                                         ldxp, uim, uom);
-    if (head > 0) {
-      cudaError_t ej = cudaStreamWaitEvent(st, rs->join, 0);
-      if (ej != cudaSuccess) return (int)ej;
-    }
+      cube_loss_wf_kernel<T, IO, kWfUnr><<<blocks, kWfWarps * 32, smem, st>>>(
+          x, xp, weight, inertia, mu, half, dt, eps, B, loss, force, iters, partials, (grad || sums || means) ? 1 : 0,
+          skip_flag, dyn, ldx, ldxp, u_init, u_out, 0, 0);
+    race_rows = race_blocks;
   } else {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cube_loss_kernel<T, IO>, kLossThreads, 0);
