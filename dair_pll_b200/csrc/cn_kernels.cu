@@ -118,107 +118,16 @@ cube_loss_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* 
 }
 
 // ---------------------------------------------------------------------------
-// Racing blocks for the EXPENSIVE head of a cost-ordered batch (DPLL_LOSS_RACE).
+// Racing warps for the EXPENSIVE head of a cost-ordered batch (DPLL_LOSS_RACE); see cube_loss_wf_kernel.
 //
 // A launch lasts at least as long as its longest Newton chain (~45 dependent visits of ~2.5 us on the bench batch), which
 // is all that is left of a small launch -- the strong-scaling shard of a data-parallel step.  How long a chain gets depends
 // on where it starts: over eight different start points on the feasible segment (cube_loss_start) the SHORTEST chain of the
 // worst sample is 26 visits instead of 47 (over the best four: 28), and only 92 of 39,016 solves still need 20 or more.
-// The optimum is unique, so any of them gives the same answer.  Here every sample of the head gets four (or eight) lanes,
-// one start point each; after every visit the group votes, the first lane to converge hands its solution to the group and
-// the group stops.  One lane per group then runs the ordinary epilogue.  The kernel runs beside the wavefront kernel (which
-// takes the rest of the batch) on a second stream; its partial sums go to rows of their own.  Measured (kernel time of a
-// shard of the cost-ordered 1M bench batch): 65,536 pairs 125 -> 83 us, 131,072 pairs 129 -> 106 us, 262,144 pairs 171 ->
-// 151 us; four lanes beat eight (the racing warps share the SM sub-partitions with the wavefront warps, and a visit of a
-// warp that shares its sub-partition takes 2.65 us instead of 2.0).
+// The optimum is unique, so any of them gives the same answer.
 // ---------------------------------------------------------------------------
-constexpr int kRaceThreads = 128;
-constexpr int kRaceLanes = 4;                          // start points per sample
-
-template <typename T, typename IO, int kRaceLanes>
-__device__ __forceinline__ void
-cube_loss_race_block(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
-                     const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half, T dt, T eps,
-                     int64_t H, IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
-                     T* __restrict__ partials, int want_grad, int64_t ldx, int64_t ldxp, IO* __restrict__ u_out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int group = lane / kRaceLanes, v = lane % kRaceLanes;
-  const int64_t b = ((int64_t)blockIdx.x * (kRaceThreads / 32) + warp) * (32 / kRaceLanes) + group;
-  const bool valid = b < H;
-  cn::CubeParams<T> P;
-  load_cube_params<T, IO>(P, inertia, mu, half, dt, eps);
-  const cn::SolverCfg<T> cfg = cn::default_cfg<T>();
-  T store[cn::CUBE_PROB_FIELDS];
-  const cn::CubeProb<T> S{store, 1};
-  cn::CubeLossAux<T> A;
-  T u[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, d[6], d0 = T(0), best = T(-1);
-  cn::CubeTrial<T> tr{T(1), T(0), T(1)};
-  int it = 0;
-  bool active = false;
-  if (valid) {
-    T xs[13], xps[13];
-#pragma unroll
-    for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * ldx + i]); xps[i] = T(xp[b * ldxp + i]); }
-    cn::cube_loss_prologue<T, 4>(P, xs, xps, S, A);
-    if (!cn::cube_trivially_solved<T, 4>(S)) {
-      active = true;
-      // eight starts on the segment u = (1 - a) dv: multiples of the fraction at which the first contact activates
-      // (7 = the wavefront kernel's choice), the round-1 start u = 0, and a fixed fraction
-      const T factor = v == 0 ? T(CN_LOSS_START_FACTOR > 0 ? CN_LOSS_START_FACTOR : 7.0)
-                     : v == 1 ? T(2) : v == 2 ? T(60) : v == 4 ? T(4) : v == 5 ? T(25) : v == 6 ? T(12) : T(0);
-      if (v == 3) cn::cube_loss_start_fraction<T>(A, T(0.3), u);          // (lanes 0-3 are the best set of four)
-      else cn::cube_loss_start<T>(A, factor, u);
-    }
-  }
-  while (__any_sync(0xffffffffu, active)) {
-    int st = cn::NEWTON_CONTINUE;
-    if (active) st = cn::cube_newton_visit<T, 4>(P, S, cfg, u, d, d0, best, tr, it);
-    const unsigned fin = __ballot_sync(0xffffffffu, active && st == cn::NEWTON_DONE);
-    const unsigned gfin = (fin >> (group * kRaceLanes)) & ((1u << kRaceLanes) - 1u);
-    const int src = gfin ? group * kRaceLanes + (__ffs(gfin) - 1) : lane;      // the group's first finisher, else myself
-#pragma unroll
-    for (int i = 0; i < 6; ++i) u[i] = __shfl_sync(0xffffffffu, u[i], src);
-    it = __shfl_sync(0xffffffffu, it, src);
-    if (gfin) active = false;
-  }
-  T acc[kNAcc];
-#pragma unroll
-  for (int i = 0; i < kNAcc; ++i) acc[i] = T(0);
-  if (valid && v == 0) {
-    T gs[DPLL_CUBE_NPARAM], fo[12];
-#pragma unroll
-    for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) gs[i] = T(0);
-    const T l = cn::cube_loss_epilogue<T, 4>(P, S, A, u, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr);
-    if (force) {
-#pragma unroll
-      for (int i = 0; i < 12; ++i) force[b * 12 + i] = IO(fo[i]);
-    }
-    const T w = weight ? T(weight[b]) : T(1);
-#pragma unroll
-    for (int i = 0; i < DPLL_CUBE_NPARAM; ++i) acc[i] = w * gs[i];
-    if (loss) loss[b] = IO(l);
-    acc[14] = l;
-    if (iters) iters[b] = it & 0xff;
-    if (u_out) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) u_out[b * 6 + i] = IO(u[i]);
-    }
-  }
-  if (!partials) return;
-  __shared__ T red[kRaceThreads / 32][kNAcc];
-#pragma unroll
-  for (int i = 0; i < kNAcc; ++i) {
-    const T sum = warp_sum(acc[i]);
-    if (lane == 0) red[warp][i] = sum;
-  }
-  __syncthreads();
-  if (threadIdx.x < kNAcc) {
-    T sum = T(0);
-#pragma unroll
-    for (int w = 0; w < kRaceThreads / 32; ++w) sum += red[w][threadIdx.x];
-    partials[(int64_t)blockIdx.x * kNAcc + threadIdx.x] = sum;
-  }
-}
+constexpr int kRaceLanes = 4;                          // start points per sample: factors 7, 2, 60 of a_min and the fraction 0.3
+constexpr int kRaceSamples = 32 / kRaceLanes;          // samples per racing warp
 
 // ---------------------------------------------------------------------------
 // Wavefront variant of the loss kernel.
@@ -284,21 +193,23 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
   // the second block of every SM consumes the batch from its cheap end, so that no two warps of long chains share
   // an SM sub-partition -- 0.427 vs 0.398 ms at 1,048,576 pairs, 0.143 vs 0.129 ms at 131,072.)
   if (skip_flag && *skip_flag) return;
-  // DPLL_LOSS_RACE: blocks [0, race_blocks) race the first `head` samples (the expensive head of a cost-ordered batch),
-  // the others run the wavefront scheduler over the rest (a separate instantiation: the racing code costs
-  // registers -- 254 against 230 -- and instruction-cache space that launches without a raced head should not pay)
-  if (RACE && (int)blockIdx.x < race_blocks) {
-    cube_loss_race_block<T, IO, kRaceLanes>(x, xp, weight, inertia, mu, half, dt, eps, head, loss, force, iters, partials,
-                                            want_grad, ldx, ldxp, u_out);
-    return;
+  // DPLL_LOSS_RACE (the RACE instantiation): the warps of blocks [0, race_blocks) are RACING warps for the first `head`
+  // samples (the expensive head of a cost-ordered batch); the other blocks run the wavefront scheduler over the rest.  A
+  // racing warp takes eight samples and gives each four slots with different start points; it then runs through the very
+  // same phases -- PE pass 1 builds and parks the problems, N visits all slots, after every visit the slots of one sample
+  // vote: the first to converge wins, its siblings are dropped, PE pass 0 finalises the winner.  The same code instances as
+  // the wavefront warps, so the two kinds of warps share the instruction cache (a first version with a per-thread racing
+  // body in the same launch spent 21% of its stall samples waiting for instructions).
+  const bool race_warp = RACE && (int)blockIdx.x < race_blocks;
+  if (!race_warp) {
+    x += head * ldx; xp += head * ldxp; B -= head;
+    if (weight) weight += head;
+    if (loss) loss += head;
+    if (force) force += head * 12;
+    if (iters) iters += head;
+    if (u_init) u_init += head * 6;
+    if (u_out) u_out += head * 6;
   }
-  x += head * ldx; xp += head * ldxp; B -= head;
-  if (weight) weight += head;
-  if (loss) loss += head;
-  if (force) force += head * 12;
-  if (iters) iters += head;
-  if (u_init) u_init += head * 6;
-  if (u_out) u_out += head * 6;
   const int wf_block = (int)blockIdx.x - race_blocks, wf_blocks = (int)gridDim.x - race_blocks;
   extern __shared__ __align__(16) unsigned char wf_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -315,12 +226,20 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
   // static contiguous sample range of this warp
   const int64_t gw = (int64_t)wf_block * kWfWarps + warp, W = (int64_t)wf_blocks * kWfWarps;
   const int64_t base = B / W, rem = B % W;
-  const int64_t lo = dyn_counter ? 0 : gw * base + (gw < rem ? gw : rem);
-  const int64_t hi = dyn_counter ? B : lo + base + (gw < rem ? 1 : 0);
+  const int64_t lo = (dyn_counter || race_warp) ? 0 : gw * base + (gw < rem ? gw : rem);
+  const int64_t hi = race_warp ? 0 : (dyn_counter ? B : lo + base + (gw < rem ? 1 : 0));
   int64_t next = lo;               // static: next unread sample of the range; dynamic: B once the counter ran out
 
   for (int s = lane; s < kWfSlots; s += 32) { pool->q_done[s] = (uint8_t)s; pool->sample[s] = -1; }
   int n_act = 0, n_done = kWfSlots, h_act = 0, h_done = 0, n_in = 0, h_in = 0;
+  if (race_warp) {
+    // no triage: the warp's kRaceSamples samples x kRaceLanes start points wait in q_in (entry = sample | start << 28)
+    const int64_t first = ((int64_t)blockIdx.x * kWfWarps + warp) * kRaceSamples;
+    const int64_t left = head - first;
+    const int cnt = left <= 0 ? 0 : (left < kRaceSamples ? (int)left : kRaceSamples);
+    if (lane < cnt * kRaceLanes) pool->q_in[lane] = (int32_t)(first + lane / kRaceLanes) | ((lane % kRaceLanes) << 28);
+    n_in = cnt * kRaceLanes;
+  }
   __syncwarp();
 
   while (true) {
@@ -415,6 +334,13 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
         pool->field[46][slot] = d0;
         pool->field[47][slot] = tr.alpha; pool->field[48][slot] = tr.lo; pool->field[49][slot] = tr.hi;
       }
+      if (race_warp) {
+        // the slots of one sample vote: the first finisher wins, its siblings give their slots back unfinalised
+        const int sid = on ? pool->sample[slot] : -2 - lane;
+        const unsigned grp = __match_any_sync(0xffffffffu, sid);
+        const unsigned fin = __ballot_sync(0xffffffffu, on && st == cn::NEWTON_DONE);
+        if (on && (grp & fin) && lane != __ffs(grp & fin) - 1) { pool->sample[slot] = -1; st = cn::NEWTON_DONE; }
+      }
       __syncwarp();          // ring entries read above may be overwritten below (queue full): order the accesses
       const unsigned m_done = __ballot_sync(0xffffffffu, st == cn::NEWTON_DONE);
       const unsigned m_act = __ballot_sync(0xffffffffu, st == cn::NEWTON_CONTINUE);
@@ -443,7 +369,9 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
         }
         const bool work = pass == 0 ? (on && old >= 0) : (lane < n_new);
         if (work) {
-          const int64_t b = lo + (pass == 0 ? old : pool->q_in[(h_in + lane) % kWfSlots]);
+          const int32_t ent = pass == 0 ? old : pool->q_in[(h_in + lane) % kWfSlots];
+          const int start = race_warp ? (ent >> 28) & 7 : 0;          // (pass 1 of a racing warp: which start point)
+          const int64_t b = lo + (race_warp ? (ent & 0x0fffffff) : ent);
           T xs[13], xps[13];
 #pragma unroll
           for (int i = 0; i < 13; ++i) { xs[i] = T(x[b * ldx + i]); xps[i] = T(xp[b * ldxp + i]); }
@@ -476,7 +404,8 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
             pool->sample[slot] = -1;
           } else {
             T us[6];
-            cn::cube_loss_start<T>(A, T(CN_LOSS_START_FACTOR), us);
+            if (start == 3) cn::cube_loss_start_fraction<T>(A, T(0.3), us);
+            else cn::cube_loss_start<T>(A, start == 1 ? T(2) : start == 2 ? T(60) : T(CN_LOSS_START_FACTOR), us);
 #pragma unroll
             for (int i = 0; i < 6; ++i) pool->field[33 + i][slot] = u_init ? T(u_init[b * 6 + i]) : us[i];
             pool->field[39][slot] = T(-1);
@@ -1129,8 +1058,8 @@ int launch_cube_loss(int variant, const IO* x, const IO* xp, const IO* weight, c
     if ((flags & DPLL_LOSS_RACE) && variant == 2 && small && !u_init && B >= 4096 && B <= kRaceMaxBatch) {
       head = B / 64;
       if (head > kRaceMaxHead) head = kRaceMaxHead;
-      head -= head % (kRaceThreads / kRaceLanes);
-      race_blocks = (int)(head / (kRaceThreads / kRaceLanes));
+      head -= head % (kWfWarps * kRaceSamples);
+      race_blocks = (int)(head / (kWfWarps * kRaceSamples));
       // an SM holds two blocks: leave the racing blocks their share of the resident set
       if (blocks > cap - race_blocks) blocks = (int)(cap - race_blocks > 1 ? cap - race_blocks : 1);
     }
