@@ -138,10 +138,11 @@ int dpll_cube_loss_leaf_f32(const float* x, const float* x_plus, const float* we
  *       and ends with the cheap samples: no serial tail.  Per-sample outputs are unaffected; the summed
  *       gradient is reproducible to rounding only.
  *       DPLL_LOSS_RACE (with DPLL_LOSS_DYNAMIC, cold solves, 4,096 <= B <= 300,000) -- the batch is cost-ordered, so its
- *       first B/64 (<= 2,048) samples are the expensive ones: they are solved by a racing kernel on a second stream
- *       (four start points per sample on four lanes, first to converge wins; the optimum is unique) while the
- *       wavefront kernel takes the rest.  A small launch lasts as long as its longest Newton chain; racing shortens
- *       the worst chain from ~47 to ~28 visits.  Per-sample outputs as without the flag, up to the solver tolerance.
+ *       first B/64 (<= 2,048) samples are the expensive ones: they go to racing warps in the first blocks of the same
+ *       launch (four start points per sample in four slots, a vote after every Newton visit, first to converge wins;
+ *       the optimum is unique) while the other blocks take the rest.  A small launch lasts as long as its longest
+ *       Newton chain; racing shortens the worst chain from ~47 to ~28 visits.  Per-sample outputs as without the
+ *       flag, up to the solver tolerance.
  *   comm  : nullable communicator (dpll_comm_create).  When given, the reduction kernel exchanges
  *       [grad_leaf 15 | loss sum | B] with every peer over NVLink itself and the outputs are the sums over
  *       ranks, bitwise identical on every rank; every rank of the communicator must make the call.
