@@ -41,6 +41,21 @@ inline DeviceInfo device_info() {
   return {cached_sms, dev};
 }
 
+// Tosses per warp of a rollout launch.  A toss is a chain of dependent steps, so a warp is issue-bound by its own
+// instruction stream whatever its number of active lanes (ncu, 4,096 x 80 at four tosses per warp: 2.2 lanes per instruction
+// with the FP64 pipe 64% busy), and two warps on one SM sub-partition slow each other down.  Small batches therefore get ONE
+// block per SM -- one warp per sub-partition -- with as many tosses per warp as that takes (4,096 x 80: 7 per warp; measured
+// 2.61 ms at 4 per warp, 2.04 at 8, 2.32 at 12, 2.45 at 16); only when that would put more than 12 tosses on a warp (the warp
+// advances at the pace of its slowest toss) are all resident warps used.
+inline int rollout_tosses_per_warp(int64_t B, int sms, int64_t resident_warps) {
+  const int64_t warps1 = (int64_t)sms * (kLossThreads / 32);
+  int64_t lpw = (B + warps1 - 1) / warps1;
+  if (lpw > 12) lpw = (B + resident_warps - 1) / resident_warps;
+  if (lpw < 1) lpw = 1;
+  if (lpw > 32) lpw = 32;
+  return (int)lpw;
+}
+
 template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -963,9 +978,7 @@ int launch_elbow_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO
   if (per_sm < 1) per_sm = 1;
   const int64_t cap = (int64_t)di.sms * per_sm;
   const int64_t warps = cap * (kLossThreads / 32);
-  int lpw = (int)((B + warps - 1) / warps);
-  if (lpw < 1) lpw = 1;
-  if (lpw > 32) lpw = 32;
+  const int lpw = rollout_tosses_per_warp(B, di.sms, warps);
   const int64_t per_block = (int64_t)lpw * (kLossThreads / 32);
   const int64_t need = (B + per_block - 1) / per_block;
   const int blocks = (int)(need < cap ? need : cap);
@@ -1115,9 +1128,7 @@ int launch_cube_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO*
   if (per_sm < 1) per_sm = 1;
   const int64_t cap = (int64_t)di.sms * per_sm;                      // resident blocks
   const int64_t warps = cap * (kLossThreads / 32);
-  int lpw = (int)((B + warps - 1) / warps);                          // tosses per warp when spread over all of them
-  if (lpw < 1) lpw = 1;
-  if (lpw > 32) lpw = 32;
+  const int lpw = rollout_tosses_per_warp(B, di.sms, warps);
   const int64_t per_block = (int64_t)lpw * (kLossThreads / 32);
   const int64_t need = (B + per_block - 1) / per_block;
   const int blocks = (int)(need < cap ? need : cap);
