@@ -601,7 +601,11 @@ CN_HD bool elbow_loss_sample_phase(const ElbowParams<T>& P, const SolverCfg<T>& 
 // ---------------------------------------------------------------------------
 template <typename T>
 CN_HD int elbow_step_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, const T* x, const T* pts, T* xn,
-                            T* force_out) {
+                            T* force_out, T* u_out = nullptr, const T* u_fixed = nullptr) {
+  // u_out: receives the QP optimum u* (world twist + hinge rate; v+ = v- + u*).  u_fixed: the optimum is KNOWN (kept by the
+  // forward rollout): instead of solving, take ONE Newton step at it.  In plain arithmetic that changes nothing; in
+  // dual-number arithmetic with u_fixed entered as a constant the step's tangent is -H(u*)^-1 dg/d(direction) -- the
+  // implicit-function derivative of the solve -- at the cost of one evaluation instead of a whole dual-number solve.
   T store[ELBOW_PROB_FIELDS];
   const ElbowProb<T> S{store, 1};
   ElbowKin<T> K;
@@ -624,7 +628,21 @@ CN_HD int elbow_step_sample(const ElbowParams<T>& P, const SolverCfg<T>& cfg, co
     S.q(3 * c + 2) = e[2] + (S.rho(3 * c + 2) + x[6]) * inv_dt;
   }
   T u[7] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
-  const int it = elbow_solve(P, S, cfg, u);
+  int it = 0;
+  if (u_fixed) {
+    for (int i = 0; i < 7; ++i) u[i] = u_fixed[i];
+    if (!elbow_trivially_solved(S)) {
+      T g[7], H[49], res2, scale2, inv_diag[7], ng[7], d[7];
+      elbow_eval<T, true>(P, S, u, g, H, res2, scale2);
+      chol_factor<T, 7>(H, inv_diag);
+      for (int i = 0; i < 7; ++i) ng[i] = -g[i];
+      chol_solve<T, 7>(H, inv_diag, ng, d);
+      for (int i = 0; i < 7; ++i) u[i] += d[i];
+    }
+  } else {
+    it = elbow_solve(P, S, cfg, u);
+  }
+  if (u_out) for (int i = 0; i < 7; ++i) u_out[i] = u[i];
   if (force_out)
     for (int c = 0; c < EL_NC; ++c) {
       T r[3], f[3];

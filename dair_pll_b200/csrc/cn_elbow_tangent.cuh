@@ -16,7 +16,7 @@ constexpr int ELBOW_NPARAM_TAN = 28;
 // xbar: upstream gradient w.r.t. traj[1..steps] (steps x 15).  Returns sum_s xbar_s . d x_s / d (direction).
 template <typename B>
 CN_HD B elbow_rollout_tangent(const B* inertia, const B* mu, const B* half, const B* kin, B dt, B eps, const B* x0,
-                              int steps, const B* xbar, int dir) {
+                              int steps, const B* xbar, int dir, const B* usol = nullptr) {
   typedef DualN<B, 1> D;
   D din[20], dmu[2], dh[6], dkin[12];
   for (int i = 0; i < 20; ++i) { din[i] = D(inertia[i]); if (dir == i) din[i].d[0] = B(1); }
@@ -34,7 +34,13 @@ CN_HD B elbow_rollout_tangent(const B* inertia, const B* mu, const B* half, cons
   for (int i = 0; i < 15; ++i) { x[i] = D(x0[i]); if (dir == ELBOW_NPARAM_TAN + i) x[i].d[0] = B(1); }
   B g = B(0);
   for (int s = 0; s < steps; ++s) {
-    elbow_step_sample<D>(P, cfg, x, (const D*)nullptr, xn, (D*)nullptr);
+    if (usol) {      // the forward rollout kept every step's optimum: one Newton step at it instead of a dual-number solve
+      D uf[7];
+      for (int i = 0; i < 7; ++i) uf[i] = D(usol[s * 7 + i]);
+      elbow_step_sample<D>(P, cfg, x, (const D*)nullptr, xn, (D*)nullptr, (D*)nullptr, uf);
+    } else {
+      elbow_step_sample<D>(P, cfg, x, (const D*)nullptr, xn, (D*)nullptr);
+    }
     for (int i = 0; i < 15; ++i) { g += xbar[s * 15 + i] * xn[i].d[0]; x[i] = xn[i]; }
   }
   return g;
@@ -50,7 +56,7 @@ constexpr int ELBOW_PTS_NPARAM = 22;
 
 template <typename B>
 CN_HD B elbow_step_pts_tangent(const B* inertia, const B* mu, const B* kin, B dt, B eps, const B* x0, const B* pts,
-                               const B* xbar, int dir) {
+                               const B* xbar, int dir, const B* usol = nullptr) {
   typedef DualN<B, 1> D;
   D din[20], dmu[2], dh[6], dkin[12], dp[24];
   for (int i = 0; i < 20; ++i) { din[i] = D(inertia[i]); if (dir == i) din[i].d[0] = B(1); }
@@ -67,7 +73,13 @@ CN_HD B elbow_step_pts_tangent(const B* inertia, const B* mu, const B* kin, B dt
   cfg.polish = true;
   D x[15], xn[15];
   for (int i = 0; i < 15; ++i) { x[i] = D(x0[i]); if (dir == ELBOW_PTS_NPARAM + 24 + i) x[i].d[0] = B(1); }
-  elbow_step_sample<D>(P, cfg, x, dp, xn, (D*)nullptr);
+  if (usol) {
+    D uf[7];
+    for (int i = 0; i < 7; ++i) uf[i] = D(usol[i]);
+    elbow_step_sample<D>(P, cfg, x, dp, xn, (D*)nullptr, (D*)nullptr, uf);
+  } else {
+    elbow_step_sample<D>(P, cfg, x, dp, xn, (D*)nullptr);
+  }
   B g = B(0);
   for (int i = 0; i < 15; ++i) g += xbar[i] * xn[i].d[0];
   return g;

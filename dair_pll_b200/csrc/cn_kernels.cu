@@ -860,7 +860,7 @@ __global__ void __launch_bounds__(kLossThreads)
 elbow_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, const IO* __restrict__ mu,
                      const IO* __restrict__ half, const IO* __restrict__ kin, const IO* __restrict__ pts, T dt, T eps,
                      int64_t B, int steps, IO* __restrict__ traj, IO* __restrict__ force, int32_t* __restrict__ iters,
-                     int lanes_per_warp) {
+                     int lanes_per_warp, IO* __restrict__ usol) {
   const int lane = threadIdx.x & 31;              // small batches are spread thinly, as in cube_rollout_kernel
   if (lane >= lanes_per_warp) return;
   cn::ElbowParams<T> P;
@@ -875,7 +875,10 @@ elbow_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, 
     if (pts) for (int i = 0; i < 24; ++i) pt[i] = T(pts[b * 24 + i]);
     int total = 0;
     for (int s = 0; s < steps; ++s) {
-      total += cn::elbow_step_sample<T>(P, cfg, xc, pts ? pt : (const T*)nullptr, xn, force ? fo : (T*)nullptr);
+      T us[7];
+      total += cn::elbow_step_sample<T>(P, cfg, xc, pts ? pt : (const T*)nullptr, xn, force ? fo : (T*)nullptr,
+                                        usol ? us : (T*)nullptr);
+      if (usol) for (int i = 0; i < 7; ++i) usol[(b * steps + s) * 7 + i] = IO(us[i]);
       if (force) for (int i = 0; i < 24; ++i) force[(b * steps + s) * 24 + i] = IO(fo[i]);
       for (int i = 0; i < 15; ++i) { xc[i] = xn[i]; out[(int64_t)(s + 1) * 15 + i] = IO(xn[i]); }
     }
@@ -967,7 +970,8 @@ int launch_elbow_loss(int variant, const IO* x, const IO* xp, const IO* weight, 
 
 template <typename T, typename IO>
 int launch_elbow_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO* half, const IO* kin, const IO* pts,
-                         T dt, T eps, int64_t B, int32_t steps, IO* traj, IO* force, int32_t* iters, void* stream) {
+                         T dt, T eps, int64_t B, int32_t steps, IO* traj, IO* force, int32_t* iters, void* stream,
+                         IO* usol = nullptr) {
   if (B < 0 || steps < 0 || !inertia || !mu || (!half && !pts) || !kin || (pts && steps > 1)) return DPLL_EINVAL;
   if (B > 0 && (!x0 || !traj)) return DPLL_EINVAL;
   if (B == 0) return DPLL_OK;
@@ -983,7 +987,7 @@ int launch_elbow_rollout(const IO* x0, const IO* inertia, const IO* mu, const IO
   const int64_t need = (B + per_block - 1) / per_block;
   const int blocks = (int)(need < cap ? need : cap);
   elbow_rollout_kernel<T, IO><<<blocks, kLossThreads, 0, st>>>(x0, inertia, mu, half, kin, pts, dt, eps, B, steps, traj,
-                                                              force, iters, lpw);
+                                                              force, iters, lpw, usol);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPLL_OK : (int)e;
 }
@@ -1352,6 +1356,14 @@ int dpll_elbow_rollout_f64(const double* x0, const double* inertia, const double
                            double* force, int32_t* iters, void* stream) {
   return launch_elbow_rollout<double, double>(x0, inertia, mu_pair, half, kin, pts, dt, eps, B, steps, traj, force, iters,
                                               stream);
+}
+
+int dpll_elbow_rollout_saved_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,
+                                 const double* kin, const double* pts, double dt, double eps, int64_t B, int32_t steps,
+                                 double* traj, double* usol, void* stream) {
+  if (B > 0 && steps > 0 && !usol) return DPLL_EINVAL;
+  return launch_elbow_rollout<double, double>(x0, inertia, mu_pair, half, kin, pts, dt, eps, B, steps, traj, nullptr, nullptr,
+                                              stream, usol);
 }
 
 int dpll_elbow_rollout_f32(const float* x0, const float* inertia, const float* mu_pair, const float* half,

@@ -473,6 +473,25 @@ class ElbowContactNetsLossPts(torch.autograd.Function):
                 None, None, None)
 
 
+def elbow_rollout_saved(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Optional[Tensor], kin: Tensor, dt: float,
+                        steps: int, eps: float = 1e-4, pts: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """``dpll_elbow_rollout_saved_f64``: trajectory (B, steps+1, 15) and every step's QP optimum usol (B, steps, 7), which
+    the backward (forward-mode tangents) turns into one evaluation per step instead of a dual-number solve.  float64."""
+    _check_inputs(x0, inertia, mu_pair, kin)
+    f64 = torch.float64
+    a = [t.detach().to(f64).contiguous() for t in (x0, inertia, mu_pair, kin)]
+    h = half.detach().to(f64).contiguous() if half is not None else None
+    pt = pts.detach().to(f64).contiguous() if pts is not None else None
+    B = x0.shape[0]
+    traj = torch.empty((B, steps + 1, 15), dtype=f64, device=x0.device)
+    usol = torch.empty((B, steps, 7), dtype=f64, device=x0.device)
+    with torch.cuda.device(x0.device):
+        rc = _lib.load().dpll_elbow_rollout_saved_f64(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(h), _ptr(a[3]), _ptr(pt), dt, eps,
+                                                      B, steps, _ptr(traj), _ptr(usol), _stream())
+    _lib.check(rc, 'dpll_elbow_rollout_saved')
+    return traj, usol
+
+
 def elbow_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Optional[Tensor], kin: Tensor, dt: float,
                   steps: int, eps: float = 1e-4, want_force: bool = False,
                   pts: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
@@ -549,18 +568,19 @@ class CubeRollout(torch.autograd.Function):
 
 class ElbowRollout(torch.autograd.Function):
     """Differentiable rollout of the learnable two-body (elbow) system with box geometries: traj (B, steps+1, 15).
-    Backward = ``dpll_elbow_rollout_grad_f64`` (forward-mode tangents, 43 directions per toss)."""
+    Backward = ``dpll_elbow_rollout_grad_saved_f64`` (forward-mode tangents, 43 directions per toss; every step's QP
+    optimum is kept by the forward, so a dual-number step is one evaluation + one 7x7 solve at it, not a solve)."""
 
     @staticmethod
     def forward(ctx, x0, inertia, mu_pair, half, kin, dt, steps, eps):
-        traj, _ = elbow_rollout(x0, inertia, mu_pair, half, kin, dt, steps, eps)
+        traj, usol = elbow_rollout_saved(x0, inertia, mu_pair, half, kin, dt, steps, eps)
         ctx.dt, ctx.steps, ctx.eps = dt, steps, eps
-        ctx.save_for_backward(x0, inertia, mu_pair, half, kin)
-        return traj
+        ctx.save_for_backward(x0, inertia, mu_pair, half, kin, usol)
+        return traj.to(x0.dtype)
 
     @staticmethod
     def backward(ctx, gtraj):
-        x0, inertia, mu_pair, half, kin = ctx.saved_tensors
+        x0, inertia, mu_pair, half, kin, usol = ctx.saved_tensors
         B, steps = x0.shape[0], ctx.steps
         f64 = torch.float64
         xbar = gtraj[:, 1:, :].to(f64).contiguous()
@@ -569,10 +589,10 @@ class ElbowRollout(torch.autograd.Function):
         if B > 0 and steps > 0:
             a = [t.detach().to(f64).contiguous() for t in (x0, inertia, mu_pair, half, kin)]
             with torch.cuda.device(x0.device):
-                rc = _lib.load().dpll_elbow_rollout_grad_f64(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(a[4]),
-                                                             ctx.dt, ctx.eps, B, steps, _ptr(xbar), _ptr(gparams),
-                                                             _ptr(gx0), _stream())
-            _lib.check(rc, 'dpll_elbow_rollout_grad')
+                rc = _lib.load().dpll_elbow_rollout_grad_saved_f64(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(a[4]),
+                                                                   _ptr(usol), ctx.dt, ctx.eps, B, steps, _ptr(xbar),
+                                                                   _ptr(gparams), _ptr(gx0), _stream())
+            _lib.check(rc, 'dpll_elbow_rollout_grad_saved')
         g = gparams.sum(0)
         gx = (gx0 + gtraj[:, 0, :].to(f64)).to(x0.dtype)
         return (gx, g[0:20].reshape(inertia.shape).to(inertia.dtype), g[20:22].reshape(mu_pair.shape).to(mu_pair.dtype),
@@ -587,14 +607,14 @@ class ElbowStepPts(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, inertia, mu_pair, pts, kin, dt, eps):
-        traj, _ = elbow_rollout(x, inertia, mu_pair, None, kin, dt, 1, eps, pts=pts)
+        traj, usol = elbow_rollout_saved(x, inertia, mu_pair, None, kin, dt, 1, eps, pts=pts)
         ctx.dt, ctx.eps = dt, eps
-        ctx.save_for_backward(x, inertia, mu_pair, pts, kin)
-        return traj[:, 1]
+        ctx.save_for_backward(x, inertia, mu_pair, pts, kin, usol)
+        return traj[:, 1].to(x.dtype)
 
     @staticmethod
     def backward(ctx, gnext):
-        x, inertia, mu_pair, pts, kin = ctx.saved_tensors
+        x, inertia, mu_pair, pts, kin, usol = ctx.saved_tensors
         B = x.shape[0]
         f64 = torch.float64
         gparams = torch.zeros((B, 22), dtype=f64, device=x.device)
@@ -605,8 +625,8 @@ class ElbowStepPts(torch.autograd.Function):
             xbar = gnext.to(f64).contiguous()
             with torch.cuda.device(x.device):
                 rc = _lib.load().dpll_elbow_step_pts_grad_f64(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(a[4]),
-                                                              ctx.dt, ctx.eps, B, _ptr(xbar), _ptr(gparams), _ptr(gpts),
-                                                              _ptr(gx), _stream())
+                                                              _ptr(usol), ctx.dt, ctx.eps, B, _ptr(xbar), _ptr(gparams),
+                                                              _ptr(gpts), _ptr(gx), _stream())
             _lib.check(rc, 'dpll_elbow_step_pts_grad')
         g = gparams.sum(0)
         return (gx.to(x.dtype), g[0:20].reshape(inertia.shape).to(inertia.dtype),

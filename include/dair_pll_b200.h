@@ -44,7 +44,7 @@ extern "C" {
 #define DPLL_EWORKSPACE (-2) /* workspace too small */
 #define DPLL_ECOMM (-3)      /* a peer did not arrive within the exchange's timeout */
 
-#define DPLL_VERSION 202     /* bumped with every change of a signature below; the binding checks it */
+#define DPLL_VERSION 203     /* bumped with every change of a signature below; the binding checks it */
 
 #define DPLL_CUBE_NX 13
 #define DPLL_CUBE_NC 4
@@ -365,8 +365,22 @@ int dpll_elbow_rollout_grad_f64(const double* x0, const double* inertia, const d
  * sample, implicit derivative of the QP by the polishing Newton step.
  */
 int dpll_elbow_step_pts_grad_f64(const double* x, const double* inertia, const double* mu_pair, const double* kin,
-                                 const double* pts, double dt, double eps, int64_t B, const double* xbar,
-                                 double* gparams, double* gpts, double* gx, void* stream);
+                                 const double* pts, const double* usol, double dt, double eps, int64_t B,
+                                 const double* xbar, double* gparams, double* gpts, double* gx, void* stream);
+
+/*
+ * The two-body rollout keeping every step's QP optimum, usol (B, steps, 7) (world twist of the first link + hinge rate;
+ * v+ = v- + u*), and the forward-mode backward that uses it: with the optimum known, a dual-number step is ONE evaluation
+ * and one 7x7 Cholesky solve at u* (whose tangent is the implicit-function derivative) instead of a whole dual-number
+ * Newton solve.  usol nullable in the two *_grad entry points (then every step is solved again in dual arithmetic, as
+ * dpll_elbow_rollout_grad_f64 does).  pts as in dpll_elbow_rollout_f64 (steps <= 1 when given).
+ */
+int dpll_elbow_rollout_saved_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,
+                                 const double* kin, const double* pts, double dt, double eps, int64_t B, int32_t steps,
+                                 double* traj, double* usol, void* stream);
+int dpll_elbow_rollout_grad_saved_f64(const double* x0, const double* inertia, const double* mu_pair, const double* half,
+                                      const double* kin, const double* usol, double dt, double eps, int64_t B,
+                                      int32_t steps, const double* xbar, double* gparams, double* gx0, void* stream);
 
 /*
  * The same two operations for the elbow (assets/contactnets_elbow.urdf: floating base + one

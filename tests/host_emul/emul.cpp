@@ -266,6 +266,29 @@ int emul_cube_rollout_backward_f64(const double* x0, const double* inertia, cons
   }
   return 0;
 }
+// the same with every step's optimum kept by a plain forward rollout (one evaluation per dual-number step)
+int emul_elbow_rollout_grad_saved_f64(const double* x0, const double* inertia, const double* mu, const double* half,
+                                      const double* kin, double dt, double eps, int64_t B, int steps, const double* xbar,
+                                      double* gparams, double* gx0) {
+  ElbowParams<double> P;
+  elbow_params_init<double>(P, inertia, mu, half, kin, dt, eps);
+  const SolverCfg<double> cfg = default_cfg<double>();
+  std::vector<double> usol((size_t)steps * 7);
+  for (int64_t b = 0; b < B; ++b) {
+    double x[15], xn[15];
+    for (int i = 0; i < 15; ++i) x[i] = x0[15 * b + i];
+    for (int s = 0; s < steps; ++s) {
+      elbow_step_sample<double>(P, cfg, x, (const double*)nullptr, xn, (double*)nullptr, &usol[(size_t)s * 7]);
+      for (int i = 0; i < 15; ++i) x[i] = xn[i];
+    }
+    for (int dir = 0; dir < ELBOW_NTAN; ++dir) {
+      const double g = elbow_rollout_tangent<double>(inertia, mu, half, kin, dt, eps, x0 + 15 * b, steps,
+                                                     xbar + (int64_t)b * steps * 15, dir, usol.data());
+      if (dir < ELBOW_NPARAM_TAN) gparams[ELBOW_NPARAM_TAN * b + dir] = g; else gx0[15 * b + dir - ELBOW_NPARAM_TAN] = g;
+    }
+  }
+  return 0;
+}
 int emul_elbow_rollout_grad_f64(const double* x0, const double* inertia, const double* mu, const double* half,
                                 const double* kin, double dt, double eps, int64_t B, int steps, const double* xbar,
                                 double* gparams, double* gx0) {

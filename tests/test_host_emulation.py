@@ -259,6 +259,28 @@ def test_elbow_step_tangents_match_oracle_autograd():
     assert max_rel_to_scale(gl, np.stack([p.grad.numpy().reshape(3) for p in P.length_params])) < 1e-9
 
 
+def test_elbow_tangents_with_kept_optima_equal_the_dual_number_solves():
+    """dpll_elbow_rollout_grad_saved_f64's arithmetic: with every step's QP optimum kept by the forward rollout, a
+    dual-number step is ONE evaluation + one 7x7 solve at the optimum; its tangents must equal those of the full
+    dual-number Newton solves (the implicit-function derivative either way)."""
+    lib = host_emulation_lib()
+    g = load_golden('elbow_perturbed')
+    inertia, mu, half = elbow_kernel_level_params(g)
+    x0 = np.ascontiguousarray(g['sim_x0'][:10])
+    B, steps = x0.shape[0], 4
+    rng = np.random.default_rng(2)
+    xbar = rng.standard_normal((B, steps, 15))
+    out = []
+    for fn in (lib.emul_elbow_rollout_grad_f64, lib.emul_elbow_rollout_grad_saved_f64):
+        gparams, gx0 = np.zeros((B, 28)), np.zeros((B, 15))
+        fn(dptr(x0), dptr(inertia), dptr(mu), dptr(half), dptr(ELBOW_KIN), ctypes.c_double(float(g['dt'])),
+           ctypes.c_double(1e-4), ctypes.c_int64(B), ctypes.c_int(steps), dptr(xbar), dptr(gparams), dptr(gx0))
+        out.append((gparams, gx0))
+    assert np.abs(out[0][0]).max() > 0
+    assert max_rel_to_scale(out[1][0], out[0][0]) < 1e-9
+    assert max_rel_to_scale(out[1][1], out[0][1]) < 1e-9
+
+
 def test_free_flight_fast_path_equals_the_generic_path():
     """The triage phase's register-only evaluation of free-flight samples: it fires exactly on the samples
     whose solve is trivial (0 iterations, zero forces) and gives the generic path's loss and gradient."""
