@@ -776,4 +776,103 @@ CN_HD T elbow_loss_sample_wf(const ElbowParams<T>& P, const SolverCfg<T>& cfg, c
   return elbow_loss_epilogue_wf<T, T>(P, S, E, A, u, grad, force_out, grad_pts, T(1));
 }
 
+// Learnable time step of the two-body system on this file's algebra (closed-form mass terms and inverse, 17-number mass
+// record, packed 7x7 Hessian) -- the plain-arithmetic step of the rollout kernels.  Same mathematics as elbow_step_sample
+// (cn_elbow.cuh: forward_dynamics multibody_learnable_system.py:199-304 + VelocityIntegrator.step integrator.py:153-162 +
+// FloatingBaseSpace.exponential state_space.py:466-486), which stays as the dual-number instance of the backward; the two
+// agree to rounding (host-emulation test).  u_out: the QP optimum (v+ = v- + u*), kept for the backward.
+template <typename T>
+CN_HD int elbow_step_sample_wf(const ElbowParams<T>& P, const SolverCfg<T>& cfg, const T* x, const T* pts, T* xn,
+                               T* force_out, T* u_out) {
+  T store[EW_REC];
+  const ElbowRec<T> S{store, 1};
+  ElbowSetup<T> E;
+  elbow_setup(P, x, E);
+  elbow_minv_setup(E);
+  T vW[7], F[7], b2[6], acc[7], vm[7];
+  elbow_to_world(E.R1, x + 8, vW);
+  elbow_force17(P, E, vW, F, b2);
+  elbow_minv(E, F, acc);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) vm[i] = vW[i] + P.dt * acc[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) S.Ic(i) = E.Ic[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { S.mc(i) = E.mc[i]; S.hw(i) = E.hw[i]; S.hv(i) = E.hv[i]; }
+  S.mt() = E.mt; S.ht() = E.ht;
+  uint32_t sel0 = 0u, sel1 = 0u;
+  if (!pts) {
+    const T d1[3] = {-E.R1[6], -E.R1[7], -E.R1[8]}, d2[3] = {-E.R2[6], -E.R2[7], -E.R2[8]};
+    sel0 = cube_select_corners(d1, P.h[0]);
+    sel1 = cube_select_corners(d2, P.h[1]);
+  }
+  const T inv_dt = T(1) / P.dt;
+  bool open = true;
+#pragma unroll 1
+  for (int c = 0; c < EL_NC; ++c) {
+    const T mu = elbow_mu(P, c);
+    T p[3], rho[3], hcol[3], e[3];
+    elbow_witness<T, T>(P, sel0, sel1, pts, c, p);
+    elbow_contact_geometry(E, c, p, rho, hcol);
+    point_vel7(rho, hcol, vm, e);
+    const T q0 = mu * e[0], q1 = mu * e[1], qn = e[2] + (rho[2] + x[6]) * inv_dt;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      S.rho(3 * c + i) = rho[i];
+      if (c >= 4) S.hc(3 * (c - 4) + i) = hcol[i];
+    }
+    S.q(3 * c) = q0; S.q(3 * c + 1) = q1; S.q(3 * c + 2) = qn;
+    open = open && (qn >= T(0)) && (q0 * q0 + q1 * q1 <= qn * qn);
+  }
+  T u[7] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
+  int it = 0;
+  if (!open) {
+    T d[7], d0 = T(0), best = T(-1);
+    CubeTrial<T> tr{T(1), T(0), T(1)};
+    while (elbow_newton_visit<T>(P, S, cfg, u, d, d0, best, tr, it) != NEWTON_DONE) {}
+  }
+  if (u_out) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) u_out[i] = u[i];
+  }
+  if (force_out) {
+#pragma unroll 1
+    for (int c = 0; c < EL_NC; ++c) {
+      const T mu = elbow_mu(P, c);
+      T rho[3], hcol[3], e[3], f[3];
+      elbow_rec_contact(S, c, rho, hcol);
+      point_vel7(rho, hcol, u, e);
+      const T r[3] = {mu * e[0] + S.q(3 * c), mu * e[1] + S.q(3 * c + 1), e[2] + S.q(3 * c + 2)};
+      cone_eval<T, false>(r, P.inv_eps, mu, f, (T*)nullptr);
+      force_out[c] = f[2]; force_out[8 + 2 * c] = f[0]; force_out[8 + 2 * c + 1] = f[1];
+    }
+  }
+  // v+ = v- + u (world twist) -> state coordinates, then q+ = q (+) v+ dt
+  T vnW[7], vn[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) vnW[i] = vm[i] + u[i];
+  rot3t(E.R1, vnW, vn);
+#pragma unroll
+  for (int i = 3; i < 7; ++i) vn[i] = vnW[i];
+  const T rx = vn[0] * P.dt, ry = vn[1] * P.dt, rz = vn[2] * P.dt;
+  const T ang = t_sqrt(rx * rx + ry * ry + rz * rz);
+  const T half = T(0.5) * ang;
+  using ::sin;          // (cn_dual.cuh's overloads for dual numbers would otherwise hide the scalar ones in this namespace)
+  using ::cos;
+  const T sinc = half > T(0) ? sin(half) / half : T(1);
+  const T dw = cos(half), k = T(0.5) * sinc;
+  const T dx = rx * k, dy = ry * k, dz = rz * k;
+  const T qw = x[0], qx = x[1], qy = x[2], qz = x[3];
+  xn[0] = qw * dw - (qx * dx + qy * dy + qz * dz);
+  xn[1] = qw * dx + dw * qx + (qy * dz - qz * dy);
+  xn[2] = qw * dy + dw * qy + (qz * dx - qx * dz);
+  xn[3] = qw * dz + dw * qz + (qx * dy - qy * dx);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) xn[4 + i] = x[4 + i] + vn[3 + i] * P.dt;
+  xn[7] = x[7] + vn[6] * P.dt;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) xn[8 + i] = vn[i];
+  return it & 0xff;
+}
+
 }  // namespace cn

@@ -11,6 +11,7 @@
 #include "cn_cube.cuh"
 #include "cn_params.cuh"
 #include "cn_elbow.cuh"
+#include "cn_elbow_wf.cuh"
 #include "cn_comm.cuh"
 
 // wavefront kernel of the two-body system (cn_elbow_wf.cu)
@@ -876,8 +877,8 @@ elbow_rollout_kernel(const IO* __restrict__ x0, const IO* __restrict__ inertia, 
     int total = 0;
     for (int s = 0; s < steps; ++s) {
       T us[7];
-      total += cn::elbow_step_sample<T>(P, cfg, xc, pts ? pt : (const T*)nullptr, xn, force ? fo : (T*)nullptr,
-                                        usol ? us : (T*)nullptr);
+      total += cn::elbow_step_sample_wf<T>(P, cfg, xc, pts ? pt : (const T*)nullptr, xn, force ? fo : (T*)nullptr,
+                                           usol ? us : (T*)nullptr);
       if (usol) for (int i = 0; i < 7; ++i) usol[(b * steps + s) * 7 + i] = IO(us[i]);
       if (force) for (int i = 0; i < 24; ++i) force[(b * steps + s) * 24 + i] = IO(fo[i]);
       for (int i = 0; i < 15; ++i) { xc[i] = xn[i]; out[(int64_t)(s + 1) * 15 + i] = IO(xn[i]); }

@@ -221,6 +221,18 @@ int emul_elbow_loss_wf_f64(const double* x, const double* xp, const double* iner
   }
   return 0;
 }
+// the rollout kernels' step (closed-form mass terms, cn_elbow_wf.cuh)
+int emul_elbow_step_wf_f64(const double* x, const double* inertia, const double* mu, const double* half,
+                           const double* kin, const double* pts, double dt, double eps, int64_t B, double* xn,
+                           double* force, double* usol) {
+  ElbowParams<double> P;
+  elbow_params_init<double>(P, inertia, mu, half, kin, dt, eps);
+  SolverCfg<double> cfg = default_cfg<double>();
+  for (int64_t b = 0; b < B; ++b)
+    elbow_step_sample_wf<double>(P, cfg, x + 15 * b, pts ? pts + 24 * b : nullptr, xn + 15 * b,
+                                 force ? force + 24 * b : nullptr, usol ? usol + 7 * b : nullptr);
+  return 0;
+}
 int emul_elbow_step_f64(const double* x, const double* inertia, const double* mu, const double* half,
                         const double* kin, double dt, double eps, int64_t B, double* xn, double* force, int32_t* iters) {
   ElbowParams<double> P;

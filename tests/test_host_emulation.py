@@ -259,6 +259,38 @@ def test_elbow_step_tangents_match_oracle_autograd():
     assert max_rel_to_scale(gl, np.stack([p.grad.numpy().reshape(3) for p in P.length_params])) < 1e-9
 
 
+def test_elbow_closed_form_step_equals_the_dense_step_and_the_reference_golden():
+    """The rollout kernels' step of the two-body system (elbow_step_sample_wf: closed-form mass terms and inverse, packed
+    Hessian) against the reference-code golden (one step, 1e-9) and against the dense formulation that the backward
+    differentiates, over a multi-step rollout on random states (next states and contact forces)."""
+    from dair_pll_b200 import synthetic
+    lib = host_emulation_lib()
+    g = load_golden('elbow_perturbed')
+    inertia, mu, half = elbow_kernel_level_params(g)
+    dt = ctypes.c_double(float(g['dt']))
+    x0 = np.ascontiguousarray(g['sim_x0'])
+    xn, us = np.zeros_like(x0), np.zeros((x0.shape[0], 7))
+    lib.emul_elbow_step_wf_f64(dptr(x0), dptr(inertia), dptr(mu), dptr(half), dptr(ELBOW_KIN), None, dt, ctypes.c_double(1e-4),
+                               ctypes.c_int64(x0.shape[0]), dptr(xn), None, dptr(us))
+    assert np.abs(xn - g['sim_traj'][:, 1]).max() < 1e-9
+    x = synthetic.elbow_states(600, seed=9).numpy().copy()
+    worst_x = worst_f = 0.0
+    active = 0
+    for _ in range(4):
+        a, b = np.zeros_like(x), np.zeros_like(x)
+        fa, fb = np.zeros((x.shape[0], 24)), np.zeros((x.shape[0], 24))
+        lib.emul_elbow_step_wf_f64(dptr(x), dptr(inertia), dptr(mu), dptr(half), dptr(ELBOW_KIN), None, dt,
+                                   ctypes.c_double(1e-4), ctypes.c_int64(x.shape[0]), dptr(a), dptr(fa), None)
+        lib.emul_elbow_step_f64(dptr(x), dptr(inertia), dptr(mu), dptr(half), dptr(ELBOW_KIN), dt, ctypes.c_double(1e-4),
+                                ctypes.c_int64(x.shape[0]), dptr(b), dptr(fb), None)
+        worst_x = max(worst_x, np.abs(a - b).max())
+        worst_f = max(worst_f, np.abs(fa - fb).max() / max(np.abs(fb).max(), 1e-300))
+        active += int((np.abs(fb).max(-1) > 0).sum())
+        x = b
+    assert active > 200                       # the comparison does exercise the solver
+    assert worst_x < 1e-9 and worst_f < 1e-7, (worst_x, worst_f)
+
+
 def test_elbow_tangents_with_kept_optima_equal_the_dual_number_solves():
     """dpll_elbow_rollout_grad_saved_f64's arithmetic: with every step's QP optimum kept by the forward rollout, a
     dual-number step is ONE evaluation + one 7x7 solve at the optimum; its tangents must equal those of the full
