@@ -1,3 +1,5 @@
+"""A few launches of the wavefront kernel with racing warps on a 131,072-pair shard of the cost-ordered bench batch (then two
+without racing) -- the command profiled under ncu / compute-sanitizer.  Not a benchmark."""
 import sys, torch
 sys.path.insert(0, '.')
 import bench

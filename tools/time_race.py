@@ -1,3 +1,5 @@
+"""Kernel time of strong-scaling shards (every 16th / 8th / 4th sample of the cost-ordered 1M bench batch) through the training
+entry point, with and without racing warps for the expensive head (DPLL_LOSS_RACE).  CUDA events; not the bench."""
 import sys, torch
 sys.path.insert(0, '.')
 import bench
