@@ -7,6 +7,7 @@
 #pragma once
 #include "cn_elbow.cuh"
 #include "cn_dual.cuh"
+#include "cn_elbow_wf.cuh"
 
 namespace cn {
 
@@ -37,7 +38,7 @@ CN_HD B elbow_rollout_tangent(const B* inertia, const B* mu, const B* half, cons
     if (usol) {      // the forward rollout kept every step's optimum: one Newton step at it instead of a dual-number solve
       D uf[7];
       for (int i = 0; i < 7; ++i) uf[i] = D(usol[s * 7 + i]);
-      elbow_step_sample<D>(P, cfg, x, (const D*)nullptr, xn, (D*)nullptr, (D*)nullptr, uf);
+      elbow_step_sample_wf<D>(P, cfg, x, (const D*)nullptr, xn, (D*)nullptr, (D*)nullptr, uf);
     } else {
       elbow_step_sample<D>(P, cfg, x, (const D*)nullptr, xn, (D*)nullptr);
     }
@@ -76,7 +77,7 @@ CN_HD B elbow_step_pts_tangent(const B* inertia, const B* mu, const B* kin, B dt
   if (usol) {
     D uf[7];
     for (int i = 0; i < 7; ++i) uf[i] = D(usol[i]);
-    elbow_step_sample<D>(P, cfg, x, dp, xn, (D*)nullptr, (D*)nullptr, uf);
+    elbow_step_sample_wf<D>(P, cfg, x, dp, xn, (D*)nullptr, (D*)nullptr, uf);
   } else {
     elbow_step_sample<D>(P, cfg, x, dp, xn, (D*)nullptr);
   }

@@ -783,7 +783,9 @@ CN_HD T elbow_loss_sample_wf(const ElbowParams<T>& P, const SolverCfg<T>& cfg, c
 // agree to rounding (host-emulation test).  u_out: the QP optimum (v+ = v- + u*), kept for the backward.
 template <typename T>
 CN_HD int elbow_step_sample_wf(const ElbowParams<T>& P, const SolverCfg<T>& cfg, const T* x, const T* pts, T* xn,
-                               T* force_out, T* u_out) {
+                               T* force_out, T* u_out, const T* u_fixed = nullptr) {
+  // u_fixed: the optimum is known (kept by the forward rollout) and entered as a constant; ONE Newton step at it then
+  // carries, in dual-number arithmetic, the implicit-function derivative of the solve (see elbow_step_sample, cn_elbow.cuh)
   T store[EW_REC];
   const ElbowRec<T> S{store, 1};
   ElbowSetup<T> E;
@@ -826,7 +828,17 @@ CN_HD int elbow_step_sample_wf(const ElbowParams<T>& P, const SolverCfg<T>& cfg,
   }
   T u[7] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
   int it = 0;
-  if (!open) {
+  if (u_fixed) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) u[i] = u_fixed[i];
+    if (!open) {
+      T g[7], H[28], d[7], res2, scale2;
+      elbow_eval_wf<T, true>(P, S, u, g, H, res2, scale2);
+      chol7_packed_solve_neg<T>(H, g, d);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) u[i] += d[i];
+    }
+  } else if (!open) {
     T d[7], d0 = T(0), best = T(-1);
     CubeTrial<T> tr{T(1), T(0), T(1)};
     while (elbow_newton_visit<T>(P, S, cfg, u, d, d0, best, tr, it) != NEWTON_DONE) {}
