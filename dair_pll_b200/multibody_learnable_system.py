@@ -208,8 +208,15 @@ class MultibodyLearnableSystem(System):
         if self._kind() == 'cube' and self.multibody_terms.contact_terms.has_witness_point_geometry():
             # the witness points depend on the orientation: the time loop stays on the host, one step per launch
             if torch.is_grad_enabled() and (x_0.requires_grad or any(p.requires_grad for p in self.multibody_terms.parameters())):
-                raise NotImplementedError('the rollout with Sphere / Polygon geometry has no backward: evaluate it under '
-                                          'torch.no_grad(), or train with contactnets_loss')
+                # differentiable (prediction loss): every step an autograd node (36-direction tangent kernel); the support
+                # points are ordinary torch functions of the state and the shape parameters, so their cotangent reaches both
+                inertia, mu, _ = self._cube_params(torch.float64)
+                xs = [self._flat(x_0).to(torch.float64)]
+                for _ in range(steps):
+                    pts, n_c = self._body_witness_points(xs[-1][:, :4])
+                    xs.append(ops.BodyStepPts.apply(xs[-1], inertia, mu, pts, n_c, float(self.dt), STEP_EPS))
+                traj = torch.stack(xs, 1).to(x_0.dtype)
+                return traj.reshape(batch + (steps + 1, self.space.n_x))
             with torch.no_grad():
                 inertia, mu, _ = self._cube_params(torch.float64)
                 xs = [self._flat(x_0).to(torch.float64)]

@@ -697,6 +697,38 @@ def body_step_pts(x: Tensor, inertia: Tensor, mu_pair: Tensor, pts: Tensor, n_co
     return out
 
 
+class BodyStepPts(torch.autograd.Function):
+    """ONE differentiable learnable step of a single floating body with witness points (Sphere, Polygon): x (B,13), pts
+    (B,4,3) -> next state (B,13).  Backward = ``dpll_body_step_pts_grad_f64`` (36 forward-mode directions per sample); the
+    points' cotangent flows on through the caller's autograd graph into the shape parameters and the state."""
+
+    @staticmethod
+    def forward(ctx, x, inertia, mu_pair, pts, n_contacts, dt, eps):
+        ctx.n_c, ctx.dt, ctx.eps = n_contacts, dt, eps
+        ctx.save_for_backward(x, inertia, mu_pair, pts)
+        return body_step_pts(x.detach(), inertia.detach(), mu_pair.detach(), pts.detach(), n_contacts, dt, eps)
+
+    @staticmethod
+    def backward(ctx, gnext):
+        x, inertia, mu_pair, pts = ctx.saved_tensors
+        B = x.shape[0]
+        f64 = torch.float64
+        gparams = torch.zeros((B, 11), dtype=f64, device=x.device)
+        gpts = torch.zeros((B, 12), dtype=f64, device=x.device)
+        gx = torch.zeros((B, 13), dtype=f64, device=x.device)
+        if B > 0:
+            a = [t.detach().to(f64).contiguous() for t in (x, inertia, mu_pair, pts)]
+            xbar = gnext.to(f64).contiguous()
+            with torch.cuda.device(x.device):
+                rc = _lib.load().dpll_body_step_pts_grad_f64(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), ctx.n_c, ctx.dt,
+                                                             ctx.eps, B, _ptr(xbar), _ptr(gparams), _ptr(gpts), _ptr(gx),
+                                                             _stream())
+            _lib.check(rc, 'dpll_body_step_pts_grad')
+        g = gparams.sum(0)
+        return (gx.to(x.dtype), g[0:10].reshape(inertia.shape).to(inertia.dtype), g[10:11].reshape(mu_pair.shape).to(mu_pair.dtype),
+                gpts.reshape(pts.shape).to(pts.dtype), None, None, None)
+
+
 class ChainContactNetsLoss(torch.autograd.Function):
     """ContactNets loss of a generic floating-base serial chain of ``n`` links (``dpll_chain_loss_f64``,
     csrc/cn_chain.cuh): differentiable w.r.t. inertia (n,10), mu_pair (n), half (n,3); float64."""

@@ -44,7 +44,7 @@ extern "C" {
 #define DPLL_EWORKSPACE (-2) /* workspace too small */
 #define DPLL_ECOMM (-3)      /* a peer did not arrive within the exchange's timeout */
 
-#define DPLL_VERSION 203     /* bumped with every change of a signature below; the binding checks it */
+#define DPLL_VERSION 204     /* bumped with every change of a signature below; the binding checks it */
 
 #define DPLL_CUBE_NX 13
 #define DPLL_CUBE_NC 4
@@ -293,6 +293,16 @@ int dpll_body_loss_pts_f64(const double* x, const double* x_plus, const double* 
 int dpll_body_step_pts_f64(const double* x, const double* inertia, const double* mu_pair, const double* pts,
                            int32_t n_contacts, double dt, double eps, int64_t B, double* x_next, double* force,
                            void* stream);
+
+/*
+ * Backward of ONE witness-point step (the prediction-loss path for Sphere / Polygon geometries, whose support points
+ * depend on the state, so that rollout runs step by step): given xbar (B, 13) w.r.t. the next state, gparams (B, 11) =
+ * [d/d inertia (10) | d/d mu_pair], gpts (B, 12) and gx (B, 13) w.r.t. the current state at fixed points.  Forward-mode
+ * tangents through the step code, 36 directions per sample.
+ */
+int dpll_body_step_pts_grad_f64(const double* x, const double* inertia, const double* mu_pair, const double* pts,
+                                int32_t n_contacts, double dt, double eps, int64_t B, const double* xbar,
+                                double* gparams, double* gpts, double* gx, void* stream);
 
 /*
  * Dense dynamics terms of the cube in the reference's coordinates and ordering, for callers of

@@ -70,6 +70,23 @@ def case(name, geom, learn_name, support, seed):
     p = getattr(geom, learn_name)
     out['shape_param'] = p.detach().numpy()
     out['grad_shape_param'] = p.grad.numpy()
+    # prediction-loss path: a 3-step rollout by the reference's own integrator, weighted sum of the states, autograd
+    # through every step's QP -> gradients of theta, friction, the shape parameter and the initial state
+    for q in system.parameters():
+        q.grad = None
+    m, steps = 40, 3
+    x0 = x[:m].clone().requires_grad_()
+    gw = torch.Generator().manual_seed(seed + 2)
+    w = torch.randn(m, steps, 13, generator=gw, dtype=torch.float64)
+    xs, cur = [], x0
+    for _ in range(steps):
+        cur, _ = system.integrator.step(cur, torch.zeros(m, 1))
+        xs.append(cur)
+    traj = torch.stack(xs, 1)
+    (traj * w).sum().backward()
+    out.update(roll_x0=x0.detach().numpy(), roll_w=w.numpy(), roll_traj=traj.detach().numpy(),
+               roll_grad_x0=x0.grad.numpy(), roll_grad_theta=mt.lagrangian_terms.inertial_parameters.grad.numpy(),
+               roll_grad_friction=mt.contact_terms.friction_params.grad.numpy(), roll_grad_shape_param=p.grad.numpy())
     path = os.path.join(ROOT, 'tests', 'golden', f'shape_{name}.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, 'mean loss', float(loss.mean()), 'in contact', float((loss.detach() > 1e-12).float().mean()))

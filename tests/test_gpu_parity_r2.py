@@ -422,6 +422,21 @@ def test_sphere_and_polygon_geometries_match_reference_golden(name, assets_dir):
         traj, _ = s.simulate(x.unsqueeze(-2), torch.zeros(x.shape[0], 1, device=DEV), 2)
     assert np.abs(traj[:, 1].cpu().numpy() - g['x_next']).max() < 1e-9
     assert torch.isfinite(traj).all()
+    # prediction-loss path: 3-step rollout, gradients of theta / friction / shape parameter / initial state against the
+    # reference's own integrator differentiated by autograd (the support points depend on the state: a sphere's d r)
+    for p in s.parameters():
+        p.grad = None
+    x0 = torch.from_numpy(g['roll_x0']).to(DEV).requires_grad_()
+    w = torch.from_numpy(g['roll_w']).to(DEV)
+    steps = w.shape[1]
+    tr, _ = s.simulate(x0.unsqueeze(-2), torch.zeros(x0.shape[0], 1, device=DEV), steps)
+    (tr[:, 1:] * w).sum().backward()
+    assert np.abs(tr[:, 1:].detach().cpu().numpy() - g['roll_traj']).max() < 1e-8
+    tol = 1e-7      # the reference form of the velocity update loses ~cond(Q) eps of the derivatives
+    assert max_rel_to_scale(x0.grad.cpu().numpy(), g['roll_grad_x0']) < tol
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), g['roll_grad_theta']) < tol
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), g['roll_grad_friction']) < tol
+    assert max_rel_to_scale(leaf().grad.cpu().numpy(), g['roll_grad_shape_param']) < tol
 
 
 def test_warm_started_solves_give_the_same_results_in_fewer_iterations(assets_dir):
