@@ -263,12 +263,12 @@ class MultibodyLearnableSystem(System):
                 traj, _ = ops.elbow_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(), kin,
                                             float(self.dt), steps, STEP_EPS)
         elif self._kind() == 'chain':
-            if torch.is_grad_enabled() and (x_0.requires_grad or any(p.requires_grad for p in self.multibody_terms.parameters())):
-                raise NotImplementedError('the generic chain rollout has no backward: evaluate it under torch.no_grad(), '
-                                          'or train with contactnets_loss')
-            with torch.no_grad():
-                inertia, mu, half, kin, n = self._chain_params(x_0.device)
-                traj = ops.chain_rollout(self._flat(x_0).to(torch.float64), inertia, mu, half, kin, n, float(self.dt),
+            inertia, mu, half, kin, n = self._chain_params(x_0.device)
+            xf = self._flat(x_0).to(torch.float64)
+            if torch.is_grad_enabled() and any(t.requires_grad for t in (x_0, inertia, mu, half)):
+                traj = ops.ChainRollout.apply(xf, inertia, mu, half, kin, n, float(self.dt), steps, STEP_EPS).to(x_0.dtype)
+            else:
+                traj = ops.chain_rollout(xf.detach(), inertia.detach(), mu.detach(), half.detach(), kin, n, float(self.dt),
                                          steps, STEP_EPS).to(x_0.dtype)
         else:
             raise NotImplementedError(f'no kernel specialisation for system kind {self._kind()!r}')

@@ -791,6 +791,37 @@ def chain_rollout(x0: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, ki
     return traj
 
 
+class ChainRollout(torch.autograd.Function):
+    """Differentiable rollout of a generic serial chain of ``n`` links: traj (B, steps+1, n_x).  Backward =
+    ``dpll_chain_rollout_grad_f64`` (forward-mode tangents, 14 n + n_x directions per toss).  float64."""
+
+    @staticmethod
+    def forward(ctx, x0, inertia, mu_pair, half, kin, n, dt, steps, eps):
+        ctx.n, ctx.dt, ctx.steps, ctx.eps = n, dt, steps, eps
+        ctx.save_for_backward(x0, inertia, mu_pair, half, kin)
+        return chain_rollout(x0.detach(), inertia.detach(), mu_pair.detach(), half.detach(), kin, n, dt, steps, eps)
+
+    @staticmethod
+    def backward(ctx, gtraj):
+        x0, inertia, mu_pair, half, kin = ctx.saved_tensors
+        B, n, steps, nx = x0.shape[0], ctx.n, ctx.steps, x0.shape[1]
+        f64 = torch.float64
+        xbar = gtraj[:, 1:, :].to(f64).contiguous()
+        gparams = torch.zeros((B, 14 * n), dtype=f64, device=x0.device)
+        gx0 = torch.zeros((B, nx), dtype=f64, device=x0.device)
+        if B > 0 and steps > 0:
+            a = [t.detach().to(f64).contiguous() for t in (x0, inertia, mu_pair, half, kin)]
+            with torch.cuda.device(x0.device):
+                rc = _lib.load().dpll_chain_rollout_grad_f64(n, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(a[4]),
+                                                             ctx.dt, ctx.eps, B, steps, _ptr(xbar), _ptr(gparams), _ptr(gx0),
+                                                             _stream())
+            _lib.check(rc, 'dpll_chain_rollout_grad')
+        g = gparams.sum(0)
+        gx = (gx0 + gtraj[:, 0, :].to(f64)).to(x0.dtype)
+        return (gx, g[0:10 * n].reshape(inertia.shape).to(inertia.dtype), g[10 * n:11 * n].reshape(mu_pair.shape).to(mu_pair.dtype),
+                g[11 * n:14 * n].reshape(half.shape).to(half.dtype), None, None, None, None, None)
+
+
 def cube_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor):
     """``dpll_cube_terms_f64``: (delassus (B,12,12), M (B,6,6), J (B,12,6), phi (B,4), acc (B,6)) in the order
     ``MultibodyTerms.forward`` returns them (multibody_terms.py:584-609).  fp64 only, no autograd."""

@@ -44,7 +44,7 @@ extern "C" {
 #define DPLL_EWORKSPACE (-2) /* workspace too small */
 #define DPLL_ECOMM (-3)      /* a peer did not arrive within the exchange's timeout */
 
-#define DPLL_VERSION 204     /* bumped with every change of a signature below; the binding checks it */
+#define DPLL_VERSION 205     /* bumped with every change of a signature below; the binding checks it */
 
 #define DPLL_CUBE_NX 13
 #define DPLL_CUBE_NC 4
@@ -461,6 +461,12 @@ int dpll_chain_loss_f64(int32_t n_links, const double* x, const double* x_plus, 
 int dpll_chain_rollout_f64(int32_t n_links, const double* x0, const double* inertia, const double* mu_pair,
                            const double* half, const double* kin, double dt, double eps, int64_t B, int32_t steps,
                            double* traj, void* stream);
+/* Backward of the chain rollout (prediction loss): xbar (B, steps, n_x) w.r.t. traj[:, 1:] -> gparams (B, 14 n) =
+ * [d/d inertia (10 n) | d/d mu_pair (n) | d/d half (3 n)] and gx0 (B, n_x), by forward-mode tangents through the step code
+ * (14 n + n_x directions per toss), as dpll_elbow_rollout_grad_f64. */
+int dpll_chain_rollout_grad_f64(int32_t n_links, const double* x0, const double* inertia, const double* mu_pair,
+                                const double* half, const double* kin, double dt, double eps, int64_t B, int32_t steps,
+                                const double* xbar, double* gparams, double* gx0, void* stream);
 
 /*
  * Parameter preparation of any system and its chain rule, one launch each (csrc/cn_leaf.cu): theta (n_bodies, 10)

@@ -81,6 +81,24 @@ def main():
                grad_theta=mt.lagrangian_terms.inertial_parameters.grad.numpy(),
                grad_friction=mt.contact_terms.friction_params.grad.numpy(),
                grad_length=np.stack([mt.contact_terms.geometries[i].length_params.grad.numpy().reshape(3) for i in range(3)]))
+    # prediction-loss path: 3-step rollout by the reference's own integrator, weighted sum of the states, autograd through
+    # every step's QP -> gradients of theta, friction, box lengths and the initial state
+    for q in system.parameters():
+        q.grad = None
+    m, steps = 24, 3
+    x0 = x[:m].clone().requires_grad_()
+    w = torch.randn(m, steps, 17, generator=torch.Generator().manual_seed(13), dtype=torch.float64)
+    xs, cur = [], x0
+    for _ in range(steps):
+        cur, _ = system.integrator.step(cur, torch.zeros(m, 1))
+        xs.append(cur)
+    traj = torch.stack(xs, 1)
+    (traj * w).sum().backward()
+    out.update(roll_x0=x0.detach().numpy(), roll_w=w.numpy(), roll_traj=traj.detach().numpy(), roll_grad_x0=x0.grad.numpy(),
+               roll_grad_theta=mt.lagrangian_terms.inertial_parameters.grad.numpy(),
+               roll_grad_friction=mt.contact_terms.friction_params.grad.numpy(),
+               roll_grad_length=np.stack([mt.contact_terms.geometries[i].length_params.grad.numpy().reshape(3)
+                                          for i in range(3)]))
     path = os.path.join(ROOT, 'tests', 'golden', 'chain3.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, 'mean loss', float(loss.mean()))

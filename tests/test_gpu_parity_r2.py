@@ -520,8 +520,21 @@ def test_generic_chain_three_links_matches_reference_golden(assets_dir):
     with torch.no_grad():
         one, _ = s.simulate(traj[:, 1:2], torch.zeros(x.shape[0], 1, device=DEV), 1)
     assert (one[:, 1] - traj[:, 2]).abs().max().item() < 1e-12
-    with pytest.raises(NotImplementedError):
-        s.simulate(x.unsqueeze(-2), torch.zeros(x.shape[0], 1, device=DEV), 1)     # no backward for the generic rollout
+    # prediction-loss path: 3-step rollout gradients (forward-mode tangents, dpll_chain_rollout_grad_f64) against the
+    # reference's own integrator differentiated by autograd
+    for p in s.parameters():
+        p.grad = None
+    x0 = torch.from_numpy(g['roll_x0']).to(DEV).requires_grad_()
+    w = torch.from_numpy(g['roll_w']).to(DEV)
+    tr, _ = s.simulate(x0.unsqueeze(-2), torch.zeros(x0.shape[0], 1, device=DEV), w.shape[1])
+    (tr[:, 1:] * w).sum().backward()
+    assert np.abs(tr[:, 1:].detach().cpu().numpy() - g['roll_traj']).max() < 1e-8
+    tol = 1e-7      # the reference form of the velocity update loses ~cond(Q) eps of the derivatives
+    gt, gf, *gl = _leaf_grads(s)
+    assert max_rel_to_scale(x0.grad.cpu().numpy(), g['roll_grad_x0']) < tol
+    assert max_rel_to_scale(gt, g['roll_grad_theta']) < tol
+    assert max_rel_to_scale(gf, g['roll_grad_friction']) < tol
+    assert max_rel_to_scale(np.stack([a.reshape(3) for a in gl]), g['roll_grad_length']) < tol
 
 
 @pytest.mark.parametrize('name', ['elbow_nominal', 'elbow_perturbed'])
