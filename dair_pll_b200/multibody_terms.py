@@ -152,8 +152,11 @@ class MultibodyTerms(Module):
                 phi.reshape(batch + (n_c,)), acc.reshape(batch + (n_v,)))
 
     def scalars_and_meshes(self):
-        """Summary scalars per body (multibody_terms.py:536-582); no meshes for box geometries."""
-        scalars = {}
+        """Summary scalars per body and, for learned (``DeepSupportConvex``) geometries, the extracted mesh with its
+        bounding-box diameters and centre (multibody_terms.py:536-582)."""
+        from dair_pll_b200.deep_support_function import extract_mesh
+        from dair_pll_b200.geometry import DeepSupportConvex
+        scalars, meshes = {}, {}
         mu = self.contact_terms.get_friction_coefficients()
         for body, pi in zip(self.spec.bodies, self.lagrangian_terms.pi_cm()):
             for k, val in InertialParameterConverter.pi_cm_to_scalars(pi).items():
@@ -162,4 +165,12 @@ class MultibodyTerms(Module):
                 for k, val in self.contact_terms.geometries[gi].scalars().items():
                     scalars[f'{body.name}_{k}'] = val
                 scalars[f'{body.name}_mu'] = mu[gi].item()
-        return scalars, {}
+                geometry = self.contact_terms.geometries[gi]
+                if isinstance(geometry, DeepSupportConvex):
+                    mesh = extract_mesh(geometry.network)
+                    meshes[body.name] = mesh
+                    lo, hi = mesh.vertices.min(dim=0).values, mesh.vertices.max(dim=0).values
+                    for axis, dia, cen in zip('xyz', hi - lo, lo + (hi - lo) / 2):
+                        scalars[f'{body.name}_diameter_{axis}'] = dia.item()
+                        scalars[f'{body.name}_center_{axis}'] = cen.item()
+        return scalars, meshes

@@ -765,3 +765,75 @@ def test_racing_kernel_for_the_expensive_head_gives_the_same_results(assets_dir)
     system.race_expensive_head = False
     plain = step()
     assert abs(plain.item() - eager.item()) < 1e-11 * abs(eager.item())
+
+
+@pytest.mark.parametrize('depth', [1, 3, 4])
+def test_support_network_of_other_depths_matches_the_reference_class(depth):
+    """``HomogeneousICNN`` at depths other than the default 2 (deep_support_function.py:125-266): support points and the
+    gradients of a linear functional of them with respect to EVERY weight against the reference's own class
+    (tests/golden/icnn_depth.npz, oracle/gen_golden_icnn_depth.py), 1e-12."""
+    from dair_pll_b200.deep_support_function import HomogeneousICNN
+    g = load_golden('icnn_depth')
+    width = int(g['width'])
+    net = HomogeneousICNN(depth, width, negative_slope=0.5)
+    with torch.no_grad():
+        for i, w in enumerate(net.input_weights):
+            w.copy_(torch.from_numpy(g[f'd{depth}_in{i}']))
+        for i, w in enumerate(net.hidden_weights):
+            w.copy_(torch.from_numpy(g[f'd{depth}_hid{i}']))
+        net.output_weight.copy_(torch.from_numpy(g[f'd{depth}_out']))
+    net = net.to(DEV)
+    d = torch.from_numpy(g['directions']).to(DEV)
+    c = torch.from_numpy(g['cotangent']).to(DEV)
+    p = net(d)
+    assert max_rel_to_scale(p.detach().cpu().numpy(), g[f'd{depth}_p']) < 1e-12
+    (p * c).sum().backward()
+    for i, w in enumerate(net.input_weights):
+        assert max_rel_to_scale(w.grad.cpu().numpy(), g[f'd{depth}_gin{i}']) < 1e-12, ('input', i)
+    for i, w in enumerate(net.hidden_weights):
+        assert max_rel_to_scale(w.grad.cpu().numpy(), g[f'd{depth}_ghid{i}']) < 1e-12, ('hidden', i)
+    assert max_rel_to_scale(net.output_weight.grad.cpu().numpy(), g[f'd{depth}_gout']) < 1e-12
+
+
+def test_summary_mesh_matches_the_reference_extraction():
+    """``extract_mesh`` (deep_support_function.py:95-122) of a depth-3 network evaluated on the device against the mesh
+    the reference's own function extracted from the same weights: same vertices (1e-10 absolute), same set of
+    outward-wound triangles."""
+    from dair_pll_b200.deep_support_function import HomogeneousICNN, extract_mesh
+    g = load_golden('icnn_depth')
+    net = HomogeneousICNN(3, int(g['width']), negative_slope=0.5)
+    with torch.no_grad():
+        for i, w in enumerate(net.input_weights):
+            w.copy_(torch.from_numpy(g[f'd3_in{i}']))
+        for i, w in enumerate(net.hidden_weights):
+            w.copy_(torch.from_numpy(g[f'd3_hid{i}']))
+        net.output_weight.copy_(torch.from_numpy(g['d3_out']))
+    mesh = extract_mesh(net.to(DEV))
+    gv, gf = g['d3_mesh_vertices'], g['d3_mesh_faces']
+    key = lambda v: tuple(np.round(np.asarray(v) * 1e10).astype(np.int64).tolist())   # noqa: E731  (shape is ~0.1 across)
+    assert {key(v) for v in mesh.vertices.numpy()} == {key(v) for v in gv}
+
+    def canon(vertices, faces):   # oriented triangles by vertex coordinates, rotation-invariant
+        out = set()
+        for f in faces.tolist():
+            tri = [key(vertices[i]) for i in f]
+            k = tri.index(min(tri))
+            out.add((tri[k], tri[(k + 1) % 3], tri[(k + 2) % 3]))
+        return out
+    assert canon(mesh.vertices.numpy(), mesh.faces.numpy()) == canon(gv, gf)
+
+
+def test_elbow_mesh_summary_carries_the_learned_meshes(assets_dir):
+    """``MultibodyLearnableSystem.summary`` for the learned-geometry elbow (multibody_learnable_system.py:313-333,
+    multibody_terms.py:566-580): one mesh per link from the default depth-2 tensor-core networks, with the bounding-box
+    scalars; every mesh is a closed convex surface (Euler characteristic 2) whose vertices are support points."""
+    system = MultibodyLearnableSystem({'elbow': os.path.join(assets_dir, 'elbow_mesh.urdf')}, DT).to(DEV)
+    summary = system.summary({})
+    assert len(summary.meshes) == 2
+    for name, mesh in summary.meshes.items():
+        v, f = mesh.vertices.shape[0], mesh.faces.shape[0]
+        edges = {tuple(sorted((tri[i], tri[(i + 1) % 3]))) for tri in mesh.faces.tolist() for i in range(3)}
+        assert v - len(edges) + f == 2
+        for axis in 'xyz':
+            assert summary.scalars[f'{name}_diameter_{axis}'] > 0
+            assert f'{name}_center_{axis}' in summary.scalars

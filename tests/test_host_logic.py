@@ -308,3 +308,32 @@ def test_chain_spec_carries_rotated_joint_frames(assets_dir):
     x[:, 0] = 1
     with pytest.raises(RuntimeError, match='no CPU path'):
         s.contactnets_loss(x, torch.zeros(2, 0), x)
+
+
+def test_extract_mesh_of_a_box_support_function_and_cpu_refusal():
+    """``extract_mesh`` (deep_support_function.py:95-122) on a closed-form support function: a box's support points are
+    its corners, so the 296 sampled directions collapse to the 8 distinct vertices and the hull has 12 triangles, every
+    one wound counter-clockwise seen from outside; the sampled direction set equals the reference's formula; a network of
+    any depth refuses CPU tensors (there is no CPU path)."""
+    from dair_pll_b200.deep_support_function import (HomogeneousICNN, extract_mesh, extract_obj, outward_normal_hyperplanes,
+                                                     surface_directions)
+    d = surface_directions()
+    assert d.shape == (296, 3) and d.dtype == torch.float32
+    assert torch.allclose(d.norm(dim=-1), torch.ones(296), atol=1e-6)
+    half = torch.tensor([0.05, 0.03, 0.02], dtype=torch.float64)
+    box = lambda dirs: torch.where(dirs >= 0, half, -half)   # noqa: E731
+    mesh = extract_mesh(box)
+    assert mesh.vertices.shape == (8, 3) and mesh.faces.shape == (12, 3)
+    normals, backwards, offsets = outward_normal_hyperplanes(mesh.vertices, mesh.faces)
+    assert not backwards.any()
+    a, b, c = (mesh.vertices[mesh.faces[:, i]] for i in range(3))
+    assert ((torch.linalg.cross(b - a, c - a) * normals).sum(-1) > 0).all()
+    # every face plane is one of the six box planes
+    assert torch.allclose(offsets, (normals.abs() * half).sum(-1), atol=1e-15)
+    text = extract_obj(box)
+    assert text.count('\nf ') + text.startswith('f ') == 12 and text.count('v ') == 8 and text.count('vn ') == 12
+    for depth in (1, 2, 3):
+        net = HomogeneousICNN(depth, 16)
+        assert len(net.hidden_weights) == depth - 1 and len(net.input_weights) == depth
+        with pytest.raises(RuntimeError, match='no CPU path'):
+            net(torch.zeros(4, 3, dtype=torch.float64))
