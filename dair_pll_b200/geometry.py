@@ -19,8 +19,29 @@ from dair_pll_b200.deep_support_function import HomogeneousICNN
 _TOTAL_ORDERING = ['Plane', 'Polygon', 'Box', 'Sphere', 'DeepSupportConvex']  # geometry.py:46
 
 
+def place_in_link_frame(geometry: 'CollisionGeometry', directions: Tensor) -> Tensor:
+    """Support points (*, n, 3) of ``geometry`` for LINK-frame directions (*, 3), in the link frame: the query direction
+    goes into the collision frame (R_BG^T d), the points come back (p_BG + R_BG p).  ``geometry.frame`` is None when the
+    two frames coincide (multibody_terms.py:299-303: the reference gets R_WG, p_WG from Drake per geometry frame)."""
+    if geometry.frame is None:
+        return geometry.support_points(directions)
+    offset, rot = (t.to(directions.dtype) for t in geometry.frame)
+    return geometry.support_points(directions @ rot) @ rot.t() + offset
+
+
 class CollisionGeometry(Module):
     """Base class; ``>`` / ``<`` follow the reference's type ordering used to orient pairs."""
+
+    def set_frame(self, offset: Tensor, rotation: Tensor) -> None:
+        """Collision frame in the link frame (URDF ``<collision><origin xyz rpy>``): non-persistent buffers, so they follow
+        ``.to(device)`` and stay out of the state_dict (the reference keeps them inside Drake's plant)."""
+        self.register_buffer('frame_offset', offset.to(torch.float64).reshape(3), persistent=False)
+        self.register_buffer('frame_rotation', rotation.to(torch.float64).reshape(3, 3), persistent=False)
+
+    @property
+    def frame(self):
+        """(offset (3,), rotation (3, 3)) or None when the collision frame is the link frame."""
+        return (self.frame_offset, self.frame_rotation) if hasattr(self, 'frame_offset') else None
 
     def __ge__(self, other) -> bool:
         return _TOTAL_ORDERING.index(type(self).__name__) > _TOTAL_ORDERING.index(type(other).__name__)
@@ -50,6 +71,17 @@ class Box(CollisionGeometry):
 
     def get_half_lengths(self) -> Tensor:
         return self.length_params.abs()
+
+    def support_points(self, directions: Tensor) -> Tensor:
+        """(*, 3) directions -> (*, n_query, 3): the ``n_query`` corners with the largest support, by ascending vertex
+        index i = 4 x + 2 y + z, bit set = +h (geometry.py:39-41, 162-202, 399-403).  Used when the box sits in a
+        collision frame of its own (the box kernels select the corners themselves)."""
+        signs = torch.tensor([[(i >> 2) & 1, (i >> 1) & 1, i & 1] for i in range(8)], dtype=directions.dtype,
+                             device=directions.device) * 2 - 1
+        verts = signs * self.get_half_lengths().to(directions.dtype)
+        sel = torch.topk(directions @ verts.t(), self.n_query, dim=-1, sorted=False).indices
+        sel, _ = torch.sort(sel, dim=-1)
+        return verts[sel]
 
     def scalars(self) -> Dict[str, float]:
         return {f'len_{ax}': 2 * v.item() for ax, v in zip('xyz', self.get_half_lengths().reshape(-1))}

@@ -15,6 +15,7 @@ import torch
 from torch import Tensor
 
 from dair_pll_b200 import ops
+from dair_pll_b200.geometry import place_in_link_frame
 from dair_pll_b200.integrator import VelocityIntegrator
 from dair_pll_b200.multibody_terms import MultibodyTerms
 from dair_pll_b200.system import System, SystemSummary
@@ -83,7 +84,7 @@ class MultibodyLearnableSystem(System):
         w, x, y, z = quat.unbind(-1)
         s = 2.0 / (w * w + x * x + y * y + z * z)
         d = -torch.stack((s * (x * z - w * y), s * (y * z + w * x), 1 - s * (x * x + y * y)), -1)
-        p = geom.support_points(d)
+        p = place_in_link_frame(geom, d)
         n_c = p.shape[-2]
         if n_c < 4:
             p = torch.cat((p, p.new_zeros(p.shape[:-2] + (4 - n_c, 3))), -2)

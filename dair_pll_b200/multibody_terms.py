@@ -54,6 +54,12 @@ class ContactTerms(Module):
                 geoms.append(DeepSupportConvex(g.mesh_vertices()))
             else:
                 raise NotImplementedError(f'geometry kind {g.kind!r}')
+        if spec.kind == 'cube':
+            # single floating body: a collision frame of its own is honoured through the witness-point kernels
+            # (the multi-link kernels take the frame offsets in their kinematic table instead)
+            for geom, g in zip(geoms, spec.geometries):
+                if g.body >= 0 and g.has_frame():
+                    geom.set_frame(torch.tensor(g.offset, dtype=torch.float64), g.rotation())
         self.geometries = ModuleList(geoms)
         self.friction_params = Parameter(torch.tensor([g.mu for g in spec.geometries], dtype=torch.float64),
                                          requires_grad=True)
@@ -87,8 +93,9 @@ class ContactTerms(Module):
         return any(isinstance(g, DeepSupportConvex) for g in self.geometries)
 
     def has_witness_point_geometry(self) -> bool:
-        """True if a body geometry is evaluated through its support points here (Sphere, Polygon)."""
-        return any(isinstance(g, (Sphere, Polygon)) for g in self.geometries)
+        """True if a body geometry is evaluated through its support points here (Sphere, Polygon, or any shape that sits
+        in a collision frame of its own)."""
+        return any(isinstance(g, (Sphere, Polygon)) or g.frame is not None for g in self.geometries)
 
 
 class MultibodyTerms(Module):
@@ -134,6 +141,9 @@ class MultibodyTerms(Module):
         batch = q.shape[:-1]
         inertia, mu, half = self.kernel_parameters(q.dtype)
         if self.spec.kind == 'cube':
+            if self.contact_terms.has_witness_point_geometry():
+                raise NotImplementedError('dense terms export is provided for a box in the link frame (other shapes and '
+                                          'framed boxes go through the witness-point kernels)')
             D, M, J, phi, acc = ops.cube_terms(q.reshape(-1, 7), v.reshape(-1, 6), inertia.detach().reshape(10),
                                                mu.detach().reshape(1), half[0].detach())
         elif self.spec.kind == 'elbow':

@@ -55,6 +55,15 @@ class GeometrySpec:
     mesh_file: Optional[str] = None
     mu: float = 1.0
     radius: Optional[float] = None
+    rpy: Tuple[float, float, float] = (0., 0., 0.)   # fixed rotation link frame -> collision frame (<collision><origin rpy>)
+
+    def has_frame(self) -> bool:
+        """True if the collision frame differs from the link frame."""
+        return any(abs(a) > 0 for a in self.offset) or any(abs(a) > 0 for a in self.rpy)
+
+    def rotation(self) -> torch.Tensor:
+        """(3, 3) link frame <- collision frame, URDF convention R = Rz(yaw) Ry(pitch) Rx(roll)."""
+        return _rpy_matrix(self.rpy)
 
     def mesh_vertices(self) -> torch.Tensor:
         """Vertices of the Wavefront .obj (only ``v x y z`` records are needed: the reference uses them
@@ -157,8 +166,7 @@ class SystemSpec:
             for col in link.findall('collision'):
                 corigin = col.find('origin')
                 offset = _floats(corigin.get('xyz') if corigin is not None else None, 3)
-                if corigin is not None and any(abs(a) > 0 for a in _floats(corigin.get('rpy'), 3)):
-                    raise NotImplementedError('rotated collision frames are not supported')
+                crpy = _floats(corigin.get('rpy'), 3) if corigin is not None else (0., 0., 0.)
                 mu = 1.0
                 for prox in col.iter():
                     if prox.tag.endswith('mu_static'):
@@ -167,16 +175,16 @@ class SystemSpec:
                 box, mesh, sphere = geom.find('box'), geom.find('mesh'), geom.find('sphere')
                 if sphere is not None:
                     geometries.append(GeometrySpec(len(bodies) - 1, 'sphere', offset, None, None, mu,
-                                                   float(sphere.get('radius'))))
+                                                   float(sphere.get('radius')), crpy))
                 elif box is not None:
                     size = _floats(box.get('size'), 3)
                     geometries.append(GeometrySpec(len(bodies) - 1, 'box', offset,
-                                                   tuple(0.5 * s for s in size), None, mu))
+                                                   tuple(0.5 * s for s in size), None, mu, None, crpy))
                 elif mesh is not None:
                     fname = mesh.get('filename')
                     if not os.path.isabs(fname):
                         fname = os.path.join(os.path.dirname(os.path.abspath(path)), fname)
-                    geometries.append(GeometrySpec(len(bodies) - 1, 'mesh', offset, None, fname, mu))
+                    geometries.append(GeometrySpec(len(bodies) - 1, 'mesh', offset, None, fname, mu, None, crpy))
                 else:
                     raise NotImplementedError('only <box>, <sphere> and <mesh> collision geometries are supported')
         joints = []
@@ -212,10 +220,12 @@ class SystemSpec:
             if geometries[0].kind not in ('box', 'sphere'):
                 raise NotImplementedError('the single-body kernels take a <box> or <sphere> collision geometry '
                                           '(a Polygon is set through the module API)')
-            if any(abs(o) > 0 for o in geometries[0].offset):
-                raise NotImplementedError('a collision frame offset from the link origin is not supported for a single '
-                                          'floating body (the two-body kernels take offsets)')
+            # a collision frame that differs from the link frame (offset and / or rotation) is handled through the
+            # witness-point kernels: the contact points are support points of the shape, moved into the link frame
         else:
+            if any(any(abs(a) > 0 for a in g.rpy) for g in geometries):
+                raise NotImplementedError('rotated collision frames are supported for a single floating body only '
+                                          '(the multi-link kernels take collision-frame offsets)')
             if [g.body for g in geometries] != list(range(len(bodies))):
                 raise NotImplementedError('the multi-link kernels take one collision geometry per link')
             if kind == 'chain' and any(g.kind != 'box' for g in geometries):

@@ -80,6 +80,16 @@ class TreeSpec:
     geometry_offset: List[Tuple[float, float, float]] = field(default_factory=list)
     joint_rpy: List[Tuple[float, float, float]] = field(default_factory=list)   # fixed rotation parent -> joint frame
                                                                                 # (URDF <origin rpy>); empty = none
+    geometry_rpy: List[Tuple[float, float, float]] = field(default_factory=list)  # fixed rotation link -> collision frame
+                                                                                # (URDF <collision><origin rpy>); empty = none
+
+    def geometry_rotation(self, g: int, dtype) -> Tensor:
+        """Fixed rotation of geometry g's collision frame in its link (R = Rz(yaw) Ry(pitch) Rx(roll))."""
+        if not self.geometry_rpy:
+            return torch.eye(3, dtype=dtype)
+        r, p, y = (torch.tensor(v, dtype=dtype) for v in self.geometry_rpy[g])
+        ex, ey, ez = (torch.tensor(v, dtype=dtype) for v in ((1., 0., 0.), (0., 1., 0.), (0., 0., 1.)))
+        return axis_rot(ez, y) @ axis_rot(ey, p) @ axis_rot(ex, r)
 
     def joint_rotation(self, i: int, dtype) -> Tensor:
         """Fixed rotation of joint i's frame in its parent link (URDF convention R = Rz(yaw) Ry(pitch) Rx(roll))."""
@@ -117,6 +127,13 @@ ELBOW_TREE = TreeSpec(parent=[-1, 0], joint_origin=[(0., 0., 0.), (-0.035, 0.06,
 
 
 # a three-link chain with an off-axis, rotated second joint (tests of the generic chain kernels; not a reference asset)
+# one floating body whose collision geometry sits in a frame of its own, offset and rotated in the link (tests of the
+# collision-frame handling of the single-body path; not a reference asset)
+FRAMED_BODY_TREE = TreeSpec(parent=[-1], joint_origin=[(0., 0., 0.)], axis=[(0., 0., 1.)],
+                            geometry_body=[0, -1], geometry_offset=[(0.012, -0.02, 0.015), (0., 0., 0.)],
+                            geometry_rpy=[(0.3, -0.2, 0.5), (0., 0., 0.)])
+
+
 CHAIN3_TREE = TreeSpec(parent=[-1, 0, 1],
                        joint_origin=[(0., 0., 0.), (-0.035, 0.06, 0.), (0.07, 0.01, -0.02)],
                        axis=[(0., 0., 1.), (0., 1., 0.), (0.6, 0., 0.8)],
@@ -221,7 +238,8 @@ class TreeCallables:
     def geometry_rotations(self, q: Tensor) -> Tensor:
         R, _, _, _, _, _, _ = self.kinematics(q)
         eye = torch.eye(3, dtype=q.dtype).expand(q.shape[:-1] + (3, 3))
-        return torch.stack([eye if b < 0 else R[b] for b in self.tree.geometry_body], -3)
+        return torch.stack([eye if b < 0 else R[b] @ self.tree.geometry_rotation(g, q.dtype)
+                            for g, b in enumerate(self.tree.geometry_body)], -3)
 
     def geometry_translations(self, q: Tensor) -> Tensor:
         R, o, _, _, _, _, _ = self.kinematics(q)

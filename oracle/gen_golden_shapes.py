@@ -1,4 +1,4 @@
-"""ORACLE (test infrastructure).  Writes tests/golden/shape_{sphere,polygon}.npz by running the REFERENCE's own
+"""ORACLE (test infrastructure).  Writes tests/golden/shape_{sphere,polygon,framed_box}.npz by running the REFERENCE's own
 ``contactnets_loss`` / ``sim_step`` (through oracle/ref_shim.py) for a single floating body whose collision geometry
 is the reference's ``Sphere`` (dair_pll/geometry.py:415-456) or ``Polygon`` (:220-252) against the ground plane.
 Needs /root/reference: build container only; the fixtures are committed.
@@ -48,11 +48,11 @@ def rot(quat):
     return _quat_to_rot(quat)
 
 
-def case(name, geom, learn_name, support, seed):
+def case(name, geom, learn_name, support, seed, tree='cube'):
     pi_cm = torch.tensor([[0.31, 0.31 * 0.002, -0.31 * 0.001, 0.31 * 0.0015, 6.1e-4, 7.3e-4, 6.6e-4, 1e-5, -2e-5, 1.5e-5]],
                          dtype=torch.float64)
     friction = torch.tensor([0.4, 0.9], dtype=torch.float64)
-    system = ref_shim.build_reference_system('cube', DT, pi_cm, friction, None, body_geometries=[geom])
+    system = ref_shim.build_reference_system(tree, DT, pi_cm, friction, None, body_geometries=[geom])
     n = 320
     x = states(n, seed, support)
     with torch.no_grad():
@@ -107,6 +107,21 @@ def main():
         row = rot(q)[:, 2, :]                       # R[2, :]: height of vertex v is row . v
         return -(row @ verts.t()).min(dim=1).values
     case('polygon', poly, 'vertices', support, 202)
+    # a Box (geometry.py:359-413) in a collision frame that is offset and rotated in the link (FRAMED_BODY_TREE): the
+    # reference gets R_WG, p_WG and the geometry Jacobian per collision frame (multibody_terms.py:299-310)
+    from dair_pll.geometry import Box
+    from oracle.callables import FRAMED_BODY_TREE, TreeCallables
+    half = torch.tensor([0.05, 0.035, 0.025], dtype=torch.float64)
+    box = Box(half, 4)
+    off = torch.tensor(FRAMED_BODY_TREE.geometry_offset[0], dtype=torch.float64)
+    Rg = FRAMED_BODY_TREE.geometry_rotation(0, torch.float64)
+    signs = torch.tensor([[(i >> 2) & 1, (i >> 1) & 1, i & 1] for i in range(8)], dtype=torch.float64) * 2 - 1
+    corners = off + (signs * half) @ Rg.t()                     # link frame
+
+    def support_framed(q):
+        row = rot(q)[:, 2, :]
+        return -(row @ corners.t()).min(dim=1).values
+    case('framed_box', box, 'length_params', support_framed, 303, tree=FRAMED_BODY_TREE)
 
 
 if __name__ == '__main__':

@@ -387,7 +387,7 @@ def test_reverse_mode_rollout_backward_matches_forward_mode(assets_dir):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in s.parameters())
 
 
-@pytest.mark.parametrize('name', ['shape_sphere', 'shape_polygon'])
+@pytest.mark.parametrize('name', ['shape_sphere', 'shape_polygon', 'shape_framed_box'])
 def test_sphere_and_polygon_geometries_match_reference_golden(name, assets_dir):
     """SURVEY 8(f) N4, plane-convex half: a floating body with the reference's Sphere (geometry.py:415-456) or Polygon
     (:220-252) collision geometry through the module API -- the geometry module evaluates the support points, the
@@ -395,9 +395,16 @@ def test_sphere_and_polygon_geometries_match_reference_golden(name, assets_dir):
     the reference's own classes: losses, gradients of theta / friction / radius or vertices, next states, at 1e-9."""
     from dair_pll_b200.geometry import Polygon
     g = load_golden(name)
-    s = MultibodyLearnableSystem({'body': os.path.join(assets_dir, 'sphere.urdf')}, float(g['dt']))
+    urdf = 'framed_box.urdf' if name == 'shape_framed_box' else 'sphere.urdf'
+    s = MultibodyLearnableSystem({'body': os.path.join(assets_dir, urdf)}, float(g['dt']))
     ct = s.multibody_terms.contact_terms
-    if name == 'shape_polygon':
+    if name == 'shape_framed_box':
+        # a Box in a collision frame offset and rotated in the link (URDF <collision><origin xyz rpy>): the frame comes
+        # from the URDF, the contact points are the placed box's support points
+        with torch.no_grad():
+            ct.geometries[0].length_params.copy_(torch.from_numpy(g['shape_param']))
+        leaf = lambda: ct.geometries[0].length_params       # noqa: E731
+    elif name == 'shape_polygon':
         ct.geometries[0] = Polygon(torch.from_numpy(g['shape_param']), 4)
         leaf = lambda: ct.geometries[0].vertices            # noqa: E731
     else:

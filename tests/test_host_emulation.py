@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from oracle import contactnets_oracle as co
+from dair_pll_b200.geometry import place_in_link_frame
 from oracle.callables import CUBE_TREE, TreeCallables
 from tests.util import dptr, host_emulation_lib, kernel_level_params, load_golden, max_rel_to_scale, rel_err
 
@@ -403,10 +404,16 @@ def test_reverse_mode_step_adjoint_matches_forward_mode_tangents(steps):
 
 def _shape_case(name):
     """golden + the product's geometry object and the witness points it yields on the CPU (torch ops)"""
-    from dair_pll_b200.geometry import Polygon, Sphere
+    from dair_pll_b200.geometry import Box, Polygon, Sphere
     g = load_golden(name)
     p = torch.from_numpy(g['shape_param'])
-    geom = Sphere(p) if name == 'shape_sphere' else Polygon(p, 4)
+    if name == 'shape_framed_box':
+        # the Box sits in a collision frame offset and rotated in the link (oracle.callables.FRAMED_BODY_TREE)
+        from oracle.callables import FRAMED_BODY_TREE as tree
+        geom = Box(p.reshape(3), 4)
+        geom.set_frame(torch.tensor(tree.geometry_offset[0], dtype=torch.float64), tree.geometry_rotation(0, torch.float64))
+    else:
+        geom = Sphere(p) if name == 'shape_sphere' else Polygon(p, 4)
     return g, geom
 
 
@@ -416,7 +423,7 @@ def _support_direction(quat):
     return -torch.stack((s * (x * z - w * y), s * (y * z + w * x), 1 - s * (x * x + y * y)), -1)
 
 
-@pytest.mark.parametrize('name', ['shape_sphere', 'shape_polygon'])
+@pytest.mark.parametrize('name', ['shape_sphere', 'shape_polygon', 'shape_framed_box'])
 def test_witness_point_device_math_matches_reference_golden(name):
     """N4 (plane-convex contacts beyond the box): the witness-point loss / step code against goldens produced by the
     REFERENCE's own Sphere and Polygon classes (oracle/gen_golden_shapes.py): losses, gradients of theta, friction
@@ -432,7 +439,7 @@ def test_witness_point_device_math_matches_reference_golden(name):
     B = x.shape[0]
 
     def witness(states):
-        p = geom.support_points(_support_direction(torch.from_numpy(states[:, :4])))
+        p = place_in_link_frame(geom, _support_direction(torch.from_numpy(states[:, :4])))
         n_c = p.shape[-2]
         full = torch.cat((p, p.new_zeros(B, 4 - n_c, 3)), -2) if n_c < 4 else p
         return p, full, n_c
@@ -448,7 +455,8 @@ def test_witness_point_device_math_matches_reference_golden(name):
     # chain rule to the leaves (golden gradients are of loss.mean())
     torch.cat((inertia_t, mu_t)).backward(torch.from_numpy(g11 / B))
     p.backward(torch.from_numpy(gp[:, :n_c] / B))
-    shape_leaf = geom.length_param if name == 'shape_sphere' else geom.vertices
+    shape_leaf = {'shape_sphere': lambda: geom.length_param, 'shape_polygon': lambda: geom.vertices,
+                  'shape_framed_box': lambda: geom.length_params}[name]()
     assert max_rel_to_scale(theta.grad.numpy(), g['grad_theta']) < 1e-9
     assert max_rel_to_scale(fr.grad.numpy(), g['grad_friction']) < 1e-9
     assert max_rel_to_scale(shape_leaf.grad.numpy(), g['grad_shape_param']) < 1e-9

@@ -271,14 +271,30 @@ def test_peer_allreduce_protocol_model():
 
 
 def test_urdf_ingestion_rejects_what_the_kernels_do_not_model(tmp_path):
-    """Models the kernels would silently mis-simulate are refused at construction: a single floating box whose
-    collision frame is offset from the link origin, and a joint axis is normalised as Drake does on parsing."""
+    """Models the kernels would silently mis-simulate are refused at construction (a rotated collision frame on a
+    multi-link system); a single floating body's collision frame (offset and rotation) is carried to its geometry and
+    equals the oracle tree's; a joint axis is normalised as Drake does on parsing."""
+    from dair_pll_b200.geometry import place_in_link_frame
     from dair_pll_b200.system_spec import SystemSpec
-    cube = open(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'cube.urdf')).read()
-    assert '<collision>' in cube
-    shifted = cube.replace('<collision>', '<collision>\n      <origin xyz="0.01 0 0" rpy="0 0 0"/>', 1)
-    p = tmp_path / 'shifted.urdf'
-    p.write_text(shifted)
+    from oracle.callables import FRAMED_BODY_TREE as tree
+    framed = MultibodyLearnableSystem({'body': os.path.join(ROOT, 'dair_pll_b200', 'assets', 'framed_box.urdf')}, 0.0068)
+    ct = framed.multibody_terms.contact_terms
+    assert ct.has_witness_point_geometry() and ct.geometries[0].frame is not None and ct.geometries[1].frame is None
+    off, rot = ct.geometries[0].frame
+    assert torch.allclose(off, torch.tensor(tree.geometry_offset[0], dtype=torch.float64), atol=0, rtol=0)
+    assert torch.allclose(rot, tree.geometry_rotation(0, torch.float64), atol=1e-15)
+    assert 'frame_offset' not in ''.join(framed.state_dict().keys())          # checkpoint keys as the reference's
+    # the lowest corners of the placed box in a direction are its support points
+    d = torch.tensor([[0.3, -0.5, -0.8]], dtype=torch.float64)
+    pts = place_in_link_frame(ct.geometries[0], d)[0]
+    signs = torch.tensor([[(i >> 2) & 1, (i >> 1) & 1, i & 1] for i in range(8)], dtype=torch.float64) * 2 - 1
+    corners = off + (signs * ct.geometries[0].get_half_lengths()) @ rot.t()
+    best = torch.topk(corners @ d[0], 4).values
+    assert torch.allclose(torch.sort(pts @ d[0]).values, torch.sort(best).values, atol=1e-15)
+    elbow = open(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow.urdf')).read()
+    p = tmp_path / 'rotated.urdf'
+    p.write_text(elbow.replace('<origin xyz="0.035 0 0" rpy="0 0 0"/>\n      <geometry>', '<origin xyz="0.035 0 0" rpy="0.1 0 0"/>\n      <geometry>', 1))
+    assert 'rpy="0.1 0 0"' in p.read_text()
     with pytest.raises(NotImplementedError):
         SystemSpec.from_urdf(str(p))
     elbow = open(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow.urdf')).read()
