@@ -21,8 +21,18 @@
 
 namespace {
 
-constexpr int kEwSlots = 32;
-constexpr int kEwWarps = 4;
+#ifndef CN_EW_SLOTS
+#define CN_EW_SLOTS 32
+#endif
+#ifndef CN_EW_WARPS
+#define CN_EW_WARPS 4
+#endif
+constexpr int kEwSlots = CN_EW_SLOTS;
+#ifndef CN_EW_PE_MIN
+#define CN_EW_PE_MIN (kEwSlots / 2)
+#endif
+constexpr int kEwPeMin = CN_EW_PE_MIN;     // a PE phase runs once this many slots wait in the done queue
+constexpr int kEwWarps = CN_EW_WARPS;
 constexpr int kEwQin = 64;
 constexpr int kEwNAcc = 32;       // 28 parameter gradients + loss sum + pad
 constexpr int kEwMaxBlocks = 148 * 16;
@@ -130,7 +140,7 @@ elbow_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const 
       if (n_act > 0) phase = 1;
       else if (n_done > 0) phase = 0;
       else break;
-    } else if (n_done >= kEwSlots / 2) phase = 0;
+    } else if (n_done >= kEwPeMin) phase = 0;
     else phase = 1;
 
     if (phase == 2) {
