@@ -749,7 +749,9 @@ def main():
                    'eager_ms_per_step': orders[args.order]['eager_ms_per_step']},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'step': e2e_note, 'chunks': loader.chunks,
-                'host_binding': host_binding},
+                'host_binding': host_binding,
+                # what bounds it: the pinned-memory copy of every step's inputs over this rank's PCIe link
+                'h2d_gb_per_s': h2d / ms_e2e / 1e6},
         'gpu_launches': 3 * orders[args.order]['timed_steps'],   # per step: parameter preparation + loss/backward +
                                                                   # reduce/chain rule(/exchange)
         'roofline': {'bound': 'fp64_cuda_core',
