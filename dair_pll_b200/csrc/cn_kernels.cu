@@ -178,7 +178,18 @@ constexpr int kWfUnrPE = CN_WF_UNR_PE;   // ... and inside the prologue / epilog
 #define CN_WF_MIN_PER_WARP 128
 #endif
 constexpr int kWfMinPerWarp = CN_WF_MIN_PER_WARP;   // fewest samples a warp should get before more warps are used
-constexpr int kWfSlots = 64;
+#ifndef CN_WF_SLOTS
+#define CN_WF_SLOTS 64
+#endif
+#ifndef CN_WF_PE_MIN
+#define CN_WF_PE_MIN 32
+#endif
+#ifndef CN_WF_MIN_BLOCKS
+#define CN_WF_MIN_BLOCKS 1
+#endif
+constexpr int kWfSlots = CN_WF_SLOTS;      // sample slots per warp
+constexpr int kWfPeMin = CN_WF_PE_MIN;     // a PE phase runs once this many slots wait in the done queue
+constexpr int kWfQin = 64;                 // FIFO of triaged samples waiting for a slot (< 32 + 32 entries)
 constexpr int kWfWarps = 4;
 constexpr int kWfFields = 50;   // IW 6 | mcW 3 | rho 12 | q 12 | u 6 | best_res2 1 | d 6 | d0 1 | alpha, lo, hi
 
@@ -187,11 +198,11 @@ template <typename T> struct WfWarpPool {
   int32_t sample[kWfSlots];     // offset of the slot's sample in the warp's range; -1 = empty
   int32_t iters[kWfSlots];
   uint8_t q_act[kWfSlots], q_done[kWfSlots];
-  int32_t q_in[kWfSlots];       // offsets of triaged samples that need the solver, waiting for a slot
+  int32_t q_in[kWfQin];         // offsets of triaged samples that need the solver, waiting for a slot
 };
 
 template <typename T, typename IO, int UNR, bool RACE = false>
-__global__ void __launch_bounds__(kWfWarps * 32)
+__global__ void __launch_bounds__(kWfWarps * 32, CN_WF_MIN_BLOCKS)
 cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const IO* __restrict__ weight,
                     const IO* __restrict__ inertia, const IO* __restrict__ mu, const IO* __restrict__ half, T dt,
                     T eps, int64_t B, IO* __restrict__ loss, IO* __restrict__ force, int32_t* __restrict__ iters,
@@ -270,7 +281,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
       if (n_act > 0) phase = 1;
       else if (n_done > 0) phase = 0;
       else break;
-    } else if (n_done >= 32) phase = 0;
+    } else if (n_done >= kWfPeMin) phase = 0;
     else phase = 1;
 
     if (phase == 2) {
@@ -315,7 +326,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
         }
       }
       const unsigned m_q = __ballot_sync(0xffffffffu, queue);
-      if (queue) pool->q_in[(h_in + n_in + __popc(m_q & lt_mask)) % kWfSlots] = (int32_t)(b - lo);
+      if (queue) pool->q_in[(h_in + n_in + __popc(m_q & lt_mask)) % kWfQin] = (int32_t)(b - lo);
       n_in += __popc(m_q);
       next = dyn_counter ? (first >= B ? B : lo) : next + cnt;
 #ifndef CN_NO_PREFETCH
@@ -385,7 +396,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
         }
         const bool work = pass == 0 ? (on && old >= 0) : (lane < n_new);
         if (work) {
-          const int32_t ent = pass == 0 ? old : pool->q_in[(h_in + lane) % kWfSlots];
+          const int32_t ent = pass == 0 ? old : pool->q_in[(h_in + lane) % kWfQin];
           const int start = race_warp ? (ent >> 28) & 7 : 0;          // (pass 1 of a racing warp: which start point)
           const int64_t b = lo + (race_warp ? (ent & 0x0fffffff) : ent);
           T xs[13], xps[13];
@@ -432,7 +443,7 @@ cube_loss_wf_kernel(const IO* __restrict__ x, const IO* __restrict__ xp, const I
           }
         }
       }
-      h_in = (h_in + n_new) % kWfSlots; n_in -= n_new;
+      h_in = (h_in + n_new) % kWfQin; n_in -= n_new;
       const bool more = next < hi || n_in > 0;             // empty slots are only kept while input remains
       __syncwarp();
       const unsigned m_act = __ballot_sync(0xffffffffu, to_active);
