@@ -1,5 +1,6 @@
-// Generic floating-base serial chain of N rigid links joined by N-1 revolute joints, one box geometry per link against
-// the ground plane: n_q = 7 + (N-1), n_v = 6 + (N-1), 4 N contacts.  SURVEY.md section 8(f) N2, first slice: what the
+// Generic floating-base kinematic TREE of N rigid links joined by N-1 revolute joints (a serial chain or a branching tree:
+// link b > 0 hangs off link par(b) < b), one box geometry per link against the ground plane: n_q = 7 + (N-1),
+// n_v = 6 + (N-1), 4 N contacts.  SURVEY.md section 8(f) N2, first slice: what the
 // reference derives symbolically for ANY plant (multibody_terms.py:114-157 mass matrix / bias forces, :267-319 geometry
 // rotations / translations / spatial Jacobians) evaluated here by recursion over the links instead of per-asset closed
 // forms -- joint frames may be rotated against their parent link (URDF <origin rpy>), inertial frames are rotated on
@@ -9,24 +10,27 @@
 // multibody_learnable_system.py:104-197, forward_dynamics :199-304, top-k support geometry.py:162-202, plane-convex
 // collision :553-582, the cone QP of sappy); same internal coordinates, world twist of link 0 plus the joint rates:
 //   u^ = [w_W0 ; v_W(o_0) ; td_1 .. td_{N-1}] = blkdiag(R_0, I3, I) v_state.
-// Link i:  R_i = R_{i-1} Rfix_i Rot(axis_i, theta_i),  o_i = o_{i-1} + R_{i-1} pJ_i,  a_i = R_{i-1} Rfix_i axis_i,
-//   twist   w_i = w_0 + sum_{j<=i} a_j td_j,   v_i = v_0 + w_0 x o_i + sum_{j<=i} td_j a_j x (o_i - o_j)      (= T_i u^)
-//   bias    al_i = al_{i-1} + (w_{i-1} x a_i) td_i,   be_i = be_{i-1} + al_{i-1} x r_i + w_{i-1} x (w_{i-1} x r_i)
+// Link i with parent p = par(i) (serial chain: p = i - 1) and ancestor joints anc(i) = the joints on the path root -> i:
+//   R_i = R_p Rfix_i Rot(axis_i, theta_i),  o_i = o_p + R_p pJ_i,  a_i = R_p Rfix_i axis_i,
+//   twist   w_i = w_0 + sum_{j in anc(i)} a_j td_j,   v_i = v_0 + w_0 x o_i + sum_{j in anc(i)} td_j a_j x (o_i - o_j)   (= T_i u^)
+//   bias    al_i = al_p + (w_p x a_i) td_i,   be_i = be_p + al_p x r_i + w_p x (w_p x r_i),   r_i = o_i - o_p
 //   M^ = sum_i T_i^T M_i T_i,   F^ = sum_i T_i^T (F_i - M_i [al_i ; be_i])      (M_i, F_i as in cn_elbow.cuh)
-// Contact c on link i:  J_c = [-S(rho_c), I3, a_j x (rho_c - o_j) for j <= i, 0 for j > i].
+// Contact c on link i:  J_c = [-S(rho_c), I3, a_j x (rho_c - o_j) for j in anc(i), 0 otherwise].
 // Plain per-thread arrays and loops: this is the general path (one sample per thread), not a tuned one.
 #pragma once
 #include "cn_elbow.cuh"
 
 namespace cn {
 
-constexpr int CH_NKIN = 18;     // per link: [joint origin 3 | joint rpy as rotation matrix 9 | axis 3 | box offset 3]
+constexpr int CH_NKIN = 19;     // per link: [joint origin 3 | joint rpy as rotation matrix 9 | axis 3 | box offset 3 | parent link]
 
 template <typename T, int N> struct ChainParams {
   static constexpr int NV = 6 + N - 1, NC = 4 * N, K = 3 * NC;
   ElbowBody<T> body[N];
   T mu[N], h[N][3], off[N][3];
   T pJ[N][3], Rfix[N][9], axis[N][3];      // entry 0 unused
+  int par[N];                              // parent link (par[b] < b; entry 0 unused)
+  unsigned anc[N];                         // bit j set: joint j (1..N-1) lies on the path from the root to link b
   T dt, eps, inv_eps, grav;
   T dscale[6 + N - 1];
 };
@@ -52,6 +56,11 @@ CN_HD void chain_params_init(ChainParams<T, N>& P, const T* inertia, const T* mu
     const T* kn = kin + CH_NKIN * b;
     for (int i = 0; i < 3; ++i) { P.h[b][i] = half[3 * b + i]; P.pJ[b][i] = kn[i]; P.axis[b][i] = kn[12 + i]; P.off[b][i] = kn[15 + i]; }
     for (int i = 0; i < 9; ++i) P.Rfix[b][i] = kn[3 + i];
+    // parent index travels as a number in the table; clamped to [0, b - 1] so that a bad table cannot index out of range
+    int pb = b > 0 ? (int)to_double(kn[18]) : 0;
+    pb = pb < 0 ? 0 : (pb > b - 1 ? (b > 0 ? b - 1 : 0) : pb);
+    P.par[b] = pb;
+    P.anc[b] = b > 0 ? (P.anc[pb] | (1u << b)) : 0u;
     msum += B.m;
     for (int i = 0; i < 3; ++i) Isum[i] += B.Io[i];
   }
@@ -63,19 +72,22 @@ CN_HD void chain_params_init(ChainParams<T, N>& P, const T* inertia, const T* mu
 template <typename T, int N> struct ChainKin {
   T R[N][9], o[N][3], a[N][3];      // world rotations, origins relative to o_0, joint axes (a[0] unused)
   uint32_t sel[N];
+  unsigned anc[N];                  // copy of ChainParams::anc (the twist maps below take only the kinematics)
 };
 
 template <typename T, int N> CN_HD void chain_kinematics(const ChainParams<T, N>& P, const T* q, ChainKin<T, N>& K) {
   quat_to_rot(q, K.R[0]);
   for (int i = 0; i < 3; ++i) { K.o[0][i] = T(0); K.a[0][i] = T(0); }
+  for (int b = 0; b < N; ++b) K.anc[b] = P.anc[b];
   for (int b = 1; b < N; ++b) {
     T Rjf[9], Rj[9], r[3];
-    mat3_mul(K.R[b - 1], P.Rfix[b], Rjf);
+    const int p = P.par[b];
+    mat3_mul(K.R[p], P.Rfix[b], Rjf);
     rot3(Rjf, P.axis[b], K.a[b]);
     axis_angle_rot(P.axis[b], q[6 + b], Rj);
     mat3_mul(Rjf, Rj, K.R[b]);
-    rot3(K.R[b - 1], P.pJ[b], r);
-    for (int i = 0; i < 3; ++i) K.o[b][i] = K.o[b - 1][i] + r[i];
+    rot3(K.R[p], P.pJ[b], r);
+    for (int i = 0; i < 3; ++i) K.o[b][i] = K.o[p][i] + r[i];
   }
 }
 
@@ -85,6 +97,7 @@ template <typename T, int N> CN_HD void chain_T(const ChainKin<T, N>& K, int b, 
   cross3(u, K.o[b], wxo);
   for (int i = 0; i < 3; ++i) { V[i] = u[i]; V[3 + i] = u[3 + i] + wxo[i]; }
   for (int j = 1; j <= b; ++j) {
+    if (!((K.anc[b] >> j) & 1u)) continue;
     T d[3], axd[3];
     for (int i = 0; i < 3; ++i) d[i] = K.o[b][i] - K.o[j][i];
     cross3(K.a[j], d, axd);
@@ -98,7 +111,7 @@ template <typename T, int N> CN_HD void chain_Tt(const ChainKin<T, N>& K, int b,
   cross3(K.o[b], W + 3, oxf);
   for (int i = 0; i < 3; ++i) { o[i] = W[i] + oxf[i]; o[3 + i] = W[3 + i]; }
   for (int j = 1; j < N; ++j) {
-    if (j <= b) {
+    if ((K.anc[b] >> j) & 1u) {
       T d[3], axd[3];
       for (int i = 0; i < 3; ++i) d[i] = K.o[b][i] - K.o[j][i];
       cross3(K.a[j], d, axd);
@@ -116,23 +129,26 @@ CN_HD void chain_mass_force(const ChainParams<T, N>& P, const ChainKin<T, N>& K,
   for (int i = 0; i < NV * NV; ++i) M[i] = T(0);
   for (int i = 0; i < NV; ++i) F[i] = T(0);
   const T g[3] = {T(0), T(0), -P.grav};
-  T wprev[3] = {T(0), T(0), T(0)}, al[3] = {T(0), T(0), T(0)}, be[3] = {T(0), T(0), T(0)};
+  T wl[N][3], all[N][3], bel[N][3];       // per link: angular velocity, velocity-product accelerations
   for (int b = 0; b < N; ++b) {
     const ElbowBody<T>& B = P.body[b];
     T Mi[36], cW[3], V[6], bias[6];
     body_mass_world(B, K.R[b], Mi, cW);
     chain_T<T, N>(K, b, uW, V);
     if (b > 0) {
-      // al_b = al_{b-1} + (w_{b-1} x a_b) td_b ;  be_b = be_{b-1} + al_{b-1} x r_b + w_{b-1} x (w_{b-1} x r_b)
+      // al_b = al_p + (w_p x a_b) td_b ;  be_b = be_p + al_p x r_b + w_p x (w_p x r_b),  p = parent of b
+      const int p = P.par[b];
       T r[3], wxa[3], alxr[3], wxr[3], wwr[3];
-      for (int i = 0; i < 3; ++i) r[i] = K.o[b][i] - K.o[b - 1][i];
-      cross3(wprev, K.a[b], wxa);
-      cross3(al, r, alxr);
-      cross3(wprev, r, wxr); cross3(wprev, wxr, wwr);
-      for (int i = 0; i < 3; ++i) { be[i] += alxr[i] + wwr[i]; }
-      for (int i = 0; i < 3; ++i) { al[i] += wxa[i] * uW[5 + b]; }
+      for (int i = 0; i < 3; ++i) r[i] = K.o[b][i] - K.o[p][i];
+      cross3(wl[p], K.a[b], wxa);
+      cross3(all[p], r, alxr);
+      cross3(wl[p], r, wxr); cross3(wl[p], wxr, wwr);
+      for (int i = 0; i < 3; ++i) { bel[b][i] = bel[p][i] + alxr[i] + wwr[i]; }
+      for (int i = 0; i < 3; ++i) { all[b][i] = all[p][i] + wxa[i] * uW[5 + b]; }
+    } else {
+      for (int i = 0; i < 3; ++i) { all[0][i] = T(0); bel[0][i] = T(0); }
     }
-    for (int i = 0; i < 3; ++i) { bias[i] = al[i]; bias[3 + i] = be[i]; wprev[i] = V[i]; }
+    for (int i = 0; i < 3; ++i) { bias[i] = all[b][i]; bias[3 + i] = bel[b][i]; wl[b][i] = V[i]; }
     if (bias_out) for (int i = 0; i < 6; ++i) bias_out[6 * b + i] = bias[i];
     T Iw[3], wIw[3], cg[3], wc[3], wwc[3], Fi[6];
     for (int i = 0; i < 3; ++i) Iw[i] = Mi[6 * i] * V[0] + Mi[6 * i + 1] * V[1] + Mi[6 * i + 2] * V[2];
@@ -184,7 +200,7 @@ CN_HD void chain_contacts(const ChainParams<T, N>& P, ChainKin<T, N>& K, ChainPr
       for (int i = 0; i < 3; ++i) S.rho[3 * cc + i] = K.o[b][i] + r[i];
       for (int j = 1; j < N; ++j) {
         T hcol[3] = {T(0), T(0), T(0)};
-        if (j <= b) {
+        if ((K.anc[b] >> j) & 1u) {
           T dd[3];
           for (int i = 0; i < 3; ++i) dd[i] = S.rho[3 * cc + i] - K.o[j][i];
           cross3(K.a[j], dd, hcol);

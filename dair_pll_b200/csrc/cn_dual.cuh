@@ -53,6 +53,7 @@ CN_DUAL_TPL CN_HD CN_D sqrt(const CN_D& a) {
   for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * k;
   return r;
 }
+CN_DUAL_TPL CN_HD double to_double(const CN_D& a) { return to_double(a.v); }
 CN_DUAL_TPL CN_HD CN_D fabs(const CN_D& a) { return a.v < B(0) ? -a : a; }
 CN_DUAL_TPL CN_HD CN_D sin(const CN_D& a) { CN_D r; r.v = ::sin(a.v); const B c = ::cos(a.v); for (int i = 0; i < N; ++i) r.d[i] = c * a.d[i]; return r; }
 CN_DUAL_TPL CN_HD CN_D cos(const CN_D& a) { CN_D r; r.v = ::cos(a.v); const B s = -::sin(a.v); for (int i = 0; i < N; ++i) r.d[i] = s * a.d[i]; return r; }

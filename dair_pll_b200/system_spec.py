@@ -105,7 +105,7 @@ def _rpy_matrix(rpy) -> torch.Tensor:
 
 @dataclass
 class SystemSpec:
-    kind: str                                   # 'cube' (1 floating body) | 'elbow' (+1 hinge) | 'chain' (generic serial chain)
+    kind: str                                   # 'cube' (1 floating body) | 'elbow' (+1 hinge) | 'chain' (generic tree, <= 4 links)
     bodies: List[BodySpec]
     joints: List[JointSpec]
     geometries: List[GeometrySpec]              # body geometries first, ground last
@@ -202,18 +202,22 @@ class SystemSpec:
                                     names.index(joint.find('child').get('link')),
                                     _floats(jo.get('xyz') if jo is not None else None, 3),
                                     tuple(a / norm for a in ax), jrpy))  # Drake normalises the axis on parsing
-        serial = len(joints) == len(bodies) - 1 and all(j.parent == k and j.child == k + 1 for k, j in enumerate(joints))
+        # a kinematic tree listed root first: joint k's child is link k + 1 (so joint order = link order, which is also the
+        # order of the joint coordinates in the state) and its parent is any earlier link
+        tree = len(joints) == len(bodies) - 1 and all(j.child == k + 1 and 0 <= j.parent <= k for k, j in enumerate(joints))
+        serial = tree and all(j.parent == k for k, j in enumerate(joints))
         rotated = any(any(abs(a) > 0 for a in j.rpy) for j in joints)
         if len(bodies) == 1 and not joints:
             kind = 'cube'
         elif len(bodies) == 2 and serial and not rotated:
             kind = 'elbow'                      # the specialised two-body kernels
-        elif 2 <= len(bodies) <= 4 and serial:
-            kind = 'chain'                      # generic serial chain (csrc/cn_chain.cuh): rotated joint frames allowed
+        elif 2 <= len(bodies) <= 4 and tree:
+            kind = 'chain'                      # generic tree (csrc/cn_chain.cuh): serial or branching, rotated joint frames
         else:
             raise NotImplementedError(
-                'kernels cover a single floating body, a floating body with one revolute child, and serial chains of '
-                'up to 4 links listed base to tip; branching trees need the symbolic path (SURVEY.md section 8(f) N2)')
+                'kernels cover a single floating body, a floating body with one revolute child, and kinematic trees of up '
+                'to 4 links joined by revolute joints, links listed root first with joint k leading to link k + 1; larger '
+                'trees need the symbolic path (SURVEY.md section 8(f) N2)')
         if kind == 'cube':
             if len(geometries) != 1:
                 raise NotImplementedError('the single-body kernels take exactly one collision geometry')

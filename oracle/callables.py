@@ -142,6 +142,16 @@ CHAIN3_TREE = TreeSpec(parent=[-1, 0, 1],
                        joint_rpy=[(0., 0., 0.), (0., 0., 0.), (0.3, -0.2, 0.5)])
 
 
+# a branching four-link tree: links 1 and 2 hang off the root, link 3 off link 2 (rotated joint frames on two joints); tests
+# of the generic tree kernels, not a reference asset
+TREE4_TREE = TreeSpec(parent=[-1, 0, 0, 2],
+                      joint_origin=[(0., 0., 0.), (-0.035, 0.06, 0.), (0.05, -0.04, 0.01), (0.06, 0.0, -0.015)],
+                      axis=[(0., 0., 1.), (0., 1., 0.), (1., 0., 0.), (0.6, 0., 0.8)],
+                      geometry_body=[0, 1, 2, 3, -1],
+                      geometry_offset=[(0., 0., 0.), (0.035, 0., 0.), (0.0, -0.03, 0.), (0.03, -0.01, 0.), (0., 0., 0.)],
+                      joint_rpy=[(0., 0., 0.), (0., 0., 0.), (0.2, 0.1, -0.3), (0.3, -0.2, 0.5)])
+
+
 class TreeCallables:
     """The five callables for a :class:`TreeSpec` (see module docstring)."""
 

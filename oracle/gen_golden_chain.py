@@ -1,6 +1,7 @@
-"""ORACLE (test infrastructure).  Writes tests/golden/chain3.npz by running the REFERENCE's own ``contactnets_loss`` /
-``sim_step`` (through oracle/ref_shim.py) for a three-link floating chain (oracle/callables.py:CHAIN3_TREE: off-axis
-second joint with a rotated joint frame, one box per link) -- the fixture of the generic chain kernels (SURVEY.md 8(f)
+"""ORACLE (test infrastructure).  Writes tests/golden/chain3.npz and tests/golden/tree4.npz by running the REFERENCE's own
+``contactnets_loss`` / ``sim_step`` (through oracle/ref_shim.py) for a three-link floating chain (oracle/callables.py:
+CHAIN3_TREE: off-axis second joint with a rotated joint frame, one box per link) and for a BRANCHING four-link tree
+(TREE4_TREE: two links off the root, a third off one of them) -- the fixtures of the generic tree kernels (SURVEY.md 8(f)
 N2).  Needs /root/reference: build container only; the fixture is committed.
 
     python -m oracle.gen_golden_chain
@@ -18,76 +19,81 @@ sys.path.insert(0, ROOT)
 warnings.filterwarnings('ignore')
 
 from oracle import ref_shim  # noqa: E402
-from oracle.callables import CHAIN3_TREE, TreeCallables  # noqa: E402
+from oracle.callables import CHAIN3_TREE, TREE4_TREE, TreeCallables  # noqa: E402
 
 DT = 0.0068
 HALF = np.array([[0.05, 0.025, 0.025], [0.045, 0.03, 0.02], [0.03, 0.02, 0.035]])
 
 
-def lowest_corner(calls, q):
+HALF4 = np.array([[0.05, 0.025, 0.025], [0.045, 0.03, 0.02], [0.03, 0.035, 0.02], [0.03, 0.02, 0.035]])
+
+
+def lowest_corner(calls, q, half=HALF):
     """z of the lowest box corner of any link at the configuration q (with its stored position)."""
     R = calls.geometry_rotations(q)
     p = calls.geometry_translations(q)
     low = []
-    for g in range(3):
-        ext = (R[:, g, 2, :].abs() * torch.from_numpy(HALF[g])).sum(-1)
+    for g in range(len(half)):
+        ext = (R[:, g, 2, :].abs() * torch.from_numpy(half[g])).sum(-1)
         low.append(p[:, g, 2] - ext)
     return torch.stack(low, -1).min(-1).values
 
 
-def states(n, seed, calls):
+def states(n, seed, calls, half=HALF):
+    nj = len(half) - 1
     g = torch.Generator().manual_seed(seed)
     quat = torch.randn(n, 4, generator=g, dtype=torch.float64)
     quat = quat / quat.norm(dim=-1, keepdim=True)
     xy = torch.rand(n, 2, generator=g, dtype=torch.float64) - 0.5
-    th = (2 * torch.rand(n, 2, generator=g, dtype=torch.float64) - 1) * 2.5
+    th = (2 * torch.rand(n, nj, generator=g, dtype=torch.float64) - 1) * 2.5
     q = torch.cat((quat, xy, torch.zeros(n, 1, dtype=torch.float64), th), -1)
     near = torch.rand(n, generator=g, dtype=torch.float64) < 0.7
     u = torch.rand(n, generator=g, dtype=torch.float64)
     delta = torch.where(near, -0.004 + 0.01 * u, 0.01 + 0.1 * u)
-    q[:, 6] = -lowest_corner(calls, q) + delta
+    q[:, 6] = -lowest_corner(calls, q, half) + delta
     omega = 4.0 * torch.randn(n, 3, generator=g, dtype=torch.float64)
     vel = 0.7 * torch.randn(n, 3, generator=g, dtype=torch.float64)
-    rate = 5.0 * torch.randn(n, 2, generator=g, dtype=torch.float64)
+    rate = 5.0 * torch.randn(n, nj, generator=g, dtype=torch.float64)
     return torch.cat((q, omega, vel, rate), -1)
 
 
-def main():
-    ref_shim.import_reference()
-    calls = TreeCallables(CHAIN3_TREE)
+def make(tree, half, coms, friction, name, n, m):
+    calls = TreeCallables(tree)
+    nb = len(half)
     gen = torch.Generator().manual_seed(7)
     rows = []
-    for com0 in ((0., 0., 0.), (0.035, 0., 0.), (0.03, -0.01, 0.)):
-        m = 0.3 + 0.1 * torch.rand(1, generator=gen, dtype=torch.float64)
+    for com0 in coms:
+        mass = 0.3 + 0.1 * torch.rand(1, generator=gen, dtype=torch.float64)
         c = torch.tensor(com0, dtype=torch.float64) + 0.004 * (2 * torch.rand(3, generator=gen, dtype=torch.float64) - 1)
         diag = 6e-4 * (1 + 0.2 * (2 * torch.rand(3, generator=gen, dtype=torch.float64) - 1))
         offd = 2e-5 * (2 * torch.rand(3, generator=gen, dtype=torch.float64) - 1)
-        rows.append(torch.cat((m, m * c, diag, offd)))
+        rows.append(torch.cat((mass, mass * c, diag, offd)))
     pi_cm = torch.stack(rows)
-    friction = torch.tensor([0.3, 0.45, 0.25, 0.9], dtype=torch.float64)
-    system = ref_shim.build_reference_system(CHAIN3_TREE, DT, pi_cm, friction, [h.tolist() for h in HALF])
-    n = 256
-    x = states(n, 11, calls)
+    friction = torch.tensor(friction, dtype=torch.float64)
+    system = ref_shim.build_reference_system(tree, DT, pi_cm, friction, [h.tolist() for h in half])
+    x = states(n, 11, calls, half)
+    nx = x.shape[1]
+    nq = 7 + nb - 1
     with torch.no_grad():
         nxt, _ = system.integrator.step(x, torch.zeros(n, 1))
     x_plus = nxt.clone()
-    x_plus[:, 9:] += 0.02 * torch.randn(n, 8, generator=torch.Generator().manual_seed(12), dtype=torch.float64)
+    x_plus[:, nq:] += 0.02 * torch.randn(n, nx - nq, generator=torch.Generator().manual_seed(12), dtype=torch.float64)
     loss = system.contactnets_loss(x, torch.zeros(n, 0), x_plus)
     loss.mean().backward()
     mt = system.multibody_terms
     out = dict(dt=np.array(DT), x=x.numpy(), x_plus=x_plus.numpy(), x_next=nxt.numpy(), pi_cm=pi_cm.numpy(),
                theta=mt.lagrangian_terms.inertial_parameters.detach().numpy(), friction_params=friction.numpy(),
-               half_lengths=HALF, loss=loss.detach().numpy(),
+               half_lengths=half, loss=loss.detach().numpy(),
                grad_theta=mt.lagrangian_terms.inertial_parameters.grad.numpy(),
                grad_friction=mt.contact_terms.friction_params.grad.numpy(),
-               grad_length=np.stack([mt.contact_terms.geometries[i].length_params.grad.numpy().reshape(3) for i in range(3)]))
+               grad_length=np.stack([mt.contact_terms.geometries[i].length_params.grad.numpy().reshape(3) for i in range(nb)]))
     # prediction-loss path: 3-step rollout by the reference's own integrator, weighted sum of the states, autograd through
     # every step's QP -> gradients of theta, friction, box lengths and the initial state
     for q in system.parameters():
         q.grad = None
-    m, steps = 24, 3
+    steps = 3
     x0 = x[:m].clone().requires_grad_()
-    w = torch.randn(m, steps, 17, generator=torch.Generator().manual_seed(13), dtype=torch.float64)
+    w = torch.randn(m, steps, nx, generator=torch.Generator().manual_seed(13), dtype=torch.float64)
     xs, cur = [], x0
     for _ in range(steps):
         cur, _ = system.integrator.step(cur, torch.zeros(m, 1))
@@ -98,10 +104,17 @@ def main():
                roll_grad_theta=mt.lagrangian_terms.inertial_parameters.grad.numpy(),
                roll_grad_friction=mt.contact_terms.friction_params.grad.numpy(),
                roll_grad_length=np.stack([mt.contact_terms.geometries[i].length_params.grad.numpy().reshape(3)
-                                          for i in range(3)]))
-    path = os.path.join(ROOT, 'tests', 'golden', 'chain3.npz')
+                                          for i in range(nb)]))
+    path = os.path.join(ROOT, 'tests', 'golden', f'{name}.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, 'mean loss', float(loss.mean()))
+
+
+def main():
+    ref_shim.import_reference()
+    make(CHAIN3_TREE, HALF, ((0., 0., 0.), (0.035, 0., 0.), (0.03, -0.01, 0.)), [0.3, 0.45, 0.25, 0.9], 'chain3', 256, 24)
+    make(TREE4_TREE, HALF4, ((0., 0., 0.), (0.035, 0., 0.), (0.0, -0.03, 0.), (0.03, -0.01, 0.)),
+         [0.3, 0.45, 0.35, 0.25, 0.9], 'tree4', 192, 16)
 
 
 if __name__ == '__main__':

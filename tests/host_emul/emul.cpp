@@ -12,7 +12,7 @@
 #include <vector>
 #include <cstdint>
 using namespace cn;
-// generic serial chain (cn_chain.cuh), N = 2 or 3 links
+// generic kinematic tree (cn_chain.cuh), N = 2 .. 4 links
 template <int N>
 static int chain_loss_emul(const double* x, const double* xp, const double* inertia, const double* mu, const double* half,
                            const double* kin, double dt, double eps, int64_t B, double* loss, double* force, int32_t* iters,
@@ -132,12 +132,14 @@ int emul_chain_loss_f64(int n, const double* x, const double* xp, const double* 
                         int32_t* iters, double* grad) {
   if (n == 2) return chain_loss_emul<2>(x, xp, inertia, mu, half, kin, dt, eps, B, loss, force, iters, grad);
   if (n == 3) return chain_loss_emul<3>(x, xp, inertia, mu, half, kin, dt, eps, B, loss, force, iters, grad);
+  if (n == 4) return chain_loss_emul<4>(x, xp, inertia, mu, half, kin, dt, eps, B, loss, force, iters, grad);
   return -1;
 }
 int emul_chain_step_f64(int n, const double* x, const double* inertia, const double* mu, const double* half,
                         const double* kin, double dt, double eps, int64_t B, double* xn) {
   if (n == 2) return chain_step_emul<2>(x, inertia, mu, half, kin, dt, eps, B, xn);
   if (n == 3) return chain_step_emul<3>(x, inertia, mu, half, kin, dt, eps, B, xn);
+  if (n == 4) return chain_step_emul<4>(x, inertia, mu, half, kin, dt, eps, B, xn);
   return -1;
 }
 // single floating body with witness points (Sphere / Polygon / any plane-convex pair)

@@ -501,13 +501,15 @@ def _chain_system(g, urdf, n):
     return s.to(DEV)
 
 
-def test_generic_chain_three_links_matches_reference_golden(assets_dir):
-    """N2 first slice: a three-link URDF with a rotated, off-axis second joint goes URDF -> SystemSpec -> the generic
-    serial-chain kernels; losses, every parameter gradient and a time step against the reference's own
-    contactnets_loss / sim_step (tests/golden/chain3.npz, oracle/gen_golden_chain.py)."""
-    g = load_golden('chain3')
-    s = _chain_system(g, os.path.join(assets_dir, 'chain3.urdf'), 3)
-    assert s._kind() == 'chain' and s.space.n_x == 17
+@pytest.mark.parametrize('name, n_links', [('chain3', 3), ('tree4', 4)])
+def test_generic_chain_and_tree_match_reference_golden(name, n_links, assets_dir):
+    """N2: a three-link URDF with a rotated, off-axis second joint, and a BRANCHING four-link URDF (two links off the
+    root, a third off one of them), go URDF -> SystemSpec -> the generic tree kernels; losses, every parameter gradient
+    and a time step against the reference's own contactnets_loss / sim_step (tests/golden/{chain3,tree4}.npz,
+    oracle/gen_golden_chain.py)."""
+    g = load_golden(name)
+    s = _chain_system(g, os.path.join(assets_dir, f'{name}.urdf'), n_links)
+    assert s._kind() == 'chain' and s.space.n_x == 13 + 2 * (n_links - 1)
     x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
     loss = s.contactnets_loss(x, None, xp)
     loss.mean().backward()
@@ -551,9 +553,9 @@ def test_generic_chain_two_links_reproduces_the_elbow_kernels(name, assets_dir):
     x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
     s = _chain_system(g, os.path.join(assets_dir, 'elbow.urdf'), 2)
     inertia, mu, half, kin = (t.detach() for t in s._elbow_params(torch.float64, torch.device(DEV)))
-    kin18 = torch.tensor([0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1, *kin[6:9].tolist(),
-                          *kin[0:3].tolist(), 1, 0, 0, 0, 1, 0, 0, 0, 1, *kin[3:6].tolist(), *kin[9:12].tolist()],
-                         dtype=torch.float64, device=DEV)
+    kin18 = torch.tensor([0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1, *kin[6:9].tolist(), 0,
+                          *kin[0:3].tolist(), 1, 0, 0, 0, 1, 0, 0, 0, 1, *kin[3:6].tolist(), *kin[9:12].tolist(), 0],
+                         dtype=torch.float64, device=DEV)      # per link: ... | parent link
     inertia.requires_grad_(); mu.requires_grad_(); half.requires_grad_()
     loss = ops.ChainContactNetsLoss.apply(x, xp, inertia, mu, half, kin18, 2, float(g['dt']), 1e-3)
     loss.sum().backward()
@@ -647,7 +649,7 @@ def test_elbow_support_directions_kernel_matches_the_tensor_formula(assets_dir):
         assert (got - ref).abs().max().item() < 1e-14
 
 
-@pytest.mark.parametrize('name', ['cube', 'elbow', 'chain3'])
+@pytest.mark.parametrize('name', ['cube', 'elbow', 'chain3', 'tree4'])
 def test_leaf_preparation_kernels_match_the_host_parameter_graph(name, assets_dir):
     """dpll_leaf_prepare_f64 / dpll_leaf_backward_f64 (one launch each) against the PyTorch graph they replace --
     theta -> [m, c, I_cm/m] (inertia.py:205-234, 304-331, 376-382), pairwise friction (multibody_terms.py:466-471),

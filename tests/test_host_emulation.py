@@ -472,11 +472,12 @@ def test_witness_point_device_math_matches_reference_golden(name):
 # ---- generic serial chain (cn_chain.cuh) -----------------------------------------------------------
 
 def chain_kin_rows(tree):
-    """(n, 18) kinematic table of dpll_chain_*: [joint origin | fixed rotation row-major | axis | box offset]."""
+    """(n, 19) kinematic table of dpll_chain_*: [joint origin | fixed rotation row-major | axis | box offset | parent]."""
     rows = []
     for b in range(tree.n_bodies):
         Rfix = tree.joint_rotation(b, torch.float64).numpy().reshape(-1) if b > 0 else np.eye(3).reshape(-1)
-        rows.append(np.concatenate((tree.joint_origin[b], Rfix, tree.axis[b], tree.geometry_offset[b])))
+        rows.append(np.concatenate((tree.joint_origin[b], Rfix, tree.axis[b], tree.geometry_offset[b],
+                                    [float(max(tree.parent[b], 0))])))
     return np.ascontiguousarray(np.stack(rows))
 
 
@@ -510,25 +511,29 @@ def emul_chain_loss(n, g, kin, x, xp, eps=1e-3):
     return loss, force, iters, grad
 
 
-def test_chain3_device_math_matches_reference_golden():
-    """Three links, rotated off-axis second joint: loss, parameter gradients and one time step against the REFERENCE's
-    own contactnets_loss / sim_step run on oracle/callables.py:CHAIN3_TREE (oracle/gen_golden_chain.py)."""
-    from oracle.callables import CHAIN3_TREE
-    g = load_golden('chain3')
-    kin = chain_kin_rows(CHAIN3_TREE)
+@pytest.mark.parametrize('name', ['chain3', 'tree4'])
+def test_chain_and_tree_device_math_matches_reference_golden(name):
+    """Three links in series with a rotated off-axis second joint (CHAIN3_TREE) and a BRANCHING four-link tree (TREE4_TREE:
+    two links off the root, a third off one of them): loss, parameter gradients and one time step against the REFERENCE's
+    own contactnets_loss / sim_step run on the oracle's tree callables (oracle/gen_golden_chain.py)."""
+    from oracle.callables import CHAIN3_TREE, TREE4_TREE
+    tree = {'chain3': CHAIN3_TREE, 'tree4': TREE4_TREE}[name]
+    n = tree.n_bodies
+    g = load_golden(name)
+    kin = chain_kin_rows(tree)
     x, xp = np.ascontiguousarray(g['x']), np.ascontiguousarray(g['x_plus'])
     B = x.shape[0]
-    loss, _, iters, grad = emul_chain_loss(3, g, kin, x, xp)
+    loss, _, iters, grad = emul_chain_loss(n, g, kin, x, xp)
     assert np.abs(loss - g['loss']).max() < 1e-12
     assert rel_err(loss, g['loss'], 1e-9).max() < 1e-9
-    gt, gf, gl = chain_grad_to_leaves(g, grad / B, 3)
+    gt, gf, gl = chain_grad_to_leaves(g, grad / B, n)
     assert max_rel_to_scale(gt, g['grad_theta']) < 1e-9
     assert max_rel_to_scale(gf, g['grad_friction']) < 1e-9
     assert max_rel_to_scale(gl, g['grad_length']) < 1e-9
     assert iters.max() <= 60
-    inertia, mu, half = chain_kernel_level_params(g, 3)
+    inertia, mu, half = chain_kernel_level_params(g, n)
     xn = np.zeros_like(x)
-    rc = host_emulation_lib().emul_chain_step_f64(ctypes.c_int(3), dptr(x), dptr(inertia), dptr(mu), dptr(half), dptr(kin),
+    rc = host_emulation_lib().emul_chain_step_f64(ctypes.c_int(n), dptr(x), dptr(inertia), dptr(mu), dptr(half), dptr(kin),
                                                   ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-4),
                                                   ctypes.c_int64(B), dptr(xn))
     assert rc == 0

@@ -305,6 +305,34 @@ def test_urdf_ingestion_rejects_what_the_kernels_do_not_model(tmp_path):
     assert spec.joints[0].axis == (0.0, 1.0, 0.0)
 
 
+def test_branching_tree_spec_and_what_is_still_refused(assets_dir, tmp_path):
+    """N2: a branching four-link tree parses into the 'chain' kind with each link's parent in the kinematic table (equal to
+    the oracle tree's); trees whose links are not listed root first, or with more than four links, are refused."""
+    from oracle.callables import TREE4_TREE
+    from tests.test_host_emulation import chain_kin_rows
+    s = MultibodyLearnableSystem({'tree4': os.path.join(assets_dir, 'tree4.urdf')}, 0.0068)
+    spec = s.multibody_terms.spec
+    assert (spec.kind, spec.n_q, spec.n_v, spec.n_x, spec.n_contacts) == ('chain', 10, 9, 19, 16)
+    assert [j.parent for j in spec.joints] == [0, 0, 2] and [j.child for j in spec.joints] == [1, 2, 3]
+    _, _, _, kin, n = s._chain_params(torch.device('cpu'))
+    assert n == 4 and np.allclose(kin.numpy().reshape(4, 19), chain_kin_rows(TREE4_TREE), rtol=0, atol=1e-15)
+    text = open(os.path.join(assets_dir, 'tree4.urdf')).read()
+    # the joint to link 3 declared before the joint to link 2: joint order would no longer be link order
+    j2 = text[text.index('<joint name="joint_2"'):text.index('<joint name="joint_3"')]
+    j3 = text[text.index('<joint name="joint_3"'):text.index('</robot>')]
+    p = tmp_path / 'reordered.urdf'
+    p.write_text(text.replace(j2 + j3, j3 + j2))
+    with pytest.raises(NotImplementedError):
+        SystemSpec.from_urdf(str(p))
+    # a fifth link
+    link = text[text.index('  <link name="link_3">'):text.index('  <joint name="joint_1"')]
+    p5 = tmp_path / 'five.urdf'
+    p5.write_text(text.replace('</robot>', link.replace('link_3', 'link_4') +
+                               j3.replace('joint_3', 'joint_4').replace('child link="link_3"', 'child link="link_4"') + '</robot>'))
+    with pytest.raises(NotImplementedError):
+        SystemSpec.from_urdf(str(p5))
+
+
 def test_chain_spec_carries_rotated_joint_frames(assets_dir):
     """N2 first slice: a three-link serial chain parses into the 'chain' kind; the kinematic table handed to
     dpll_chain_* (joint origin | fixed joint-frame rotation | axis | box offset per link) equals the one the
@@ -317,7 +345,7 @@ def test_chain_spec_carries_rotated_joint_frames(assets_dir):
     assert spec.collision_pairs == [(3, 0), (3, 1), (3, 2)]
     inertia, mu, half, kin, n = s._chain_params(torch.device('cpu'))
     assert n == 3 and inertia.shape == (30,) and mu.shape == (3,) and half.shape == (9,)
-    assert np.allclose(kin.numpy().reshape(3, 18), chain_kin_rows(CHAIN3_TREE), rtol=0, atol=1e-15)
+    assert np.allclose(kin.numpy().reshape(3, 19), chain_kin_rows(CHAIN3_TREE), rtol=0, atol=1e-15)
     names = [k for k, _ in s.named_parameters()]
     assert 'multibody_terms.contact_terms.geometries.2.length_params' in names
     x = torch.zeros(2, 17, dtype=torch.float64)
