@@ -8,8 +8,8 @@
 namespace {
 
 constexpr int kChThreads = 64;
-constexpr int kChNAcc = 64;                 // 14 N parameter gradients + loss sum (N <= 4: 57)
-constexpr int kChMaxBlocks = 148 * 8;       // partials fit the common workspace (dpll_workspace_bytes)
+constexpr int kChNAcc = 96;                 // 14 N parameter gradients + loss sum (N <= 6: 85)
+constexpr int kChMaxBlocks = 148 * 5;       // partials fit the common workspace (dpll_workspace_bytes)
 
 template <typename T> __device__ __forceinline__ T ch_warp_sum(T v) {
 #pragma unroll
@@ -51,10 +51,10 @@ chain_loss_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __
     if (lane == 0) red[warp][i] = s;
   }
   __syncthreads();
-  if (threadIdx.x <= NP) {
+  for (int i = threadIdx.x; i <= NP; i += kChThreads) {
     T s = T(0);
-    for (int w = 0; w < kChThreads / 32; ++w) s += red[w][threadIdx.x];
-    partials[(int64_t)blockIdx.x * kChNAcc + threadIdx.x] = s;
+    for (int w = 0; w < kChThreads / 32; ++w) s += red[w][i];
+    partials[(int64_t)blockIdx.x * kChNAcc + i] = s;
   }
 }
 
@@ -141,6 +141,10 @@ int dpll_chain_loss_f64(int32_t n_links, const double* x, const double* x_plus, 
                                         loss_sum, workspace, workspace_bytes, st);
     case 3: return launch_chain_loss<3>(x, x_plus, weight, inertia, mu_pair, half, kin, dt, eps, B, loss, force, iters, grad,
                                         loss_sum, workspace, workspace_bytes, st);
+    case 5: return launch_chain_loss<5>(x, x_plus, weight, inertia, mu_pair, half, kin, dt, eps, B, loss, force, iters, grad,
+                                        loss_sum, workspace, workspace_bytes, st);
+    case 6: return launch_chain_loss<6>(x, x_plus, weight, inertia, mu_pair, half, kin, dt, eps, B, loss, force, iters, grad,
+                                        loss_sum, workspace, workspace_bytes, st);
     case 4: return launch_chain_loss<4>(x, x_plus, weight, inertia, mu_pair, half, kin, dt, eps, B, loss, force, iters, grad,
                                         loss_sum, workspace, workspace_bytes, st);
     default: return DPLL_EINVAL;
@@ -158,6 +162,8 @@ int dpll_chain_rollout_f64(int32_t n_links, const double* x0, const double* iner
     case 2: return launch_chain_rollout<2>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, st);
     case 3: return launch_chain_rollout<3>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, st);
     case 4: return launch_chain_rollout<4>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, st);
+    case 5: return launch_chain_rollout<5>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, st);
+    case 6: return launch_chain_rollout<6>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, st);
     default: return DPLL_EINVAL;
   }
 }

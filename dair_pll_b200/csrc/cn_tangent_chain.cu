@@ -49,6 +49,8 @@ int dpll_chain_rollout_grad_f64(int32_t n_links, const double* x0, const double*
     case 2: return launch<2>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, xbar, gparams, gx0, st);
     case 3: return launch<3>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, xbar, gparams, gx0, st);
     case 4: return launch<4>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, xbar, gparams, gx0, st);
+    case 5: return launch<5>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, xbar, gparams, gx0, st);
+    case 6: return launch<6>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, xbar, gparams, gx0, st);
     default: return DPLL_EINVAL;
   }
 }

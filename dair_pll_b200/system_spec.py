@@ -105,7 +105,7 @@ def _rpy_matrix(rpy) -> torch.Tensor:
 
 @dataclass
 class SystemSpec:
-    kind: str                                   # 'cube' (1 floating body) | 'elbow' (+1 hinge) | 'chain' (generic tree, <= 4 links)
+    kind: str                                   # 'cube' (1 floating body) | 'elbow' (+1 hinge) | 'chain' (generic tree, <= 6 links)
     bodies: List[BodySpec]
     joints: List[JointSpec]
     geometries: List[GeometrySpec]              # body geometries first, ground last
@@ -211,12 +211,12 @@ class SystemSpec:
             kind = 'cube'
         elif len(bodies) == 2 and serial and not rotated:
             kind = 'elbow'                      # the specialised two-body kernels
-        elif 2 <= len(bodies) <= 4 and tree:
+        elif 2 <= len(bodies) <= 6 and tree:
             kind = 'chain'                      # generic tree (csrc/cn_chain.cuh): serial or branching, rotated joint frames
         else:
             raise NotImplementedError(
                 'kernels cover a single floating body, a floating body with one revolute child, and kinematic trees of up '
-                'to 4 links joined by revolute joints, links listed root first with joint k leading to link k + 1; larger '
+                'to 6 links joined by revolute joints, links listed root first with joint k leading to link k + 1; larger '
                 'trees need the symbolic path (SURVEY.md section 8(f) N2)')
         if kind == 'cube':
             if len(geometries) != 1:

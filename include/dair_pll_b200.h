@@ -444,7 +444,7 @@ int dpll_elbow_rollout_f32(const float* x0, const float* inertia, const float* m
                            void* stream);
 
 /*
- * Generic floating-base kinematic tree: n_links = 2..4 rigid links joined by revolute
+ * Generic floating-base kinematic tree: n_links = 2..6 rigid links joined by revolute
  * joints -- a serial chain or a branching tree, link b > 0 hanging off any link parent(b) < b -- one box per link
  * against the ground: what the reference derives symbolically for any plant
  * (multibody_terms.py:114-157, 267-319) evaluated by recursion over the links (csrc/cn_chain.cuh), for models the

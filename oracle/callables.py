@@ -152,6 +152,18 @@ TREE4_TREE = TreeSpec(parent=[-1, 0, 0, 2],
                       joint_rpy=[(0., 0., 0.), (0., 0., 0.), (0.2, 0.1, -0.3), (0.3, -0.2, 0.5)])
 
 
+# a six-link tree: three limbs off the root, two of them with a second segment (tests of the generic tree kernels at their
+# largest instantiation; not a reference asset)
+TREE6_TREE = TreeSpec(parent=[-1, 0, 0, 0, 1, 3],
+                      joint_origin=[(0., 0., 0.), (0.05, 0.04, 0.), (-0.05, 0.04, 0.), (0.0, -0.05, 0.01),
+                                    (0.06, 0.0, -0.01), (0.0, -0.06, 0.0)],
+                      axis=[(0., 0., 1.), (0., 1., 0.), (1., 0., 0.), (0., 0., 1.), (0.6, 0., 0.8), (0., 1., 0.)],
+                      geometry_body=[0, 1, 2, 3, 4, 5, -1],
+                      geometry_offset=[(0., 0., 0.), (0.03, 0., 0.), (-0.03, 0., 0.), (0., -0.03, 0.), (0.03, -0.01, 0.),
+                                       (0., -0.03, 0.01), (0., 0., 0.)],
+                      joint_rpy=[(0., 0., 0.), (0., 0., 0.3), (0.2, 0.1, -0.3), (0., 0., 0.), (0.3, -0.2, 0.5), (0.1, 0., 0.)])
+
+
 class TreeCallables:
     """The five callables for a :class:`TreeSpec` (see module docstring)."""
 

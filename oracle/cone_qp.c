@@ -34,7 +34,7 @@
 #include <omp.h>
 #endif
 
-#define MAXC 16
+#define MAXC 24
 #define MAXV 12
 #define MAXK (3 * MAXC)
 

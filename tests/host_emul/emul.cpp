@@ -12,7 +12,7 @@
 #include <vector>
 #include <cstdint>
 using namespace cn;
-// generic kinematic tree (cn_chain.cuh), N = 2 .. 4 links
+// generic kinematic tree (cn_chain.cuh), N = 2 .. 6 links
 template <int N>
 static int chain_loss_emul(const double* x, const double* xp, const double* inertia, const double* mu, const double* half,
                            const double* kin, double dt, double eps, int64_t B, double* loss, double* force, int32_t* iters,
@@ -133,6 +133,8 @@ int emul_chain_loss_f64(int n, const double* x, const double* xp, const double* 
   if (n == 2) return chain_loss_emul<2>(x, xp, inertia, mu, half, kin, dt, eps, B, loss, force, iters, grad);
   if (n == 3) return chain_loss_emul<3>(x, xp, inertia, mu, half, kin, dt, eps, B, loss, force, iters, grad);
   if (n == 4) return chain_loss_emul<4>(x, xp, inertia, mu, half, kin, dt, eps, B, loss, force, iters, grad);
+  if (n == 5) return chain_loss_emul<5>(x, xp, inertia, mu, half, kin, dt, eps, B, loss, force, iters, grad);
+  if (n == 6) return chain_loss_emul<6>(x, xp, inertia, mu, half, kin, dt, eps, B, loss, force, iters, grad);
   return -1;
 }
 int emul_chain_step_f64(int n, const double* x, const double* inertia, const double* mu, const double* half,
@@ -140,6 +142,8 @@ int emul_chain_step_f64(int n, const double* x, const double* inertia, const dou
   if (n == 2) return chain_step_emul<2>(x, inertia, mu, half, kin, dt, eps, B, xn);
   if (n == 3) return chain_step_emul<3>(x, inertia, mu, half, kin, dt, eps, B, xn);
   if (n == 4) return chain_step_emul<4>(x, inertia, mu, half, kin, dt, eps, B, xn);
+  if (n == 5) return chain_step_emul<5>(x, inertia, mu, half, kin, dt, eps, B, xn);
+  if (n == 6) return chain_step_emul<6>(x, inertia, mu, half, kin, dt, eps, B, xn);
   return -1;
 }
 // single floating body with witness points (Sphere / Polygon / any plane-convex pair)

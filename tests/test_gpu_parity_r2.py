@@ -501,7 +501,7 @@ def _chain_system(g, urdf, n):
     return s.to(DEV)
 
 
-@pytest.mark.parametrize('name, n_links', [('chain3', 3), ('tree4', 4)])
+@pytest.mark.parametrize('name, n_links', [('chain3', 3), ('tree4', 4), ('tree6', 6)])
 def test_generic_chain_and_tree_match_reference_golden(name, n_links, assets_dir):
     """N2: a three-link URDF with a rotated, off-axis second joint, and a BRANCHING four-link URDF (two links off the
     root, a third off one of them), go URDF -> SystemSpec -> the generic tree kernels; losses, every parameter gradient
@@ -649,7 +649,7 @@ def test_elbow_support_directions_kernel_matches_the_tensor_formula(assets_dir):
         assert (got - ref).abs().max().item() < 1e-14
 
 
-@pytest.mark.parametrize('name', ['cube', 'elbow', 'chain3', 'tree4'])
+@pytest.mark.parametrize('name', ['cube', 'elbow', 'chain3', 'tree4', 'tree6'])
 def test_leaf_preparation_kernels_match_the_host_parameter_graph(name, assets_dir):
     """dpll_leaf_prepare_f64 / dpll_leaf_backward_f64 (one launch each) against the PyTorch graph they replace --
     theta -> [m, c, I_cm/m] (inertia.py:205-234, 304-331, 376-382), pairwise friction (multibody_terms.py:466-471),

@@ -511,13 +511,14 @@ def emul_chain_loss(n, g, kin, x, xp, eps=1e-3):
     return loss, force, iters, grad
 
 
-@pytest.mark.parametrize('name', ['chain3', 'tree4'])
+@pytest.mark.parametrize('name', ['chain3', 'tree4', 'tree6'])
 def test_chain_and_tree_device_math_matches_reference_golden(name):
     """Three links in series with a rotated off-axis second joint (CHAIN3_TREE) and a BRANCHING four-link tree (TREE4_TREE:
-    two links off the root, a third off one of them): loss, parameter gradients and one time step against the REFERENCE's
+    two links off the root, a third off one of them) and a six-link tree (TREE6_TREE, the largest instantiation): loss,
+    parameter gradients and one time step against the REFERENCE's
     own contactnets_loss / sim_step run on the oracle's tree callables (oracle/gen_golden_chain.py)."""
-    from oracle.callables import CHAIN3_TREE, TREE4_TREE
-    tree = {'chain3': CHAIN3_TREE, 'tree4': TREE4_TREE}[name]
+    from oracle.callables import CHAIN3_TREE, TREE4_TREE, TREE6_TREE
+    tree = {'chain3': CHAIN3_TREE, 'tree4': TREE4_TREE, 'tree6': TREE6_TREE}[name]
     n = tree.n_bodies
     g = load_golden(name)
     kin = chain_kin_rows(tree)

@@ -307,7 +307,7 @@ def test_urdf_ingestion_rejects_what_the_kernels_do_not_model(tmp_path):
 
 def test_branching_tree_spec_and_what_is_still_refused(assets_dir, tmp_path):
     """N2: a branching four-link tree parses into the 'chain' kind with each link's parent in the kinematic table (equal to
-    the oracle tree's); trees whose links are not listed root first, or with more than four links, are refused."""
+    the oracle tree's); trees whose links are not listed root first, or with more than six links, are refused."""
     from oracle.callables import TREE4_TREE
     from tests.test_host_emulation import chain_kin_rows
     s = MultibodyLearnableSystem({'tree4': os.path.join(assets_dir, 'tree4.urdf')}, 0.0068)
@@ -324,11 +324,13 @@ def test_branching_tree_spec_and_what_is_still_refused(assets_dir, tmp_path):
     p.write_text(text.replace(j2 + j3, j3 + j2))
     with pytest.raises(NotImplementedError):
         SystemSpec.from_urdf(str(p))
-    # a fifth link
+    # more links than the largest instantiation (six)
     link = text[text.index('  <link name="link_3">'):text.index('  <joint name="joint_1"')]
     p5 = tmp_path / 'five.urdf'
-    p5.write_text(text.replace('</robot>', link.replace('link_3', 'link_4') +
-                               j3.replace('joint_3', 'joint_4').replace('child link="link_3"', 'child link="link_4"') + '</robot>'))
+    extra = ''.join(link.replace('link_3', f'link_{k}') for k in (4, 5, 6))
+    extra += ''.join(j3.replace('joint_3', f'joint_{k}').replace('child link="link_3"', f'child link="link_{k}"') for k in (4, 5, 6))
+    p5.write_text(text.replace(link, link + extra.split('<joint')[0]).replace('</robot>', '<joint' + '<joint'.join(extra.split('<joint')[1:]) + '</robot>'))
+    assert len(SystemSpec.from_urdf(os.path.join(assets_dir, 'tree6.urdf')).bodies) == 6
     with pytest.raises(NotImplementedError):
         SystemSpec.from_urdf(str(p5))
 
