@@ -22,13 +22,15 @@
 
 namespace cn {
 
-constexpr int CH_NKIN = 19;     // per link: [joint origin 3 | joint rpy as rotation matrix 9 | axis 3 | box offset 3 | parent link]
+constexpr int CH_NKIN = 28;     // per link: [joint origin 3 | joint rpy as rotation matrix 9 | axis 3 | box offset 3 | parent link |
+                                //            rotation link <- collision frame 9]
 
 template <typename T, int N> struct ChainParams {
   static constexpr int NV = 6 + N - 1, NC = 4 * N, K = 3 * NC;
   ElbowBody<T> body[N];
   T mu[N], h[N][3], off[N][3];
   T pJ[N][3], Rfix[N][9], axis[N][3];      // entry 0 unused
+  T Rg[N][9];                              // rotation link frame <- collision (box) frame (URDF <collision><origin rpy>)
   int par[N];                              // parent link (par[b] < b; entry 0 unused)
   unsigned anc[N];                         // bit j set: joint j (1..N-1) lies on the path from the root to link b
   T dt, eps, inv_eps, grav;
@@ -55,7 +57,7 @@ CN_HD void chain_params_init(ChainParams<T, N>& P, const T* inertia, const T* mu
     P.mu[b] = mu[b];
     const T* kn = kin + CH_NKIN * b;
     for (int i = 0; i < 3; ++i) { P.h[b][i] = half[3 * b + i]; P.pJ[b][i] = kn[i]; P.axis[b][i] = kn[12 + i]; P.off[b][i] = kn[15 + i]; }
-    for (int i = 0; i < 9; ++i) P.Rfix[b][i] = kn[3 + i];
+    for (int i = 0; i < 9; ++i) { P.Rfix[b][i] = kn[3 + i]; P.Rg[b][i] = kn[19 + i]; }
     // parent index travels as a number in the table; clamped to [0, b - 1] so that a bad table cannot index out of range
     int pb = b > 0 ? (int)to_double(kn[18]) : 0;
     pb = pb < 0 ? 0 : (pb > b - 1 ? (b > 0 ? b - 1 : 0) : pb);
@@ -190,11 +192,16 @@ template <typename T, int N>
 CN_HD void chain_contacts(const ChainParams<T, N>& P, ChainKin<T, N>& K, ChainProb<T, N>& S) {
   for (int b = 0; b < N; ++b) {
     const T* R = K.R[b];
-    const T d[3] = {-R[6], -R[7], -R[8]};
+    // support direction -R_WG^T e_z in the box's own frame, R_WG = R_link Rg  (geometry.py:560-567)
+    const T dl[3] = {-R[6], -R[7], -R[8]};
+    T d[3];
+    rot3t(P.Rg[b], dl, d);
     K.sel[b] = cube_select_corners(d, P.h[b]);
     for (int c = 0; c < 4; ++c) {
-      T p[3], r[3];
-      for (int k = 0; k < 3; ++k) p[k] = P.off[b][k] + sgn_bit<T>(K.sel[b], c, k) * P.h[b][k];
+      T pg[3], p[3], r[3];
+      for (int k = 0; k < 3; ++k) pg[k] = sgn_bit<T>(K.sel[b], c, k) * P.h[b][k];
+      rot3(P.Rg[b], pg, p);
+      for (int k = 0; k < 3; ++k) p[k] += P.off[b][k];
       rot3(R, p, r);
       const int cc = 4 * b + c;
       for (int i = 0; i < 3; ++i) S.rho[3 * cc + i] = K.o[b][i] + r[i];
@@ -487,8 +494,11 @@ CN_HD T chain_loss_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, c
     rot3t(R, pw, pB);
     const T phic = S.rho[3 * c + 2] + pos_z;
     const T phibar = (phic > T(0) ? fn : (phic < T(0) ? -fn : T(0))) - T(2) * t_max(-phic, T(0));
-    for (int k = 0; k < 3; ++k)
-      grad[11 * N + 3 * bi + k] += sgn_bit<T>(K.sel[bi], cl, k) * (pB[k] + phibar * R[6 + k]);
+    // d loss / d (corner in the link frame), taken back into the box frame: d corner / d h_k = Rg[:, k] sgn_k
+    T gl[3], gg[3];
+    for (int k = 0; k < 3; ++k) gl[k] = pB[k] + phibar * R[6 + k];
+    rot3t(P.Rg[bi], gl, gg);
+    for (int k = 0; k < 3; ++k) grad[11 * N + 3 * bi + k] += sgn_bit<T>(K.sel[bi], cl, k) * gg[k];
   }
   return loss;
 }

@@ -209,8 +209,8 @@ class SystemSpec:
         rotated = any(any(abs(a) > 0 for a in j.rpy) for j in joints)
         if len(bodies) == 1 and not joints:
             kind = 'cube'
-        elif len(bodies) == 2 and serial and not rotated:
-            kind = 'elbow'                      # the specialised two-body kernels
+        elif len(bodies) == 2 and serial and not rotated and not any(any(abs(a) > 0 for a in g.rpy) for g in geometries):
+            kind = 'elbow'                      # the specialised two-body kernels (unrotated joint and collision frames)
         elif 2 <= len(bodies) <= 6 and tree:
             kind = 'chain'                      # generic tree (csrc/cn_chain.cuh): serial or branching, rotated joint frames
         else:
@@ -227,9 +227,6 @@ class SystemSpec:
             # a collision frame that differs from the link frame (offset and / or rotation) is handled through the
             # witness-point kernels: the contact points are support points of the shape, moved into the link frame
         else:
-            if any(any(abs(a) > 0 for a in g.rpy) for g in geometries):
-                raise NotImplementedError('rotated collision frames are supported for a single floating body only '
-                                          '(the multi-link kernels take collision-frame offsets)')
             if [g.body for g in geometries] != list(range(len(bodies))):
                 raise NotImplementedError('the multi-link kernels take one collision geometry per link')
             if kind == 'chain' and any(g.kind != 'box' for g in geometries):

@@ -142,6 +142,13 @@ CHAIN3_TREE = TreeSpec(parent=[-1, 0, 1],
                        joint_rpy=[(0., 0., 0.), (0., 0., 0.), (0.3, -0.2, 0.5)])
 
 
+# CHAIN3_TREE with every box in a collision frame ROTATED against its link (URDF <collision><origin rpy>)
+CHAIN3R_TREE = TreeSpec(parent=CHAIN3_TREE.parent, joint_origin=CHAIN3_TREE.joint_origin, axis=CHAIN3_TREE.axis,
+                        geometry_body=CHAIN3_TREE.geometry_body, geometry_offset=CHAIN3_TREE.geometry_offset,
+                        joint_rpy=CHAIN3_TREE.joint_rpy,
+                        geometry_rpy=[(0.4, 0., 0.), (0.1, -0.3, 0.2), (0., 0.5, -0.4), (0., 0., 0.)])
+
+
 # a branching four-link tree: links 1 and 2 hang off the root, link 3 off link 2 (rotated joint frames on two joints); tests
 # of the generic tree kernels, not a reference asset
 TREE4_TREE = TreeSpec(parent=[-1, 0, 0, 2],

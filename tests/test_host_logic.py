@@ -271,8 +271,9 @@ def test_peer_allreduce_protocol_model():
 
 
 def test_urdf_ingestion_rejects_what_the_kernels_do_not_model(tmp_path):
-    """Models the kernels would silently mis-simulate are refused at construction (a rotated collision frame on a
-    multi-link system); a single floating body's collision frame (offset and rotation) is carried to its geometry and
+    """Models the kernels would silently mis-simulate are refused at construction (a learned geometry in a rotated
+    collision frame); a box's rotated collision frame sends a two-link system to the generic tree kernels; a single
+    floating body's collision frame (offset and rotation) is carried to its geometry and
     equals the oracle tree's; a joint axis is normalised as Drake does on parsing."""
     from dair_pll_b200.geometry import place_in_link_frame
     from dair_pll_b200.system_spec import SystemSpec
@@ -291,12 +292,22 @@ def test_urdf_ingestion_rejects_what_the_kernels_do_not_model(tmp_path):
     corners = off + (signs * ct.geometries[0].get_half_lengths()) @ rot.t()
     best = torch.topk(corners @ d[0], 4).values
     assert torch.allclose(torch.sort(pts @ d[0]).values, torch.sort(best).values, atol=1e-15)
+    # a rotated collision frame on a two-link system: not the specialised elbow kernels but the generic tree kernels
     elbow = open(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow.urdf')).read()
     p = tmp_path / 'rotated.urdf'
     p.write_text(elbow.replace('<origin xyz="0.035 0 0" rpy="0 0 0"/>\n      <geometry>', '<origin xyz="0.035 0 0" rpy="0.1 0 0"/>\n      <geometry>', 1))
     assert 'rpy="0.1 0 0"' in p.read_text()
+    rotated = SystemSpec.from_urdf(str(p))
+    assert rotated.kind == 'chain' and rotated.geometries[1].rpy == (0.1, 0.0, 0.0)
+    assert SystemSpec.from_urdf(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow.urdf')).kind == 'elbow'
+    # ... which take boxes: a learned (mesh) geometry in a rotated collision frame is refused
+    mesh = open(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow_mesh.urdf')).read()
+    assert 'rpy="0 0 0"/>\n      <geometry><mesh' in mesh
+    pm = tmp_path / 'rotated_mesh.urdf'
+    pm.write_text(mesh.replace('rpy="0 0 0"/>\n      <geometry><mesh', 'rpy="0.1 0 0"/>\n      <geometry><mesh', 1)
+                  .replace('elbow_half.obj', os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow_half.obj')))
     with pytest.raises(NotImplementedError):
-        SystemSpec.from_urdf(str(p))
+        SystemSpec.from_urdf(str(pm))
     elbow = open(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow.urdf')).read()
     assert 'xyz="0 1 0"' in elbow
     p2 = tmp_path / 'axis.urdf'
@@ -315,7 +326,7 @@ def test_branching_tree_spec_and_what_is_still_refused(assets_dir, tmp_path):
     assert (spec.kind, spec.n_q, spec.n_v, spec.n_x, spec.n_contacts) == ('chain', 10, 9, 19, 16)
     assert [j.parent for j in spec.joints] == [0, 0, 2] and [j.child for j in spec.joints] == [1, 2, 3]
     _, _, _, kin, n = s._chain_params(torch.device('cpu'))
-    assert n == 4 and np.allclose(kin.numpy().reshape(4, 19), chain_kin_rows(TREE4_TREE), rtol=0, atol=1e-15)
+    assert n == 4 and np.allclose(kin.numpy().reshape(4, 28), chain_kin_rows(TREE4_TREE), rtol=0, atol=1e-15)
     text = open(os.path.join(assets_dir, 'tree4.urdf')).read()
     # the joint to link 3 declared before the joint to link 2: joint order would no longer be link order
     j2 = text[text.index('<joint name="joint_2"'):text.index('<joint name="joint_3"')]
@@ -347,7 +358,7 @@ def test_chain_spec_carries_rotated_joint_frames(assets_dir):
     assert spec.collision_pairs == [(3, 0), (3, 1), (3, 2)]
     inertia, mu, half, kin, n = s._chain_params(torch.device('cpu'))
     assert n == 3 and inertia.shape == (30,) and mu.shape == (3,) and half.shape == (9,)
-    assert np.allclose(kin.numpy().reshape(3, 19), chain_kin_rows(CHAIN3_TREE), rtol=0, atol=1e-15)
+    assert np.allclose(kin.numpy().reshape(3, 28), chain_kin_rows(CHAIN3_TREE), rtol=0, atol=1e-15)
     names = [k for k, _ in s.named_parameters()]
     assert 'multibody_terms.contact_terms.geometries.2.length_params' in names
     x = torch.zeros(2, 17, dtype=torch.float64)
