@@ -390,6 +390,33 @@ def secondary_configs(device, peak_flops):
                                     'measured int8 figure exists)',
                      'note': 'exact fp64 result from int8 digit-plane products; FP64-equivalent work of the replaced GEMMs: '
                              '4.28e6 FLOP per sample'}}
+    # generic kinematic tree (one sample per thread, the general path, not a tuned one): the branching
+    # four-link tree of the tests, its fixture states tiled to 65,536 pairs
+    import numpy as np
+    fx = np.load(os.path.join(ROOT, 'tests', 'golden', 'tree4.npz'))
+    tree = MultibodyLearnableSystem({'tree4': os.path.join(ROOT, 'dair_pll_b200', 'assets', 'tree4.urdf')}, DT)
+    sd = {'multibody_terms.lagrangian_terms.inertial_parameters': torch.from_numpy(fx['theta']),
+          'multibody_terms.contact_terms.friction_params': torch.from_numpy(fx['friction_params'])}
+    for i in range(4):
+        sd[f'multibody_terms.contact_terms.geometries.{i}.length_params'] = torch.from_numpy(fx['half_lengths'][i]).reshape(1, 3)
+    tree.load_state_dict(sd)
+    tree = tree.to(device)
+    Bt = 65536
+    reps = (Bt + fx['x'].shape[0] - 1) // fx['x'].shape[0]
+    xt = torch.from_numpy(fx['x']).to(device).repeat(reps, 1)[:Bt].contiguous()
+    xpt = torch.from_numpy(fx['x_plus']).to(device).repeat(reps, 1)[:Bt].contiguous()
+    params_t = list(tree.parameters())
+
+    def tree_step():
+        for p in params_t:
+            p.grad = None
+        loss = tree.contactnets_loss(xt, None, xpt)
+        loss.mean().backward()
+        return loss.detach()
+    ms = _time_gpu(tree_step, device, 5, warmup=2)
+    out['tree4_loss_backward_B65536_f64'] = {
+        'ms': ms, 'samples_per_s': Bt / ms * 1e3, 'step': 'eager public-API step',
+        'note': 'generic tree kernels (csrc/cn_chain.cuh): four links, 16 contacts, 9 velocities; fixture states tiled'}
     return out
 
 

@@ -16,14 +16,17 @@
 //   bias    al_i = al_p + (w_p x a_i) td_i,   be_i = be_p + al_p x r_i + w_p x (w_p x r_i),   r_i = o_i - o_p
 //   M^ = sum_i T_i^T M_i T_i,   F^ = sum_i T_i^T (F_i - M_i [al_i ; be_i])      (M_i, F_i as in cn_elbow.cuh)
 // Contact c on link i:  J_c = [-S(rho_c), I3, a_j x (rho_c - o_j) for j in anc(i), 0 otherwise].
+// A PRISMATIC joint i (URDF type="prismatic") keeps the joint frame's orientation and slides the child along a_i:
+//   R_i = R_p Rfix_i,  o_i = o_p + R_p pJ_i + a_i q_i;  its column of T and of J_c is [0 ; a_i] (no lever arm);
+//   al_i = al_p,  be_i = be_p + al_p x r_i + w_p x (w_p x r_i) + 2 (w_p x a_i) td_i.
 // Plain per-thread arrays and loops: this is the general path (one sample per thread), not a tuned one.
 #pragma once
 #include "cn_elbow.cuh"
 
 namespace cn {
 
-constexpr int CH_NKIN = 28;     // per link: [joint origin 3 | joint rpy as rotation matrix 9 | axis 3 | box offset 3 | parent link |
-                                //            rotation link <- collision frame 9]
+constexpr int CH_NKIN = 29;     // per link: [joint origin 3 | joint rpy as rotation matrix 9 | axis 3 | box offset 3 | parent link |
+                                //            rotation link <- collision frame 9 | joint type: 0 revolute, 1 prismatic]
 
 template <typename T, int N> struct ChainParams {
   static constexpr int NV = 6 + N - 1, NC = 4 * N, K = 3 * NC;
@@ -33,6 +36,7 @@ template <typename T, int N> struct ChainParams {
   T Rg[N][9];                              // rotation link frame <- collision (box) frame (URDF <collision><origin rpy>)
   int par[N];                              // parent link (par[b] < b; entry 0 unused)
   unsigned anc[N];                         // bit j set: joint j (1..N-1) lies on the path from the root to link b
+  unsigned pris;                           // bit j set: joint j slides along its axis (prismatic) instead of turning
   T dt, eps, inv_eps, grav;
   T dscale[6 + N - 1];
 };
@@ -41,6 +45,7 @@ template <typename T, int N> struct ChainParams {
 template <typename T, int N>
 CN_HD void chain_params_init(ChainParams<T, N>& P, const T* inertia, const T* mu, const T* half, const T* kin, T dt, T eps) {
   T msum = T(0), Isum[3] = {T(0), T(0), T(0)};
+  P.pris = 0u;
   for (int b = 0; b < N; ++b) {
     ElbowBody<T>& B = P.body[b];
     const T* in = inertia + 10 * b;
@@ -63,33 +68,40 @@ CN_HD void chain_params_init(ChainParams<T, N>& P, const T* inertia, const T* mu
     pb = pb < 0 ? 0 : (pb > b - 1 ? (b > 0 ? b - 1 : 0) : pb);
     P.par[b] = pb;
     P.anc[b] = b > 0 ? (P.anc[pb] | (1u << b)) : 0u;
+    if (b > 0 && to_double(kn[28]) > 0.5) P.pris |= 1u << b;
     msum += B.m;
     for (int i = 0; i < 3; ++i) Isum[i] += B.Io[i];
   }
   P.dt = dt; P.eps = eps; P.inv_eps = T(1) / eps; P.grav = T(9.81);
   for (int i = 0; i < 3; ++i) { P.dscale[i] = T(1) / Isum[i]; P.dscale[3 + i] = T(1) / msum; }
-  for (int j = 1; j < N; ++j) P.dscale[5 + j] = T(1) / P.body[j].Io[1];
+  for (int j = 1; j < N; ++j) P.dscale[5 + j] = ((P.pris >> j) & 1u) ? T(1) / P.body[j].m : T(1) / P.body[j].Io[1];
 }
 
 template <typename T, int N> struct ChainKin {
   T R[N][9], o[N][3], a[N][3];      // world rotations, origins relative to o_0, joint axes (a[0] unused)
   uint32_t sel[N];
-  unsigned anc[N];                  // copy of ChainParams::anc (the twist maps below take only the kinematics)
+  unsigned anc[N], pris;            // copies of ChainParams::anc / pris (the twist maps below take only the kinematics)
 };
 
 template <typename T, int N> CN_HD void chain_kinematics(const ChainParams<T, N>& P, const T* q, ChainKin<T, N>& K) {
   quat_to_rot(q, K.R[0]);
   for (int i = 0; i < 3; ++i) { K.o[0][i] = T(0); K.a[0][i] = T(0); }
   for (int b = 0; b < N; ++b) K.anc[b] = P.anc[b];
+  K.pris = P.pris;
   for (int b = 1; b < N; ++b) {
     T Rjf[9], Rj[9], r[3];
     const int p = P.par[b];
     mat3_mul(K.R[p], P.Rfix[b], Rjf);
     rot3(Rjf, P.axis[b], K.a[b]);
-    axis_angle_rot(P.axis[b], q[6 + b], Rj);
-    mat3_mul(Rjf, Rj, K.R[b]);
     rot3(K.R[p], P.pJ[b], r);
-    for (int i = 0; i < 3; ++i) K.o[b][i] = K.o[p][i] + r[i];
+    if ((P.pris >> b) & 1u) {
+      for (int i = 0; i < 9; ++i) K.R[b][i] = Rjf[i];
+      for (int i = 0; i < 3; ++i) K.o[b][i] = K.o[p][i] + r[i] + K.a[b][i] * q[6 + b];
+    } else {
+      axis_angle_rot(P.axis[b], q[6 + b], Rj);
+      mat3_mul(Rjf, Rj, K.R[b]);
+      for (int i = 0; i < 3; ++i) K.o[b][i] = K.o[p][i] + r[i];
+    }
   }
 }
 
@@ -100,6 +112,10 @@ template <typename T, int N> CN_HD void chain_T(const ChainKin<T, N>& K, int b, 
   for (int i = 0; i < 3; ++i) { V[i] = u[i]; V[3 + i] = u[3 + i] + wxo[i]; }
   for (int j = 1; j <= b; ++j) {
     if (!((K.anc[b] >> j) & 1u)) continue;
+    if ((K.pris >> j) & 1u) {
+      for (int i = 0; i < 3; ++i) V[3 + i] += K.a[j][i] * u[5 + j];
+      continue;
+    }
     T d[3], axd[3];
     for (int i = 0; i < 3; ++i) d[i] = K.o[b][i] - K.o[j][i];
     cross3(K.a[j], d, axd);
@@ -113,7 +129,9 @@ template <typename T, int N> CN_HD void chain_Tt(const ChainKin<T, N>& K, int b,
   cross3(K.o[b], W + 3, oxf);
   for (int i = 0; i < 3; ++i) { o[i] = W[i] + oxf[i]; o[3 + i] = W[3 + i]; }
   for (int j = 1; j < N; ++j) {
-    if ((K.anc[b] >> j) & 1u) {
+    if (((K.anc[b] >> j) & 1u) && ((K.pris >> j) & 1u)) {
+      o[5 + j] = dot3(K.a[j], W + 3);
+    } else if ((K.anc[b] >> j) & 1u) {
       T d[3], axd[3];
       for (int i = 0; i < 3; ++i) d[i] = K.o[b][i] - K.o[j][i];
       cross3(K.a[j], d, axd);
@@ -145,8 +163,13 @@ CN_HD void chain_mass_force(const ChainParams<T, N>& P, const ChainKin<T, N>& K,
       cross3(wl[p], K.a[b], wxa);
       cross3(all[p], r, alxr);
       cross3(wl[p], r, wxr); cross3(wl[p], wxr, wwr);
-      for (int i = 0; i < 3; ++i) { bel[b][i] = bel[p][i] + alxr[i] + wwr[i]; }
-      for (int i = 0; i < 3; ++i) { all[b][i] = all[p][i] + wxa[i] * uW[5 + b]; }
+      if ((P.pris >> b) & 1u) {
+        for (int i = 0; i < 3; ++i) { bel[b][i] = bel[p][i] + alxr[i] + wwr[i] + T(2) * wxa[i] * uW[5 + b]; }
+        for (int i = 0; i < 3; ++i) { all[b][i] = all[p][i]; }
+      } else {
+        for (int i = 0; i < 3; ++i) { bel[b][i] = bel[p][i] + alxr[i] + wwr[i]; }
+        for (int i = 0; i < 3; ++i) { all[b][i] = all[p][i] + wxa[i] * uW[5 + b]; }
+      }
     } else {
       for (int i = 0; i < 3; ++i) { all[0][i] = T(0); bel[0][i] = T(0); }
     }
@@ -207,7 +230,9 @@ CN_HD void chain_contacts(const ChainParams<T, N>& P, ChainKin<T, N>& K, ChainPr
       for (int i = 0; i < 3; ++i) S.rho[3 * cc + i] = K.o[b][i] + r[i];
       for (int j = 1; j < N; ++j) {
         T hcol[3] = {T(0), T(0), T(0)};
-        if ((K.anc[b] >> j) & 1u) {
+        if (((K.anc[b] >> j) & 1u) && ((K.pris >> j) & 1u)) {
+          for (int i = 0; i < 3; ++i) hcol[i] = K.a[j][i];
+        } else if ((K.anc[b] >> j) & 1u) {
           T dd[3];
           for (int i = 0; i < 3; ++i) dd[i] = S.rho[3 * cc + i] - K.o[j][i];
           cross3(K.a[j], dd, hcol);

@@ -109,7 +109,7 @@ class MultibodyLearnableSystem(System):
         return inertia.reshape(20), mu.reshape(2), (torch.cat(half) if half else None), kin
 
     def _chain_params(self, device: torch.device):
-        """Generic kinematic tree: (inertia (n*10), mu (n), half (n*3), kin (n*28), n), float64."""
+        """Generic kinematic tree: (inertia (n*10), mu (n), half (n*3), kin (n*29), n), float64."""
         inertia, mu, half = self.multibody_terms.kernel_parameters(torch.float64)
         spec = self.multibody_terms.spec
         n = len(spec.bodies)
@@ -119,12 +119,12 @@ class MultibodyLearnableSystem(System):
             for b in range(n):
                 if b == 0:
                     rows += [0.] * 3 + [1., 0., 0., 0., 1., 0., 0., 0., 1.] + [0., 0., 1.]
-                    parent = 0
+                    parent, sliding = 0, 0.
                 else:
                     j = spec.joints[b - 1]          # joint b - 1 is the one whose child is link b (SystemSpec orders them)
                     rows += [*j.origin, *j.rotation(), *j.axis]
-                    parent = j.parent
-                rows += [*spec.geometries[b].offset, float(parent), *spec.geometries[b].rotation().reshape(-1).tolist()]
+                    parent, sliding = j.parent, float(j.prismatic)
+                rows += [*spec.geometries[b].offset, float(parent), *spec.geometries[b].rotation().reshape(-1).tolist(), sliding]
             self._kin_cache[key] = torch.tensor(rows, dtype=torch.float64, device=device)
         return inertia.reshape(-1), mu.reshape(-1), torch.cat(half), self._kin_cache[key], n
 

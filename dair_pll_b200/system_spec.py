@@ -84,6 +84,7 @@ class JointSpec:
     origin: Tuple[float, float, float]
     axis: Tuple[float, float, float]
     rpy: Tuple[float, float, float] = (0., 0., 0.)        # fixed rotation parent link -> joint frame
+    prismatic: bool = False                               # slides along the axis (URDF type="prismatic") instead of turning
 
     def rotation(self) -> Tuple[float, ...]:
         """Row-major 3x3 of the URDF rotation R = Rz(yaw) Ry(pitch) Rx(roll)."""
@@ -189,7 +190,7 @@ class SystemSpec:
                     raise NotImplementedError('only <box>, <sphere> and <mesh> collision geometries are supported')
         joints = []
         for joint in root.findall('joint'):
-            if joint.get('type') not in ('continuous', 'revolute'):
+            if joint.get('type') not in ('continuous', 'revolute', 'prismatic'):
                 raise NotImplementedError(f'joint type {joint.get("type")}')
             jo = joint.find('origin')
             jrpy = _floats(jo.get('rpy'), 3) if jo is not None else (0., 0., 0.)
@@ -201,7 +202,8 @@ class SystemSpec:
             joints.append(JointSpec(names.index(joint.find('parent').get('link')),
                                     names.index(joint.find('child').get('link')),
                                     _floats(jo.get('xyz') if jo is not None else None, 3),
-                                    tuple(a / norm for a in ax), jrpy))  # Drake normalises the axis on parsing
+                                    tuple(a / norm for a in ax), jrpy,   # Drake normalises the axis on parsing
+                                    joint.get('type') == 'prismatic'))
         # a kinematic tree listed root first: joint k's child is link k + 1 (so joint order = link order, which is also the
         # order of the joint coordinates in the state) and its parent is any earlier link
         tree = len(joints) == len(bodies) - 1 and all(j.child == k + 1 and 0 <= j.parent <= k for k, j in enumerate(joints))
@@ -209,14 +211,15 @@ class SystemSpec:
         rotated = any(any(abs(a) > 0 for a in j.rpy) for j in joints)
         if len(bodies) == 1 and not joints:
             kind = 'cube'
-        elif len(bodies) == 2 and serial and not rotated and not any(any(abs(a) > 0 for a in g.rpy) for g in geometries):
+        elif len(bodies) == 2 and serial and not rotated and not joints[0].prismatic \
+                and not any(any(abs(a) > 0 for a in g.rpy) for g in geometries):
             kind = 'elbow'                      # the specialised two-body kernels (unrotated joint and collision frames)
         elif 2 <= len(bodies) <= 6 and tree:
             kind = 'chain'                      # generic tree (csrc/cn_chain.cuh): serial or branching, rotated joint frames
         else:
             raise NotImplementedError(
                 'kernels cover a single floating body, a floating body with one revolute child, and kinematic trees of up '
-                'to 6 links joined by revolute joints, links listed root first with joint k leading to link k + 1; larger '
+                'to 6 links joined by revolute or prismatic joints, links listed root first with joint k leading to link k + 1; larger '
                 'trees need the symbolic path (SURVEY.md section 8(f) N2)')
         if kind == 'cube':
             if len(geometries) != 1:

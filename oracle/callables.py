@@ -82,6 +82,11 @@ class TreeSpec:
                                                                                 # (URDF <origin rpy>); empty = none
     geometry_rpy: List[Tuple[float, float, float]] = field(default_factory=list)  # fixed rotation link -> collision frame
                                                                                 # (URDF <collision><origin rpy>); empty = none
+    prismatic: List[bool] = field(default_factory=list)    # joint i slides along its axis instead of turning about it
+                                                           # (URDF type="prismatic"); empty = all revolute
+
+    def is_prismatic(self, i: int) -> bool:
+        return bool(self.prismatic) and bool(self.prismatic[i])
 
     def geometry_rotation(self, g: int, dtype) -> Tensor:
         """Fixed rotation of geometry g's collision frame in its link (R = Rz(yaw) Ry(pitch) Rx(roll))."""
@@ -149,6 +154,17 @@ CHAIN3R_TREE = TreeSpec(parent=CHAIN3_TREE.parent, joint_origin=CHAIN3_TREE.join
                         geometry_rpy=[(0.4, 0., 0.), (0.1, -0.3, 0.2), (0., 0.5, -0.4), (0., 0., 0.)])
 
 
+# three links: a hinge, then a SLIDING (prismatic) joint in a rotated joint frame (tests of the prismatic branch of the generic
+# tree kernels and of this module's own prismatic kinematics; not a reference asset)
+SLIDER3_TREE = TreeSpec(parent=[-1, 0, 1],
+                        joint_origin=[(0., 0., 0.), (-0.035, 0.06, 0.), (0.05, 0.01, -0.02)],
+                        axis=[(0., 0., 1.), (0., 1., 0.), (0.6, 0., 0.8)],
+                        geometry_body=[0, 1, 2, -1],
+                        geometry_offset=[(0., 0., 0.), (0.035, 0., 0.), (0.02, -0.01, 0.), (0., 0., 0.)],
+                        joint_rpy=[(0., 0., 0.), (0., 0., 0.), (0.3, -0.2, 0.5)],
+                        prismatic=[False, False, True])
+
+
 # a branching four-link tree: links 1 and 2 hang off the root, link 3 off link 2 (rotated joint frames on two joints); tests
 # of the generic tree kernels, not a reference asset
 TREE4_TREE = TreeSpec(parent=[-1, 0, 0, 2],
@@ -200,6 +216,28 @@ class TreeCallables:
             p = tree.parent[i]
             a = torch.tensor(tree.axis[i], dtype=dt)
             pj = torch.tensor(tree.joint_origin[i], dtype=dt)
+            if tree.is_prismatic(i):
+                # sliding joint: the child keeps the joint frame's orientation and moves by d = q_i along the axis;
+                #   o_i = o_p + R_p (pJ + Rfix a d),  w_i = w_p,  v_i = v_p + w_p x (o_i - o_p) + (R_p Rfix a) d'
+                # velocity-product acceleration of the origin: ... + w_p x (w_p x r) + 2 w_p x (R_p Rfix a) d'
+                Rfix = tree.joint_rotation(i, dt)
+                RjT = Rfix.transpose(-1, -2).expand(batch + (3, 3))
+                e = eye6[5 + i]
+                af = Rfix @ a                                         # axis in the parent link's frame
+                rp = pj + af * q[..., 6 + i][..., None]               # (*, 3) child origin in the parent frame
+                R.append(R[p] @ Rfix)
+                o.append(o[p] + (R[p] @ rp[..., None])[..., 0])
+                Tw.append(RjT @ Tw[p])
+                Tv.append(Tv[p] - R[p] @ skew(rp) @ Tw[p] + (R[p] @ af)[..., None] * e)
+                if v is not None:
+                    rate = v[..., 5 + i]
+                    w_p = om[p]
+                    om.append((RjT @ w_p[..., None])[..., 0])
+                    al.append((RjT @ al[p][..., None])[..., 0])
+                    wxwxr = torch.cross(w_p, torch.cross(w_p, rp, dim=-1), dim=-1)
+                    cor = 2 * rate[..., None] * torch.cross(w_p, af.expand_as(w_p), dim=-1)
+                    be.append(be[p] + (R[p] @ (wxwxr - torch.cross(rp, al[p], dim=-1) + cor)[..., None])[..., 0])
+                continue
             Rj = tree.joint_rotation(i, dt) @ axis_rot(a, q[..., 6 + i])
             RjT = Rj.transpose(-1, -2)
             e = eye6[5 + i]

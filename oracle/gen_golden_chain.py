@@ -1,4 +1,4 @@
-"""ORACLE (test infrastructure).  Writes tests/golden/chain3.npz, chain3r.npz (rotated collision frames), tree4.npz and tree6.npz by running the REFERENCE's own
+"""ORACLE (test infrastructure).  Writes tests/golden/chain3.npz, chain3r.npz (rotated collision frames), slider3.npz (a prismatic joint), tree4.npz and tree6.npz by running the REFERENCE's own
 ``contactnets_loss`` / ``sim_step`` (through oracle/ref_shim.py) for a three-link floating chain (oracle/callables.py:
 CHAIN3_TREE: off-axis second joint with a rotated joint frame, one box per link) and for a BRANCHING four-link tree
 (TREE4_TREE: two links off the root, a third off one of them) and a six-link tree (TREE6_TREE) -- the fixtures of the generic tree kernels (SURVEY.md 8(f)
@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 warnings.filterwarnings('ignore')
 
 from oracle import ref_shim  # noqa: E402
-from oracle.callables import CHAIN3_TREE, CHAIN3R_TREE, TREE4_TREE, TREE6_TREE, TreeCallables  # noqa: E402
+from oracle.callables import CHAIN3_TREE, CHAIN3R_TREE, SLIDER3_TREE, TREE4_TREE, TREE6_TREE, TreeCallables  # noqa: E402
 
 DT = 0.0068
 HALF = np.array([[0.05, 0.025, 0.025], [0.045, 0.03, 0.02], [0.03, 0.02, 0.035]])
@@ -48,6 +48,9 @@ def states(n, seed, calls, half=HALF):
     quat = quat / quat.norm(dim=-1, keepdim=True)
     xy = torch.rand(n, 2, generator=g, dtype=torch.float64) - 0.5
     th = (2 * torch.rand(n, nj, generator=g, dtype=torch.float64) - 1) * 2.5
+    for j in range(nj):
+        if calls.tree.is_prismatic(j + 1):
+            th[:, j] *= 0.02                     # a sliding joint's coordinate is a length (m)
     q = torch.cat((quat, xy, torch.zeros(n, 1, dtype=torch.float64), th), -1)
     near = torch.rand(n, generator=g, dtype=torch.float64) < 0.7
     u = torch.rand(n, generator=g, dtype=torch.float64)
@@ -116,6 +119,7 @@ def main():
     ref_shim.import_reference()
     make(CHAIN3_TREE, HALF, ((0., 0., 0.), (0.035, 0., 0.), (0.03, -0.01, 0.)), [0.3, 0.45, 0.25, 0.9], 'chain3', 256, 24)
     make(CHAIN3R_TREE, HALF, ((0., 0., 0.), (0.035, 0., 0.), (0.03, -0.01, 0.)), [0.3, 0.45, 0.25, 0.9], 'chain3r', 128, 8)
+    make(SLIDER3_TREE, HALF, ((0., 0., 0.), (0.035, 0., 0.), (0.02, -0.01, 0.)), [0.3, 0.45, 0.25, 0.9], 'slider3', 128, 8)
     make(TREE4_TREE, HALF4, ((0., 0., 0.), (0.035, 0., 0.), (0.0, -0.03, 0.), (0.03, -0.01, 0.)),
          [0.3, 0.45, 0.35, 0.25, 0.9], 'tree4', 192, 16)
     make(TREE6_TREE, HALF6, ((0., 0., 0.), (0.03, 0., 0.), (-0.03, 0., 0.), (0., -0.03, 0.), (0.03, -0.01, 0.), (0., -0.03, 0.01)),

@@ -501,7 +501,7 @@ def _chain_system(g, urdf, n):
     return s.to(DEV)
 
 
-@pytest.mark.parametrize('name, n_links', [('chain3', 3), ('chain3r', 3), ('tree4', 4), ('tree6', 6)])
+@pytest.mark.parametrize('name, n_links', [('chain3', 3), ('chain3r', 3), ('slider3', 3), ('tree4', 4), ('tree6', 6)])
 def test_generic_chain_and_tree_match_reference_golden(name, n_links, assets_dir):
     """N2: a three-link URDF with a rotated, off-axis second joint, and a BRANCHING four-link URDF (two links off the
     root, a third off one of them), go URDF -> SystemSpec -> the generic tree kernels; losses, every parameter gradient
@@ -554,9 +554,9 @@ def test_generic_chain_two_links_reproduces_the_elbow_kernels(name, assets_dir):
     s = _chain_system(g, os.path.join(assets_dir, 'elbow.urdf'), 2)
     inertia, mu, half, kin = (t.detach() for t in s._elbow_params(torch.float64, torch.device(DEV)))
     eye = [1, 0, 0, 0, 1, 0, 0, 0, 1]
-    kin18 = torch.tensor([0, 0, 0, *eye, 0, 0, 1, *kin[6:9].tolist(), 0, *eye,
-                          *kin[0:3].tolist(), *eye, *kin[3:6].tolist(), *kin[9:12].tolist(), 0, *eye],
-                         dtype=torch.float64, device=DEV)      # per link: ... | parent link | collision-frame rotation
+    kin18 = torch.tensor([0, 0, 0, *eye, 0, 0, 1, *kin[6:9].tolist(), 0, *eye, 0,
+                          *kin[0:3].tolist(), *eye, *kin[3:6].tolist(), *kin[9:12].tolist(), 0, *eye, 0],
+                         dtype=torch.float64, device=DEV)      # per link: ... | parent link | collision-frame rotation | type
     inertia.requires_grad_(); mu.requires_grad_(); half.requires_grad_()
     loss = ops.ChainContactNetsLoss.apply(x, xp, inertia, mu, half, kin18, 2, float(g['dt']), 1e-3)
     loss.sum().backward()

@@ -472,13 +472,14 @@ def test_witness_point_device_math_matches_reference_golden(name):
 # ---- generic serial chain (cn_chain.cuh) -----------------------------------------------------------
 
 def chain_kin_rows(tree):
-    """(n, 28) kinematic table of dpll_chain_*: [joint origin | fixed rotation row-major | axis | box offset | parent |
-    rotation link <- collision frame row-major]."""
+    """(n, 29) kinematic table of dpll_chain_*: [joint origin | fixed rotation row-major | axis | box offset | parent |
+    rotation link <- collision frame row-major | joint type (1 = prismatic)]."""
     rows = []
     for b in range(tree.n_bodies):
         Rfix = tree.joint_rotation(b, torch.float64).numpy().reshape(-1) if b > 0 else np.eye(3).reshape(-1)
         rows.append(np.concatenate((tree.joint_origin[b], Rfix, tree.axis[b], tree.geometry_offset[b],
-                                    [float(max(tree.parent[b], 0))], tree.geometry_rotation(b, torch.float64).numpy().reshape(-1))))
+                                    [float(max(tree.parent[b], 0))], tree.geometry_rotation(b, torch.float64).numpy().reshape(-1),
+                                    [float(tree.is_prismatic(b))])))
     return np.ascontiguousarray(np.stack(rows))
 
 
@@ -512,15 +513,15 @@ def emul_chain_loss(n, g, kin, x, xp, eps=1e-3):
     return loss, force, iters, grad
 
 
-@pytest.mark.parametrize('name', ['chain3', 'chain3r', 'tree4', 'tree6'])
+@pytest.mark.parametrize('name', ['chain3', 'chain3r', 'slider3', 'tree4', 'tree6'])
 def test_chain_and_tree_device_math_matches_reference_golden(name):
     """Three links in series with a rotated off-axis second joint (CHAIN3_TREE), the same with every box in a ROTATED
-    collision frame (CHAIN3R_TREE), a BRANCHING four-link tree (TREE4_TREE:
+    collision frame (CHAIN3R_TREE), a hinge followed by a SLIDING joint (SLIDER3_TREE), a BRANCHING four-link tree (TREE4_TREE:
     two links off the root, a third off one of them) and a six-link tree (TREE6_TREE, the largest instantiation): loss,
     parameter gradients and one time step against the REFERENCE's
     own contactnets_loss / sim_step run on the oracle's tree callables (oracle/gen_golden_chain.py)."""
-    from oracle.callables import CHAIN3_TREE, CHAIN3R_TREE, TREE4_TREE, TREE6_TREE
-    tree = {'chain3': CHAIN3_TREE, 'chain3r': CHAIN3R_TREE, 'tree4': TREE4_TREE, 'tree6': TREE6_TREE}[name]
+    from oracle.callables import CHAIN3_TREE, CHAIN3R_TREE, SLIDER3_TREE, TREE4_TREE, TREE6_TREE
+    tree = {'chain3': CHAIN3_TREE, 'chain3r': CHAIN3R_TREE, 'slider3': SLIDER3_TREE, 'tree4': TREE4_TREE, 'tree6': TREE6_TREE}[name]
     n = tree.n_bodies
     g = load_golden(name)
     kin = chain_kin_rows(tree)

@@ -7,7 +7,7 @@ import torch
 
 from oracle import cone_qp
 from oracle import contactnets_oracle as co
-from oracle.callables import CUBE_TREE, ELBOW_TREE, TreeCallables
+from oracle.callables import CUBE_TREE, ELBOW_TREE, SLIDER3_TREE, TREE4_TREE, TREE6_TREE, TreeCallables
 from tests.util import load_golden, max_rel_to_scale, oracle_params_from_golden, rel_err
 
 CASES = ['cube_real_nominal', 'cube_real_perturbed', 'cube_synthetic']
@@ -139,7 +139,8 @@ def test_elbow_matches_reference_python(name):
     assert np.abs(traj - g['sim_traj']).max() < 1e-6
 
 
-@pytest.mark.parametrize('tree,n_q,seed', [(CUBE_TREE, 7, 1), (ELBOW_TREE, 8, 2)])
+@pytest.mark.parametrize('tree,n_q,seed', [(CUBE_TREE, 7, 1), (ELBOW_TREE, 8, 2), (TREE4_TREE, 10, 3), (TREE6_TREE, 12, 4),
+                                           (SLIDER3_TREE, 9, 5)])
 def test_restated_callables_satisfy_the_power_balance(tree, n_q, seed):
     """Physics certificate for the un-vendored symbolic callables (parity unpinned): along the
     contact-free flow q' = q (+) v dt the generated M(q) and F(q, v) must conserve energy,
@@ -151,9 +152,25 @@ def test_restated_callables_satisfy_the_power_balance(tree, n_q, seed):
     if tree is CUBE_TREE:
         pi, _, _ = synthetic.cube_learnables_perturbed(0)
         x = synthetic.cube_states(64, seed=seed)
-    else:
+    elif tree is ELBOW_TREE:
         pi, _, _ = synthetic.elbow_learnables_perturbed(0)
         x = synthetic.elbow_states(64, seed=seed)
+    else:
+        # branching trees and the sliding joint: random inertias (off-centre, non-diagonal) and random states
+        g = torch.Generator().manual_seed(seed)
+        nb = tree.n_bodies
+        m = 0.3 + 0.1 * torch.rand(nb, 1, generator=g, dtype=torch.float64)
+        c = 0.02 * (2 * torch.rand(nb, 3, generator=g, dtype=torch.float64) - 1)
+        diag = 6e-4 * (1 + 0.3 * (2 * torch.rand(nb, 3, generator=g, dtype=torch.float64) - 1))
+        offd = 5e-5 * (2 * torch.rand(nb, 3, generator=g, dtype=torch.float64) - 1)
+        pi = torch.cat((m, m * c, diag, offd), -1)
+        quat = torch.randn(64, 4, generator=g, dtype=torch.float64)
+        quat = quat / quat.norm(dim=-1, keepdim=True)
+        pos = torch.rand(64, 3, generator=g, dtype=torch.float64)
+        joints = 0.8 * (2 * torch.rand(64, nb - 1, generator=g, dtype=torch.float64) - 1)
+        vel = torch.cat((4 * torch.randn(64, 3, generator=g, dtype=torch.float64), torch.randn(64, 3, generator=g, dtype=torch.float64),
+                         3 * torch.randn(64, nb - 1, generator=g, dtype=torch.float64)), -1)
+        x = torch.cat((quat, pos, joints, vel), -1)
     inertia = co.theta_to_inertia_vector(co.pi_cm_to_theta(pi))
     q, v = x[:, :n_q], x[:, n_q:]
     ine = inertia.expand(q.shape[:-1] + inertia.shape)
@@ -204,3 +221,32 @@ def test_elbow_with_learned_geometry_matches_reference_python():
     with torch.no_grad():
         traj = co.simulate(ELBOW_CALLS, P, torch.from_numpy(g['sim_x0']), float(g['dt']), g['sim_traj'].shape[1] - 1)
     assert np.abs(traj.numpy()[:, 1] - g['sim_traj'][:, 1]).max() < 1e-9
+
+
+@pytest.mark.parametrize('tree,seed', [(ELBOW_TREE, 2), (TREE4_TREE, 3), (TREE6_TREE, 4), (SLIDER3_TREE, 5)])
+def test_restated_geometry_jacobians_equal_the_derivative_of_the_kinematics(tree, seed):
+    """Second certificate for the un-vendored callables (parity unpinned): along the flow q' = q (+) v dt every collision
+    frame's origin moves with J_v v and turns with J_w v -- d/dt p_WG = J_v v, d/dt R_WG = S(J_w v) R_WG -- central
+    differences of geometry_translations / geometry_rotations against geometry_spatial_jacobians (multibody_terms.py:
+    299-310), for hinges, branching trees and the sliding joint."""
+    calls = TreeCallables(tree)
+    g = torch.Generator().manual_seed(seed)
+    nb = tree.n_bodies
+    quat = torch.randn(32, 4, generator=g, dtype=torch.float64)
+    quat = quat / quat.norm(dim=-1, keepdim=True)
+    q = torch.cat((quat, torch.rand(32, 3, generator=g, dtype=torch.float64),
+                   0.8 * (2 * torch.rand(32, nb - 1, generator=g, dtype=torch.float64) - 1)), -1)
+    v = torch.randn(32, 6 + nb - 1, generator=g, dtype=torch.float64)
+
+    def flow(h):
+        return torch.cat((co.quat_mul(q[:, :4], co.quat_exp(v[:, :3] * h)), q[:, 4:] + v[:, 3:] * h), -1)
+    h = 1e-6
+    J = calls.geometry_spatial_jacobians(q)                       # (32, n_g, 6, n_v)
+    twist = (J @ v[:, None, :, None])[..., 0]                      # (32, n_g, 6) = [omega_W ; v_W]
+    pdot = (calls.geometry_translations(flow(h)) - calls.geometry_translations(flow(-h))) / (2 * h)
+    assert (pdot - twist[..., 3:]).abs().max().item() < 1e-8
+    R = calls.geometry_rotations(q)
+    Rdot = (calls.geometry_rotations(flow(h)) - calls.geometry_rotations(flow(-h))) / (2 * h)
+    W = Rdot @ R.transpose(-1, -2)                                 # = S(omega_W)
+    omega = torch.stack((W[..., 2, 1], W[..., 0, 2], W[..., 1, 0]), -1)
+    assert (omega - twist[..., :3]).abs().max().item() < 1e-8
