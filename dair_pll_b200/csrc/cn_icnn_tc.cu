@@ -163,6 +163,37 @@ __device__ __noinline__ double exact_z1(const double* sW0, const double* __restr
   return z + (dx * Wd1[i] + dy * Wd1[TC_W + i] + dz * Wd1[2 * TC_W + i]);
 }
 
+// Rare-path correction, run AFTER a tile's hot loop for the entries whose |z1| fell below the tolerance (a 42-bit Jacobian
+// must not decide the mask there; about one entry in 4e9): bit (8 c + q) of `flagged` marks hidden unit
+// i = 32 c + 8 ch + q of this thread, `positive` the sign the hot loop used.  z1_i and Y_k[i] are recomputed in plain fp64
+// from the weights (one pass over the 256 units of layer 0); if the exact sign differs, p is corrected by the difference
+// of the two slopes and the recorded mask bit is rewritten.
+template <bool RECORD>
+__device__ __noinline__ void redo_entries(const double* sW0, const double* __restrict__ consts, const double* __restrict__ Wh,
+                                          double dx, double dy, double dz, double slope, int ch, unsigned long long flagged,
+                                          unsigned long long positive, double& p0, double& p1, double& p2,
+                                          uint8_t* __restrict__ m1t, int64_t ldk, int64_t row) {
+  const double* Wd1 = consts + TC_C_WD1;
+  while (flagged) {
+    const int bit = __ffsll((long long)flagged) - 1;
+    flagged &= flagged - 1;
+    const int i = (bit / kCols) * TC_NC + ch * kCols + (bit % kCols);
+    double y0 = Wd1[i], y1 = Wd1[TC_W + i], y2 = Wd1[2 * TC_W + i], z = 0;
+    for (int j = 0; j < TC_W; ++j) {
+      const double lin = dx * sW0[j] + dy * sW0[TC_W + j] + dz * sW0[2 * TC_W + j];
+      const double m0 = lin > 0 ? 1.0 : slope, wh = fabs(Wh[j * TC_W + i]);
+      y0 += m0 * sW0[j] * wh; y1 += m0 * sW0[TC_W + j] * wh; y2 += m0 * sW0[2 * TC_W + j] * wh;
+      z += (lin > 0 ? lin : slope * lin) * wh;
+    }
+    z += dx * Wd1[i] + dy * Wd1[TC_W + i] + dz * Wd1[2 * TC_W + i];
+    const bool was = (positive >> bit) & 1ull, is = z > 0;
+    if (was == is) continue;
+    const double dm = (is ? 1.0 - slope : slope - 1.0) * consts[TC_C_COL + 8 * i + 7];      // (m_exact - m_used) |w_out|_i
+    p0 = fma(dm, y0, p0); p1 = fma(dm, y1, p1); p2 = fma(dm, y2, p2);
+    if (RECORD) m1t[(int64_t)i * ldk + row] = is ? 1 : 0;
+  }
+}
+
 // RECORD = false: support points p of all D rows.  RECORD = true (the backward's first pass over the compacted active
 // rows): the row count comes from device memory (*n_ptr <= D, no host read), and instead of p the two layers' slope-mask
 // bits are written as TRANSPOSED byte matrices -- m0t[j][row] in {0x00, 0xFF}, m1t[i][row] in {0, 1}, row stride ldk --
@@ -302,6 +333,8 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const int64_t* __restric
         if (lane == 0) mbar_arrive(bar(kBarAReady));
       }
       double p0 = 0, p1 = 0, p2 = 0;
+      unsigned long long flagged = 0, positive = 0;
+      static_assert(TC_CHUNKS * kCols <= 64, "one flag bit per (chunk, column) of a thread");
 #pragma unroll 1
       for (int c = 0; c < TC_CHUNKS; ++c) {
         const uint32_t n = (uint32_t)(it * TC_CHUNKS + c);
@@ -335,8 +368,17 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const int64_t* __restric
             else if (k == 1) Y1[q] = y;
             else {
               double z = dx * Y0[q] + dy * Y1[q] + dz * y;
+#ifdef TC_EXACT_INLINE
               if (fabs(z) < sC[TC_C_COL + 8 * i + 6] && valid)
                 z = exact_z1(sW0, consts + TC_C_WD1, Wh, dx, dy, dz, slope, i);
+#else
+              // |z1| below the tolerance: the entry is flagged and settled in plain fp64 AFTER the tile's hot loop
+              // (redo_entries) -- a call inside this loop cost 160-260 bytes of spills around it
+              if (fabs(z) < sC[TC_C_COL + 8 * i + 6]) {
+                flagged |= 1ull << (c * kCols + q);
+                if (z > 0) positive |= 1ull << (c * kCols + q);
+              }
+#endif
               const double m = z > 0 ? 1.0 : slope;
               if (RECORD) m1t[(int64_t)i * ldk + row] = z > 0 ? 1 : 0;
               p0 = fma(m, Y0[q], p0);
@@ -346,6 +388,9 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const int64_t* __restric
           }
         }
       }
+#ifndef TC_EXACT_INLINE
+      if (flagged && valid) redo_entries<RECORD>(sW0, consts, Wh, dx, dy, dz, slope, ch, flagged, positive, p0, p1, p2, m1t, ldk, row);
+#endif
       if (RECORD) continue;
       // the column groups of a row meet in shared memory
       double* sPt = sP + (it & 1) * ((kSplit - 1) * kTileRows * 3);
@@ -412,7 +457,7 @@ icnn_tc_prepare_kernel(const double* __restrict__ Wd0, const double* __restrict_
   }
   if (j == 0) {
     consts[TC_C_COL + 8 * i + 6] = wo * (TC_ZTOL_REL * abs_total);
-    consts[TC_C_COL + 8 * i + 7] = 0.0;
+    consts[TC_C_COL + 8 * i + 7] = wo;                      // read by redo_columns only
   }
 }
 

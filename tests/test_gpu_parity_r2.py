@@ -596,9 +596,18 @@ def test_tensor_core_support_points_match_the_fp64_layer_path(slope):
         if rows <= 129 and slope == 0.5:
             po = co.icnn_support(dict(Wd0=ws[0], Wd1=ws[1], Wh=ws[2], wout=ws[3]), d)
             assert (got.cpu() - po).abs().max().item() < 1e-11 * scale
-    # a zero direction row (what a padded tile sees) gives the zero point, not NaN
-    z = ops.icnn_support_points_tc(torch.zeros(3, 3, dtype=torch.float64, device=DEV), *wd, slope)
+    # a zero direction row (what a padded tile sees) gives a finite point -- the one of the all-negative mask -- not NaN
+    zero = torch.zeros(3, 3, dtype=torch.float64, device=DEV)
+    z = ops.icnn_support_points_tc(zero, *wd, slope)
     assert torch.isfinite(z).all()
+    assert (z - ops.icnn_support_forward(zero, *wd, slope)[0]).abs().max().item() < 1e-11 * scale
+    # the rare-path fallback on EVERY entry: directions scaled by 1e-12 put every |z1| below its tolerance, so every
+    # (row, column group) is redone in plain fp64 after the tile loop; support points are homogeneous of degree 0 in the
+    # direction, so the answer is the one of the unscaled directions
+    d = torch.randn(300, 3, generator=torch.Generator().manual_seed(77), dtype=torch.float64).to(DEV)
+    tiny = ops.icnn_support_points_tc(d * 1e-12, *wd, slope)
+    ref = ops.icnn_support_forward(d, *wd, slope)[0]
+    assert (tiny - ref).abs().max().item() < 1e-11 * ref.abs().max().item()
 
 
 def test_support_network_backward_visits_only_rows_with_a_cotangent():
