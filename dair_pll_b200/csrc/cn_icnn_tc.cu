@@ -152,17 +152,6 @@ __device__ __forceinline__ double horner_i2d(const int32_t* a) {
   return __longlong_as_double(v + 0x4338000000000000LL) - 6755399441055744.0;
 }
 
-// z1_i in plain fp64 for one row (the rare |z1| ~ 0 case, where a 42-bit Jacobian must not decide the mask)
-__device__ __noinline__ double exact_z1(const double* sW0, const double* __restrict__ Wd1, const double* __restrict__ Wh,
-                                        double dx, double dy, double dz, double slope, int i) {
-  double z = 0;
-  for (int j = 0; j < TC_W; ++j) {
-    const double lin = dx * sW0[j] + dy * sW0[TC_W + j] + dz * sW0[2 * TC_W + j];
-    z += (lin > 0 ? lin : slope * lin) * fabs(Wh[j * TC_W + i]);
-  }
-  return z + (dx * Wd1[i] + dy * Wd1[TC_W + i] + dz * Wd1[2 * TC_W + i]);
-}
-
 // Rare-path correction, run AFTER a tile's hot loop for the entries whose |z1| fell below the tolerance (a 42-bit Jacobian
 // must not decide the mask there; about one entry in 4e9): bit (8 c + q) of `flagged` marks hidden unit
 // i = 32 c + 8 ch + q of this thread, `positive` the sign the hot loop used.  z1_i and Y_k[i] are recomputed in plain fp64
@@ -339,58 +328,71 @@ icnn_tc_kernel(const double* __restrict__ d, int64_t D, const int64_t* __restric
       for (int c = 0; c < TC_CHUNKS; ++c) {
         const uint32_t n = (uint32_t)(it * TC_CHUNKS + c);
         double Y0[kCols], Y1[kCols];
+        // reconstructed Jacobian entry |w_out|_i Y_k[i] of column q from its three accumulators
+        auto entry = [&](const int32_t (&a)[TC_NACC][kCols], int k, int q) {
+          const int i = c * TC_NC + ch * kCols + q;
+          int32_t aq[TC_NACC];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          int32_t a[TC_NACC][kCols];
-          mbar_wait(bar(kBarAccFull + k), n & 1u);
-          __syncwarp();
-          tc_fence_after();
+          for (int t = 0; t < TC_NACC; ++t) aq[t] = a[t][q];
+          const double v = horner_i2d(aq);
+          const double2 cb = *reinterpret_cast<const double2*>(sC + TC_C_COL + 8 * i + 2 * k);
+          return fma(cb.x, v, cb.y);
+        };
+        auto load_set = [&](int32_t (&a)[TC_NACC][kCols], int k) {
 #pragma unroll
           for (int t = 0; t < TC_NACC; ++t) {
             const uint32_t ta = tmem_lane + kColAcc + (uint32_t)((k * TC_NACC + t) * TC_NC + ch * kCols);
             if constexpr (kCols == 16) tmem_ld16(ta, a[t]);
             else tmem_ld8(ta, a[t]);
           }
+        };
+        {
+          // the accumulator sets of k = 0 and k = 1 are fetched TOGETHER (one exposed TMEM-load latency instead of two: the
+          // tensor pipe runs ahead of this epilogue, so both are normally complete) and handed back at once
+          int32_t a0[TC_NACC][kCols], a1[TC_NACC][kCols];
+          mbar_wait(bar(kBarAccFull + 0), n & 1u);
+          mbar_wait(bar(kBarAccFull + 1), n & 1u);
+          __syncwarp();
+          tc_fence_after();
+          load_set(a0, 0);
+          load_set(a1, 1);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(kBarAccEmpty + k));     // the tensor pipe may overwrite this set
+          if (lane == 0) { mbar_arrive(bar(kBarAccEmpty + 0)); mbar_arrive(bar(kBarAccEmpty + 1)); }
+#pragma unroll
+          for (int q = 0; q < kCols; ++q) { Y0[q] = entry(a0, 0, q); Y1[q] = entry(a1, 1, q); }
+        }
+        {
+          int32_t a[TC_NACC][kCols];
+          mbar_wait(bar(kBarAccFull + 2), n & 1u);
+          __syncwarp();
+          tc_fence_after();
+          load_set(a, 2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(kBarAccEmpty + 2));     // the tensor pipe may overwrite this set
 #pragma unroll
           for (int q = 0; q < kCols; ++q) {
             const int i = c * TC_NC + ch * kCols + q;
-            int32_t aq[TC_NACC];
-#pragma unroll
-            for (int t = 0; t < TC_NACC; ++t) aq[t] = a[t][q];
-            const double v = horner_i2d(aq);
-            const double2 cb = *reinterpret_cast<const double2*>(sC + TC_C_COL + 8 * i + 2 * k);
-            const double y = fma(cb.x, v, cb.y);
-            if (k == 0) Y0[q] = y;
-            else if (k == 1) Y1[q] = y;
-            else {
-              double z = dx * Y0[q] + dy * Y1[q] + dz * y;
-#ifdef TC_EXACT_INLINE
-              if (fabs(z) < sC[TC_C_COL + 8 * i + 6] && valid)
-                z = exact_z1(sW0, consts + TC_C_WD1, Wh, dx, dy, dz, slope, i);
-#else
-              // |z1| below the tolerance: the entry is flagged and settled in plain fp64 AFTER the tile's hot loop
-              // (redo_entries) -- a call inside this loop cost 160-260 bytes of spills around it
-              if (fabs(z) < sC[TC_C_COL + 8 * i + 6]) {
-                flagged |= 1ull << (c * kCols + q);
-                if (z > 0) positive |= 1ull << (c * kCols + q);
-              }
-#endif
-              const double m = z > 0 ? 1.0 : slope;
-              if (RECORD) m1t[(int64_t)i * ldk + row] = z > 0 ? 1 : 0;
-              p0 = fma(m, Y0[q], p0);
-              p1 = fma(m, Y1[q], p1);
-              p2 = fma(m, y, p2);
+            const double y = entry(a, 2, q);
+            const double z = dx * Y0[q] + dy * Y1[q] + dz * y;
+            // |z1| below the tolerance: the entry is flagged and settled in plain fp64 AFTER the tile's hot loop
+            // (redo_entries) -- a call inside this loop cost 160-260 bytes of spills around it
+            if (fabs(z) < sC[TC_C_COL + 8 * i + 6]) {
+              flagged |= 1ull << (c * kCols + q);
+              if (z > 0) positive |= 1ull << (c * kCols + q);
             }
+            const double m = z > 0 ? 1.0 : slope;
+            if (RECORD) m1t[(int64_t)i * ldk + row] = z > 0 ? 1 : 0;
+            p0 = fma(m, Y0[q], p0);
+            p1 = fma(m, Y1[q], p1);
+            p2 = fma(m, y, p2);
           }
         }
       }
-#ifndef TC_EXACT_INLINE
       if (flagged && valid) redo_entries<RECORD>(sW0, consts, Wh, dx, dy, dz, slope, ch, flagged, positive, p0, p1, p2, m1t, ldk, row);
-#endif
       if (RECORD) continue;
       // the column groups of a row meet in shared memory
       double* sPt = sP + (it & 1) * ((kSplit - 1) * kTileRows * 3);
