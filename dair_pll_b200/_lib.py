@@ -9,7 +9,7 @@ import os
 from dair_pll_b200 import build as _build
 
 _LIB = None
-ABI_VERSION = 208        # DPLL_VERSION of include/dair_pll_b200.h this binding was written against
+ABI_VERSION = 209        # DPLL_VERSION of include/dair_pll_b200.h this binding was written against
 
 _c_void_p = ctypes.c_void_p
 _i64, _i32, _f64, _f32, _sz = ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_float, ctypes.c_size_t

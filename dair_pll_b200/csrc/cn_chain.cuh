@@ -25,8 +25,10 @@
 
 namespace cn {
 
-constexpr int CH_NKIN = 29;     // per link: [joint origin 3 | joint rpy as rotation matrix 9 | axis 3 | box offset 3 | parent link |
-                                //            rotation link <- collision frame 9 | joint type: 0 revolute, 1 prismatic]
+constexpr double CH_OFF = 1e6;  // normal entry of the QP vector of an empty box slot's contacts (m/s; deep in the polar cone)
+constexpr int CH_NKIN = 31;     // row b = link b: [joint origin 3 | joint rpy as rotation matrix 9 | axis 3 | . | parent link | . |
+                                //   joint type: 0 revolute, 1 prismatic] and box SLOT b: [box offset 3 (entries 15-17) | rotation
+                                //   link <- collision frame 9 (19-27) | link the box sits on (29) | slot in use (30)]
 
 template <typename T, int N> struct ChainParams {
   static constexpr int NV = 6 + N - 1, NC = 4 * N, K = 3 * NC;
@@ -37,6 +39,8 @@ template <typename T, int N> struct ChainParams {
   int par[N];                              // parent link (par[b] < b; entry 0 unused)
   unsigned anc[N];                         // bit j set: joint j (1..N-1) lies on the path from the root to link b
   unsigned pris;                           // bit j set: joint j slides along its axis (prismatic) instead of turning
+  int glink[N];                            // box slot g sits on link glink[g] (any distribution of <= N boxes over the links)
+  unsigned gon;                            // bit g set: slot g holds a box (its four contacts exist)
   T dt, eps, inv_eps, grav;
   T dscale[6 + N - 1];
 };
@@ -45,7 +49,7 @@ template <typename T, int N> struct ChainParams {
 template <typename T, int N>
 CN_HD void chain_params_init(ChainParams<T, N>& P, const T* inertia, const T* mu, const T* half, const T* kin, T dt, T eps) {
   T msum = T(0), Isum[3] = {T(0), T(0), T(0)};
-  P.pris = 0u;
+  P.pris = 0u; P.gon = 0u;
   for (int b = 0; b < N; ++b) {
     ElbowBody<T>& B = P.body[b];
     const T* in = inertia + 10 * b;
@@ -69,6 +73,9 @@ CN_HD void chain_params_init(ChainParams<T, N>& P, const T* inertia, const T* mu
     P.par[b] = pb;
     P.anc[b] = b > 0 ? (P.anc[pb] | (1u << b)) : 0u;
     if (b > 0 && to_double(kn[28]) > 0.5) P.pris |= 1u << b;
+    int gl = (int)to_double(kn[29]);
+    P.glink[b] = gl < 0 ? 0 : (gl > N - 1 ? N - 1 : gl);
+    if (to_double(kn[30]) > 0.5) P.gon |= 1u << b;
     msum += B.m;
     for (int i = 0; i < 3; ++i) Isum[i] += B.Io[i];
   }
@@ -213,8 +220,21 @@ template <typename T, int N> struct ChainProb {
 
 template <typename T, int N>
 CN_HD void chain_contacts(const ChainParams<T, N>& P, ChainKin<T, N>& K, ChainProb<T, N>& S) {
-  for (int b = 0; b < N; ++b) {
-    const T* R = K.R[b];
+  for (int b = 0; b < N; ++b) {             // b: box slot; l: the link it sits on
+    const int l = P.glink[b];
+    if (!((P.gon >> b) & 1u)) {
+      // empty slot: its four contacts get a zero Jacobian here and a residual deep in the polar cone where the QP vector is
+      // built (zero force, zero curvature), and take no part in the loss
+      K.sel[b] = 0u;
+      for (int c = 0; c < 4; ++c) {
+        const int cc = 4 * b + c;
+        for (int i = 0; i < 3; ++i) S.rho[3 * cc + i] = T(0);
+        for (int j = 1; j < N; ++j)
+          for (int i = 0; i < 3; ++i) S.hc[3 * (cc * (N - 1) + (j - 1)) + i] = T(0);
+      }
+      continue;
+    }
+    const T* R = K.R[l];
     // support direction -R_WG^T e_z in the box's own frame, R_WG = R_link Rg  (geometry.py:560-567)
     const T dl[3] = {-R[6], -R[7], -R[8]};
     T d[3];
@@ -227,12 +247,12 @@ CN_HD void chain_contacts(const ChainParams<T, N>& P, ChainKin<T, N>& K, ChainPr
       for (int k = 0; k < 3; ++k) p[k] += P.off[b][k];
       rot3(R, p, r);
       const int cc = 4 * b + c;
-      for (int i = 0; i < 3; ++i) S.rho[3 * cc + i] = K.o[b][i] + r[i];
+      for (int i = 0; i < 3; ++i) S.rho[3 * cc + i] = K.o[l][i] + r[i];
       for (int j = 1; j < N; ++j) {
         T hcol[3] = {T(0), T(0), T(0)};
-        if (((K.anc[b] >> j) & 1u) && ((K.pris >> j) & 1u)) {
+        if (((K.anc[l] >> j) & 1u) && ((K.pris >> j) & 1u)) {
           for (int i = 0; i < 3; ++i) hcol[i] = K.a[j][i];
-        } else if ((K.anc[b] >> j) & 1u) {
+        } else if ((K.anc[l] >> j) & 1u) {
           T dd[3];
           for (int i = 0; i < 3; ++i) dd[i] = S.rho[3 * cc + i] - K.o[j][i];
           cross3(K.a[j], dd, hcol);
@@ -410,6 +430,10 @@ CN_HD T chain_loss_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, c
     const T sx = mu * ev[0], sy = mu * ev[1];
     const T speed2 = sx * sx + sy * sy;
     const T speed = speed2 * t_rsqrt(t_max(speed2, t_tiny<T>()));
+    if (!((P.gon >> (c >> 2)) & 1u)) {           // empty box slot: deep in the polar cone, no penetration term
+      S.q[3 * c] = T(0); S.q[3 * c + 1] = T(0); S.q[3 * c + 2] = T(CH_OFF);
+      continue;
+    }
     const T phic = S.rho[3 * c + 2] + pos_z;
     S.q[3 * c] = -mu * ed[0] + P.dt * sx;
     S.q[3 * c + 1] = -mu * ed[1] + P.dt * sy;
@@ -497,9 +521,11 @@ CN_HD T chain_loss_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, c
     rigid_body_inertia_adjoint<T>(P.body[bi].m, P.body[bi].c, R, wB, P.grav, Kww, Nm, trvv, lm, grad + 10 * bi);
   }
   for (int c = 0; c < NC; ++c) {
-    const int bi = c >> 2, cl = c & 3;
+    const int bi = c >> 2, cl = c & 3;           // bi: box slot (mu, half lengths); li: its link (kinematics)
+    if (!((P.gon >> bi) & 1u)) continue;
+    const int li = P.glink[bi];
     const T mu = P.mu[bi];
-    const T* R = K.R[bi];
+    const T* R = K.R[li];
     T eb[3], ev[3];
     chain_point_vel<T, N>(S, c, b, eb);
     chain_point_vel<T, N>(S, c, vp, ev);
@@ -512,8 +538,8 @@ CN_HD T chain_loss_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, c
     const T ft[3] = {mu * ftx, mu * fty, fn};
     const T gt[3] = {mu * gx, mu * gy, T(0)};
     T Vb[6], Vv[6], w1[3], w2[3], pw[3], pB[3];
-    chain_T<T, N>(K, bi, b, Vb);
-    chain_T<T, N>(K, bi, vp, Vv);
+    chain_T<T, N>(K, li, b, Vb);
+    chain_T<T, N>(K, li, vp, Vv);
     cross3(ft, Vb, w1); cross3(gt, Vv, w2);           // angular parts of the link's twists (world)
     for (int i = 0; i < 3; ++i) pw[i] = w1[i] + w2[i];
     rot3t(R, pw, pB);
@@ -550,7 +576,7 @@ CN_HD int chain_step_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg,
     chain_point_vel<T, N>(S, c, vm, e);
     S.q[3 * c] = mu * e[0];
     S.q[3 * c + 1] = mu * e[1];
-    S.q[3 * c + 2] = e[2] + (S.rho[3 * c + 2] + x[6]) * inv_dt;
+    S.q[3 * c + 2] = ((P.gon >> (c >> 2)) & 1u) ? e[2] + (S.rho[3 * c + 2] + x[6]) * inv_dt : T(CH_OFF);
   }
   T u[NV];
   for (int i = 0; i < NV; ++i) u[i] = T(0);

@@ -109,10 +109,13 @@ class MultibodyLearnableSystem(System):
         return inertia.reshape(20), mu.reshape(2), (torch.cat(half) if half else None), kin
 
     def _chain_params(self, device: torch.device):
-        """Generic kinematic tree: (inertia (n*10), mu (n), half (n*3), kin (n*29), n), float64."""
+        """Generic kinematic tree: (inertia (n*10), mu (n), half (n*3), kin (n*31), n), float64.  The kernels have n box
+        slots; the system's boxes (any distribution over the links, at most n) fill the first ones, the rest are switched off
+        in the kinematic table and padded here (their gradient entries are dropped by the padding's autograd)."""
         inertia, mu, half = self.multibody_terms.kernel_parameters(torch.float64)
         spec = self.multibody_terms.spec
         n = len(spec.bodies)
+        boxes = [g for g in spec.geometries if g.body >= 0]
         key = ('chain', str(device))
         if key not in self._kin_cache:
             rows = []
@@ -124,9 +127,17 @@ class MultibodyLearnableSystem(System):
                     j = spec.joints[b - 1]          # joint b - 1 is the one whose child is link b (SystemSpec orders them)
                     rows += [*j.origin, *j.rotation(), *j.axis]
                     parent, sliding = j.parent, float(j.prismatic)
-                rows += [*spec.geometries[b].offset, float(parent), *spec.geometries[b].rotation().reshape(-1).tolist(), sliding]
+                if b < len(boxes):
+                    g = boxes[b]
+                    rows += [*g.offset, float(parent), *g.rotation().reshape(-1).tolist(), sliding, float(g.body), 1.]
+                else:
+                    rows += [0., 0., 0., float(parent), 1., 0., 0., 0., 1., 0., 0., 0., 1., sliding, 0., 0.]
             self._kin_cache[key] = torch.tensor(rows, dtype=torch.float64, device=device)
-        return inertia.reshape(-1), mu.reshape(-1), torch.cat(half), self._kin_cache[key], n
+        mu, half = mu.reshape(-1), torch.cat(half)
+        if len(boxes) < n:
+            mu = torch.cat((mu, mu.new_ones(n - len(boxes))))
+            half = torch.cat((half, half.new_zeros(3 * (n - len(boxes)))))
+        return inertia.reshape(-1), mu, half, self._kin_cache[key], n
 
     def _elbow_witness_points(self, q: Tensor) -> Tensor:
         """(B, 8) configurations -> (B, 8, 3) witness points of the two learned geometries against the

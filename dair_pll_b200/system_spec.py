@@ -212,6 +212,7 @@ class SystemSpec:
         if len(bodies) == 1 and not joints:
             kind = 'cube'
         elif len(bodies) == 2 and serial and not rotated and not joints[0].prismatic \
+                and [g.body for g in geometries] == [0, 1] \
                 and not any(any(abs(a) > 0 for a in g.rpy) for g in geometries):
             kind = 'elbow'                      # the specialised two-body kernels (unrotated joint and collision frames)
         elif 2 <= len(bodies) <= 6 and tree:
@@ -229,11 +230,13 @@ class SystemSpec:
                                           '(a Polygon is set through the module API)')
             # a collision frame that differs from the link frame (offset and / or rotation) is handled through the
             # witness-point kernels: the contact points are support points of the shape, moved into the link frame
-        else:
-            if [g.body for g in geometries] != list(range(len(bodies))):
-                raise NotImplementedError('the multi-link kernels take one collision geometry per link')
-            if kind == 'chain' and any(g.kind != 'box' for g in geometries):
-                raise NotImplementedError('the generic chain kernels take <box> collision geometries')
+        elif kind == 'chain':
+            # the generic tree kernels have as many box slots as links; a slot may sit on any link, so the boxes can be spread
+            # over the links in any way (several on one link, none on another) as long as there are no more boxes than links
+            if any(g.kind != 'box' for g in geometries):
+                raise NotImplementedError('the generic tree kernels take <box> collision geometries')
+            if not 1 <= len(geometries) <= len(bodies):
+                raise NotImplementedError('the generic tree kernels take between one box and as many boxes as there are links')
         if len({g.kind for g in geometries}) > 1:
             raise NotImplementedError('mixed box / mesh collision geometries in one system are not supported')
         ground = len(geometries)

@@ -44,7 +44,7 @@ extern "C" {
 #define DPLL_EWORKSPACE (-2) /* workspace too small */
 #define DPLL_ECOMM (-3)      /* a peer did not arrive within the exchange's timeout */
 
-#define DPLL_VERSION 208     /* bumped with every change of a signature below; the binding checks it */
+#define DPLL_VERSION 209     /* bumped with every change of a signature below; the binding checks it */
 
 #define DPLL_CUBE_NX 13
 #define DPLL_CUBE_NC 4
@@ -450,10 +450,13 @@ int dpll_elbow_rollout_f32(const float* x0, const float* inertia, const float* m
  * (multibody_terms.py:114-157, 267-319) evaluated by recursion over the links (csrc/cn_chain.cuh), for models the
  * specialised cube / elbow kernels do not cover.  States (B, 13 + 2 (n-1)) = [quat | pos | joint angles | w_body |
  * v_world | joint rates] (joint b - 1 is the one whose child is link b); inertia (n, 10), mu_pair (n) (ground-link i),
- * half (n, 3); kin (n, 29) per link = [joint origin in the parent link (3) | fixed rotation parent -> joint frame,
- * row-major (9) | joint axis (3) | box offset in the link (3) | index of the parent link, as a number (1) | rotation
- * link frame <- collision (box) frame, row-major (9) | joint type: 0 revolute / continuous, 1 prismatic (1)] (row 0:
- * only the box offset and rotation are used; a parent index outside [0, b - 1] is clamped).  grad (14 n) = [d/d inertia (10 n) | d/d mu_pair (n) |
+ * half (n, 3); kin (n, 31): row b carries LINK b's joint -- [joint origin in the parent link (0:3) | fixed rotation parent
+ * -> joint frame, row-major (3:12) | joint axis (12:15) | index of the parent link, as a number (18) | joint type: 0
+ * revolute / continuous, 1 prismatic (28)] -- and BOX SLOT b -- [box offset in its link (15:18) | rotation link frame <-
+ * collision (box) frame, row-major (19:28) | index of the link the box sits on (29) | 1 if the slot holds a box, 0 if it is
+ * empty (30)]: there are as many box slots as links and a slot may sit on ANY link, so up to n boxes can be spread over the
+ * links in any way; mu_pair, half and the gradient entries are per slot (empty slots: ignored / zero).  Row 0 has no joint;
+ * a parent index outside [0, b - 1] and a box link outside [0, n - 1] are clamped.  grad (14 n) = [d/d inertia (10 n) | d/d mu_pair (n) |
  * d/d half (3 n)] of sum_b w_b loss_b; force (B, 12 n) = [normals (4 n) ; (tx, ty) (4 n)], links in order, contacts by
  * ascending vertex index.  One sample per thread.  dpll_chain_rollout_f64: traj (B, steps+1, n_x).
  */

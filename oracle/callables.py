@@ -175,6 +175,17 @@ TREE4_TREE = TreeSpec(parent=[-1, 0, 0, 2],
                       joint_rpy=[(0., 0., 0.), (0., 0., 0.), (0.2, 0.1, -0.3), (0.3, -0.2, 0.5)])
 
 
+# TREE4_TREE's kinematics with the boxes distributed UNEVENLY over the links: two on the root, none on links 1 and 2, one on
+# link 3 (tests of the box-slot handling of the generic tree kernels; not a reference asset)
+TREE4G_TREE = TreeSpec(parent=[-1, 0, 0, 2],
+                       joint_origin=[(0., 0., 0.), (-0.035, 0.06, 0.), (0.05, -0.04, 0.01), (0.06, 0.0, -0.015)],
+                       axis=[(0., 0., 1.), (0., 1., 0.), (1., 0., 0.), (0.6, 0., 0.8)],
+                       geometry_body=[0, 0, 3, -1],
+                       geometry_offset=[(0.02, 0., 0.), (-0.04, 0.01, 0.015), (0.03, -0.01, 0.), (0., 0., 0.)],
+                       joint_rpy=[(0., 0., 0.), (0., 0., 0.), (0.2, 0.1, -0.3), (0.3, -0.2, 0.5)],
+                       geometry_rpy=[(0., 0., 0.), (0.3, 0., 0.2), (0., 0., 0.), (0., 0., 0.)])
+
+
 # a six-link tree: three limbs off the root, two of them with a second segment (tests of the generic tree kernels at their
 # largest instantiation; not a reference asset)
 TREE6_TREE = TreeSpec(parent=[-1, 0, 0, 0, 1, 3],

@@ -1,4 +1,4 @@
-"""ORACLE (test infrastructure).  Writes tests/golden/chain3.npz, chain3r.npz (rotated collision frames), slider3.npz (a prismatic joint), tree4.npz and tree6.npz by running the REFERENCE's own
+"""ORACLE (test infrastructure).  Writes tests/golden/chain3.npz, chain3r.npz (rotated collision frames), slider3.npz (a prismatic joint), tree4.npz, tree4g.npz (boxes spread unevenly over the links) and tree6.npz by running the REFERENCE's own
 ``contactnets_loss`` / ``sim_step`` (through oracle/ref_shim.py) for a three-link floating chain (oracle/callables.py:
 CHAIN3_TREE: off-axis second joint with a rotated joint frame, one box per link) and for a BRANCHING four-link tree
 (TREE4_TREE: two links off the root, a third off one of them) and a six-link tree (TREE6_TREE) -- the fixtures of the generic tree kernels (SURVEY.md 8(f)
@@ -19,7 +19,8 @@ sys.path.insert(0, ROOT)
 warnings.filterwarnings('ignore')
 
 from oracle import ref_shim  # noqa: E402
-from oracle.callables import CHAIN3_TREE, CHAIN3R_TREE, SLIDER3_TREE, TREE4_TREE, TREE6_TREE, TreeCallables  # noqa: E402
+from oracle.callables import (CHAIN3_TREE, CHAIN3R_TREE, SLIDER3_TREE, TREE4_TREE, TREE4G_TREE, TREE6_TREE,  # noqa: E402
+                              TreeCallables)
 
 DT = 0.0068
 HALF = np.array([[0.05, 0.025, 0.025], [0.045, 0.03, 0.02], [0.03, 0.02, 0.035]])
@@ -42,7 +43,7 @@ def lowest_corner(calls, q, half=HALF):
 
 
 def states(n, seed, calls, half=HALF):
-    nj = len(half) - 1
+    nj = calls.tree.n_bodies - 1
     g = torch.Generator().manual_seed(seed)
     quat = torch.randn(n, 4, generator=g, dtype=torch.float64)
     quat = quat / quat.norm(dim=-1, keepdim=True)
@@ -64,7 +65,8 @@ def states(n, seed, calls, half=HALF):
 
 def make(tree, half, coms, friction, name, n, m):
     calls = TreeCallables(tree)
-    nb = len(half)
+    nb = tree.n_bodies
+    ng = len(half)                         # box geometries (any distribution over the links)
     gen = torch.Generator().manual_seed(7)
     rows = []
     for com0 in coms:
@@ -91,7 +93,7 @@ def make(tree, half, coms, friction, name, n, m):
                half_lengths=half, loss=loss.detach().numpy(),
                grad_theta=mt.lagrangian_terms.inertial_parameters.grad.numpy(),
                grad_friction=mt.contact_terms.friction_params.grad.numpy(),
-               grad_length=np.stack([mt.contact_terms.geometries[i].length_params.grad.numpy().reshape(3) for i in range(nb)]))
+               grad_length=np.stack([mt.contact_terms.geometries[i].length_params.grad.numpy().reshape(3) for i in range(ng)]))
     # prediction-loss path: 3-step rollout by the reference's own integrator, weighted sum of the states, autograd through
     # every step's QP -> gradients of theta, friction, box lengths and the initial state
     for q in system.parameters():
@@ -109,7 +111,7 @@ def make(tree, half, coms, friction, name, n, m):
                roll_grad_theta=mt.lagrangian_terms.inertial_parameters.grad.numpy(),
                roll_grad_friction=mt.contact_terms.friction_params.grad.numpy(),
                roll_grad_length=np.stack([mt.contact_terms.geometries[i].length_params.grad.numpy().reshape(3)
-                                          for i in range(nb)]))
+                                          for i in range(ng)]))
     path = os.path.join(ROOT, 'tests', 'golden', f'{name}.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, 'mean loss', float(loss.mean()))
@@ -122,6 +124,8 @@ def main():
     make(SLIDER3_TREE, HALF, ((0., 0., 0.), (0.035, 0., 0.), (0.02, -0.01, 0.)), [0.3, 0.45, 0.25, 0.9], 'slider3', 128, 8)
     make(TREE4_TREE, HALF4, ((0., 0., 0.), (0.035, 0., 0.), (0.0, -0.03, 0.), (0.03, -0.01, 0.)),
          [0.3, 0.45, 0.35, 0.25, 0.9], 'tree4', 192, 16)
+    make(TREE4G_TREE, HALF4[:3], ((0., 0., 0.), (0.035, 0., 0.), (0.0, -0.03, 0.), (0.03, -0.01, 0.)),
+         [0.3, 0.45, 0.25, 0.9], 'tree4g', 128, 8)
     make(TREE6_TREE, HALF6, ((0., 0., 0.), (0.03, 0., 0.), (-0.03, 0., 0.), (0., -0.03, 0.), (0.03, -0.01, 0.), (0., -0.03, 0.01)),
          [0.3, 0.45, 0.35, 0.25, 0.5, 0.4, 0.9], 'tree6', 128, 8)
 

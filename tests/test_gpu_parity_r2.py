@@ -495,13 +495,14 @@ def _chain_system(g, urdf, n):
     s = MultibodyLearnableSystem({'chain': urdf}, float(g['dt']))
     sd = {'multibody_terms.lagrangian_terms.inertial_parameters': torch.from_numpy(g['theta']),
           'multibody_terms.contact_terms.friction_params': torch.from_numpy(g['friction_params'])}
-    for i in range(n):
+    for i in range(g['half_lengths'].shape[0]):      # one entry per box (tree4g: fewer boxes than links)
         sd[f'multibody_terms.contact_terms.geometries.{i}.length_params'] = torch.from_numpy(g['half_lengths'][i]).reshape(1, 3)
     s.load_state_dict(sd)
     return s.to(DEV)
 
 
-@pytest.mark.parametrize('name, n_links', [('chain3', 3), ('chain3r', 3), ('slider3', 3), ('tree4', 4), ('tree6', 6)])
+@pytest.mark.parametrize('name, n_links', [('chain3', 3), ('chain3r', 3), ('slider3', 3), ('tree4', 4), ('tree4g', 4),
+                                           ('tree6', 6)])
 def test_generic_chain_and_tree_match_reference_golden(name, n_links, assets_dir):
     """N2: a three-link URDF with a rotated, off-axis second joint, and a BRANCHING four-link URDF (two links off the
     root, a third off one of them), go URDF -> SystemSpec -> the generic tree kernels; losses, every parameter gradient
@@ -554,9 +555,9 @@ def test_generic_chain_two_links_reproduces_the_elbow_kernels(name, assets_dir):
     s = _chain_system(g, os.path.join(assets_dir, 'elbow.urdf'), 2)
     inertia, mu, half, kin = (t.detach() for t in s._elbow_params(torch.float64, torch.device(DEV)))
     eye = [1, 0, 0, 0, 1, 0, 0, 0, 1]
-    kin18 = torch.tensor([0, 0, 0, *eye, 0, 0, 1, *kin[6:9].tolist(), 0, *eye, 0,
-                          *kin[0:3].tolist(), *eye, *kin[3:6].tolist(), *kin[9:12].tolist(), 0, *eye, 0],
-                         dtype=torch.float64, device=DEV)      # per link: ... | parent link | collision-frame rotation | type
+    kin18 = torch.tensor([0, 0, 0, *eye, 0, 0, 1, *kin[6:9].tolist(), 0, *eye, 0, 0, 1,
+                          *kin[0:3].tolist(), *eye, *kin[3:6].tolist(), *kin[9:12].tolist(), 0, *eye, 0, 1, 1],
+                         dtype=torch.float64, device=DEV)      # ... | parent | collision-frame rotation | type | box link | used
     inertia.requires_grad_(); mu.requires_grad_(); half.requires_grad_()
     loss = ops.ChainContactNetsLoss.apply(x, xp, inertia, mu, half, kin18, 2, float(g['dt']), 1e-3)
     loss.sum().backward()
@@ -659,7 +660,7 @@ def test_elbow_support_directions_kernel_matches_the_tensor_formula(assets_dir):
         assert (got - ref).abs().max().item() < 1e-14
 
 
-@pytest.mark.parametrize('name', ['cube', 'elbow', 'chain3', 'tree4', 'tree6'])
+@pytest.mark.parametrize('name', ['cube', 'elbow', 'chain3', 'tree4', 'tree4g', 'tree6'])
 def test_leaf_preparation_kernels_match_the_host_parameter_graph(name, assets_dir):
     """dpll_leaf_prepare_f64 / dpll_leaf_backward_f64 (one launch each) against the PyTorch graph they replace --
     theta -> [m, c, I_cm/m] (inertia.py:205-234, 304-331, 376-382), pairwise friction (multibody_terms.py:466-471),

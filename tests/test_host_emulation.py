@@ -472,22 +472,33 @@ def test_witness_point_device_math_matches_reference_golden(name):
 # ---- generic serial chain (cn_chain.cuh) -----------------------------------------------------------
 
 def chain_kin_rows(tree):
-    """(n, 29) kinematic table of dpll_chain_*: [joint origin | fixed rotation row-major | axis | box offset | parent |
-    rotation link <- collision frame row-major | joint type (1 = prismatic)]."""
+    """(n, 31) kinematic table of dpll_chain_*.  Row b, link part: [joint origin | fixed rotation row-major | axis | . |
+    parent | . | joint type (1 = prismatic)]; row b, box-slot part: [box offset (15:18) | rotation link <- collision frame
+    row-major (19:28) | link the box sits on (29) | slot in use (30)] -- the tree's body geometries fill the first slots."""
+    n = tree.n_bodies
+    n_geoms = len(tree.geometry_body) - 1
     rows = []
-    for b in range(tree.n_bodies):
+    for b in range(n):
         Rfix = tree.joint_rotation(b, torch.float64).numpy().reshape(-1) if b > 0 else np.eye(3).reshape(-1)
-        rows.append(np.concatenate((tree.joint_origin[b], Rfix, tree.axis[b], tree.geometry_offset[b],
-                                    [float(max(tree.parent[b], 0))], tree.geometry_rotation(b, torch.float64).numpy().reshape(-1),
-                                    [float(tree.is_prismatic(b))])))
+        if b < n_geoms:
+            off, Rg, link, used = tree.geometry_offset[b], tree.geometry_rotation(b, torch.float64).numpy().reshape(-1), \
+                tree.geometry_body[b], 1.0
+        else:
+            off, Rg, link, used = (0., 0., 0.), np.eye(3).reshape(-1), 0, 0.0
+        rows.append(np.concatenate((tree.joint_origin[b], Rfix, tree.axis[b], off, [float(max(tree.parent[b], 0))], Rg,
+                                    [float(tree.is_prismatic(b))], [float(link)], [used])))
     return np.ascontiguousarray(np.stack(rows))
 
 
 def chain_kernel_level_params(g, n):
+    """inertia (10 n), pair friction and half lengths of the n box slots (empty slots: 1 and 0)."""
     inertia = co.theta_to_inertia_vector(torch.from_numpy(g['theta'])).reshape(10 * n).numpy()
     mu = np.abs(g['friction_params'])
-    mu_pair = np.array([2 * mu[n] * mu[i] / (mu[n] + mu[i]) for i in range(n)])
-    return inertia, mu_pair, np.abs(g['half_lengths']).reshape(3 * n).copy()
+    ng = len(mu) - 1                                        # body geometries; the ground is last
+    mu_pair = np.array([2 * mu[ng] * mu[i] / (mu[ng] + mu[i]) for i in range(ng)] + [1.0] * (n - ng))
+    half = np.zeros((n, 3))
+    half[:ng] = np.abs(g['half_lengths'])
+    return inertia, mu_pair, half.reshape(3 * n).copy()
 
 
 def chain_grad_to_leaves(g, grad, n):
@@ -495,8 +506,11 @@ def chain_grad_to_leaves(g, grad, n):
     fr = torch.from_numpy(g['friction_params']).clone().requires_grad_()
     ln = torch.from_numpy(g['half_lengths']).clone().requires_grad_()
     mu = fr.abs()
+    ng = mu.shape[0] - 1
+    pad_mu = [torch.ones((), dtype=torch.float64)] * (n - ng)
     flat = torch.cat((co.theta_to_inertia_vector(theta).reshape(10 * n),
-                      torch.stack([2 * mu[n] * mu[i] / (mu[n] + mu[i]) for i in range(n)]), ln.abs().reshape(3 * n)))
+                      torch.stack([2 * mu[ng] * mu[i] / (mu[ng] + mu[i]) for i in range(ng)] + pad_mu),
+                      ln.abs().reshape(3 * ng), torch.zeros(3 * (n - ng), dtype=torch.float64)))
     flat.backward(torch.from_numpy(np.asarray(grad, dtype=np.float64)))
     return theta.grad.numpy(), fr.grad.numpy(), ln.grad.numpy()
 
@@ -513,15 +527,17 @@ def emul_chain_loss(n, g, kin, x, xp, eps=1e-3):
     return loss, force, iters, grad
 
 
-@pytest.mark.parametrize('name', ['chain3', 'chain3r', 'slider3', 'tree4', 'tree6'])
+@pytest.mark.parametrize('name', ['chain3', 'chain3r', 'slider3', 'tree4', 'tree4g', 'tree6'])
 def test_chain_and_tree_device_math_matches_reference_golden(name):
     """Three links in series with a rotated off-axis second joint (CHAIN3_TREE), the same with every box in a ROTATED
     collision frame (CHAIN3R_TREE), a hinge followed by a SLIDING joint (SLIDER3_TREE), a BRANCHING four-link tree (TREE4_TREE:
-    two links off the root, a third off one of them) and a six-link tree (TREE6_TREE, the largest instantiation): loss,
+    two links off the root, a third off one of them), the same tree with its boxes spread UNEVENLY over the links (TREE4G_TREE:
+    two on the root, none on two links) and a six-link tree (TREE6_TREE, the largest instantiation): loss,
     parameter gradients and one time step against the REFERENCE's
     own contactnets_loss / sim_step run on the oracle's tree callables (oracle/gen_golden_chain.py)."""
-    from oracle.callables import CHAIN3_TREE, CHAIN3R_TREE, SLIDER3_TREE, TREE4_TREE, TREE6_TREE
-    tree = {'chain3': CHAIN3_TREE, 'chain3r': CHAIN3R_TREE, 'slider3': SLIDER3_TREE, 'tree4': TREE4_TREE, 'tree6': TREE6_TREE}[name]
+    from oracle.callables import CHAIN3_TREE, CHAIN3R_TREE, SLIDER3_TREE, TREE4_TREE, TREE4G_TREE, TREE6_TREE
+    tree = {'chain3': CHAIN3_TREE, 'chain3r': CHAIN3R_TREE, 'slider3': SLIDER3_TREE, 'tree4': TREE4_TREE,
+            'tree4g': TREE4G_TREE, 'tree6': TREE6_TREE}[name]
     n = tree.n_bodies
     g = load_golden(name)
     kin = chain_kin_rows(tree)

@@ -326,7 +326,16 @@ def test_branching_tree_spec_and_what_is_still_refused(assets_dir, tmp_path):
     assert (spec.kind, spec.n_q, spec.n_v, spec.n_x, spec.n_contacts) == ('chain', 10, 9, 19, 16)
     assert [j.parent for j in spec.joints] == [0, 0, 2] and [j.child for j in spec.joints] == [1, 2, 3]
     _, _, _, kin, n = s._chain_params(torch.device('cpu'))
-    assert n == 4 and np.allclose(kin.numpy().reshape(4, 29), chain_kin_rows(TREE4_TREE), rtol=0, atol=1e-15)
+    assert n == 4 and np.allclose(kin.numpy().reshape(4, 31), chain_kin_rows(TREE4_TREE), rtol=0, atol=1e-15)
+    # boxes spread unevenly over the links (two on the root, none on links 1 and 2): box slots with their own link index
+    from oracle.callables import TREE4G_TREE
+    sg = MultibodyLearnableSystem({'tree4g': os.path.join(assets_dir, 'tree4g.urdf')}, 0.0068)
+    assert [g.body for g in sg.multibody_terms.spec.geometries] == [0, 0, 3, -1] and sg.multibody_terms.spec.n_contacts == 12
+    _, mu_g, half_g, kin_g, n_g = sg._chain_params(torch.device('cpu'))
+    assert n_g == 4 and mu_g.shape == (4,) and half_g.shape == (12,) and (half_g[9:] == 0).all()
+    assert np.allclose(kin_g.numpy().reshape(4, 31), chain_kin_rows(TREE4G_TREE), rtol=0, atol=1e-15)
+    assert sorted(k for k, _ in sg.named_parameters() if 'length_params' in k) == [
+        f'multibody_terms.contact_terms.geometries.{i}.length_params' for i in range(3)]
     text = open(os.path.join(assets_dir, 'tree4.urdf')).read()
     # the joint to link 3 declared before the joint to link 2: joint order would no longer be link order
     j2 = text[text.index('<joint name="joint_2"'):text.index('<joint name="joint_3"')]
@@ -358,7 +367,7 @@ def test_chain_spec_carries_rotated_joint_frames(assets_dir):
     assert spec.collision_pairs == [(3, 0), (3, 1), (3, 2)]
     inertia, mu, half, kin, n = s._chain_params(torch.device('cpu'))
     assert n == 3 and inertia.shape == (30,) and mu.shape == (3,) and half.shape == (9,)
-    assert np.allclose(kin.numpy().reshape(3, 29), chain_kin_rows(CHAIN3_TREE), rtol=0, atol=1e-15)
+    assert np.allclose(kin.numpy().reshape(3, 31), chain_kin_rows(CHAIN3_TREE), rtol=0, atol=1e-15)
     names = [k for k, _ in s.named_parameters()]
     assert 'multibody_terms.contact_terms.geometries.2.length_params' in names
     x = torch.zeros(2, 17, dtype=torch.float64)
