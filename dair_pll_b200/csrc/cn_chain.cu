@@ -125,6 +125,36 @@ int launch_chain_rollout(const double* x0, const double* inertia, const double* 
   return e == cudaSuccess ? DPLL_OK : (int)e;
 }
 
+// Dense terms export (MultibodyTerms.forward, multibody_terms.py:584-609) for a tree; one sample per thread.
+template <typename T, int N>
+__global__ void __launch_bounds__(kChThreads)
+chain_terms_kernel(const T* __restrict__ q, const T* __restrict__ v, const T* __restrict__ inertia, const T* __restrict__ mu,
+                   const T* __restrict__ half, const T* __restrict__ kin, int n_boxes, int64_t B, T* __restrict__ M,
+                   T* __restrict__ J, T* __restrict__ phi, T* __restrict__ acc, T* __restrict__ D) {
+  constexpr int NV = 6 + N - 1, NQ = 7 + N - 1;
+  cn::ChainParams<T, N> P;
+  cn::chain_params_init<T, N>(P, inertia, mu, half, kin, T(1), T(1));
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int nc = 4 * n_boxes, kk = 3 * nc;
+  T qs[NQ], vs[NV];
+  for (int i = 0; i < NQ; ++i) qs[i] = q[b * NQ + i];
+  for (int i = 0; i < NV; ++i) vs[i] = v[b * NV + i];
+  // outputs are assembled in place (global memory): M, J and D are this sample's own rows
+  cn::chain_terms_sample<T, N>(P, qs, vs, n_boxes, M + b * NV * NV, J + b * kk * NV, phi + b * nc, acc + b * NV,
+                               D ? D + b * kk * kk : (T*)nullptr);
+}
+
+template <int N>
+int launch_chain_terms(const double* q, const double* v, const double* inertia, const double* mu, const double* half,
+                       const double* kin, int n_boxes, int64_t B, double* M, double* J, double* phi, double* acc, double* D,
+                       cudaStream_t st) {
+  const int blocks = (int)((B + kChThreads - 1) / kChThreads);
+  chain_terms_kernel<double, N><<<blocks, kChThreads, 0, st>>>(q, v, inertia, mu, half, kin, n_boxes, B, M, J, phi, acc, D);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPLL_OK : (int)e;
+}
+
 }  // namespace
 
 extern "C" {
@@ -164,6 +194,23 @@ int dpll_chain_rollout_f64(int32_t n_links, const double* x0, const double* iner
     case 4: return launch_chain_rollout<4>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, st);
     case 5: return launch_chain_rollout<5>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, st);
     case 6: return launch_chain_rollout<6>(x0, inertia, mu_pair, half, kin, dt, eps, B, steps, traj, st);
+    default: return DPLL_EINVAL;
+  }
+}
+
+int dpll_chain_terms_f64(int32_t n_links, int32_t n_boxes, const double* q, const double* v, const double* inertia,
+                         const double* mu_pair, const double* half, const double* kin, int64_t B, double* M, double* J,
+                         double* phi, double* acc, double* delassus, void* stream) {
+  if (B < 0 || n_boxes < 1 || n_boxes > n_links || !inertia || !mu_pair || !half || !kin) return DPLL_EINVAL;
+  if (B > 0 && (!q || !v || !M || !J || !phi || !acc)) return DPLL_EINVAL;
+  if (B == 0) return DPLL_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (n_links) {
+    case 2: return launch_chain_terms<2>(q, v, inertia, mu_pair, half, kin, n_boxes, B, M, J, phi, acc, delassus, st);
+    case 3: return launch_chain_terms<3>(q, v, inertia, mu_pair, half, kin, n_boxes, B, M, J, phi, acc, delassus, st);
+    case 4: return launch_chain_terms<4>(q, v, inertia, mu_pair, half, kin, n_boxes, B, M, J, phi, acc, delassus, st);
+    case 5: return launch_chain_terms<5>(q, v, inertia, mu_pair, half, kin, n_boxes, B, M, J, phi, acc, delassus, st);
+    case 6: return launch_chain_terms<6>(q, v, inertia, mu_pair, half, kin, n_boxes, B, M, J, phi, acc, delassus, st);
     default: return DPLL_EINVAL;
   }
 }

@@ -604,4 +604,93 @@ CN_HD int chain_step_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg,
   return it;
 }
 
+// ---------------------------------------------------------------------------
+// Dense dynamics terms of a tree in the reference's own coordinates and ordering, for callers of MultibodyTerms.forward
+// (multibody_terms.py:584-609): M (NV x NV), J (3 nc x NV) = [J_n (nc rows) ; mu J_t (x, y interleaved per contact,
+// 2 nc rows)] (:401-426), phi (nc), contact-free acceleration (NV), Delassus operator D = J M^-1 J^T (3 nc x 3 nc, nullable),
+// nc = 4 n_boxes: the contacts of the first n_boxes box slots (the system's boxes in their order), each box by ascending
+// vertex index.  State velocity v = [w_body0 ; v_world ; joint rates] = T^T u^ with T = blkdiag(R_0, I3, I) (orthogonal), so
+// M = T^T M^ T, J = J^ T, a = T^T a^  (as elbow_terms_sample does for the two-body system).
+// ---------------------------------------------------------------------------
+template <typename T, int N>
+CN_HD void chain_terms_sample(const ChainParams<T, N>& P, const T* q, const T* v, int n_boxes, T* M, T* J, T* phi, T* acc, T* D) {
+  constexpr int NV = 6 + N - 1, NC = 4 * N;
+  const int nc = 4 * n_boxes, kk = 3 * nc;
+  ChainKin<T, N> K;
+  ChainProb<T, N> S;
+  chain_kinematics<T, N>(P, q, K);
+  T vW[NV], F[NV], MW[NV * NV], LM[NV * NV], LMinv[NV], aW[NV];
+  chain_to_world<T, N>(K.R[0], v, vW);
+  chain_mass_force<T, N>(P, K, vW, MW, F, (T*)nullptr);
+  for (int i = 0; i < NV * NV; ++i) LM[i] = MW[i];
+  chol_factor<T, NV>(LM, LMinv);
+  chol_solve<T, NV>(LM, LMinv, F, aW);
+  const T* R = K.R[0];
+  rot3t(R, aW, acc);
+  for (int i = 3; i < NV; ++i) acc[i] = aW[i];
+  T tmp[NV * NV];
+  for (int i = 0; i < NV; ++i) {                      // tmp = M^ T  (columns 0..2 rotated)
+    const T* row = MW + NV * i;
+    for (int j = 0; j < 3; ++j) tmp[NV * i + j] = row[0] * R[j] + row[1] * R[3 + j] + row[2] * R[6 + j];
+    for (int j = 3; j < NV; ++j) tmp[NV * i + j] = row[j];
+  }
+  for (int j = 0; j < NV; ++j) {                      // M = T^T tmp  (rows 0..2 rotated)
+    for (int i = 0; i < 3; ++i) M[NV * i + j] = R[i] * tmp[j] + R[3 + i] * tmp[NV + j] + R[6 + i] * tmp[2 * NV + j];
+    for (int i = 3; i < NV; ++i) M[NV * i + j] = tmp[NV * i + j];
+  }
+  chain_contacts<T, N>(P, K, S);
+  for (int c = 0; c < nc && c < NC; ++c) {
+    const T mu = P.mu[c >> 2];
+    const T rho[3] = {S.rho[3 * c], S.rho[3 * c + 1], S.rho[3 * c + 2]};
+    phi[c] = rho[2] + q[6];
+    T E[9];                                            // (-S(rho)) R_0: the angular block in state coordinates
+    for (int j = 0; j < 3; ++j) {
+      const T col[3] = {R[j], R[3 + j], R[6 + j]};
+      T cr[3];
+      cross3(rho, col, cr);
+      for (int i = 0; i < 3; ++i) E[3 * i + j] = -cr[i];
+    }
+    T* jn = J + NV * c;
+    T* jx = J + NV * (nc + 2 * c);
+    T* jy = J + NV * (nc + 2 * c + 1);
+    for (int j = 0; j < 3; ++j) {
+      jn[j] = E[6 + j]; jx[j] = mu * E[j]; jy[j] = mu * E[3 + j];
+      jn[3 + j] = j == 2 ? T(1) : T(0);
+      jx[3 + j] = j == 0 ? mu : T(0);
+      jy[3 + j] = j == 1 ? mu : T(0);
+    }
+    for (int j = 1; j < N; ++j) {
+      const T* hcol = S.hc + 3 * (c * (N - 1) + (j - 1));
+      jn[5 + j] = hcol[2]; jx[5 + j] = mu * hcol[0]; jy[5 + j] = mu * hcol[1];
+    }
+  }
+  if (D) {
+    // D = J M^-1 J^T with M = L L^T (Cholesky of the state-coordinate M): D_ab = W_a . W_b with W_r = L^-1 J_r^T.  The
+    // W_r are recomputed per pair instead of being kept (3 nc x NV doubles per thread): this is an export, not a hot loop.
+    T LS[NV * NV], LSinv[NV];
+    for (int i = 0; i < NV * NV; ++i) LS[i] = M[i];
+    chol_factor<T, NV>(LS, LSinv);
+    for (int a = 0; a < kk; ++a) {
+      T Wa[NV];
+      for (int i = 0; i < NV; ++i) {
+        T sa = J[NV * a + i];
+        for (int m = 0; m < i; ++m) sa -= LS[NV * i + m] * Wa[m];
+        Wa[i] = sa * LSinv[i];
+      }
+      for (int b = 0; b <= a; ++b) {
+        T Wb[NV];
+        for (int i = 0; i < NV; ++i) {
+          T sb = J[NV * b + i];
+          for (int m = 0; m < i; ++m) sb -= LS[NV * i + m] * Wb[m];
+          Wb[i] = sb * LSinv[i];
+        }
+        T sdot = T(0);
+        for (int k = 0; k < NV; ++k) sdot += Wa[k] * Wb[k];
+        D[kk * a + b] = sdot;
+        D[kk * b + a] = sdot;
+      }
+    }
+  }
+}
+
 }  // namespace cn

@@ -116,28 +116,12 @@ class MultibodyLearnableSystem(System):
         spec = self.multibody_terms.spec
         n = len(spec.bodies)
         boxes = [g for g in spec.geometries if g.body >= 0]
-        key = ('chain', str(device))
-        if key not in self._kin_cache:
-            rows = []
-            for b in range(n):
-                if b == 0:
-                    rows += [0.] * 3 + [1., 0., 0., 0., 1., 0., 0., 0., 1.] + [0., 0., 1.]
-                    parent, sliding = 0, 0.
-                else:
-                    j = spec.joints[b - 1]          # joint b - 1 is the one whose child is link b (SystemSpec orders them)
-                    rows += [*j.origin, *j.rotation(), *j.axis]
-                    parent, sliding = j.parent, float(j.prismatic)
-                if b < len(boxes):
-                    g = boxes[b]
-                    rows += [*g.offset, float(parent), *g.rotation().reshape(-1).tolist(), sliding, float(g.body), 1.]
-                else:
-                    rows += [0., 0., 0., float(parent), 1., 0., 0., 0., 1., 0., 0., 0., 1., sliding, 0., 0.]
-            self._kin_cache[key] = torch.tensor(rows, dtype=torch.float64, device=device)
+        kin = self.multibody_terms.chain_kinematic_table(device)
         mu, half = mu.reshape(-1), torch.cat(half)
         if len(boxes) < n:
             mu = torch.cat((mu, mu.new_ones(n - len(boxes))))
             half = torch.cat((half, half.new_zeros(3 * (n - len(boxes)))))
-        return inertia.reshape(-1), mu, half, self._kin_cache[key], n
+        return inertia.reshape(-1), mu, half, kin, n
 
     def _elbow_witness_points(self, q: Tensor) -> Tensor:
         """(B, 8) configurations -> (B, 8, 3) witness points of the two learned geometries against the

@@ -155,11 +155,46 @@ class MultibodyTerms(Module):
                                 *self.spec.geometries[1].offset], dtype=q.dtype, device=q.device)
             D, M, J, phi, acc = ops.elbow_terms(q.reshape(-1, 8), v.reshape(-1, 7), inertia.detach().reshape(20),
                                                 mu.detach().reshape(2), torch.cat(half).detach(), kin)
+        elif self.spec.kind == 'chain':
+            n = len(self.spec.bodies)
+            n_boxes = len(half)
+            kin = self.chain_kinematic_table(q.device)
+            mu_s, half_s = mu.detach().reshape(-1), torch.cat(half).detach()
+            if n_boxes < n:                      # the kernels have n box slots; the unused ones are switched off in `kin`
+                mu_s = torch.cat((mu_s, mu_s.new_ones(n - n_boxes)))
+                half_s = torch.cat((half_s, half_s.new_zeros(3 * (n - n_boxes))))
+            D, M, J, phi, acc = ops.chain_terms(q.reshape(-1, 7 + n - 1), v.reshape(-1, 6 + n - 1), inertia.detach().reshape(-1),
+                                                mu_s, half_s, kin, n, n_boxes)
         else:
             raise NotImplementedError(f'no kernel specialisation for system kind {self.spec.kind!r}')
         n_v, k, n_c = M.shape[-1], J.shape[-2], phi.shape[-1]
         return (D.reshape(batch + (k, k)), M.reshape(batch + (n_v, n_v)), J.reshape(batch + (k, n_v)),
                 phi.reshape(batch + (n_c,)), acc.reshape(batch + (n_v,)))
+
+    def chain_kinematic_table(self, device) -> Tensor:
+        """(n * 31,) float64 kinematic table of the generic tree kernels (include/dair_pll_b200.h, dpll_chain_loss_f64):
+        per row the link's joint and the box slot of the same index; created once per device."""
+        key = str(device)
+        cache = self.__dict__.setdefault('_chain_kin_cache', {})
+        if key not in cache:
+            spec = self.spec
+            boxes = [g for g in spec.geometries if g.body >= 0]
+            rows = []
+            for b in range(len(spec.bodies)):
+                if b == 0:
+                    rows += [0.] * 3 + [1., 0., 0., 0., 1., 0., 0., 0., 1.] + [0., 0., 1.]
+                    parent, sliding = 0, 0.
+                else:
+                    j = spec.joints[b - 1]          # joint b - 1 is the one whose child is link b (SystemSpec orders them)
+                    rows += [*j.origin, *j.rotation(), *j.axis]
+                    parent, sliding = j.parent, float(j.prismatic)
+                if b < len(boxes):
+                    g = boxes[b]
+                    rows += [*g.offset, float(parent), *g.rotation().reshape(-1).tolist(), sliding, float(g.body), 1.]
+                else:
+                    rows += [0., 0., 0., float(parent), 1., 0., 0., 0., 1., 0., 0., 0., 1., sliding, 0., 0.]
+            cache[key] = torch.tensor(rows, dtype=torch.float64, device=device)
+        return cache[key]
 
     def scalars_and_meshes(self):
         """Summary scalars per body and, for learned (``DeepSupportConvex``) geometries, the extracted mesh with its

@@ -864,6 +864,28 @@ def elbow_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Te
     return D, M, J, phi, acc
 
 
+def chain_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, kin: Tensor, n: int, n_boxes: int):
+    """``dpll_chain_terms_f64``: (delassus (B,12g,12g), M (B,nv,nv), J (B,12g,nv), phi (B,4g), acc (B,nv)) of a tree of ``n``
+    links with ``g = n_boxes`` boxes, in the order ``MultibodyTerms.forward`` returns them (multibody_terms.py:584-609).
+    fp64 only, no autograd."""
+    _check_inputs(q, v, inertia, mu_pair, half, kin)
+    if q.dtype != torch.float64:
+        raise TypeError('chain_terms is provided in float64')
+    q, v = q.contiguous(), v.contiguous()
+    B, dev, nv, k = q.shape[0], q.device, 6 + n - 1, 12 * n_boxes
+    M = torch.empty((B, nv, nv), dtype=q.dtype, device=dev)
+    J = torch.empty((B, k, nv), dtype=q.dtype, device=dev)
+    phi = torch.empty((B, 4 * n_boxes), dtype=q.dtype, device=dev)
+    acc = torch.empty((B, nv), dtype=q.dtype, device=dev)
+    D = torch.empty((B, k, k), dtype=q.dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().dpll_chain_terms_f64(n, n_boxes, _ptr(q), _ptr(v), _ptr(inertia.contiguous()), _ptr(mu_pair.contiguous()),
+                                              _ptr(half.contiguous()), _ptr(kin.contiguous()), B, _ptr(M), _ptr(J),
+                                              _ptr(phi), _ptr(acc), _ptr(D), _stream())
+    _lib.check(rc, 'dpll_chain_terms')
+    return D, M, J, phi, acc
+
+
 class LeafPrepare(torch.autograd.Function):
     """Learnable leaves -> callable-level parameters, one launch each way (``dpll_leaf_prepare_f64`` /
     ``dpll_leaf_backward_f64``, csrc/cn_leaf.cu): theta (n_bodies, 10) -> inertia (n_bodies, 10); friction_params

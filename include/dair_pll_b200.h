@@ -44,7 +44,7 @@ extern "C" {
 #define DPLL_EWORKSPACE (-2) /* workspace too small */
 #define DPLL_ECOMM (-3)      /* a peer did not arrive within the exchange's timeout */
 
-#define DPLL_VERSION 209     /* bumped with every change of a signature below; the binding checks it */
+#define DPLL_VERSION 210     /* bumped with every change of a signature below; the binding checks it */
 
 #define DPLL_CUBE_NX 13
 #define DPLL_CUBE_NC 4
@@ -473,6 +473,17 @@ int dpll_chain_rollout_f64(int32_t n_links, const double* x0, const double* iner
 int dpll_chain_rollout_grad_f64(int32_t n_links, const double* x0, const double* inertia, const double* mu_pair,
                                 const double* half, const double* kin, double dt, double eps, int64_t B, int32_t steps,
                                 const double* xbar, double* gparams, double* gx0, void* stream);
+
+/*
+ * Dense terms export of MultibodyTerms.forward (multibody_terms.py:584-609) for a tree (same tables as dpll_chain_loss_f64):
+ * q (B, 7 + n - 1), v (B, n_v = 6 + n - 1) -> M (B, n_v, n_v), J (B, 12 n_boxes, n_v) = [normals (4 n_boxes) ; mu (x, y)
+ * interleaved per contact (8 n_boxes)], phi (B, 4 n_boxes), contact-free acceleration (B, n_v), delassus (B, 12 n_boxes,
+ * 12 n_boxes) (nullable) -- the contacts of the first n_boxes box slots (1 <= n_boxes <= n_links), each box by ascending
+ * vertex index; state coordinates as the reference's (body-frame angular velocity of link 0).
+ */
+int dpll_chain_terms_f64(int32_t n_links, int32_t n_boxes, const double* q, const double* v, const double* inertia,
+                         const double* mu_pair, const double* half, const double* kin, int64_t B, double* M, double* J,
+                         double* phi, double* acc, double* delassus, void* stream);
 
 /*
  * Parameter preparation of any system and its chain rule, one launch each (csrc/cn_leaf.cu): theta (n_bodies, 10)

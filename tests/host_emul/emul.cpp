@@ -39,6 +39,19 @@ static int chain_step_emul(const double* x, const double* inertia, const double*
   for (int64_t b = 0; b < B; ++b) chain_step_sample<double, N>(P, cfg, x + NX * b, xn + NX * b);
   return 0;
 }
+template <int N>
+static int chain_terms_emul(int g, const double* q, const double* v, const double* inertia, const double* mu, const double* half,
+                            const double* kin, int64_t B, double* M, double* J, double* phi, double* acc, double* D) {
+  constexpr int NV = 6 + N - 1, NQ = 7 + N - 1;
+  ChainParams<double, N> P;
+  chain_params_init<double, N>(P, inertia, mu, half, kin, 1.0, 1.0);
+  const int nc = 4 * g, kk = 3 * nc;
+  for (int64_t b = 0; b < B; ++b)
+    chain_terms_sample<double, N>(P, q + NQ * b, v + NV * b, g, M + NV * NV * b, J + kk * NV * b, phi + nc * b, acc + NV * b,
+                                  D + kk * kk * b);
+  return 0;
+}
+
 extern "C" {
 // digit planes of the tensor-core support-point kernel (cn_icnn_tc.cuh): column of n weights -> digits, value the planes
 // stand for, image offsets
@@ -178,6 +191,13 @@ int emul_elbow_terms_f64(const double* q, const double* v, const double* inertia
   for (int64_t b = 0; b < B; ++b)
     elbow_terms_sample<double>(P, q + 8 * b, v + 7 * b, M + 49 * b, J + 168 * b, phi + 8 * b, acc + 7 * b, D + 576 * b);
   return 0;
+}
+int emul_chain_terms_f64(int n, int g, const double* q, const double* v, const double* inertia, const double* mu,
+                         const double* half, const double* kin, int64_t B, double* M, double* J, double* phi, double* acc,
+                         double* D) {
+  if (n == 3) return chain_terms_emul<3>(g, q, v, inertia, mu, half, kin, B, M, J, phi, acc, D);
+  if (n == 4) return chain_terms_emul<4>(g, q, v, inertia, mu, half, kin, B, M, J, phi, acc, D);
+  return 1;
 }
 // theta -> inertia vector and the reverse-direction product g^T J via dual numbers (as the reduce kernel does)
 int emul_theta_chain_f64(const double* theta, const double* g_inertia, double* inertia, double* grad_theta) {

@@ -547,6 +547,33 @@ def test_generic_chain_and_tree_match_reference_golden(name, n_links, assets_dir
     assert max_rel_to_scale(np.stack([a.reshape(3) for a in gl]), g['roll_grad_length']) < tol
 
 
+@pytest.mark.parametrize('name', ['chain3r', 'slider3', 'tree4g', 'tree6'])
+def test_tree_dense_terms_match_oracle(name, assets_dir):
+    """MultibodyTerms.forward for the generic trees (multibody_terms.py:584-609; dpll_chain_terms_f64) through the module
+    API: the (delassus, M, J, phi, acceleration) tuple against the oracle's tree callables at the golden states -- rotated
+    collision frames, the sliding joint, fewer boxes than links, six links."""
+    from oracle import contactnets_oracle as co
+    from oracle.callables import CHAIN3R_TREE, SLIDER3_TREE, TREE4G_TREE, TREE6_TREE, TreeCallables
+    from tests.util import oracle_params_from_golden
+    tree = {'chain3r': CHAIN3R_TREE, 'slider3': SLIDER3_TREE, 'tree4g': TREE4G_TREE, 'tree6': TREE6_TREE}[name]
+    n, n_boxes = tree.n_bodies, len(tree.geometry_body) - 1
+    g = load_golden(name)
+    s = _chain_system(g, os.path.join(assets_dir, f'{name}.urdf'), n)
+    xp = torch.from_numpy(g['x_plus']).to(DEV)
+    nq, nv, k = 7 + n - 1, 6 + n - 1, 12 * n_boxes
+    D, M, J, phi, acc = s.multibody_terms(xp[:, :nq], xp[:, nq:], None)
+    assert D.shape[1:] == (k, k) and M.shape[1:] == (nv, nv) and J.shape[1:] == (k, nv) and phi.shape[1:] == (4 * n_boxes,)
+    P = oracle_params_from_golden(g, requires_grad=False)
+    with torch.no_grad():
+        Mo, Jo, phio, acco = co.multibody_terms(TreeCallables(tree), P, xp.cpu()[:, :nq], xp.cpu()[:, nq:])
+        Do = Jo @ torch.linalg.solve(Mo, Jo.transpose(-1, -2))
+    assert np.abs(M.cpu().numpy() - Mo.numpy()).max() < 1e-14 * max(1.0, np.abs(Mo.numpy()).max())
+    assert np.abs(J.cpu().numpy() - Jo.numpy()).max() < 1e-13
+    assert np.abs(phi.cpu().numpy() - phio.numpy()).max() < 1e-14
+    assert np.abs(acc.cpu().numpy() - acco.numpy()).max() < 1e-9 * max(1.0, np.abs(acco.numpy()).max())
+    assert np.abs(D.cpu().numpy() - Do.numpy()).max() < 1e-9 * np.abs(Do.numpy()).max()
+
+
 @pytest.mark.parametrize('name', ['elbow_nominal', 'elbow_perturbed'])
 def test_generic_chain_two_links_reproduces_the_elbow_kernels(name, assets_dir):
     """The generic recursion at N = 2 against the reference goldens of the elbow AND against the specialised kernels."""

@@ -614,3 +614,35 @@ def test_tensor_core_digit_planes_are_exact_to_42_bits():
                 for i in (0, 7, 8, 31, 32, 255):
                     seen[lib.emul_tc_image_offset(k, s_, j, i)] += 1
     assert seen.max() == 1 and seen.sum() == 3 * 6 * 36
+
+
+@pytest.mark.parametrize('name', ['chain3r', 'slider3', 'tree4g'])
+def test_tree_dense_terms_match_oracle(name):
+    """MultibodyTerms.forward for the generic trees (dpll_chain_terms_f64's per-sample code): M, J, phi, the contact-free
+    acceleration and the Delassus operator against the oracle's tree callables at the golden states -- rotated collision
+    frames, the sliding joint, boxes spread unevenly over the links (fewer boxes than links)."""
+    from oracle.callables import CHAIN3R_TREE, SLIDER3_TREE, TREE4G_TREE
+    from tests.util import oracle_params_from_golden
+    tree = {'chain3r': CHAIN3R_TREE, 'slider3': SLIDER3_TREE, 'tree4g': TREE4G_TREE}[name]
+    n, n_boxes = tree.n_bodies, len(tree.geometry_body) - 1
+    g = load_golden(name)
+    lib = host_emulation_lib()
+    inertia, mu, half = chain_kernel_level_params(g, n)
+    kin = chain_kin_rows(tree)
+    xp = g['x_plus']
+    B, nq, nv, k = xp.shape[0], 7 + n - 1, 6 + n - 1, 12 * n_boxes
+    q, v = np.ascontiguousarray(xp[:, :nq]), np.ascontiguousarray(xp[:, nq:])
+    M, J, phi = np.zeros((B, nv, nv)), np.zeros((B, k, nv)), np.zeros((B, 4 * n_boxes))
+    acc, D = np.zeros((B, nv)), np.zeros((B, k, k))
+    rc = lib.emul_chain_terms_f64(ctypes.c_int(n), ctypes.c_int(n_boxes), dptr(q), dptr(v), dptr(inertia), dptr(mu), dptr(half),
+                                  dptr(kin), ctypes.c_int64(B), dptr(M), dptr(J), dptr(phi), dptr(acc), dptr(D))
+    assert rc == 0
+    P = oracle_params_from_golden(g, requires_grad=False)
+    with torch.no_grad():
+        Mo, Jo, phio, acco = co.multibody_terms(TreeCallables(tree), P, torch.from_numpy(q), torch.from_numpy(v))
+        Do = Jo @ torch.linalg.solve(Mo, Jo.transpose(-1, -2))
+    assert np.abs(M - Mo.numpy()).max() < 1e-14 * max(1.0, np.abs(Mo.numpy()).max())
+    assert np.abs(J - Jo.numpy()).max() < 1e-13
+    assert np.abs(phi - phio.numpy()).max() < 1e-14
+    assert np.abs(acc - acco.numpy()).max() < 1e-9 * max(1.0, np.abs(acco.numpy()).max())
+    assert np.abs(D - Do.numpy()).max() < 1e-9 * np.abs(Do.numpy()).max()
