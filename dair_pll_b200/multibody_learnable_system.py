@@ -142,7 +142,11 @@ class MultibodyLearnableSystem(System):
         # third row of R2 = R1 Rot(axis, th):  r Rot = r cos + (r x a) sin + a (a.r)(1 - cos)
         row2 = row * torch.cos(th) + torch.linalg.cross(row, axis.expand_as(row)) * torch.sin(th) \
             + axis * (row @ axis)[:, None] * (1 - torch.cos(th))
-        return torch.cat((geoms[0].get_vertices(-row), geoms[1].get_vertices(-row2)), -2)
+        # per geometry: a learned shape answers through its network, a box (mixed box / mesh systems) with its corners --
+        # ordinary torch functions of the box lengths, so the kernel's d loss / d witness point reaches them by autograd
+        def points(geom, d):
+            return geom.get_vertices(d) if isinstance(geom, DeepSupportConvex) else geom.support_points(d)
+        return torch.cat((points(geoms[0], -row), points(geoms[1], -row2)), -2)
 
     # -- ContactNets loss --------------------------------------------------
     def contactnets_loss(self, x: Tensor, u: Tensor, x_plus: Tensor, loss_pool=None) -> Tensor:

@@ -237,8 +237,9 @@ class SystemSpec:
                 raise NotImplementedError('the generic tree kernels take <box> collision geometries')
             if not 1 <= len(geometries) <= len(bodies):
                 raise NotImplementedError('the generic tree kernels take between one box and as many boxes as there are links')
-        if len({g.kind for g in geometries}) > 1:
-            raise NotImplementedError('mixed box / mesh collision geometries in one system are not supported')
+        if len({g.kind for g in geometries}) > 1 and kind != 'elbow':
+            # (the two-body kernels take witness points per link, so one link may carry a box and the other a learned mesh)
+            raise NotImplementedError('mixed collision geometry kinds are supported for the two-body (elbow) system only')
         ground = len(geometries)
         geometries.append(GeometrySpec(-1, 'plane', (0., 0., 0.), None, None, 1.0))
         pairs = [(ground, g) for g in range(ground)]

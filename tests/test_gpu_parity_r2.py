@@ -884,3 +884,47 @@ def test_elbow_mesh_summary_carries_the_learned_meshes(assets_dir):
         for axis in 'xyz':
             assert summary.scalars[f'{name}_diameter_{axis}'] > 0
             assert f'{name}_center_{axis}' in summary.scalars
+
+
+def test_mixed_box_and_learned_geometry_elbow_matches_reference_golden(assets_dir):
+    """The two-body system with a Box on the first link and a DeepSupportConvex on the second (mixed collision geometry):
+    the box's corners and the network's support points meet as witness points of the same kernels; loss, the gradients of
+    theta, friction, the BOX LENGTHS and every network weight, and a 3-step rollout against a golden produced by the
+    reference's own classes (oracle/gen_golden_mixed.py), 1e-9."""
+    from dair_pll_b200.deep_support_function import HomogeneousICNN
+    from dair_pll_b200.geometry import Box, DeepSupportConvex
+    g = load_golden('elbow_mixed_w64')
+    s = MultibodyLearnableSystem({'elbow': os.path.join(assets_dir, 'elbow_mixed.urdf')}, float(g['dt']))
+    geoms = s.multibody_terms.contact_terms.geometries
+    assert isinstance(geoms[0], Box) and isinstance(geoms[1], DeepSupportConvex) and s._kind() == 'elbow'
+    geoms[1].network = HomogeneousICNN(2, 64)
+    geoms[1].perturbations = torch.from_numpy(g['net_perturbations'])
+    pre = 'multibody_terms.contact_terms.geometries.'
+    s.load_state_dict({'multibody_terms.lagrangian_terms.inertial_parameters': torch.from_numpy(g['theta']),
+                       'multibody_terms.contact_terms.friction_params': torch.from_numpy(g['friction_params']),
+                       pre + '0.length_params': torch.from_numpy(g['box_length_params']),
+                       pre + '1.network.input_weights.0': torch.from_numpy(g['net_Wd0']),
+                       pre + '1.network.input_weights.1': torch.from_numpy(g['net_Wd1']),
+                       pre + '1.network.hidden_weights.0': torch.from_numpy(g['net_Wh']),
+                       pre + '1.network.output_weight': torch.from_numpy(g['net_wout'])})
+    s = s.to(DEV)
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    loss = s.contactnets_loss(x, None, xp)
+    loss.mean().backward()
+    l = loss.detach().cpu().numpy()
+    assert np.abs(l - g['loss']).max() < 1e-12
+    assert rel_err(l, g['loss'], 1e-9).max() < 1e-9
+    mt = s.multibody_terms
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(geoms[0].length_params.grad.cpu().numpy(), g['grad_box_length_params']) < 1e-9
+    net = geoms[1].network
+    for k, p_ in (('Wd0', net.input_weights[0]), ('Wd1', net.input_weights[1]), ('Wh', net.hidden_weights[0]),
+                  ('wout', net.output_weight)):
+        assert max_rel_to_scale(p_.grad.cpu().numpy(), g[f'net_grad_{k}']) < 1e-9, k
+    x0 = torch.from_numpy(g['sim_x0']).to(DEV)
+    with torch.no_grad():
+        traj, _ = s.simulate(x0.unsqueeze(-2), torch.zeros(x0.shape[0], 1, device=DEV), g['sim_traj'].shape[1] - 1)
+    t = traj.cpu().numpy()
+    assert np.abs(t[:, 1] - g['sim_traj'][:, 1]).max() < 1e-9
+    assert np.abs(t - g['sim_traj']).max() < 1e-6

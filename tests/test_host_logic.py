@@ -403,3 +403,19 @@ def test_extract_mesh_of_a_box_support_function_and_cpu_refusal():
         assert len(net.hidden_weights) == depth - 1 and len(net.input_weights) == depth
         with pytest.raises(RuntimeError, match='no CPU path'):
             net(torch.zeros(4, 3, dtype=torch.float64))
+
+
+def test_mixed_box_and_mesh_elbow_parses(assets_dir):
+    """A box on one link and a learned mesh on the other is the two-body kind with witness points per link (no box lengths
+    in the kernel-level parameters: the box's corners reach the kernels as points); mixed kinds on other systems are refused."""
+    from dair_pll_b200.geometry import Box, DeepSupportConvex
+    s = MultibodyLearnableSystem({'elbow': os.path.join(assets_dir, 'elbow_mixed.urdf')}, 0.0068)
+    spec = s.multibody_terms.spec
+    assert spec.kind == 'elbow' and [g.kind for g in spec.geometries] == ['box', 'mesh', 'plane']
+    geoms = s.multibody_terms.contact_terms.geometries
+    assert isinstance(geoms[0], Box) and isinstance(geoms[1], DeepSupportConvex)
+    _, _, half = s.multibody_terms.kernel_parameters(torch.float64)
+    assert half == []
+    names = [k for k, _ in s.named_parameters()]
+    assert 'multibody_terms.contact_terms.geometries.0.length_params' in names
+    assert 'multibody_terms.contact_terms.geometries.1.network.output_weight' in names
