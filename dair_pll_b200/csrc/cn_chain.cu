@@ -22,7 +22,10 @@ __global__ void __launch_bounds__(kChThreads)
 chain_loss_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __restrict__ weight,
                   const T* __restrict__ inertia, const T* __restrict__ mu, const T* __restrict__ half,
                   const T* __restrict__ kin, T dt, T eps, int64_t B, T* __restrict__ loss, T* __restrict__ force,
-                  int32_t* __restrict__ iters, T* __restrict__ partials, int want_grad) {
+                  int32_t* __restrict__ iters, T* __restrict__ partials, int want_grad,
+                  const T* __restrict__ pts = nullptr, unsigned npts = 0u, T* __restrict__ grad_pts = nullptr) {
+  // pts (nullable, (B, N, 4, 3)): witness points per box slot instead of box corners (half is then unused and may be
+  // null); grad_pts (nullable, same shape): w_b d loss_b / d pts_b
   constexpr int NX = 13 + 2 * (N - 1), NP = 14 * N, NF = 12 * N;
   cn::ChainParams<T, N> P;
   cn::chain_params_init<T, N>(P, inertia, mu, half, kin, dt, eps);
@@ -35,9 +38,13 @@ chain_loss_kernel(const T* __restrict__ x, const T* __restrict__ xp, const T* __
     for (int i = 0; i < NX; ++i) { xs[i] = x[b * NX + i]; xps[i] = xp[b * NX + i]; }
     for (int i = 0; i < NP; ++i) gs[i] = T(0);
     int it;
-    const T l = cn::chain_loss_sample<T, N>(P, cfg, xs, xps, want_grad ? gs : (T*)nullptr, force ? fo : (T*)nullptr, &it);
+    T ps[12 * N], gps[12 * N];
+    if (pts) for (int i = 0; i < 12 * N; ++i) ps[i] = pts[b * 12 * N + i];
+    const T l = cn::chain_loss_sample<T, N>(P, cfg, xs, xps, (want_grad || grad_pts) ? gs : (T*)nullptr, force ? fo : (T*)nullptr, &it,
+                                            pts ? ps : (const T*)nullptr, npts, grad_pts ? gps : (T*)nullptr);
     if (force) for (int i = 0; i < NF; ++i) force[b * NF + i] = fo[i];
     const T w = weight ? weight[b] : T(1);
+    if (grad_pts) for (int i = 0; i < 12 * N; ++i) grad_pts[b * 12 * N + i] = w * gps[i];
     for (int i = 0; i < NP; ++i) acc[i] += w * gs[i];
     if (loss) loss[b] = l;
     acc[NP] += l;
@@ -97,7 +104,7 @@ template <int N>
 int launch_chain_loss(const double* x, const double* xp, const double* weight, const double* inertia, const double* mu,
                       const double* half, const double* kin, double dt, double eps, int64_t B, double* loss, double* force,
                       int32_t* iters, double* grad, double* loss_sum, void* workspace, size_t workspace_bytes,
-                      cudaStream_t st) {
+                      cudaStream_t st, const double* pts = nullptr, unsigned npts = 0u, double* grad_pts = nullptr) {
   const bool want_red = grad || loss_sum;
   if (want_red && (!workspace || workspace_bytes < dpll_workspace_bytes())) return DPLL_EWORKSPACE;
   int64_t need = (B + kChThreads - 1) / kChThreads;
@@ -105,7 +112,7 @@ int launch_chain_loss(const double* x, const double* xp, const double* weight, c
   if (blocks < 1) blocks = 1;
   double* partials = want_red ? static_cast<double*>(workspace) : nullptr;
   chain_loss_kernel<double, N><<<blocks, kChThreads, 0, st>>>(x, xp, weight, inertia, mu, half, kin, dt, eps, B, loss, force,
-                                                             iters, partials, grad ? 1 : 0);
+                                                             iters, partials, grad ? 1 : 0, pts, npts, grad_pts);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (want_red) {
@@ -213,6 +220,25 @@ int dpll_chain_terms_f64(int32_t n_links, int32_t n_boxes, const double* q, cons
     case 6: return launch_chain_terms<6>(q, v, inertia, mu_pair, half, kin, n_boxes, B, M, J, phi, acc, delassus, st);
     default: return DPLL_EINVAL;
   }
+}
+
+int dpll_chain_loss_pts_f64(int32_t n_links, const double* x, const double* x_plus, const double* weight, const double* inertia,
+                            const double* mu_pair, const double* kin, const double* pts, uint32_t n_pts_packed, double dt,
+                            double eps, int64_t B, double* loss, double* grad_pts, double* grad, double* loss_sum,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || !inertia || !mu_pair || !kin) return DPLL_EINVAL;
+  if (B > 0 && (!x || !x_plus || !pts)) return DPLL_EINVAL;
+  if (B == 0) return DPLL_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define DPLL_CHAIN_PTS_CASE(NL)                                                                                               \
+  case NL:                                                                                                                    \
+    return launch_chain_loss<NL>(x, x_plus, weight, inertia, mu_pair, nullptr, kin, dt, eps, B, loss, nullptr, nullptr, grad,  \
+                                 loss_sum, workspace, workspace_bytes, st, pts, n_pts_packed, grad_pts);
+  switch (n_links) {
+    DPLL_CHAIN_PTS_CASE(2) DPLL_CHAIN_PTS_CASE(3) DPLL_CHAIN_PTS_CASE(4) DPLL_CHAIN_PTS_CASE(5) DPLL_CHAIN_PTS_CASE(6)
+    default: return DPLL_EINVAL;
+  }
+#undef DPLL_CHAIN_PTS_CASE
 }
 
 }  // extern "C"

@@ -45,7 +45,7 @@ template <typename T, int N> struct ChainParams {
   T dscale[6 + N - 1];
 };
 
-// inertia: N x 10, mu: N, half: N x 3, kin: N x CH_NKIN
+// inertia: N x 10, mu: N, half: N x 3 (nullable: witness-point entry points), kin: N x CH_NKIN
 template <typename T, int N>
 CN_HD void chain_params_init(ChainParams<T, N>& P, const T* inertia, const T* mu, const T* half, const T* kin, T dt, T eps) {
   T msum = T(0), Isum[3] = {T(0), T(0), T(0)};
@@ -65,7 +65,7 @@ CN_HD void chain_params_init(ChainParams<T, N>& P, const T* inertia, const T* mu
     B.Io[5] = B.Isym[5] - m * cy * cz;
     P.mu[b] = mu[b];
     const T* kn = kin + CH_NKIN * b;
-    for (int i = 0; i < 3; ++i) { P.h[b][i] = half[3 * b + i]; P.pJ[b][i] = kn[i]; P.axis[b][i] = kn[12 + i]; P.off[b][i] = kn[15 + i]; }
+    for (int i = 0; i < 3; ++i) { P.h[b][i] = half ? half[3 * b + i] : T(0); P.pJ[b][i] = kn[i]; P.axis[b][i] = kn[12 + i]; P.off[b][i] = kn[15 + i]; }
     for (int i = 0; i < 9; ++i) { P.Rfix[b][i] = kn[3 + i]; P.Rg[b][i] = kn[19 + i]; }
     // parent index travels as a number in the table; clamped to [0, b - 1] so that a bad table cannot index out of range
     int pb = b > 0 ? (int)to_double(kn[18]) : 0;
@@ -216,12 +216,42 @@ CN_HD void chain_mass_force(const ChainParams<T, N>& P, const ChainKin<T, N>& K,
 template <typename T, int N> struct ChainProb {
   static constexpr int NV = 6 + N - 1, NC = 4 * N;
   T M[NV * NV], rho[3 * NC], hc[3 * NC * (N - 1) + 1], q[3 * NC];
+  unsigned con;     // bit c set: contact c exists (box slots in use: all four corners; witness points: the first n of a slot)
 };
 
+// pts (nullable, 12 N): WITNESS POINTS instead of box corners -- contact c of slot b is the point pts[3 (4 b + c) ..] given in
+// the frame of the slot's link (the caller evaluates the shapes' support points in the direction -R_link^T e_z and places them:
+// a sphere's single point, a polygon's top vertices, a network's outputs, box corners in any collision frame); npts packs
+// the number of points of slot b in bits 3 b .. 3 b + 2 (0 .. 4).  Same contact machinery downstream.
 template <typename T, int N>
-CN_HD void chain_contacts(const ChainParams<T, N>& P, ChainKin<T, N>& K, ChainProb<T, N>& S) {
+CN_HD void chain_contacts(const ChainParams<T, N>& P, ChainKin<T, N>& K, ChainProb<T, N>& S, const T* pts = nullptr,
+                          unsigned npts = 0u) {
+  S.con = 0u;
   for (int b = 0; b < N; ++b) {             // b: box slot; l: the link it sits on
     const int l = P.glink[b];
+    if (pts) {
+      const int np = (int)((npts >> (3 * b)) & 7u);
+      K.sel[b] = 0u;
+      for (int c = 0; c < 4; ++c) {
+        const int cc = 4 * b + c;
+        const bool on = ((P.gon >> b) & 1u) && c < np;
+        T r[3] = {T(0), T(0), T(0)};
+        if (on) { rot3(K.R[l], pts + 3 * cc, r); S.con |= 1u << cc; }
+        for (int i = 0; i < 3; ++i) S.rho[3 * cc + i] = on ? K.o[l][i] + r[i] : T(0);
+        for (int j = 1; j < N; ++j) {
+          T hcol[3] = {T(0), T(0), T(0)};
+          if (on && ((K.anc[l] >> j) & 1u) && ((K.pris >> j) & 1u)) {
+            for (int i = 0; i < 3; ++i) hcol[i] = K.a[j][i];
+          } else if (on && ((K.anc[l] >> j) & 1u)) {
+            T dd[3];
+            for (int i = 0; i < 3; ++i) dd[i] = S.rho[3 * cc + i] - K.o[j][i];
+            cross3(K.a[j], dd, hcol);
+          }
+          for (int i = 0; i < 3; ++i) S.hc[3 * (cc * (N - 1) + (j - 1)) + i] = hcol[i];
+        }
+      }
+      continue;
+    }
     if (!((P.gon >> b) & 1u)) {
       // empty slot: its four contacts get a zero Jacobian here and a residual deep in the polar cone where the QP vector is
       // built (zero force, zero curvature), and take no part in the loss
@@ -240,6 +270,7 @@ CN_HD void chain_contacts(const ChainParams<T, N>& P, ChainKin<T, N>& K, ChainPr
     T d[3];
     rot3t(P.Rg[b], dl, d);
     K.sel[b] = cube_select_corners(d, P.h[b]);
+    S.con |= 15u << (4 * b);
     for (int c = 0; c < 4; ++c) {
       T pg[3], p[3], r[3];
       for (int k = 0; k < 3; ++k) pg[k] = sgn_bit<T>(K.sel[b], c, k) * P.h[b][k];
@@ -406,7 +437,7 @@ template <typename T, int N> CN_HD void chain_to_world(const T* R0, const T* v, 
 // nullable): [n (NC); (tx, ty) (NC)].
 template <typename T, int N>
 CN_HD T chain_loss_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, const T* x, const T* xp, T* grad,
-                          T* force_out, int* iters_out) {
+                          T* force_out, int* iters_out, const T* pts = nullptr, unsigned npts = 0u, T* grad_pts = nullptr) {
   constexpr int NV = 6 + N - 1, NC = 4 * N, NQ = 7 + N - 1;
   ChainKin<T, N> K;
   ChainProb<T, N> S;
@@ -420,7 +451,7 @@ CN_HD T chain_loss_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, c
   chol_factor<T, NV>(LM, LMinv);
   chol_solve<T, NV>(LM, LMinv, F, acc);
   for (int i = 0; i < NV; ++i) dv[i] = vp[i] - (vold[i] + P.dt * acc[i]);
-  chain_contacts<T, N>(P, K, S);
+  chain_contacts<T, N>(P, K, S, pts, npts);
   T pen = T(0);
   for (int c = 0; c < NC; ++c) {
     const T mu = P.mu[c >> 2];
@@ -430,7 +461,7 @@ CN_HD T chain_loss_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, c
     const T sx = mu * ev[0], sy = mu * ev[1];
     const T speed2 = sx * sx + sy * sy;
     const T speed = speed2 * t_rsqrt(t_max(speed2, t_tiny<T>()));
-    if (!((P.gon >> (c >> 2)) & 1u)) {           // empty box slot: deep in the polar cone, no penetration term
+    if (!((S.con >> c) & 1u)) {                   // no such contact: deep in the polar cone, no penetration term
       S.q[3 * c] = T(0); S.q[3 * c + 1] = T(0); S.q[3 * c + 2] = T(CH_OFF);
       continue;
     }
@@ -522,7 +553,10 @@ CN_HD T chain_loss_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, c
   }
   for (int c = 0; c < NC; ++c) {
     const int bi = c >> 2, cl = c & 3;           // bi: box slot (mu, half lengths); li: its link (kinematics)
-    if (!((P.gon >> bi) & 1u)) continue;
+    if (!((S.con >> c) & 1u)) {
+      if (grad_pts) for (int k = 0; k < 3; ++k) grad_pts[3 * c + k] = T(0);
+      continue;
+    }
     const int li = P.glink[bi];
     const T mu = P.mu[bi];
     const T* R = K.R[li];
@@ -548,6 +582,10 @@ CN_HD T chain_loss_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, c
     // d loss / d (corner in the link frame), taken back into the box frame: d corner / d h_k = Rg[:, k] sgn_k
     T gl[3], gg[3];
     for (int k = 0; k < 3; ++k) gl[k] = pB[k] + phibar * R[6 + k];
+    if (pts) {                                    // witness points: d loss / d (point in its link's frame) goes to the caller
+      if (grad_pts) for (int k = 0; k < 3; ++k) grad_pts[3 * c + k] = gl[k];
+      continue;
+    }
     rot3t(P.Rg[bi], gl, gg);
     for (int k = 0; k < 3; ++k) grad[11 * N + 3 * bi + k] += sgn_bit<T>(K.sel[bi], cl, k) * gg[k];
   }
@@ -556,7 +594,8 @@ CN_HD T chain_loss_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, c
 
 // learnable time step (forward_dynamics :260-304 + the Lie-group update): x (NQ + NV) -> xn
 template <typename T, int N>
-CN_HD int chain_step_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, const T* x, T* xn) {
+CN_HD int chain_step_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg, const T* x, T* xn, const T* pts = nullptr,
+                            unsigned npts = 0u) {
   constexpr int NV = 6 + N - 1, NC = 4 * N, NQ = 7 + N - 1;
   ChainKin<T, N> K;
   ChainProb<T, N> S;
@@ -568,15 +607,16 @@ CN_HD int chain_step_sample(const ChainParams<T, N>& P, const SolverCfg<T>& cfg,
   chol_factor<T, NV>(LM, LMinv);
   chol_solve<T, NV>(LM, LMinv, F, acc);
   for (int i = 0; i < NV; ++i) vm[i] = vW[i] + P.dt * acc[i];
-  chain_contacts<T, N>(P, K, S);
+  chain_contacts<T, N>(P, K, S, pts, npts);
   const T inv_dt = T(1) / P.dt;
   for (int c = 0; c < NC; ++c) {
     const T mu = P.mu[c >> 2];
     T e[3];
     chain_point_vel<T, N>(S, c, vm, e);
-    S.q[3 * c] = mu * e[0];
-    S.q[3 * c + 1] = mu * e[1];
-    S.q[3 * c + 2] = ((P.gon >> (c >> 2)) & 1u) ? e[2] + (S.rho[3 * c + 2] + x[6]) * inv_dt : T(CH_OFF);
+    const bool on = (S.con >> c) & 1u;             // (a contact that does not exist: deep in the polar cone, as in the loss)
+    S.q[3 * c] = on ? mu * e[0] : T(0);
+    S.q[3 * c + 1] = on ? mu * e[1] : T(0);
+    S.q[3 * c + 2] = on ? e[2] + (S.rho[3 * c + 2] + x[6]) * inv_dt : T(CH_OFF);
   }
   T u[NV];
   for (int i = 0; i < NV; ++i) u[i] = T(0);

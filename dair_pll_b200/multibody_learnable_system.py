@@ -108,6 +108,10 @@ class MultibodyLearnableSystem(System):
         kin, _ = self._elbow_kin(dtype, device)
         return inertia.reshape(20), mu.reshape(2), (torch.cat(half) if half else None), kin
 
+    def _chain_boxes_only(self) -> bool:
+        from dair_pll_b200.geometry import Box, Plane
+        return all(isinstance(g, (Box, Plane)) for g in self.multibody_terms.contact_terms.geometries)
+
     def _chain_params(self, device: torch.device):
         """Generic kinematic tree: (inertia (n*10), mu (n), half (n*3), kin (n*31), n), float64.  The kernels have n box
         slots; the system's boxes (any distribution over the links, at most n) fill the first ones, the rest are switched off
@@ -195,6 +199,19 @@ class MultibodyLearnableSystem(System):
                 # mean() / sum() of the result reuse the launch's own reduction and fused gradient (ops.BatchLoss)
                 return ops.batch_loss(loss.reshape(batch), sums, means, 28, (inertia, mu, half),
                                       iters.reshape(batch) if self.record_newton_iters else None)
+        elif self._kind() == 'chain' and not self._chain_boxes_only():
+            # other shapes than boxes on the links: each shape's support points (host side, ordinary torch functions of the
+            # shape parameters) become the witness points of the tree kernels
+            mt = self.multibody_terms
+            n = len(mt.spec.bodies)
+            inertia, mu, _ = mt.kernel_parameters(torch.float64)
+            mu = mu.reshape(-1)
+            if mu.shape[0] < n:
+                mu = torch.cat((mu, mu.new_ones(n - mu.shape[0])))
+            xf, xpf = self._flat(x).to(torch.float64), self._flat(x_plus).to(torch.float64)
+            pts, packed = mt.chain_witness_points(xpf[:, :7 + n - 1])
+            loss = ops.ChainWitnessPointLoss.apply(xf, xpf, inertia.reshape(-1), mu, pts, mt.chain_kinematic_table(x.device, True),
+                                                   n, packed, float(self.dt), LOSS_EPS).to(x.dtype)
         elif self._kind() == 'chain':
             inertia, mu, half, kin, n = self._chain_params(x.device)
             loss = ops.ChainContactNetsLoss.apply(self._flat(x).to(torch.float64), self._flat(x_plus).to(torch.float64),
@@ -264,6 +281,12 @@ class MultibodyLearnableSystem(System):
             else:
                 traj, _ = ops.elbow_rollout(self._flat(x_0), inertia.detach(), mu.detach(), half.detach(), kin,
                                             float(self.dt), steps, STEP_EPS)
+        elif self._kind() == 'chain' and not self._chain_boxes_only():
+            # (the step with witness points exists in the device math and agrees with the reference on the host emulation;
+            # its GPU entry point is not shipped: see DESIGN.md section 8)
+            raise NotImplementedError('the time step of trees with non-box shapes has no GPU entry point yet (the ContactNets '
+                                      'loss of such systems is provided; rollouts: boxes on trees, every shape on one or two '
+                                      'bodies)')
         elif self._kind() == 'chain':
             inertia, mu, half, kin, n = self._chain_params(x_0.device)
             xf = self._flat(x_0).to(torch.float64)

@@ -156,6 +156,9 @@ class MultibodyTerms(Module):
             D, M, J, phi, acc = ops.elbow_terms(q.reshape(-1, 8), v.reshape(-1, 7), inertia.detach().reshape(20),
                                                 mu.detach().reshape(2), torch.cat(half).detach(), kin)
         elif self.spec.kind == 'chain':
+            if not half:
+                raise NotImplementedError('dense terms export is provided for box geometries (other shapes reach the tree '
+                                          'kernels as witness points)')
             n = len(self.spec.bodies)
             n_boxes = len(half)
             kin = self.chain_kinematic_table(q.device)
@@ -171,10 +174,11 @@ class MultibodyTerms(Module):
         return (D.reshape(batch + (k, k)), M.reshape(batch + (n_v, n_v)), J.reshape(batch + (k, n_v)),
                 phi.reshape(batch + (n_c,)), acc.reshape(batch + (n_v,)))
 
-    def chain_kinematic_table(self, device) -> Tensor:
+    def chain_kinematic_table(self, device, witness: bool = False) -> Tensor:
         """(n * 31,) float64 kinematic table of the generic tree kernels (include/dair_pll_b200.h, dpll_chain_loss_f64):
-        per row the link's joint and the box slot of the same index; created once per device."""
-        key = str(device)
+        per row the link's joint and the box slot of the same index; created once per device.  ``witness``: the table of the
+        witness-point entry points -- the points arrive in link coordinates, so the slots carry no placement of their own."""
+        key = (str(device), witness)
         cache = self.__dict__.setdefault('_chain_kin_cache', {})
         if key not in cache:
             spec = self.spec
@@ -188,13 +192,65 @@ class MultibodyTerms(Module):
                     j = spec.joints[b - 1]          # joint b - 1 is the one whose child is link b (SystemSpec orders them)
                     rows += [*j.origin, *j.rotation(), *j.axis]
                     parent, sliding = j.parent, float(j.prismatic)
-                if b < len(boxes):
+                if b < len(boxes) and witness:
+                    rows += [0., 0., 0., float(parent), 1., 0., 0., 0., 1., 0., 0., 0., 1., sliding, float(boxes[b].body), 1.]
+                elif b < len(boxes):
                     g = boxes[b]
                     rows += [*g.offset, float(parent), *g.rotation().reshape(-1).tolist(), sliding, float(g.body), 1.]
                 else:
                     rows += [0., 0., 0., float(parent), 1., 0., 0., 0., 1., 0., 0., 0., 1., sliding, 0., 0.]
             cache[key] = torch.tensor(rows, dtype=torch.float64, device=device)
         return cache[key]
+
+    def chain_link_rotations(self, q: Tensor) -> Tensor:
+        """(B, n_q) configurations of a tree -> (B, n, 3, 3) world rotations of its links: R_0 from the (not necessarily unit)
+        base quaternion as Drake forms it, R_b = R_parent Rfix_b Rot(axis_b, q_b) (a sliding joint keeps its joint frame's
+        orientation).  Plain torch: the witness points of non-box shapes are evaluated on the host side of the kernels."""
+        from dair_pll_b200.system_spec import _rpy_matrix
+        w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        s = 2.0 / (w * w + x * x + y * y + z * z)
+        R0 = torch.stack((torch.stack((1 - s * (y * y + z * z), s * (x * y - w * z), s * (x * z + w * y)), -1),
+                          torch.stack((s * (x * y + w * z), 1 - s * (x * x + z * z), s * (y * z - w * x)), -1),
+                          torch.stack((s * (x * z - w * y), s * (y * z + w * x), 1 - s * (x * x + y * y)), -1)), -2)
+        rots = [R0]
+        for b, joint in enumerate(self.spec.joints, start=1):
+            Rfix = _rpy_matrix(joint.rpy).to(q)
+            R = rots[joint.parent] @ Rfix
+            if not joint.prismatic:
+                a = torch.tensor(joint.axis, dtype=q.dtype, device=q.device)
+                K = torch.zeros(3, 3, dtype=q.dtype, device=q.device)
+                K[0, 1], K[0, 2], K[1, 0], K[1, 2], K[2, 0], K[2, 1] = -a[2], a[1], a[2], -a[0], -a[1], a[0]
+                th = q[:, 6 + b]
+                Rj = torch.eye(3, dtype=q.dtype, device=q.device) + torch.sin(th)[:, None, None] * K \
+                    + (1 - torch.cos(th))[:, None, None] * (K @ K)
+                R = R @ Rj
+            rots.append(R)
+        return torch.stack(rots, 1)
+
+    def chain_witness_points(self, q: Tensor):
+        """Witness points of every body geometry of a tree against the ground, in the frame of the geometry's LINK:
+        ((B, n_slots, 4, 3) with unused rows zero, per-slot point counts packed 3 bits each) -- each shape's support points
+        (geometry.py:553-582) in the direction -R_WG^T e_z, placed by the collision frame's offset and rotation."""
+        R = self.chain_link_rotations(q)
+        n = len(self.spec.bodies)
+        pts, packed = [], 0
+        bodies = [g for g in self.spec.geometries if g.body >= 0]
+        for slot, (gs, geom) in enumerate(zip(bodies, self.contact_terms.geometries)):
+            d_link = -R[:, gs.body, 2, :]
+            Rg = gs.rotation().to(q)
+            off = torch.tensor(gs.offset, dtype=q.dtype, device=q.device)
+            d_geom = d_link @ Rg
+            from dair_pll_b200.geometry import DeepSupportConvex
+            p = geom.get_vertices(d_geom) if isinstance(geom, DeepSupportConvex) else geom.support_points(d_geom)
+            k = p.shape[-2]
+            p = p @ Rg.t() + off
+            if k < 4:
+                p = torch.cat((p, p.new_zeros(p.shape[:-2] + (4 - k, 3))), -2)
+            pts.append(p)
+            packed |= k << (3 * slot)
+        for _ in range(n - len(bodies)):
+            pts.append(q.new_zeros((q.shape[0], 4, 3)))
+        return torch.stack(pts, 1), packed
 
     def scalars_and_meshes(self):
         """Summary scalars per body and, for learned (``DeepSupportConvex``) geometries, the extracted mesh with its

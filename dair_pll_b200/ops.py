@@ -864,6 +864,55 @@ def elbow_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Te
     return D, M, J, phi, acc
 
 
+class ChainWitnessPointLoss(torch.autograd.Function):
+    """ContactNets loss of a generic tree of ``n`` links whose contact sets are given by witness points ``pts``
+    (B, n, 4, 3) in link coordinates (``n_pts_packed``: points per slot, 3 bits each) -- spheres, polygons, learned meshes,
+    boxes in any frame on any link: ``dpll_chain_loss_pts_f64``.  Differentiable w.r.t. inertia (n,10), mu_pair (n) and
+    ``pts``; float64."""
+
+    @staticmethod
+    def forward(ctx, x, x_plus, inertia, mu_pair, pts, kin, n, n_pts_packed, dt, eps):
+        _check_inputs(x, x_plus, inertia, mu_pair, pts, kin)
+        if x.dtype != torch.float64:
+            raise TypeError('the generic tree kernels are provided in float64')
+        n_x = 13 + 2 * (n - 1)
+        x, x_plus, pts = x.contiguous(), x_plus.contiguous(), pts.contiguous()
+        B, dev = x.shape[0], x.device
+        if x.dim() != 2 or x.shape[1] != n_x or x_plus.shape != x.shape or tuple(pts.shape) != (B, n, 4, 3):
+            raise ValueError(f'expected (B,{n_x}) states and (B,{n},4,3) points, got {tuple(x.shape)} / {tuple(pts.shape)}')
+        loss = torch.empty(B, dtype=x.dtype, device=dev)
+        gpts = torch.empty_like(pts)
+        ws = _workspace(dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().dpll_chain_loss_pts_f64(n, _ptr(x), _ptr(x_plus), None, _ptr(inertia.contiguous()),
+                                                     _ptr(mu_pair.contiguous()), _ptr(kin.contiguous()), _ptr(pts), n_pts_packed,
+                                                     dt, eps, B, _ptr(loss), _ptr(gpts), None, None, _ptr(ws), ws.numel(),
+                                                     _stream())
+        _lib.check(rc, 'dpll_chain_loss_pts')
+        ctx.args = (n, n_pts_packed, dt, eps)
+        ctx.shapes = (inertia.shape, mu_pair.shape)
+        ctx.save_for_backward(gpts, x, x_plus, inertia, mu_pair, pts, kin)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        gpts, x, x_plus, inertia, mu_pair, pts, kin = ctx.saved_tensors
+        n, packed, dt, eps = ctx.args
+        B, dev = x.shape[0], x.device
+        g = torch.zeros(14 * n, dtype=x.dtype, device=dev)
+        if B > 0:
+            w = grad_loss.contiguous()
+            ws = _workspace(dev)
+            with torch.cuda.device(dev):
+                rc = _lib.load().dpll_chain_loss_pts_f64(n, _ptr(x), _ptr(x_plus), _ptr(w), _ptr(inertia.contiguous()),
+                                                         _ptr(mu_pair.contiguous()), _ptr(kin.contiguous()), _ptr(pts), packed,
+                                                         dt, eps, B, None, None, _ptr(g), None, _ptr(ws), ws.numel(), _stream())
+            _lib.check(rc, 'dpll_chain_loss_pts')
+        s_in, s_mu = ctx.shapes
+        return (None, None, g[:10 * n].reshape(s_in), g[10 * n:11 * n].reshape(s_mu), gpts * grad_loss.reshape(-1, 1, 1, 1), None,
+                None, None, None, None)
+
+
 def chain_terms(q: Tensor, v: Tensor, inertia: Tensor, mu_pair: Tensor, half: Tensor, kin: Tensor, n: int, n_boxes: int):
     """``dpll_chain_terms_f64``: (delassus (B,12g,12g), M (B,nv,nv), J (B,12g,nv), phi (B,4g), acc (B,nv)) of a tree of ``n``
     links with ``g = n_boxes`` boxes, in the order ``MultibodyTerms.forward`` returns them (multibody_terms.py:584-609).

@@ -233,13 +233,12 @@ class SystemSpec:
         elif kind == 'chain':
             # the generic tree kernels have as many box slots as links; a slot may sit on any link, so the boxes can be spread
             # over the links in any way (several on one link, none on another) as long as there are no more boxes than links
-            if any(g.kind != 'box' for g in geometries):
-                raise NotImplementedError('the generic tree kernels take <box> collision geometries')
+            # (boxes go to the kernels as lengths; spheres, meshes and any mix of shapes as witness points per slot)
             if not 1 <= len(geometries) <= len(bodies):
-                raise NotImplementedError('the generic tree kernels take between one box and as many boxes as there are links')
-        if len({g.kind for g in geometries}) > 1 and kind != 'elbow':
-            # (the two-body kernels take witness points per link, so one link may carry a box and the other a learned mesh)
-            raise NotImplementedError('mixed collision geometry kinds are supported for the two-body (elbow) system only')
+                raise NotImplementedError('the generic tree kernels take between one collision geometry and as many as there '
+                                          'are links')
+        # (mixed geometry kinds: the two-body and the tree kernels take witness points per link / slot, so the links may carry
+        # different kinds of shapes; a single body has one geometry)
         ground = len(geometries)
         geometries.append(GeometrySpec(-1, 'plane', (0., 0., 0.), None, None, 1.0))
         pairs = [(ground, g) for g in range(ground)]

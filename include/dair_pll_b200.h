@@ -44,7 +44,7 @@ extern "C" {
 #define DPLL_EWORKSPACE (-2) /* workspace too small */
 #define DPLL_ECOMM (-3)      /* a peer did not arrive within the exchange's timeout */
 
-#define DPLL_VERSION 210     /* bumped with every change of a signature below; the binding checks it */
+#define DPLL_VERSION 212     /* bumped with every change of a signature below; the binding checks it */
 
 #define DPLL_CUBE_NX 13
 #define DPLL_CUBE_NC 4
@@ -473,6 +473,22 @@ int dpll_chain_rollout_f64(int32_t n_links, const double* x0, const double* iner
 int dpll_chain_rollout_grad_f64(int32_t n_links, const double* x0, const double* inertia, const double* mu_pair,
                                 const double* half, const double* kin, double dt, double eps, int64_t B, int32_t steps,
                                 const double* xbar, double* gparams, double* gx0, void* stream);
+
+/*
+ * The tree LOSS kernel with WITNESS POINTS instead of box corners (as dpll_body_loss_pts_f64 / the elbow's `pts` for the
+ * specialised systems): any plane-convex shape on any link -- GeometryCollider.collide_plane_convex, geometry.py:553-582,
+ * is "the shape's support points in the direction -R_WG^T e_z", whatever the shape (Sphere :415-456, Polygon :220-252,
+ * DeepSupportConvex :255-325, a Box in any collision frame).  pts (B, n, 4, 3): per box SLOT up to four points in the frame
+ * of the slot's LINK (the caller evaluates and places them); n_pts_packed: the number of points of slot b in bits
+ * 3 b .. 3 b + 2; kin as for dpll_chain_loss_f64 with the slots' own offset / rotation unused (the points are already in
+ * link coordinates).  grad_pts (B, n, 4, 3) nullable: w_b d loss_b / d pts_b; grad (14 n) nullable: [d/d inertia (10 n) |
+ * d/d mu_pair (n) | zeros (3 n)] of sum_b w_b loss_b.  (The time step with witness points exists in the device math,
+ * chain_step_sample, and is checked against the reference on the host emulation; it has no entry point yet.)
+ */
+int dpll_chain_loss_pts_f64(int32_t n_links, const double* x, const double* x_plus, const double* weight,
+                            const double* inertia, const double* mu_pair, const double* kin, const double* pts,
+                            uint32_t n_pts_packed, double dt, double eps, int64_t B, double* loss, double* grad_pts,
+                            double* grad, double* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Dense terms export of MultibodyTerms.forward (multibody_terms.py:584-609) for a tree (same tables as dpll_chain_loss_f64):

@@ -117,8 +117,54 @@ def make(tree, half, coms, friction, name, n, m):
     print('wrote', path, 'mean loss', float(loss.mean()))
 
 
+def make_shapes():
+    """tests/golden/chain3s.npz: CHAIN3_TREE's kinematics with the reference's Box on link 0, Sphere on link 1 and Polygon
+    on link 2 (geometry.py:359-413, 415-456, 220-252) -- the fixture of the witness-point form of the tree kernels."""
+    from dair_pll.geometry import Box, Polygon, Sphere
+    from torch.nn import Module, Parameter
+    from oracle.gen_golden_shapes import POLY
+    tree = CHAIN3_TREE
+    calls = TreeCallables(tree)
+    box = Box(torch.from_numpy(HALF[0]), 4)
+    sphere = Sphere.__new__(Sphere)                 # (Sphere.__init__ cannot run as written: see gen_golden_shapes.py)
+    Module.__init__(sphere)
+    sphere.length_param = Parameter(torch.tensor(0.03, dtype=torch.float64))
+    poly = Polygon(torch.from_numpy(POLY) * 0.6, 4)
+    gen = torch.Generator().manual_seed(7)
+    rows = []
+    for com0 in ((0., 0., 0.), (0.035, 0., 0.), (0.03, -0.01, 0.)):
+        mass = 0.3 + 0.1 * torch.rand(1, generator=gen, dtype=torch.float64)
+        c = torch.tensor(com0, dtype=torch.float64) + 0.004 * (2 * torch.rand(3, generator=gen, dtype=torch.float64) - 1)
+        diag = 6e-4 * (1 + 0.2 * (2 * torch.rand(3, generator=gen, dtype=torch.float64) - 1))
+        offd = 2e-5 * (2 * torch.rand(3, generator=gen, dtype=torch.float64) - 1)
+        rows.append(torch.cat((mass, mass * c, diag, offd)))
+    pi_cm = torch.stack(rows)
+    friction = torch.tensor([0.3, 0.45, 0.25, 0.9], dtype=torch.float64)
+    system = ref_shim.build_reference_system(tree, DT, pi_cm, friction, None, body_geometries=[box, sphere, poly])
+    n = 160
+    x = states(n, 21, calls, np.array([HALF[0], [0.03, 0.03, 0.03], np.abs(POLY * 0.6).max(0)]))
+    with torch.no_grad():
+        nxt, _ = system.integrator.step(x, torch.zeros(n, 1))
+    x_plus = nxt.clone()
+    x_plus[:, 9:] += 0.02 * torch.randn(n, 8, generator=torch.Generator().manual_seed(22), dtype=torch.float64)
+    loss = system.contactnets_loss(x, torch.zeros(n, 0), x_plus)
+    loss.mean().backward()
+    mt = system.multibody_terms
+    out = dict(dt=np.array(DT), x=x.numpy(), x_plus=x_plus.numpy(), x_next=nxt.numpy(), pi_cm=pi_cm.numpy(),
+               theta=mt.lagrangian_terms.inertial_parameters.detach().numpy(), friction_params=friction.numpy(),
+               loss=loss.detach().numpy(), grad_theta=mt.lagrangian_terms.inertial_parameters.grad.numpy(),
+               grad_friction=mt.contact_terms.friction_params.grad.numpy(),
+               box_length_params=box.length_params.detach().numpy(), grad_box_length_params=box.length_params.grad.numpy(),
+               sphere_radius=sphere.length_param.detach().numpy(), grad_sphere_radius=sphere.length_param.grad.numpy(),
+               polygon_vertices=poly.vertices.detach().numpy(), grad_polygon_vertices=poly.vertices.grad.numpy())
+    path = os.path.join(ROOT, 'tests', 'golden', 'chain3s.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, 'mean loss', float(loss.mean()))
+
+
 def main():
     ref_shim.import_reference()
+    make_shapes()
     make(CHAIN3_TREE, HALF, ((0., 0., 0.), (0.035, 0., 0.), (0.03, -0.01, 0.)), [0.3, 0.45, 0.25, 0.9], 'chain3', 256, 24)
     make(CHAIN3R_TREE, HALF, ((0., 0., 0.), (0.035, 0., 0.), (0.03, -0.01, 0.)), [0.3, 0.45, 0.25, 0.9], 'chain3r', 128, 8)
     make(SLIDER3_TREE, HALF, ((0., 0., 0.), (0.035, 0., 0.), (0.02, -0.01, 0.)), [0.3, 0.45, 0.25, 0.9], 'slider3', 128, 8)

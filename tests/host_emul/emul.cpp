@@ -52,6 +52,35 @@ static int chain_terms_emul(int g, const double* q, const double* v, const doubl
   return 0;
 }
 
+template <int N>
+static int chain_loss_pts_emul(const double* x, const double* xp, const double* inertia, const double* mu, const double* kin,
+                               const double* pts, unsigned npts, double dt, double eps, int64_t B, double* loss, double* grad,
+                               double* grad_pts) {
+  constexpr int NX = 13 + 2 * (N - 1);
+  double half[3 * N] = {0};
+  ChainParams<double, N> P;
+  chain_params_init<double, N>(P, inertia, mu, half, kin, dt, eps);
+  const SolverCfg<double> cfg = default_cfg<double>();
+  for (int i = 0; i < 14 * N; ++i) grad[i] = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    int it;
+    loss[b] = chain_loss_sample<double, N>(P, cfg, x + NX * b, xp + NX * b, grad, nullptr, &it, pts + 12 * N * b, npts,
+                                           grad_pts + 12 * N * b);
+  }
+  return 0;
+}
+template <int N>
+static int chain_step_pts_emul(const double* x, const double* inertia, const double* mu, const double* kin, const double* pts,
+                               unsigned npts, double dt, double eps, int64_t B, double* xn) {
+  constexpr int NX = 13 + 2 * (N - 1);
+  double half[3 * N] = {0};
+  ChainParams<double, N> P;
+  chain_params_init<double, N>(P, inertia, mu, half, kin, dt, eps);
+  const SolverCfg<double> cfg = default_cfg<double>();
+  for (int64_t b = 0; b < B; ++b) chain_step_sample<double, N>(P, cfg, x + NX * b, xn + NX * b, pts + 12 * N * b, npts);
+  return 0;
+}
+
 extern "C" {
 // digit planes of the tensor-core support-point kernel (cn_icnn_tc.cuh): column of n weights -> digits, value the planes
 // stand for, image offsets
@@ -191,6 +220,19 @@ int emul_elbow_terms_f64(const double* q, const double* v, const double* inertia
   for (int64_t b = 0; b < B; ++b)
     elbow_terms_sample<double>(P, q + 8 * b, v + 7 * b, M + 49 * b, J + 168 * b, phi + 8 * b, acc + 7 * b, D + 576 * b);
   return 0;
+}
+int emul_chain_loss_pts_f64(int n, const double* x, const double* xp, const double* inertia, const double* mu,
+                            const double* kin, const double* pts, unsigned npts, double dt, double eps, int64_t B,
+                            double* loss, double* grad, double* grad_pts) {
+  if (n == 3) return chain_loss_pts_emul<3>(x, xp, inertia, mu, kin, pts, npts, dt, eps, B, loss, grad, grad_pts);
+  if (n == 4) return chain_loss_pts_emul<4>(x, xp, inertia, mu, kin, pts, npts, dt, eps, B, loss, grad, grad_pts);
+  return 1;
+}
+int emul_chain_step_pts_f64(int n, const double* x, const double* inertia, const double* mu, const double* kin,
+                            const double* pts, unsigned npts, double dt, double eps, int64_t B, double* xn) {
+  if (n == 3) return chain_step_pts_emul<3>(x, inertia, mu, kin, pts, npts, dt, eps, B, xn);
+  if (n == 4) return chain_step_pts_emul<4>(x, inertia, mu, kin, pts, npts, dt, eps, B, xn);
+  return 1;
 }
 int emul_chain_terms_f64(int n, int g, const double* q, const double* v, const double* inertia, const double* mu,
                          const double* half, const double* kin, int64_t B, double* M, double* J, double* phi, double* acc,

@@ -928,3 +928,36 @@ def test_mixed_box_and_learned_geometry_elbow_matches_reference_golden(assets_di
     t = traj.cpu().numpy()
     assert np.abs(t[:, 1] - g['sim_traj'][:, 1]).max() < 1e-9
     assert np.abs(t - g['sim_traj']).max() < 1e-6
+
+
+def test_tree_with_sphere_and_polygon_links_matches_reference_golden(assets_dir):
+    """Any plane-convex shape on any link of a tree (witness-point form of the tree kernels, dpll_chain_loss_pts_f64): the three-link chain with the reference's Box on link 0, Sphere on link 1 and Polygon on link 2
+    through the module API -- the shapes' support points from the host side (torch forward kinematics + the geometry
+    classes), everything else in the kernels -- against a golden produced by the reference's own classes
+    (oracle/gen_golden_chain.py:make_shapes): losses and the gradients of theta, friction, box lengths, radius and vertices at 1e-9."""
+    from dair_pll_b200.geometry import Polygon, Sphere
+    g = load_golden('chain3s')
+    s = MultibodyLearnableSystem({'chain3': os.path.join(assets_dir, 'chain3.urdf')}, float(g['dt']))
+    ct = s.multibody_terms.contact_terms
+    ct.geometries[1] = Sphere(torch.from_numpy(g['sphere_radius']))
+    ct.geometries[2] = Polygon(torch.from_numpy(g['polygon_vertices']), 4)
+    with torch.no_grad():
+        s.multibody_terms.lagrangian_terms.inertial_parameters.copy_(torch.from_numpy(g['theta']))
+        ct.friction_params.copy_(torch.from_numpy(g['friction_params']))
+        ct.geometries[0].length_params.copy_(torch.from_numpy(g['box_length_params']))
+    s = s.to(DEV)
+    x, xp = torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['x_plus']).to(DEV)
+    loss = s.contactnets_loss(x, None, xp)
+    loss.mean().backward()
+    l = loss.detach().cpu().numpy()
+    assert np.abs(l - g['loss']).max() < 1e-12
+    assert rel_err(l, g['loss'], 1e-9).max() < 1e-9
+    mt = s.multibody_terms
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.cpu().numpy(), g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(mt.contact_terms.friction_params.grad.cpu().numpy(), g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(ct.geometries[0].length_params.grad.cpu().numpy(), g['grad_box_length_params']) < 1e-9
+    assert max_rel_to_scale(ct.geometries[1].length_param.grad.cpu().numpy(), g['grad_sphere_radius']) < 1e-9
+    assert max_rel_to_scale(ct.geometries[2].vertices.grad.cpu().numpy(), g['grad_polygon_vertices']) < 1e-9
+    # (the time step of such systems has no GPU entry point yet: refused, not approximated)
+    with pytest.raises(NotImplementedError), torch.no_grad():
+        s.simulate(x.unsqueeze(-2), torch.zeros(x.shape[0], 1, device=DEV), 2)

@@ -646,3 +646,58 @@ def test_tree_dense_terms_match_oracle(name):
     assert np.abs(phi - phio.numpy()).max() < 1e-14
     assert np.abs(acc - acco.numpy()).max() < 1e-9 * max(1.0, np.abs(acco.numpy()).max())
     assert np.abs(D - Do.numpy()).max() < 1e-9 * np.abs(Do.numpy()).max()
+
+
+def test_tree_witness_point_device_math_matches_reference_golden(assets_dir):
+    """The witness-point form of the tree kernels (chain_loss_sample / chain_step_sample with pts): CHAIN3_TREE's kinematics
+    with the reference's Box on link 0, Sphere on link 1 and Polygon on link 2 (oracle/gen_golden_chain.py:make_shapes) --
+    the shapes' support points come from the product's own host code (MultibodyTerms.chain_witness_points: torch forward
+    kinematics + the geometry classes), the loss, its gradients w.r.t. theta, friction, the box lengths, the sphere's radius
+    and the polygon's vertices (chain rule through the points) and one time step from the device math, at 1e-9."""
+    import os
+    from dair_pll_b200.geometry import Polygon, Sphere
+    from dair_pll_b200.multibody_learnable_system import MultibodyLearnableSystem
+    g = load_golden('chain3s')
+    s = MultibodyLearnableSystem({'chain3': os.path.join(assets_dir, 'chain3.urdf')}, float(g['dt']))
+    mt = s.multibody_terms
+    ct = mt.contact_terms
+    ct.geometries[1] = Sphere(torch.from_numpy(g['sphere_radius']))
+    ct.geometries[2] = Polygon(torch.from_numpy(g['polygon_vertices']), 4)
+    with torch.no_grad():
+        mt.lagrangian_terms.inertial_parameters.copy_(torch.from_numpy(g['theta']))
+        ct.friction_params.copy_(torch.from_numpy(g['friction_params']))
+        ct.geometries[0].length_params.copy_(torch.from_numpy(g['box_length_params']))
+    n = 3
+    x, xp = np.ascontiguousarray(g['x']), np.ascontiguousarray(g['x_plus'])
+    B = x.shape[0]
+    pts_t, packed = mt.chain_witness_points(torch.from_numpy(xp[:, :9]))
+    assert packed == (4 | (1 << 3) | (4 << 6)) and pts_t.shape == (B, 3, 4, 3)
+    kin = np.ascontiguousarray(mt.chain_kinematic_table(torch.device('cpu'), witness=True).numpy())
+    inertia_t = mt.lagrangian_terms.inertia_vector().reshape(10 * n)
+    mu_t = ct.pair_friction().reshape(n)
+    inertia, mu = inertia_t.detach().numpy().copy(), mu_t.detach().numpy().copy()
+    pts = np.ascontiguousarray(pts_t.detach().numpy())
+    lib = host_emulation_lib()
+    loss, grad, gp = np.zeros(B), np.zeros(14 * n), np.zeros((B, n, 4, 3))
+    rc = lib.emul_chain_loss_pts_f64(ctypes.c_int(n), dptr(x), dptr(xp), dptr(inertia), dptr(mu), dptr(kin), dptr(pts),
+                                     ctypes.c_uint(packed), ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-3),
+                                     ctypes.c_int64(B), dptr(loss), dptr(grad), dptr(gp))
+    assert rc == 0
+    assert np.abs(loss - g['loss']).max() < 1e-12
+    assert rel_err(loss, g['loss'], 1e-9).max() < 1e-9
+    # chain rule to the leaves (golden gradients are of loss.mean())
+    torch.cat((inertia_t, mu_t)).backward(torch.from_numpy(grad[:11 * n] / B))
+    pts_t.backward(torch.from_numpy(gp / B))
+    assert max_rel_to_scale(mt.lagrangian_terms.inertial_parameters.grad.numpy(), g['grad_theta']) < 1e-9
+    assert max_rel_to_scale(ct.friction_params.grad.numpy(), g['grad_friction']) < 1e-9
+    assert max_rel_to_scale(ct.geometries[0].length_params.grad.numpy(), g['grad_box_length_params']) < 1e-9
+    assert max_rel_to_scale(ct.geometries[1].length_param.grad.numpy(), g['grad_sphere_radius']) < 1e-9
+    assert max_rel_to_scale(ct.geometries[2].vertices.grad.numpy(), g['grad_polygon_vertices']) < 1e-9
+    # one learnable time step
+    pts0, packed0 = mt.chain_witness_points(torch.from_numpy(x[:, :9]))
+    p0 = np.ascontiguousarray(pts0.detach().numpy())
+    xn = np.zeros_like(x)
+    rc = lib.emul_chain_step_pts_f64(ctypes.c_int(n), dptr(x), dptr(inertia), dptr(mu), dptr(kin), dptr(p0), ctypes.c_uint(packed0),
+                                     ctypes.c_double(float(g['dt'])), ctypes.c_double(1e-4), ctypes.c_int64(B), dptr(xn))
+    assert rc == 0
+    assert np.abs(xn - g['x_next']).max() < 1e-9

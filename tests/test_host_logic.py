@@ -271,9 +271,9 @@ def test_peer_allreduce_protocol_model():
 
 
 def test_urdf_ingestion_rejects_what_the_kernels_do_not_model(tmp_path):
-    """Models the kernels would silently mis-simulate are refused at construction (a learned geometry in a rotated
-    collision frame); a box's rotated collision frame sends a two-link system to the generic tree kernels; a single
-    floating body's collision frame (offset and rotation) is carried to its geometry and
+    """Models the kernels would silently mis-simulate are refused at construction (more collision geometries than links);
+    a rotated collision frame sends a two-link system to the generic tree kernels (boxes as lengths, learned meshes as
+    witness points); a single floating body's collision frame (offset and rotation) is carried to its geometry and
     equals the oracle tree's; a joint axis is normalised as Drake does on parsing."""
     from dair_pll_b200.geometry import place_in_link_frame
     from dair_pll_b200.system_spec import SystemSpec
@@ -300,14 +300,23 @@ def test_urdf_ingestion_rejects_what_the_kernels_do_not_model(tmp_path):
     rotated = SystemSpec.from_urdf(str(p))
     assert rotated.kind == 'chain' and rotated.geometries[1].rpy == (0.1, 0.0, 0.0)
     assert SystemSpec.from_urdf(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow.urdf')).kind == 'elbow'
-    # ... which take boxes: a learned (mesh) geometry in a rotated collision frame is refused
+    # ... and so does a learned (mesh) geometry in a rotated collision frame: its support points become witness points
     mesh = open(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow_mesh.urdf')).read()
     assert 'rpy="0 0 0"/>\n      <geometry><mesh' in mesh
     pm = tmp_path / 'rotated_mesh.urdf'
     pm.write_text(mesh.replace('rpy="0 0 0"/>\n      <geometry><mesh', 'rpy="0.1 0 0"/>\n      <geometry><mesh', 1)
                   .replace('elbow_half.obj', os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow_half.obj')))
+    rm = SystemSpec.from_urdf(str(pm))
+    assert rm.kind == 'chain' and [g.kind for g in rm.geometries] == ['mesh', 'mesh', 'plane']
+    # more collision geometries than links is what the tree kernels' slots cannot hold
+    two = elbow.replace('</collision>\n  </link>\n  <link name="elbow_2">',
+                        '</collision>\n' + elbow[elbow.index('    <collision>'):elbow.index('</collision>') + 12] * 2
+                        + '\n  </link>\n  <link name="elbow_2">', 1)
+    pt = tmp_path / 'crowded.urdf'
+    pt.write_text(two)
+    assert len(SystemSpec.from_urdf(str(p)).geometries) == 3
     with pytest.raises(NotImplementedError):
-        SystemSpec.from_urdf(str(pm))
+        SystemSpec.from_urdf(str(pt))
     elbow = open(os.path.join(ROOT, 'dair_pll_b200', 'assets', 'elbow.urdf')).read()
     assert 'xyz="0 1 0"' in elbow
     p2 = tmp_path / 'axis.urdf'
