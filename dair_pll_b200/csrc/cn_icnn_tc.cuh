@@ -36,10 +36,10 @@ constexpr int TC_UNITS = 3 * TC_CHUNKS;              // (chunk, k) units per 128
 constexpr int TC_SLICE_BYTES = TC_NC * TC_W;         // one digit plane of one unit: N x K int8 = 8 KB
 constexpr int TC_UNIT_BYTES = TC_NS * TC_SLICE_BYTES;          // 48 KB
 constexpr int TC_IMG_BYTES = TC_UNITS * TC_UNIT_BYTES;         // 1,179,648 B: all planes, in shared-memory image order
-// constants (doubles): per hidden unit i eight values [coef_0, base_0, coef_1, base_1, coef_2, base_2, ztol, 0] with the
+// constants (doubles): per hidden unit i eight values [coef_0, base_0, coef_1, base_1, coef_2, base_2, ztol, |wout|_i] with the
 // output weight |wout|_i folded in (Y'_k = |wout|_i Y_k = base_k + coef_k * integer), then Wd0[3][W], Wd1[3][W]
 constexpr int TC_C_COL = 0, TC_C_WD0 = 8 * TC_W, TC_C_WD1 = 11 * TC_W, TC_NCONST = 14 * TC_W;
-constexpr int TC_NCONST_SMEM = 11 * TC_W;            // what the kernel keeps in shared memory (Wd1 is only read by exact_z1)
+constexpr int TC_NCONST_SMEM = 11 * TC_W;            // what the kernel keeps in shared memory (Wd1 is only read by the rare-path correction, redo_entries)
 constexpr double TC_ZTOL_REL = 1e-9;                 // |z1| below this fraction of its scale is re-evaluated in fp64
 
 // K-major, no-swizzle UMMA canonical layout of an (rows x 256 B) int8 operand: 8-row x 16-byte core matrices,
